@@ -1,0 +1,202 @@
+/* sos_b200.h -- C ABI of libsos_b200.so (sm_100a only).
+ *
+ * Drop-in boundary of the B200-native hot path for
+ * henryxrl/Listening-to-Sound-of-Silence-for-Speech-Denoising.  The reference has no FFI of its own (it is
+ * pure Python over PyTorch 1.3 + librosa 0.7.1); every entry point below replaces a library call the
+ * reference makes at the cited file:line (paths relative to the reference root; M1 =
+ * model_1_silent_interval_detection/audioonly_model, M2 = model_2_audio_denoising/audio_denoising_model).
+ *
+ * Conventions
+ *   - every function returns 0 (SOS_OK) or a negative code; sos_last_error() gives the message
+ *   - the caller owns all memory: device pointers, contiguous, fp32 unless stated; nothing is allocated
+ *     per call (only the constant DFT tables at sos_init) and nothing synchronises the device
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*-compatible handle)
+ *   - activations inside the networks are NHWC fp32 ("pixel-major"): (N, H=freq, W=time, C)
+ *   - a "view" is 8 x int32: H, W, Hp, Wp, ph, pw, ld, coff = logical window H x W at offset (ph, pw) of a
+ *     (N, Hp, Wp, ld) buffer, channels [coff, coff+C)
+ */
+#ifndef SOS_B200_H
+#define SOS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+#define SOS_OK 0
+#define SOS_ERR_ARG -1
+#define SOS_ERR_CUDA -2
+#define SOS_ERR_UNSUPPORTED -3
+
+const char* sos_last_error(void);
+int sos_version(void);
+/* Builds the constant windowed-DFT tables on the current device (idempotent). */
+int sos_init(void);
+
+/* ------------------------------------------------------------------------------------------------ transforms
+ * sos_stft_forward   M2/transform.py:188-193 fast_stft -> librosa.stft(y, 510, 158, 400), called from
+ *                    M2/dataset.py:234-237, M1/dataset.py:288, M2/predict.py:320-326.
+ *   wave (B, L) -> spec_out (B, 2, 256, T), T = 1 + L/158  (the Dataset item layout, M2/dataset.py:255-259).
+ *   gate_mode 0: plain.  1: wave * mask (noise gate, M2/predict.py:317, M2/dataset.py:229).
+ *   2: wave * (1 - mask) (M2/dataset.py:193).  The mask is the reference's bit string -> sample mask
+ *   (M2/tools.py:340-362): bits (B, n_bits) uint8 with 0 = silent, frame_lo[i] = int(i * ratio) (n_bits + 1
+ *   entries, computed by the caller with the reference's own float expression), ratio = sr / fps.
+ */
+int sos_stft_forward(const float* wave, int64_t batch, int64_t length, float* spec_out, const uint8_t* bits,
+                     int64_t n_bits, const int32_t* frame_lo, double ratio, int gate_mode, cudaStream_t stream);
+/* sos_istft_forward  M2/transform.py:196-202 fast_istft -> librosa.istft(S, 158, 400); M2/predict.py:424-447.
+ *   spec (B, 2, 256, T) -> wave_out (B, 158 (T-1)).  frames_ws: workspace B*T*400 floats.
+ *   crm_or_null != NULL fuses fast_icRM_sigmoid (M2/transform.py:141-153): spec is then the mixture Y. */
+int sos_istft_forward(const float* spec, const float* crm_or_null, int64_t batch, int64_t n_frames, float* frames_ws,
+                      float* wave_out, cudaStream_t stream);
+/* sos_gate_wave      M2/tools.py:340-362 + the gating multiplies; mode as gate_mode above (1 or 2). */
+int sos_gate_wave(const float* wave, int64_t batch, int64_t length, const uint8_t* bits, int64_t n_bits,
+                  const int32_t* frame_lo, double ratio, int mode, float* out_or_null, float* mask_or_null,
+                  cudaStream_t stream);
+/* sos_icrm_*         M2/transform.py:156-169 batch_fast_icRM_sigmoid (and its gradient w.r.t. crm).
+ *   Y, crm, rec: (B, 2, plane) with plane = 256*T. */
+int sos_icrm_forward(const float* Y, const float* crm, float* rec, int64_t batch, int64_t plane, float a, float b,
+                     cudaStream_t stream);
+int sos_icrm_backward(const float* Y, const float* crm, const float* grad_rec, float* grad_crm, int64_t batch,
+                      int64_t plane, float a, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ losses / optimiser
+ * nn.MSELoss / nn.BCEWithLogitsLoss (M2/agent.py:172-190, M1/agent.py:185-202): *loss_sum += sum of
+ * element losses (caller divides by n); grad = dloss/dpred * grad_scale when grad != NULL. */
+int sos_mse_fwd_bwd(const float* pred, const float* target, int64_t n, float* loss_sum, float* grad_or_null,
+                    float grad_scale, cudaStream_t stream);
+int sos_bce_logits_fwd_bwd(const float* logits, const float* labels, int64_t n, float* loss_sum, float* grad_or_null,
+                           float grad_scale, cudaStream_t stream);
+/* optim.Adam(lr) defaults (M2/agent.py:167-170, M1/agent.py:175-183) over one flat buffer; step >= 1. */
+int sos_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int64_t step, float grad_scale, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ BatchNorm + activation
+ * nn.BatchNorm2d(eps 1e-5, momentum 0.1) + ReLU / PReLU of ConvBlock (M2/networks.py:28-51),
+ * Conv2dBlock (M1/networks.py:28-51), Down/UpConvBlock (M2/networks.py:97-149) over NHWC rows.
+ * act: 0 none, 1 ReLU, 2 PReLU (single slope).  partial: sos_bn_partial_blocks(rows, C) * 3 * C floats. */
+int sos_bn_partial_blocks(int64_t rows, int64_t channels);
+int sos_bn_stats(const float* y, int64_t rows, int64_t channels, float* partial, cudaStream_t stream);
+int sos_bn_finalize(const float* partial, int64_t rows, int64_t channels, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
+                    float* shift, cudaStream_t stream);
+int sos_bn_eval_coeffs(int64_t channels, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, float* scale, float* shift, cudaStream_t stream);
+int sos_bn_act(const float* y, float* z, const int32_t* z_view, int64_t rows, int64_t channels, const float* scale,
+               const float* shift, int act, const float* slope, cudaStream_t stream);
+int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y, float* dy, int64_t rows, int64_t channels,
+                        const float* scale, const float* shift, const float* mean, const float* invstd, int act,
+                        const float* slope, float* partial, float* dgamma, float* dbeta, float* dslope, float* m1, float* m2,
+                        cudaStream_t stream);
+/* eval-mode backward of z = act(y*scale+shift): dy = dz*act'(pre)*scale (no batch statistics). */
+int sos_affine_act_backward(const float* dz, const int32_t* dz_view, const float* y, float* dy, int64_t rows,
+                            int64_t channels, const float* scale, const float* shift, int act, const float* slope,
+                            cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ layout
+ * NCHW <-> NHWC, torch.cat slices / F.interpolate(nearest) size fix-ups (M2/networks.py:198-204),
+ * nn.ReflectionPad2d borders (M2/networks.py:104,129) and the encoder -> LSTM reshape + nearest resample
+ * (M1/networks.py:131-135, M2/networks.py:83-86). */
+int sos_nchw_to_nhwc(const float* x, int64_t batch, int64_t channels, float* out, const int32_t* out_view,
+                     int64_t slice_channels, cudaStream_t stream);
+int sos_nhwc_to_nchw(const float* in, const int32_t* in_view, int64_t batch, int64_t channels, float* out,
+                     cudaStream_t stream);
+int sos_copy_view(const float* src, const int32_t* src_view, float* dst, const int32_t* dst_view, int64_t batch,
+                  int64_t channels, int accumulate, cudaStream_t stream);
+int sos_copy_view_backward(const float* grad_dst, const int32_t* dst_view, float* grad_src, const int32_t* src_view,
+                           int64_t batch, int64_t channels, cudaStream_t stream);
+int sos_reflect_fill(float* buf, int64_t batch, int64_t H, int64_t W, int64_t pad, int64_t channels, cudaStream_t stream);
+int sos_reflect_fold(float* grad_buf, int64_t batch, int64_t H, int64_t W, int64_t pad, int64_t channels,
+                     cudaStream_t stream);
+int sos_feat_to_seq(const float* in, int64_t B, int64_t F, int64_t T, int64_t C, float* out, int64_t V, int64_t ld,
+                    int64_t coff, cudaStream_t stream);
+int sos_feat_to_seq_backward(const float* grad_out, int64_t B, int64_t F, int64_t T, int64_t C, float* grad_in_zeroed,
+                             int64_t V, int64_t ld, int64_t coff, cudaStream_t stream);
+/* out (cols, rows) = in (rows, cols)^T */
+int sos_transpose(const float* in, int64_t rows, int64_t cols, float* out, cudaStream_t stream);
+/* y[r][c] = act(y[r][c] + bias[c]) in place; act 0 none, 1 ReLU, 3 sigmoid.  ld = row pitch (floats). */
+int sos_bias_act(float* y, int64_t rows, int64_t cols, int64_t ld, const float* bias, int act, cudaStream_t stream);
+/* dpre = dy * act'(y) (y = saved OUTPUT of the activation); dbias[c] += sum_r dpre (dbias zeroed by caller). */
+int sos_bias_act_backward(const float* dy, const float* y, float* dpre, int64_t rows, int64_t cols, int64_t ld, int act,
+                          float* dbias_or_null, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ weights
+ * PyTorch conv weight (Cout, Cin, kh, kw) -> GEMM operand.
+ *   mode 0: forward   [Cout][ntaps * CinP], k = tap * CinP + ci
+ *   mode 1: data grad [Cin][ntaps * CoutP], k = tap' * CoutP + co with tap' the flipped tap */
+int sos_pack_conv_weight(const float* w, int64_t Cout, int64_t Cin, int64_t kh, int64_t kw, int64_t CinP, int64_t CoutP,
+                         int mode, float* out, cudaStream_t stream);
+/* wgrad buffer [tap][CoutP][CinP] -> PyTorch (Cout, Cin, kh, kw) (transposed=0) or ConvTranspose (Cin, Cout, kh, kw)
+ * (transposed=1, in which case src is [tap][CinP'][CoutP'] with the roles swapped by the caller). */
+int sos_unpack_wgrad(const float* src, int64_t Cout, int64_t Cin, int64_t ntaps, int64_t CinP, float* dst, int accumulate,
+                     cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ tensor-core tap GEMM
+ * One kernel family (tcgen05 kind::tf32, fp32 accumulate in TMEM, TMA-staged operands) serves
+ *   nn.Conv2d of Conv2dBlock / ConvBlock / DownConvBlock (M1/networks.py:36, M2/networks.py:36,105-106),
+ *   nn.ConvTranspose2d of UpConvBlock as 4 sub-pixel convs (M2/networks.py:130-131),
+ *   their data gradients (flipped taps), and the nn.Linear / LSTM input projections as 1-tap GEMMs
+ *   (M1/networks.py:95-98, M2/networks.py:64-70).
+ *
+ *   y[n, oh*osh+oph, ow*osw+opw, y_coff + co] = epi( sum_t sum_ci x[n, oh*stride + tap_dh[t], ow*stride + tap_dw[t], ci]
+ *                                                      * wk[co][t*Cin + ci] )
+ *   x  : (N, H, W, Cin) NHWC fp32, Cin % 8 == 0; out-of-range pixels read as zero
+ *   wk : (Cout, ntaps*Cin) row-major (sos_pack_conv_weight layout)
+ *   y  : (N, YH, YW, Cy) NHWC fp32; epi: v*epi_scale[co]+epi_shift[co] (optional) then act (0/1 relu/2 prelu)
+ */
+typedef struct sos_conv_args {
+  const float* x;
+  const float* wk;
+  float* y;
+  const int32_t* tap_dh;   /* host arrays, ntaps entries */
+  const int32_t* tap_dw;
+  int64_t N, H, W, Cin;
+  int64_t Cout, OH, OW;
+  int64_t ntaps, stride;
+  int64_t YH, YW, Cy, y_coff;
+  int64_t osh, osw, oph, opw;
+  const float* epi_scale;  /* device, Cout entries, or NULL */
+  const float* epi_shift;
+  int64_t act;
+  const float* slope;      /* device scalar for act == 2 */
+  int64_t force_plan;      /* -1 = automatic */
+  int32_t* plan_out;       /* host, 8 ints, or NULL */
+} sos_conv_args;
+int sos_conv2d_tc(const sos_conv_args* args, cudaStream_t stream);
+
+/* Weight gradient of the same operator (split over pixels, accumulated with fp32 atomics):
+ *   dw[t][co][ci] += sum_{n,oh,ow} dy[n, oh, ow, dy_coff + co] * x[n, oh*stride + tap_dh[t], ow*stride + tap_dw[t], ci]
+ *   dy : (N, OH, OW, Cdy) NHWC;  dw : [ntaps][Cout][Cin] fp32, zeroed by the caller.
+ *   Tensor-core path needs Cin % 16 == 0, Cout % 16 == 0, Cout <= 128*8; otherwise a CUDA-core kernel runs. */
+typedef struct sos_wgrad_args {
+  const float* x;
+  const float* dy;
+  float* dw;
+  const int32_t* tap_dh;
+  const int32_t* tap_dw;
+  int64_t N, H, W, Cin;
+  int64_t Cout, OH, OW, Cdy, dy_coff;
+  int64_t ntaps, stride;
+  int64_t force_plan;
+  int32_t* plan_out;
+} sos_wgrad_args;
+int sos_conv2d_wgrad(const sos_wgrad_args* args, cudaStream_t stream);
+
+/* ------------------------------------------------------------------------------------------------ LSTM recurrence
+ * nn.LSTM(bidirectional, 1 layer) of M1/networks.py:95,147-148 and M2/networks.py:64,88-89 after the input
+ * projection: gx (T, B, 2, 4H) = x W_ih^T + b_ih + b_hh per direction (gate order i, f, g, o).
+ *   w_hh (2, 4H, H);  out (T, B, 2H) = [h_fwd | h_rev];  gates_ws (T, B, 2, 4H) activated gates, cell_ws (T, B, 2, H).
+ * backward: dout (T, B, 2H) -> dgx (T, B, 2, 4H) (pre-activation gate grads), dw_hh (2, 4H, H) accumulated. */
+int sos_lstm_forward(const float* gx, const float* w_hh, int64_t T, int64_t B, int64_t H, float* out, float* gates_ws,
+                     float* cell_ws, cudaStream_t stream);
+int sos_lstm_backward(const float* dout, const float* w_hh, const float* out, const float* gates_ws, const float* cell_ws,
+                      int64_t T, int64_t B, int64_t H, float* dgx, float* dh_ws, float* dc_ws, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOS_B200_H */

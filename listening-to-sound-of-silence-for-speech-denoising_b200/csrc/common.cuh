@@ -1,0 +1,64 @@
+// Shared helpers for the sos-b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define SOS_OK 0
+#define SOS_ERR_ARG -1
+#define SOS_ERR_CUDA -2
+#define SOS_ERR_UNSUPPORTED -3
+
+void sos_set_error(const char* fmt, ...);
+
+#define SOS_CHECK_ARG(cond, ...)                  \
+  do {                                            \
+    if (!(cond)) {                                \
+      sos_set_error(__VA_ARGS__);                 \
+      return SOS_ERR_ARG;                         \
+    }                                             \
+  } while (0)
+
+#define SOS_CHECK_LAUNCH(name)                                                  \
+  do {                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                       \
+    if (e__ != cudaSuccess) {                                                   \
+      sos_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));    \
+      return SOS_ERR_CUDA;                                                      \
+    }                                                                           \
+  } while (0)
+
+static inline int sos_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum of `v`; result valid in thread 0.  blockDim.x multiple of 32, <= 1024.
+__device__ __forceinline__ float block_sum(float v, float* smem32) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) smem32[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    v = (lane < (int)((blockDim.x + 31) >> 5)) ? smem32[lane] : 0.f;
+    v = warp_sum(v);
+  }
+  __syncthreads();
+  return v;
+}

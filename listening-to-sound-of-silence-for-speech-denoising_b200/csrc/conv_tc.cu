@@ -1,0 +1,386 @@
+// Tap-list implicit GEMM on the 5th-gen tensor cores (tcgen05, kind::tf32, fp32 accumulate in TMEM).
+//
+// Every convolution on the hot path (zero-"same" dilated convs of the SID / ContextAggNet encoders,
+// reflect-padded / strided / transposed convs of InpaintNet, data gradients of all of them) and the plain
+// GEMMs (LSTM input projection, MLP head) are instances of
+//
+//     out[n, oh, ow, :] = epilogue( sum_t  in[n, oh*s + dh_t, ow*s + dw_t, :] . W_t^T )
+//
+// over NHWC fp32 activations.  Out-of-range input pixels read as zero (TMA out-of-bounds fill), so zero
+// padding costs nothing; reflect padding is materialised by the producer layer.
+//
+// CTA = 192 threads, persistent over output tiles:
+//   warp 0    TMA producer: per k-step one activation box per sub-tile (+ halo rows along the slow tile axis,
+//             shared by every tap that differs only by a slow-axis shift) and one weight box per tap
+//   warp 1    MMA issuer (single elected lane), accumulators double-buffered in TMEM
+//   warps 2-5 epilogue: tcgen05.ld -> affine/activation -> smem staging -> TMA store (clips the ragged edge)
+// An output tile is 128 pixels = SB (slow) x FB (fast) pixels of one image (FB = 8 or 128).  The slow axis may be
+// a dilation lattice (pixels q*g + r for fixed phase r), which turns a dilated tap shift into a shift by whole
+// 8-row swizzle atoms of the same staged box.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "sos_b200.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace ptx;
+using namespace tc;
+
+constexpr int kThreadsTc = 192;
+constexpr int kStagingBytes = 2 * 128 * 32 * 4;      // two 128 x 32 fp32 buffers
+struct alignas(64) TcParams {
+  CUtensorMap mapA, mapB, mapD;
+  int total_ctiles, n_nblk, tiles_fast_g, tiles_slow, n_phase;
+  int S, N, cbe, n_chunks, n_groups;
+  int FB, SB, stride;
+  int cin;                       // K elements per tap in the weight matrix
+  int ec;                        // epilogue / store chunk width (16 or 32 channels)
+  int n_stages, stage_bytes, a_box_bytes, a_box_stride, b_tile_stride;
+  int layout_type, sbo;
+  uint32_t idesc;
+  const float* scale;            // optional per-output-channel affine (eval-mode BN / bias) ...
+  const float* shift;
+  int act;                       // 0 none, 1 relu, 2 prelu
+  const float* slope;
+  TapGroup groups[kMaxGroups];
+};
+
+struct TileCoord { int nb, tfg, ts, ph, n; };
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
+  TileCoord c;
+  c.nb = t % p.n_nblk; t /= p.n_nblk;
+  c.tfg = t % p.tiles_fast_g; t /= p.tiles_fast_g;
+  c.ts = t % p.tiles_slow; t /= p.tiles_slow;
+  c.ph = t % p.n_phase;
+  c.n = t / p.n_phase;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // smem carve-up: [stages][staging][barriers]
+  const uint32_t stages_base = smem_base;
+  const uint32_t staging_base = stages_base + (uint32_t)p.n_stages * p.stage_bytes;
+  const uint32_t bar_base = staging_base + kStagingBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (16 + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (32 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (34 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * 36;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.mapA);
+    prefetch_tmap(&p.mapB);
+    prefetch_tmap(&p.mapD);
+    for (int s = 0; s < p.n_stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int loads_per_tile = p.n_groups * p.n_chunks;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ct = blockIdx.x; ct < p.total_ctiles; ct += gridDim.x) {
+        const TileCoord tc = decode_tile(p, ct);
+        for (int g = 0; g < p.n_groups; ++g) {
+          const TapGroup& grp = p.groups[g];
+          const uint32_t tx_bytes = (uint32_t)p.S * p.a_box_bytes + (uint32_t)grp.n_sub * (p.N * p.cbe * 4);
+          for (int c = 0; c < p.n_chunks; ++c) {
+            mbar_wait(empty_bar(stage), phase ^ 1, 100);
+            mbar_expect_tx(full_bar(stage), tx_bytes);
+            const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
+            for (int s = 0; s < p.S; ++s) {
+              const int fast0 = ((tc.tfg * p.S + s) * p.FB) * p.stride + grp.d_fast;
+              const int slow0 = (tc.ts * p.SB) * p.stride + grp.d_slow;
+              tma_load_5d(sbase + (uint32_t)s * p.a_box_stride, &p.mapA, full_bar(stage), c * p.cbe, fast0, slow0, tc.ph, tc.n);
+            }
+            const uint32_t bbase = sbase + (uint32_t)p.S * p.a_box_stride;
+            for (int j = 0; j < grp.n_sub; ++j)
+              tma_load_2d(bbase + (uint32_t)j * p.b_tile_stride, &p.mapB, full_bar(stage), grp.tap[j] * p.cin + c * p.cbe,
+                          tc.nb * p.N);
+            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int kk_per_chunk = p.cbe / 8;
+    for (int ct = blockIdx.x; ct < p.total_ctiles; ct += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1, 200);
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + (uint32_t)acc * 256;
+      int l = 0;
+      for (int g = 0; g < p.n_groups; ++g) {
+        const TapGroup& grp = p.groups[g];
+        for (int c = 0; c < p.n_chunks; ++c, ++l) {
+          mbar_wait(full_bar(stage), phase, 201);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
+            const uint32_t bbase = sbase + (uint32_t)p.S * p.a_box_stride;
+            for (int s = 0; s < p.S; ++s) {
+              for (int j = 0; j < grp.n_sub; ++j) {
+                const uint32_t a_addr = sbase + (uint32_t)s * p.a_box_stride + (uint32_t)grp.a_off[j] * (p.FB * p.cbe * 4);
+                const uint32_t b_addr = bbase + (uint32_t)j * p.b_tile_stride;
+                for (int kk = 0; kk < kk_per_chunk; ++kk) {
+                  const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, p.sbo, p.layout_type);
+                  const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, p.sbo, p.layout_type);
+                  umma_tf32(d_base + (uint32_t)s * p.N, ad, bd, p.idesc, (l | j | kk) != 0);
+                }
+              }
+            }
+            umma_commit(empty_bar(stage));                 // frees the smem stage when these MMAs retire
+            if (l == loads_per_tile - 1) umma_commit(tfull_bar(acc));
+          }
+          __syncwarp();
+          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;                // accumulator row = pixel within the tile
+    const int ethread = threadIdx.x - 64;         // 0..127
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int buf = 0;
+    const float slope = (p.act == 2 && p.slope) ? *p.slope : 0.f;
+    const int n_ec = p.N / p.ec;
+    for (int ct = blockIdx.x; ct < p.total_ctiles; ct += gridDim.x) {
+      const TileCoord tc = decode_tile(p, ct);
+      mbar_wait(tfull_bar(acc), acc_phase, 300);
+      tc_fence_after();
+      for (int s = 0; s < p.S; ++s) {
+        for (int cc = 0; cc < n_ec; ++cc) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + s * p.N + cc * p.ec);
+          uint32_t r[32];
+          tmem_ld16(taddr, r);
+          if (p.ec == 32) tmem_ld16(taddr + 16, r + 16);
+          tmem_ld_wait();
+          const int ch0 = tc.nb * p.N + cc * p.ec;
+          if (p.scale || p.act) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < p.ec) {
+                float v = __uint_as_float(r[i]);
+                if (p.scale) v = fmaf(v, __ldg(p.scale + ch0 + i), __ldg(p.shift + ch0 + i));
+                if (p.act == 1) v = fmaxf(v, 0.f);
+                else if (p.act == 2) v = v > 0.f ? v : v * slope;
+                r[i] = __float_as_uint(v);
+              }
+            }
+          }
+          // make sure the TMA store that last read this staging buffer has drained
+          if (ethread == 0) bulk_wait_read<1>();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const uint32_t sbuf = staging_base + (uint32_t)buf * (128 * 32 * 4);
+          const uint32_t srow = sbuf + (uint32_t)row * (p.ec * 4);
+          const int nv = p.ec / 4;                 // float4 per row: 8 or 4
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < nv) {
+              const int j = (i + row) % nv;        // rotate to spread banks
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + j * 16), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                           "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                           : "memory");
+            }
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (ethread == 0) {
+            tma_store_5d(&p.mapD, sbuf, ch0, (tc.tfg * p.S + s) * p.FB, tc.ts * p.SB, tc.ph, tc.n);
+            bulk_commit();
+          }
+          buf ^= 1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (ethread == 0) bulk_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
+  SOS_CHECK_ARG(ap != nullptr, "sos_conv2d_tc: null args");
+  const sos_conv_args& a = *ap;
+  SOS_CHECK_ARG(a.x && a.wk && a.y && a.tap_dh && a.tap_dw, "sos_conv2d_tc: null pointer");
+  SOS_CHECK_ARG(a.N > 0 && a.H > 0 && a.W > 0 && a.Cin >= 8 && a.Cin % 8 == 0, "sos_conv2d_tc: Cin must be a positive multiple of 8 (got %lld)",
+                (long long)a.Cin);
+  SOS_CHECK_ARG(a.Cout > 0 && a.OH > 0 && a.OW > 0 && a.ntaps > 0 && a.ntaps <= 49, "sos_conv2d_tc: bad output shape / taps");
+  SOS_CHECK_ARG(a.stride == 1 || a.stride == 2, "sos_conv2d_tc: stride must be 1 or 2");
+  SOS_CHECK_ARG(a.osh >= 1 && a.osw >= 1 && a.oph >= 0 && a.opw >= 0 && a.oph < a.osh && a.opw < a.osw, "sos_conv2d_tc: bad output lattice");
+  SOS_CHECK_ARG(a.Cy % 4 == 0 && a.y_coff % 4 == 0 && a.y_coff < a.Cy, "sos_conv2d_tc: output channels / offset must be multiples of 4");
+  SOS_CHECK_ARG(((uintptr_t)a.x % 16) == 0 && ((uintptr_t)a.y % 16) == 0 && ((uintptr_t)a.wk % 16) == 0, "sos_conv2d_tc: pointers must be 16-byte aligned");
+  SOS_CHECK_ARG((a.OH - 1) * a.osh + a.oph < a.YH && (a.OW - 1) * a.osw + a.opw < a.YW, "sos_conv2d_tc: output lattice exceeds the output buffer");
+
+  // ---- choose orientation / sharing
+  Geometry geo{(int)a.ntaps, a.tap_dh, a.tap_dw, (int)a.H, (int)a.W, (int)a.OH, (int)a.OW, (int)a.stride, (int)a.Cin, (int)a.Cout,
+               a.osh == 1 && a.osw == 1 && a.oph == 0 && a.opw == 0, kMaxSub};
+  Plan best;
+  for (int fw = 1; fw >= 0; --fw)
+    for (int sh = 1; sh >= 0; --sh) {
+      Plan pl;
+      if (build_plan(geo, fw != 0, sh != 0, pl) && pl.cost < best.cost) best = pl;
+    }
+  SOS_CHECK_ARG(best.cost < 1e299, "sos_conv2d_tc: no feasible plan");
+  if (a.force_plan >= 0) {            // test hook: bit0 = fast_is_w, bit1 = share
+    Plan pl;
+    SOS_CHECK_ARG(build_plan(geo, (a.force_plan & 1) != 0, (a.force_plan & 2) != 0, pl), "sos_conv2d_tc: forced plan %d not applicable", (int)a.force_plan);
+    best = pl;
+  }
+  const Plan& pl = best;
+
+  static TcParams p;                  // kernel parameter block (copied at launch)
+  memset(&p, 0, sizeof(p));
+  const int Cin = (int)a.Cin, Cout = (int)a.Cout;
+  const int Ntot = round_up(Cout, 16);
+  int N = Ntot, n_nblk = 1;
+  if (Ntot > 256) {
+    int best_waste = 1 << 30;
+    for (int nb = ceil_div(Ntot, 256); nb <= ceil_div(Ntot, 256) + 4; ++nb) {
+      const int n = round_up(ceil_div(Ntot, nb), 16);
+      if (n <= 256 && n * nb - Ntot < best_waste) { best_waste = n * nb - Ntot; N = n; n_nblk = nb; }
+    }
+  }
+  p.N = N;
+  p.n_nblk = n_nblk;
+  p.cbe = Cin % 32 == 0 ? 32 : (Cin % 16 == 0 ? 16 : 8);
+  p.n_chunks = Cin / p.cbe;
+  p.cin = Cin;
+  p.ec = (N % 32 == 0) ? 32 : 16;
+  p.FB = pl.FB;
+  p.SB = pl.SB;
+  p.S = (n_nblk > 1 || pl.S * N > 256) ? 1 : pl.S;
+  p.stride = (int)a.stride;
+  p.n_groups = (int)pl.groups.size();
+  for (int i = 0; i < p.n_groups; ++i) p.groups[i] = pl.groups[i];
+  const int cb = p.cbe * 4;
+  p.layout_type = cb == 128 ? 2 : (cb == 64 ? 4 : 6);
+  p.sbo = 8 * cb;
+  p.idesc = make_idesc_tf32(128, N, 0, 0);
+  const int box_slow = pl.SB + pl.halo;
+  p.a_box_bytes = box_slow * pl.FB * cb;
+  p.a_box_stride = round_up(p.a_box_bytes, 1024);
+  p.b_tile_stride = round_up(N * cb, 1024);
+  int max_sub = 1;
+  for (auto& g : pl.groups) max_sub = std::max(max_sub, (int)g.n_sub);
+  p.stage_bytes = p.S * p.a_box_stride + max_sub * p.b_tile_stride;
+  const int avail = kSmemLimit - 1024 - kStagingBytes - 512;
+  p.n_stages = std::min(8, avail / p.stage_bytes);
+  SOS_CHECK_ARG(p.n_stages >= 2, "sos_conv2d_tc: pipeline stage of %d bytes does not fit twice in shared memory", p.stage_bytes);
+  p.scale = a.epi_scale;
+  p.shift = a.epi_shift;
+  p.act = (int)a.act;
+  p.slope = a.slope;
+  SOS_CHECK_ARG((a.epi_scale == nullptr) == (a.epi_shift == nullptr), "sos_conv2d_tc: epi_scale and epi_shift go together");
+
+  // ---- tensor maps.  Dim order: (channel, fast, slow/g, phase(g), image)
+  const bool fw = pl.fast_is_w;
+  const int g = pl.g;
+  const uint64_t pixA = (uint64_t)Cin * 4;
+  const uint64_t in_fast = fw ? a.W : a.H, in_slow = fw ? a.H : a.W;
+  const uint64_t sA_fast = fw ? pixA : pixA * a.W, sA_slow = fw ? pixA * a.W : pixA;
+  {
+    uint64_t dims[5] = {(uint64_t)Cin, in_fast, in_slow / g, (uint64_t)g, (uint64_t)a.N};
+    uint64_t str[5] = {4, sA_fast, sA_slow * g, sA_slow, pixA * a.H * a.W};
+    uint32_t box[5] = {(uint32_t)p.cbe, (uint32_t)(pl.FB * a.stride), (uint32_t)(box_slow * a.stride), 1, 1};
+    uint32_t es[5] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1, 1};
+    SOS_CHECK_ARG(box[1] <= 256 && box[2] <= 256, "sos_conv2d_tc: activation box too large");
+    const CUtensorMapSwizzle sw = cb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (cb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    if (int e = encode_map(&p.mapA, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, a.x, dims, str, box, es, sw, "activations")) return e;
+    uint64_t bd[2] = {(uint64_t)a.ntaps * Cin, (uint64_t)Cout};
+    uint64_t bs[2] = {4, (uint64_t)a.ntaps * Cin * 4};
+    uint32_t bb[2] = {(uint32_t)p.cbe, (uint32_t)N};
+    uint32_t be[2] = {1, 1};
+    if (int e = encode_map(&p.mapB, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, a.wk, bd, bs, bb, be, sw, "weights")) return e;
+  }
+  const int out_fast = fw ? (int)a.OW : (int)a.OH, out_slow = fw ? (int)a.OH : (int)a.OW;
+  {
+    const uint64_t pixY = (uint64_t)a.Cy * 4;
+    const uint64_t rowY = pixY * a.YW;
+    // output pixel (oh, ow) lives at (oh*osh + oph, ow*osw + opw)
+    const uint64_t sY_h = rowY * a.osh, sY_w = pixY * a.osw;
+    const float* base = a.y + a.y_coff + ((uint64_t)a.oph * a.YW + a.opw) * a.Cy;
+    const int cstore = std::min(round_up(Cout, 4), (int)(a.Cy - a.y_coff));
+    const uint64_t sY_fast = fw ? sY_w : sY_h, sY_slow = fw ? sY_h : sY_w;
+    uint64_t dims[5] = {(uint64_t)cstore, (uint64_t)out_fast, (uint64_t)(out_slow / g), (uint64_t)g, (uint64_t)a.N};
+    uint64_t str[5] = {4, sY_fast, sY_slow * g, sY_slow, pixY * a.YH * a.YW};
+    uint32_t box[5] = {(uint32_t)p.ec, (uint32_t)pl.FB, (uint32_t)pl.SB, 1, 1};
+    uint32_t es[5] = {1, 1, 1, 1, 1};
+    if (int e = encode_map(&p.mapD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_NONE, "output")) return e;
+  }
+  const int tiles_fast = ceil_div(out_fast, pl.FB);
+  p.tiles_fast_g = ceil_div(tiles_fast, p.S);
+  p.tiles_slow = ceil_div(out_slow / g, pl.SB);
+  p.n_phase = g;
+  const long long total = (long long)a.N * g * p.tiles_slow * p.tiles_fast_g * n_nblk;
+  SOS_CHECK_ARG(total < (1ll << 31), "sos_conv2d_tc: too many tiles");
+  p.total_ctiles = (int)total;
+
+  const int smem = 1024 + p.n_stages * p.stage_bytes + kStagingBytes + 512;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(tapgemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess) {
+      sos_set_error("sos_conv2d_tc: cannot raise dynamic shared memory to %d bytes: %s", kSmemLimit, cudaGetErrorString(cudaGetLastError()));
+      return SOS_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int grid = (int)std::min<long long>(total, sos_num_sms());
+  tapgemm_tf32_kernel<<<grid, kThreadsTc, smem, stream>>>(p);
+  SOS_CHECK_LAUNCH("sos_conv2d_tc");
+  if (a.plan_out) {
+    a.plan_out[0] = pl.fast_is_w;
+    a.plan_out[1] = pl.share;
+    a.plan_out[2] = pl.g;
+    a.plan_out[3] = p.S;
+    a.plan_out[4] = p.n_groups;
+    a.plan_out[5] = p.n_stages;
+    a.plan_out[6] = p.stage_bytes;
+    a.plan_out[7] = grid;
+  }
+  return SOS_OK;
+}

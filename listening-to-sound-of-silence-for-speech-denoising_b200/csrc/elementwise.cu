@@ -1,0 +1,845 @@
+// HBM-bound elementwise / reduction kernels of the hot path:
+//   complex-ratio-mask recovery (fwd/bwd)      M2/transform.py:156-169
+//   MSE / BCE-with-logits losses (fwd + grad)  M2/agent.py:172-190, M1/agent.py:185-202
+//   Adam step                                  M2/agent.py:167-170 (torch.optim.Adam defaults)
+//   BatchNorm (train/eval) + ReLU/PReLU fwd/bwd over NHWC activations
+//   layout changes (NCHW <-> NHWC, reflect borders, nearest resize, concat slices)
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+inline int grid_for(long long n, int per_block = kThreads, int max_blocks = 148 * 16) {
+  long long g = ceil_div_ll(n, per_block);
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ----------------------------------------------------------------------------- cRM
+__device__ __forceinline__ float crm_to_m(float c, float inv_a, float b) {
+  return inv_a * (logf(c / (1.f - c + 1e-8f) + 1e-10f) + b);
+}
+
+__global__ void icrm_fwd_kernel(const float* __restrict__ Y, const float* __restrict__ crm, float* __restrict__ rec,
+                                long long plane, long long total, float inv_a, float b) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long bi = e / plane, r = e - bi * plane;
+    const long long i0 = bi * 2 * plane + r, i1 = i0 + plane;
+    const float mr = crm_to_m(crm[i0], inv_a, b), mi = crm_to_m(crm[i1], inv_a, b);
+    const float yr = Y[i0], yi = Y[i1];
+    rec[i0] = mr * yr - mi * yi;
+    rec[i1] = mr * yi + mi * yr;
+  }
+}
+
+__device__ __forceinline__ float crm_dm_dc(float c, float inv_a) {
+  const float den = 1.f - c + 1e-8f;
+  const float u = c / den;
+  return inv_a * ((1.f + 1e-8f) / (den * den)) / (u + 1e-10f);
+}
+
+__global__ void icrm_bwd_kernel(const float* __restrict__ Y, const float* __restrict__ crm, const float* __restrict__ grec,
+                                float* __restrict__ gcrm, long long plane, long long total, float inv_a) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long bi = e / plane, r = e - bi * plane;
+    const long long i0 = bi * 2 * plane + r, i1 = i0 + plane;
+    const float yr = Y[i0], yi = Y[i1], gr = grec[i0], gi = grec[i1];
+    gcrm[i0] = (gr * yr + gi * yi) * crm_dm_dc(crm[i0], inv_a);
+    gcrm[i1] = (gi * yr - gr * yi) * crm_dm_dc(crm[i1], inv_a);
+  }
+}
+
+// ----------------------------------------------------------------------------- losses
+__global__ void mse_kernel(const float* __restrict__ pred, const float* __restrict__ tgt, long long n, float* __restrict__ loss_sum,
+                           float* __restrict__ grad, float gscale) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const float d = pred[e] - tgt[e];
+    acc = fmaf(d, d, acc);
+    if (grad) grad[e] = d * gscale;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0 && loss_sum) atomicAdd(loss_sum, acc);
+}
+
+__global__ void bce_kernel(const float* __restrict__ x, const float* __restrict__ y, long long n, float* __restrict__ loss_sum,
+                           float* __restrict__ grad, float gscale) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const float v = x[e], t = y[e];
+    acc += fmaxf(v, 0.f) - v * t + log1pf(expf(-fabsf(v)));
+    if (grad) grad[e] = (1.f / (1.f + expf(-v)) - t) * gscale;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0 && loss_sum) atomicAdd(loss_sum, acc);
+}
+
+// ----------------------------------------------------------------------------- Adam
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr_over_bc1, float b1, float b2, float eps, float inv_sqrt_bc2, float gscale) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const float gr = g[e] * gscale;
+    const float mm = b1 * m[e] + (1.f - b1) * gr;
+    const float vv = b2 * v[e] + (1.f - b2) * gr * gr;
+    m[e] = mm;
+    v[e] = vv;
+    p[e] -= lr_over_bc1 * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
+  }
+}
+
+// ----------------------------------------------------------------------------- views
+struct View {
+  int H, W;     // logical extent
+  int Hp, Wp;   // buffer extent
+  int ph, pw;   // offset of the logical window inside the buffer
+  int ld;       // channels per pixel in the buffer
+  int coff;     // first channel of the slice
+};
+__device__ __forceinline__ long long view_pix(const View& v, long long pix) {   // pix = (n*H + h)*W + w
+  const int w = (int)(pix % v.W);
+  const long long t = pix / v.W;
+  const int h = (int)(t % v.H);
+  const long long n = t / v.H;
+  return ((n * v.Hp + h + v.ph) * v.Wp + (w + v.pw)) * (long long)v.ld + v.coff;
+}
+
+// ----------------------------------------------------------------------------- BatchNorm
+// y dense [P][C]; each thread owns one float4 channel group and strides over rows.
+__global__ void __launch_bounds__(kThreads) bn_stats_kernel(const float* __restrict__ y, long long P, int C,
+                                                             float* __restrict__ partial /*[grid][2][C]*/) {
+  extern __shared__ float sm[];                 // [rows][2][C]
+  const int cg = C >> 2;
+  const int rows = kThreads / cg;
+  const int r = threadIdx.x / cg, c4 = threadIdx.x - r * cg;
+  float4 s = {0, 0, 0, 0}, q = {0, 0, 0, 0};
+  if (r < rows) {
+    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
+      const float4 v = *reinterpret_cast<const float4*>(y + p * C + c4 * 4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    }
+    float* d = sm + (size_t)r * 2 * C;
+    *reinterpret_cast<float4*>(d + c4 * 4) = s;
+    *reinterpret_cast<float4*>(d + C + c4 * 4) = q;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += kThreads) {
+    float a = 0.f;
+    for (int rr = 0; rr < rows; ++rr) a += sm[(size_t)rr * 2 * C + i];
+    partial[(size_t)blockIdx.x * 2 * C + i] = a;
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int G, int C, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   float* __restrict__ scale_out, float* __restrict__ shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0, q = 0;
+  for (int g = 0; g < G; ++g) {
+    s += partial[(size_t)g * 2 * C + c];
+    q += partial[(size_t)g * 2 * C + C + c];
+  }
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0) var = 0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  mean_out[c] = (float)mean;
+  invstd_out[c] = invstd;
+  const float sc = gamma[c] * invstd;
+  scale_out[c] = sc;
+  shift_out[c] = beta[c] - (float)mean * sc;
+  if (running_mean) {
+    const double unbiased = count > 1 ? var * count / (count - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = 1.f / sqrtf(rv[c] + eps);
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - rm[c] * sc;
+}
+
+__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return v > 0.f ? v : v * slope;
+  return v;
+}
+
+// z(view) = act(y * scale + shift);  y dense [P][C]
+__global__ void __launch_bounds__(kThreads) bn_act_kernel(const float* __restrict__ y, float* __restrict__ z, long long P, int C,
+                                                           const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                                           const float* __restrict__ slope_ptr, View zv) {
+  const int cg = C >> 2;
+  const float slope = slope_ptr ? *slope_ptr : 0.f;
+  const long long total = P * cg;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / cg;
+    const int c = (int)(e - p * cg) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(y + p * C + c);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+    float4 o;
+    o.x = act_fwd(fmaf(v.x, sc.x, sh.x), act, slope);
+    o.y = act_fwd(fmaf(v.y, sc.y, sh.y), act, slope);
+    o.z = act_fwd(fmaf(v.z, sc.z, sh.z), act, slope);
+    o.w = act_fwd(fmaf(v.w, sc.w, sh.w), act, slope);
+    *reinterpret_cast<float4*>(z + view_pix(zv, p) + c) = o;
+  }
+}
+
+// Backward pass 1: per-channel sums of dpre and dpre*xhat (+ PReLU slope grad).
+//   pre = y*scale+shift, dpre = dz * act'(pre), xhat = (y-mean)*invstd
+__global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __restrict__ dz, View dzv, const float* __restrict__ y,
+                                                                  long long P, int C, const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift, const float* __restrict__ mean,
+                                                                  const float* __restrict__ invstd, int act,
+                                                                  const float* __restrict__ slope_ptr,
+                                                                  float* __restrict__ partial /*[grid][3][C]*/) {
+  extern __shared__ float sm[];                 // [rows][3][C]
+  const int cg = C >> 2;
+  const int rows = kThreads / cg;
+  const int r = threadIdx.x / cg, c4 = threadIdx.x - r * cg;
+  const float slope = slope_ptr ? *slope_ptr : 0.f;
+  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, s3[4] = {0, 0, 0, 0};
+  if (r < rows) {
+    const int c = c4 * 4;
+    float sc[4], sh[4], mu[4], is[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { sc[i] = scale[c + i]; sh[i] = shift[c + i]; mu[i] = mean[c + i]; is[i] = invstd[c + i]; }
+    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
+      const float4 yv4 = *reinterpret_cast<const float4*>(y + p * C + c);
+      const float4 dz4 = *reinterpret_cast<const float4*>(dz + view_pix(dzv, p) + c);
+      const float yv[4] = {yv4.x, yv4.y, yv4.z, yv4.w}, dv[4] = {dz4.x, dz4.y, dz4.z, dz4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float pre = fmaf(yv[i], sc[i], sh[i]);
+        float dpre = dv[i];
+        if (act == 1) dpre = pre > 0.f ? dpre : 0.f;
+        else if (act == 2) { if (pre <= 0.f) { s3[i] = fmaf(dv[i], pre, s3[i]); dpre *= slope; } }
+        s1[i] += dpre;
+        s2[i] = fmaf(dpre, (yv[i] - mu[i]) * is[i], s2[i]);
+      }
+    }
+    float* d = sm + (size_t)r * 3 * C;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { d[c + i] = s1[i]; d[C + c + i] = s2[i]; d[2 * C + c + i] = s3[i]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += kThreads) {
+    float a = 0.f;
+    for (int rr = 0; rr < rows; ++rr) a += sm[(size_t)rr * 3 * C + i];
+    partial[(size_t)blockIdx.x * 3 * C + i] = a;
+  }
+}
+
+// Backward finalize: dgamma, dbeta, dslope and the two per-channel means used by pass 2.
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int G, int C, double count, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ dslope, float* __restrict__ m1,
+                                       float* __restrict__ m2) {
+  __shared__ float red[32];
+  float s3_local = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s1 = 0, s2 = 0, s3 = 0;
+    for (int g = 0; g < G; ++g) {
+      s1 += partial[(size_t)g * 3 * C + c];
+      s2 += partial[(size_t)g * 3 * C + C + c];
+      s3 += partial[(size_t)g * 3 * C + 2 * C + c];
+    }
+    dbeta[c] = (float)s1;
+    dgamma[c] = (float)s2;
+    m1[c] = (float)(s1 / count);
+    m2[c] = (float)(s2 / count);
+    s3_local += (float)s3;
+  }
+  s3_local = block_sum(s3_local, red);
+  if (threadIdx.x == 0 && dslope) *dslope = s3_local;
+}
+
+// Backward pass 2: dy = scale * (dpre - m1 - xhat*m2)      (scale = gamma*invstd)
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __restrict__ dz, View dzv, const float* __restrict__ y,
+                                                                 float* __restrict__ dy, long long P, int C,
+                                                                 const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                 const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                 const float* __restrict__ m1, const float* __restrict__ m2, int act,
+                                                                 const float* __restrict__ slope_ptr) {
+  const int cg = C >> 2;
+  const float slope = slope_ptr ? *slope_ptr : 0.f;
+  const long long total = P * cg;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / cg;
+    const int c = (int)(e - p * cg) * 4;
+    const float4 yv4 = *reinterpret_cast<const float4*>(y + p * C + c);
+    const float4 dz4 = *reinterpret_cast<const float4*>(dz + view_pix(dzv, p) + c);
+    const float yv[4] = {yv4.x, yv4.y, yv4.z, yv4.w}, dv[4] = {dz4.x, dz4.y, dz4.z, dz4.w};
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float sc = scale[c + i];
+      const float pre = fmaf(yv[i], sc, shift[c + i]);
+      float dpre = dv[i];
+      if (act == 1) dpre = pre > 0.f ? dpre : 0.f;
+      else if (act == 2) dpre = pre > 0.f ? dpre : dpre * slope;
+      const float xhat = (yv[i] - mean[c + i]) * invstd[c + i];
+      o[i] = sc * (dpre - m1[c + i] - xhat * m2[c + i]);
+    }
+    *reinterpret_cast<float4*>(dy + p * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// Eval-mode backward of z = act(y*scale + shift): dy = dz * act'(pre) * scale.
+__global__ void __launch_bounds__(kThreads) affine_act_bwd_kernel(const float* __restrict__ dz, View dzv, const float* __restrict__ y,
+                                                                   float* __restrict__ dy, long long P, int C,
+                                                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                   int act, const float* __restrict__ slope_ptr) {
+  const int cg = C >> 2;
+  const float slope = slope_ptr ? *slope_ptr : 0.f;
+  const long long total = P * cg;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / cg;
+    const int c = (int)(e - p * cg) * 4;
+    const float4 yv4 = *reinterpret_cast<const float4*>(y + p * C + c);
+    const float4 dz4 = *reinterpret_cast<const float4*>(dz + view_pix(dzv, p) + c);
+    const float yv[4] = {yv4.x, yv4.y, yv4.z, yv4.w}, dv[4] = {dz4.x, dz4.y, dz4.z, dz4.w};
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float sc = scale[c + i];
+      const float pre = fmaf(yv[i], sc, shift[c + i]);
+      float dpre = dv[i];
+      if (act == 1) dpre = pre > 0.f ? dpre : 0.f;
+      else if (act == 2) dpre = pre > 0.f ? dpre : dpre * slope;
+      o[i] = sc * dpre;
+    }
+    *reinterpret_cast<float4*>(dy + p * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// Tiled transpose: out (cols, rows) = in (rows, cols)^T.
+__global__ void transpose_kernel(const float* __restrict__ in, long long rows, long long cols, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const long long r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const long long c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+// y[r][c] = act(y[r][c] + bias[c]);  act 0 none, 1 relu, 3 sigmoid
+__global__ void bias_act_kernel(float* __restrict__ y, long long rows, int cols, long long ld, const float* __restrict__ bias, int act) {
+  const long long total = rows * cols;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / cols;
+    const int c = (int)(e - r * cols);
+    float v = y[r * ld + c] + (bias ? bias[c] : 0.f);
+    if (act == 1) v = fmaxf(v, 0.f);
+    else if (act == 3) v = 1.f / (1.f + expf(-v));
+    y[r * ld + c] = v;
+  }
+}
+
+// dpre = dy * act'(y_out);  dbias[c] += sum_r dpre[r][c].  One block column-strip of 32 columns x 256 rows per iteration.
+__global__ void bias_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dpre, long long rows,
+                                    int cols, long long ld, int act, float* __restrict__ dbias) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < cols) {
+    for (long long r = (long long)blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8) {
+      float g = dy[r * ld + c];
+      const float o = y[r * ld + c];
+      if (act == 1) g = o > 0.f ? g : 0.f;
+      else if (act == 3) g = g * o * (1.f - o);
+      dpre[r * ld + c] = g;
+      acc += g;
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols && dbias) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    atomicAdd(dbias + c, s);
+  }
+}
+
+// ----------------------------------------------------------------------------- layout
+// NCHW (B,C,H,W) -> view of NHWC buffer; channels >= C inside the slice width Cw are zero filled.
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, float* __restrict__ out, View ov, int Cw, long long P) {
+  const long long total = P * Cw;
+  const long long plane = (long long)ov.H * ov.W;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / Cw;
+    const int c = (int)(e - p * Cw);
+    const long long n = p / plane, r = p - n * plane;
+    out[view_pix(ov, p) + c] = c < C ? x[(n * C + c) * plane + r] : 0.f;
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, View iv, float* __restrict__ out, int C, long long P) {
+  const long long plane = (long long)iv.H * iv.W;
+  const long long total = P * C;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long n = e / (plane * C);
+    const long long rem = e - n * plane * C;
+    const int c = (int)(rem / plane);
+    const long long r = rem - c * plane;
+    out[e] = in[view_pix(iv, n * plane + r) + c];
+  }
+}
+
+// dst(view, H x W) = src(view, Hs x Ws) with PyTorch 'nearest' index map; C channels copied.
+// accumulate: dst += src (used for gradient fan-in)
+__global__ void copy_view_kernel(const float* __restrict__ src, View sv, float* __restrict__ dst, View dv, int C, long long Pd,
+                                 int accumulate) {
+  const int cg = C >> 2;
+  const long long total = Pd * cg;
+  const float sh = (float)sv.H / (float)dv.H, sw = (float)sv.W / (float)dv.W;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / cg;
+    const int c = (int)(e - p * cg) * 4;
+    const int w = (int)(p % dv.W);
+    const long long t = p / dv.W;
+    const int h = (int)(t % dv.H);
+    const long long n = t / dv.H;
+    int hs = h, ws = w;
+    if (sv.H != dv.H) hs = min((int)floorf(h * sh), sv.H - 1);
+    if (sv.W != dv.W) ws = min((int)floorf(w * sw), sv.W - 1);
+    const long long ps = (n * sv.H + hs) * sv.W + ws;
+    float4 v = *reinterpret_cast<const float4*>(src + view_pix(sv, ps) + c);
+    float* d = dst + view_pix(dv, p) + c;
+    if (accumulate) {
+      const float4 o = *reinterpret_cast<const float4*>(d);
+      v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+    }
+    *reinterpret_cast<float4*>(d) = v;
+  }
+}
+
+// Adjoint of copy_view with resize: gsrc(view) += gdst(view) through the nearest map (atomic when many-to-one).
+__global__ void copy_view_bwd_kernel(const float* __restrict__ gdst, View dv, float* __restrict__ gsrc, View sv, int C, long long Pd) {
+  const long long total = Pd * C;
+  const float sh = (float)sv.H / (float)dv.H, sw = (float)sv.W / (float)dv.W;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / C;
+    const int c = (int)(e - p * C);
+    const int w = (int)(p % dv.W);
+    const long long t = p / dv.W;
+    const int h = (int)(t % dv.H);
+    const long long n = t / dv.H;
+    int hs = h, ws = w;
+    if (sv.H != dv.H) hs = min((int)floorf(h * sh), sv.H - 1);
+    if (sv.W != dv.W) ws = min((int)floorf(w * sw), sv.W - 1);
+    const long long ps = (n * sv.H + hs) * sv.W + ws;
+    atomicAdd(gsrc + view_pix(sv, ps) + c, gdst[view_pix(dv, p) + c]);
+  }
+}
+
+__device__ __forceinline__ int reflect_coord(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// Fill the border of a padded NHWC buffer (B,Hp,Wp,C) by reflection of its interior (H x W at offset p).
+__global__ void reflect_fill_kernel(float* __restrict__ buf, int B, int H, int W, int pad, int C) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad, cg = C >> 2;
+  const long long total = (long long)B * Hp * Wp * cg;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % cg) * 4;
+    long long t = e / cg;
+    const int wp = (int)(t % Wp); t /= Wp;
+    const int hp = (int)(t % Hp);
+    const long long n = t / Hp;
+    const int h = hp - pad, w = wp - pad;
+    if (h >= 0 && h < H && w >= 0 && w < W) continue;
+    const int hs = reflect_coord(h, H) + pad, ws = reflect_coord(w, W) + pad;
+    *reinterpret_cast<float4*>(buf + ((n * Hp + hp) * Wp + wp) * (long long)C + c) =
+        *reinterpret_cast<const float4*>(buf + ((n * Hp + hs) * Wp + ws) * (long long)C + c);
+  }
+}
+
+// Adjoint: fold border gradients back into the interior (in place).  One thread per interior element gathers
+// the (up to 8) border positions that mirror onto it, so no atomics are needed.
+__global__ void reflect_fold_kernel(float* __restrict__ g, int B, int H, int W, int pad, int C) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad, cg = C >> 2;
+  const long long total = (long long)B * H * W * cg;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % cg) * 4;
+    long long t = e / cg;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const long long n = t / H;
+    // rows that map to h: h itself, -h (if 1<=h<=pad), 2(H-1)-h (if H-1-pad <= h <= H-2)
+    int hs[3], nh = 0, ws[3], nw = 0;
+    hs[nh++] = h;
+    if (h >= 1 && h <= pad) hs[nh++] = -h;
+    if (h <= H - 2 && h >= H - 1 - pad) hs[nh++] = 2 * (H - 1) - h;
+    ws[nw++] = w;
+    if (w >= 1 && w <= pad) ws[nw++] = -w;
+    if (w <= W - 2 && w >= W - 1 - pad) ws[nw++] = 2 * (W - 1) - w;
+    float4 acc = {0, 0, 0, 0};
+    for (int i = 0; i < nh; ++i)
+      for (int j = 0; j < nw; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(g + ((n * Hp + hs[i] + pad) * Wp + ws[j] + pad) * (long long)C + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    __syncwarp();
+    *reinterpret_cast<float4*>(g + ((n * Hp + h + pad) * Wp + w + pad) * (long long)C + c) = acc;
+  }
+}
+
+// Encoder output NHWC (B,F,T,C) -> LSTM sequence (V,B,ld) at column offset, feature index c*F+f,
+// with the reference's nearest resample T -> V  (M1/networks.py:131-133; src = floor(i*T/V)).
+__global__ void feat_to_seq_kernel(const float* __restrict__ in, int B, int F, int T, int C, float* __restrict__ out, int V, int ld,
+                                   int coff) {
+  const long long total = (long long)V * B * C * F;
+  const float scale = (float)T / (float)V;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(e % F);
+    long long t = e / F;
+    const int c = (int)(t % C); t /= C;
+    const int b = (int)(t % B);
+    const int v = (int)(t / B);
+    const int ts = (V == T) ? v : min((int)floorf(v * scale), T - 1);
+    out[((long long)v * B + b) * ld + coff + c * F + f] = in[(((long long)b * F + f) * T + ts) * C + c];
+  }
+}
+
+__global__ void feat_to_seq_bwd_kernel(const float* __restrict__ gout, int B, int F, int T, int C, float* __restrict__ gin, int V, int ld,
+                                       int coff) {
+  const long long total = (long long)V * B * C * F;
+  const float scale = (float)T / (float)V;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(e % F);
+    long long t = e / F;
+    const int c = (int)(t % C); t /= C;
+    const int b = (int)(t % B);
+    const int v = (int)(t / B);
+    const int ts = (V == T) ? v : min((int)floorf(v * scale), T - 1);
+    atomicAdd(gin + (((long long)b * F + f) * T + ts) * C + c, gout[((long long)v * B + b) * ld + coff + c * F + f]);
+  }
+}
+
+// ----------------------------------------------------------------------------- weight packing
+// PyTorch conv weight (Cout,Cin,kh,kw) -> GEMM B operand [Cout][ntaps*CinP], k = tap*CinP + ci (zero for ci >= Cin)
+//   mode 0: forward            tap = a*kw + b
+//   mode 1: data gradient      rows = Cin, cols = tap'*CoutP + co with tap' the flipped tap (a'=kh-1-a, b'=kw-1-b)
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int kh, int kw, int CinP, int CoutP, int mode,
+                                        float* __restrict__ out) {
+  const int ntaps = kh * kw;
+  const long long total = mode == 0 ? (long long)Cout * ntaps * CinP : (long long)Cin * ntaps * CoutP;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    if (mode == 0) {
+      const int ci = (int)(e % CinP);
+      const long long t = e / CinP;
+      const int tap = (int)(t % ntaps);
+      const int co = (int)(t / ntaps);
+      out[e] = ci < Cin ? w[((long long)co * Cin + ci) * ntaps + tap] : 0.f;
+    } else {
+      const int co = (int)(e % CoutP);
+      const long long t = e / CoutP;
+      const int tapf = (int)(t % ntaps);
+      const int ci = (int)(t / ntaps);
+      const int tap = ntaps - 1 - tapf;
+      out[e] = co < Cout ? w[((long long)co * Cin + ci) * ntaps + tap] : 0.f;
+    }
+  }
+}
+
+// wgrad result [taps][CoutP?]... -> PyTorch layout.  src is [tap][Cout][CinP] (tap-major), dst (Cout,Cin,kh,kw).
+__global__ void unpack_wgrad_kernel(const float* __restrict__ src, int Cout, int Cin, int ntaps, int CinP, float* __restrict__ dst,
+                                    int accumulate) {
+  const long long total = (long long)Cout * Cin * ntaps;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(e % ntaps);
+    const long long t = e / ntaps;
+    const int ci = (int)(t % Cin);
+    const int co = (int)(t / Cin);
+    const float v = src[((long long)tap * Cout + co) * CinP + ci];
+    dst[e] = accumulate ? dst[e] + v : v;
+  }
+}
+
+}  // namespace
+
+// ============================================================================= C ABI
+extern "C" {
+
+int sos_icrm_forward(const float* Y, const float* crm, float* rec, int64_t batch, int64_t plane, float a, float b,
+                     cudaStream_t stream) {
+  SOS_CHECK_ARG(Y && crm && rec && batch > 0 && plane > 0 && a != 0.f, "sos_icrm_forward: bad arguments");
+  const long long total = batch * plane;
+  icrm_fwd_kernel<<<grid_for(total), kThreads, 0, stream>>>(Y, crm, rec, plane, total, 1.f / a, b);
+  SOS_CHECK_LAUNCH("sos_icrm_forward");
+  return SOS_OK;
+}
+
+int sos_icrm_backward(const float* Y, const float* crm, const float* grad_rec, float* grad_crm, int64_t batch, int64_t plane,
+                      float a, cudaStream_t stream) {
+  SOS_CHECK_ARG(Y && crm && grad_rec && grad_crm && batch > 0 && plane > 0 && a != 0.f, "sos_icrm_backward: bad arguments");
+  const long long total = batch * plane;
+  icrm_bwd_kernel<<<grid_for(total), kThreads, 0, stream>>>(Y, crm, grad_rec, grad_crm, plane, total, 1.f / a);
+  SOS_CHECK_LAUNCH("sos_icrm_backward");
+  return SOS_OK;
+}
+
+int sos_mse_fwd_bwd(const float* pred, const float* target, int64_t n, float* loss_sum, float* grad_or_null, float grad_scale,
+                    cudaStream_t stream) {
+  SOS_CHECK_ARG(pred && target && n > 0, "sos_mse_fwd_bwd: bad arguments");
+  mse_kernel<<<grid_for(n, kThreads, 148 * 4), kThreads, 0, stream>>>(pred, target, n, loss_sum, grad_or_null, grad_scale);
+  SOS_CHECK_LAUNCH("sos_mse_fwd_bwd");
+  return SOS_OK;
+}
+
+int sos_bce_logits_fwd_bwd(const float* logits, const float* labels, int64_t n, float* loss_sum, float* grad_or_null,
+                           float grad_scale, cudaStream_t stream) {
+  SOS_CHECK_ARG(logits && labels && n > 0, "sos_bce_logits_fwd_bwd: bad arguments");
+  bce_kernel<<<grid_for(n, kThreads, 148), kThreads, 0, stream>>>(logits, labels, n, loss_sum, grad_or_null, grad_scale);
+  SOS_CHECK_LAUNCH("sos_bce_logits_fwd_bwd");
+  return SOS_OK;
+}
+
+int sos_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                  float eps, int64_t step, float grad_scale, cudaStream_t stream) {
+  SOS_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "sos_adam_step: bad arguments");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<grid_for(n), kThreads, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(lr / bc1), beta1, beta2, eps,
+                                                    (float)(1.0 / sqrt(bc2)), grad_scale);
+  SOS_CHECK_LAUNCH("sos_adam_step");
+  return SOS_OK;
+}
+
+// views are passed as 8 ints: H, W, Hp, Wp, ph, pw, ld, coff
+static View mk_view(const int32_t* v) { return View{v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]}; }
+static bool view_ok(const View& v, int C) {
+  return v.H > 0 && v.W > 0 && v.Hp >= v.H + v.ph && v.Wp >= v.W + v.pw && v.ph >= 0 && v.pw >= 0 && v.ld >= v.coff + C &&
+         (v.ld % 4) == 0 && (v.coff % 4) == 0;
+}
+
+int sos_bn_partial_blocks(int64_t rows, int64_t channels) {
+  if (channels < 4 || channels % 4 || channels > 1024) return 0;
+  const int rpb = kThreads / (int)(channels / 4);
+  long long g = ceil_div_ll(rows, (long long)rpb * 8);
+  if (g > 148 * 4) g = 148 * 4;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int sos_bn_stats(const float* y, int64_t rows, int64_t channels, float* partial, cudaStream_t stream) {
+  const int G = sos_bn_partial_blocks(rows, channels);
+  SOS_CHECK_ARG(y && partial && rows > 0 && G > 0, "sos_bn_stats: bad arguments (channels must be a multiple of 4, <= 1024)");
+  const int C = (int)channels, rpb = kThreads / (C / 4);
+  const size_t smem = (size_t)rpb * 2 * C * sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(bn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  bn_stats_kernel<<<G, kThreads, smem, stream>>>(y, rows, C, partial);
+  SOS_CHECK_LAUNCH("sos_bn_stats");
+  return SOS_OK;
+}
+
+int sos_bn_finalize(const float* partial, int64_t rows, int64_t channels, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale, float* shift,
+                    cudaStream_t stream) {
+  const int G = sos_bn_partial_blocks(rows, channels);
+  SOS_CHECK_ARG(partial && gamma && beta && mean && invstd && scale && shift && G > 0, "sos_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<ceil_div((int)channels, 128), 128, 0, stream>>>(partial, G, (int)channels, (double)rows, gamma, beta, eps, momentum,
+                                                                      running_mean, running_var, mean, invstd, scale, shift);
+  SOS_CHECK_LAUNCH("sos_bn_finalize");
+  return SOS_OK;
+}
+
+int sos_bn_eval_coeffs(int64_t channels, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float eps, float* scale, float* shift, cudaStream_t stream) {
+  SOS_CHECK_ARG(channels > 0 && gamma && beta && running_mean && running_var && scale && shift, "sos_bn_eval_coeffs: bad arguments");
+  bn_eval_coeffs_kernel<<<ceil_div((int)channels, 128), 128, 0, stream>>>((int)channels, gamma, beta, running_mean, running_var, eps,
+                                                                         scale, shift);
+  SOS_CHECK_LAUNCH("sos_bn_eval_coeffs");
+  return SOS_OK;
+}
+
+int sos_bn_act(const float* y, float* z, const int32_t* z_view, int64_t rows, int64_t channels, const float* scale,
+               const float* shift, int act, const float* slope, cudaStream_t stream) {
+  SOS_CHECK_ARG(y && z && z_view && scale && shift && rows > 0 && channels >= 4 && channels % 4 == 0, "sos_bn_act: bad arguments");
+  const View zv = mk_view(z_view);
+  SOS_CHECK_ARG(view_ok(zv, (int)channels) && rows % ((long long)zv.H * zv.W) == 0, "sos_bn_act: inconsistent view");
+  SOS_CHECK_ARG(act != 2 || slope, "sos_bn_act: PReLU needs a slope pointer");
+  bn_act_kernel<<<grid_for(rows * (channels / 4)), kThreads, 0, stream>>>(y, z, rows, (int)channels, scale, shift, act, slope, zv);
+  SOS_CHECK_LAUNCH("sos_bn_act");
+  return SOS_OK;
+}
+
+int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y, float* dy, int64_t rows, int64_t channels,
+                        const float* scale, const float* shift, const float* mean, const float* invstd, int act, const float* slope,
+                        float* partial, float* dgamma, float* dbeta, float* dslope, float* m1, float* m2, cudaStream_t stream) {
+  const int G = sos_bn_partial_blocks(rows, channels);
+  SOS_CHECK_ARG(dz && dz_view && y && dy && scale && shift && mean && invstd && partial && dgamma && dbeta && m1 && m2 && G > 0,
+                "sos_bn_act_backward: bad arguments");
+  const View dv = mk_view(dz_view);
+  const int C = (int)channels;
+  SOS_CHECK_ARG(view_ok(dv, C) && rows % ((long long)dv.H * dv.W) == 0, "sos_bn_act_backward: inconsistent view");
+  SOS_CHECK_ARG(act != 2 || (slope && dslope), "sos_bn_act_backward: PReLU needs slope and dslope");
+  const int rpb = kThreads / (C / 4);
+  const size_t smem = (size_t)rpb * 3 * C * sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  bn_bwd_reduce_kernel<<<G, kThreads, smem, stream>>>(dz, dv, y, rows, C, scale, shift, mean, invstd, act, slope, partial);
+  SOS_CHECK_LAUNCH("sos_bn_act_backward(reduce)");
+  bn_bwd_finalize_kernel<<<1, 256, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta, act == 2 ? dslope : nullptr, m1, m2);
+  SOS_CHECK_LAUNCH("sos_bn_act_backward(finalize)");
+  bn_bwd_apply_kernel<<<grid_for(rows * (channels / 4)), kThreads, 0, stream>>>(dz, dv, y, dy, rows, C, scale, shift, mean, invstd, m1,
+                                                                                 m2, act, slope);
+  SOS_CHECK_LAUNCH("sos_bn_act_backward(apply)");
+  return SOS_OK;
+}
+
+int sos_affine_act_backward(const float* dz, const int32_t* dz_view, const float* y, float* dy, int64_t rows, int64_t channels,
+                            const float* scale, const float* shift, int act, const float* slope, cudaStream_t stream) {
+  SOS_CHECK_ARG(dz && dz_view && y && dy && scale && shift && rows > 0 && channels >= 4 && channels % 4 == 0,
+                "sos_affine_act_backward: bad arguments");
+  const View dv = mk_view(dz_view);
+  SOS_CHECK_ARG(view_ok(dv, (int)channels) && rows % ((long long)dv.H * dv.W) == 0, "sos_affine_act_backward: inconsistent view");
+  SOS_CHECK_ARG(act != 2 || slope, "sos_affine_act_backward: PReLU needs a slope pointer");
+  affine_act_bwd_kernel<<<grid_for(rows * (channels / 4)), kThreads, 0, stream>>>(dz, dv, y, dy, rows, (int)channels, scale, shift, act,
+                                                                                   slope);
+  SOS_CHECK_LAUNCH("sos_affine_act_backward");
+  return SOS_OK;
+}
+
+int sos_transpose(const float* in, int64_t rows, int64_t cols, float* out, cudaStream_t stream) {
+  SOS_CHECK_ARG(in && out && rows > 0 && cols > 0 && ceil_div_ll(rows, 32) <= 65535, "sos_transpose: bad arguments");
+  dim3 grid((unsigned)ceil_div_ll(cols, 32), (unsigned)ceil_div_ll(rows, 32));
+  transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, rows, cols, out);
+  SOS_CHECK_LAUNCH("sos_transpose");
+  return SOS_OK;
+}
+
+int sos_bias_act(float* y, int64_t rows, int64_t cols, int64_t ld, const float* bias, int act, cudaStream_t stream) {
+  SOS_CHECK_ARG(y && rows > 0 && cols > 0 && ld >= cols && (act == 0 || act == 1 || act == 3), "sos_bias_act: bad arguments");
+  bias_act_kernel<<<grid_for(rows * cols), kThreads, 0, stream>>>(y, rows, (int)cols, ld, bias, act);
+  SOS_CHECK_LAUNCH("sos_bias_act");
+  return SOS_OK;
+}
+
+int sos_bias_act_backward(const float* dy, const float* y, float* dpre, int64_t rows, int64_t cols, int64_t ld, int act,
+                          float* dbias_or_null, cudaStream_t stream) {
+  SOS_CHECK_ARG(dy && y && dpre && rows > 0 && cols > 0 && ld >= cols && (act == 0 || act == 1 || act == 3),
+                "sos_bias_act_backward: bad arguments");
+  long long gy = ceil_div_ll(rows, 8 * 16);
+  if (gy > 64) gy = 64;
+  dim3 grid((unsigned)ceil_div_ll(cols, 32), (unsigned)gy);
+  bias_act_bwd_kernel<<<grid, dim3(32, 8), 0, stream>>>(dy, y, dpre, rows, (int)cols, ld, act, dbias_or_null);
+  SOS_CHECK_LAUNCH("sos_bias_act_backward");
+  return SOS_OK;
+}
+
+int sos_nchw_to_nhwc(const float* x, int64_t batch, int64_t channels, float* out, const int32_t* out_view, int64_t slice_channels,
+                     cudaStream_t stream) {
+  SOS_CHECK_ARG(x && out && out_view && batch > 0 && channels > 0 && slice_channels >= channels, "sos_nchw_to_nhwc: bad arguments");
+  const View ov = mk_view(out_view);
+  SOS_CHECK_ARG(view_ok(ov, (int)slice_channels), "sos_nchw_to_nhwc: inconsistent view");
+  const long long P = batch * ov.H * ov.W;
+  nchw_to_nhwc_kernel<<<grid_for(P * slice_channels), kThreads, 0, stream>>>(x, (int)channels, out, ov, (int)slice_channels, P);
+  SOS_CHECK_LAUNCH("sos_nchw_to_nhwc");
+  return SOS_OK;
+}
+
+int sos_nhwc_to_nchw(const float* in, const int32_t* in_view, int64_t batch, int64_t channels, float* out, cudaStream_t stream) {
+  SOS_CHECK_ARG(in && in_view && out && batch > 0 && channels > 0, "sos_nhwc_to_nchw: bad arguments");
+  const View iv = mk_view(in_view);
+  SOS_CHECK_ARG(iv.ld >= iv.coff + channels, "sos_nhwc_to_nchw: inconsistent view");
+  const long long P = batch * iv.H * iv.W;
+  nhwc_to_nchw_kernel<<<grid_for(P * channels), kThreads, 0, stream>>>(in, iv, out, (int)channels, P);
+  SOS_CHECK_LAUNCH("sos_nhwc_to_nchw");
+  return SOS_OK;
+}
+
+int sos_copy_view(const float* src, const int32_t* src_view, float* dst, const int32_t* dst_view, int64_t batch, int64_t channels,
+                  int accumulate, cudaStream_t stream) {
+  SOS_CHECK_ARG(src && dst && src_view && dst_view && batch > 0 && channels >= 4 && channels % 4 == 0, "sos_copy_view: bad arguments");
+  const View sv = mk_view(src_view), dv = mk_view(dst_view);
+  SOS_CHECK_ARG(view_ok(sv, (int)channels) && view_ok(dv, (int)channels), "sos_copy_view: inconsistent view");
+  const long long Pd = batch * dv.H * dv.W;
+  copy_view_kernel<<<grid_for(Pd * (channels / 4)), kThreads, 0, stream>>>(src, sv, dst, dv, (int)channels, Pd, accumulate);
+  SOS_CHECK_LAUNCH("sos_copy_view");
+  return SOS_OK;
+}
+
+int sos_copy_view_backward(const float* grad_dst, const int32_t* dst_view, float* grad_src, const int32_t* src_view, int64_t batch,
+                           int64_t channels, cudaStream_t stream) {
+  SOS_CHECK_ARG(grad_dst && grad_src && src_view && dst_view && batch > 0 && channels > 0, "sos_copy_view_backward: bad arguments");
+  const View sv = mk_view(src_view), dv = mk_view(dst_view);
+  const long long Pd = batch * dv.H * dv.W;
+  copy_view_bwd_kernel<<<grid_for(Pd * channels), kThreads, 0, stream>>>(grad_dst, dv, grad_src, sv, (int)channels, Pd);
+  SOS_CHECK_LAUNCH("sos_copy_view_backward");
+  return SOS_OK;
+}
+
+int sos_reflect_fill(float* buf, int64_t batch, int64_t H, int64_t W, int64_t pad, int64_t channels, cudaStream_t stream) {
+  SOS_CHECK_ARG(buf && batch > 0 && pad >= 0 && pad < H && pad < W && channels % 4 == 0, "sos_reflect_fill: bad arguments (pad must be < H, W)");
+  if (pad == 0) return SOS_OK;
+  const long long total = batch * (H + 2 * pad) * (W + 2 * pad) * (channels / 4);
+  reflect_fill_kernel<<<grid_for(total), kThreads, 0, stream>>>(buf, (int)batch, (int)H, (int)W, (int)pad, (int)channels);
+  SOS_CHECK_LAUNCH("sos_reflect_fill");
+  return SOS_OK;
+}
+
+int sos_reflect_fold(float* grad_buf, int64_t batch, int64_t H, int64_t W, int64_t pad, int64_t channels, cudaStream_t stream) {
+  SOS_CHECK_ARG(grad_buf && batch > 0 && pad >= 0 && pad < H && pad < W && channels % 4 == 0, "sos_reflect_fold: bad arguments");
+  if (pad == 0) return SOS_OK;
+  // every interior element only reads border cells and itself, and writes itself -> safe in place
+  reflect_fold_kernel<<<grid_for(batch * H * W * (channels / 4)), kThreads, 0, stream>>>(grad_buf, (int)batch, (int)H, (int)W, (int)pad,
+                                                                                          (int)channels);
+  SOS_CHECK_LAUNCH("sos_reflect_fold");
+  return SOS_OK;
+}
+
+int sos_feat_to_seq(const float* in, int64_t B, int64_t F, int64_t T, int64_t C, float* out, int64_t V, int64_t ld, int64_t coff,
+                    cudaStream_t stream) {
+  SOS_CHECK_ARG(in && out && B > 0 && F > 0 && T > 0 && C > 0 && V > 0 && ld >= coff + C * F, "sos_feat_to_seq: bad arguments");
+  feat_to_seq_kernel<<<grid_for(V * B * C * F), kThreads, 0, stream>>>(in, (int)B, (int)F, (int)T, (int)C, out, (int)V, (int)ld, (int)coff);
+  SOS_CHECK_LAUNCH("sos_feat_to_seq");
+  return SOS_OK;
+}
+
+int sos_feat_to_seq_backward(const float* grad_out, int64_t B, int64_t F, int64_t T, int64_t C, float* grad_in_zeroed, int64_t V,
+                             int64_t ld, int64_t coff, cudaStream_t stream) {
+  SOS_CHECK_ARG(grad_out && grad_in_zeroed && B > 0 && F > 0 && T > 0 && C > 0 && V > 0, "sos_feat_to_seq_backward: bad arguments");
+  feat_to_seq_bwd_kernel<<<grid_for(V * B * C * F), kThreads, 0, stream>>>(grad_out, (int)B, (int)F, (int)T, (int)C, grad_in_zeroed, (int)V,
+                                                                          (int)ld, (int)coff);
+  SOS_CHECK_LAUNCH("sos_feat_to_seq_backward");
+  return SOS_OK;
+}
+
+int sos_pack_conv_weight(const float* w, int64_t Cout, int64_t Cin, int64_t kh, int64_t kw, int64_t CinP, int64_t CoutP, int mode,
+                         float* out, cudaStream_t stream) {
+  SOS_CHECK_ARG(w && out && Cout > 0 && Cin > 0 && kh > 0 && kw > 0 && CinP >= Cin && CoutP >= Cout && (mode == 0 || mode == 1),
+                "sos_pack_conv_weight: bad arguments");
+  const long long total = mode == 0 ? Cout * kh * kw * CinP : Cin * kh * kw * CoutP;
+  pack_conv_weight_kernel<<<grid_for(total), kThreads, 0, stream>>>(w, (int)Cout, (int)Cin, (int)kh, (int)kw, (int)CinP, (int)CoutP, mode, out);
+  SOS_CHECK_LAUNCH("sos_pack_conv_weight");
+  return SOS_OK;
+}
+
+int sos_unpack_wgrad(const float* src, int64_t Cout, int64_t Cin, int64_t ntaps, int64_t CinP, float* dst, int accumulate,
+                     cudaStream_t stream) {
+  SOS_CHECK_ARG(src && dst && Cout > 0 && Cin > 0 && ntaps > 0 && CinP >= Cin, "sos_unpack_wgrad: bad arguments");
+  unpack_wgrad_kernel<<<grid_for(Cout * Cin * ntaps), kThreads, 0, stream>>>(src, (int)Cout, (int)Cin, (int)ntaps, (int)CinP, dst, accumulate);
+  SOS_CHECK_LAUNCH("sos_unpack_wgrad");
+  return SOS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,303 @@
+// STFT / iSTFT kernels for the reference's fixed transform
+//   n_fft = 510, hop = 158, win = periodic Hann(400) zero padded to 510
+// (reference: M2/transform.py:6-8,188-202 -> librosa 0.7.1 stft/istft).
+//
+// Both directions are formulated as a small dense real DFT against a
+// constant table that already contains the window:
+//   STFT : C[t][j] = sum_{n<400} x[reflect(158 t + n - 200)] * Wf[n][j],  j<512 (re | im)
+//   iSTFT: F[t][n] = sum_{j<512} S[j][t] * Wi[j][n]   followed by a gather
+//          overlap-add (each output sample sums <= 3 frames, no atomics) that
+//          also divides by the running sum of squared windows (librosa's
+//          window_sumsquare) and trims n_fft/2 on both ends.
+// The silent-interval gate (bits -> sample mask, M2/tools.py:340-362) is fused
+// into the STFT frame load; the complex-ratio-mask recovery
+// (M2/transform.py:141-169) can be fused into the iSTFT spectrum load.
+#include "common.cuh"
+#include <math.h>
+#include <vector>
+
+namespace {
+
+constexpr int kNfft = 510, kHop = 158, kWin = 400, kBins = 256, kLpad = 55, kJ = 512;
+
+float* g_wf = nullptr;   // [400][512]
+float* g_wi = nullptr;   // [512][400]
+float* g_w2 = nullptr;   // [400] squared window (float32, like librosa)
+
+int init_tables() {
+  if (g_wf) return SOS_OK;
+  std::vector<float> wf((size_t)kWin * kJ), wi((size_t)kJ * kWin), w2(kWin);
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int n = 0; n < kWin; ++n) {
+    const double w = 0.5 - 0.5 * cos(two_pi * n / kWin);
+    w2[n] = (float)(w * w);
+    const int m = n + kLpad;
+    for (int k = 0; k < kBins; ++k) {
+      const int ph = (int)(((long long)m * k) % kNfft);
+      const double a = two_pi * ph / kNfft;
+      wf[(size_t)n * kJ + k] = (float)(w * cos(a));
+      wf[(size_t)n * kJ + kBins + k] = (float)(-w * sin(a));
+      const double coef = (k == 0 || k == kBins - 1) ? 1.0 : 2.0;
+      wi[(size_t)k * kWin + n] = (float)(coef * w * cos(a) / kNfft);
+      wi[(size_t)(kBins + k) * kWin + n] = (k == 0 || k == kBins - 1) ? 0.f : (float)(-coef * w * sin(a) / kNfft);
+    }
+  }
+  if (cudaMalloc(&g_wf, wf.size() * 4) != cudaSuccess || cudaMalloc(&g_wi, wi.size() * 4) != cudaSuccess ||
+      cudaMalloc(&g_w2, w2.size() * 4) != cudaSuccess) {
+    sos_set_error("stft: cudaMalloc of DFT tables failed");
+    g_wf = nullptr;
+    return SOS_ERR_CUDA;
+  }
+  cudaMemcpy(g_wf, wf.data(), wf.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(g_wi, wi.data(), wi.size() * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(g_w2, w2.data(), w2.size() * 4, cudaMemcpyHostToDevice);
+  return SOS_OK;
+}
+
+// The reference's bit-string -> sample mask (1 = silent), M2/tools.py:340-362.
+// frame_lo[i] = int(i * ratio) computed on the host with the reference's own
+// float expression; frame i writes [frame_lo[i], frame_lo[i+1]-1) and the
+// one-sample gap frame_lo[i+1]-1 (and any tail) stays 0.  The second pass
+// flips every run of equal values shorter than 5 samples (runs are taken on
+// the pre-flip values), which fills the gap between two silent frames and
+// handles clips truncated in the middle of a frame.
+__device__ __forceinline__ int frame_of(int s, int nb, const int* __restrict__ frame_lo, float inv_ratio) {
+  int i = (int)((float)s * inv_ratio);
+  if (i > nb) i = nb;
+  while (i > 0 && frame_lo[i] > s) --i;
+  while (i < nb && frame_lo[i + 1] <= s) ++i;
+  return i;                                        // nb means "after the last frame"
+}
+
+__device__ __forceinline__ int preflip(int s, const uint8_t* __restrict__ bits, int nb, const int* __restrict__ frame_lo,
+                                       float inv_ratio) {
+  const int i = frame_of(s, nb, frame_lo, inv_ratio);
+  if (i >= nb) return 0;
+  return (s < frame_lo[i + 1] - 1 && bits[i] == 0) ? 1 : 0;
+}
+
+__device__ __forceinline__ float sample_mask(int s, int L, const uint8_t* __restrict__ bits, int nb,
+                                             const int* __restrict__ frame_lo, float inv_ratio) {
+  const int i = frame_of(s, nb, frame_lo, inv_ratio);
+  if (i < nb) {                                    // fast path: deep inside a frame
+    const int lo = frame_lo[i], hi = frame_lo[i + 1] - 1;
+    if (s - lo >= 4 && hi - s > 4 && L - s > 4) return bits[i] == 0 ? 1.f : 0.f;
+  }
+  const int v = preflip(s, bits, nb, frame_lo, inv_ratio);
+  int a = 0, b = 0;
+  while (a < 4 && s - a - 1 >= 0 && preflip(s - a - 1, bits, nb, frame_lo, inv_ratio) == v) ++a;
+  while (b < 4 && s + b + 1 < L && preflip(s + b + 1, bits, nb, frame_lo, inv_ratio) == v) ++b;
+  return (a + 1 + b < 5) ? (float)(1 - v) : (float)v;
+}
+
+__device__ __forceinline__ int reflect_idx(int j, int L) {
+  if (j < 0) j = -j;
+  if (j >= L) j = 2 * (L - 1) - j;
+  return j;
+}
+
+// ---------------------------------------------------------------------------
+// STFT: block tile 64 frames x 64 outputs, K = 400 in steps of 16.
+// grid = (ceil(T/64), 8, B), block = 256.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stft_fwd_kernel(const float* __restrict__ wave, int L, int T,
+                                                       const float* __restrict__ wf, float* __restrict__ out,
+                                                       const uint8_t* __restrict__ bits, int nb,
+                                                       const int* __restrict__ frame_lo, float inv_ratio, int gate_mode) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int b = blockIdx.z, t0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const float* x = wave + (size_t)b * L;
+  const uint8_t* bb = bits ? bits + (size_t)b * nb : nullptr;
+  float acc[4][4] = {};
+  for (int n0 = 0; n0 < kWin; n0 += 16) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + r * 256;          // 1024 = 64 frames x 16 samples
+      const int nn = e & 15, tt = e >> 4;
+      const int t = t0 + tt;
+      float v = 0.f;
+      if (t < T) {
+        const int s = reflect_idx(t * kHop + n0 + nn - 200, L);
+        v = x[s];
+        if (gate_mode) {
+          const float m = sample_mask(s, L, bb, nb, frame_lo, inv_ratio);
+          v *= (gate_mode == 1) ? m : (1.f - m);
+        }
+      }
+      As[nn][tt] = v;
+      const int jj = e & 63, nb2 = e >> 6;
+      Bs[nb2][jj] = wf[(size_t)(n0 + nb2) * kJ + j0 + jj];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][tx * 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&Bs[k][ty * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int jg = j0 + ty * 4 + j;
+    const int c = jg >> 8, k = jg & 255;
+    float* o = out + (((size_t)b * 2 + c) * kBins + k) * T;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 + tx * 4 + i;
+      if (t < T) o[t] = acc[i][j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// iSTFT stage 1: windowed inverse DFT frames  F[b][t][n], n < 400.
+// grid = (ceil(T/64), ceil(400/64), B), block = 256.
+// If `crm` is given the spectrum is recovered on the fly:
+//   M = 10*log(crm/(1-crm+1e-8)+1e-10);  S = M (*) Y   (complex product)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float icrm_m(float c, float inv_a, float bcoef) {
+  return inv_a * (logf(c / (1.f - c + 1e-8f) + 1e-10f) + bcoef);
+}
+
+__global__ void __launch_bounds__(256) istft_frames_kernel(const float* __restrict__ spec, const float* __restrict__ crm,
+                                                           int T, const float* __restrict__ wi, float* __restrict__ frames) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int b = blockIdx.z, t0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const float* S = spec + (size_t)b * 2 * kBins * T;
+  const float* C = crm ? crm + (size_t)b * 2 * kBins * T : nullptr;
+  float acc[4][4] = {};
+  for (int j0 = 0; j0 < kJ; j0 += 16) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int e = tid + r * 256;
+      const int tt = e & 63, jj = e >> 6;       // coalesced along t
+      const int t = t0 + tt, j = j0 + jj;
+      float v = 0.f;
+      if (t < T) {
+        if (!C) {
+          v = S[(size_t)j * T + t];
+        } else {
+          const int k = j & 255;
+          const float yr = S[(size_t)k * T + t], yi = S[(size_t)(kBins + k) * T + t];
+          const float mr = icrm_m(C[(size_t)k * T + t], 10.f, 0.f), mi = icrm_m(C[(size_t)(kBins + k) * T + t], 10.f, 0.f);
+          v = (j < kBins) ? (mr * yr - mi * yi) : (mr * yi + mi * yr);
+        }
+      }
+      As[jj][tt] = v;
+      const int nn = e & 63, jb = e >> 6;
+      const int n = n0 + nn;
+      Bs[jb][nn] = (n < kWin) ? wi[(size_t)(j0 + jb) * kWin + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int t = t0 + ty * 4 + i;
+    if (t >= T) continue;
+    float* o = frames + ((size_t)b * T + t) * kWin;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < kWin) o[n] = acc[i][j];
+    }
+  }
+}
+
+// iSTFT stage 2: gather overlap-add + window-sum-square normalisation + trim.
+__global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict__ frames, int T, const float* __restrict__ w2,
+                                                        float* __restrict__ wave, int out_len) {
+  const int b = blockIdx.y;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= out_len) return;
+  const int p = s + kNfft / 2;                 // index in the untrimmed signal
+  // frames t with 0 <= p - 158 t - 55 < 400
+  int t_hi = (p - kLpad) / kHop;
+  if (t_hi > T - 1) t_hi = T - 1;
+  int t_lo = (p - kLpad - (kWin - 1) + kHop - 1) / kHop;
+  if (p - kLpad - (kWin - 1) < 0) t_lo = 0;
+  float y = 0.f, wss = 0.f;
+  for (int t = t_lo; t <= t_hi; ++t) {         // increasing t: same add order as librosa
+    const int n = p - kHop * t - kLpad;
+    y += frames[((size_t)b * T + t) * kWin + n];
+    wss += w2[n];
+  }
+  if (wss > 1.17549435e-38f) y /= wss;
+  wave[(size_t)b * out_len + s] = y;
+}
+
+__global__ void gate_wave_kernel(const float* __restrict__ wave, int L, const uint8_t* __restrict__ bits, int nb,
+                                 const int* __restrict__ frame_lo, float inv_ratio, int mode, float* __restrict__ out,
+                                 float* __restrict__ mask_out) {
+  const int b = blockIdx.y;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= L) return;
+  const float m = sample_mask(s, L, bits + (size_t)b * nb, nb, frame_lo, inv_ratio);
+  if (out) out[(size_t)b * L + s] = wave[(size_t)b * L + s] * (mode == 1 ? m : 1.f - m);
+  if (mask_out) mask_out[(size_t)b * L + s] = m;
+}
+
+}  // namespace
+
+extern "C" int sos_init(void) { return init_tables(); }
+
+extern "C" int sos_stft_forward(const float* wave, int64_t batch, int64_t length, float* spec_out, const uint8_t* bits,
+                                int64_t n_bits, const int32_t* frame_lo, double ratio, int gate_mode, cudaStream_t stream) {
+  SOS_CHECK_ARG(wave && spec_out && batch > 0 && length > kNfft / 2, "sos_stft_forward: bad arguments (need length > 255)");
+  SOS_CHECK_ARG(gate_mode == 0 || (bits && frame_lo && n_bits > 0 && ratio > 0), "sos_stft_forward: gating needs bits/frame_lo/ratio");
+  SOS_CHECK_ARG(batch <= 65535, "sos_stft_forward: batch > 65535");
+  if (int e = init_tables()) return e;
+  const int T = 1 + (int)(length / kHop);
+  dim3 grid(ceil_div(T, 64), kJ / 64, (unsigned)batch);
+  stft_fwd_kernel<<<grid, 256, 0, stream>>>(wave, (int)length, T, g_wf, spec_out, gate_mode ? bits : nullptr, (int)n_bits,
+                                            frame_lo, gate_mode ? (float)(1.0 / ratio) : 0.f, gate_mode);
+  SOS_CHECK_LAUNCH("sos_stft_forward");
+  return SOS_OK;
+}
+
+extern "C" int sos_istft_forward(const float* spec, const float* crm_or_null, int64_t batch, int64_t n_frames, float* frames_ws,
+                                 float* wave_out, cudaStream_t stream) {
+  SOS_CHECK_ARG(spec && frames_ws && wave_out && batch > 0 && n_frames > 1, "sos_istft_forward: bad arguments");
+  SOS_CHECK_ARG(batch <= 65535, "sos_istft_forward: batch > 65535");
+  if (int e = init_tables()) return e;
+  const int T = (int)n_frames;
+  dim3 g1(ceil_div(T, 64), ceil_div(kWin, 64), (unsigned)batch);
+  istft_frames_kernel<<<g1, 256, 0, stream>>>(spec, crm_or_null, T, g_wi, frames_ws);
+  SOS_CHECK_LAUNCH("sos_istft_forward(frames)");
+  const int out_len = kHop * (T - 1);
+  dim3 g2(ceil_div(out_len, 256), (unsigned)batch);
+  istft_ola_kernel<<<g2, 256, 0, stream>>>(frames_ws, T, g_w2, wave_out, out_len);
+  SOS_CHECK_LAUNCH("sos_istft_forward(ola)");
+  return SOS_OK;
+}
+
+extern "C" int sos_gate_wave(const float* wave, int64_t batch, int64_t length, const uint8_t* bits, int64_t n_bits,
+                             const int32_t* frame_lo, double ratio, int mode, float* out_or_null, float* mask_or_null,
+                             cudaStream_t stream) {
+  SOS_CHECK_ARG(batch > 0 && length > 0 && bits && frame_lo && n_bits > 0 && ratio > 0, "sos_gate_wave: bad arguments");
+  SOS_CHECK_ARG(out_or_null == nullptr || wave != nullptr, "sos_gate_wave: wave required when out is given");
+  dim3 grid(ceil_div((int)length, 256), (unsigned)batch);
+  gate_wave_kernel<<<grid, 256, 0, stream>>>(wave, (int)length, bits, (int)n_bits, frame_lo, (float)(1.0 / ratio), mode, out_or_null,
+                                             mask_or_null);
+  SOS_CHECK_LAUNCH("sos_gate_wave");
+  return SOS_OK;
+}

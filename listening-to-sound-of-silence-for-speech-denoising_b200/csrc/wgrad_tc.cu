@@ -1,0 +1,397 @@
+// Weight gradient of the tap-list operator on the 5th-gen tensor cores (tcgen05 kind::tf32, fp32 accumulate in TMEM).
+//
+//     dw[t][co][ci] += sum_{pixels p} dy[p][co] * x[p*s + off_t][ci]
+//
+// is a GEMM whose reduction axis is the pixel axis, so both operands are consumed "MN-major": a staged NHWC box
+// [pixel][channel chunk] is exactly the canonical MN-major swizzled tile (one 32/64/128-byte row per k index).
+//   A = dy tile   (M = 128 output channels of one channel block, K = 8 pixels per MMA)
+//   B = x box     (N = Cin, same K) -- one box per tap group, shared by the taps that differ by a slow-axis shift
+//   D = dw[t] block, one TMEM accumulator (N columns) per tap, up to 512 columns per job
+// Work item = (job, pixel slice): a job is a set of tap groups of one output-channel block whose accumulators fit in
+// TMEM; the pixel tiles are split into slices so that all SMs are busy and jobs of the same slice run concurrently
+// (their operand boxes hit in L2).  Partial sums are merged with fp32 atomics (red.global.add).
+//
+// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 drain TMEM at the end of each work item.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "sos_b200.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace ptx;
+using namespace tc;
+
+constexpr int kThreadsWg = 192;
+constexpr int kMaxJobs = 100;
+
+struct alignas(64) WgParams {
+  CUtensorMap mapX, mapDY;
+  int n_jobs, n_slices, tiles_per_slice, total_tiles;
+  int tiles_fast, tiles_slow, n_phase;
+  int FB, SB, stride;
+  int Cin, Cout, N;
+  int cbi, n_ci_chunks, cbo;
+  int x_box_bytes, x_box_stride, dy_chunk_bytes, dy_chunk_stride, x_off;
+  int stage_bytes, n_stages;
+  int layout_a, layout_b;
+  uint32_t idesc;
+  float* dw;
+  int16_t job_coblk[kMaxJobs], job_g0[kMaxJobs], job_ng[kMaxJobs];
+  TapGroup groups[kMaxGroups];
+};
+
+struct WgTile { int tf, ts, ph, n; };
+__device__ __forceinline__ WgTile decode_wg_tile(const WgParams& p, int t) {
+  WgTile c;
+  c.tf = t % p.tiles_fast; t /= p.tiles_fast;
+  c.ts = t % p.tiles_slow; t /= p.tiles_slow;
+  c.ph = t % p.n_phase;
+  c.n = t / p.n_phase;
+  return c;
+}
+
+__device__ __forceinline__ void umma_tf32_wg(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  umma_tf32(d_tmem, adesc, bdesc, idesc, accumulate);
+}
+
+__global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // barriers live at the front (the operand stages may be over-read by the padded MMA rows, never the barriers)
+  const uint32_t bar_base = smem_base;
+  const uint32_t stages_base = smem_base + 1024;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (16 + s); };
+  const uint32_t tfull_bar = bar_base + 8u * 32, tempty_bar = bar_base + 8u * 33;
+  const uint32_t tmem_slot = bar_base + 8u * 34;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.mapX);
+    prefetch_tmap(&p.mapDY);
+    for (int s = 0; s < p.n_stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int n_items = p.n_jobs * p.n_slices;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
+        const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
+        const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
+        const int coblk = p.job_coblk[job], g0 = p.job_g0[job], ng = p.job_ng[job];
+        const int co_here = min(128, p.Cout - coblk * 128);
+        const int n_co_chunks = (co_here + p.cbo - 1) / p.cbo;
+        const uint32_t tx = (uint32_t)n_co_chunks * p.dy_chunk_bytes + (uint32_t)ng * p.n_ci_chunks * p.x_box_bytes;
+        for (int tile = t0; tile < t1; ++tile) {
+          const WgTile tc = decode_wg_tile(p, tile);
+          mbar_wait(empty_bar(stage), phase ^ 1, 500);
+          mbar_expect_tx(full_bar(stage), tx);
+          const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
+          for (int cc = 0; cc < n_co_chunks; ++cc)
+            tma_load_5d(sbase + (uint32_t)cc * p.dy_chunk_stride, &p.mapDY, full_bar(stage), coblk * 128 + cc * p.cbo, tc.tf * p.FB,
+                        tc.ts * p.SB, tc.ph, tc.n);
+          for (int gi = 0; gi < ng; ++gi) {
+            const TapGroup& grp = p.groups[g0 + gi];
+            const uint32_t xb = sbase + p.x_off + (uint32_t)gi * p.n_ci_chunks * p.x_box_stride;
+            for (int c = 0; c < p.n_ci_chunks; ++c)
+              tma_load_5d(xb + (uint32_t)c * p.x_box_stride, &p.mapX, full_bar(stage), c * p.cbi, tc.tf * p.FB * p.stride + grp.d_fast,
+                          tc.ts * p.SB * p.stride + grp.d_slow, tc.ph, tc.n);
+          }
+          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    int stage = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const uint32_t a_kstep = 8u * p.cbo * 4u, b_kstep = 8u * p.cbi * 4u;     // 8 pixels (one k step) of one chunk
+    for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
+      const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
+      const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
+      if (t0 >= t1) continue;
+      const int g0 = p.job_g0[job], ng = p.job_ng[job];
+      mbar_wait(tempty_bar, acc_phase ^ 1, 600);
+      tc_fence_after();
+      for (int tile = t0; tile < t1; ++tile) {
+        mbar_wait(full_bar(stage), phase, 601);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
+          int slot = 0;
+          for (int gi = 0; gi < ng; ++gi) {
+            const TapGroup& grp = p.groups[g0 + gi];
+            const uint32_t xb = sbase + p.x_off + (uint32_t)gi * p.n_ci_chunks * p.x_box_stride;
+            for (int j = 0; j < grp.n_sub; ++j, ++slot) {
+              const uint32_t d = tmem_base + (uint32_t)slot * p.N;
+              for (int ks = 0; ks < p.SB; ++ks) {
+                const uint64_t ad = make_smem_desc(sbase + ks * a_kstep, p.dy_chunk_stride, a_kstep, p.layout_a);
+                const uint64_t bd = make_smem_desc(xb + (ks + grp.a_off[j]) * b_kstep, p.x_box_stride, b_kstep, p.layout_b);
+                umma_tf32_wg(d, ad, bd, p.idesc, (tile != t0 || ks != 0) ? 1u : 0u);
+              }
+            }
+          }
+          umma_commit(empty_bar(stage));
+          if (tile == t1 - 1) umma_commit(tfull_bar);
+        }
+        __syncwarp();
+        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+      }
+      acc_phase ^= 1;
+    }
+  } else {
+    // ===================================================================== drain (warps 2..5)
+    const int q = warp & 3;
+    uint32_t acc_phase = 0;
+    for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
+      const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
+      const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
+      if (t0 >= t1) continue;
+      const int coblk = p.job_coblk[job], g0 = p.job_g0[job], ng = p.job_ng[job];
+      const int co = coblk * 128 + q * 32 + lane;
+      mbar_wait(tfull_bar, acc_phase, 700);
+      tc_fence_after();
+      int slot = 0;
+      for (int gi = 0; gi < ng; ++gi) {
+        const TapGroup& grp = p.groups[g0 + gi];
+        for (int j = 0; j < grp.n_sub; ++j, ++slot) {
+          float* dst = p.dw + ((size_t)grp.tap[j] * p.Cout + co) * p.Cin;
+          for (int c0 = 0; c0 < p.N; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * p.N + c0), r);
+            tmem_ld_wait();
+            if (co < p.Cout) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < p.Cin) atomicAdd(dst + c0 + i, __uint_as_float(r[i]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+      acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
+  SOS_CHECK_ARG(ap != nullptr, "sos_conv2d_wgrad: null args");
+  const sos_wgrad_args& a = *ap;
+  SOS_CHECK_ARG(a.x && a.dy && a.dw && a.tap_dh && a.tap_dw, "sos_conv2d_wgrad: null pointer");
+  SOS_CHECK_ARG(a.N > 0 && a.H > 0 && a.W > 0 && a.OH > 0 && a.OW > 0 && a.ntaps > 0 && a.ntaps <= 49, "sos_conv2d_wgrad: bad shape");
+  SOS_CHECK_ARG(a.Cin >= 8 && a.Cin % 8 == 0 && a.Cin <= 256, "sos_conv2d_wgrad: Cin must be a multiple of 8 in [8, 256] (got %lld)",
+                (long long)a.Cin);
+  SOS_CHECK_ARG(a.Cout >= 8 && a.Cout % 8 == 0 && a.Cout <= 1024, "sos_conv2d_wgrad: Cout must be a multiple of 8 in [8, 1024] (got %lld)",
+                (long long)a.Cout);
+  SOS_CHECK_ARG(a.Cdy % 4 == 0 && a.dy_coff % 4 == 0 && a.dy_coff + a.Cout <= a.Cdy, "sos_conv2d_wgrad: bad dy channel slice");
+  SOS_CHECK_ARG(a.stride == 1 || a.stride == 2, "sos_conv2d_wgrad: stride must be 1 or 2");
+  SOS_CHECK_ARG(((uintptr_t)a.x % 16) == 0 && ((uintptr_t)a.dy % 16) == 0, "sos_conv2d_wgrad: pointers must be 16-byte aligned");
+
+  Geometry geo{(int)a.ntaps, a.tap_dh, a.tap_dw, (int)a.H, (int)a.W, (int)a.OH, (int)a.OW, (int)a.stride, (int)a.Cin, (int)a.Cout, true,
+               std::min(kMaxSub, 512 / round_up((int)a.Cin, 16))};
+  Plan best;
+  for (int fw = 1; fw >= 0; --fw)
+    for (int sh = 1; sh >= 0; --sh) {
+      Plan pl;
+      if (build_plan(geo, fw != 0, sh != 0, pl) && pl.FB == 8 && pl.cost < best.cost) best = pl;
+    }
+  if (a.force_plan >= 0) {
+    Plan pl;
+    SOS_CHECK_ARG(build_plan(geo, (a.force_plan & 1) != 0, (a.force_plan & 2) != 0, pl) && pl.FB == 8,
+                  "sos_conv2d_wgrad: forced plan %d not applicable", (int)a.force_plan);
+    best = pl;
+  }
+  SOS_CHECK_ARG(best.cost < 1e299, "sos_conv2d_wgrad: no feasible plan");
+  const Plan& pl = best;
+
+  static WgParams p;
+  memset(&p, 0, sizeof(p));
+  const int Cin = (int)a.Cin, Cout = (int)a.Cout;
+  p.Cin = Cin;
+  p.Cout = Cout;
+  p.N = round_up(Cin, 16);
+  p.cbi = Cin % 32 == 0 ? 32 : (Cin % 16 == 0 ? 16 : 8);
+  p.n_ci_chunks = Cin / p.cbi;
+  p.cbo = Cout % 32 == 0 ? 32 : (Cout % 16 == 0 ? 16 : 8);
+  p.FB = 8;
+  p.stride = (int)a.stride;
+  p.dw = a.dw;
+  auto layout_of = [](int cb) { return cb == 128 ? 2 : (cb == 64 ? 4 : 6); };
+  p.layout_a = layout_of(p.cbo * 4);
+  p.layout_b = layout_of(p.cbi * 4);
+  p.idesc = make_idesc_tf32(128, p.N, 1, 1);
+
+  // ---- jobs: tap groups packed into TMEM (512 columns) per output-channel block; at most kMaxJobGroups boxes per stage
+  const int n_acc = 512 / p.N;
+  const int n_coblk = ceil_div(Cout, 128);
+  const int n_groups = (int)pl.groups.size();
+  SOS_CHECK_ARG(n_groups <= kMaxGroups, "sos_conv2d_wgrad: too many tap groups");
+  for (int i = 0; i < n_groups; ++i) {
+    p.groups[i] = pl.groups[i];
+    SOS_CHECK_ARG(pl.groups[i].n_sub <= n_acc, "sos_conv2d_wgrad: tap group does not fit in TMEM");
+  }
+  const int co_blk_ch = std::min(128, Cout);
+  const int n_co_chunks_max = ceil_div(co_blk_ch, p.cbo);
+  int max_ng = 1;
+  // choose SB (pixels per tile = 8*SB) and groups per job so that at least 2 stages fit
+  int SB = 16, groups_per_job = 1;
+  const int avail = kSmemLimit - 2048;
+  auto stage_bytes_for = [&](int sb, int ng, int* x_off_out, int* reach_out) {
+    const int dy_chunk = sb * 8 * p.cbo * 4;
+    const int dy_stride = round_up(dy_chunk, 1024);
+    const int x_box = (sb + pl.halo) * 8 * p.cbi * 4;
+    const int x_stride = round_up(x_box, 1024);
+    const int x_off = n_co_chunks_max * dy_stride;
+    const int used = x_off + ng * p.n_ci_chunks * x_stride;
+    // the padded MMA rows (M = 128, N rounded to 16) read past the staged chunks: keep that inside the stage
+    const int reach_a = (128 / p.cbo) * dy_stride;
+    const int reach_b = x_off + ((ng - 1) * p.n_ci_chunks + p.N / p.cbi) * x_stride;
+    if (x_off_out) *x_off_out = x_off;
+    if (reach_out) *reach_out = std::max(reach_a, reach_b);
+    return used;
+  };
+  for (;;) {
+    int reach = 0;
+    const int used = stage_bytes_for(SB, 1, nullptr, &reach);
+    if (2 * used + std::max(0, reach - used) <= avail || SB == 2) break;
+    SB /= 2;
+  }
+  // more groups per job (sharing the staged dy tile) while TMEM and 3 stages allow
+  {
+    int taps_in = 0;
+    for (int ng = 2; ng <= n_groups; ++ng) {
+      taps_in = 0;
+      for (int i = 0; i < ng; ++i) taps_in += pl.groups[i].n_sub;
+      int reach = 0;
+      const int used = stage_bytes_for(SB, ng, nullptr, &reach);
+      if (taps_in > n_acc || 3 * used + std::max(0, reach - used) > avail) break;
+      groups_per_job = ng;
+    }
+  }
+  int reach = 0;
+  const int used = stage_bytes_for(SB, groups_per_job, &p.x_off, &reach);
+  p.SB = SB;
+  p.dy_chunk_bytes = SB * 8 * p.cbo * 4;
+  p.dy_chunk_stride = round_up(p.dy_chunk_bytes, 1024);
+  p.x_box_bytes = (SB + pl.halo) * 8 * p.cbi * 4;
+  p.x_box_stride = round_up(p.x_box_bytes, 1024);
+  p.stage_bytes = used;
+  const int tail = std::max(0, reach - used);
+  p.n_stages = std::min(8, (avail - tail) / used);
+  SOS_CHECK_ARG(p.n_stages >= 1, "sos_conv2d_wgrad: stage of %d bytes does not fit in shared memory", used);
+
+  int n_jobs = 0;
+  for (int cb = 0; cb < n_coblk; ++cb) {
+    int g = 0;
+    while (g < n_groups) {
+      int ng = 0, taps_in = 0;
+      while (g + ng < n_groups && ng < groups_per_job && taps_in + pl.groups[g + ng].n_sub <= n_acc) {
+        taps_in += pl.groups[g + ng].n_sub;
+        ++ng;
+      }
+      SOS_CHECK_ARG(n_jobs < kMaxJobs, "sos_conv2d_wgrad: too many jobs");
+      p.job_coblk[n_jobs] = (int16_t)cb;
+      p.job_g0[n_jobs] = (int16_t)g;
+      p.job_ng[n_jobs] = (int16_t)ng;
+      max_ng = std::max(max_ng, ng);
+      ++n_jobs;
+      g += ng;
+    }
+  }
+  p.n_jobs = n_jobs;
+
+  // ---- tensor maps, dim order (channel, fast, slow/g, phase(g), image)
+  const bool fw = pl.fast_is_w;
+  const int g = pl.g;
+  {
+    const uint64_t pix = (uint64_t)Cin * 4;
+    const uint64_t in_fast = fw ? a.W : a.H, in_slow = fw ? a.H : a.W;
+    const uint64_t s_fast = fw ? pix : pix * a.W, s_slow = fw ? pix * a.W : pix;
+    uint64_t dims[5] = {(uint64_t)Cin, in_fast, in_slow / g, (uint64_t)g, (uint64_t)a.N};
+    uint64_t str[5] = {4, s_fast, s_slow * g, s_slow, pix * a.H * a.W};
+    uint32_t box[5] = {(uint32_t)p.cbi, (uint32_t)(8 * a.stride), (uint32_t)((SB + pl.halo) * a.stride), 1, 1};
+    uint32_t es[5] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1, 1};
+    SOS_CHECK_ARG(box[2] <= 256, "sos_conv2d_wgrad: activation box too large");
+    const int cb = p.cbi * 4;
+    const CUtensorMapSwizzle sw = cb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (cb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    if (int e = encode_map(&p.mapX, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, a.x, dims, str, box, es, sw, "wgrad activations")) return e;
+  }
+  const int out_fast = fw ? (int)a.OW : (int)a.OH, out_slow = fw ? (int)a.OH : (int)a.OW;
+  {
+    const uint64_t pix = (uint64_t)a.Cdy * 4;
+    const uint64_t s_fast = fw ? pix : pix * a.OW, s_slow = fw ? pix * a.OW : pix;
+    uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)out_fast, (uint64_t)(out_slow / g), (uint64_t)g, (uint64_t)a.N};
+    uint64_t str[5] = {4, s_fast, s_slow * g, s_slow, pix * a.OH * a.OW};
+    uint32_t box[5] = {(uint32_t)p.cbo, 8, (uint32_t)SB, 1, 1};
+    uint32_t es[5] = {1, 1, 1, 1, 1};
+    const int cb = p.cbo * 4;
+    const CUtensorMapSwizzle sw = cb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (cb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    if (int e = encode_map(&p.mapDY, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, a.dy + a.dy_coff, dims, str, box, es, sw, "wgrad output grads"))
+      return e;
+  }
+  p.tiles_fast = ceil_div(out_fast, 8);
+  p.tiles_slow = ceil_div(out_slow / g, SB);
+  p.n_phase = g;
+  const long long total = (long long)a.N * g * p.tiles_slow * p.tiles_fast;
+  SOS_CHECK_ARG(total < (1ll << 30), "sos_conv2d_wgrad: too many tiles");
+  p.total_tiles = (int)total;
+  const int sms = sos_num_sms();
+  p.n_slices = std::max(1, std::min((int)total, sms / std::max(1, n_jobs)));
+  p.tiles_per_slice = ceil_div((int)total, p.n_slices);
+  p.n_slices = ceil_div((int)total, p.tiles_per_slice);
+
+  const int smem = 2048 + p.n_stages * p.stage_bytes + tail;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess) {
+      sos_set_error("sos_conv2d_wgrad: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+      return SOS_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const int grid = std::min(p.n_jobs * p.n_slices, sms);
+  wgrad_tf32_kernel<<<grid, kThreadsWg, smem, stream>>>(p);
+  SOS_CHECK_LAUNCH("sos_conv2d_wgrad");
+  if (a.plan_out) {
+    a.plan_out[0] = pl.fast_is_w;
+    a.plan_out[1] = pl.share;
+    a.plan_out[2] = pl.g;
+    a.plan_out[3] = SB;
+    a.plan_out[4] = n_jobs;
+    a.plan_out[5] = p.n_stages;
+    a.plan_out[6] = p.stage_bytes;
+    a.plan_out[7] = p.n_slices;
+  }
+  return SOS_OK;
+}

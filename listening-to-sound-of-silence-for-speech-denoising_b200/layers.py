@@ -1,0 +1,357 @@
+"""Autograd building blocks over the sm_100a kernels (NHWC fp32 activations).
+
+Each Function's forward and backward enqueue kernels of libsos_b200.so through `ops`; PyTorch autograd only
+records the graph.  Reference semantics:
+  TapConv       nn.Conv2d / nn.ConvTranspose2d (bias=False) of M1/networks.py:36, M2/networks.py:36,105-106,130-131
+  BNAct         nn.BatchNorm2d + ReLU / PReLU   of the same blocks
+  PadCat        torch.cat + F.interpolate(nearest) + nn.ReflectionPad2d (M2/networks.py:104,129,198-204)
+  FeatToSeq     view/interpolate/permute before the LSTMs (M1/networks.py:131-135, M2/networks.py:83-86)
+  BiLSTM        nn.LSTM(bidirectional=True) (M1/networks.py:95, M2/networks.py:64)
+"""
+import torch
+
+from . import ops
+
+
+def _round8(c):
+    return (c + 7) // 8 * 8
+
+
+# ----------------------------------------------------------------------------------------------- geometry
+class ConvGeom:
+    """Tap lists of one convolution in the three roles (forward, data gradient, weight gradient)."""
+
+    def __init__(self, kind, kh, kw, dh=1, dw=1, stride=1):
+        assert kind in ("zero", "valid", "convT")
+        self.kind, self.kh, self.kw, self.dh, self.dw, self.stride = kind, kh, kw, dh, dw, stride
+        if kind == "convT":
+            assert (kh, kw, stride) == (3, 3, 2)
+        taps = [(a, b) for a in range(kh) for b in range(kw)]
+        self.taps = taps
+        if kind == "zero":
+            self.off = [((a - (kh - 1) // 2) * dh, (b - (kw - 1) // 2) * dw) for a, b in taps]
+        elif kind == "valid":
+            self.off = [(a * dh, b * dw) for a, b in taps]
+        else:
+            self.off = [(a - 1, b - 1) for a, b in taps]        # offsets of dy relative to 2*iy (used by dgrad / wgrad)
+
+    def out_size(self, H, W):
+        if self.kind == "zero":
+            return H, W
+        if self.kind == "valid":
+            return (H - (self.kh - 1) * self.dh - 1) // self.stride + 1, (W - (self.kw - 1) * self.dw - 1) // self.stride + 1
+        return 2 * H, 2 * W
+
+
+def _pack_fwd(w, taps, cin_p):
+    """(Cout, Cin, kh, kw) -> (Cout, len(taps)*cin_p), k = t*cin_p + ci."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    sel = torch.stack([w[:, :, a, b] for a, b in taps], dim=1)            # (Cout, ntaps, Cin)
+    if cin_p != Cin:
+        sel = torch.nn.functional.pad(sel, (0, cin_p - Cin))
+    return sel.reshape(Cout, len(taps) * cin_p).contiguous()
+
+
+def _conv_forward(x, w, g, epi=None):
+    """x NHWC (N,H,W,Cin_p); w PyTorch layout.  Returns y NHWC (N,OH,OW,round8(Cout))."""
+    N, H, W, cin_p = x.shape
+    OH, OW = g.out_size(H, W)
+    kw = dict(epi_scale=epi[0], epi_shift=epi[1], act=epi[2], slope=epi[3]) if epi else {}
+    if g.kind != "convT":
+        Cout = w.shape[0]
+        wk = _pack_fwd(w, g.taps, cin_p)
+        return ops.conv_tc(x, wk, [o[0] for o in g.off], [o[1] for o in g.off], Cout, OH, OW, g.stride, **kw)
+    # ConvTranspose2d(k3, s2, p1, output_padding=1): oy = 2*iy - 1 + ky  ->  four sub-pixel convolutions
+    Cout = w.shape[1]
+    wc = w.permute(1, 0, 2, 3)                                             # (Cout, Cin, ky, kx)
+    Cy = _round8(Cout)
+    y = (torch.zeros if Cy != Cout else torch.empty)(N, OH, OW, Cy, device=x.device, dtype=torch.float32)
+    ph_taps = {0: [(1, 0)], 1: [(0, 1), (2, 0)]}                          # phase -> [(k, input offset)]
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = [(ky, kx) for ky, _ in ph_taps[py] for kx, _ in ph_taps[px]]
+            offs = [(oy, ox) for _, oy in ph_taps[py] for _, ox in ph_taps[px]]
+            wk = _pack_fwd(wc, taps, cin_p)
+            ops.conv_tc(x, wk, [o[0] for o in offs], [o[1] for o in offs], Cout, H, W, 1, y=y, lattice=(2, 2, py, px), **kw)
+    return y
+
+
+def _conv_dgrad(dy, w, g, x_shape):
+    """Gradient w.r.t. the (possibly reflect-padded) NHWC input buffer."""
+    N, H, W, cin_p = x_shape
+    cout_p = dy.shape[3]
+    if g.kind == "convT":
+        # dx[iy] = sum_k dy[2*iy - 1 + ky] w[ci][co][ky]: a stride-2 tap conv over dy
+        Cin = w.shape[0]
+        wk = _pack_fwd(w, g.taps, cout_p)                                  # rows ci, k = t*cout_p + co
+        return ops.conv_tc(dy, wk, [o[0] for o in g.off], [o[1] for o in g.off], Cin, H, W, 2)
+    Cin = w.shape[1]
+    wt = w.permute(1, 0, 2, 3)                                             # (Cin, Cout, kh, kw)
+    if g.stride == 1:
+        wk = _pack_fwd(wt, g.taps, cout_p)
+        return ops.conv_tc(dy, wk, [-o[0] for o in g.off], [-o[1] for o in g.off], Cin, H, W, 1)
+    # stride 2: four output phases of the input lattice
+    dx = torch.empty(N, H, W, _round8(Cin), device=dy.device, dtype=torch.float32)
+    assert _round8(Cin) == Cin
+    for py in (0, 1):
+        for px in (0, 1):
+            sel = [(t, o) for t, o in zip(g.taps, g.off) if (py - o[0]) % 2 == 0 and (px - o[1]) % 2 == 0]
+            oh, ow = (H - py + 1) // 2, (W - px + 1) // 2
+            if not sel:
+                dx[:, py::2, px::2].zero_()
+                continue
+            wk = _pack_fwd(wt, [t for t, _ in sel], cout_p)
+            ops.conv_tc(dy, wk, [(py - o[0]) // 2 for _, o in sel], [(px - o[1]) // 2 for _, o in sel], Cin, oh, ow, 1, y=dx,
+                        lattice=(2, 2, py, px))
+    return dx
+
+
+def _conv_wgrad(x, dy, w, g):
+    """Returns the gradient in w's own layout."""
+    if g.kind == "convT":
+        Cin, Cout = w.shape[0], w.shape[1]
+        # roles swapped: "input" = dy (2H x 2W), "output grad" = x (H x W), stride 2
+        dwt = ops.conv_wgrad(dy, x, [o[0] for o in g.off], [o[1] for o in g.off], x.shape[3], x.shape[1], x.shape[2], 2)
+        # dwt (ntaps, Cin_p, Cout_p) -> (Cin, Cout, kh, kw)
+        return dwt[:, :Cin, :Cout].permute(1, 2, 0).reshape(Cin, Cout, g.kh, g.kw).contiguous()
+    Cout, Cin = w.shape[0], w.shape[1]
+    OH, OW = dy.shape[1], dy.shape[2]
+    dwt = ops.conv_wgrad(x, dy, [o[0] for o in g.off], [o[1] for o in g.off], dy.shape[3], OH, OW, g.stride)
+    return dwt[:, :Cout, :Cin].permute(1, 2, 0).reshape(Cout, Cin, g.kh, g.kw).contiguous()
+
+
+class TapConv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, g):
+        ctx.g = g
+        ctx.save_for_backward(x, w)
+        return _conv_forward(x, w, g)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        g = ctx.g
+        dy = dy.contiguous()
+        dx = _conv_dgrad(dy, w, g, x.shape) if ctx.needs_input_grad[0] else None
+        dw = _conv_wgrad(x, dy, w, g) if ctx.needs_input_grad[1] else None
+        return dx, dw, None
+
+
+def conv_fused_eval(x, w, g, scale, shift, act, slope):
+    """Inference path: BN (running stats) + activation folded into the GEMM epilogue."""
+    return _conv_forward(x, w, g, epi=(scale, shift, act, slope))
+
+
+# ----------------------------------------------------------------------------------------------- BatchNorm + act
+class BNActTrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, gamma, beta, slope, running_mean, running_var, eps, momentum, act):
+        z, stats = ops.bn_train_forward(y, gamma, beta, running_mean, running_var, eps, momentum, act, slope)
+        ctx.act = act
+        ctx.save_for_backward(y, stats, slope if slope is not None else torch.empty(0))
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        y, stats, slope = ctx.saved_tensors
+        slope = slope if slope.numel() else None
+        dy, dgamma, dbeta, dslope = ops.bn_train_backward(dz.contiguous(), y, stats, ctx.act, slope)
+        return dy, dgamma, dbeta, dslope, None, None, None, None, None
+
+
+def bn_act(y, bn, act, slope, training):
+    """y NHWC with C = round8(bn.num_features).  bn: nn.BatchNorm2d holding the reference-named parameters."""
+    Cp, Cn = y.shape[3], bn.num_features
+    gamma, beta, rm, rv = bn.weight, bn.bias, bn.running_mean, bn.running_var
+    if Cp != Cn:                                                          # padded channels: gamma = beta = 0 -> z = 0
+        pad = (0, Cp - Cn)
+        gamma, beta = torch.nn.functional.pad(gamma, pad), torch.nn.functional.pad(beta, pad)
+        rm_p, rv_p = torch.nn.functional.pad(rm, pad), torch.nn.functional.pad(rv, pad, value=1.0)
+    else:
+        rm_p, rv_p = rm, rv
+    if training:
+        z = BNActTrain.apply(y, gamma, beta, slope, rm_p, rv_p, bn.eps, bn.momentum, act)
+        if Cp != Cn:
+            with torch.no_grad():
+                rm.copy_(rm_p[:Cn])
+                rv.copy_(rv_p[:Cn])
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+        return z
+    # eval with autograd: plain tensor expression (not a hot path; inference uses conv_fused_eval)
+    scale = gamma * torch.rsqrt(rv_p + bn.eps)
+    pre = y * scale + (beta - rm_p * scale)
+    if act == ops.ACT_RELU:
+        return torch.relu(pre)
+    if act == ops.ACT_PRELU:
+        return torch.where(pre > 0, pre, pre * slope)
+    return pre
+
+
+# ----------------------------------------------------------------------------------------------- pad + concat
+class PadCat(torch.autograd.Function):
+    """Reflect-padded concatenation of NHWC maps (nearest-resized to the first map's size when they differ)."""
+
+    @staticmethod
+    def forward(ctx, pad, H, W, *srcs):
+        N = srcs[0].shape[0]
+        Ct = sum(s.shape[3] for s in srcs)
+        buf = torch.empty(N, H + 2 * pad, W + 2 * pad, Ct, device=srcs[0].device, dtype=torch.float32)
+        coff = 0
+        meta = []
+        for s in srcs:
+            _, Hs, Ws, Cs = s.shape
+            ops.copy_view(s, ops.view8(Hs, Ws, ld=Cs), buf, ops.view8(H, W, H + 2 * pad, W + 2 * pad, pad, pad, Ct, coff), N, Cs)
+            meta.append((Hs, Ws, Cs, coff))
+            coff += Cs
+        if pad:
+            ops.reflect_fill(buf, H, W, pad)
+        ctx.meta, ctx.pad, ctx.H, ctx.W, ctx.N, ctx.Ct = meta, pad, H, W, N, Ct
+        return buf
+
+    @staticmethod
+    def backward(ctx, gbuf):
+        pad, H, W, N, Ct = ctx.pad, ctx.H, ctx.W, ctx.N, ctx.Ct
+        g = gbuf.contiguous()
+        if pad:
+            g = g.clone()
+            ops.reflect_fold(g, H, W, pad)
+        grads = []
+        for i, (Hs, Ws, Cs, coff) in enumerate(ctx.meta):
+            if not ctx.needs_input_grad[3 + i]:
+                grads.append(None)
+                continue
+            dv = ops.view8(H, W, H + 2 * pad, W + 2 * pad, pad, pad, Ct, coff)
+            if (Hs, Ws) == (H, W):
+                gs = torch.empty(N, Hs, Ws, Cs, device=g.device, dtype=torch.float32)
+                ops.copy_view(g, dv, gs, ops.view8(Hs, Ws, ld=Cs), N, Cs)
+            else:
+                gs = torch.zeros(N, Hs, Ws, Cs, device=g.device, dtype=torch.float32)
+                ops.copy_view_backward(g, dv, gs, ops.view8(Hs, Ws, ld=Cs), N, Cs)
+            grads.append(gs)
+        return (None, None, None, *grads)
+
+
+# ----------------------------------------------------------------------------------------------- layout changes
+class ToNCHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, channels):
+        ctx.cp = x.shape[3]
+        return ops.nhwc_to_nchw(x, channels)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.nchw_to_nhwc(g.contiguous(), ctx.cp), None
+
+
+class FeatToSeq(torch.autograd.Function):
+    """Encoder outputs (B,F,T,C_i) NHWC -> LSTM input (V, B, sum C_i*F), feature = c*F + f (per source, concatenated)."""
+
+    @staticmethod
+    def forward(ctx, V, real_channels, *srcs):
+        B, F, T, _ = srcs[0].shape
+        ld = sum(c * F for c in real_channels)
+        out = torch.empty(V, B, ld, device=srcs[0].device, dtype=torch.float32)
+        coff = 0
+        ctx.meta = []
+        for s, c in zip(srcs, real_channels):
+            # only the first c channels are real: view the padded NHWC map as C = Cp and let the kernel skip the rest
+            sc = s if s.shape[3] == c else s[..., :c].contiguous()
+            ops.feat_to_seq(sc, out, V, coff)
+            ctx.meta.append((tuple(s.shape), c, coff))
+            coff += c * F
+        ctx.V = V
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        gout = gout.contiguous()
+        grads = []
+        for shape, c, coff in ctx.meta:
+            B, F, T, Cp = shape
+            g = ops.feat_to_seq_backward(gout, (B, F, T, c), ctx.V, coff)
+            if Cp != c:
+                g = torch.nn.functional.pad(g, (0, Cp - c))
+            grads.append(g)
+        return (None, None, *grads)
+
+
+# ----------------------------------------------------------------------------------------------- LSTM
+class BiLSTMFn(torch.autograd.Function):
+    """Single-layer bidirectional LSTM.  Input projection / weight gradients are plain library GEMMs
+    (torch.matmul -> cuBLAS); the recurrence runs in the sos_lstm_* kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        T, B, I = x.shape
+        H = w_hh.shape[1]
+        W = torch.cat([w_ih, w_ih_r], dim=0)                                # (8H, I)
+        bias = torch.cat([b_ih + b_hh, b_ih_r + b_hh_r])
+        gx = torch.addmm(bias, x.reshape(T * B, I), W.t()).view(T, B, 2, 4 * H)
+        whh = torch.stack([w_hh, w_hh_r]).contiguous()
+        out, gates, cell = ops.lstm_forward(gx, whh)
+        ctx.save_for_backward(x, W, whh, out, gates, cell)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, W, whh, out, gates, cell = ctx.saved_tensors
+        T, B, I = x.shape
+        H = whh.shape[2]
+        dgx = ops.lstm_backward(dout.contiguous(), whh, out, gates, cell)   # (T,B,2,4H)
+        flat = dgx.view(T * B, 8 * H)
+        dx = (flat @ W).view(T, B, I) if ctx.needs_input_grad[0] else None
+        dW = flat.t() @ x.reshape(T * B, I)                                 # (8H, I)
+        db = flat.sum(0)
+        hprev_f = torch.zeros(T, B, H, device=x.device, dtype=torch.float32)
+        hprev_f[1:] = out[:-1, :, :H]
+        hprev_r = torch.zeros(T, B, H, device=x.device, dtype=torch.float32)
+        hprev_r[:-1] = out[1:, :, H:]
+        dwhh_f = dgx[:, :, 0].reshape(T * B, 4 * H).t() @ hprev_f.view(T * B, H)
+        dwhh_r = dgx[:, :, 1].reshape(T * B, 4 * H).t() @ hprev_r.view(T * B, H)
+        return (dx, dW[:4 * H], dwhh_f, db[:4 * H], db[:4 * H], dW[4 * H:], dwhh_r, db[4 * H:], db[4 * H:])
+
+
+# ----------------------------------------------------------------------------------------------- cRM + losses
+class ICRM(torch.autograd.Function):
+    """batch_fast_icRM_sigmoid (M2/transform.py:156-169); gradient flows to the mask only."""
+
+    @staticmethod
+    def forward(ctx, Y, crm, a, b):
+        Y, crm = Y.contiguous(), crm.contiguous()
+        ctx.a = a
+        ctx.save_for_backward(Y, crm)
+        return ops.icrm_forward(Y, crm, a, b)
+
+    @staticmethod
+    def backward(ctx, grec):
+        Y, crm = ctx.saved_tensors
+        return None, ops.icrm_backward(Y, crm, grec.contiguous(), ctx.a), None, None
+
+
+class MSELoss(torch.autograd.Function):
+    """nn.MSELoss() (mean); loss and gradient come out of one pass."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        loss, grad = ops.mse_fwd_bwd(pred.contiguous(), target.contiguous(), ctx.needs_input_grad[0])
+        ctx.save_for_backward(grad if grad is not None else torch.empty(0))
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None
+
+
+class BCEWithLogitsLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        loss, grad = ops.bce_fwd_bwd(logits.contiguous(), labels.contiguous(), ctx.needs_input_grad[0])
+        ctx.save_for_backward(grad if grad is not None else torch.empty(0))
+        return loss.squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None

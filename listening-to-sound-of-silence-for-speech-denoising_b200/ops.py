@@ -1,0 +1,325 @@
+"""Thin tensor-level wrappers over the C ABI (include/sos_b200.h).
+
+Every function takes CUDA fp32 tensors, enqueues kernels of libsos_b200.so on PyTorch's current stream and
+returns tensors.  PyTorch is used for device memory and streams only; there is no fallback path.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvArgs, WgradArgs, check, lib
+
+_I32 = C.c_int32
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype in (torch.float32, torch.uint8, torch.int32), (t.device, t.dtype)
+    assert t.is_contiguous(), "sos_b200 ops need contiguous tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def _count(n=1):
+    _lib.launch_count += n
+
+
+def init():
+    if not torch.cuda.is_available():
+        raise _lib.SosError("sos_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    check(lib().sos_init(), "sos_init")
+
+
+def view8(H, W, Hp=None, Wp=None, ph=0, pw=0, ld=0, coff=0):
+    Hp = H if Hp is None else Hp
+    Wp = W if Wp is None else Wp
+    return (_I32 * 8)(H, W, Hp, Wp, ph, pw, ld, coff)
+
+
+# ----------------------------------------------------------------------------------------------- transforms
+def frame_lo_table(n_bits, ratio):
+    """int(i * ratio) for i = 0..n_bits, with the reference's own float arithmetic (M2/tools.py:347-349)."""
+    return [int(i * ratio) for i in range(n_bits + 1)]
+
+
+def stft(wave, bits=None, ratio=None, gate_mode=0):
+    """wave (B, L) -> (B, 2, 256, T).  bits (B, n_bits) uint8 (0 = silent) gates the waveform first."""
+    B, L = wave.shape
+    T = 1 + L // 158
+    out = torch.empty(B, 2, 256, T, device=wave.device, dtype=torch.float32)
+    if gate_mode:
+        nb = bits.shape[1]
+        flo = torch.tensor(frame_lo_table(nb, ratio), dtype=torch.int32, device=wave.device)
+        check(lib().sos_stft_forward(_p(wave), B, L, _p(out), _p(bits), nb, _p(flo), float(ratio), gate_mode, _stream()), "sos_stft_forward")
+    else:
+        check(lib().sos_stft_forward(_p(wave), B, L, _p(out), None, 0, None, 0.0, 0, _stream()), "sos_stft_forward")
+    _count()
+    return out
+
+
+def istft(spec, crm=None):
+    """spec (B, 2, 256, T) -> (B, 158 (T-1)); with crm the complex-ratio-mask recovery is fused in."""
+    B, _, F, T = spec.shape
+    assert F == 256
+    ws = torch.empty(B * T * 400, device=spec.device, dtype=torch.float32)
+    out = torch.empty(B, 158 * (T - 1), device=spec.device, dtype=torch.float32)
+    check(lib().sos_istft_forward(_p(spec), _p(crm), B, T, _p(ws), _p(out), _stream()), "sos_istft_forward")
+    _count(2)
+    return out
+
+
+def gate_wave(wave, bits, ratio, mode=1, want_mask=False):
+    B, L = wave.shape
+    nb = bits.shape[1]
+    flo = torch.tensor(frame_lo_table(nb, ratio), dtype=torch.int32, device=wave.device)
+    out = torch.empty_like(wave)
+    mask = torch.empty_like(wave) if want_mask else None
+    check(lib().sos_gate_wave(_p(wave), B, L, _p(bits), nb, _p(flo), float(ratio), mode, _p(out), _p(mask), _stream()), "sos_gate_wave")
+    _count()
+    return (out, mask) if want_mask else out
+
+
+def icrm_forward(Y, crm, a=0.1, b=0.0):
+    B = Y.shape[0]
+    plane = Y[0, 0].numel()
+    rec = torch.empty_like(Y)
+    check(lib().sos_icrm_forward(_p(Y), _p(crm), _p(rec), B, plane, a, b, _stream()), "sos_icrm_forward")
+    _count()
+    return rec
+
+
+def icrm_backward(Y, crm, grad_rec, a=0.1):
+    B = Y.shape[0]
+    plane = Y[0, 0].numel()
+    g = torch.empty_like(crm)
+    check(lib().sos_icrm_backward(_p(Y), _p(crm), _p(grad_rec), _p(g), B, plane, a, _stream()), "sos_icrm_backward")
+    _count()
+    return g
+
+
+# ----------------------------------------------------------------------------------------------- losses / optimiser
+def mse_fwd_bwd(pred, target, want_grad, grad_scale=1.0):
+    n = pred.numel()
+    loss = torch.zeros(1, device=pred.device, dtype=torch.float32)
+    grad = torch.empty_like(pred) if want_grad else None
+    check(lib().sos_mse_fwd_bwd(_p(pred), _p(target), n, _p(loss), _p(grad), 2.0 * grad_scale / n, _stream()), "sos_mse_fwd_bwd")
+    _count()
+    return loss / n, grad
+
+
+def bce_fwd_bwd(logits, labels, want_grad, grad_scale=1.0):
+    n = logits.numel()
+    loss = torch.zeros(1, device=logits.device, dtype=torch.float32)
+    grad = torch.empty_like(logits) if want_grad else None
+    check(lib().sos_bce_logits_fwd_bwd(_p(logits), _p(labels), n, _p(loss), _p(grad), grad_scale / n, _stream()), "sos_bce_logits_fwd_bwd")
+    _count()
+    return loss / n, grad
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    check(lib().sos_adam_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), lr, beta1, beta2, eps, step, grad_scale,
+                              _stream()), "sos_adam_step")
+    _count()
+
+
+# ----------------------------------------------------------------------------------------------- BatchNorm + activation
+ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
+
+
+def bn_train_forward(y, gamma, beta, running_mean, running_var, eps, momentum, act, slope):
+    """y (..., C) dense NHWC rows.  Returns z and the tensors backward needs; updates running stats in place."""
+    Cn = y.shape[-1]
+    rows = y.numel() // Cn
+    G = lib().sos_bn_partial_blocks(rows, Cn)
+    if G <= 0:
+        raise _lib.SosError(f"BatchNorm over {Cn} channels is not supported (need a multiple of 4, <= 1024)")
+    partial = torch.empty(G * 3 * Cn, device=y.device, dtype=torch.float32)
+    stats = torch.empty(4, Cn, device=y.device, dtype=torch.float32)          # mean, invstd, scale, shift
+    check(lib().sos_bn_stats(_p(y), rows, Cn, _p(partial), _stream()), "sos_bn_stats")
+    check(lib().sos_bn_finalize(_p(partial), rows, Cn, _p(gamma), _p(beta), eps, momentum, _p(running_mean), _p(running_var),
+                                C.c_void_p(stats[0].data_ptr()), C.c_void_p(stats[1].data_ptr()), C.c_void_p(stats[2].data_ptr()),
+                                C.c_void_p(stats[3].data_ptr()), _stream()), "sos_bn_finalize")
+    z = torch.empty_like(y)
+    H, W = y.shape[-3], y.shape[-2]
+    check(lib().sos_bn_act(_p(y), _p(z), view8(H, W, ld=Cn), rows, Cn, C.c_void_p(stats[2].data_ptr()), C.c_void_p(stats[3].data_ptr()),
+                           act, _p(slope), _stream()), "sos_bn_act")
+    _count(3)
+    return z, stats
+
+
+def bn_train_backward(dz, y, stats, act, slope):
+    Cn = y.shape[-1]
+    rows = y.numel() // Cn
+    G = lib().sos_bn_partial_blocks(rows, Cn)
+    partial = torch.empty(G * 3 * Cn, device=y.device, dtype=torch.float32)
+    dy = torch.empty_like(y)
+    out = torch.empty(4, Cn, device=y.device, dtype=torch.float32)             # dgamma, dbeta, m1, m2
+    dslope = torch.zeros(1, device=y.device, dtype=torch.float32) if act == ACT_PRELU else None
+    H, W = y.shape[-3], y.shape[-2]
+    sp = lambda i: C.c_void_p(stats[i].data_ptr())
+    op = lambda i: C.c_void_p(out[i].data_ptr())
+    check(lib().sos_bn_act_backward(_p(dz), view8(H, W, ld=Cn), _p(y), _p(dy), rows, Cn, sp(2), sp(3), sp(0), sp(1), act, _p(slope),
+                                    _p(partial), op(0), op(1), _p(dslope), op(2), op(3), _stream()), "sos_bn_act_backward")
+    _count(3)
+    return dy, out[0], out[1], dslope
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps):
+    Cn = gamma.numel()
+    coeffs = torch.empty(2, Cn, device=gamma.device, dtype=torch.float32)
+    check(lib().sos_bn_eval_coeffs(Cn, _p(gamma), _p(beta), _p(running_mean), _p(running_var), eps, C.c_void_p(coeffs[0].data_ptr()),
+                                   C.c_void_p(coeffs[1].data_ptr()), _stream()), "sos_bn_eval_coeffs")
+    _count()
+    return coeffs[0], coeffs[1]
+
+
+# ----------------------------------------------------------------------------------------------- layout
+def nchw_to_nhwc(x, channels_padded):
+    """(B, C, H, W) -> dense (B, H, W, Cp) with zero padded channels."""
+    B, Cc, H, W = x.shape
+    out = torch.empty(B, H, W, channels_padded, device=x.device, dtype=torch.float32)
+    check(lib().sos_nchw_to_nhwc(_p(x), B, Cc, _p(out), view8(H, W, ld=channels_padded), channels_padded, _stream()), "sos_nchw_to_nhwc")
+    _count()
+    return out
+
+
+def nhwc_to_nchw(x, channels):
+    B, H, W, Cp = x.shape
+    out = torch.empty(B, channels, H, W, device=x.device, dtype=torch.float32)
+    check(lib().sos_nhwc_to_nchw(_p(x), view8(H, W, ld=Cp), B, channels, _p(out), _stream()), "sos_nhwc_to_nchw")
+    _count()
+    return out
+
+
+def copy_view(src, sview, dst, dview, batch, channels, accumulate=False):
+    check(lib().sos_copy_view(_p(src), sview, _p(dst), dview, batch, channels, int(accumulate), _stream()), "sos_copy_view")
+    _count()
+
+
+def copy_view_backward(gdst, dview, gsrc, sview, batch, channels):
+    check(lib().sos_copy_view_backward(_p(gdst), dview, _p(gsrc), sview, batch, channels, _stream()), "sos_copy_view_backward")
+    _count()
+
+
+def reflect_fill(buf, H, W, pad):
+    B, Hp, Wp, Cn = buf.shape
+    assert Hp == H + 2 * pad and Wp == W + 2 * pad
+    check(lib().sos_reflect_fill(_p(buf), B, H, W, pad, Cn, _stream()), "sos_reflect_fill")
+    _count()
+
+
+def reflect_fold(gbuf, H, W, pad):
+    B, Hp, Wp, Cn = gbuf.shape
+    check(lib().sos_reflect_fold(_p(gbuf), B, H, W, pad, Cn, _stream()), "sos_reflect_fold")
+    _count()
+
+
+def feat_to_seq(x, out, V, coff):
+    """x NHWC (B, F, T, C) -> out (V, B, ld)[:, :, coff + c*F + f] with nearest resample T -> V."""
+    B, F, T, Cn = x.shape
+    check(lib().sos_feat_to_seq(_p(x), B, F, T, Cn, _p(out), V, out.shape[2], coff, _stream()), "sos_feat_to_seq")
+    _count()
+
+
+def feat_to_seq_backward(gout, shape, V, coff):
+    B, F, T, Cn = shape
+    gin = torch.zeros(shape, device=gout.device, dtype=torch.float32)
+    check(lib().sos_feat_to_seq_backward(_p(gout), B, F, T, Cn, _p(gin), V, gout.shape[2], coff, _stream()), "sos_feat_to_seq_backward")
+    _count()
+    return gin
+
+
+# ----------------------------------------------------------------------------------------------- tensor-core tap GEMM
+def _i32arr(v):
+    return (_I32 * len(v))(*[int(a) for a in v])
+
+
+def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lattice=(1, 1, 0, 0), epi_scale=None, epi_shift=None,
+            act=0, slope=None, force_plan=-1, plan_out=None):
+    """Tap-list implicit GEMM on tcgen05 (see include/sos_b200.h: sos_conv2d_tc).
+
+    x (N, H, W, Cin) NHWC; wk (Cout, ntaps*Cin); y (N, YH, YW, Cy) is allocated when None (dense, Cy = Cout
+    rounded up to 8, zero filled if padded)."""
+    N, H, W, Cin = x.shape
+    ntaps = len(tap_dh)
+    assert wk.shape == (Cout, ntaps * Cin), (wk.shape, Cout, ntaps, Cin)
+    if y is None:
+        Cy = (Cout + 7) // 8 * 8
+        osh, osw, _, _ = lattice
+        alloc = torch.zeros if (Cy != Cout) else torch.empty
+        y = alloc(N, OH * osh, OW * osw, Cy, device=x.device, dtype=torch.float32)
+    a = ConvArgs()
+    a.x, a.wk, a.y = x.data_ptr(), wk.data_ptr(), y.data_ptr()
+    dh, dw = _i32arr(tap_dh), _i32arr(tap_dw)
+    a.tap_dh, a.tap_dw = dh, dw
+    a.N, a.H, a.W, a.Cin = N, H, W, Cin
+    a.Cout, a.OH, a.OW = Cout, OH, OW
+    a.ntaps, a.stride = ntaps, stride
+    a.YH, a.YW, a.Cy, a.y_coff = y.shape[1], y.shape[2], y.shape[3], y_coff
+    a.osh, a.osw, a.oph, a.opw = lattice
+    a.epi_scale = epi_scale.data_ptr() if epi_scale is not None else None
+    a.epi_shift = epi_shift.data_ptr() if epi_shift is not None else None
+    a.act = act
+    a.slope = slope.data_ptr() if slope is not None else None
+    a.force_plan = force_plan
+    po = (_I32 * 8)() if plan_out is not None else None
+    a.plan_out = po
+    assert x.is_contiguous() and wk.is_contiguous() and y.is_contiguous()
+    check(lib().sos_conv2d_tc(C.byref(a), _stream()), "sos_conv2d_tc")
+    _count()
+    if plan_out is not None:
+        plan_out[:] = list(po)
+    return y
+
+
+def conv_wgrad(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_plan=-1, plan_out=None):
+    """dw[t][co][ci] = sum_pixels dy[p][dy_coff+co] * x[p*stride + off_t][ci]  ->  (ntaps, Cout, Cin)."""
+    N, H, W, Cin = x.shape
+    ntaps = len(tap_dh)
+    assert dy.shape[0] == N and dy.shape[1] == OH and dy.shape[2] == OW, (dy.shape, N, OH, OW)
+    dw = torch.zeros(ntaps, Cout, Cin, device=x.device, dtype=torch.float32)
+    a = WgradArgs()
+    a.x, a.dy, a.dw = x.data_ptr(), dy.data_ptr(), dw.data_ptr()
+    dh, dwv = _i32arr(tap_dh), _i32arr(tap_dw)
+    a.tap_dh, a.tap_dw = dh, dwv
+    a.N, a.H, a.W, a.Cin = N, H, W, Cin
+    a.Cout, a.OH, a.OW, a.Cdy, a.dy_coff = Cout, OH, OW, dy.shape[3], dy_coff
+    a.ntaps, a.stride = ntaps, stride
+    a.force_plan = force_plan
+    po = (_I32 * 8)() if plan_out is not None else None
+    a.plan_out = po
+    assert x.is_contiguous() and dy.is_contiguous()
+    check(lib().sos_conv2d_wgrad(C.byref(a), _stream()), "sos_conv2d_wgrad")
+    _count()
+    if plan_out is not None:
+        plan_out[:] = list(po)
+    return dw
+
+
+# ----------------------------------------------------------------------------------------------- LSTM recurrence
+def lstm_forward(gx, w_hh):
+    """gx (T, B, 2, 4H), w_hh (2, 4H, H) -> out (T, B, 2H), gates (T, B, 2, 4H), cell (T, B, 2, H)."""
+    T, B, _, H4 = gx.shape
+    H = H4 // 4
+    out = torch.empty(T, B, 2 * H, device=gx.device, dtype=torch.float32)
+    gates = torch.empty_like(gx)
+    cell = torch.empty(T, B, 2, H, device=gx.device, dtype=torch.float32)
+    check(lib().sos_lstm_forward(_p(gx), _p(w_hh), T, B, H, _p(out), _p(gates), _p(cell), _stream()), "sos_lstm_forward")
+    _count(T)
+    return out, gates, cell
+
+
+def lstm_backward(dout, w_hh, out, gates, cell):
+    T, B, _, H4 = gates.shape
+    H = H4 // 4
+    dgx = torch.empty_like(gates)
+    dc = torch.empty(B, 2, H, device=dout.device, dtype=torch.float32)
+    check(lib().sos_lstm_backward(_p(dout), _p(w_hh), _p(out), _p(gates), _p(cell), T, B, H, _p(dgx), None, _p(dc), _stream()),
+          "sos_lstm_backward")
+    _count(T)
+    return dgx

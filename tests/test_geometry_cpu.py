@@ -1,0 +1,57 @@
+"""Host-side geometry of the tap convolutions (no GPU): with the two tensor-core entry points replaced by a CPU
+emulation of their documented semantics, forward / data-gradient / weight-gradient of every convolution kind on the
+hot path must match PyTorch's own convolutions."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import sos_b200  # noqa: F401
+from sos_b200 import layers as L, ops
+from tests import _emul
+
+CASES = [
+    ("zero", 8, 16, (5, 5), (2, 2), 1, 2, 12, 11),
+    ("zero", 8, 8, (1, 7), (1, 1), 1, 1, 6, 13),
+    ("zero", 16, 4, (1, 1), (1, 1), 1, 1, 6, 7),
+    ("valid", 8, 16, (5, 5), (1, 1), 2, 2, 15, 12),
+    ("valid", 8, 16, (5, 5), (1, 1), 2, 1, 14, 13),
+    ("valid", 16, 8, (3, 3), (4, 4), 1, 1, 14, 13),
+    ("valid", 8, 2, (3, 3), (1, 1), 1, 1, 9, 8),
+    ("convT", 16, 8, (3, 3), (1, 1), 2, 2, 5, 7),
+]
+
+
+@pytest.fixture()
+def emulated(monkeypatch):
+    monkeypatch.setattr(ops, "conv_tc", _emul.conv_tc)
+    monkeypatch.setattr(ops, "conv_wgrad", _emul.conv_wgrad)
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-k{c[3][0]}x{c[3][1]}-d{c[4][0]}-s{c[5]}-{c[7]}x{c[8]}")
+def test_tap_geometry(emulated, case):
+    kind, Cin, Cout, k, d, stride, N, H, W = case
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N, Cin, H, W, generator=g, dtype=torch.float64).float().requires_grad_(True)
+    if kind == "convT":
+        w = torch.randn(Cin, Cout, 3, 3, generator=g).requires_grad_(True)
+        ref = F.conv_transpose2d(x, w, None, 2, 1, 1)
+    elif kind == "zero":
+        w = torch.randn(Cout, Cin, *k, generator=g).requires_grad_(True)
+        ref = F.conv2d(x, w, None, 1, ((k[0] - 1) // 2 * d[0], (k[1] - 1) // 2 * d[1]), d)
+    else:
+        w = torch.randn(Cout, Cin, *k, generator=g).requires_grad_(True)
+        ref = F.conv2d(x, w, None, stride, 0, d)
+    go = torch.randn(ref.shape, generator=g)
+    ref.backward(go)
+    geom = L.ConvGeom(kind, k[0], k[1], d[0], d[1], stride)
+    xh = x.detach().permute(0, 2, 3, 1).contiguous()
+    y = L._conv_forward(xh, w.detach(), geom)
+    assert y.shape[1:3] == ref.shape[2:]
+    assert torch.allclose(y[..., :Cout].permute(0, 3, 1, 2), ref.detach(), atol=1e-4)
+    assert float(y[..., Cout:].abs().max() if y.shape[3] > Cout else 0) == 0
+    cp = y.shape[3]
+    gy = F.pad(go.permute(0, 2, 3, 1), (0, cp - Cout)).contiguous()
+    dx = L._conv_dgrad(gy, w.detach(), geom, xh.shape)
+    assert torch.allclose(dx[..., :Cin].permute(0, 3, 1, 2), x.grad, atol=1e-4)
+    dw = L._conv_wgrad(xh, gy, w.detach(), geom)
+    assert torch.allclose(dw, w.grad, atol=1e-3)

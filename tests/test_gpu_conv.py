@@ -1,0 +1,126 @@
+"""GPU parity of the tcgen05 tap GEMM (forward / data gradient / weight gradient) against plain PyTorch fp32 convolutions
+on the CPU.  The kernels compute in TF32 (10-bit mantissa operands, fp32 accumulate): tolerance 4e-3 of the output scale."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 4e-3
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def _ref_conv(x, w, kind, k, d, stride):
+    """x NCHW cpu, returns NCHW."""
+    if kind == "zero":
+        pad = ((k[0] - 1) // 2 * d[0], (k[1] - 1) // 2 * d[1])
+        return F.conv2d(x, w, None, 1, pad, d)
+    if kind == "valid":
+        return F.conv2d(x, w, None, stride, 0, d)
+    return F.conv_transpose2d(x, w, None, 2, 1, 1)
+
+
+CASES = [
+    # kind, Cin, Cout, k, d, stride, N, H, W
+    ("zero", 32, 32, (1, 1), (1, 1), 1, 1, 16, 24),
+    ("zero", 48, 48, (5, 5), (1, 1), 1, 2, 32, 27),
+    ("zero", 96, 96, (5, 5), (2, 2), 1, 1, 32, 43),
+    ("zero", 96, 96, (5, 5), (8, 1), 1, 1, 64, 19),
+    ("zero", 48, 48, (5, 5), (16, 16), 1, 1, 64, 37),
+    ("zero", 2, 96, (1, 7), (1, 1), 1, 2, 16, 29),
+    ("zero", 96, 96, (7, 1), (1, 1), 1, 1, 32, 21),
+    ("zero", 96, 8, (1, 1), (1, 1), 1, 2, 16, 21),
+    ("zero", 48, 4, (1, 1), (1, 1), 1, 1, 16, 21),
+    ("valid", 2, 64, (5, 5), (1, 1), 1, 1, 36, 27),
+    ("valid", 64, 128, (5, 5), (1, 1), 2, 2, 36, 31),
+    ("valid", 128, 128, (5, 5), (1, 1), 1, 1, 20, 23),
+    ("valid", 256, 256, (3, 3), (1, 1), 2, 1, 34, 29),
+    ("valid", 256, 256, (3, 3), (4, 4), 1, 1, 24, 21),
+    ("valid", 64, 2, (3, 3), (1, 1), 1, 1, 18, 23),
+    ("convT", 256, 128, (3, 3), (1, 1), 2, 1, 16, 13),
+    ("convT", 128, 64, (3, 3), (1, 1), 2, 2, 8, 11),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-{c[1]}to{c[2]}-k{c[3][0]}x{c[3][1]}-d{c[4][0]}x{c[4][1]}-s{c[5]}")
+def test_tapconv_fwd_bwd(cuda, case):
+    from sos_b200 import layers as L, ops
+    kind, Cin, Cout, k, d, stride, N, H, W = case
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    if kind == "convT":
+        w = torch.randn(Cin, Cout, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    else:
+        w = torch.randn(Cout, Cin, k[0], k[1], generator=g) / (Cin * k[0] * k[1]) ** 0.5
+    x.requires_grad_(True)
+    w.requires_grad_(True)
+    y_ref = _ref_conv(x, w, kind, k, d, stride)
+    gy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(gy)
+
+    geom = L.ConvGeom(kind, k[0], k[1], d[0], d[1], stride)
+    cin_p = (Cin + 7) // 8 * 8
+    xd = ops.nchw_to_nhwc(x.detach().to(cuda), cin_p).requires_grad_(True)
+    wd = w.detach().to(cuda).requires_grad_(True)
+    y = L.TapConv.apply(xd, wd, geom)
+    torch.cuda.synchronize()
+    y_nchw = ops.nhwc_to_nchw(y, Cout).cpu()
+    assert y_nchw.shape == y_ref.shape
+    e_f = _rel(y_nchw, y_ref.detach())
+    gyd = ops.nchw_to_nhwc(gy.to(cuda), y.shape[3])
+    y.backward(gyd)
+    torch.cuda.synchronize()
+    e_w = _rel(wd.grad.cpu(), w.grad)
+    dx = ops.nhwc_to_nchw(xd.grad, Cin).cpu()
+    e_x = _rel(dx, x.grad)
+    print(f"\n{case}: fwd {e_f:.2e} dgrad {e_x:.2e} wgrad {e_w:.2e}")
+    assert e_f < TOL, f"forward rel err {e_f}"
+    assert e_x < TOL, f"dgrad rel err {e_x}"
+    assert e_w < TOL, f"wgrad rel err {e_w}"
+
+
+@pytest.mark.parametrize("plan", [0, 1, 2, 3])
+@pytest.mark.parametrize("d", [(1, 1), (4, 4), (2, 1)])
+def test_conv_forced_plans(cuda, plan, d):
+    """Every orientation / box-sharing plan of the forward kernel must give the same answer."""
+    from sos_b200 import layers as L, ops
+    Cin, Cout, N, H, W = 48, 48, 1, 32, 40
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 5, 5, generator=g) / (Cin * 25) ** 0.5
+    y_ref = F.conv2d(x, w, None, 1, (2 * d[0], 2 * d[1]), d)
+    geom = L.ConvGeom("zero", 5, 5, d[0], d[1], 1)
+    xd = ops.nchw_to_nhwc(x.to(cuda), Cin)
+    wk = L._pack_fwd(w.to(cuda), geom.taps, Cin)
+    info = [0] * 8
+    try:
+        y = ops.conv_tc(xd, wk, [o[0] for o in geom.off], [o[1] for o in geom.off], Cout, H, W, 1, force_plan=plan, plan_out=info)
+    except Exception as e:                              # a plan may be inapplicable (e.g. lattice does not divide the axis)
+        if "not applicable" in str(e):
+            pytest.skip(str(e))
+        raise
+    torch.cuda.synchronize()
+    e = _rel(ops.nhwc_to_nchw(y, Cout).cpu(), y_ref)
+    print(f"\nplan {plan} d {d}: info {info} err {e:.2e}")
+    assert e < TOL
+
+
+def test_conv_fused_epilogue(cuda):
+    from sos_b200 import layers as L, ops
+    Cin, Cout, N, H, W = 96, 96, 2, 32, 27
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 5, 5, generator=g) / (Cin * 25) ** 0.5
+    sc, sh = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g) * 0.1
+    slope = torch.tensor([0.25])
+    y_ref = F.conv2d(x, w, None, 1, 2, 1) * sc[None, :, None, None] + sh[None, :, None, None]
+    geom = L.ConvGeom("zero", 5, 5, 1, 1, 1)
+    xd = ops.nchw_to_nhwc(x.to(cuda), Cin)
+    for act, ref in ((1, torch.relu(y_ref)), (2, torch.where(y_ref > 0, y_ref, 0.25 * y_ref)), (0, y_ref)):
+        y = L.conv_fused_eval(xd, w.to(cuda), geom, sc.to(cuda), sh.to(cuda), act, slope.to(cuda))
+        torch.cuda.synchronize()
+        e = _rel(ops.nhwc_to_nchw(y, Cout).cpu(), ref)
+        assert e < TOL, (act, e)

@@ -1,0 +1,201 @@
+"""GPU parity of the HBM-bound kernels (STFT / iSTFT / gating / cRM / losses / Adam / BN / layout) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_stft_matches_oracle(cuda):
+    from sos_b200 import transform
+    from oracle import synth, transform as otf
+    for length in (8000, 28000, 32000):
+        clips = synth.make_batch(2, length=length)
+        got = transform.stft_batch(torch.tensor(clips["mixed"], device=cuda)).cpu().numpy()
+        want = otf.stft_batch(clips["mixed"])
+        assert got.shape == want.shape
+        err = np.abs(got - want).max()
+        assert err < 2e-4, (length, err)          # |S| up to ~50; fp32 dot products of 400 terms
+
+
+def test_stft_golden_fixture(cuda, golden_dir):
+    from sos_b200 import transform
+    z = np.load(golden_dir + "/transform.npz")
+    got = transform.fast_stft(z["mixed"])
+    assert got.shape == z["fast_stft_mixed"].shape
+    assert np.abs(got - z["fast_stft_mixed"]).max() < 2e-4
+    wav = transform.fast_istft(z["fast_stft_mixed"])
+    assert wav.shape == z["fast_istft_mixed"].shape
+    assert np.abs(wav - z["fast_istft_mixed"]).max() < 2e-5
+    rec = transform.fast_icRM_sigmoid(z["fast_stft_mixed"], z["fast_cRM_sigmoid"])
+    ref = z["fast_icRM_sigmoid"]
+    assert np.abs(rec - ref).max() < 1e-3 * max(1.0, np.abs(ref).max())
+
+
+def test_istft_roundtrip_and_fused_crm(cuda):
+    from sos_b200 import transform, ops
+    from oracle import synth, transform as otf
+    clips = synth.make_batch(3, length=32000)
+    wave = torch.tensor(clips["mixed"], device=cuda)
+    spec = transform.stft_batch(wave)
+    back = transform.istft_batch(spec).cpu().numpy()
+    assert back.shape == (3, 158 * (spec.shape[3] - 1))
+    assert np.abs(back - clips["mixed"][:, :back.shape[1]]).max() < 1e-4          # STFT -> iSTFT round trip
+    want = otf.istft_batch(spec.cpu().numpy())
+    assert np.abs(back - want).max() < 2e-5
+    crm = torch.rand(spec.shape, device=cuda) * 0.5 + 0.25
+    fused = transform.istft_batch(spec, crm)
+    unfused = transform.istft_batch(ops.icrm_forward(spec, crm))
+    assert float((fused - unfused).abs().max()) < 1e-4 * float(unfused.abs().max() + 1)
+
+
+def test_gating_bit_exact(cuda, golden_dir):
+    from sos_b200 import tools
+    z = np.load(golden_dir + "/tools.npz")
+    n = 0
+    for key in z.files:
+        if not key.startswith("mask:"):
+            continue
+        _, length, ratio, bits = key.split(":")
+        length, ratio = int(length), float(ratio)
+        want = np.unpackbits(z[key])[:length].astype(np.float32)
+        audio = torch.zeros(1, length, device=cuda)
+        got = tools.convert_bitstreammask_to_audiomask(audio, ratio, [bits]).cpu().numpy()[0]
+        assert np.array_equal(got, want), key[:40]
+        n += 1
+    assert n >= 20
+
+
+def test_gated_stft_equals_gate_then_stft(cuda):
+    from sos_b200 import transform, tools
+    from oracle import synth, transform as otf, gating
+    clips = synth.make_batch(2, length=32000)
+    wave = torch.tensor(clips["mixed"], device=cuda)
+    bits = tools.bits_to_tensor(clips["bits"], cuda)
+    ratio = 16000 / 30.0
+    fused = transform.stft_batch(wave, bits, ratio, 1).cpu().numpy()
+    want = otf.stft_batch(np.stack([gating.gate_noise(w, ratio, b) for w, b in zip(clips["mixed"], clips["bits"])]))
+    assert np.abs(fused - want).max() < 2e-4
+
+
+def test_icrm_forward_backward(cuda):
+    from sos_b200 import transform
+    from oracle import transform as otf
+    g = torch.Generator().manual_seed(3)
+    Y = torch.randn(2, 2, 256, 19, generator=g)
+    crm = torch.rand(2, 2, 256, 19, generator=g) * 0.98 + 0.01
+    crm.requires_grad_(True)
+    ref = otf.batch_fast_icRM_sigmoid(Y, crm)
+    go = torch.randn(ref.shape, generator=g)
+    ref.backward(go)
+    c2 = crm.detach().to(cuda).requires_grad_(True)
+    got = transform.batch_fast_icRM_sigmoid(Y.to(cuda), c2)
+    got.backward(go.to(cuda))
+    assert float((got.cpu() - ref.detach()).abs().max()) < 1e-3
+    assert float((c2.grad.cpu() - crm.grad).abs().max() / crm.grad.abs().max()) < 1e-4
+
+
+def test_losses_and_adam(cuda):
+    from sos_b200 import layers as L, ops
+    g = torch.Generator().manual_seed(4)
+    a, b = torch.randn(3, 2, 256, 11, generator=g), torch.randn(3, 2, 256, 11, generator=g)
+    a.requires_grad_(True)
+    ref = torch.nn.MSELoss()(a, b)
+    ref.backward()
+    ad = a.detach().to(cuda).requires_grad_(True)
+    got = L.MSELoss.apply(ad, b.to(cuda))
+    got.backward()
+    assert abs(float(got) - float(ref)) < 1e-5 * abs(float(ref))
+    assert float((ad.grad.cpu() - a.grad).abs().max()) < 1e-7
+    x, y = torch.randn(5, 60, generator=g) * 3, (torch.rand(5, 60, generator=g) > 0.5).float()
+    x.requires_grad_(True)
+    ref = torch.nn.BCEWithLogitsLoss()(x, y)
+    ref.backward()
+    xd = x.detach().to(cuda).requires_grad_(True)
+    got = L.BCEWithLogitsLoss.apply(xd, y.to(cuda))
+    got.backward()
+    assert abs(float(got) - float(ref)) < 1e-5
+    assert float((xd.grad.cpu() - x.grad).abs().max()) < 1e-7
+    # Adam: 3 steps against torch.optim.Adam
+    p = torch.randn(1000, generator=g)
+    grads = [torch.randn(1000, generator=g) for _ in range(3)]
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=1e-3)
+    pd, m, v = p.to(cuda), torch.zeros(1000, device=cuda), torch.zeros(1000, device=cuda)
+    for i, gr in enumerate(grads):
+        pr.grad = gr.clone()
+        opt.step()
+        ops.adam_step(pd, gr.to(cuda), m, v, 1e-3, i + 1)
+    assert float((pd.cpu() - pr.detach()).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize("act", [1, 2])
+@pytest.mark.parametrize("C", [48, 96, 8, 256])
+def test_bn_act_train(cuda, act, C):
+    from sos_b200 import layers as L, ops
+    g = torch.Generator().manual_seed(C + act)
+    y = torch.randn(2, C, 12, 17, generator=g) * 2 + 0.5
+    bn = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(C, generator=g) * 0.1)
+    prelu = torch.nn.PReLU()
+    y.requires_grad_(True)
+    ref = bn(y)
+    ref = torch.relu(ref) if act == 1 else prelu(ref)
+    go = torch.randn(ref.shape, generator=g)
+    ref.backward(go)
+    bn2 = torch.nn.BatchNorm2d(C).to(cuda)
+    with torch.no_grad():
+        bn2.weight.copy_(bn.weight.detach())
+        bn2.bias.copy_(bn.bias.detach())
+    slope = torch.nn.Parameter(torch.tensor([0.25], device=cuda)) if act == 2 else None
+    yd = ops.nchw_to_nhwc(y.detach().to(cuda), C).requires_grad_(True)
+    z = L.bn_act(yd, bn2, act, slope, True)
+    z.backward(ops.nchw_to_nhwc(go.to(cuda), C))
+    assert float((ops.nhwc_to_nchw(z, C).cpu() - ref.detach()).abs().max()) < 2e-5
+    assert float((ops.nhwc_to_nchw(yd.grad, C).cpu() - y.grad).abs().max()) < 1e-4 * float(y.grad.abs().max() + 1)
+    assert float((bn2.weight.grad.cpu() - bn.weight.grad).abs().max()) < 1e-3 * float(bn.weight.grad.abs().max() + 1)
+    assert float((bn2.bias.grad.cpu() - bn.bias.grad).abs().max()) < 1e-3 * float(bn.bias.grad.abs().max() + 1)
+    assert float((bn2.running_mean.cpu() - bn.running_mean).abs().max()) < 1e-6
+    assert float((bn2.running_var.cpu() - bn.running_var).abs().max()) < 1e-5
+    if act == 2:
+        assert abs(float(slope.grad) - float(prelu.weight.grad)) < 1e-3 * (abs(float(prelu.weight.grad)) + 1)
+
+
+def test_padcat_reflect_resize(cuda):
+    from sos_b200 import layers as L, ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(8)
+    a = torch.randn(2, 64, 16, 22, generator=g, requires_grad=True)       # will be resized to 16 x 21
+    b = torch.randn(2, 64, 16, 21, generator=g, requires_grad=True)
+    ref = F.pad(torch.cat([F.interpolate(a, (16, 21)), b], 1), (3, 3, 3, 3), mode="reflect")
+    go = torch.randn(ref.shape, generator=g)
+    ref.backward(go)
+    ad = ops.nchw_to_nhwc(a.detach().to(cuda), 64).requires_grad_(True)
+    bd = ops.nchw_to_nhwc(b.detach().to(cuda), 64).requires_grad_(True)
+    out = L.PadCat.apply(3, 16, 21, ad, bd)
+    out.backward(ops.nchw_to_nhwc(go.to(cuda), 128))
+    assert float((ops.nhwc_to_nchw(out, 128).cpu() - ref.detach()).abs().max()) == 0.0
+    assert float((ops.nhwc_to_nchw(ad.grad, 64).cpu() - a.grad).abs().max()) < 1e-5
+    assert float((ops.nhwc_to_nchw(bd.grad, 64).cpu() - b.grad).abs().max()) < 1e-5
+
+
+def test_bilstm_matches_torch(cuda):
+    from sos_b200 import networks
+    torch.manual_seed(2)
+    ref = torch.nn.LSTM(96, 40, bidirectional=True)
+    mine = networks.BiLSTM(96, 40, bidirectional=True)
+    mine.load_state_dict(ref.state_dict())
+    mine = mine.to(cuda)
+    x = torch.randn(13, 5, 96, requires_grad=True)
+    out, _ = ref(x)
+    go = torch.randn(out.shape)
+    out.backward(go)
+    xd = x.detach().to(cuda).requires_grad_(True)
+    got = mine(xd)
+    got.backward(go.to(cuda))
+    assert float((got.cpu() - out.detach()).abs().max()) < 1e-5
+    assert float((xd.grad.cpu() - x.grad).abs().max()) < 1e-5
+    for (k, p), (_, q) in zip(ref.named_parameters(), mine.named_parameters()):
+        assert float((q.grad.cpu() - p.grad).abs().max()) < 1e-4 * float(p.grad.abs().max() + 1), k
