@@ -75,10 +75,16 @@ int sos_bce_logits_fwd_bwd(const float* logits, const float* labels, int64_t n, 
 int sos_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, int64_t step, float grad_scale, cudaStream_t stream);
 
+/* In-place round-to-nearest of fp32 values to TF32 (10-bit mantissa).  The tensor-core GEMMs below read TF32 operands by
+ * TRUNCATING fp32; every producer of such an operand (packed weights, network inputs, BatchNorm outputs, gradient maps)
+ * rounds instead, either through this call or through the SOS_ACT_ROUND_TF32 flag OR-ed into an `act` argument. */
+#define SOS_ACT_ROUND_TF32 16
+int sos_round_tf32(float* x, int64_t n, cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------------------ BatchNorm + activation
  * nn.BatchNorm2d(eps 1e-5, momentum 0.1) + ReLU / PReLU of ConvBlock (M2/networks.py:28-51),
  * Conv2dBlock (M1/networks.py:28-51), Down/UpConvBlock (M2/networks.py:97-149) over NHWC rows.
- * act: 0 none, 1 ReLU, 2 PReLU (single slope).  partial: sos_bn_partial_blocks(rows, C) * 3 * C floats. */
+ * act: 0 none, 1 ReLU, 2 PReLU (single slope), optionally | SOS_ACT_ROUND_TF32 (output feeds a tensor-core GEMM).  partial: sos_bn_partial_blocks(rows, C) * 3 * C floats. */
 int sos_bn_partial_blocks(int64_t rows, int64_t channels);
 int sos_bn_stats(const float* y, int64_t rows, int64_t channels, float* partial, cudaStream_t stream);
 int sos_bn_finalize(const float* partial, int64_t rows, int64_t channels, const float* gamma, const float* beta, float eps,

@@ -49,6 +49,7 @@ _SIGS = {
     "sos_icrm_backward": (C.c_int, [c_f, c_f, c_f, c_f, i64, i64, C.c_float, S]),
     "sos_mse_fwd_bwd": (C.c_int, [c_f, c_f, i64, c_f, c_f, C.c_float, S]),
     "sos_bce_logits_fwd_bwd": (C.c_int, [c_f, c_f, i64, c_f, c_f, C.c_float, S]),
+    "sos_round_tf32": (C.c_int, [c_f, i64, S]),
     "sos_adam_step": (C.c_int, [c_f, c_f, c_f, c_f, i64, C.c_float, C.c_float, C.c_float, C.c_float, i64, C.c_float, S]),
     "sos_bn_partial_blocks": (C.c_int, [i64, i64]),
     "sos_bn_stats": (C.c_int, [c_f, i64, i64, c_f, S]),

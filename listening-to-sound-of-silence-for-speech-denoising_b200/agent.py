@@ -1,0 +1,317 @@
+"""Training-step drivers with the reference's agent surface, on the sm_100a kernels.
+
+  get_agent(config)                      M2/agent.py:16-17, M1/agent.py:16-17
+  MyAgent.forward(data)                  M2/agent.py:176-190   -> ((n_pred, mask), {"stage1", "stage2"})
+  SIDAgent.forward(data)                 M1/agent.py:189-206   -> (logits, {"bce"})
+  update_network / train_func / val_func M2/agent.py:101-141
+  save_ckpt / load_ckpt                  M2/agent.py:57-95     (same dict keys; model_state_dict has the reference's names)
+  build_net (nn.DataParallel)            M2/agent.py:153-165   -> replaced by one process per GPU + ONE NCCL all-reduce of the
+                                                                  flat gradient buffer per step (FlatAdam.step)
+
+Differences from the reference that are part of the design: the optimiser state lives in one flat fp32 buffer
+(parameters, gradients, exp_avg, exp_avg_sq are views of four contiguous allocations) so that Adam is one kernel launch
+and the data-parallel exchange is one collective; the data dict may carry WAVEFORMS ("mixed_wave", ... + "bits"), in which
+case the four STFTs and the silent-interval gate run on the device (the reference does them in DataLoader workers).
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from . import layers as L
+from . import ops, transform
+from .networks import get_network
+
+PHASE_TRAINING, PHASE_TESTING = "train", "test"
+
+
+class TrainClock(object):
+    """M2/utils.py TrainClock: epoch / minibatch / step counters with the same checkpoint dict."""
+
+    def __init__(self):
+        self.epoch, self.minibatch, self.step = 1, 0, 0
+
+    def tick(self):
+        self.minibatch += 1
+        self.step += 1
+
+    def tock(self):
+        self.epoch += 1
+        self.minibatch = 0
+
+    def make_checkpoint(self):
+        return {"epoch": self.epoch, "minibatch": self.minibatch, "step": self.step}
+
+    def restore_checkpoint(self, d):
+        self.epoch, self.minibatch, self.step = d["epoch"], d["minibatch"], d["step"]
+
+
+class FlatAdam(object):
+    """optim.Adam(params, lr) (betas 0.9/0.999, eps 1e-8, no weight decay; M2/agent.py:167-170) over ONE flat buffer.
+
+    Parameters and their .grad become views of two contiguous fp32 allocations, so a step is: (optional) one NCCL
+    all-reduce of the flat gradient (sum, then 1/world folded into the Adam kernel's grad_scale) + one Adam kernel.
+    `param_groups` / `state_dict()` keep the shape torch's StepLR and the reference's checkpoint code expect.
+    """
+
+    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8, process_group=None):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        # keep every slice 16-byte aligned for the vectorised kernels
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.numel = off
+        self.flat_param = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.flat_grad = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(off, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(off, device=dev, dtype=torch.float32)
+        for p, o in zip(self.params, self.offsets):
+            self.flat_param[o:o + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[o:o + p.numel()].view(p.shape)
+            p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+        self.param_groups = [{"lr": lr, "initial_lr": lr, "betas": betas, "eps": eps, "params": self.params}]
+        self.defaults = {"lr": lr}
+        self.step_count = 0
+        self.group = process_group
+        self.n_real = n
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_grad.zero_()
+        for p, o in zip(self.params, self.offsets):            # autograd may have replaced .grad; re-attach the views
+            if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
+                p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+
+    def step(self):
+        world = 1
+        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            world = torch.distributed.get_world_size(self.group)
+            if world > 1:
+                torch.distributed.all_reduce(self.flat_grad, group=self.group)        # ncclAllReduce(sum) over NVLink
+        self.step_count += 1
+        g = self.param_groups[0]
+        ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], self.step_count, g["betas"][0],
+                      g["betas"][1], g["eps"], grad_scale=1.0 / world)
+
+    # torch.optim-shaped checkpoint: {"state": {i: {step, exp_avg, exp_avg_sq}}, "param_groups": [...]}
+    def state_dict(self):
+        state = {}
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            state[i] = {"step": torch.tensor(float(self.step_count)),
+                        "exp_avg": self.exp_avg[o:o + p.numel()].view(p.shape).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[o:o + p.numel()].view(p.shape).clone()}
+        g = self.param_groups[0]
+        return {"state": state if self.step_count else {},
+                "param_groups": [{"lr": g["lr"], "betas": g["betas"], "eps": g["eps"], "weight_decay": 0, "amsgrad": False,
+                                  "initial_lr": g["initial_lr"], "params": list(range(len(self.params)))}]}
+
+    def load_state_dict(self, sd):
+        g = sd["param_groups"][0]
+        self.param_groups[0].update(lr=g["lr"], betas=tuple(g["betas"]), eps=g["eps"])
+        self.param_groups[0]["initial_lr"] = g.get("initial_lr", g["lr"])
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            st = sd["state"].get(i)
+            if st is None:
+                continue
+            self.step_count = int(float(st["step"]))
+            self.exp_avg[o:o + p.numel()].copy_(st["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + p.numel()].copy_(st["exp_avg_sq"].reshape(-1))
+
+
+class StepLR(object):
+    """optim.lr_scheduler.StepLR(optimizer, step_size, gamma=0.1) stepped once per epoch (M2/agent.py:108-111,170)."""
+
+    def __init__(self, optimizer, step_size, gamma=0.1):
+        self.optimizer, self.step_size, self.gamma, self.last_epoch = optimizer, step_size, gamma, 0
+
+    def step(self, epoch=None):
+        self.last_epoch = self.last_epoch + 1 if epoch is None else epoch
+        for g in self.optimizer.param_groups:
+            g["lr"] = g["initial_lr"] * self.gamma ** (self.last_epoch // self.step_size)
+
+    def state_dict(self):
+        return {"step_size": self.step_size, "gamma": self.gamma, "last_epoch": self.last_epoch}
+
+    def load_state_dict(self, d):
+        self.step_size, self.gamma, self.last_epoch = d["step_size"], d["gamma"], d["last_epoch"]
+
+
+class _Config(object):
+    """The attributes of M2/common.py Config / M1/common.py Config that the agents read."""
+    lr = 1e-3                   # M2/common.py:55
+    lr_step_size = 15           # M2/common.py:56
+    batch_size = 40
+    model = "joint"             # "joint" (M2) or "sid" (M1)
+    log_dir = None
+    model_dir = None
+    sr = 16000
+    fps = 30.0
+
+
+def default_config(**kw):
+    c = _Config()
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+class BaseAgent(object):
+    def __init__(self, config):
+        ops.init()
+        self.config = config
+        self.log_dir = getattr(config, "log_dir", None)
+        self.model_dir = getattr(config, "model_dir", None)
+        self.clock = TrainClock()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.batch_size = getattr(config, "batch_size", None)
+        self.net = self.build_net(config)
+        self.set_loss_function()
+        self.set_optimizer(config)
+        self.last_losses = {}
+
+    # -- reference: nn.DataParallel(net.cuda()) when several GPUs are visible.  Here: this process owns ONE GPU; when
+    #    torch.distributed is initialised every rank builds the same net (same seed) and FlatAdam all-reduces gradients.
+    def build_net(self, config):
+        raise NotImplementedError
+
+    def set_loss_function(self):
+        self.criterion = L.MSELoss.apply
+
+    def set_optimizer(self, config):
+        self.optimizer = FlatAdam(self.net.parameters(), getattr(config, "lr", 1e-3))
+        self.scheduler = StepLR(self.optimizer, getattr(config, "lr_step_size", 15))
+
+    def save_ckpt(self, name=None):
+        path = os.path.join(self.model_dir, ("ckpt_epoch{}.pth".format(self.clock.epoch)) if name is None else "{}.pth".format(name))
+        torch.save({"clock": self.clock.make_checkpoint(),
+                    "model_state_dict": {k: v.detach().cpu().clone() for k, v in self.net.state_dict().items()},
+                    "optimizer_state_dict": self.optimizer.state_dict(),
+                    "scheduler_state_dict": self.scheduler.state_dict()}, path)
+        return path
+
+    def load_ckpt(self, name=None):
+        name = name if name == "latest" else "ckpt_epoch{}".format(name)
+        path = os.path.join(self.model_dir, "{}.pth".format(name))
+        if not os.path.exists(path):
+            raise ValueError("Checkpoint {} not exists.".format(path))
+        ck = torch.load(path, map_location="cpu")
+        with torch.no_grad():                                   # copy INTO the flat views (keeps the optimiser's aliasing)
+            own = self.net.state_dict()
+            for k, v in ck["model_state_dict"].items():
+                own[k].copy_(v)
+        self.optimizer.load_state_dict(ck["optimizer_state_dict"])
+        self.scheduler.load_state_dict(ck["scheduler_state_dict"])
+        self.clock.restore_checkpoint(ck["clock"])
+
+    def forward(self, data):
+        raise NotImplementedError
+
+    def update_network(self, loss_dict):
+        loss = sum(loss_dict.values())
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.optimizer.step()
+
+    def update_learning_rate(self):
+        self.scheduler.step(self.clock.epoch)
+
+    def record_losses(self, loss_dict, mode=PHASE_TRAINING):
+        # the reference calls .item() on every loss here (a device sync per loss per step, M2/agent.py:113-119); the
+        # losses stay on the device and are read only when someone asks (`loss_values()`).
+        self.last_losses = {k: v.detach() for k, v in loss_dict.items()}
+
+    def loss_values(self):
+        return {k: float(v) for k, v in self.last_losses.items()}
+
+    def train_func(self, data):
+        self.net.train()
+        outputs, losses = self.forward(data)
+        self.update_network(losses)
+        self.record_losses(losses, PHASE_TRAINING)
+        return outputs, losses
+
+    def val_func(self, data):
+        self.net.eval()
+        with torch.no_grad():
+            outputs, losses = self.forward(data)
+        self.record_losses(losses, PHASE_TESTING)
+        return outputs, losses
+
+
+def _dev(t, device):
+    return t.to(device, non_blocking=True) if torch.is_tensor(t) else torch.as_tensor(t).to(device, non_blocking=True)
+
+
+class MyAgent(BaseAgent):
+    """Stage-2 (JointModel) trainer, M2/agent.py:144-233."""
+
+    def build_net(self, config):
+        return get_network(config).to(self.device)
+
+    def spectrograms(self, data):
+        """Dataset item dict (M2/dataset.py:311-320) with spectrograms, or waveforms + bit strings to transform here."""
+        d = self.device
+        if "mixed" in data:
+            return tuple(_dev(data[k], d).float() for k in ("mixed", "noise", "clean", "full_noise"))
+        mixed_w = _dev(data["mixed_wave"], d)
+        bits = _dev(data["bits"], d)
+        ratio = getattr(self.config, "sr", 16000) / getattr(self.config, "fps", 30.0)
+        mixed = transform.stft_batch(mixed_w)
+        noise = transform.stft_batch(mixed_w, bits, ratio, 1)                 # noise_sig = mixed * mask, gate fused
+        clean = transform.stft_batch(_dev(data["clean_wave"], d))
+        full = transform.stft_batch(_dev(data["full_noise_wave"], d))
+        return mixed, noise, clean, full
+
+    def forward(self, data):
+        mixed, noise, clean, full_noise = self.spectrograms(data)
+        pred_noise, mask = self.net(mixed, noise)
+        rec = transform.batch_fast_icRM_sigmoid(mixed, mask)
+        self.last_rec = rec
+        l1 = self.criterion(pred_noise, full_noise)
+        l2 = self.criterion(rec, clean)
+        return (pred_noise, mask), {"stage1": l1, "stage2": l2}
+
+    def evaluate(self, dataloader):
+        self.net.eval()
+        tot, n = 0.0, 0
+        with torch.no_grad():
+            for data in dataloader:
+                _, losses = self.forward(data)
+                tot += float(losses["stage2"])
+                n += 1
+        return tot / max(n, 1)
+
+
+class SIDAgent(BaseAgent):
+    """Stage-1 (AudioVisualNet) trainer, M1/agent.py:144-237: BCEWithLogitsLoss on (B, 60) labels."""
+
+    def build_net(self, config):
+        return get_network().to(self.device)
+
+    def set_loss_function(self):
+        self.criterion = L.BCEWithLogitsLoss.apply
+
+    def forward(self, data):
+        d = self.device
+        audio = _dev(data["audio"], d).float() if "audio" in data else transform.stft_batch(_dev(data["mixed_wave"], d))
+        label = _dev(data["label"], d).float()
+        logits = self.net(audio, label.shape[1])
+        return logits, {"bce": self.criterion(logits, label)}
+
+    def evaluate(self, dataloader):
+        """frame accuracy at the 0.5 threshold (M1/agent.py:209-230)."""
+        self.net.eval()
+        ok, n = 0, 0
+        with torch.no_grad():
+            for data in dataloader:
+                logits, _ = self.forward(data)
+                pred = (torch.sigmoid(logits) >= 0.5).float()
+                ok += int((pred == _dev(data["label"], self.device)).sum())
+                n += pred.numel()
+        return ok / max(n, 1)
+
+
+def get_agent(config):
+    return SIDAgent(config) if getattr(config, "model", "joint") == "sid" else MyAgent(config)

@@ -43,6 +43,17 @@ static inline int sos_num_sms() {
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
+// Round-to-nearest (ties away) fp32 -> tf32, kept in an fp32 container.  tcgen05 kind::tf32 TRUNCATES the low 13
+// mantissa bits of its operands, a systematic -2^-12 relative bias per operand; producers of tensor-core operands
+// round here instead so that the MMA sees exactly representable values.
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+#define SOS_ACT_MASK 15
+#define SOS_ACT_ROUND_TF32 16
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

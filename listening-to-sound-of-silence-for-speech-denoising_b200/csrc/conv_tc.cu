@@ -28,7 +28,6 @@ using namespace ptx;
 using namespace tc;
 
 constexpr int kThreadsTc = 192;
-constexpr int kStagingBytes = 2 * 128 * 32 * 4;      // two 128 x 32 fp32 buffers
 struct alignas(64) TcParams {
   CUtensorMap mapA, mapB, mapD;
   int total_ctiles, n_nblk, tiles_fast_g, tiles_slow, n_phase;
@@ -36,7 +35,7 @@ struct alignas(64) TcParams {
   int FB, SB, stride;
   int cin;                       // K elements per tap in the weight matrix
   int ec;                        // epilogue / store chunk width (16 or 32 channels)
-  int n_stages, stage_bytes, a_box_bytes, a_box_stride, b_tile_stride;
+  int n_stages, stage_bytes, a_box_bytes, a_box_stride, b_tile_stride, staging_bytes;
   int layout_type, sbo;
   uint32_t idesc;
   const float* scale;            // optional per-output-channel affine (eval-mode BN / bias) ...
@@ -65,7 +64,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
   // smem carve-up: [stages][staging][barriers]
   const uint32_t stages_base = smem_base;
   const uint32_t staging_base = stages_base + (uint32_t)p.n_stages * p.stage_bytes;
-  const uint32_t bar_base = staging_base + kStagingBytes;
+  const uint32_t bar_base = staging_base + (uint32_t)p.staging_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (16 + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (32 + s); };
@@ -175,7 +174,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
     int acc = 0;
     uint32_t acc_phase = 0;
     int buf = 0;
-    const float slope = (p.act == 2 && p.slope) ? *p.slope : 0.f;
+    const float slope = ((p.act & SOS_ACT_MASK) == 2 && p.slope) ? *p.slope : 0.f;
     const int n_ec = p.N / p.ec;
     for (int ct = blockIdx.x; ct < p.total_ctiles; ct += gridDim.x) {
       const TileCoord tc = decode_tile(p, ct);
@@ -190,13 +189,16 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
           tmem_ld_wait();
           const int ch0 = tc.nb * p.N + cc * p.ec;
           if (p.scale || p.act) {
+            const int act = p.act & SOS_ACT_MASK;
+            const bool rnd = (p.act & SOS_ACT_ROUND_TF32) != 0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               if (i < p.ec) {
                 float v = __uint_as_float(r[i]);
                 if (p.scale) v = fmaf(v, __ldg(p.scale + ch0 + i), __ldg(p.shift + ch0 + i));
-                if (p.act == 1) v = fmaxf(v, 0.f);
-                else if (p.act == 2) v = v > 0.f ? v : v * slope;
+                if (act == 1) v = fmaxf(v, 0.f);
+                else if (act == 2) v = v > 0.f ? v : v * slope;
+                if (rnd) v = tf32_rna(v);
                 r[i] = __float_as_uint(v);
               }
             }
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
           // make sure the TMA store that last read this staging buffer has drained
           if (ethread == 0) bulk_wait_read<1>();
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          const uint32_t sbuf = staging_base + (uint32_t)buf * (128 * 32 * 4);
+          const uint32_t sbuf = staging_base + (uint32_t)buf * (128 * p.ec * 4);
           const uint32_t srow = sbuf + (uint32_t)row * (p.ec * 4);
           const int nv = p.ec / 4;                 // float4 per row: 8 or 4
 #pragma unroll
@@ -256,25 +258,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG(((uintptr_t)a.x % 16) == 0 && ((uintptr_t)a.y % 16) == 0 && ((uintptr_t)a.wk % 16) == 0, "sos_conv2d_tc: pointers must be 16-byte aligned");
   SOS_CHECK_ARG((a.OH - 1) * a.osh + a.oph < a.YH && (a.OW - 1) * a.osw + a.opw < a.YW, "sos_conv2d_tc: output lattice exceeds the output buffer");
 
-  // ---- choose orientation / sharing
-  Geometry geo{(int)a.ntaps, a.tap_dh, a.tap_dw, (int)a.H, (int)a.W, (int)a.OH, (int)a.OW, (int)a.stride, (int)a.Cin, (int)a.Cout,
-               a.osh == 1 && a.osw == 1 && a.oph == 0 && a.opw == 0, kMaxSub};
-  Plan best;
-  for (int fw = 1; fw >= 0; --fw)
-    for (int sh = 1; sh >= 0; --sh) {
-      Plan pl;
-      if (build_plan(geo, fw != 0, sh != 0, pl) && pl.cost < best.cost) best = pl;
-    }
-  SOS_CHECK_ARG(best.cost < 1e299, "sos_conv2d_tc: no feasible plan");
-  if (a.force_plan >= 0) {            // test hook: bit0 = fast_is_w, bit1 = share
-    Plan pl;
-    SOS_CHECK_ARG(build_plan(geo, (a.force_plan & 1) != 0, (a.force_plan & 2) != 0, pl), "sos_conv2d_tc: forced plan %d not applicable", (int)a.force_plan);
-    best = pl;
-  }
-  const Plan& pl = best;
-
-  static TcParams p;                  // kernel parameter block (copied at launch)
-  memset(&p, 0, sizeof(p));
+  // ---- output-channel blocking
   const int Cin = (int)a.Cin, Cout = (int)a.Cout;
   const int Ntot = round_up(Cout, 16);
   int N = Ntot, n_nblk = 1;
@@ -285,15 +269,70 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
       if (n <= 256 && n * nb - Ntot < best_waste) { best_waste = n * nb - Ntot; N = n; n_nblk = nb; }
     }
   }
+  const int ec = (N % 32 == 0) ? 32 : 16;
+  const int staging_bytes = 2 * 128 * ec * 4;
+  const int avail = kSmemLimit - 1024 - staging_bytes - 512;
+
+  // ---- choose orientation / box sharing / taps per box / channel chunk / sub-tiles: the cheapest candidate (tensor time vs
+  //      L2->smem feed time per output pixel) whose pipeline stage fits at least twice (three times preferred) in shared memory
+  Geometry geo{(int)a.ntaps, a.tap_dh, a.tap_dw, (int)a.H, (int)a.W, (int)a.OH, (int)a.OW, (int)a.stride, Cin, Cout,
+               a.osh == 1 && a.osw == 1 && a.oph == 0 && a.opw == 0, kMaxSub};
+  struct Cand { Plan pl; int cbe = 0, S = 0, n_stages = 0, stage_bytes = 0, a_box_bytes = 0; double cost = 1e300; };
+  Cand best;
+  auto consider = [&](const Plan& pl, int cbe, int S) {
+    if (n_nblk > 1 || S * N > 256) S = 1;
+    const int cb = cbe * 4;
+    const int a_box = (pl.SB + pl.halo) * pl.FB * cb;
+    int max_sub = 1;
+    for (auto& g : pl.groups) max_sub = std::max(max_sub, (int)g.n_sub);
+    const int stage = S * round_up(a_box, 1024) + max_sub * round_up(N * cb, 1024);
+    const int n_stages = std::min(8, avail / stage);
+    if (n_stages < 2) return;
+    const int out_fast = pl.fast_is_w ? (int)a.OW : (int)a.OH, out_slow = pl.fast_is_w ? (int)a.OH : (int)a.OW;
+    const int tiles_fast = ceil_div(out_fast, pl.FB);
+    const double mma = (double)a.ntaps * (Cin / 8) * S * (128.0 * N / 256.0);
+    const double bytes = ((double)pl.groups.size() * S * (pl.SB + pl.halo) * pl.FB + (double)a.ntaps * N) * Cin * 4.0;
+    const int lat_slow = out_slow / pl.g;
+    const double util = ((double)lat_slow / (ceil_div(lat_slow, pl.SB) * pl.SB)) * ((double)out_fast / (ceil_div(tiles_fast, S) * S * pl.FB));
+    double cost = std::max(mma, bytes / 40.0) / (util * S);
+    if (n_stages < 3) cost *= 1.3;
+    if (cost < best.cost) { best.pl = pl; best.cbe = cbe; best.S = S; best.n_stages = n_stages; best.stage_bytes = stage; best.a_box_bytes = a_box; best.cost = cost; }
+  };
+  auto sweep = [&](bool fw, bool sh) -> bool {
+    bool any = false;
+    for (int ms = sh ? kMaxSub : 1; ms >= 1; --ms) {
+      geo.max_sub = ms;
+      Plan pl;
+      if (!build_plan(geo, fw, sh, pl)) continue;
+      any = true;
+      for (int cbe = 32; cbe >= 8; cbe >>= 1) {
+        if (Cin % cbe) continue;
+        consider(pl, cbe, 2);
+        consider(pl, cbe, 1);
+      }
+    }
+    return any;
+  };
+  if (a.force_plan >= 0) {            // test hook: bit0 = fast_is_w, bit1 = share
+    SOS_CHECK_ARG(sweep((a.force_plan & 1) != 0, (a.force_plan & 2) != 0), "sos_conv2d_tc: forced plan %d not applicable", (int)a.force_plan);
+  } else {
+    for (int fw = 1; fw >= 0; --fw)
+      for (int sh = 1; sh >= 0; --sh) sweep(fw != 0, sh != 0);
+  }
+  SOS_CHECK_ARG(best.cost < 1e299, "sos_conv2d_tc: no feasible plan (Cin %d Cout %d taps %d)", Cin, Cout, (int)a.ntaps);
+  const Plan& pl = best.pl;
+
+  static TcParams p;                  // kernel parameter block (copied at launch)
+  memset(&p, 0, sizeof(p));
   p.N = N;
   p.n_nblk = n_nblk;
-  p.cbe = Cin % 32 == 0 ? 32 : (Cin % 16 == 0 ? 16 : 8);
+  p.cbe = best.cbe;
   p.n_chunks = Cin / p.cbe;
   p.cin = Cin;
-  p.ec = (N % 32 == 0) ? 32 : 16;
+  p.ec = ec;
   p.FB = pl.FB;
   p.SB = pl.SB;
-  p.S = (n_nblk > 1 || pl.S * N > 256) ? 1 : pl.S;
+  p.S = best.S;
   p.stride = (int)a.stride;
   p.n_groups = (int)pl.groups.size();
   for (int i = 0; i < p.n_groups; ++i) p.groups[i] = pl.groups[i];
@@ -302,15 +341,12 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   p.sbo = 8 * cb;
   p.idesc = make_idesc_tf32(128, N, 0, 0);
   const int box_slow = pl.SB + pl.halo;
-  p.a_box_bytes = box_slow * pl.FB * cb;
+  p.a_box_bytes = best.a_box_bytes;
   p.a_box_stride = round_up(p.a_box_bytes, 1024);
   p.b_tile_stride = round_up(N * cb, 1024);
-  int max_sub = 1;
-  for (auto& g : pl.groups) max_sub = std::max(max_sub, (int)g.n_sub);
-  p.stage_bytes = p.S * p.a_box_stride + max_sub * p.b_tile_stride;
-  const int avail = kSmemLimit - 1024 - kStagingBytes - 512;
-  p.n_stages = std::min(8, avail / p.stage_bytes);
-  SOS_CHECK_ARG(p.n_stages >= 2, "sos_conv2d_tc: pipeline stage of %d bytes does not fit twice in shared memory", p.stage_bytes);
+  p.stage_bytes = best.stage_bytes;
+  p.n_stages = best.n_stages;
+  p.staging_bytes = staging_bytes;
   p.scale = a.epi_scale;
   p.shift = a.epi_shift;
   p.act = (int)a.act;
@@ -360,7 +396,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG(total < (1ll << 31), "sos_conv2d_tc: too many tiles");
   p.total_ctiles = (int)total;
 
-  const int smem = 1024 + p.n_stages * p.stage_bytes + kStagingBytes + 512;
+  const int smem = 1024 + p.n_stages * p.stage_bytes + staging_bytes + 512;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(tapgemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess) {

@@ -90,6 +90,10 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+__global__ void round_tf32_kernel(float* __restrict__ x, long long n) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) x[e] = tf32_rna(x[e]);
+}
+
 // ----------------------------------------------------------------------------- views
 struct View {
   int H, W;     // logical extent
@@ -183,6 +187,8 @@ __global__ void __launch_bounds__(kThreads) bn_act_kernel(const float* __restric
                                                            const float* __restrict__ slope_ptr, View zv) {
   const int cg = C >> 2;
   const float slope = slope_ptr ? *slope_ptr : 0.f;
+  const bool rnd = (act & SOS_ACT_ROUND_TF32) != 0;
+  act &= SOS_ACT_MASK;
   const long long total = P * cg;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long p = e / cg;
@@ -194,6 +200,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_kernel(const float* __restric
     o.y = act_fwd(fmaf(v.y, sc.y, sh.y), act, slope);
     o.z = act_fwd(fmaf(v.z, sc.z, sh.z), act, slope);
     o.w = act_fwd(fmaf(v.w, sc.w, sh.w), act, slope);
+    if (rnd) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
     *reinterpret_cast<float4*>(z + view_pix(zv, p) + c) = o;
   }
 }
@@ -211,6 +218,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __
   const int rows = kThreads / cg;
   const int r = threadIdx.x / cg, c4 = threadIdx.x - r * cg;
   const float slope = slope_ptr ? *slope_ptr : 0.f;
+  act &= SOS_ACT_MASK;
   float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, s3[4] = {0, 0, 0, 0};
   if (r < rows) {
     const int c = c4 * 4;
@@ -275,6 +283,8 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __r
                                                                  const float* __restrict__ slope_ptr) {
   const int cg = C >> 2;
   const float slope = slope_ptr ? *slope_ptr : 0.f;
+  const bool rnd = (act & SOS_ACT_ROUND_TF32) != 0;
+  act &= SOS_ACT_MASK;
   const long long total = P * cg;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long p = e / cg;
@@ -292,6 +302,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __r
       else if (act == 2) dpre = pre > 0.f ? dpre : dpre * slope;
       const float xhat = (yv[i] - mean[c + i]) * invstd[c + i];
       o[i] = sc * (dpre - m1[c + i] - xhat * m2[c + i]);
+      if (rnd) o[i] = tf32_rna(o[i]);
     }
     *reinterpret_cast<float4*>(dy + p * C + c) = make_float4(o[0], o[1], o[2], o[3]);
   }
@@ -304,6 +315,8 @@ __global__ void __launch_bounds__(kThreads) affine_act_bwd_kernel(const float* _
                                                                    int act, const float* __restrict__ slope_ptr) {
   const int cg = C >> 2;
   const float slope = slope_ptr ? *slope_ptr : 0.f;
+  const bool rnd = (act & SOS_ACT_ROUND_TF32) != 0;
+  act &= SOS_ACT_MASK;
   const long long total = P * cg;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long p = e / cg;
@@ -320,6 +333,7 @@ __global__ void __launch_bounds__(kThreads) affine_act_bwd_kernel(const float* _
       if (act == 1) dpre = pre > 0.f ? dpre : 0.f;
       else if (act == 2) dpre = pre > 0.f ? dpre : dpre * slope;
       o[i] = sc * dpre;
+      if (rnd) o[i] = tf32_rna(o[i]);
     }
     *reinterpret_cast<float4*>(dy + p * C + c) = make_float4(o[0], o[1], o[2], o[3]);
   }
@@ -615,6 +629,13 @@ int sos_bce_logits_fwd_bwd(const float* logits, const float* labels, int64_t n, 
   return SOS_OK;
 }
 
+int sos_round_tf32(float* x, int64_t n, cudaStream_t stream) {
+  SOS_CHECK_ARG(x && n > 0, "sos_round_tf32: bad arguments");
+  round_tf32_kernel<<<grid_for(n), kThreads, 0, stream>>>(x, n);
+  SOS_CHECK_LAUNCH("sos_round_tf32");
+  return SOS_OK;
+}
+
 int sos_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
                   float eps, int64_t step, float grad_scale, cudaStream_t stream) {
   SOS_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, "sos_adam_step: bad arguments");
@@ -677,7 +698,7 @@ int sos_bn_act(const float* y, float* z, const int32_t* z_view, int64_t rows, in
   SOS_CHECK_ARG(y && z && z_view && scale && shift && rows > 0 && channels >= 4 && channels % 4 == 0, "sos_bn_act: bad arguments");
   const View zv = mk_view(z_view);
   SOS_CHECK_ARG(view_ok(zv, (int)channels) && rows % ((long long)zv.H * zv.W) == 0, "sos_bn_act: inconsistent view");
-  SOS_CHECK_ARG(act != 2 || slope, "sos_bn_act: PReLU needs a slope pointer");
+  SOS_CHECK_ARG((act & SOS_ACT_MASK) != 2 || slope, "sos_bn_act: PReLU needs a slope pointer");
   bn_act_kernel<<<grid_for(rows * (channels / 4)), kThreads, 0, stream>>>(y, z, rows, (int)channels, scale, shift, act, slope, zv);
   SOS_CHECK_LAUNCH("sos_bn_act");
   return SOS_OK;
@@ -692,13 +713,13 @@ int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y,
   const View dv = mk_view(dz_view);
   const int C = (int)channels;
   SOS_CHECK_ARG(view_ok(dv, C) && rows % ((long long)dv.H * dv.W) == 0, "sos_bn_act_backward: inconsistent view");
-  SOS_CHECK_ARG(act != 2 || (slope && dslope), "sos_bn_act_backward: PReLU needs slope and dslope");
+  SOS_CHECK_ARG((act & SOS_ACT_MASK) != 2 || (slope && dslope), "sos_bn_act_backward: PReLU needs slope and dslope");
   const int rpb = kThreads / (C / 4);
   const size_t smem = (size_t)rpb * 3 * C * sizeof(float);
   if (smem > 48 * 1024) cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   bn_bwd_reduce_kernel<<<G, kThreads, smem, stream>>>(dz, dv, y, rows, C, scale, shift, mean, invstd, act, slope, partial);
   SOS_CHECK_LAUNCH("sos_bn_act_backward(reduce)");
-  bn_bwd_finalize_kernel<<<1, 256, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta, act == 2 ? dslope : nullptr, m1, m2);
+  bn_bwd_finalize_kernel<<<1, 256, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta, (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2);
   SOS_CHECK_LAUNCH("sos_bn_act_backward(finalize)");
   bn_bwd_apply_kernel<<<grid_for(rows * (channels / 4)), kThreads, 0, stream>>>(dz, dv, y, dy, rows, C, scale, shift, mean, invstd, m1,
                                                                                  m2, act, slope);
@@ -712,7 +733,7 @@ int sos_affine_act_backward(const float* dz, const int32_t* dz_view, const float
                 "sos_affine_act_backward: bad arguments");
   const View dv = mk_view(dz_view);
   SOS_CHECK_ARG(view_ok(dv, (int)channels) && rows % ((long long)dv.H * dv.W) == 0, "sos_affine_act_backward: inconsistent view");
-  SOS_CHECK_ARG(act != 2 || slope, "sos_affine_act_backward: PReLU needs a slope pointer");
+  SOS_CHECK_ARG((act & SOS_ACT_MASK) != 2 || slope, "sos_affine_act_backward: PReLU needs a slope pointer");
   affine_act_bwd_kernel<<<grid_for(rows * (channels / 4)), kThreads, 0, stream>>>(dz, dv, y, dy, rows, (int)channels, scale, shift, act,
                                                                                    slope);
   SOS_CHECK_LAUNCH("sos_affine_act_backward");

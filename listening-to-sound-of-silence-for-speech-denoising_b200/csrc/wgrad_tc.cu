@@ -3,7 +3,10 @@
 //     dw[t][co][ci] += sum_{pixels p} dy[p][co] * x[p*s + off_t][ci]
 //
 // is a GEMM whose reduction axis is the pixel axis, so both operands are consumed "MN-major": a staged NHWC box
-// [pixel][channel chunk] is exactly the canonical MN-major swizzled tile (one 32/64/128-byte row per k index).
+// [pixel][32-channel chunk] is the canonical MN-major tile of 32-bit operands, whose only legal shared-memory layout is
+// the 128-byte swizzle with 32-byte atoms (descriptor layout type 1 = SWIZZLE_128B_BASE32B, TMA
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): one 128-byte row per k index, 4 rows per swizzle atom.  Channel counts that are
+// not multiples of 32 use the same 32-wide boxes; TMA zero-fills the out-of-range channels.
 //   A = dy tile   (M = 128 output channels of one channel block, K = 8 pixels per MMA)
 //   B = x box     (N = Cin, same K) -- one box per tap group, shared by the taps that differ by a slow-axis shift
 //   D = dw[t] block, one TMEM accumulator (N columns) per tap, up to 512 columns per job
@@ -145,8 +148,8 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
             for (int j = 0; j < grp.n_sub; ++j, ++slot) {
               const uint32_t d = tmem_base + (uint32_t)slot * p.N;
               for (int ks = 0; ks < p.SB; ++ks) {
-                const uint64_t ad = make_smem_desc(sbase + ks * a_kstep, p.dy_chunk_stride, a_kstep, p.layout_a);
-                const uint64_t bd = make_smem_desc(xb + (ks + grp.a_off[j]) * b_kstep, p.x_box_stride, b_kstep, p.layout_b);
+                const uint64_t ad = make_smem_desc(sbase + ks * a_kstep, p.dy_chunk_stride, 512, 1);
+                const uint64_t bd = make_smem_desc(xb + (ks + grp.a_off[j]) * b_kstep, p.x_box_stride, 512, 1);
                 umma_tf32_wg(d, ad, bd, p.idesc, (tile != t0 || ks != 0) ? 1u : 0u);
               }
             }
@@ -241,15 +244,13 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   p.Cin = Cin;
   p.Cout = Cout;
   p.N = round_up(Cin, 16);
-  p.cbi = Cin % 32 == 0 ? 32 : (Cin % 16 == 0 ? 16 : 8);
-  p.n_ci_chunks = Cin / p.cbi;
-  p.cbo = Cout % 32 == 0 ? 32 : (Cout % 16 == 0 ? 16 : 8);
+  p.cbi = 32;
+  p.n_ci_chunks = ceil_div(Cin, 32);
+  p.cbo = 32;
   p.FB = 8;
   p.stride = (int)a.stride;
   p.dw = a.dw;
-  auto layout_of = [](int cb) { return cb == 128 ? 2 : (cb == 64 ? 4 : 6); };
-  p.layout_a = layout_of(p.cbo * 4);
-  p.layout_b = layout_of(p.cbi * 4);
+  p.layout_a = p.layout_b = 1;
   p.idesc = make_idesc_tf32(128, p.N, 1, 1);
 
   // ---- jobs: tap groups packed into TMEM (512 columns) per output-channel block; at most kMaxJobGroups boxes per stage
@@ -276,7 +277,7 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
     const int used = x_off + ng * p.n_ci_chunks * x_stride;
     // the padded MMA rows (M = 128, N rounded to 16) read past the staged chunks: keep that inside the stage
     const int reach_a = (128 / p.cbo) * dy_stride;
-    const int reach_b = x_off + ((ng - 1) * p.n_ci_chunks + p.N / p.cbi) * x_stride;
+    const int reach_b = x_off + ng * p.n_ci_chunks * x_stride;
     if (x_off_out) *x_off_out = x_off;
     if (reach_out) *reach_out = std::max(reach_a, reach_b);
     return used;
@@ -343,8 +344,7 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
     uint32_t box[5] = {(uint32_t)p.cbi, (uint32_t)(8 * a.stride), (uint32_t)((SB + pl.halo) * a.stride), 1, 1};
     uint32_t es[5] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1, 1};
     SOS_CHECK_ARG(box[2] <= 256, "sos_conv2d_wgrad: activation box too large");
-    const int cb = p.cbi * 4;
-    const CUtensorMapSwizzle sw = cb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (cb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     if (int e = encode_map(&p.mapX, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, a.x, dims, str, box, es, sw, "wgrad activations")) return e;
   }
   const int out_fast = fw ? (int)a.OW : (int)a.OH, out_slow = fw ? (int)a.OH : (int)a.OW;
@@ -355,8 +355,7 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
     uint64_t str[5] = {4, s_fast, s_slow * g, s_slow, pix * a.OH * a.OW};
     uint32_t box[5] = {(uint32_t)p.cbo, 8, (uint32_t)SB, 1, 1};
     uint32_t es[5] = {1, 1, 1, 1, 1};
-    const int cb = p.cbo * 4;
-    const CUtensorMapSwizzle sw = cb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (cb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     if (int e = encode_map(&p.mapDY, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, a.dy + a.dy_coff, dims, str, box, es, sw, "wgrad output grads"))
       return e;
   }

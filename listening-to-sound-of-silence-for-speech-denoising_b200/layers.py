@@ -49,7 +49,7 @@ def _pack_fwd(w, taps, cin_p):
     sel = torch.stack([w[:, :, a, b] for a, b in taps], dim=1)            # (Cout, ntaps, Cin)
     if cin_p != Cin:
         sel = torch.nn.functional.pad(sel, (0, cin_p - Cin))
-    return sel.reshape(Cout, len(taps) * cin_p).contiguous()
+    return ops.round_tf32_(sel.reshape(Cout, len(taps) * cin_p).contiguous())     # torch.stack made a fresh tensor
 
 
 def _conv_forward(x, w, g, epi=None):
@@ -137,9 +137,22 @@ class TapConv(torch.autograd.Function):
         return dx, dw, None
 
 
-def conv_fused_eval(x, w, g, scale, shift, act, slope):
+def conv_fused_eval(x, w, g, scale, shift, act, slope, round_out=True):
     """Inference path: BN (running stats) + activation folded into the GEMM epilogue."""
-    return _conv_forward(x, w, g, epi=(scale, shift, act, slope))
+    return _conv_forward(x, w, g, epi=(scale, shift, act | (ops.ACT_ROUND_TF32 if round_out else 0), slope))
+
+
+class RoundTF32(torch.autograd.Function):
+    """Identity up to TF32 rounding of the value (forward) and of the gradient (backward): marks a tensor that feeds a
+    tensor-core GEMM but was produced by a plain tensor expression."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.round_tf32_(x.detach().clone().contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.round_tf32_(g.clone().contiguous())
 
 
 # ----------------------------------------------------------------------------------------------- BatchNorm + act
@@ -155,11 +168,11 @@ class BNActTrain(torch.autograd.Function):
     def backward(ctx, dz):
         y, stats, slope = ctx.saved_tensors
         slope = slope if slope.numel() else None
-        dy, dgamma, dbeta, dslope = ops.bn_train_backward(dz.contiguous(), y, stats, ctx.act, slope)
+        dy, dgamma, dbeta, dslope = ops.bn_train_backward(dz.contiguous(), y, stats, ctx.act | ops.ACT_ROUND_TF32, slope)
         return dy, dgamma, dbeta, dslope, None, None, None, None, None
 
 
-def bn_act(y, bn, act, slope, training):
+def bn_act(y, bn, act, slope, training, round_out=True):
     """y NHWC with C = round8(bn.num_features).  bn: nn.BatchNorm2d holding the reference-named parameters."""
     Cp, Cn = y.shape[3], bn.num_features
     gamma, beta, rm, rv = bn.weight, bn.bias, bn.running_mean, bn.running_var
@@ -170,7 +183,7 @@ def bn_act(y, bn, act, slope, training):
     else:
         rm_p, rv_p = rm, rv
     if training:
-        z = BNActTrain.apply(y, gamma, beta, slope, rm_p, rv_p, bn.eps, bn.momentum, act)
+        z = BNActTrain.apply(y, gamma, beta, slope, rm_p, rv_p, bn.eps, bn.momentum, act | (ops.ACT_ROUND_TF32 if round_out else 0))
         if Cp != Cn:
             with torch.no_grad():
                 rm.copy_(rm_p[:Cn])
@@ -182,10 +195,10 @@ def bn_act(y, bn, act, slope, training):
     scale = gamma * torch.rsqrt(rv_p + bn.eps)
     pre = y * scale + (beta - rm_p * scale)
     if act == ops.ACT_RELU:
-        return torch.relu(pre)
-    if act == ops.ACT_PRELU:
-        return torch.where(pre > 0, pre, pre * slope)
-    return pre
+        pre = torch.relu(pre)
+    elif act == ops.ACT_PRELU:
+        pre = torch.where(pre > 0, pre, pre * slope)
+    return RoundTF32.apply(pre) if round_out else pre
 
 
 # ----------------------------------------------------------------------------------------------- pad + concat

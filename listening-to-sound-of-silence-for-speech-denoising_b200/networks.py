@@ -22,11 +22,13 @@ DILATIONS = [(1, 1), (1, 1), (1, 1), (2, 1), (4, 1), (8, 1), (16, 1), (32, 1),
 
 
 def _fast_eval(module, *tensors):
-    return (not module.training) and not (torch.is_grad_enabled() and any(t.requires_grad for t in tensors))
+    """Inference path (BN folded into the GEMM epilogue): eval mode with autograd off."""
+    return (not module.training) and not torch.is_grad_enabled()
 
 
 class _Block(nn.Module):
     """Common driver: conv (tap GEMM) -> BatchNorm -> activation over NHWC maps."""
+    round_out = True          # the block's output feeds another tensor-core GEMM: round it to TF32 where it is produced
 
     def _run(self, x, conv, bn, act, slope_mod, geom):
         slope = slope_mod.weight if slope_mod is not None else None
@@ -43,9 +45,10 @@ class _Block(nn.Module):
                 gamma, beta, rm = (torch.nn.functional.pad(t, pad) for t in (gamma, beta, rm))
                 rv = torch.nn.functional.pad(rv, pad, value=1.0)
             scale, shift = ops.bn_eval_coeffs(gamma.detach().contiguous(), beta.detach().contiguous(), rm.contiguous(), rv.contiguous(), bn.eps)
-            return L.conv_fused_eval(x, conv.weight.detach(), geom, scale, shift, act, slope.detach() if slope is not None else None)
+            return L.conv_fused_eval(x, conv.weight.detach(), geom, scale, shift, act, slope.detach() if slope is not None else None,
+                                     self.round_out)
         y = L.TapConv.apply(x, conv.weight, geom)
-        return L.bn_act(y, bn, act, slope, self.training)
+        return L.bn_act(y, bn, act, slope, self.training, self.round_out)
 
 
 class ConvBlock(_Block):
@@ -110,7 +113,7 @@ class UpConvBlock(_Block):
 
 def _to_nhwc(x):
     """(B, 2, 256, T) NCHW -> NHWC with channels zero-padded to 8."""
-    return ops.nchw_to_nhwc(x.contiguous().float(), 8)
+    return ops.round_tf32_(ops.nchw_to_nhwc(x.contiguous().float(), 8))
 
 
 class _NHWCInput(torch.autograd.Function):
@@ -139,6 +142,7 @@ class BiLSTM(nn.LSTM):
 def _make_enc(kernel_sizes, dilations, nf, outf):
     enc = [ConvBlock(2 if i == 0 else nf, nf, kernel_sizes[i], dilations[i]) for i in range(len(kernel_sizes))]
     enc.append(ConvBlock(nf, outf, (1, 1), (1, 1)))
+    enc[-1].round_out = False                                             # feeds the LSTM input projection (fp32 GEMM)
     return nn.Sequential(*enc)
 
 
@@ -233,7 +237,8 @@ class JointModel(nn.Module):
     def forward(self, x, n):
         xh, nh = _nhwc_in(x), _nhwc_in(n)
         n_pred_nhwc = self.stage1.forward_nhwc(nh, xh)
-        out = self.stage2.forward_nhwc(xh, n_pred_nhwc)
+        out = self.stage2.forward_nhwc(xh, L.RoundTF32.apply(n_pred_nhwc) if n_pred_nhwc.requires_grad else
+                                       ops.round_tf32_(n_pred_nhwc.clone()))
         return L.ToNCHW.apply(n_pred_nhwc, 2), out
 
 

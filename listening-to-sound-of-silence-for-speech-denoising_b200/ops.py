@@ -129,6 +129,14 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999
 
 # ----------------------------------------------------------------------------------------------- BatchNorm + activation
 ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
+ACT_ROUND_TF32 = 16          # OR into `act`: round the output to TF32 (it feeds a tensor-core GEMM)
+
+
+def round_tf32_(x):
+    """In-place round-to-nearest to TF32 (operands of the tcgen05 kind::tf32 GEMMs are otherwise truncated)."""
+    check(lib().sos_round_tf32(_p(x), x.numel(), _stream()), "sos_round_tf32")
+    _count()
+    return x
 
 
 def bn_train_forward(y, gamma, beta, running_mean, running_var, eps, momentum, act, slope):
@@ -159,7 +167,7 @@ def bn_train_backward(dz, y, stats, act, slope):
     partial = torch.empty(G * 3 * Cn, device=y.device, dtype=torch.float32)
     dy = torch.empty_like(y)
     out = torch.empty(4, Cn, device=y.device, dtype=torch.float32)             # dgamma, dbeta, m1, m2
-    dslope = torch.zeros(1, device=y.device, dtype=torch.float32) if act == ACT_PRELU else None
+    dslope = torch.zeros(1, device=y.device, dtype=torch.float32) if (act & 15) == ACT_PRELU else None
     H, W = y.shape[-3], y.shape[-2]
     sp = lambda i: C.c_void_p(stats[i].data_ptr())
     op = lambda i: C.c_void_p(out[i].data_ptr())

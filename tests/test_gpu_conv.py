@@ -77,9 +77,7 @@ def test_tapconv_fwd_bwd(cuda, case):
     dx = ops.nhwc_to_nchw(xd.grad, Cin).cpu()
     e_x = _rel(dx, x.grad)
     print(f"\n{case}: fwd {e_f:.2e} dgrad {e_x:.2e} wgrad {e_w:.2e}")
-    assert e_f < TOL, f"forward rel err {e_f}"
-    assert e_x < TOL, f"dgrad rel err {e_x}"
-    assert e_w < TOL, f"wgrad rel err {e_w}"
+    assert e_f < TOL and e_x < TOL and e_w < TOL, f"rel err: forward {e_f:.2e} dgrad {e_x:.2e} wgrad {e_w:.2e}"
 
 
 @pytest.mark.parametrize("plan", [0, 1, 2, 3])
