@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the two-stage denoising hot path (BASELINE.json metric: clips/sec, 2 s @ 16 kHz, fwd+bwd).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path, one rank per GPU (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port) on the host cores
+
+One "step" = BASELINE.json configs[1]: a batch of 32 synthetic 2 s clips per GPU through
+  4 x STFT (mixed, silent-interval-gated noise, clean, full noise)  ->  SID fwd+bwd (BCE)  ->  JointModel fwd+bwd (2 x MSE
+  through the cRM recovery)  ->  iSTFT of the recovered spectrogram  ->  fused Adam on both networks
+(+ one NCCL all-reduce of each flat gradient buffer when N > 1; per-GPU batch fixed = weak scaling).
+`value` is measured with the waveforms already resident in HBM; `e2e` repeats the measurement through the same public API
+with the step's inputs coming from pinned host memory and the losses + denoised waveforms read back every step.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+SR, LENGTH, FPS = 16000, 32000, 30.0
+SNRS = [-10, -7, -3, 0, 3, 7, 10]
+METRIC = "clips/sec (2 s @16 kHz) fwd+bwd"
+WORKLOAD = "batch=32 2 s clips per GPU, full STFT->SID->U-Net->iSTFT fwd+bwd training step (BASELINE configs[1])"
+
+
+# ----------------------------------------------------------------------------------------------- synthetic clips
+def synth_batch(batch, length=LENGTH, sr=SR, start=0):
+    """Deterministic noisy-speech clips (SURVEY.md 8d recipe, vectorised): harmonic 'speech' silenced on random silent
+    intervals, low-passed Gaussian noise, mixed at SNRS[i % 7] and normalised to max |mixed| = 0.5."""
+    from scipy.signal import lfilter
+    n_bits = int(round(length / sr * FPS))
+    ratio = sr / FPS
+    t = np.arange(length) / sr
+    out = {k: np.zeros((batch, length), np.float32) for k in ("mixed", "clean", "full_noise")}
+    bits = np.zeros((batch, n_bits), np.uint8)
+    for i in range(batch):
+        rng = np.random.default_rng(1234 + start + i)
+        b, state = [], int(rng.integers(0, 2))
+        while len(b) < n_bits:
+            b.extend([state] * int(rng.integers(3, 21)))
+            state ^= 1
+        b = np.array(b[:n_bits], np.uint8)
+        bits[i] = b
+        mask = np.zeros(length)
+        for j in range(n_bits):
+            if b[j] == 0:
+                lo, hi = int(j * ratio), int((j + 1) * ratio - 1)
+                mask[lo:hi + (1 if j + 1 < n_bits and b[j + 1] == 0 else 0)] = 1
+        f0 = rng.uniform(100, 250)
+        speech = sum(np.sin(2 * np.pi * f0 * h * t + rng.uniform(0, 2 * np.pi)) / h for h in range(1, 6))
+        speech = speech * 0.5 * (1 - np.cos(2 * np.pi * 4.0 * t)) * (1 - mask)
+        noise = lfilter([0.05], [1, -0.95], rng.standard_normal(length))
+        sp, snr = np.sum(speech ** 2), SNRS[(start + i) % 7]
+        if sp > 0:
+            noise = noise * np.sqrt(sp / 10 ** (snr / 10)) / (np.sqrt(np.sum(noise ** 2)) + 1e-30)
+        mixed = speech + noise
+        scale = np.max(np.abs(mixed)) / 0.5
+        out["mixed"][i], out["clean"][i], out["full_noise"][i] = mixed / scale, speech / scale, noise / scale
+    out["bits"] = bits
+    out["label"] = bits.astype(np.float32)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        try:
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                                  "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.proc = p
+        for line in p.stdout:
+            if self.stop_flag:
+                break
+            self.samples.append([c.strip() for c in line.split(",")])
+        p.kill()
+
+    def summary(self):
+        self.stop_flag = True
+        if hasattr(self, "proc"):
+            self.proc.kill()
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(s) > 3 + j and s[3 + j].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.samples[0][1]), "power_w_max": max(float(s[2]) for s in self.samples),
+                "samples": len(sm), "reasons": reasons}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm (CPU)
+def cpu_step_factory(batch, length=LENGTH):
+    """The reference algorithm on the host cores through the CPU oracle (a port: /root/reference does not travel to the
+    GPU box): numpy/torch STFT x4 -> SID fwd+bwd -> Joint fwd+bwd -> iSTFT -> Adam.  Returns (step_fn, n_clips)."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import nets, transform as otf
+    from oracle.gating import bits_to_sample_mask
+    torch.set_num_threads(os.cpu_count() or 1)
+    data = synth_batch(batch, length)
+    sid_sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in nets.synth_state_dict(nets.sid_shapes(), 3).items()}
+    jt_sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in nets.synth_state_dict(nets.joint_shapes(), 4).items()}
+    params = [v for v in list(sid_sd.values()) + list(jt_sd.values()) if v.requires_grad]
+    opt = torch.optim.Adam(params, 1e-3)
+    ratio = SR / FPS
+    bit_strings = ["".join(str(int(b)) for b in row) for row in data["bits"]]
+
+    def step():
+        masks = np.stack([bits_to_sample_mask(length, ratio, b) for b in bit_strings]).astype(np.float32)
+        mixed = torch.tensor(otf.stft_batch(data["mixed"]))
+        noise = torch.tensor(otf.stft_batch(data["mixed"] * masks))
+        clean = torch.tensor(otf.stft_batch(data["clean"]))
+        full = torch.tensor(otf.stft_batch(data["full_noise"]))
+        opt.zero_grad()
+        logits = nets.sid_forward(sid_sd, mixed, data["label"].shape[1], training=True)
+        l0 = F.binary_cross_entropy_with_logits(logits, torch.tensor(data["label"]))
+        l0.backward()
+        n_pred, mask = nets.joint_forward(jt_sd, mixed, noise, training=True)
+        rec = otf.batch_fast_icRM_sigmoid(mixed, mask)
+        l1, l2 = F.mse_loss(n_pred, full), F.mse_loss(rec, clean)
+        (l1 + l2).backward()
+        opt.step()
+        otf.istft_batch(rec.detach().numpy())
+        return float(l0.detach()), float(l1.detach()), float(l2.detach())
+
+    return step, batch
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = args.ref_batch
+    step, n = cpu_step_factory(batch)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    cores = os.cpu_count() or 1
+    sample = f"{batch} clips per step (same STFT->SID->Joint->iSTFT->Adam fwd+bwd step, BatchNorm over {batch} clips), {args.steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ----------------------------------------------------------------------------------------------- this repo's arm (GPU)
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import sos_b200
+    from sos_b200 import _lib, agent as ag, ops, transform
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the sos_b200 hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ops.init()
+    B = args.batch
+    ratio = SR / FPS
+
+    torch.manual_seed(0)
+    sid = ag.SIDAgent(ag.default_config(model="sid"))
+    torch.manual_seed(1)
+    joint = ag.MyAgent(ag.default_config(model="joint", sr=SR, fps=FPS))
+
+    host = synth_batch(B, LENGTH, SR, start=rank * B)
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in pinned.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+    out_host = {"wave": torch.empty(B, 158 * (LENGTH // 158), dtype=torch.float32).pin_memory(), "loss": torch.empty(3, dtype=torch.float32).pin_memory()}
+    d2h_bytes = sum(v.numel() * v.element_size() for v in out_host.values())
+
+    def step(src, e2e):
+        d = {k: v.to(dev, non_blocking=True) for k, v in src.items()} if e2e else src
+        mixed = transform.stft_batch(d["mixed"])
+        noise = transform.stft_batch(d["mixed"], d["bits"], ratio, 1)
+        clean = transform.stft_batch(d["clean"])
+        full = transform.stft_batch(d["full_noise"])
+        _, l_sid = sid.train_func({"audio": mixed, "label": d["label"]})
+        _, l_jt = joint.train_func({"mixed": mixed, "noise": noise, "clean": clean, "full_noise": full})
+        wave = transform.istft_batch(joint.last_rec.detach())
+        if e2e:
+            out_host["loss"].copy_(torch.stack([l_sid["bce"].detach(), l_jt["stage1"].detach(), l_jt["stage2"].detach()]), non_blocking=True)
+            out_host["wave"].copy_(wave, non_blocking=True)
+            torch.cuda.current_stream().synchronize()          # the user holds the step's result before the next step
+        return wave
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(src, e2e, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(src, e2e)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident, False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ops.profile_start()
+    n0 = _lib.launch_count
+    ms = timed(resident, False, args.steps)
+    launches = _lib.launch_count - n0
+    prof = ops.profile_stop()
+    clocks = sampler.summary() if sampler else None
+    step(pinned, True)
+    ms_e2e = timed(pinned, True, args.steps)
+    clips = world * B * args.steps
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        peak_src = "measured (MEASURED_PEAKS.json, sustained bf16 cuBLAS)" if peaks else "fallback (B200_PROFILING.md)"
+        # cuBLAS TF32 on the same box, for scale: the conv kernels issue tcgen05 kind::tf32, whose hardware peak is half of bf16
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(8192, 8192, device=dev)
+        b = torch.randn(8192, 8192, device=dev)
+        for _ in range(3):
+            a @ b
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(10):
+            a @ b
+        t1.record()
+        torch.cuda.synchronize()
+        tf32_peak = 10 * 2 * 8192 ** 3 / (t0.elapsed_time(t1) * 1e-3) / 1e12
+        torch.backends.cuda.matmul.allow_tf32 = False
+        del a, b
+        kern = {}
+        for name, rec in prof.items():
+            if rec["ms"] > 0:
+                kern[name] = {"launches": rec["n"], "ms_per_step": rec["ms"] / args.steps, "avg_launch_us": 1e3 * rec["ms"] / max(rec["n"], 1),
+                              "tflops": rec["flops"] / (rec["ms"] * 1e-3) / 1e12 if rec["flops"] else None,
+                              "gbs": rec["bytes"] / (rec["ms"] * 1e-3) / 1e9 if rec["bytes"] else None}
+        dom = max((k for k in kern if kern[k]["tflops"]), key=lambda k: kern[k]["ms_per_step"], default=None)
+        roofline = None
+        if dom:
+            ach = kern[dom]["tflops"]
+            roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
+                        "traffic": None, "peak_source": peak_src, "mma_kind": "tcgen05 kind::tf32 (hardware peak = 1/2 bf16)",
+                        "tf32_cublas_tflops_measured_here": tf32_peak, "frac_of_tf32_cublas": ach / tf32_peak,
+                        "share_of_step": kern[dom]["ms_per_step"] / (ms / args.steps)}
+        if "stft" in kern and kern["stft"]["gbs"]:
+            kern["stft"]["hbm_frac"] = kern["stft"]["gbs"] / hbm_peak
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cstep, n = cpu_step_factory(args.ref_batch)
+            t0 = time.perf_counter()
+            cstep()
+            dt = time.perf_counter() - t0
+            cpu = {"value": n / dt, "unit": "clips/s", "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": f"one {n}-clip step of the same workload (no warm-up), {dt:.1f} s"}
+        print(json.dumps({
+            "metric": METRIC, "value": clips / (ms * 1e-3), "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": world * B, "samples_per_clip": LENGTH, "frames": 1 + LENGTH // 158,
+                       "parallelism": f"dp{world} (NCCL all-reduce of the flat gradient buffers)" if world > 1 else "single GPU",
+                       "l2": "no explicit flush: the step's activation working set (tens of GB) is far larger than the 126 MB L2"},
+            "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": "clips/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kern, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sos_b200", choices=["sos_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
+    ap.add_argument("--ref-batch", type=int, default=2, help="clips per step of the CPU arm (a bounded sample of the workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

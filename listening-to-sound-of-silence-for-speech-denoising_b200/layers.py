@@ -17,13 +17,39 @@ def _round8(c):
     return (c + 7) // 8 * 8
 
 
+# ----------------------------------------------------------------------------------------------- arithmetic mode
+# Default: every convolution is ONE tensor-core pass over TF32-rounded operands (the contract cuDNN applies to the
+# reference's nn.Conv2d on Ampere+ GPUs).  Precise mode (verification / fp32-parity runs, 3x the tensor work): operands are
+# split x = hi + lo with hi = tf32(x), lo = tf32(x - hi), and a convolution is hi*hi + lo*hi + hi*lo (error ~2^-21, i.e.
+# fp32-grade), forward, data gradient and weight gradient alike; producers then do not round.
+_PRECISE = False
+
+
+def set_precise(flag):
+    global _PRECISE
+    old, _PRECISE = _PRECISE, bool(flag)
+    return old
+
+
+def precise():
+    return _PRECISE
+
+
+def _split(t):
+    hi = ops.round_tf32_(t.detach().clone().contiguous())
+    lo = ops.round_tf32_((t.detach() - hi).contiguous())
+    return hi, lo
+
+
 # ----------------------------------------------------------------------------------------------- geometry
 class ConvGeom:
     """Tap lists of one convolution in the three roles (forward, data gradient, weight gradient)."""
 
-    def __init__(self, kind, kh, kw, dh=1, dw=1, stride=1):
+    def __init__(self, kind, kh, kw, dh=1, dw=1, stride=1, round_dy=False):
         assert kind in ("zero", "valid", "convT")
         self.kind, self.kh, self.kw, self.dh, self.dw, self.stride = kind, kh, kw, dh, dw, stride
+        # True when the output gradient does not come from a BatchNorm backward kernel (which rounds it to TF32 itself)
+        self.round_dy = round_dy
         if kind == "convT":
             assert (kh, kw, stride) == (3, 3, 2)
         taps = [(a, b) for a in range(kh) for b in range(kw)]
@@ -60,7 +86,7 @@ def _conv_forward(x, w, g, epi=None):
     if g.kind != "convT":
         Cout = w.shape[0]
         wk = _pack_fwd(w, g.taps, cin_p)
-        return ops.conv_tc(x, wk, [o[0] for o in g.off], [o[1] for o in g.off], Cout, OH, OW, g.stride, **kw)
+        return ops.conv_tc(x, wk, [o[0] for o in g.off], [o[1] for o in g.off], Cout, OH, OW, g.stride, k_real=w.shape[1], **kw)
     # ConvTranspose2d(k3, s2, p1, output_padding=1): oy = 2*iy - 1 + ky  ->  four sub-pixel convolutions
     Cout = w.shape[1]
     wc = w.permute(1, 0, 2, 3)                                             # (Cout, Cin, ky, kx)
@@ -72,7 +98,7 @@ def _conv_forward(x, w, g, epi=None):
             taps = [(ky, kx) for ky, _ in ph_taps[py] for kx, _ in ph_taps[px]]
             offs = [(oy, ox) for _, oy in ph_taps[py] for _, ox in ph_taps[px]]
             wk = _pack_fwd(wc, taps, cin_p)
-            ops.conv_tc(x, wk, [o[0] for o in offs], [o[1] for o in offs], Cout, H, W, 1, y=y, lattice=(2, 2, py, px), **kw)
+            ops.conv_tc(x, wk, [o[0] for o in offs], [o[1] for o in offs], Cout, H, W, 1, y=y, lattice=(2, 2, py, px), k_real=w.shape[0], **kw)
     return y
 
 
@@ -84,12 +110,12 @@ def _conv_dgrad(dy, w, g, x_shape):
         # dx[iy] = sum_k dy[2*iy - 1 + ky] w[ci][co][ky]: a stride-2 tap conv over dy
         Cin = w.shape[0]
         wk = _pack_fwd(w, g.taps, cout_p)                                  # rows ci, k = t*cout_p + co
-        return ops.conv_tc(dy, wk, [o[0] for o in g.off], [o[1] for o in g.off], Cin, H, W, 2)
+        return ops.conv_tc(dy, wk, [o[0] for o in g.off], [o[1] for o in g.off], Cin, H, W, 2, k_real=w.shape[1], tag="conv_dgrad")
     Cin = w.shape[1]
     wt = w.permute(1, 0, 2, 3)                                             # (Cin, Cout, kh, kw)
     if g.stride == 1:
         wk = _pack_fwd(wt, g.taps, cout_p)
-        return ops.conv_tc(dy, wk, [-o[0] for o in g.off], [-o[1] for o in g.off], Cin, H, W, 1)
+        return ops.conv_tc(dy, wk, [-o[0] for o in g.off], [-o[1] for o in g.off], Cin, H, W, 1, k_real=w.shape[0], tag="conv_dgrad")
     # stride 2: four output phases of the input lattice
     dx = torch.empty(N, H, W, _round8(Cin), device=dy.device, dtype=torch.float32)
     assert _round8(Cin) == Cin
@@ -102,7 +128,7 @@ def _conv_dgrad(dy, w, g, x_shape):
                 continue
             wk = _pack_fwd(wt, [t for t, _ in sel], cout_p)
             ops.conv_tc(dy, wk, [(py - o[0]) // 2 for _, o in sel], [(px - o[1]) // 2 for _, o in sel], Cin, oh, ow, 1, y=dx,
-                        lattice=(2, 2, py, px))
+                        lattice=(2, 2, py, px), k_real=w.shape[0], tag="conv_dgrad")
     return dx
 
 
@@ -111,12 +137,12 @@ def _conv_wgrad(x, dy, w, g):
     if g.kind == "convT":
         Cin, Cout = w.shape[0], w.shape[1]
         # roles swapped: "input" = dy (2H x 2W), "output grad" = x (H x W), stride 2
-        dwt = ops.conv_wgrad(dy, x, [o[0] for o in g.off], [o[1] for o in g.off], x.shape[3], x.shape[1], x.shape[2], 2)
+        dwt = ops.conv_wgrad(dy, x, [o[0] for o in g.off], [o[1] for o in g.off], x.shape[3], x.shape[1], x.shape[2], 2, real=(Cout, Cin))
         # dwt (ntaps, Cin_p, Cout_p) -> (Cin, Cout, kh, kw)
         return dwt[:, :Cin, :Cout].permute(1, 2, 0).reshape(Cin, Cout, g.kh, g.kw).contiguous()
     Cout, Cin = w.shape[0], w.shape[1]
     OH, OW = dy.shape[1], dy.shape[2]
-    dwt = ops.conv_wgrad(x, dy, [o[0] for o in g.off], [o[1] for o in g.off], dy.shape[3], OH, OW, g.stride)
+    dwt = ops.conv_wgrad(x, dy, [o[0] for o in g.off], [o[1] for o in g.off], dy.shape[3], OH, OW, g.stride, real=(Cin, Cout))
     return dwt[:, :Cout, :Cin].permute(1, 2, 0).reshape(Cout, Cin, g.kh, g.kw).contiguous()
 
 
@@ -125,6 +151,10 @@ class TapConv(torch.autograd.Function):
     def forward(ctx, x, w, g):
         ctx.g = g
         ctx.save_for_backward(x, w)
+        ctx.precise = _PRECISE
+        if _PRECISE:
+            (xh, xl), (wh, wl) = _split(x), _split(w)
+            return _conv_forward(xh, wh, g) + _conv_forward(xl, wh, g) + _conv_forward(xh, wl, g)
         return _conv_forward(x, w, g)
 
     @staticmethod
@@ -132,6 +162,16 @@ class TapConv(torch.autograd.Function):
         x, w = ctx.saved_tensors
         g = ctx.g
         dy = dy.contiguous()
+        if ctx.precise:
+            (xh, xl), (wh, wl), (dh, dl) = _split(x), _split(w), _split(dy)
+            dx = dw = None
+            if ctx.needs_input_grad[0]:
+                dx = _conv_dgrad(dh, wh, g, x.shape) + _conv_dgrad(dl, wh, g, x.shape) + _conv_dgrad(dh, wl, g, x.shape)
+            if ctx.needs_input_grad[1]:
+                dw = _conv_wgrad(xh, dh, w, g) + _conv_wgrad(xl, dh, w, g) + _conv_wgrad(xh, dl, w, g)
+            return dx, dw, None
+        if g.round_dy:
+            dy = ops.round_tf32_(dy.clone())
         dx = _conv_dgrad(dy, w, g, x.shape) if ctx.needs_input_grad[0] else None
         dw = _conv_wgrad(x, dy, w, g) if ctx.needs_input_grad[1] else None
         return dx, dw, None
@@ -143,24 +183,24 @@ def conv_fused_eval(x, w, g, scale, shift, act, slope, round_out=True):
 
 
 class RoundTF32(torch.autograd.Function):
-    """Identity up to TF32 rounding of the value (forward) and of the gradient (backward): marks a tensor that feeds a
-    tensor-core GEMM but was produced by a plain tensor expression."""
+    """Identity up to TF32 rounding of the value (straight-through gradient): marks a tensor that feeds a tensor-core GEMM
+    but was produced by a plain tensor expression."""
 
     @staticmethod
     def forward(ctx, x):
-        return ops.round_tf32_(x.detach().clone().contiguous())
+        return x.detach().clone() if _PRECISE else ops.round_tf32_(x.detach().clone().contiguous())
 
     @staticmethod
     def backward(ctx, g):
-        return ops.round_tf32_(g.clone().contiguous())
+        return g
 
 
 # ----------------------------------------------------------------------------------------------- BatchNorm + act
 class BNActTrain(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y, gamma, beta, slope, running_mean, running_var, eps, momentum, act):
+    def forward(ctx, y, gamma, beta, slope, running_mean, running_var, eps, momentum, act, round_grad=True):
         z, stats = ops.bn_train_forward(y, gamma, beta, running_mean, running_var, eps, momentum, act, slope)
-        ctx.act = act
+        ctx.act = (act & 15) | (ops.ACT_ROUND_TF32 if round_grad else 0)
         ctx.save_for_backward(y, stats, slope if slope is not None else torch.empty(0))
         return z
 
@@ -168,13 +208,15 @@ class BNActTrain(torch.autograd.Function):
     def backward(ctx, dz):
         y, stats, slope = ctx.saved_tensors
         slope = slope if slope.numel() else None
-        dy, dgamma, dbeta, dslope = ops.bn_train_backward(dz.contiguous(), y, stats, ctx.act | ops.ACT_ROUND_TF32, slope)
-        return dy, dgamma, dbeta, dslope, None, None, None, None, None
+        dy, dgamma, dbeta, dslope = ops.bn_train_backward(dz.contiguous(), y, stats, ctx.act, slope)
+        return dy, dgamma, dbeta, dslope, None, None, None, None, None, None
 
 
-def bn_act(y, bn, act, slope, training, round_out=True):
+def bn_act(y, bn, act, slope, training, round_out=True, round_grad=True):
     """y NHWC with C = round8(bn.num_features).  bn: nn.BatchNorm2d holding the reference-named parameters."""
     Cp, Cn = y.shape[3], bn.num_features
+    if _PRECISE:
+        round_out = round_grad = False
     gamma, beta, rm, rv = bn.weight, bn.bias, bn.running_mean, bn.running_var
     if Cp != Cn:                                                          # padded channels: gamma = beta = 0 -> z = 0
         pad = (0, Cp - Cn)
@@ -183,7 +225,8 @@ def bn_act(y, bn, act, slope, training, round_out=True):
     else:
         rm_p, rv_p = rm, rv
     if training:
-        z = BNActTrain.apply(y, gamma, beta, slope, rm_p, rv_p, bn.eps, bn.momentum, act | (ops.ACT_ROUND_TF32 if round_out else 0))
+        z = BNActTrain.apply(y, gamma, beta, slope, rm_p, rv_p, bn.eps, bn.momentum, act | (ops.ACT_ROUND_TF32 if round_out else 0),
+                             round_grad)
         if Cp != Cn:
             with torch.no_grad():
                 rm.copy_(rm_p[:Cn])

@@ -23,7 +23,7 @@ DILATIONS = [(1, 1), (1, 1), (1, 1), (2, 1), (4, 1), (8, 1), (16, 1), (32, 1),
 
 def _fast_eval(module, *tensors):
     """Inference path (BN folded into the GEMM epilogue): eval mode with autograd off."""
-    return (not module.training) and not torch.is_grad_enabled()
+    return (not module.training) and not torch.is_grad_enabled() and not L.precise()
 
 
 class _Block(nn.Module):
@@ -83,7 +83,7 @@ class DownConvBlock(_Block):
             block.append(nn.PReLU())
         self.block = nn.Sequential(*block)
         self.has_norm = norm_fn == 'bn'
-        self.geom = L.ConvGeom("valid", kernel_size, kernel_size, dilation, dilation, stride)
+        self.geom = L.ConvGeom("valid", kernel_size, kernel_size, dilation, dilation, stride, round_dy=norm_fn != 'bn')
 
     def forward(self, *srcs, size=None):
         H, W = size if size is not None else (srcs[0].shape[1], srcs[0].shape[2])
@@ -113,7 +113,8 @@ class UpConvBlock(_Block):
 
 def _to_nhwc(x):
     """(B, 2, 256, T) NCHW -> NHWC with channels zero-padded to 8."""
-    return ops.round_tf32_(ops.nchw_to_nhwc(x.contiguous().float(), 8))
+    y = ops.nchw_to_nhwc(x.contiguous().float(), 8)
+    return y if L.precise() else ops.round_tf32_(y)
 
 
 class _NHWCInput(torch.autograd.Function):
@@ -237,8 +238,7 @@ class JointModel(nn.Module):
     def forward(self, x, n):
         xh, nh = _nhwc_in(x), _nhwc_in(n)
         n_pred_nhwc = self.stage1.forward_nhwc(nh, xh)
-        out = self.stage2.forward_nhwc(xh, L.RoundTF32.apply(n_pred_nhwc) if n_pred_nhwc.requires_grad else
-                                       ops.round_tf32_(n_pred_nhwc.clone()))
+        out = self.stage2.forward_nhwc(xh, L.RoundTF32.apply(n_pred_nhwc))
         return L.ToNCHW.apply(n_pred_nhwc, 2), out
 
 

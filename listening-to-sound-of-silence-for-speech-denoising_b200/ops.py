@@ -29,6 +29,47 @@ def _count(n=1):
     _lib.launch_count += n
 
 
+# ----------------------------------------------------------------------------------------------- per-kernel timing (bench.py)
+_prof = None
+
+
+def profile_start():
+    """Start recording a CUDA event pair (on the launching stream) around every tensor-core / transform launch."""
+    global _prof
+    _prof = []
+
+
+def _pb():
+    if _prof is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _pe(name, e0, flops=0.0, nbytes=0.0):
+    if e0 is None:
+        return
+    e1 = torch.cuda.Event(enable_timing=True)
+    e1.record()
+    _prof.append((name, e0, e1, flops, nbytes))
+
+
+def profile_stop():
+    """-> {kernel family: {"n": launches, "ms": device time, "flops": algorithmic FLOPs, "bytes": algorithmic bytes}}"""
+    global _prof
+    rec, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1, fl, by in rec:
+        d = out.setdefault(name, {"n": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        d["n"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["flops"] += fl
+        d["bytes"] += by
+    return out
+
+
 def init():
     if not torch.cuda.is_available():
         raise _lib.SosError("sos_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -52,12 +93,14 @@ def stft(wave, bits=None, ratio=None, gate_mode=0):
     B, L = wave.shape
     T = 1 + L // 158
     out = torch.empty(B, 2, 256, T, device=wave.device, dtype=torch.float32)
+    e0 = _pb()
     if gate_mode:
         nb = bits.shape[1]
         flo = torch.tensor(frame_lo_table(nb, ratio), dtype=torch.int32, device=wave.device)
         check(lib().sos_stft_forward(_p(wave), B, L, _p(out), _p(bits), nb, _p(flo), float(ratio), gate_mode, _stream()), "sos_stft_forward")
     else:
         check(lib().sos_stft_forward(_p(wave), B, L, _p(out), None, 0, None, 0.0, 0, _stream()), "sos_stft_forward")
+    _pe("stft", e0, 0.0, 4.0 * B * L + 4.0 * out.numel())
     _count()
     return out
 
@@ -68,7 +111,9 @@ def istft(spec, crm=None):
     assert F == 256
     ws = torch.empty(B * T * 400, device=spec.device, dtype=torch.float32)
     out = torch.empty(B, 158 * (T - 1), device=spec.device, dtype=torch.float32)
+    e0 = _pb()
     check(lib().sos_istft_forward(_p(spec), _p(crm), B, T, _p(ws), _p(out), _stream()), "sos_istft_forward")
+    _pe("istft", e0, 0.0, 4.0 * spec.numel() * (2 if crm is not None else 1) + 4.0 * out.numel())
     _count(2)
     return out
 
@@ -248,7 +293,7 @@ def _i32arr(v):
 
 
 def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lattice=(1, 1, 0, 0), epi_scale=None, epi_shift=None,
-            act=0, slope=None, force_plan=-1, plan_out=None):
+            act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag="conv_fwd"):
     """Tap-list implicit GEMM on tcgen05 (see include/sos_b200.h: sos_conv2d_tc).
 
     x (N, H, W, Cin) NHWC; wk (Cout, ntaps*Cin); y (N, YH, YW, Cy) is allocated when None (dense, Cy = Cout
@@ -278,14 +323,16 @@ def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lat
     po = (_I32 * 8)() if plan_out is not None else None
     a.plan_out = po
     assert x.is_contiguous() and wk.is_contiguous() and y.is_contiguous()
+    e0 = _pb()
     check(lib().sos_conv2d_tc(C.byref(a), _stream()), "sos_conv2d_tc")
+    _pe(tag, e0, 2.0 * N * OH * OW * Cout * (k_real or Cin) * ntaps)
     _count()
     if plan_out is not None:
         plan_out[:] = list(po)
     return y
 
 
-def conv_wgrad(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_plan=-1, plan_out=None):
+def conv_wgrad(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_plan=-1, plan_out=None, real=None):
     """dw[t][co][ci] = sum_pixels dy[p][dy_coff+co] * x[p*stride + off_t][ci]  ->  (ntaps, Cout, Cin)."""
     N, H, W, Cin = x.shape
     ntaps = len(tap_dh)
@@ -302,7 +349,10 @@ def conv_wgrad(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_p
     po = (_I32 * 8)() if plan_out is not None else None
     a.plan_out = po
     assert x.is_contiguous() and dy.is_contiguous()
+    e0 = _pb()
     check(lib().sos_conv2d_wgrad(C.byref(a), _stream()), "sos_conv2d_wgrad")
+    ci_r, co_r = real or (Cin, Cout)
+    _pe("conv_wgrad", e0, 2.0 * N * OH * OW * co_r * ci_r * ntaps)
     _count()
     if plan_out is not None:
         plan_out[:] = list(po)

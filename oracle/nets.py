@@ -20,6 +20,82 @@ DL = [(1, 1), (1, 1), (1, 1), (2, 1), (4, 1), (8, 1), (16, 1), (32, 1),
 SID_KS, SID_DL = KS[:11], DL[:11]                          # M1/networks.py:91-92
 BN_EPS, BN_MOM = 1e-5, 0.1
 
+# ---------------------------------------------------------------------------
+# Arithmetic contract of the convolutions.
+#   TF32 = False : plain fp32 (what the golden vectors from the reference hold)
+#   TF32 = True  : "TF32 contract" -- every convolution multiplies operands rounded
+#                  (to nearest, ties away: PTX cvt.rna.tf32.f32) to a 10-bit mantissa and
+#                  accumulates in fp32, forward AND backward (data and weight gradients
+#                  see the rounded output gradient).  This is what the tcgen05
+#                  kind::tf32 kernels compute, and what PyTorch's own cuDNN path does
+#                  for the reference's nn.Conv2d on Ampere+ GPUs (allow_tf32 = True).
+# ---------------------------------------------------------------------------
+TF32 = False
+
+
+class tf32_contract(object):
+    def __enter__(self):
+        global TF32
+        self.old, TF32 = TF32, True
+
+    def __exit__(self, *a):
+        global TF32
+        TF32 = self.old
+
+
+def round_tf32(t):
+    """fp32 -> nearest TF32 (ties away from zero), kept in fp32."""
+    i = t.detach().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class _TF32Conv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, stride, dilation, padding):
+        xr, wr = round_tf32(x), round_tf32(w)
+        ctx.save_for_backward(xr, wr)
+        ctx.cfg = (stride, dilation, padding)
+        return F.conv2d(xr, wr, None, stride, padding, dilation)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xr, wr = ctx.saved_tensors
+        stride, dilation, padding = ctx.cfg
+        dyr = round_tf32(dy)
+        dx = torch.nn.grad.conv2d_input(xr.shape, wr, dyr, stride, padding, dilation)
+        dw = torch.nn.grad.conv2d_weight(xr, wr.shape, dyr, stride, padding, dilation)
+        return dx, dw, None, None, None
+
+
+class _TF32ConvT(torch.autograd.Function):
+    """ConvTranspose2d(k3, s2, p1, output_padding=1) under the same contract."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        xr, wr = round_tf32(x), round_tf32(w)
+        ctx.save_for_backward(xr, wr)
+        return F.conv_transpose2d(xr, wr, None, 2, 1, 1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xr, wr = ctx.saved_tensors
+        dyr = round_tf32(dy)
+        dx = F.conv2d(dyr, wr, None, 2, 1)                      # the transposed conv is the data gradient of this conv
+        dw = torch.nn.grad.conv2d_weight(dyr, wr.shape, xr, 2, 1)
+        return dx, dw
+
+
+def _conv(x, w, stride=1, padding=0, dilation=1):
+    if TF32:
+        return _TF32Conv.apply(x, w, stride, dilation, padding)
+    return F.conv2d(x, w, None, stride, padding, dilation)
+
+
+def _convT(x, w):
+    if TF32:
+        return _TF32ConvT.apply(x, w)
+    return F.conv_transpose2d(x, w, None, 2, 1, 1)
+
 
 def _bn(sd, pfx, y, training, stats_out):
     rm, rv = sd[pfx + ".running_mean"], sd[pfx + ".running_var"]
@@ -37,7 +113,7 @@ def _bn(sd, pfx, y, training, stats_out):
 def _zero_block(sd, pfx, x, k, d, training, stats_out):
     """Conv(bias=False, zero 'same' pad) + BN + ReLU  (ConvBlock / Conv2dBlock)."""
     pad = ((k[0] - 1) // 2 * d[0], (k[1] - 1) // 2 * d[1])
-    y = F.conv2d(x, sd[pfx + ".block.0.weight"], None, 1, pad, d)
+    y = _conv(x, sd[pfx + ".block.0.weight"], 1, pad, d)
     return F.relu(_bn(sd, pfx + ".block.1", y, training, stats_out))
 
 
@@ -84,15 +160,15 @@ def _down(sd, pfx, x, k, stride, d, training, stats_out, norm=True):
     p = (k - 1) // 2 * d
     x = F.pad(x, (p, p, p, p), mode="reflect")
     if not norm:
-        return F.conv2d(x, sd[pfx + ".block.1.weight"], sd[pfx + ".block.1.bias"], stride, 0, d)
-    y = F.conv2d(x, sd[pfx + ".block.1.weight"], None, stride, 0, d)
+        return _conv(x, sd[pfx + ".block.1.weight"], stride, 0, d) + sd[pfx + ".block.1.bias"].view(1, -1, 1, 1)
+    y = _conv(x, sd[pfx + ".block.1.weight"], stride, 0, d)
     return F.prelu(_bn(sd, pfx + ".block.2", y, training, stats_out), sd[pfx + ".block.3.weight"])
 
 
 def _up(sd, pfx, x, training, stats_out):
     """ConvTranspose2d(k3,s2,p1,output_padding=1) + BN + PReLU (UpConvBlock :120-149;
     `dilation` lands in the output_padding slot, :130)."""
-    y = F.conv_transpose2d(x, sd[pfx + ".block.0.weight"], None, 2, 1, 1)
+    y = _convT(x, sd[pfx + ".block.0.weight"])
     return F.prelu(_bn(sd, pfx + ".block.1", y, training, stats_out), sd[pfx + ".block.2.weight"])
 
 

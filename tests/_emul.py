@@ -13,7 +13,7 @@ def _gather(x, dh, dw, OH, OW, stride):
 
 
 def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lattice=(1, 1, 0, 0), epi_scale=None, epi_shift=None,
-            act=0, slope=None, force_plan=-1, plan_out=None):
+            act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag=None):
     N, H, W, Cin = x.shape
     osh, osw, oph, opw = lattice
     if y is None:
@@ -31,7 +31,7 @@ def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lat
     return y
 
 
-def conv_wgrad(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_plan=-1, plan_out=None):
+def conv_wgrad(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_plan=-1, plan_out=None, real=None):
     N, H, W, Cin = x.shape
     dw_ = torch.zeros(len(tap_dh), Cout, Cin)
     d = dy[..., dy_coff:dy_coff + Cout].reshape(-1, Cout)

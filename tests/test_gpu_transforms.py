@@ -151,7 +151,7 @@ def test_bn_act_train(cuda, act, C):
         bn2.bias.copy_(bn.bias.detach())
     slope = torch.nn.Parameter(torch.tensor([0.25], device=cuda)) if act == 2 else None
     yd = ops.nchw_to_nhwc(y.detach().to(cuda), C).requires_grad_(True)
-    z = L.bn_act(yd, bn2, act, slope, True)
+    z = L.bn_act(yd, bn2, act, slope, True, round_out=False, round_grad=False)
     z.backward(ops.nchw_to_nhwc(go.to(cuda), C))
     assert float((ops.nhwc_to_nchw(z, C).cpu() - ref.detach()).abs().max()) < 2e-5
     assert float((ops.nhwc_to_nchw(yd.grad, C).cpu() - y.grad).abs().max()) < 1e-4 * float(y.grad.abs().max() + 1)
