@@ -28,6 +28,7 @@ using namespace ptx;
 using namespace tc;
 
 constexpr int kThreadsTc = 192;
+constexpr int kMaxProg = 144;             // entries of the deduplicated MMA programs
 struct alignas(64) TcParams {
   CUtensorMap mapA, mapB, mapD;
   int total_ctiles, n_nblk, tiles_fast_g, tiles_slow, n_phase;
@@ -43,6 +44,12 @@ struct alignas(64) TcParams {
   int act;                       // 0 none, 1 relu, 2 prelu
   const float* slope;
   TapGroup groups[kMaxGroups];
+  // MMA program: one entry per tcgen05.mma of a pipeline stage (same for every tile / channel chunk; tap groups with the
+  // same structure share one program): x = A descriptor address delta (16-byte units), y = B delta, z = accumulator column
+  // offset, w = 1 for the first MMA of a sub-tile's k loop.  Keeps the single issuing thread at a handful of instructions
+  // per MMA (one 24/48-cycle MMA per 8 fp32 of K leaves no room for address arithmetic).
+  int16_t prog0[kMaxGroups], prog_n[kMaxGroups];
+  uint4 prog[kMaxProg];
 };
 
 struct TileCoord { int nb, tfg, ts, ph, n; };
@@ -100,29 +107,29 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int ct = blockIdx.x; ct < p.total_ctiles; ct += gridDim.x) {
-        const TileCoord tc = decode_tile(p, ct);
-        for (int g = 0; g < p.n_groups; ++g) {
-          const TapGroup& grp = p.groups[g];
-          const uint32_t tx_bytes = (uint32_t)p.S * p.a_box_bytes + (uint32_t)grp.n_sub * (p.N * p.cbe * 4);
-          for (int c = 0; c < p.n_chunks; ++c) {
-            mbar_wait(empty_bar(stage), phase ^ 1, 100);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int ct = blockIdx.x; ct < p.total_ctiles; ct += gridDim.x) {
+      const TileCoord tc = decode_tile(p, ct);
+      const int fast_t = tc.tfg * p.S * p.FB * p.stride, slow_t = tc.ts * p.SB * p.stride, wrow = tc.nb * p.N;
+      for (int g = 0; g < p.n_groups; ++g) {
+        const TapGroup& grp = p.groups[g];
+        const int n_sub = grp.n_sub;
+        const uint32_t tx_bytes = (uint32_t)p.S * p.a_box_bytes + (uint32_t)n_sub * (p.N * p.cbe * 4);
+        const int fast0 = fast_t + grp.d_fast, slow0 = slow_t + grp.d_slow;
+        for (int c = 0; c < p.n_chunks; ++c) {
+          mbar_wait(empty_bar(stage), phase ^ 1, 100);
+          if (elect_one_sync()) {
             mbar_expect_tx(full_bar(stage), tx_bytes);
             const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
-            for (int s = 0; s < p.S; ++s) {
-              const int fast0 = ((tc.tfg * p.S + s) * p.FB) * p.stride + grp.d_fast;
-              const int slow0 = (tc.ts * p.SB) * p.stride + grp.d_slow;
-              tma_load_5d(sbase + (uint32_t)s * p.a_box_stride, &p.mapA, full_bar(stage), c * p.cbe, fast0, slow0, tc.ph, tc.n);
-            }
+            for (int s = 0; s < p.S; ++s)
+              tma_load_5d(sbase + (uint32_t)s * p.a_box_stride, &p.mapA, full_bar(stage), c * p.cbe, fast0 + s * p.FB * p.stride, slow0, tc.ph, tc.n);
             const uint32_t bbase = sbase + (uint32_t)p.S * p.a_box_stride;
-            for (int j = 0; j < grp.n_sub; ++j)
-              tma_load_2d(bbase + (uint32_t)j * p.b_tile_stride, &p.mapB, full_bar(stage), grp.tap[j] * p.cin + c * p.cbe,
-                          tc.nb * p.N);
-            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            for (int j = 0; j < n_sub; ++j)
+              tma_load_2d(bbase + (uint32_t)j * p.b_tile_stride, &p.mapB, full_bar(stage), grp.tap[j] * p.cin + c * p.cbe, wrow);
           }
+          __syncwarp();
+          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -132,30 +139,31 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int kk_per_chunk = p.cbe / 8;
+    // descriptor words: hi = SBO | version | layout (constant); lo = (address >> 4) | LBO, advanced by the program's deltas
+    const uint32_t desc_hi = (uint32_t)((p.sbo >> 4) & 0x3FFF) | (1u << 14) | ((uint32_t)(p.layout_type & 7) << 29);
+    const uint32_t lbo_bits = (16u >> 4) << 16;
+    const uint32_t idesc = p.idesc;
+    const uint32_t b_off = (uint32_t)p.S * p.a_box_stride;
     for (int ct = blockIdx.x; ct < p.total_ctiles; ct += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1, 200);
       tc_fence_after();
       const uint32_t d_base = tmem_base + (uint32_t)acc * 256;
       int l = 0;
       for (int g = 0; g < p.n_groups; ++g) {
-        const TapGroup& grp = p.groups[g];
+        const int m0 = p.prog0[g], m1 = m0 + p.prog_n[g];
         for (int c = 0; c < p.n_chunks; ++c, ++l) {
           mbar_wait(full_bar(stage), phase, 201);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one_sync()) {
             const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
-            const uint32_t bbase = sbase + (uint32_t)p.S * p.a_box_stride;
-            for (int s = 0; s < p.S; ++s) {
-              for (int j = 0; j < grp.n_sub; ++j) {
-                const uint32_t a_addr = sbase + (uint32_t)s * p.a_box_stride + (uint32_t)grp.a_off[j] * (p.FB * p.cbe * 4);
-                const uint32_t b_addr = bbase + (uint32_t)j * p.b_tile_stride;
-                for (int kk = 0; kk < kk_per_chunk; ++kk) {
-                  const uint64_t ad = make_smem_desc(a_addr + kk * 32, 16, p.sbo, p.layout_type);
-                  const uint64_t bd = make_smem_desc(b_addr + kk * 32, 16, p.sbo, p.layout_type);
-                  umma_tf32(d_base + (uint32_t)s * p.N, ad, bd, p.idesc, (l | j | kk) != 0);
-                }
-              }
+            const uint32_t a_lo = (sbase >> 4) | lbo_bits, b_lo = ((sbase + b_off) >> 4) | lbo_bits;
+            const uint32_t first_mask = l == 0 ? 1u : 0u;
+#pragma unroll 4
+            for (int m = m0; m < m1; ++m) {
+              const uint4 e = p.prog[m];
+              const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + e.x);
+              const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + e.y);
+              umma_tf32(d_base + e.z, ad, bd, idesc, (e.w & first_mask) == 0u);
             }
             umma_commit(empty_bar(stage));                 // frees the smem stage when these MMAs retire
             if (l == loads_per_tile - 1) umma_commit(tfull_bar(acc));
@@ -208,15 +216,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
           asm volatile("bar.sync 1, 128;" ::: "memory");
           const uint32_t sbuf = staging_base + (uint32_t)buf * (128 * p.ec * 4);
           const uint32_t srow = sbuf + (uint32_t)row * (p.ec * 4);
-          const int nv = p.ec / 4;                 // float4 per row: 8 or 4
+          // staging rows are written in the TMA store's swizzle (128B rows: 16-byte chunk ^= row & 7; 64B rows: chunk ^=
+          // (row >> 1) & 3), which is also bank-conflict free for a quarter-warp of consecutive rows
+          const int xr = p.ec == 32 ? (row & 7) : ((row >> 1) & 3);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (i < nv) {
-              const int j = (i + row) % nv;        // rotate to spread banks
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + j * 16), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+          for (int j = 0; j < 8; ++j) {
+            if (j < p.ec / 4)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ xr) << 4)), "r"(r[4 * j]), "r"(r[4 * j + 1]),
                            "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
                            : "memory");
-            }
           }
           fence_proxy_async_smem();
           asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -347,6 +355,27 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   p.stage_bytes = best.stage_bytes;
   p.n_stages = best.n_stages;
   p.staging_bytes = staging_bytes;
+  {
+    int n = 0;
+    const int kk_per_chunk = p.cbe / 8;
+    for (int gi = 0; gi < p.n_groups; ++gi) {
+      const TapGroup& grp = p.groups[gi];
+      int same = -1;                                      // an earlier group with the same sub-tap structure shares its program
+      for (int gj = 0; gj < gi && same < 0; ++gj)
+        if (p.groups[gj].n_sub == grp.n_sub && memcmp(p.groups[gj].a_off, grp.a_off, grp.n_sub) == 0) same = gj;
+      if (same >= 0) { p.prog0[gi] = p.prog0[same]; p.prog_n[gi] = p.prog_n[same]; continue; }
+      p.prog0[gi] = (int16_t)n;
+      for (int s2 = 0; s2 < p.S; ++s2)
+        for (int j = 0; j < grp.n_sub; ++j)
+          for (int kk = 0; kk < kk_per_chunk; ++kk) {
+            const uint32_t a_delta = (uint32_t)s2 * p.a_box_stride + (uint32_t)grp.a_off[j] * (p.FB * p.cbe * 4) + kk * 32;
+            const uint32_t b_delta = (uint32_t)j * p.b_tile_stride + kk * 32;
+            SOS_CHECK_ARG(n < kMaxProg, "sos_conv2d_tc: MMA program of %d entries is too long", n);
+            p.prog[n++] = make_uint4(a_delta >> 4, b_delta >> 4, (uint32_t)s2 * N, (j == 0 && kk == 0) ? 1u : 0u);
+          }
+      p.prog_n[gi] = (int16_t)(n - p.prog0[gi]);
+    }
+  }
   p.scale = a.epi_scale;
   p.shift = a.epi_shift;
   p.act = (int)a.act;
@@ -386,7 +415,8 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
     uint64_t str[5] = {4, sY_fast, sY_slow * g, sY_slow, pixY * a.YH * a.YW};
     uint32_t box[5] = {(uint32_t)p.ec, (uint32_t)pl.FB, (uint32_t)pl.SB, 1, 1};
     uint32_t es[5] = {1, 1, 1, 1, 1};
-    if (int e = encode_map(&p.mapD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, str, box, es, CU_TENSOR_MAP_SWIZZLE_NONE, "output")) return e;
+    if (int e = encode_map(&p.mapD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, str, box, es,
+                            ec == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "output")) return e;
   }
   const int tiles_fast = ceil_div(out_fast, pl.FB);
   p.tiles_fast_g = ceil_div(tiles_fast, p.S);

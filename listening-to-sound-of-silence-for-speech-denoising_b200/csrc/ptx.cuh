@@ -41,6 +41,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   }
 }
 
+// One lane of a fully converged warp (the compiler keeps uniform-datapath instructions such as tcgen05.mma straight-line
+// under this predicate; `lane == 0` makes it wrap each of them in an ELECT / BRA.U.ANY loop).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {

@@ -95,19 +95,19 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
-        const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
-        const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
-        const int coblk = p.job_coblk[job], g0 = p.job_g0[job], ng = p.job_ng[job];
-        const int co_here = min(128, p.Cout - coblk * 128);
-        const int n_co_chunks = (co_here + p.cbo - 1) / p.cbo;
-        const uint32_t tx = (uint32_t)n_co_chunks * p.dy_chunk_bytes + (uint32_t)ng * p.n_ci_chunks * p.x_box_bytes;
-        for (int tile = t0; tile < t1; ++tile) {
-          const WgTile tc = decode_wg_tile(p, tile);
-          mbar_wait(empty_bar(stage), phase ^ 1, 500);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
+      const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
+      const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
+      const int coblk = p.job_coblk[job], g0 = p.job_g0[job], ng = p.job_ng[job];
+      const int co_here = min(128, p.Cout - coblk * 128);
+      const int n_co_chunks = (co_here + p.cbo - 1) / p.cbo;
+      const uint32_t tx = (uint32_t)n_co_chunks * p.dy_chunk_bytes + (uint32_t)ng * p.n_ci_chunks * p.x_box_bytes;
+      for (int tile = t0; tile < t1; ++tile) {
+        const WgTile tc = decode_wg_tile(p, tile);
+        mbar_wait(empty_bar(stage), phase ^ 1, 500);
+        if (elect_one_sync()) {
           mbar_expect_tx(full_bar(stage), tx);
           const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
           for (int cc = 0; cc < n_co_chunks; ++cc)
@@ -120,8 +120,9 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
               tma_load_5d(xb + (uint32_t)c * p.x_box_stride, &p.mapX, full_bar(stage), c * p.cbi, tc.tf * p.FB * p.stride + grp.d_fast,
                           tc.ts * p.SB * p.stride + grp.d_slow, tc.ph, tc.n);
           }
-          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -129,6 +130,11 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
     int stage = 0;
     uint32_t phase = 0, acc_phase = 0;
     const uint32_t a_kstep = 8u * p.cbo * 4u, b_kstep = 8u * p.cbi * 4u;     // 8 pixels (one k step) of one chunk
+    const uint32_t a_inc = a_kstep >> 4, b_inc = b_kstep >> 4;
+    const uint32_t desc_hi = (512u >> 4) | (1u << 14) | (1u << 29);
+    const uint32_t x_lbo_bits = ((uint32_t)p.x_box_stride >> 4) << 16;
+    const uint32_t idesc = p.idesc;
+    const int SB = p.SB;
     for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
       const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
       const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
@@ -139,18 +145,25 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
       for (int tile = t0; tile < t1; ++tile) {
         mbar_wait(full_bar(stage), phase, 601);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one_sync()) {
+          // descriptor words: hi = SBO (512) | version | layout 1; lo = (address >> 4) | LBO (chunk pitch); one k step = 8 pixels
           const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
+          const uint32_t a_lo0 = (sbase >> 4) | (((uint32_t)p.dy_chunk_stride >> 4) << 16);
+          const uint32_t first = tile != t0 ? 1u : 0u;
           int slot = 0;
           for (int gi = 0; gi < ng; ++gi) {
             const TapGroup& grp = p.groups[g0 + gi];
             const uint32_t xb = sbase + p.x_off + (uint32_t)gi * p.n_ci_chunks * p.x_box_stride;
-            for (int j = 0; j < grp.n_sub; ++j, ++slot) {
+            const int n_sub = grp.n_sub;
+            for (int j = 0; j < n_sub; ++j, ++slot) {
               const uint32_t d = tmem_base + (uint32_t)slot * p.N;
-              for (int ks = 0; ks < p.SB; ++ks) {
-                const uint64_t ad = make_smem_desc(sbase + ks * a_kstep, p.dy_chunk_stride, 512, 1);
-                const uint64_t bd = make_smem_desc(xb + (ks + grp.a_off[j]) * b_kstep, p.x_box_stride, 512, 1);
-                umma_tf32_wg(d, ad, bd, p.idesc, (tile != t0 || ks != 0) ? 1u : 0u);
+              uint32_t a_lo = a_lo0;
+              uint32_t b_lo = ((xb + (uint32_t)grp.a_off[j] * b_kstep) >> 4) | x_lbo_bits;
+#pragma unroll 4
+              for (int ks = 0; ks < SB; ++ks) {
+                umma_tf32_wg(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, first | (uint32_t)ks);
+                a_lo += a_inc;
+                b_lo += b_inc;
               }
             }
           }
