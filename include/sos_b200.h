@@ -84,7 +84,8 @@ int sos_round_tf32(float* x, int64_t n, cudaStream_t stream);
 /* ------------------------------------------------------------------------------------------------ BatchNorm + activation
  * nn.BatchNorm2d(eps 1e-5, momentum 0.1) + ReLU / PReLU of ConvBlock (M2/networks.py:28-51),
  * Conv2dBlock (M1/networks.py:28-51), Down/UpConvBlock (M2/networks.py:97-149) over NHWC rows.
- * act: 0 none, 1 ReLU, 2 PReLU (single slope), optionally | SOS_ACT_ROUND_TF32 (output feeds a tensor-core GEMM).  partial: sos_bn_partial_blocks(rows, C) * 3 * C floats. */
+ * act: 0 none, 1 ReLU, 2 PReLU (single slope), optionally | SOS_ACT_ROUND_TF32 (output feeds a tensor-core GEMM).  partial: sos_bn_partial_blocks(rows, C) * 3 * C floats.
+ * sos_bn_act_backward ADDS the PReLU slope gradient into *dslope (the caller zeroes it). */
 int sos_bn_partial_blocks(int64_t rows, int64_t channels);
 int sos_bn_stats(const float* y, int64_t rows, int64_t channels, float* partial, cudaStream_t stream);
 int sos_bn_finalize(const float* partial, int64_t rows, int64_t channels, const float* gamma, const float* beta, float eps,

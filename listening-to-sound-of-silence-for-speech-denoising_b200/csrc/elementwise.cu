@@ -137,19 +137,43 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const float* __restr
   }
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int G, int C, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float* __restrict__ mean_out, float* __restrict__ invstd_out,
-                                   float* __restrict__ scale_out, float* __restrict__ shift_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0, q = 0;
-  for (int g = 0; g < G; ++g) {
-    s += partial[(size_t)g * 2 * C + c];
-    q += partial[(size_t)g * 2 * C + C + c];
+// Reduction of the per-block partial sums: a block owns 32 channels; 8 thread rows stride over the G partial blocks
+// (coalesced 128-byte reads), then combine through shared memory.  NQ quantities per channel ([g][NQ][C] layout).
+template <int NQ>
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int G, int C, int c, int gl, double (&out)[NQ],
+                                                double (*sm)[NQ][32]) {
+  double a[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) a[q] = 0;
+  if (c < C)
+    for (int g = gl; g < G; g += 8) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) a[q] += partial[((size_t)g * NQ + q) * C + c];
+    }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) sm[gl][q][threadIdx.x & 31] = a[q];
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    double t = 0;
+    for (int r = 0; r < 8; ++r) t += sm[r][q][threadIdx.x & 31];
+    out[q] = t;
   }
-  const double mean = s / count;
-  double var = q / count - mean * mean;
+}
+
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int G, int C, double count,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                          float momentum, float* __restrict__ running_mean,
+                                                          float* __restrict__ running_var, float* __restrict__ mean_out,
+                                                          float* __restrict__ invstd_out, float* __restrict__ scale_out,
+                                                          float* __restrict__ shift_out) {
+  __shared__ double sm[8][2][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), gl = threadIdx.x >> 5;
+  double r[2];
+  reduce_partials<2>(partial, G, C, c, gl, r, sm);
+  if (gl != 0 || c >= C) return;
+  const double mean = r[0] / count;
+  double var = r[1] / count - mean * mean;
   if (var < 0) var = 0;
   const float invstd = (float)(1.0 / sqrt(var + (double)eps));
   mean_out[c] = (float)mean;
@@ -251,27 +275,28 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __
   }
 }
 
-// Backward finalize: dgamma, dbeta, dslope and the two per-channel means used by pass 2.
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int G, int C, double count, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ dslope, float* __restrict__ m1,
-                                       float* __restrict__ m2) {
-  __shared__ float red[32];
-  float s3_local = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double s1 = 0, s2 = 0, s3 = 0;
-    for (int g = 0; g < G; ++g) {
-      s1 += partial[(size_t)g * 3 * C + c];
-      s2 += partial[(size_t)g * 3 * C + C + c];
-      s3 += partial[(size_t)g * 3 * C + 2 * C + c];
-    }
-    dbeta[c] = (float)s1;
-    dgamma[c] = (float)s2;
-    m1[c] = (float)(s1 / count);
-    m2[c] = (float)(s2 / count);
-    s3_local += (float)s3;
+// Backward finalize: dgamma, dbeta, dslope (atomically accumulated; zeroed by the caller) and the two per-channel means
+// used by pass 2.  Same 32-channel blocks as bn_finalize_kernel.
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int G, int C, double count,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                              float* __restrict__ dslope, float* __restrict__ m1, float* __restrict__ m2) {
+  __shared__ double sm[8][3][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), gl = threadIdx.x >> 5;
+  double r[3];
+  reduce_partials<3>(partial, G, C, c, gl, r, sm);
+  if (gl != 0) return;
+  float s3 = 0.f;
+  if (c < C) {
+    dbeta[c] = (float)r[0];
+    dgamma[c] = (float)r[1];
+    m1[c] = (float)(r[0] / count);
+    m2[c] = (float)(r[1] / count);
+    s3 = (float)r[2];
   }
-  s3_local = block_sum(s3_local, red);
-  if (threadIdx.x == 0 && dslope) *dslope = s3_local;
+  if (dslope) {
+    s3 = warp_sum(s3);
+    if ((threadIdx.x & 31) == 0) atomicAdd(dslope, s3);
+  }
 }
 
 // Backward pass 2: dy = scale * (dpre - m1 - xhat*m2)      (scale = gamma*invstd)
@@ -678,7 +703,7 @@ int sos_bn_finalize(const float* partial, int64_t rows, int64_t channels, const 
                     cudaStream_t stream) {
   const int G = sos_bn_partial_blocks(rows, channels);
   SOS_CHECK_ARG(partial && gamma && beta && mean && invstd && scale && shift && G > 0, "sos_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<ceil_div((int)channels, 128), 128, 0, stream>>>(partial, G, (int)channels, (double)rows, gamma, beta, eps, momentum,
+  bn_finalize_kernel<<<ceil_div((int)channels, 32), 256, 0, stream>>>(partial, G, (int)channels, (double)rows, gamma, beta, eps, momentum,
                                                                       running_mean, running_var, mean, invstd, scale, shift);
   SOS_CHECK_LAUNCH("sos_bn_finalize");
   return SOS_OK;
@@ -719,7 +744,7 @@ int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y,
   if (smem > 48 * 1024) cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   bn_bwd_reduce_kernel<<<G, kThreads, smem, stream>>>(dz, dv, y, rows, C, scale, shift, mean, invstd, act, slope, partial);
   SOS_CHECK_LAUNCH("sos_bn_act_backward(reduce)");
-  bn_bwd_finalize_kernel<<<1, 256, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta, (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 32), 256, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta, (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2);
   SOS_CHECK_LAUNCH("sos_bn_act_backward(finalize)");
   bn_bwd_apply_kernel<<<grid_for(rows * (channels / 4)), kThreads, 0, stream>>>(dz, dv, y, dy, rows, C, scale, shift, mean, invstd, m1,
                                                                                  m2, act, slope);

@@ -367,8 +367,10 @@ def lstm_forward(gx, w_hh):
     out = torch.empty(T, B, 2 * H, device=gx.device, dtype=torch.float32)
     gates = torch.empty_like(gx)
     cell = torch.empty(T, B, 2, H, device=gx.device, dtype=torch.float32)
+    e0 = _pb()
     check(lib().sos_lstm_forward(_p(gx), _p(w_hh), T, B, H, _p(out), _p(gates), _p(cell), _stream()), "sos_lstm_forward")
-    _count(T)
+    _pe("lstm_fwd", e0)
+    _count()
     return out, gates, cell
 
 
@@ -377,7 +379,9 @@ def lstm_backward(dout, w_hh, out, gates, cell):
     H = H4 // 4
     dgx = torch.empty_like(gates)
     dc = torch.empty(B, 2, H, device=dout.device, dtype=torch.float32)
+    e0 = _pb()
     check(lib().sos_lstm_backward(_p(dout), _p(w_hh), _p(out), _p(gates), _p(cell), T, B, H, _p(dgx), None, _p(dc), _stream()),
           "sos_lstm_backward")
-    _count(T)
+    _pe("lstm_bwd", e0)
+    _count()
     return dgx

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_conv.py -q -m gpu --timeout 600 -x > gpurun_out/pytest_conv.log 2>&1; echo "pytest conv exit $?"; tail -3 gpurun_out/pytest_conv.log
-timeout 600 python scripts/bench_conv.py 32 > gpurun_out/bench_conv.log 2>&1; echo "bench_conv exit $?"; tail -32 gpurun_out/bench_conv.log
+timeout 1200 python -m pytest tests/test_gpu_transforms.py tests/test_gpu_networks.py -q -m gpu --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -5 gpurun_out/pytest_gpu.log
+timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_b32.json 2> gpurun_out/bench_b32.err; echo "bench exit $?"; tail -c 400 gpurun_out/bench_b32.err

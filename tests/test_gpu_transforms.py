@@ -181,14 +181,17 @@ def test_padcat_reflect_resize(cuda):
     assert float((ops.nhwc_to_nchw(bd.grad, 64).cpu() - b.grad).abs().max()) < 1e-5
 
 
-def test_bilstm_matches_torch(cuda):
+@pytest.mark.parametrize("I,H,T,B", [(96, 40, 13, 5), (64, 200, 37, 40), (32, 100, 60, 3)])
+def test_bilstm_matches_torch(cuda, I, H, T, B):
+    """nn.LSTM(bidirectional) forward / backward; the larger cases run the persistent kernels over several blocks per
+    direction (the inter-step barrier) and more than one 32-clip batch tile."""
     from sos_b200 import networks
     torch.manual_seed(2)
-    ref = torch.nn.LSTM(96, 40, bidirectional=True)
-    mine = networks.BiLSTM(96, 40, bidirectional=True)
+    ref = torch.nn.LSTM(I, H, bidirectional=True)
+    mine = networks.BiLSTM(I, H, bidirectional=True)
     mine.load_state_dict(ref.state_dict())
     mine = mine.to(cuda)
-    x = torch.randn(13, 5, 96, requires_grad=True)
+    x = torch.randn(T, B, I, requires_grad=True)
     out, _ = ref(x)
     go = torch.randn(out.shape)
     out.backward(go)
