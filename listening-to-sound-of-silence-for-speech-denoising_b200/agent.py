@@ -84,12 +84,18 @@ class FlatAdam(object):
             if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
                 p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
 
-    def step(self):
+    def exchange(self):
+        """The data-parallel exchange: ONE all-reduce (sum) of the flat gradient buffer (NCCL over NVLink on the GPUs; the
+        CPU tests drive the same code over gloo).  Returns the world size; the 1/world factor is folded into the Adam kernel."""
         world = 1
         if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             world = torch.distributed.get_world_size(self.group)
             if world > 1:
                 torch.distributed.all_reduce(self.flat_grad, group=self.group)        # ncclAllReduce(sum) over NVLink
+        return world
+
+    def step(self):
+        world = self.exchange()
         self.step_count += 1
         g = self.param_groups[0]
         ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], self.step_count, g["betas"][0],
