@@ -9,10 +9,12 @@
 // over NHWC fp32 activations.  Out-of-range input pixels read as zero (TMA out-of-bounds fill), so zero
 // padding costs nothing; reflect padding is materialised by the producer layer.
 //
-// CTA = 192 threads, persistent over output tiles:
+// CTA = 224 threads, persistent over output tiles:
 //   warp 0    TMA producer: per k-step one activation box per sub-tile (+ halo rows along the slow tile axis,
 //             shared by every tap that differs only by a slow-axis shift) and one weight box per tap
-//   warp 1    MMA issuer (single elected lane), accumulators double-buffered in TMEM
+//   warp 1, 6 MMA issuers (one elected lane each), accumulators double-buffered in TMEM.  With two sub-tiles per CTA tile
+//             each issuer owns one sub-tile's accumulator: a TF32 MMA of N = 48 lasts 24 cycles, less than one thread needs
+//             to issue it, so two threads feed the tensor pipe; with one sub-tile warp 6 idles
 //   warps 2-5 epilogue: tcgen05.ld -> affine/activation -> smem staging -> TMA store (clips the ragged edge)
 // An output tile is 128 pixels = SB (slow) x FB (fast) pixels of one image (FB = 8 or 128).  The slow axis may be
 // a dilation lattice (pixels q*g + r for fixed phase r), which turns a dilated tap shift into a shift by whole
@@ -27,13 +29,14 @@ namespace {
 using namespace ptx;
 using namespace tc;
 
-constexpr int kThreadsTc = 192;
+constexpr int kThreadsTc = 224;
 constexpr int kMaxProg = 144;             // entries of the deduplicated MMA programs
 struct alignas(64) TcParams {
   CUtensorMap mapA, mapB, mapD;
   int total_ctiles, n_nblk, tiles_fast_g, tiles_slow, n_phase;
   int S, N, cbe, n_chunks, n_groups;
   int FB, SB, stride;
+  int n_issuers;                 // 1 or 2 MMA-issuing warps (2 when S == 2)
   int cin;                       // K elements per tap in the weight matrix
   int ec;                        // epilogue / store chunk width (16 or 32 channels)
   int n_stages, stage_bytes, a_box_bytes, a_box_stride, b_tile_stride, staging_bytes;
@@ -86,10 +89,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
     prefetch_tmap(&p.mapD);
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), p.n_issuers);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1);
+      mbar_init(tfull_bar(s), p.n_issuers);
       mbar_init(tempty_bar(s), 4);
     }
     fence_barrier_init();
@@ -133,8 +136,10 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+  } else if (warp == 1 || warp == 6) {
+    // ===================================================================== MMA issuer(s)
+    const int issuer = warp == 1 ? 0 : 1;
+    if (issuer < p.n_issuers) {
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -150,7 +155,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
       const uint32_t d_base = tmem_base + (uint32_t)acc * 256;
       int l = 0;
       for (int g = 0; g < p.n_groups; ++g) {
-        const int m0 = p.prog0[g], m1 = m0 + p.prog_n[g];
+        const int per = p.prog_n[g] / p.n_issuers;          // the program lists sub-tile 0's MMAs first, then sub-tile 1's
+        const int m0 = p.prog0[g] + issuer * per, m1 = m0 + per;
         for (int c = 0; c < p.n_chunks; ++c, ++l) {
           mbar_wait(full_bar(stage), phase, 201);
           tc_fence_after();
@@ -173,6 +179,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
@@ -284,7 +291,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   // ---- choose orientation / box sharing / taps per box / channel chunk / sub-tiles: the cheapest candidate (tensor time vs
   //      L2->smem feed time per output pixel) whose pipeline stage fits at least twice (three times preferred) in shared memory
   Geometry geo{(int)a.ntaps, a.tap_dh, a.tap_dw, (int)a.H, (int)a.W, (int)a.OH, (int)a.OW, (int)a.stride, Cin, Cout,
-               a.osh == 1 && a.osw == 1 && a.oph == 0 && a.opw == 0, kMaxSub};
+               a.osh == 1 && a.osw == 1 && a.oph == 0 && a.opw == 0, kMaxSub, true};
   struct Cand { Plan pl; int cbe = 0, S = 0, n_stages = 0, stage_bytes = 0, a_box_bytes = 0; double cost = 1e300; };
   Cand best;
   auto consider = [&](const Plan& pl, int cbe, int S) {
@@ -341,6 +348,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   p.FB = pl.FB;
   p.SB = pl.SB;
   p.S = best.S;
+  p.n_issuers = best.S == 2 ? 2 : 1;
   p.stride = (int)a.stride;
   p.n_groups = (int)pl.groups.size();
   for (int i = 0; i < p.n_groups; ++i) p.groups[i] = pl.groups[i];

@@ -28,6 +28,7 @@ struct Geometry {
   int Cin, Cout;
   bool lattice_out;            // output addressed densely (no sub-pixel scatter) -> dilation lattices allowed
   int max_sub;                 // most taps one staged box may serve (<= kMaxSub)
+  bool allow_wide = false;     // 16 x 8 (fast x slow) tiles for short dilation lattices (forward / dgrad kernel only)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -125,6 +126,10 @@ inline bool build_plan(const Geometry& a, bool fast_is_w, bool share, Plan& pl) 
     const bool lattice_out = a.lattice_out;
     if (g > 1 && (!lattice_out || in_slow % g != 0 || out_slow % g != 0)) return false;
     pl.g = g;
+    if (a.allow_wide && out_slow / g <= 8 && out_fast >= 16) {   // a lattice of <= 8 rows would half-fill a 16-row tile
+      pl.FB = 16;
+      pl.SB = 8;
+    }
     // group taps by fast offset
     std::vector<int> order(nt);
     for (int t = 0; t < nt; ++t) order[t] = t;

@@ -35,6 +35,7 @@ struct alignas(64) WgParams {
   int FB, SB, stride;
   int Cin, Cout, N;
   int cbi, n_ci_chunks, cbo;
+  int ksteps, shift_mul;            // 8-pixel k steps per tile; k steps per slow row (tap shifts are whole slow rows)
   int x_box_bytes, x_box_stride, dy_chunk_bytes, dy_chunk_stride, x_off;
   int stage_bytes, n_stages;
   int layout_a, layout_b;
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
     const uint32_t desc_hi = (512u >> 4) | (1u << 14) | (1u << 29);
     const uint32_t x_lbo_bits = ((uint32_t)p.x_box_stride >> 4) << 16;
     const uint32_t idesc = p.idesc;
-    const int SB = p.SB;
+    const int ksteps = p.ksteps;
     for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
       const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
       const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
@@ -158,9 +159,9 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
             for (int j = 0; j < n_sub; ++j, ++slot) {
               const uint32_t d = tmem_base + (uint32_t)slot * p.N;
               uint32_t a_lo = a_lo0;
-              uint32_t b_lo = ((xb + (uint32_t)grp.a_off[j] * b_kstep) >> 4) | x_lbo_bits;
+              uint32_t b_lo = ((xb + (uint32_t)(grp.a_off[j] * p.shift_mul) * b_kstep) >> 4) | x_lbo_bits;
 #pragma unroll 4
-              for (int ks = 0; ks < SB; ++ks) {
+              for (int ks = 0; ks < ksteps; ++ks) {
                 umma_tf32_wg(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, first | (uint32_t)ks);
                 a_lo += a_inc;
                 b_lo += b_inc;
@@ -235,16 +236,16 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG(((uintptr_t)a.x % 16) == 0 && ((uintptr_t)a.dy % 16) == 0, "sos_conv2d_wgrad: pointers must be 16-byte aligned");
 
   Geometry geo{(int)a.ntaps, a.tap_dh, a.tap_dw, (int)a.H, (int)a.W, (int)a.OH, (int)a.OW, (int)a.stride, (int)a.Cin, (int)a.Cout, true,
-               std::min(kMaxSub, 512 / round_up((int)a.Cin, 16))};
+               std::min(kMaxSub, 512 / round_up((int)a.Cin, 16)), true};
   Plan best;
   for (int fw = 1; fw >= 0; --fw)
     for (int sh = 1; sh >= 0; --sh) {
       Plan pl;
-      if (build_plan(geo, fw != 0, sh != 0, pl) && pl.FB == 8 && pl.cost < best.cost) best = pl;
+      if (build_plan(geo, fw != 0, sh != 0, pl) && pl.FB <= 16 && pl.cost < best.cost) best = pl;
     }
   if (a.force_plan >= 0) {
     Plan pl;
-    SOS_CHECK_ARG(build_plan(geo, (a.force_plan & 1) != 0, (a.force_plan & 2) != 0, pl) && pl.FB == 8,
+    SOS_CHECK_ARG(build_plan(geo, (a.force_plan & 1) != 0, (a.force_plan & 2) != 0, pl) && pl.FB <= 16,
                   "sos_conv2d_wgrad: forced plan %d not applicable", (int)a.force_plan);
     best = pl;
   }
@@ -260,7 +261,8 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   p.cbi = 32;
   p.n_ci_chunks = ceil_div(Cin, 32);
   p.cbo = 32;
-  p.FB = 8;
+  p.FB = pl.FB;                      // 8, or 16 for short dilation lattices (then SB <= 8)
+  const int fbm = pl.FB / 8;         // k steps (8 pixels) per slow row
   p.stride = (int)a.stride;
   p.dw = a.dw;
   p.layout_a = p.layout_b = 1;
@@ -279,12 +281,12 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   const int n_co_chunks_max = ceil_div(co_blk_ch, p.cbo);
   int max_ng = 1;
   // choose SB (pixels per tile = 8*SB) and groups per job so that at least 2 stages fit
-  int SB = 16, groups_per_job = 1;
+  int SB = pl.SB, groups_per_job = 1;
   const int avail = kSmemLimit - 2048;
   auto stage_bytes_for = [&](int sb, int ng, int* x_off_out, int* reach_out) {
-    const int dy_chunk = sb * 8 * p.cbo * 4;
+    const int dy_chunk = sb * p.FB * p.cbo * 4;
     const int dy_stride = round_up(dy_chunk, 1024);
-    const int x_box = (sb + pl.halo) * 8 * p.cbi * 4;
+    const int x_box = (sb + pl.halo) * p.FB * p.cbi * 4;
     const int x_stride = round_up(x_box, 1024);
     const int x_off = n_co_chunks_max * dy_stride;
     const int used = x_off + ng * p.n_ci_chunks * x_stride;
@@ -316,9 +318,11 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   int reach = 0;
   const int used = stage_bytes_for(SB, groups_per_job, &p.x_off, &reach);
   p.SB = SB;
-  p.dy_chunk_bytes = SB * 8 * p.cbo * 4;
+  p.dy_chunk_bytes = SB * p.FB * p.cbo * 4;
   p.dy_chunk_stride = round_up(p.dy_chunk_bytes, 1024);
-  p.x_box_bytes = (SB + pl.halo) * 8 * p.cbi * 4;
+  p.x_box_bytes = (SB + pl.halo) * p.FB * p.cbi * 4;
+  p.ksteps = SB * fbm;
+  p.shift_mul = fbm;
   p.x_box_stride = round_up(p.x_box_bytes, 1024);
   p.stage_bytes = used;
   const int tail = std::max(0, reach - used);
@@ -354,7 +358,7 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
     const uint64_t s_fast = fw ? pix : pix * a.W, s_slow = fw ? pix * a.W : pix;
     uint64_t dims[5] = {(uint64_t)Cin, in_fast, in_slow / g, (uint64_t)g, (uint64_t)a.N};
     uint64_t str[5] = {4, s_fast, s_slow * g, s_slow, pix * a.H * a.W};
-    uint32_t box[5] = {(uint32_t)p.cbi, (uint32_t)(8 * a.stride), (uint32_t)((SB + pl.halo) * a.stride), 1, 1};
+    uint32_t box[5] = {(uint32_t)p.cbi, (uint32_t)(p.FB * a.stride), (uint32_t)((SB + pl.halo) * a.stride), 1, 1};
     uint32_t es[5] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1, 1};
     SOS_CHECK_ARG(box[2] <= 256, "sos_conv2d_wgrad: activation box too large");
     const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
@@ -366,13 +370,13 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
     const uint64_t s_fast = fw ? pix : pix * a.OW, s_slow = fw ? pix * a.OW : pix;
     uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)out_fast, (uint64_t)(out_slow / g), (uint64_t)g, (uint64_t)a.N};
     uint64_t str[5] = {4, s_fast, s_slow * g, s_slow, pix * a.OH * a.OW};
-    uint32_t box[5] = {(uint32_t)p.cbo, 8, (uint32_t)SB, 1, 1};
+    uint32_t box[5] = {(uint32_t)p.cbo, (uint32_t)p.FB, (uint32_t)SB, 1, 1};
     uint32_t es[5] = {1, 1, 1, 1, 1};
     const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     if (int e = encode_map(&p.mapDY, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, a.dy + a.dy_coff, dims, str, box, es, sw, "wgrad output grads"))
       return e;
   }
-  p.tiles_fast = ceil_div(out_fast, 8);
+  p.tiles_fast = ceil_div(out_fast, p.FB);
   p.tiles_slow = ceil_div(out_slow / g, SB);
   p.n_phase = g;
   const long long total = (long long)a.N * g * p.tiles_slow * p.tiles_fast;

@@ -1,9 +1,6 @@
 #!/bin/bash
-# Profiling visit: per-layer table, launch list of one step, --set full captures of the two tensor-core kernels.
 mkdir -p gpurun_out
-rm -f gpurun_out/*.ncu-rep
-timeout 600 python scripts/bench_conv.py 32 > gpurun_out/bench_conv.log 2>&1; echo "bench_conv exit $?"; tail -3 gpurun_out/bench_conv.log
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python scripts/profile_step.py 32 > gpurun_out/launches.log 2>&1; echo "ncu list exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:tapgemm -s 60 -c 2 -o gpurun_out/prof_tapgemm -f python scripts/profile_step.py 32 > gpurun_out/prof_tapgemm.log 2>&1; echo "ncu tapgemm exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:wgrad_tf32 -s 30 -c 2 -o gpurun_out/prof_wgrad -f python scripts/profile_step.py 32 > gpurun_out/prof_wgrad.log 2>&1; echo "ncu wgrad exit $?"
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_b32.json 2> gpurun_out/bench_b32.err; echo "bench exit $?"; tail -c 300 gpurun_out/bench_b32.err
+timeout 900 python -m pytest tests -q -m gpu --timeout 600 -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 600 python scripts/bench_conv.py 32 d32 > gpurun_out/bench_conv_d32.log 2>&1; echo "bench_conv exit $?"; tail -5 gpurun_out/bench_conv_d32.log
+timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_b32.json 2> gpurun_out/bench_b32.err; echo "bench exit $?"; tail -c 300 gpurun_out/bench_b32.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_b32.json')); print(d['value'], d['ms_per_step']); [print(k, round(v['ms_per_step'],2)) for k,v in d['kernels'].items()]"
