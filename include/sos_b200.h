@@ -137,6 +137,11 @@ int sos_bias_act_backward(const float* dy, const float* y, float* dpre, int64_t 
  *   mode 1: data grad [Cin][ntaps * CoutP], k = tap' * CoutP + co with tap' the flipped tap */
 int sos_pack_conv_weight(const float* w, int64_t Cout, int64_t Cin, int64_t kh, int64_t kw, int64_t CinP, int64_t CoutP,
                          int mode, float* out, cudaStream_t stream);
+/* Strided gather of selected taps (any of the three GEMM roles, sub-pixel phases of transposed / strided convs):
+ *   out[r][t*KP + k] = w[r*row_stride + k*k_stride + tap_off[t]]  (elements; zero for K <= k < KP), rows x ntaps*KP, optionally
+ *   rounded to TF32.  tap_off: host array, ntaps <= 49 entries. */
+int sos_pack_taps(const float* w, int64_t rows, int64_t K, int64_t KP, int64_t row_stride, int64_t k_stride, int64_t ntaps,
+                  const int32_t* tap_off, int round_tf32, float* out, cudaStream_t stream);
 /* wgrad buffer [tap][CoutP][CinP] -> PyTorch (Cout, Cin, kh, kw) (transposed=0) or ConvTranspose (Cin, Cout, kh, kw)
  * (transposed=1, in which case src is [tap][CinP'][CoutP'] with the roles swapped by the caller). */
 int sos_unpack_wgrad(const float* src, int64_t Cout, int64_t Cin, int64_t ntaps, int64_t CinP, float* dst, int accumulate,

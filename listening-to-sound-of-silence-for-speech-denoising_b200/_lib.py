@@ -70,6 +70,7 @@ _SIGS = {
     "sos_bias_act": (C.c_int, [c_f, i64, i64, i64, c_f, C.c_int, S]),
     "sos_bias_act_backward": (C.c_int, [c_f, c_f, c_f, i64, i64, i64, C.c_int, c_f, S]),
     "sos_pack_conv_weight": (C.c_int, [c_f, i64, i64, i64, i64, i64, i64, C.c_int, c_f, S]),
+    "sos_pack_taps": (C.c_int, [c_f, i64, i64, i64, i64, i64, i64, C.POINTER(C.c_int32), C.c_int, c_f, S]),
     "sos_unpack_wgrad": (C.c_int, [c_f, i64, i64, i64, i64, c_f, C.c_int, S]),
     "sos_conv2d_tc": (C.c_int, [C.POINTER(ConvArgs), S]),
     "sos_conv2d_wgrad": (C.c_int, [C.POINTER(WgradArgs), S]),

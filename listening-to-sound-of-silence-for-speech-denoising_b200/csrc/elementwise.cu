@@ -601,6 +601,23 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int Cout, i
   }
 }
 
+// Generic strided gather of selected taps into a GEMM operand (one launch per convolution call):
+//   out[r][t*KP + k] = w[r*sr + k*sk + tap_off[t]]   (k < K; zero for K <= k < KP), optionally rounded to TF32
+struct TapOffsets { int off[49]; };
+__global__ void pack_taps_kernel(const float* __restrict__ w, int R, int K, int KP, long long sr, long long sk, int ntaps, TapOffsets taps,
+                                 int round, float* __restrict__ out) {
+  const long long total = (long long)R * ntaps * KP;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % KP);
+    const long long t2 = e / KP;
+    const int t = (int)(t2 % ntaps);
+    const int r = (int)(t2 / ntaps);
+    float v = k < K ? w[r * sr + k * sk + taps.off[t]] : 0.f;
+    if (round) v = tf32_rna(v);
+    out[e] = v;
+  }
+}
+
 // wgrad result [taps][CoutP?]... -> PyTorch layout.  src is [tap][Cout][CinP] (tap-major), dst (Cout,Cin,kh,kw).
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, int Cout, int Cin, int ntaps, int CinP, float* __restrict__ dst,
                                     int accumulate) {
@@ -877,6 +894,17 @@ int sos_pack_conv_weight(const float* w, int64_t Cout, int64_t Cin, int64_t kh, 
   const long long total = mode == 0 ? Cout * kh * kw * CinP : Cin * kh * kw * CoutP;
   pack_conv_weight_kernel<<<grid_for(total), kThreads, 0, stream>>>(w, (int)Cout, (int)Cin, (int)kh, (int)kw, (int)CinP, (int)CoutP, mode, out);
   SOS_CHECK_LAUNCH("sos_pack_conv_weight");
+  return SOS_OK;
+}
+
+int sos_pack_taps(const float* w, int64_t rows, int64_t K, int64_t KP, int64_t row_stride, int64_t k_stride, int64_t ntaps,
+                  const int32_t* tap_off, int round_tf32, float* out, cudaStream_t stream) {
+  SOS_CHECK_ARG(w && out && tap_off && rows > 0 && K > 0 && KP >= K && ntaps > 0 && ntaps <= 49, "sos_pack_taps: bad arguments");
+  TapOffsets t;
+  for (int i = 0; i < (int)ntaps; ++i) t.off[i] = tap_off[i];
+  pack_taps_kernel<<<grid_for(rows * ntaps * KP), kThreads, 0, stream>>>(w, (int)rows, (int)K, (int)KP, row_stride, k_stride, (int)ntaps, t,
+                                                                         round_tf32, out);
+  SOS_CHECK_LAUNCH("sos_pack_taps");
   return SOS_OK;
 }
 

@@ -66,10 +66,23 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_fwd_step_kernel(const float
     for (int b0 = 0; b0 < B; b0 += kBt) {
       __syncthreads();
       if (!first) {
-        for (int e = tid; e < kBt * H; e += kLstmThreads) {
-          const int bb = e / H, k = e - bb * H;
-          // written by the other blocks of this direction during the previous step: read through L2
-          h_s[k * kHsPitch + bb] = (b0 + bb < B) ? __ldcg(out + ((size_t)tp * B + b0 + bb) * 2 * H + (size_t)d * H + k) : 0.f;
+        // h_prev was written by the other blocks of this direction during the previous step: read through L2
+        if ((H & 3) == 0) {
+          const int H4 = H >> 2;
+          for (int e = tid; e < kBt * H4; e += kLstmThreads) {
+            const int bb = e / H4, k = (e - bb * H4) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b0 + bb < B) v = __ldcg(reinterpret_cast<const float4*>(out + ((size_t)tp * B + b0 + bb) * 2 * H + (size_t)d * H + k));
+            h_s[k * kHsPitch + bb] = v.x;
+            h_s[(k + 1) * kHsPitch + bb] = v.y;
+            h_s[(k + 2) * kHsPitch + bb] = v.z;
+            h_s[(k + 3) * kHsPitch + bb] = v.w;
+          }
+        } else {
+          for (int e = tid; e < kBt * H; e += kLstmThreads) {
+            const int bb = e / H, k = e - bb * H;
+            h_s[k * kHsPitch + bb] = (b0 + bb < B) ? __ldcg(out + ((size_t)tp * B + b0 + bb) * 2 * H + (size_t)d * H + k) : 0.f;
+          }
         }
       }
       // the input-projection term of this thread's four gate values, in flight during the product
@@ -146,14 +159,36 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_bwd_step_kernel(const float
     const int r = e / kUnits, u = e - r * kUnits;    // coalescing is poor (stride H) but this runs once per launch
     w_s[e] = (k0 + u < H) ? w_hh[((size_t)d * R + r) * H + k0 + u] : 0.f;
   }
+  // The elementwise operands of a step (saved gates, cell states, dout) do not depend on the other blocks: for the first
+  // batch tile they are fetched BEFORE the inter-step barrier so that their DRAM latency overlaps the wait.
+  float pf[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto fetch = [&](int step, int b0, float (&o)[7]) {
+    const int t = d == 0 ? T - 1 - step : step;
+    const int tp = d == 0 ? t - 1 : t + 1;
+    const bool has_prev = d == 0 ? (t > 0) : (t < T - 1);
+    const int j = k0 + kk, b = b0 + bb;
+    if (j < H && b < B) {
+      const size_t gi = (((size_t)t * B + b) * 2 + d) * R + j;
+      o[0] = __ldg(gates + gi); o[1] = __ldg(gates + gi + H); o[2] = __ldg(gates + gi + 2 * H); o[3] = __ldg(gates + gi + 3 * H);
+      o[4] = __ldg(cell + (((size_t)t * B + b) * 2 + d) * H + j);
+      o[5] = has_prev ? __ldg(cell + (((size_t)tp * B + b) * 2 + d) * H + j) : 0.f;
+      o[6] = __ldg(dout + ((size_t)t * B + b) * 2 * H + (size_t)d * H + j);
+    }
+  };
+  fetch(0, 0, pf);
   for (int step = 0; step < T; ++step) {
     // backward walks each direction's time axis in reverse
     const int t = d == 0 ? T - 1 - step : step;
     const int tn = d == 0 ? t + 1 : t - 1;           // the step processed just before (later in the recurrence)
-    const int tp = d == 0 ? t - 1 : t + 1;           // earlier step in the recurrence (for c_prev)
     const bool first = step == 0;
-    const bool has_prev = d == 0 ? (t > 0) : (t < T - 1);
     for (int b0 = 0; b0 < B; b0 += kBt) {
+      float cur[7];
+      if (b0 == 0) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) cur[i] = pf[i];
+      } else {
+        fetch(step, b0, cur);
+      }
       float dh_rec = 0.f;
       if (!first) {
         float acc[kUnits];
@@ -162,9 +197,22 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_bwd_step_kernel(const float
         for (int r0 = 0; r0 < R; r0 += RC) {
           const int rc = min(RC, R - r0);
           __syncthreads();
-          for (int e = tid; e < kBt * rc; e += kLstmThreads) {
-            const int b2 = e / rc, rr = e - b2 * rc;
-            g_s[rr * kGsPitch + b2] = (b0 + b2 < B) ? __ldcg(dgx + (((size_t)tn * B + b0 + b2) * 2 + d) * R + r0 + rr) : 0.f;
+          if (((rc | r0) & 3) == 0) {
+            const int rc4 = rc >> 2;
+            for (int e = tid; e < kBt * rc4; e += kLstmThreads) {
+              const int b2 = e / rc4, rr = (e - b2 * rc4) * 4;
+              float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (b0 + b2 < B) v = __ldcg(reinterpret_cast<const float4*>(dgx + (((size_t)tn * B + b0 + b2) * 2 + d) * R + r0 + rr));
+              g_s[rr * kGsPitch + b2] = v.x;
+              g_s[(rr + 1) * kGsPitch + b2] = v.y;
+              g_s[(rr + 2) * kGsPitch + b2] = v.z;
+              g_s[(rr + 3) * kGsPitch + b2] = v.w;
+            }
+          } else {
+            for (int e = tid; e < kBt * rc; e += kLstmThreads) {
+              const int b2 = e / rc, rr = e - b2 * rc;
+              g_s[rr * kGsPitch + b2] = (b0 + b2 < B) ? __ldcg(dgx + (((size_t)tn * B + b0 + b2) * 2 + d) * R + r0 + rr) : 0.f;
+            }
           }
           __syncthreads();
           const int per = (rc + 7) >> 3;
@@ -187,11 +235,9 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_bwd_step_kernel(const float
       const int j = k0 + kk, b = b0 + bb;
       if (j < H && b < B) {
         const size_t gi = (((size_t)t * B + b) * 2 + d) * R + j;
-        const float ig = gates[gi], fg = gates[gi + H], gg = gates[gi + 2 * H], og = gates[gi + 3 * H];
-        const float c = cell[(((size_t)t * B + b) * 2 + d) * H + j];
-        const float cp = has_prev ? cell[(((size_t)tp * B + b) * 2 + d) * H + j] : 0.f;
+        const float ig = cur[0], fg = cur[1], gg = cur[2], og = cur[3], c = cur[4], cp = cur[5];
         const float tc = tanhf(c);
-        const float dh = dout[((size_t)t * B + b) * 2 * H + (size_t)d * H + j] + dh_rec;
+        const float dh = cur[6] + dh_rec;
         const size_t ci = ((size_t)b * 2 + d) * H + j;
         const float dc = dh * og * (1.f - tc * tc) + (first ? 0.f : dc_ws[ci]);
         dgx[gi] = dc * gg * ig * (1.f - ig);
@@ -201,7 +247,10 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_bwd_step_kernel(const float
         dc_ws[ci] = dc * fg;
       }
     }
-    if (step + 1 < T) dir_barrier(sync + d, (unsigned)(step + 1) * gridDim.x);
+    if (step + 1 < T) {
+      fetch(step + 1, 0, pf);
+      dir_barrier(sync + d, (unsigned)(step + 1) * gridDim.x);
+    }
   }
 }
 

@@ -70,12 +70,8 @@ class ConvGeom:
 
 
 def _pack_fwd(w, taps, cin_p):
-    """(Cout, Cin, kh, kw) -> (Cout, len(taps)*cin_p), k = t*cin_p + ci."""
-    Cout, Cin = w.shape[0], w.shape[1]
-    sel = torch.stack([w[:, :, a, b] for a, b in taps], dim=1)            # (Cout, ntaps, Cin)
-    if cin_p != Cin:
-        sel = torch.nn.functional.pad(sel, (0, cin_p - Cin))
-    return ops.round_tf32_(sel.reshape(Cout, len(taps) * cin_p).contiguous())     # torch.stack made a fresh tensor
+    """(Cout, Cin, kh, kw) view -> (Cout, len(taps)*cin_p), k = t*cin_p + ci, TF32-rounded (one gather kernel)."""
+    return ops.pack_taps(w.detach(), taps, cin_p, round_tf32=True)
 
 
 def _conv_forward(x, w, g, epi=None):

@@ -292,6 +292,20 @@ def _i32arr(v):
     return (_I32 * len(v))(*[int(a) for a in v])
 
 
+def pack_taps(w, taps, k_padded, round_tf32=True):
+    """w: 4-D weight view (rows, K, kh, kw) with arbitrary strides over one storage -> (rows, len(taps)*k_padded) GEMM operand,
+    column t*k_padded + k = w[r, k, taps[t][0], taps[t][1]] (zero padded, TF32-rounded): one launch."""
+    assert w.dim() == 4 and w.is_cuda and w.dtype == torch.float32
+    R, K = w.shape[0], w.shape[1]
+    st = w.stride()
+    out = torch.empty(R, len(taps) * k_padded, device=w.device, dtype=torch.float32)
+    offs = _i32arr([a * st[2] + b * st[3] for a, b in taps])
+    check(lib().sos_pack_taps(C.c_void_p(w.data_ptr()), R, K, k_padded, st[0], st[1], len(taps), offs, int(round_tf32), _p(out), _stream()),
+          "sos_pack_taps")
+    _count()
+    return out
+
+
 def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lattice=(1, 1, 0, 0), epi_scale=None, epi_shift=None,
             act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag="conv_fwd"):
     """Tap-list implicit GEMM on tcgen05 (see include/sos_b200.h: sos_conv2d_tc).
