@@ -111,6 +111,8 @@ __device__ __forceinline__ long long view_pix(const View& v, long long pix) {   
 }
 
 // ----------------------------------------------------------------------------- BatchNorm
+constexpr int kUnroll = 4;          // independent 16-byte loads per array kept in flight by a thread
+__device__ __forceinline__ float4 ld_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 // y dense [P][C]; each thread owns one float4 channel group and strides over rows.
 __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const float* __restrict__ y, long long P, int C,
                                                              float* __restrict__ partial /*[grid][2][C]*/) {
@@ -120,10 +122,19 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const float* __restr
   const int r = threadIdx.x / cg, c4 = threadIdx.x - r * cg;
   float4 s = {0, 0, 0, 0}, q = {0, 0, 0, 0};
   if (r < rows) {
-    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
-      const float4 v = *reinterpret_cast<const float4*>(y + p * C + c4 * 4);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    const long long stride = (long long)gridDim.x * rows;
+    for (long long p0 = (long long)blockIdx.x * rows + r; p0 < P; p0 += stride * 4) {
+      float4 v4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (p0 + u * stride < P) v4[u] = __ldcs(reinterpret_cast<const float4*>(y + (p0 + u * stride) * C + c4 * 4));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (p0 + u * stride >= P) break;
+        const float4 v = v4[u];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+      }
     }
     float* d = sm + (size_t)r * 2 * C;
     *reinterpret_cast<float4*>(d + c4 * 4) = s;
@@ -249,18 +260,31 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __
     float sc[4], sh[4], mu[4], is[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { sc[i] = scale[c + i]; sh[i] = shift[c + i]; mu[i] = mean[c + i]; is[i] = invstd[c + i]; }
-    for (long long p = (long long)blockIdx.x * rows + r; p < P; p += (long long)gridDim.x * rows) {
-      const float4 yv4 = *reinterpret_cast<const float4*>(y + p * C + c);
-      const float4 dz4 = *reinterpret_cast<const float4*>(dz + view_pix(dzv, p) + c);
-      const float yv[4] = {yv4.x, yv4.y, yv4.z, yv4.w}, dv[4] = {dz4.x, dz4.y, dz4.z, dz4.w};
+    const long long stride = (long long)gridDim.x * rows;
+    const bool dense = dzv.Hp == dzv.H && dzv.Wp == dzv.W && dzv.ph == 0 && dzv.pw == 0 && dzv.ld == C && dzv.coff == 0;
+    for (long long p0 = (long long)blockIdx.x * rows + r; p0 < P; p0 += stride * kUnroll) {
+      float4 yv4[kUnroll], dz4[kUnroll];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float pre = fmaf(yv[i], sc[i], sh[i]);
-        float dpre = dv[i];
-        if (act == 1) dpre = pre > 0.f ? dpre : 0.f;
-        else if (act == 2) { if (pre <= 0.f) { s3[i] = fmaf(dv[i], pre, s3[i]); dpre *= slope; } }
-        s1[i] += dpre;
-        s2[i] = fmaf(dpre, (yv[i] - mu[i]) * is[i], s2[i]);
+      for (int u = 0; u < kUnroll; ++u) {                // kUnroll independent row loads in flight per thread
+        const long long p = p0 + u * stride;
+        if (p < P) {
+          yv4[u] = ld_stream(y + p * C + c);
+          dz4[u] = ld_stream(dz + (dense ? p * C : view_pix(dzv, p)) + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        if (p0 + u * stride >= P) break;
+        const float yv[4] = {yv4[u].x, yv4[u].y, yv4[u].z, yv4[u].w}, dv[4] = {dz4[u].x, dz4[u].y, dz4[u].z, dz4[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float pre = fmaf(yv[i], sc[i], sh[i]);
+          float dpre = dv[i];
+          if (act == 1) dpre = pre > 0.f ? dpre : 0.f;
+          else if (act == 2) { if (pre <= 0.f) { s3[i] = fmaf(dv[i], pre, s3[i]); dpre *= slope; } }
+          s1[i] += dpre;
+          s2[i] = fmaf(dpre, (yv[i] - mu[i]) * is[i], s2[i]);
+        }
       }
     }
     float* d = sm + (size_t)r * 3 * C;
@@ -330,6 +354,92 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __r
       if (rnd) o[i] = tf32_rna(o[i]);
     }
     *reinterpret_cast<float4*>(dy + p * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+
+// ----------------------------------------------------------------------------- dense fast paths
+// When every operand is a dense [P][C] array, float4 element e lives at 4*e in all of them: no pixel arithmetic, and each thread
+// keeps kUnroll independent 16-byte loads per array in flight (the grid-stride float4 loops above leave ~32 KB per SM in flight,
+// which caps them near 4.5 TB/s; HBM needs ~45 KB per SM).
+
+__global__ void __launch_bounds__(kThreads) bn_act_dense_kernel(const float* __restrict__ y, float* __restrict__ z, unsigned total, unsigned cg,
+                                                                 const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                                                 const float* __restrict__ slope_ptr) {
+  const float slope = slope_ptr ? *slope_ptr : 0.f;
+  const bool rnd = (act & SOS_ACT_ROUND_TF32) != 0;
+  act &= SOS_ACT_MASK;
+  const unsigned span = gridDim.x * blockDim.x;
+  for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += span * kUnroll) {
+    float4 v[kUnroll];
+#pragma unroll
+    for (int i = 0; i < kUnroll; ++i) {
+      const unsigned e = e0 + i * span;
+      if (e < total) v[i] = ld_stream(y + (size_t)e * 4);
+    }
+#pragma unroll
+    for (int i = 0; i < kUnroll; ++i) {
+      const unsigned e = e0 + i * span;
+      if (e >= total) break;
+      const unsigned c = (e % cg) * 4;
+      const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+      float4 o;
+      o.x = act_fwd(fmaf(v[i].x, sc.x, sh.x), act, slope);
+      o.y = act_fwd(fmaf(v[i].y, sc.y, sh.y), act, slope);
+      o.z = act_fwd(fmaf(v[i].z, sc.z, sh.z), act, slope);
+      o.w = act_fwd(fmaf(v[i].w, sc.w, sh.w), act, slope);
+      if (rnd) { o.x = tf32_rna(o.x); o.y = tf32_rna(o.y); o.z = tf32_rna(o.z); o.w = tf32_rna(o.w); }
+      *reinterpret_cast<float4*>(z + (size_t)e * 4) = o;
+    }
+  }
+}
+
+// mode 0: BatchNorm backward pass 2 (needs mean / invstd / m1 / m2); mode 1: eval-mode affine backward
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_dense_kernel(const float* __restrict__ dz, const float* __restrict__ y,
+                                                                       float* __restrict__ dy, unsigned total, unsigned cg,
+                                                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                       const float* __restrict__ m1, const float* __restrict__ m2, int act,
+                                                                       const float* __restrict__ slope_ptr) {
+  const float slope = slope_ptr ? *slope_ptr : 0.f;
+  const bool rnd = (act & SOS_ACT_ROUND_TF32) != 0;
+  act &= SOS_ACT_MASK;
+  const unsigned span = gridDim.x * blockDim.x;
+  for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += span * kUnroll) {
+    float4 yv4[kUnroll], dz4[kUnroll];
+#pragma unroll
+    for (int i = 0; i < kUnroll; ++i) {
+      const unsigned e = e0 + i * span;
+      if (e < total) {
+        yv4[i] = ld_stream(y + (size_t)e * 4);
+        dz4[i] = ld_stream(dz + (size_t)e * 4);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kUnroll; ++i) {
+      const unsigned e = e0 + i * span;
+      if (e >= total) break;
+      const unsigned c = (e % cg) * 4;
+      const float yv[4] = {yv4[i].x, yv4[i].y, yv4[i].z, yv4[i].w}, dv[4] = {dz4[i].x, dz4[i].y, dz4[i].z, dz4[i].w};
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float sc = scale[c + k];
+        const float pre = fmaf(yv[k], sc, shift[c + k]);
+        float dpre = dv[k];
+        if (act == 1) dpre = pre > 0.f ? dpre : 0.f;
+        else if (act == 2) dpre = pre > 0.f ? dpre : dpre * slope;
+        if (MODE == 0) {
+          const float xhat = (yv[k] - mean[c + k]) * invstd[c + k];
+          o[k] = sc * (dpre - m1[c + k] - xhat * m2[c + k]);
+        } else {
+          o[k] = sc * dpre;
+        }
+        if (rnd) o[k] = tf32_rna(o[k]);
+      }
+      *reinterpret_cast<float4*>(dy + (size_t)e * 4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
   }
 }
 
@@ -690,6 +800,7 @@ int sos_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 
 // views are passed as 8 ints: H, W, Hp, Wp, ph, pw, ld, coff
 static View mk_view(const int32_t* v) { return View{v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]}; }
+static bool view_dense(const View& v, int C) { return v.Hp == v.H && v.Wp == v.W && v.ph == 0 && v.pw == 0 && v.ld == C && v.coff == 0; }
 static bool view_ok(const View& v, int C) {
   return v.H > 0 && v.W > 0 && v.Hp >= v.H + v.ph && v.Wp >= v.W + v.pw && v.ph >= 0 && v.pw >= 0 && v.ld >= v.coff + C &&
          (v.ld % 4) == 0 && (v.coff % 4) == 0;
@@ -741,7 +852,12 @@ int sos_bn_act(const float* y, float* z, const int32_t* z_view, int64_t rows, in
   const View zv = mk_view(z_view);
   SOS_CHECK_ARG(view_ok(zv, (int)channels) && rows % ((long long)zv.H * zv.W) == 0, "sos_bn_act: inconsistent view");
   SOS_CHECK_ARG((act & SOS_ACT_MASK) != 2 || slope, "sos_bn_act: PReLU needs a slope pointer");
-  bn_act_kernel<<<grid_for(rows * (channels / 4)), kThreads, 0, stream>>>(y, z, rows, (int)channels, scale, shift, act, slope, zv);
+  const long long tot4 = rows * (channels / 4);
+  if (view_dense(zv, (int)channels) && tot4 < (1ll << 32))
+    bn_act_dense_kernel<<<grid_for(tot4, kThreads * kUnroll, 148 * 8), kThreads, 0, stream>>>(y, z, (unsigned)tot4, (unsigned)(channels / 4), scale,
+                                                                                              shift, act, slope);
+  else
+    bn_act_kernel<<<grid_for(tot4), kThreads, 0, stream>>>(y, z, rows, (int)channels, scale, shift, act, slope, zv);
   SOS_CHECK_LAUNCH("sos_bn_act");
   return SOS_OK;
 }
@@ -763,8 +879,12 @@ int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y,
   SOS_CHECK_LAUNCH("sos_bn_act_backward(reduce)");
   bn_bwd_finalize_kernel<<<ceil_div(C, 32), 256, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta, (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2);
   SOS_CHECK_LAUNCH("sos_bn_act_backward(finalize)");
-  bn_bwd_apply_kernel<<<grid_for(rows * (channels / 4)), kThreads, 0, stream>>>(dz, dv, y, dy, rows, C, scale, shift, mean, invstd, m1,
-                                                                                 m2, act, slope);
+  const long long tot4 = rows * (channels / 4);
+  if (view_dense(dv, C) && tot4 < (1ll << 32))
+    bn_bwd_apply_dense_kernel<0><<<grid_for(tot4, kThreads * kUnroll, 148 * 8), kThreads, 0, stream>>>(
+        dz, y, dy, (unsigned)tot4, (unsigned)(channels / 4), scale, shift, mean, invstd, m1, m2, act, slope);
+  else
+    bn_bwd_apply_kernel<<<grid_for(tot4), kThreads, 0, stream>>>(dz, dv, y, dy, rows, C, scale, shift, mean, invstd, m1, m2, act, slope);
   SOS_CHECK_LAUNCH("sos_bn_act_backward(apply)");
   return SOS_OK;
 }
@@ -776,8 +896,12 @@ int sos_affine_act_backward(const float* dz, const int32_t* dz_view, const float
   const View dv = mk_view(dz_view);
   SOS_CHECK_ARG(view_ok(dv, (int)channels) && rows % ((long long)dv.H * dv.W) == 0, "sos_affine_act_backward: inconsistent view");
   SOS_CHECK_ARG((act & SOS_ACT_MASK) != 2 || slope, "sos_affine_act_backward: PReLU needs a slope pointer");
-  affine_act_bwd_kernel<<<grid_for(rows * (channels / 4)), kThreads, 0, stream>>>(dz, dv, y, dy, rows, (int)channels, scale, shift, act,
-                                                                                   slope);
+  const long long tot4 = rows * (channels / 4);
+  if (view_dense(dv, (int)channels) && tot4 < (1ll << 32))
+    bn_bwd_apply_dense_kernel<1><<<grid_for(tot4, kThreads * kUnroll, 148 * 8), kThreads, 0, stream>>>(
+        dz, y, dy, (unsigned)tot4, (unsigned)(channels / 4), scale, shift, nullptr, nullptr, nullptr, nullptr, act, slope);
+  else
+    affine_act_bwd_kernel<<<grid_for(tot4), kThreads, 0, stream>>>(dz, dv, y, dy, rows, (int)channels, scale, shift, act, slope);
   SOS_CHECK_LAUNCH("sos_affine_act_backward");
   return SOS_OK;
 }

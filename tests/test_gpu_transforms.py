@@ -91,7 +91,8 @@ def test_icrm_forward_backward(cuda):
     c2 = crm.detach().to(cuda).requires_grad_(True)
     got = transform.batch_fast_icRM_sigmoid(Y.to(cuda), c2)
     got.backward(go.to(cuda))
-    assert float((got.cpu() - ref.detach()).abs().max()) < 1e-3
+    # M = 10*log(crm/(1-crm)) reaches +-46 and |rec| ~ 150: fp32 log/divide differ by a few ulp between libm and the device
+    assert float((got.cpu() - ref.detach()).abs().max()) < 2e-5 * float(ref.detach().abs().max())
     assert float((c2.grad.cpu() - crm.grad).abs().max() / crm.grad.abs().max()) < 1e-4
 
 
