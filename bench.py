@@ -326,6 +326,63 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_infer(args):
+    """BASELINE configs[0] / configs[3]: forward-only in-memory inference (STFT -> SID -> gate -> STFT -> JointModel -> cRM + iSTFT)
+    at --batch clips; NOT the default workload (that is the training step).  One JSON line."""
+    import torch
+    import sos_b200  # noqa: F401
+    from sos_b200 import _lib, networks, ops, pipeline
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the sos_b200 hot path has no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    ops.init()
+    B, L = args.batch, args.length
+    torch.manual_seed(0)
+    sid = networks.get_network().to(dev).eval()
+    torch.manual_seed(1)
+    joint = networks.get_network(object()).to(dev).eval()
+    host = torch.from_numpy(synth_batch(min(B, 32), L)["mixed"]).repeat((B + 31) // 32, 1)[:B].contiguous().pin_memory()
+    resident = host.to(dev)
+    out_host = torch.empty(B, 158 * (L // 158), dtype=torch.float32).pin_memory()
+    fpc = 256 if L > 64000 else None
+
+    def step(e2e):
+        w = host.to(dev, non_blocking=True) if e2e else resident
+        out = pipeline.denoise(w, sid, joint, SR, FPS, frames_per_chunk=fpc)
+        if e2e:
+            out_host.copy_(out["denoised"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    def timed(e2e):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step(e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    n0 = _lib.launch_count
+    ms = timed(False)
+    launches = _lib.launch_count - n0
+    ms_e2e = timed(True)
+    clips = B * args.steps
+    print(json.dumps({
+        "metric": "clips/sec forward-only inference", "value": clips / (ms * 1e-3), "unit": "clips/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": f"batch={B} clips of {L} samples @16 kHz, STFT->SID->gate->STFT->JointModel->cRM+iSTFT, forward only "
+                               "(BASELINE configs[0]/[3]/[4])", "batch": B, "samples_per_clip": L, "frames": 1 + L // 158,
+                   "chunked_transforms": bool(fpc)},
+        "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": "clips/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
+        "gpu_launches": launches}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -335,9 +392,14 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
     ap.add_argument("--ref-batch", type=int, default=2, help="clips per step of the CPU arm (a bounded sample of the workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="train", choices=["train", "infer"], help="train = BASELINE configs[1] (default, the metric); "
+                    "infer = forward-only inference at --batch / --length")
+    ap.add_argument("--length", type=int, default=LENGTH, help="samples per clip (infer workload)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "infer":
+        run_infer(args)
     else:
         run_gpu(args)
 

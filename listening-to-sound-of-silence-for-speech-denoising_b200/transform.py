@@ -41,6 +41,39 @@ def istft_batch(spec, crm=None):
     return ops.istft(spec.contiguous(), None if crm is None else crm.contiguous())
 
 
+def stft_chunked(waves, frames_per_chunk=256):
+    """Long-form STFT (BASELINE configs[4]: 10 s clips): the frame axis is processed in chunks of `frames_per_chunk`, each from a
+    waveform segment that overlaps its neighbours by two hops so that no kept frame touches a segment edge; only the global
+    ends are reflect-padded.  Bit-identical to `stft_batch` on the whole waveform."""
+    B, L = waves.shape
+    T = 1 + L // HOP_LENGTH
+    out = torch.empty(B, 2, 256, T, device=waves.device, dtype=torch.float32)
+    for t0 in range(0, T, frames_per_chunk):
+        t1 = min(T, t0 + frames_per_chunk)
+        lead = 2 if t0 > 0 else 0
+        a = HOP_LENGTH * (t0 - lead)
+        b = L if t1 == T else min(L, HOP_LENGTH * (t1 - 1 + 2) + 1)
+        if b < L and b - HOP_LENGTH * (t1 - 1) < N_FFT // 2 + 1:
+            b = L
+        seg = stft_batch(waves[:, a:b].contiguous())
+        out[:, :, :, t0:t1] = seg[:, :, :, lead:lead + (t1 - t0)]
+    return out
+
+
+def istft_chunked(spec, frames_per_chunk=256, crm=None):
+    """Streaming overlap-add: the inverse transform of frame chunks (each with a two-frame margin on both sides) written into
+    consecutive 158-sample hops of the output.  Bit-identical to `istft_batch` on the whole spectrogram."""
+    B, _, F, T = spec.shape
+    out = torch.empty(B, HOP_LENGTH * (T - 1), device=spec.device, dtype=torch.float32)
+    for t0 in range(0, T - 1, frames_per_chunk):
+        t1 = min(T - 1, t0 + frames_per_chunk)                 # output hops [t0, t1)
+        ta, tb = max(0, t0 - 2), min(T, t1 + 3)
+        seg = istft_batch(spec[:, :, :, ta:tb].contiguous(), None if crm is None else crm[:, :, :, ta:tb].contiguous())
+        s0 = HOP_LENGTH * (t0 - ta)
+        out[:, HOP_LENGTH * t0:HOP_LENGTH * t1] = seg[:, s0:s0 + HOP_LENGTH * (t1 - t0)]
+    return out
+
+
 def fast_stft(data, power=False, n_fft=N_FFT, hop_length=HOP_LENGTH, win_length=WIN_LENGTH):
     _check_fixed(n_fft, hop_length, win_length)
     if power:

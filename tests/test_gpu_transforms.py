@@ -203,3 +203,64 @@ def test_bilstm_matches_torch(cuda, I, H, T, B):
     assert float((xd.grad.cpu() - x.grad).abs().max()) < 1e-5
     for (k, p), (_, q) in zip(ref.named_parameters(), mine.named_parameters()):
         assert float((q.grad.cpu() - p.grad).abs().max()) < 1e-4 * float(p.grad.abs().max() + 1), k
+
+
+def test_longform_chunked_equals_unchunked(cuda):
+    """BASELINE configs[4]: 10 s clips (L = 160000, T = 1013): the chunked STFT and the streaming overlap-add are bit-identical
+    to the one-shot transforms, also for ragged chunk sizes and with the fused cRM recovery."""
+    from sos_b200 import transform
+    g = torch.Generator().manual_seed(21)
+    wave = (torch.randn(2, 160000, generator=g) * 0.2).to(cuda)
+    whole = transform.stft_batch(wave)
+    assert whole.shape == (2, 2, 256, 1013)
+    for fpc in (256, 300, 1013, 97):
+        assert torch.equal(transform.stft_chunked(wave, fpc), whole), fpc
+    w_whole = transform.istft_batch(whole)
+    crm = (torch.rand(whole.shape, generator=g) * 0.9 + 0.05).to(cuda)
+    w_crm = transform.istft_batch(whole, crm)
+    for fpc in (256, 300, 1012, 97):
+        assert torch.equal(transform.istft_chunked(whole, fpc), w_whole), fpc
+        assert torch.equal(transform.istft_chunked(whole, fpc, crm=crm), w_crm), fpc
+    # and against the oracle at this length
+    from oracle import transform as otf
+    ref = otf.stft_batch(wave[:1].cpu().numpy())
+    assert float((whole[:1].cpu() - torch.tensor(ref)).abs().max()) < 3e-4
+
+
+def test_denoise_pipeline_matches_oracle(cuda):
+    """The in-memory inference pipeline (STFT -> SID -> threshold -> gate -> STFT -> JointModel -> cRM + iSTFT) against the CPU
+    oracle run stage by stage.  The detector's 0.5 threshold is a discontinuity, so the oracle's downstream stages are fed the
+    bits the device produced; bits are compared wherever the oracle's confidence is not within 0.02 of the threshold."""
+    from sos_b200 import networks, pipeline
+    from oracle import gating, nets, synth, transform as otf
+    L, sr, fps = 12640, 16000, 30.0
+    clips = synth.make_batch(2, length=L)
+    wave = torch.tensor(clips["mixed"], device=cuda)
+    sid = networks.get_network()
+    sid.load_state_dict(nets.synth_state_dict(nets.sid_shapes(), 3))
+    joint = networks.get_network(object())
+    joint.load_state_dict(nets.synth_state_dict(nets.joint_shapes(), 4))
+    sid, joint = sid.to(cuda).eval(), joint.to(cuda).eval()
+    out = pipeline.denoise(wave, sid, joint, sr, fps)
+    n_bits = int(L / (sr / fps))
+    assert out["bits"].shape == (2, n_bits) and out["denoised"].shape == (2, 158 * (L // 158))
+    # oracle, stage by stage
+    mixed = torch.tensor(otf.stft_batch(clips["mixed"]))
+    with torch.no_grad():
+        logits = nets.sid_forward(nets.synth_state_dict(nets.sid_shapes(), 3), mixed, n_bits, training=False)
+    conf = torch.sigmoid(logits)
+    assert float((out["confidence"].cpu() - conf).abs().max()) < 5e-3
+    sure = (conf - 0.5).abs() > 0.02
+    assert bool(((out["bits"].cpu() > 0) == (conf >= 0.5))[sure].all())
+    bit_strings = ["".join(str(int(b)) for b in row) for row in out["bits"].cpu().numpy()]
+    noise_w = np.stack([gating.gate_noise(clips["mixed"][i], sr / fps, bit_strings[i]) for i in range(2)]).astype(np.float32)
+    noise = torch.tensor(otf.stft_batch(noise_w))
+    with torch.no_grad():
+        n_pred, mask = nets.joint_forward(nets.synth_state_dict(nets.joint_shapes(), 4), mixed, noise, training=False)
+    rec = otf.batch_fast_icRM_sigmoid(mixed, mask)
+    den = otf.istft_batch(rec.numpy())
+    e_mask = float((out["mask"].cpu() - mask).abs().mean())
+    e_wave = float(np.abs(out["denoised"].cpu().numpy() - den).mean())
+    print(f"denoise pipeline: mask L1 {e_mask:.2e}, waveform L1 {e_wave:.2e} (|wave| mean {np.abs(den).mean():.3f})")
+    assert e_mask < 1e-3                                            # north_star bar
+    assert e_wave < 2e-2 * float(np.abs(den).mean()) + 1e-4         # cRM recovery amplifies mask error x40 at crm = 0.5
