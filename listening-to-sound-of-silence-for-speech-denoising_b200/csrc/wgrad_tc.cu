@@ -14,6 +14,13 @@
 // TMEM; the pixel tiles are split into slices so that all SMs are busy and jobs of the same slice run concurrently
 // (their operand boxes hit in L2).  Partial sums are merged with fp32 atomics (red.global.add).
 //
+// Stacked mode (32 < Cout <= 64): an M = 128 MMA would be at least half empty, so accumulator rows 64..127 are given to a
+// SECOND tap: the dy box shifted by `delta` pixels along the fast axis (same tensor map, box origin + delta; the row tail reads
+// as zero) is staged as M chunks 2-3 next to dy[p] in chunks 0-1.  With the x box of the tap group at fast offset f, rows 0..63 then accumulate
+// that group's taps and rows 64..127 the taps of the group at fast offset f - delta: one MMA serves two taps (5 x 5 taps ->
+// 15 accumulators instead of 25).  The shifted half sees dy columns [delta, W + delta), so the tile grid is extended to
+// negative fast coordinates (zero-filled) to cover columns [0, delta) as well.
+//
 // CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 drain TMEM at the end of each work item.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -27,9 +34,15 @@ using namespace tc;
 
 constexpr int kThreadsWg = 192;
 constexpr int kMaxJobs = 100;
+constexpr int kMaxSlots = 64;
+
+// One TMEM accumulator of a job: x box `x_idx` of the stage shifted by `shift` slow rows; accumulator rows 0..63 (all 128
+// when not stacked) receive tap `tap_lo`, rows 64..127 tap `tap_hi` (-1: unused).
+struct WgSlot { int16_t x_idx, shift, tap_lo, tap_hi; };
 
 struct alignas(64) WgParams {
   CUtensorMap mapX, mapDY;
+  int stacked, delta, tf_extra;      // delta: fast-axis shift of the stacked dy box; tf_extra: tile columns added at negative fast coordinates
   int n_jobs, n_slices, tiles_per_slice, total_tiles;
   int tiles_fast, tiles_slow, n_phase;
   int FB, SB, stride;
@@ -41,14 +54,16 @@ struct alignas(64) WgParams {
   int layout_a, layout_b;
   uint32_t idesc;
   float* dw;
-  int16_t job_coblk[kMaxJobs], job_g0[kMaxJobs], job_ng[kMaxJobs];
+  int16_t job_coblk[kMaxJobs], job_g0[kMaxJobs], job_ng[kMaxJobs], job_s0[kMaxJobs], job_ns[kMaxJobs];
+  int16_t job_group[kMaxJobs * 4];   // tap groups whose x boxes a job stages (job_g0 = first index, job_ng = count)
+  WgSlot slots[kMaxSlots];
   TapGroup groups[kMaxGroups];
 };
 
 struct WgTile { int tf, ts, ph, n; };
 __device__ __forceinline__ WgTile decode_wg_tile(const WgParams& p, int t) {
   WgTile c;
-  c.tf = t % p.tiles_fast; t /= p.tiles_fast;
+  c.tf = t % p.tiles_fast - p.tf_extra; t /= p.tiles_fast;
   c.ts = t % p.tiles_slow; t /= p.tiles_slow;
   c.ph = t % p.n_phase;
   c.n = t / p.n_phase;
@@ -104,7 +119,7 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
       const int coblk = p.job_coblk[job], g0 = p.job_g0[job], ng = p.job_ng[job];
       const int co_here = min(128, p.Cout - coblk * 128);
       const int n_co_chunks = (co_here + p.cbo - 1) / p.cbo;
-      const uint32_t tx = (uint32_t)n_co_chunks * p.dy_chunk_bytes + (uint32_t)ng * p.n_ci_chunks * p.x_box_bytes;
+      const uint32_t tx = (uint32_t)n_co_chunks * (p.stacked ? 2 : 1) * p.dy_chunk_bytes + (uint32_t)ng * p.n_ci_chunks * p.x_box_bytes;
       for (int tile = t0; tile < t1; ++tile) {
         const WgTile tc = decode_wg_tile(p, tile);
         mbar_wait(empty_bar(stage), phase ^ 1, 500);
@@ -114,8 +129,12 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
           for (int cc = 0; cc < n_co_chunks; ++cc)
             tma_load_5d(sbase + (uint32_t)cc * p.dy_chunk_stride, &p.mapDY, full_bar(stage), coblk * 128 + cc * p.cbo, tc.tf * p.FB,
                         tc.ts * p.SB, tc.ph, tc.n);
+          if (p.stacked)
+            for (int cc = 0; cc < n_co_chunks; ++cc)     // M chunks 2, 3: the same channels, `delta` pixels further along the fast axis
+              tma_load_5d(sbase + (uint32_t)(2 + cc) * p.dy_chunk_stride, &p.mapDY, full_bar(stage), cc * p.cbo, tc.tf * p.FB + p.delta,
+                          tc.ts * p.SB, tc.ph, tc.n);
           for (int gi = 0; gi < ng; ++gi) {
-            const TapGroup& grp = p.groups[g0 + gi];
+            const TapGroup& grp = p.groups[p.job_group[g0 + gi]];
             const uint32_t xb = sbase + p.x_off + (uint32_t)gi * p.n_ci_chunks * p.x_box_stride;
             for (int c = 0; c < p.n_ci_chunks; ++c)
               tma_load_5d(xb + (uint32_t)c * p.x_box_stride, &p.mapX, full_bar(stage), c * p.cbi, tc.tf * p.FB * p.stride + grp.d_fast,
@@ -140,7 +159,7 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
       const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
       const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
       if (t0 >= t1) continue;
-      const int g0 = p.job_g0[job], ng = p.job_ng[job];
+      const int s0 = p.job_s0[job], ns = p.job_ns[job];
       mbar_wait(tempty_bar, acc_phase ^ 1, 600);
       tc_fence_after();
       for (int tile = t0; tile < t1; ++tile) {
@@ -150,22 +169,19 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
           // descriptor words: hi = SBO (512) | version | layout 1; lo = (address >> 4) | LBO (chunk pitch); one k step = 8 pixels
           const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
           const uint32_t a_lo0 = (sbase >> 4) | (((uint32_t)p.dy_chunk_stride >> 4) << 16);
+          const uint32_t xbase = sbase + p.x_off;
           const uint32_t first = tile != t0 ? 1u : 0u;
-          int slot = 0;
-          for (int gi = 0; gi < ng; ++gi) {
-            const TapGroup& grp = p.groups[g0 + gi];
-            const uint32_t xb = sbase + p.x_off + (uint32_t)gi * p.n_ci_chunks * p.x_box_stride;
-            const int n_sub = grp.n_sub;
-            for (int j = 0; j < n_sub; ++j, ++slot) {
-              const uint32_t d = tmem_base + (uint32_t)slot * p.N;
-              uint32_t a_lo = a_lo0;
-              uint32_t b_lo = ((xb + (uint32_t)(grp.a_off[j] * p.shift_mul) * b_kstep) >> 4) | x_lbo_bits;
+          for (int i = 0; i < ns; ++i) {
+            const WgSlot sl = p.slots[s0 + i];
+            const uint32_t d = tmem_base + (uint32_t)i * p.N;
+            const uint32_t xb = xbase + (uint32_t)sl.x_idx * p.n_ci_chunks * p.x_box_stride;
+            uint32_t a_lo = a_lo0;
+            uint32_t b_lo = ((xb + (uint32_t)(sl.shift * p.shift_mul) * b_kstep) >> 4) | x_lbo_bits;
 #pragma unroll 4
-              for (int ks = 0; ks < ksteps; ++ks) {
-                umma_tf32_wg(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, first | (uint32_t)ks);
-                a_lo += a_inc;
-                b_lo += b_inc;
-              }
+            for (int ks = 0; ks < ksteps; ++ks) {
+              umma_tf32_wg(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, first | (uint32_t)ks);
+              a_lo += a_inc;
+              b_lo += b_inc;
             }
           }
           umma_commit(empty_bar(stage));
@@ -184,24 +200,23 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
       const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
       const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
       if (t0 >= t1) continue;
-      const int coblk = p.job_coblk[job], g0 = p.job_g0[job], ng = p.job_ng[job];
-      const int co = coblk * 128 + q * 32 + lane;
+      const int coblk = p.job_coblk[job], s0 = p.job_s0[job], ns = p.job_ns[job];
+      // accumulator row q*32 + lane: output channel, and (stacked) which of the slot's two taps
+      const int co = p.stacked ? (q & 1) * 32 + lane : coblk * 128 + q * 32 + lane;
       mbar_wait(tfull_bar, acc_phase, 700);
       tc_fence_after();
-      int slot = 0;
-      for (int gi = 0; gi < ng; ++gi) {
-        const TapGroup& grp = p.groups[g0 + gi];
-        for (int j = 0; j < grp.n_sub; ++j, ++slot) {
-          float* dst = p.dw + ((size_t)grp.tap[j] * p.Cout + co) * p.Cin;
-          for (int c0 = 0; c0 < p.N; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * p.N + c0), r);
-            tmem_ld_wait();
-            if (co < p.Cout) {
+      for (int i = 0; i < ns; ++i) {
+        const WgSlot sl = p.slots[s0 + i];
+        const int tap = (p.stacked && (q >> 1)) ? sl.tap_hi : sl.tap_lo;
+        float* dst = p.dw + ((size_t)(tap < 0 ? 0 : tap) * p.Cout + co) * p.Cin;
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * p.N + c0), r);
+          tmem_ld_wait();
+          if (co < p.Cout && tap >= 0) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (c0 + i < p.Cin) atomicAdd(dst + c0 + i, __uint_as_float(r[i]));
-            }
+            for (int k = 0; k < 16; ++k)
+              if (c0 + k < p.Cin) atomicAdd(dst + c0 + k, __uint_as_float(r[k]));
           }
         }
       }
@@ -275,20 +290,65 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG(n_groups <= kMaxGroups, "sos_conv2d_wgrad: too many tap groups");
   for (int i = 0; i < n_groups; ++i) {
     p.groups[i] = pl.groups[i];
-    SOS_CHECK_ARG(pl.groups[i].n_sub <= n_acc, "sos_conv2d_wgrad: tap group does not fit in TMEM");
   }
   const int co_blk_ch = std::min(128, Cout);
   const int n_co_chunks_max = ceil_div(co_blk_ch, p.cbo);
-  int max_ng = 1;
-  // choose SB (pixels per tile = 8*SB) and groups per job so that at least 2 stages fit
+  // ---- stacked mode: pair tap groups whose fast offsets differ by `delta` and whose sub-tap structure is identical
+  int delta = 0;
+  {
+    int best_d = 1 << 30;
+    for (int i = 0; i < n_groups; ++i)
+      for (int j = 0; j < n_groups; ++j) {
+        const int d = pl.groups[i].d_fast - pl.groups[j].d_fast;
+        if (d > 0 && d < best_d) best_d = d;
+      }
+    if (best_d < (1 << 30)) delta = best_d;
+  }
+  const int out_fast_px = pl.fast_is_w ? (int)a.OW : (int)a.OH;
+  bool stacked = Cout > 32 && Cout <= 64 && a.stride == 1 && delta > 0 && delta < out_fast_px && (a.force_plan < 0 || a.force_plan < 4);
+  std::vector<int> partner(n_groups, -1), is_upper(n_groups, 0);
+  if (stacked) {
+    bool any = false;
+    std::vector<int> order(n_groups);
+    for (int i = 0; i < n_groups; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return pl.groups[x].d_fast > pl.groups[y].d_fast; });
+    for (int oi = 0; oi < n_groups; ++oi) {
+      const int A = order[oi];
+      if (is_upper[A]) continue;
+      for (int B = 0; B < n_groups; ++B) {
+        const TapGroup &ga = pl.groups[A], &gb = pl.groups[B];
+        if (B == A || is_upper[B] || partner[B] >= 0 || gb.d_fast != ga.d_fast - delta || gb.d_slow != ga.d_slow || gb.n_sub != ga.n_sub ||
+            memcmp(gb.a_off, ga.a_off, ga.n_sub) != 0)
+          continue;
+        partner[A] = B;
+        is_upper[B] = 1;
+        any = true;
+        break;
+      }
+    }
+    stacked = any;
+    if (!stacked) std::fill(is_upper.begin(), is_upper.end(), 0);
+  }
+  p.stacked = stacked;
+  p.delta = stacked ? delta : 0;
+  p.tf_extra = stacked ? ceil_div(delta, p.FB) : 0;
+  // "lead" groups stage an x box and own accumulator slots; the upper partner of a pair rides in rows 64..127
+  std::vector<int> leads;
+  for (int i = 0; i < n_groups; ++i)
+    if (!is_upper[i]) leads.push_back(i);
+  const int n_leads = (int)leads.size();
+  auto slots_of = [&](int li) { return (int)pl.groups[leads[li]].n_sub; };
+  for (int li = 0; li < n_leads; ++li) SOS_CHECK_ARG(slots_of(li) <= n_acc, "sos_conv2d_wgrad: tap group does not fit in TMEM");
+  // choose SB (pixels per tile = FB*SB) and groups per job so that at least 2 stages fit
   int SB = pl.SB, groups_per_job = 1;
   const int avail = kSmemLimit - 2048;
+  const int dy_chunks_staged = stacked ? 4 : n_co_chunks_max;
   auto stage_bytes_for = [&](int sb, int ng, int* x_off_out, int* reach_out) {
     const int dy_chunk = sb * p.FB * p.cbo * 4;
     const int dy_stride = round_up(dy_chunk, 1024);
     const int x_box = (sb + pl.halo) * p.FB * p.cbi * 4;
     const int x_stride = round_up(x_box, 1024);
-    const int x_off = n_co_chunks_max * dy_stride;
+    const int x_off = dy_chunks_staged * dy_stride;
     const int used = x_off + ng * p.n_ci_chunks * x_stride;
     // the padded MMA rows (M = 128, N rounded to 16) read past the staged chunks: keep that inside the stage
     const int reach_a = (128 / p.cbo) * dy_stride;
@@ -304,16 +364,13 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
     SB /= 2;
   }
   // more groups per job (sharing the staged dy tile) while TMEM and 3 stages allow
-  {
-    int taps_in = 0;
-    for (int ng = 2; ng <= n_groups; ++ng) {
-      taps_in = 0;
-      for (int i = 0; i < ng; ++i) taps_in += pl.groups[i].n_sub;
-      int reach = 0;
-      const int used = stage_bytes_for(SB, ng, nullptr, &reach);
-      if (taps_in > n_acc || 3 * used + std::max(0, reach - used) > avail) break;
-      groups_per_job = ng;
-    }
+  for (int ng = 2; ng <= std::min(n_leads, 4); ++ng) {
+    int slots_in = 0;
+    for (int i = 0; i < ng; ++i) slots_in += slots_of(i);
+    int reach = 0;
+    const int used = stage_bytes_for(SB, ng, nullptr, &reach);
+    if (slots_in > n_acc || 3 * used + std::max(0, reach - used) > avail) break;
+    groups_per_job = ng;
   }
   int reach = 0;
   const int used = stage_bytes_for(SB, groups_per_job, &p.x_off, &reach);
@@ -329,22 +386,31 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   p.n_stages = std::min(8, (avail - tail) / used);
   SOS_CHECK_ARG(p.n_stages >= 1, "sos_conv2d_wgrad: stage of %d bytes does not fit in shared memory", used);
 
-  int n_jobs = 0;
+  int n_jobs = 0, n_slots = 0, n_jg = 0;
   for (int cb = 0; cb < n_coblk; ++cb) {
-    int g = 0;
-    while (g < n_groups) {
-      int ng = 0, taps_in = 0;
-      while (g + ng < n_groups && ng < groups_per_job && taps_in + pl.groups[g + ng].n_sub <= n_acc) {
-        taps_in += pl.groups[g + ng].n_sub;
+    int li = 0;
+    while (li < n_leads) {
+      int ng = 0, slots_in = 0;
+      while (li + ng < n_leads && ng < groups_per_job && slots_in + slots_of(li + ng) <= n_acc) {
+        slots_in += slots_of(li + ng);
         ++ng;
       }
-      SOS_CHECK_ARG(n_jobs < kMaxJobs, "sos_conv2d_wgrad: too many jobs");
+      SOS_CHECK_ARG(ng > 0 && n_jobs < kMaxJobs && n_slots + slots_in <= kMaxSlots && n_jg + ng <= kMaxJobs * 4,
+                    "sos_conv2d_wgrad: too many jobs / accumulators");
       p.job_coblk[n_jobs] = (int16_t)cb;
-      p.job_g0[n_jobs] = (int16_t)g;
+      p.job_g0[n_jobs] = (int16_t)n_jg;
       p.job_ng[n_jobs] = (int16_t)ng;
-      max_ng = std::max(max_ng, ng);
+      p.job_s0[n_jobs] = (int16_t)n_slots;
+      p.job_ns[n_jobs] = (int16_t)slots_in;
+      for (int gi = 0; gi < ng; ++gi) {
+        const int A = leads[li + gi];
+        const TapGroup& ga = pl.groups[A];
+        p.job_group[n_jg++] = (int16_t)A;
+        for (int j = 0; j < ga.n_sub; ++j)
+          p.slots[n_slots++] = WgSlot{(int16_t)gi, (int16_t)ga.a_off[j], ga.tap[j], (int16_t)(partner[A] >= 0 ? pl.groups[partner[A]].tap[j] : -1)};
+      }
       ++n_jobs;
-      g += ng;
+      li += ng;
     }
   }
   p.n_jobs = n_jobs;
@@ -376,7 +442,7 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
     if (int e = encode_map(&p.mapDY, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, a.dy + a.dy_coff, dims, str, box, es, sw, "wgrad output grads"))
       return e;
   }
-  p.tiles_fast = ceil_div(out_fast, p.FB);
+  p.tiles_fast = ceil_div(out_fast, p.FB) + p.tf_extra;
   p.tiles_slow = ceil_div(out_slow / g, SB);
   p.n_phase = g;
   const long long total = (long long)a.N * g * p.tiles_slow * p.tiles_fast;
@@ -407,7 +473,7 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
     a.plan_out[4] = n_jobs;
     a.plan_out[5] = p.n_stages;
     a.plan_out[6] = p.stage_bytes;
-    a.plan_out[7] = p.n_slices;
+    a.plan_out[7] = p.n_slices + (stacked ? 1000 : 0);
   }
   return SOS_OK;
 }
