@@ -329,9 +329,25 @@ class FeatToSeq(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------- LSTM
+def _mm3(a, b):
+    """a @ b for the large LSTM GEMMs as a plain library GEMM (cuBLAS) at fp32-grade accuracy on the tensor cores: both operands
+    are split x = hi + lo with hi = tf32(x), lo = tf32(x - hi) (exactly representable, so the TF32 products are exact) and
+    a @ b = hi@hi + lo@hi + hi@lo (error ~2^-21 relative) -- 3 tensor-core GEMMs instead of one fp32 SIMT GEMM (~4x faster)."""
+    (ah, al), (bh, bl) = _split(a), _split(b)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        out = ah @ bh
+        out.addmm_(al, bh)
+        out.addmm_(ah, bl)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return out
+
+
 class BiLSTMFn(torch.autograd.Function):
     """Single-layer bidirectional LSTM.  Input projection / weight gradients are plain library GEMMs
-    (torch.matmul -> cuBLAS); the recurrence runs in the sos_lstm_* kernels."""
+    (cuBLAS, split-TF32 for the large ones); the recurrence runs in the sos_lstm_* kernels."""
 
     @staticmethod
     def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
@@ -339,7 +355,7 @@ class BiLSTMFn(torch.autograd.Function):
         H = w_hh.shape[1]
         W = torch.cat([w_ih, w_ih_r], dim=0)                                # (8H, I)
         bias = torch.cat([b_ih + b_hh, b_ih_r + b_hh_r])
-        gx = torch.addmm(bias, x.reshape(T * B, I), W.t()).view(T, B, 2, 4 * H)
+        gx = (_mm3(x.reshape(T * B, I), W.t()) + bias).view(T, B, 2, 4 * H)
         whh = torch.stack([w_hh, w_hh_r]).contiguous()
         out, gates, cell = ops.lstm_forward(gx, whh)
         ctx.save_for_backward(x, W, whh, out, gates, cell)
@@ -352,8 +368,8 @@ class BiLSTMFn(torch.autograd.Function):
         H = whh.shape[2]
         dgx = ops.lstm_backward(dout.contiguous(), whh, out, gates, cell)   # (T,B,2,4H)
         flat = dgx.view(T * B, 8 * H)
-        dx = (flat @ W).view(T, B, I) if ctx.needs_input_grad[0] else None
-        dW = flat.t() @ x.reshape(T * B, I)                                 # (8H, I)
+        dx = _mm3(flat, W).view(T, B, I) if ctx.needs_input_grad[0] else None
+        dW = _mm3(flat.t(), x.reshape(T * B, I))                            # (8H, I)
         db = flat.sum(0)
         hprev_f = torch.zeros(T, B, H, device=x.device, dtype=torch.float32)
         hprev_f[1:] = out[:-1, :, :H]
