@@ -2,31 +2,31 @@
 //   n_fft = 510, hop = 158, win = periodic Hann(400) zero padded to 510
 // (reference: M2/transform.py:6-8,188-202 -> librosa 0.7.1 stft/istft).
 //
-// Both directions are formulated as a small dense real DFT against a
+// The forward transform runs on the tensor cores (stft_tc.cu).  The inverse is a small dense real DFT against a
 // constant table that already contains the window:
-//   STFT : C[t][j] = sum_{n<400} x[reflect(158 t + n - 200)] * Wf[n][j],  j<512 (re | im)
 //   iSTFT: F[t][n] = sum_{j<512} S[j][t] * Wi[j][n]   followed by a gather
 //          overlap-add (each output sample sums <= 3 frames, no atomics) that
 //          also divides by the running sum of squared windows (librosa's
 //          window_sumsquare) and trims n_fft/2 on both ends.
-// The silent-interval gate (bits -> sample mask, M2/tools.py:340-362) is fused
-// into the STFT frame load; the complex-ratio-mask recovery
+// The silent-interval gate (bits -> sample mask, M2/tools.py:340-362; gate.cuh) is a standalone kernel here and can also be
+// evaluated inside the STFT frame builders; the complex-ratio-mask recovery
 // (M2/transform.py:141-169) can be fused into the iSTFT spectrum load.
 #include "common.cuh"
+#include "gate.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace {
 
 constexpr int kNfft = 510, kHop = 158, kWin = 400, kBins = 256, kLpad = 55, kJ = 512;
 
-float* g_wf = nullptr;   // [400][512]
 float* g_wi = nullptr;   // [512][400]
 float* g_w2 = nullptr;   // [400] squared window (float32, like librosa)
 
 int init_tables() {
-  if (g_wf) return SOS_OK;
-  std::vector<float> wf((size_t)kWin * kJ), wi((size_t)kJ * kWin), w2(kWin);
+  if (g_wi) return SOS_OK;
+  std::vector<float> wi((size_t)kJ * kWin), w2(kWin);
   const double two_pi = 6.283185307179586476925286766559;
   for (int n = 0; n < kWin; ++n) {
     const double w = 0.5 - 0.5 * cos(two_pi * n / kWin);
@@ -35,126 +35,21 @@ int init_tables() {
     for (int k = 0; k < kBins; ++k) {
       const int ph = (int)(((long long)m * k) % kNfft);
       const double a = two_pi * ph / kNfft;
-      wf[(size_t)n * kJ + k] = (float)(w * cos(a));
-      wf[(size_t)n * kJ + kBins + k] = (float)(-w * sin(a));
       const double coef = (k == 0 || k == kBins - 1) ? 1.0 : 2.0;
       wi[(size_t)k * kWin + n] = (float)(coef * w * cos(a) / kNfft);
       wi[(size_t)(kBins + k) * kWin + n] = (k == 0 || k == kBins - 1) ? 0.f : (float)(-coef * w * sin(a) / kNfft);
     }
   }
-  if (cudaMalloc(&g_wf, wf.size() * 4) != cudaSuccess || cudaMalloc(&g_wi, wi.size() * 4) != cudaSuccess ||
-      cudaMalloc(&g_w2, w2.size() * 4) != cudaSuccess) {
+  if (cudaMalloc(&g_wi, wi.size() * 4) != cudaSuccess || cudaMalloc(&g_w2, w2.size() * 4) != cudaSuccess) {
     sos_set_error("stft: cudaMalloc of DFT tables failed");
-    g_wf = nullptr;
+    g_wi = nullptr;
     return SOS_ERR_CUDA;
   }
-  cudaMemcpy(g_wf, wf.data(), wf.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(g_wi, wi.data(), wi.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(g_w2, w2.data(), w2.size() * 4, cudaMemcpyHostToDevice);
   return SOS_OK;
 }
 
-// The reference's bit-string -> sample mask (1 = silent), M2/tools.py:340-362.
-// frame_lo[i] = int(i * ratio) computed on the host with the reference's own
-// float expression; frame i writes [frame_lo[i], frame_lo[i+1]-1) and the
-// one-sample gap frame_lo[i+1]-1 (and any tail) stays 0.  The second pass
-// flips every run of equal values shorter than 5 samples (runs are taken on
-// the pre-flip values), which fills the gap between two silent frames and
-// handles clips truncated in the middle of a frame.
-__device__ __forceinline__ int frame_of(int s, int nb, const int* __restrict__ frame_lo, float inv_ratio) {
-  int i = (int)((float)s * inv_ratio);
-  if (i > nb) i = nb;
-  while (i > 0 && frame_lo[i] > s) --i;
-  while (i < nb && frame_lo[i + 1] <= s) ++i;
-  return i;                                        // nb means "after the last frame"
-}
-
-__device__ __forceinline__ int preflip(int s, const uint8_t* __restrict__ bits, int nb, const int* __restrict__ frame_lo,
-                                       float inv_ratio) {
-  const int i = frame_of(s, nb, frame_lo, inv_ratio);
-  if (i >= nb) return 0;
-  return (s < frame_lo[i + 1] - 1 && bits[i] == 0) ? 1 : 0;
-}
-
-__device__ __forceinline__ float sample_mask(int s, int L, const uint8_t* __restrict__ bits, int nb,
-                                             const int* __restrict__ frame_lo, float inv_ratio) {
-  const int i = frame_of(s, nb, frame_lo, inv_ratio);
-  if (i < nb) {                                    // fast path: deep inside a frame
-    const int lo = frame_lo[i], hi = frame_lo[i + 1] - 1;
-    if (s - lo >= 4 && hi - s > 4 && L - s > 4) return bits[i] == 0 ? 1.f : 0.f;
-  }
-  const int v = preflip(s, bits, nb, frame_lo, inv_ratio);
-  int a = 0, b = 0;
-  while (a < 4 && s - a - 1 >= 0 && preflip(s - a - 1, bits, nb, frame_lo, inv_ratio) == v) ++a;
-  while (b < 4 && s + b + 1 < L && preflip(s + b + 1, bits, nb, frame_lo, inv_ratio) == v) ++b;
-  return (a + 1 + b < 5) ? (float)(1 - v) : (float)v;
-}
-
-__device__ __forceinline__ int reflect_idx(int j, int L) {
-  if (j < 0) j = -j;
-  if (j >= L) j = 2 * (L - 1) - j;
-  return j;
-}
-
-// ---------------------------------------------------------------------------
-// STFT: block tile 64 frames x 64 outputs, K = 400 in steps of 16.
-// grid = (ceil(T/64), 8, B), block = 256.
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) stft_fwd_kernel(const float* __restrict__ wave, int L, int T,
-                                                       const float* __restrict__ wf, float* __restrict__ out,
-                                                       const uint8_t* __restrict__ bits, int nb,
-                                                       const int* __restrict__ frame_lo, float inv_ratio, int gate_mode) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Bs[16][64 + 4];
-  const int b = blockIdx.z, t0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const float* x = wave + (size_t)b * L;
-  const uint8_t* bb = bits ? bits + (size_t)b * nb : nullptr;
-  float acc[4][4] = {};
-  for (int n0 = 0; n0 < kWin; n0 += 16) {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int e = tid + r * 256;          // 1024 = 64 frames x 16 samples
-      const int nn = e & 15, tt = e >> 4;
-      const int t = t0 + tt;
-      float v = 0.f;
-      if (t < T) {
-        const int s = reflect_idx(t * kHop + n0 + nn - 200, L);
-        v = x[s];
-        if (gate_mode) {
-          const float m = sample_mask(s, L, bb, nb, frame_lo, inv_ratio);
-          v *= (gate_mode == 1) ? m : (1.f - m);
-        }
-      }
-      As[nn][tt] = v;
-      const int jj = e & 63, nb2 = e >> 6;
-      Bs[nb2][jj] = wf[(size_t)(n0 + nb2) * kJ + j0 + jj];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][tx * 4]);
-      const float4 w = *reinterpret_cast<const float4*>(&Bs[k][ty * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int jg = j0 + ty * 4 + j;
-    const int c = jg >> 8, k = jg & 255;
-    float* o = out + (((size_t)b * 2 + c) * kBins + k) * T;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int t = t0 + tx * 4 + i;
-      if (t < T) o[t] = acc[i][j];
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------
 // iSTFT stage 1: windowed inverse DFT frames  F[b][t][n], n < 400.
@@ -258,20 +153,21 @@ __global__ void gate_wave_kernel(const float* __restrict__ wave, int L, const ui
 
 }  // namespace
 
-extern "C" int sos_init(void) { return init_tables(); }
+int sos_stft_tc_init();
+int sos_stft_tc_launch(const float* wave, int64_t batch, int64_t length, float* spec_out, const uint8_t* bits, int64_t n_bits,
+                       const int32_t* frame_lo, double ratio, int gate_mode, cudaStream_t stream);
+
+extern "C" int sos_init(void) {
+  if (int e = init_tables()) return e;
+  return sos_stft_tc_init();
+}
 
 extern "C" int sos_stft_forward(const float* wave, int64_t batch, int64_t length, float* spec_out, const uint8_t* bits,
                                 int64_t n_bits, const int32_t* frame_lo, double ratio, int gate_mode, cudaStream_t stream) {
   SOS_CHECK_ARG(wave && spec_out && batch > 0 && length > kNfft / 2, "sos_stft_forward: bad arguments (need length > 255)");
   SOS_CHECK_ARG(gate_mode == 0 || (bits && frame_lo && n_bits > 0 && ratio > 0), "sos_stft_forward: gating needs bits/frame_lo/ratio");
   SOS_CHECK_ARG(batch <= 65535, "sos_stft_forward: batch > 65535");
-  if (int e = init_tables()) return e;
-  const int T = 1 + (int)(length / kHop);
-  dim3 grid(ceil_div(T, 64), kJ / 64, (unsigned)batch);
-  stft_fwd_kernel<<<grid, 256, 0, stream>>>(wave, (int)length, T, g_wf, spec_out, gate_mode ? bits : nullptr, (int)n_bits,
-                                            frame_lo, gate_mode ? (float)(1.0 / ratio) : 0.f, gate_mode);
-  SOS_CHECK_LAUNCH("sos_stft_forward");
-  return SOS_OK;
+  return sos_stft_tc_launch(wave, batch, length, spec_out, bits, n_bits, frame_lo, ratio, gate_mode, stream);
 }
 
 extern "C" int sos_istft_forward(const float* spec, const float* crm_or_null, int64_t batch, int64_t n_frames, float* frames_ws,

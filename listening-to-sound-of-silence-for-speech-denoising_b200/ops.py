@@ -88,11 +88,16 @@ def frame_lo_table(n_bits, ratio):
     return [int(i * ratio) for i in range(n_bits + 1)]
 
 
-def stft(wave, bits=None, ratio=None, gate_mode=0):
-    """wave (B, L) -> (B, 2, 256, T).  bits (B, n_bits) uint8 (0 = silent) gates the waveform first."""
+def stft(wave, bits=None, ratio=None, gate_mode=0, fused_gate=False):
+    """wave (B, L) -> (B, 2, 256, T).  bits (B, n_bits) uint8 (0 = silent) gates the waveform first.  By default the gate runs
+    as its own elementwise launch (sos_gate_wave) in front of the tensor-core STFT; `fused_gate=True` evaluates the mask inside
+    the STFT's frame builders instead (same result; the branchy mask logic makes that kernel ~7x slower)."""
     B, L = wave.shape
     T = 1 + L // 158
     out = torch.empty(B, 2, 256, T, device=wave.device, dtype=torch.float32)
+    if gate_mode and not fused_gate:
+        wave = gate_wave(wave, bits, ratio, gate_mode)
+        gate_mode = 0
     e0 = _pb()
     if gate_mode:
         nb = bits.shape[1]

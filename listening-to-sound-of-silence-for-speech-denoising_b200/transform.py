@@ -28,11 +28,11 @@ def _dev():
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def stft_batch(waves, bits=None, ratio=None, gate_mode=0):
-    """waves (B, L) CUDA fp32 -> (B, 2, 256, T).  Optional silent-interval gating fused into the frame load:
+def stft_batch(waves, bits=None, ratio=None, gate_mode=0, fused_gate=False):
+    """waves (B, L) CUDA fp32 -> (B, 2, 256, T).  Optional silent-interval gating of the waveform first:
     gate_mode 1 = waves * mask (noise gate), 2 = waves * (1 - mask); bits (B, n) uint8, 0 = silent."""
     ops.init()
-    return ops.stft(waves.contiguous(), bits, ratio, gate_mode)
+    return ops.stft(waves.contiguous(), bits, ratio, gate_mode, fused_gate)
 
 
 def istft_batch(spec, crm=None):

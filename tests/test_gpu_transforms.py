@@ -73,9 +73,14 @@ def test_gated_stft_equals_gate_then_stft(cuda):
     wave = torch.tensor(clips["mixed"], device=cuda)
     bits = tools.bits_to_tensor(clips["bits"], cuda)
     ratio = 16000 / 30.0
-    fused = transform.stft_batch(wave, bits, ratio, 1).cpu().numpy()
     want = otf.stft_batch(np.stack([gating.gate_noise(w, ratio, b) for w, b in zip(clips["mixed"], clips["bits"])]))
-    assert np.abs(fused - want).max() < 2e-4
+    composed = transform.stft_batch(wave, bits, ratio, 1)                     # gate launch + STFT (the default host path)
+    fused = transform.stft_batch(wave, bits, ratio, 1, fused_gate=True)       # mask evaluated inside the STFT kernel (C ABI gate_mode)
+    assert np.abs(composed.cpu().numpy() - want).max() < 2e-4
+    assert torch.equal(composed, fused)
+    clean = transform.stft_batch(wave, bits, ratio, 2, fused_gate=True)       # mode 2: wave * (1 - mask)
+    want2 = otf.stft_batch(np.stack([gating.gate_clean(w, ratio, b) for w, b in zip(clips["mixed"], clips["bits"])]))
+    assert np.abs(clean.cpu().numpy() - want2).max() < 2e-4
 
 
 def test_icrm_forward_backward(cuda):
