@@ -91,6 +91,10 @@ int sos_bn_stats(const float* y, int64_t rows, int64_t channels, float* partial,
 int sos_bn_finalize(const float* partial, int64_t rows, int64_t channels, const float* gamma, const float* beta, float eps,
                     float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
                     float* shift, cudaStream_t stream);
+/* sos_bn_finalize on partial sums produced elsewhere (the conv epilogue): partial [g_rows][2][channels]. */
+int sos_bn_finalize_partial(const float* partial, int64_t g_rows, int64_t rows, int64_t channels, const float* gamma, const float* beta,
+                            float eps, float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
+                            float* shift, cudaStream_t stream);
 int sos_bn_eval_coeffs(int64_t channels, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, float* scale, float* shift, cudaStream_t stream);
 int sos_bn_act(const float* y, float* z, const int32_t* z_view, int64_t rows, int64_t channels, const float* scale,
@@ -177,7 +181,14 @@ typedef struct sos_conv_args {
   const float* slope;      /* device scalar for act == 2 */
   int64_t force_plan;      /* -1 = automatic */
   int32_t* plan_out;       /* host, 8 ints, or NULL */
+  /* Optional fused BatchNorm statistics of the RAW outputs (training mode, M2/networks.py:37 nn.BatchNorm2d): the epilogue
+   * writes per-warp partial sums [rows][2][stats_channels] (sum | sum of squares; rows = *stats_rows_out <= sos_conv_stats_rows())
+   * for sos_bn_finalize_partial.  Needs epi_scale == NULL, act == 0, Cout <= 256. */
+  float* stats_partial;    /* device, or NULL */
+  int64_t stats_channels;
+  int32_t* stats_rows_out; /* host */
 } sos_conv_args;
+int sos_conv_stats_rows(void);   /* upper bound of *stats_rows_out (4 x SM count) */
 int sos_conv2d_tc(const sos_conv_args* args, cudaStream_t stream);
 
 /* Weight gradient of the same operator (split over pixels, accumulated with fp32 atomics):

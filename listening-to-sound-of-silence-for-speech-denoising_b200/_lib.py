@@ -25,7 +25,8 @@ class ConvArgs(C.Structure):
                 ("osh", i64), ("osw", i64), ("oph", i64), ("opw", i64),
                 ("epi_scale", C.c_void_p), ("epi_shift", C.c_void_p),
                 ("act", i64), ("slope", C.c_void_p),
-                ("force_plan", i64), ("plan_out", C.POINTER(C.c_int32))]
+                ("force_plan", i64), ("plan_out", C.POINTER(C.c_int32)),
+                ("stats_partial", C.c_void_p), ("stats_channels", i64), ("stats_rows_out", C.POINTER(C.c_int32))]
 
 
 class WgradArgs(C.Structure):
@@ -54,6 +55,8 @@ _SIGS = {
     "sos_bn_partial_blocks": (C.c_int, [i64, i64]),
     "sos_bn_stats": (C.c_int, [c_f, i64, i64, c_f, S]),
     "sos_bn_finalize": (C.c_int, [c_f, i64, i64, c_f, c_f, C.c_float, C.c_float, c_f, c_f, c_f, c_f, c_f, c_f, S]),
+    "sos_bn_finalize_partial": (C.c_int, [c_f, i64, i64, i64, c_f, c_f, C.c_float, C.c_float, c_f, c_f, c_f, c_f, c_f, c_f, S]),
+    "sos_conv_stats_rows": (C.c_int, []),
     "sos_bn_eval_coeffs": (C.c_int, [i64, c_f, c_f, c_f, c_f, C.c_float, c_f, c_f, S]),
     "sos_bn_act": (C.c_int, [c_f, c_f, i32p, i64, i64, c_f, c_f, C.c_int, c_f, S]),
     "sos_bn_act_backward": (C.c_int, [c_f, i32p, c_f, c_f, i64, i64, c_f, c_f, c_f, c_f, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, S]),

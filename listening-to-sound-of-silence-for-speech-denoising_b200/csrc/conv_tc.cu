@@ -30,6 +30,7 @@ using namespace ptx;
 using namespace tc;
 
 constexpr int kThreadsTc = 224;
+constexpr int kStatsSmem = 4 * 512 * 4;    // BatchNorm partial sums of the epilogue warps
 constexpr int kMaxProg = 144;             // entries of the deduplicated MMA programs
 struct alignas(64) TcParams {
   CUtensorMap mapA, mapB, mapD;
@@ -46,6 +47,8 @@ struct alignas(64) TcParams {
   const float* shift;
   int act;                       // 0 none, 1 relu, 2 prelu
   const float* slope;
+  float* stats;                  // optional BatchNorm partial sums [4 * grid][2][stats_c] of the RAW outputs (sum, sum of squares)
+  int stats_c, out_fast, lat_slow;
   TapGroup groups[kMaxGroups];
   // MMA program: one entry per tcgen05.mma of a pipeline stage (same for every tile / channel chunk; tap groups with the
   // same structure share one program): x = A descriptor address delta (16-byte units), y = B delta, z = accumulator column
@@ -80,6 +83,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
   auto tfull_bar = [&](int s) { return bar_base + 8u * (32 + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (34 + s); };
   const uint32_t tmem_slot = bar_base + 8u * 36;
+  // per epilogue warp: running per-channel sum / sum of squares of this CTA's tiles, [4 warps][2][256]
+  float* stats_s = reinterpret_cast<float*>(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -191,6 +196,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
     int buf = 0;
     const float slope = ((p.act & SOS_ACT_MASK) == 2 && p.slope) ? *p.slope : 0.f;
     const int n_ec = p.N / p.ec;
+    float* my_stats = stats_s + q * 512;                 // this warp's [2][256]
+    if (p.stats) {
+      for (int i = lane; i < 512; i += 32) my_stats[i] = 0.f;
+      __syncwarp();
+    }
+    // pixel of this thread's accumulator row inside the tile (rows are [slow][fast])
+    const int row_f = row % p.FB, row_s = row / p.FB;
     for (int ct = blockIdx.x; ct < p.total_ctiles; ct += gridDim.x) {
       const TileCoord tc = decode_tile(p, ct);
       mbar_wait(tfull_bar(acc), acc_phase, 300);
@@ -203,6 +215,32 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
           if (p.ec == 32) tmem_ld16(taddr + 16, r + 16);
           tmem_ld_wait();
           const int ch0 = tc.nb * p.N + cc * p.ec;
+          if (p.stats) {
+            // BatchNorm statistics of the raw outputs: transpose-reduce over the warp's 32 rows (31 shuffles per quantity),
+            // after which lane i holds the total of channel ch0 + i; rows outside the image (ragged tiles) count as zero
+            const bool in_img = (tc.tfg * p.S + s) * p.FB + row_f < p.out_fast && tc.ts * p.SB + row_s < p.lat_slow;
+            float v[32], w[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              v[i] = (in_img && i < p.ec) ? __uint_as_float(r[i]) : 0.f;
+              w[i] = v[i] * v[i];
+            }
+#pragma unroll
+            for (int st = 16; st >= 1; st >>= 1) {
+              const bool up = (lane & st) != 0;
+#pragma unroll
+              for (int i = 0; i < st; ++i) {
+                const float send_v = up ? v[i] : v[i + st], keep_v = up ? v[i + st] : v[i];
+                const float send_w = up ? w[i] : w[i + st], keep_w = up ? w[i + st] : w[i];
+                v[i] = keep_v + __shfl_xor_sync(0xffffffffu, send_v, st);
+                w[i] = keep_w + __shfl_xor_sync(0xffffffffu, send_w, st);
+              }
+            }
+            if (lane < p.ec) {                           // (for ec = 16 lanes 16..31 hold zeros)
+              my_stats[cc * p.ec + lane] += v[0];
+              my_stats[256 + cc * p.ec + lane] += w[0];
+            }
+          }
           if (p.scale || p.act) {
             const int act = p.act & SOS_ACT_MASK;
             const bool rnd = (p.act & SOS_ACT_ROUND_TF32) != 0;
@@ -248,6 +286,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (ethread == 0) bulk_wait<0>();
+    if (p.stats) {
+      __syncwarp();
+      float* dst = p.stats + (size_t)(blockIdx.x * 4 + q) * 2 * p.stats_c;
+      for (int c = lane; c < p.stats_c; c += 32) {
+        dst[c] = c < p.N ? my_stats[c] : 0.f;
+        dst[p.stats_c + c] = c < p.N ? my_stats[256 + c] : 0.f;
+      }
+    }
   }
 
   tc_fence_before();
@@ -286,7 +332,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   }
   const int ec = (N % 32 == 0) ? 32 : 16;
   const int staging_bytes = 2 * 128 * ec * 4;
-  const int avail = kSmemLimit - 1024 - staging_bytes - 512;
+  const int avail = kSmemLimit - 1024 - staging_bytes - 512 - kStatsSmem;
 
   // ---- choose orientation / box sharing / taps per box / channel chunk / sub-tiles: the cheapest candidate (tensor time vs
   //      L2->smem feed time per output pixel) whose pipeline stage fits at least twice (three times preferred) in shared memory
@@ -389,6 +435,11 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   p.act = (int)a.act;
   p.slope = a.slope;
   SOS_CHECK_ARG((a.epi_scale == nullptr) == (a.epi_shift == nullptr), "sos_conv2d_tc: epi_scale and epi_shift go together");
+  p.stats = a.stats_partial;
+  p.stats_c = (int)a.stats_channels;
+  SOS_CHECK_ARG(a.stats_partial == nullptr || (n_nblk == 1 && a.stats_channels > 0 && a.stats_channels <= 256 && a.stats_channels <= a.Cy - a.y_coff &&
+                                               a.epi_scale == nullptr && (a.act & SOS_ACT_MASK) == 0),
+                "sos_conv2d_tc: fused BatchNorm statistics need raw outputs of at most 256 channels in one channel block");
 
   // ---- tensor maps.  Dim order: (channel, fast, slow/g, phase(g), image)
   const bool fw = pl.fast_is_w;
@@ -427,6 +478,8 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
                             ec == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "output")) return e;
   }
   const int tiles_fast = ceil_div(out_fast, pl.FB);
+  p.out_fast = out_fast;
+  p.lat_slow = out_slow / g;
   p.tiles_fast_g = ceil_div(tiles_fast, p.S);
   p.tiles_slow = ceil_div(out_slow / g, pl.SB);
   p.n_phase = g;
@@ -434,7 +487,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG(total < (1ll << 31), "sos_conv2d_tc: too many tiles");
   p.total_ctiles = (int)total;
 
-  const int smem = 1024 + p.n_stages * p.stage_bytes + staging_bytes + 512;
+  const int smem = 1024 + p.n_stages * p.stage_bytes + staging_bytes + 512 + kStatsSmem;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(tapgemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess) {
@@ -446,6 +499,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   const int grid = (int)std::min<long long>(total, sos_num_sms());
   tapgemm_tf32_kernel<<<grid, kThreadsTc, smem, stream>>>(p);
   SOS_CHECK_LAUNCH("sos_conv2d_tc");
+  if (a.stats_rows_out) *a.stats_rows_out = 4 * grid;
   if (a.plan_out) {
     a.plan_out[0] = pl.fast_is_w;
     a.plan_out[1] = pl.share;
@@ -458,3 +512,5 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   }
   return SOS_OK;
 }
+
+extern "C" int sos_conv_stats_rows(void) { return 4 * sos_num_sms(); }

@@ -837,6 +837,17 @@ int sos_bn_finalize(const float* partial, int64_t rows, int64_t channels, const 
   return SOS_OK;
 }
 
+int sos_bn_finalize_partial(const float* partial, int64_t g_rows, int64_t rows, int64_t channels, const float* gamma, const float* beta,
+                            float eps, float momentum, float* running_mean, float* running_var, float* mean, float* invstd, float* scale,
+                            float* shift, cudaStream_t stream) {
+  SOS_CHECK_ARG(partial && gamma && beta && mean && invstd && scale && shift && g_rows > 0 && rows > 0 && channels > 0,
+                "sos_bn_finalize_partial: bad arguments");
+  bn_finalize_kernel<<<ceil_div((int)channels, 32), 256, 0, stream>>>(partial, (int)g_rows, (int)channels, (double)rows, gamma, beta, eps, momentum,
+                                                                     running_mean, running_var, mean, invstd, scale, shift);
+  SOS_CHECK_LAUNCH("sos_bn_finalize_partial");
+  return SOS_OK;
+}
+
 int sos_bn_eval_coeffs(int64_t channels, const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                        float eps, float* scale, float* shift, cudaStream_t stream) {
   SOS_CHECK_ARG(channels > 0 && gamma && beta && running_mean && running_var && scale && shift, "sos_bn_eval_coeffs: bad arguments");

@@ -74,28 +74,34 @@ def _pack_fwd(w, taps, cin_p):
     return ops.pack_taps(w.detach(), taps, cin_p, round_tf32=True)
 
 
-def _conv_forward(x, w, g, epi=None):
-    """x NHWC (N,H,W,Cin_p); w PyTorch layout.  Returns y NHWC (N,OH,OW,round8(Cout))."""
+def _conv_forward(x, w, g, epi=None, want_stats=False):
+    """x NHWC (N,H,W,Cin_p); w PyTorch layout.  Returns y NHWC (N,OH,OW,round8(Cout)); with want_stats also the BatchNorm
+    partial sums (G, 2, C) of y computed by the epilogue (the four sub-pixel launches of a transposed conv stack theirs)."""
     N, H, W, cin_p = x.shape
     OH, OW = g.out_size(H, W)
     kw = dict(epi_scale=epi[0], epi_shift=epi[1], act=epi[2], slope=epi[3]) if epi else {}
     if g.kind != "convT":
         Cout = w.shape[0]
         wk = _pack_fwd(w, g.taps, cin_p)
-        return ops.conv_tc(x, wk, [o[0] for o in g.off], [o[1] for o in g.off], Cout, OH, OW, g.stride, k_real=w.shape[1], **kw)
+        return ops.conv_tc(x, wk, [o[0] for o in g.off], [o[1] for o in g.off], Cout, OH, OW, g.stride, k_real=w.shape[1],
+                           want_stats=want_stats, **kw)
     # ConvTranspose2d(k3, s2, p1, output_padding=1): oy = 2*iy - 1 + ky  ->  four sub-pixel convolutions
     Cout = w.shape[1]
     wc = w.permute(1, 0, 2, 3)                                             # (Cout, Cin, ky, kx)
     Cy = _round8(Cout)
     y = (torch.zeros if Cy != Cout else torch.empty)(N, OH, OW, Cy, device=x.device, dtype=torch.float32)
     ph_taps = {0: [(1, 0)], 1: [(0, 1), (2, 0)]}                          # phase -> [(k, input offset)]
+    parts = []
     for py in (0, 1):
         for px in (0, 1):
             taps = [(ky, kx) for ky, _ in ph_taps[py] for kx, _ in ph_taps[px]]
             offs = [(oy, ox) for _, oy in ph_taps[py] for _, ox in ph_taps[px]]
             wk = _pack_fwd(wc, taps, cin_p)
-            ops.conv_tc(x, wk, [o[0] for o in offs], [o[1] for o in offs], Cout, H, W, 1, y=y, lattice=(2, 2, py, px), k_real=w.shape[0], **kw)
-    return y
+            r = ops.conv_tc(x, wk, [o[0] for o in offs], [o[1] for o in offs], Cout, H, W, 1, y=y, lattice=(2, 2, py, px), k_real=w.shape[0],
+                            want_stats=want_stats, **kw)
+            if want_stats:
+                parts.append(r[1])
+    return (y, torch.cat(parts)) if want_stats else y
 
 
 def _conv_dgrad(dy, w, g, x_shape):
@@ -143,18 +149,25 @@ def _conv_wgrad(x, dy, w, g):
 
 
 class TapConv(torch.autograd.Function):
+    """forward(x, w, geometry, want_stats=False) -> y, or (y, partial) with the BatchNorm partial sums of y from the epilogue."""
+
     @staticmethod
-    def forward(ctx, x, w, g):
+    def forward(ctx, x, w, g, want_stats=False):
         ctx.g = g
         ctx.save_for_backward(x, w)
         ctx.precise = _PRECISE
         if _PRECISE:
             (xh, xl), (wh, wl) = _split(x), _split(w)
-            return _conv_forward(xh, wh, g) + _conv_forward(xl, wh, g) + _conv_forward(xh, wl, g)
+            y = _conv_forward(xh, wh, g) + _conv_forward(xl, wh, g) + _conv_forward(xh, wl, g)
+            return (y, torch.empty(0, device=y.device)) if want_stats else y       # precise mode: statistics from the summed y
+        if want_stats:
+            y, partial = _conv_forward(x, w, g, want_stats=True)
+            ctx.mark_non_differentiable(partial)
+            return y, partial
         return _conv_forward(x, w, g)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, *unused):
         x, w = ctx.saved_tensors
         g = ctx.g
         dy = dy.contiguous()
@@ -165,12 +178,12 @@ class TapConv(torch.autograd.Function):
                 dx = _conv_dgrad(dh, wh, g, x.shape) + _conv_dgrad(dl, wh, g, x.shape) + _conv_dgrad(dh, wl, g, x.shape)
             if ctx.needs_input_grad[1]:
                 dw = _conv_wgrad(xh, dh, w, g) + _conv_wgrad(xl, dh, w, g) + _conv_wgrad(xh, dl, w, g)
-            return dx, dw, None
+            return dx, dw, None, None
         if g.round_dy:
             dy = ops.round_tf32_(dy.clone())
         dx = _conv_dgrad(dy, w, g, x.shape) if ctx.needs_input_grad[0] else None
         dw = _conv_wgrad(x, dy, w, g) if ctx.needs_input_grad[1] else None
-        return dx, dw, None
+        return dx, dw, None, None
 
 
 def conv_fused_eval(x, w, g, scale, shift, act, slope, round_out=True):
@@ -194,8 +207,8 @@ class RoundTF32(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------- BatchNorm + act
 class BNActTrain(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y, gamma, beta, slope, running_mean, running_var, eps, momentum, act, round_grad=True):
-        z, stats = ops.bn_train_forward(y, gamma, beta, running_mean, running_var, eps, momentum, act, slope)
+    def forward(ctx, y, gamma, beta, slope, running_mean, running_var, eps, momentum, act, round_grad=True, conv_partial=None):
+        z, stats = ops.bn_train_forward(y, gamma, beta, running_mean, running_var, eps, momentum, act, slope, conv_partial)
         ctx.act = (act & 15) | (ops.ACT_ROUND_TF32 if round_grad else 0)
         ctx.save_for_backward(y, stats, slope if slope is not None else torch.empty(0))
         return z
@@ -205,10 +218,10 @@ class BNActTrain(torch.autograd.Function):
         y, stats, slope = ctx.saved_tensors
         slope = slope if slope.numel() else None
         dy, dgamma, dbeta, dslope = ops.bn_train_backward(dz.contiguous(), y, stats, ctx.act, slope)
-        return dy, dgamma, dbeta, dslope, None, None, None, None, None, None
+        return dy, dgamma, dbeta, dslope, None, None, None, None, None, None, None
 
 
-def bn_act(y, bn, act, slope, training, round_out=True, round_grad=True):
+def bn_act(y, bn, act, slope, training, round_out=True, round_grad=True, conv_partial=None):
     """y NHWC with C = round8(bn.num_features).  bn: nn.BatchNorm2d holding the reference-named parameters."""
     Cp, Cn = y.shape[3], bn.num_features
     if _PRECISE:
@@ -221,8 +234,10 @@ def bn_act(y, bn, act, slope, training, round_out=True, round_grad=True):
     else:
         rm_p, rv_p = rm, rv
     if training:
+        if conv_partial is not None and conv_partial.numel() == 0:
+            conv_partial = None
         z = BNActTrain.apply(y, gamma, beta, slope, rm_p, rv_p, bn.eps, bn.momentum, act | (ops.ACT_ROUND_TF32 if round_out else 0),
-                             round_grad)
+                             round_grad, conv_partial)
         if Cp != Cn:
             with torch.no_grad():
                 rm.copy_(rm_p[:Cn])

@@ -47,8 +47,11 @@ class _Block(nn.Module):
             scale, shift = ops.bn_eval_coeffs(gamma.detach().contiguous(), beta.detach().contiguous(), rm.contiguous(), rv.contiguous(), bn.eps)
             return L.conv_fused_eval(x, conv.weight.detach(), geom, scale, shift, act, slope.detach() if slope is not None else None,
                                      self.round_out)
+        if self.training:                                                # batch statistics come out of the conv epilogue
+            y, partial = L.TapConv.apply(x, conv.weight, geom, True)
+            return L.bn_act(y, bn, act, slope, True, self.round_out, conv_partial=partial)
         y = L.TapConv.apply(x, conv.weight, geom)
-        return L.bn_act(y, bn, act, slope, self.training, self.round_out)
+        return L.bn_act(y, bn, act, slope, False, self.round_out)
 
 
 class ConvBlock(_Block):

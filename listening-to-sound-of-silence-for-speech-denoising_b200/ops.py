@@ -189,19 +189,26 @@ def round_tf32_(x):
     return x
 
 
-def bn_train_forward(y, gamma, beta, running_mean, running_var, eps, momentum, act, slope):
-    """y (..., C) dense NHWC rows.  Returns z and the tensors backward needs; updates running stats in place."""
+def bn_train_forward(y, gamma, beta, running_mean, running_var, eps, momentum, act, slope, conv_partial=None):
+    """y (..., C) dense NHWC rows.  Returns z and the tensors backward needs; updates running stats in place.
+    conv_partial: (G, 2, C) per-warp sums / sums of squares already produced by the convolution's epilogue."""
     Cn = y.shape[-1]
     rows = y.numel() // Cn
-    G = lib().sos_bn_partial_blocks(rows, Cn)
-    if G <= 0:
-        raise _lib.SosError(f"BatchNorm over {Cn} channels is not supported (need a multiple of 4, <= 1024)")
-    partial = torch.empty(G * 3 * Cn, device=y.device, dtype=torch.float32)
     stats = torch.empty(4, Cn, device=y.device, dtype=torch.float32)          # mean, invstd, scale, shift
-    check(lib().sos_bn_stats(_p(y), rows, Cn, _p(partial), _stream()), "sos_bn_stats")
-    check(lib().sos_bn_finalize(_p(partial), rows, Cn, _p(gamma), _p(beta), eps, momentum, _p(running_mean), _p(running_var),
-                                C.c_void_p(stats[0].data_ptr()), C.c_void_p(stats[1].data_ptr()), C.c_void_p(stats[2].data_ptr()),
-                                C.c_void_p(stats[3].data_ptr()), _stream()), "sos_bn_finalize")
+    sp = [C.c_void_p(stats[i].data_ptr()) for i in range(4)]
+    if conv_partial is not None:
+        assert conv_partial.shape[1:] == (2, Cn) and conv_partial.is_contiguous()
+        check(lib().sos_bn_finalize_partial(_p(conv_partial), conv_partial.shape[0], rows, Cn, _p(gamma), _p(beta), eps, momentum,
+                                            _p(running_mean), _p(running_var), sp[0], sp[1], sp[2], sp[3], _stream()), "sos_bn_finalize_partial")
+        _count(-1)
+    else:
+        G = lib().sos_bn_partial_blocks(rows, Cn)
+        if G <= 0:
+            raise _lib.SosError(f"BatchNorm over {Cn} channels is not supported (need a multiple of 4, <= 1024)")
+        partial = torch.empty(G * 3 * Cn, device=y.device, dtype=torch.float32)
+        check(lib().sos_bn_stats(_p(y), rows, Cn, _p(partial), _stream()), "sos_bn_stats")
+        check(lib().sos_bn_finalize(_p(partial), rows, Cn, _p(gamma), _p(beta), eps, momentum, _p(running_mean), _p(running_var),
+                                    sp[0], sp[1], sp[2], sp[3], _stream()), "sos_bn_finalize")
     z = torch.empty_like(y)
     H, W = y.shape[-3], y.shape[-2]
     check(lib().sos_bn_act(_p(y), _p(z), view8(H, W, ld=Cn), rows, Cn, C.c_void_p(stats[2].data_ptr()), C.c_void_p(stats[3].data_ptr()),
@@ -312,7 +319,7 @@ def pack_taps(w, taps, k_padded, round_tf32=True):
 
 
 def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lattice=(1, 1, 0, 0), epi_scale=None, epi_shift=None,
-            act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag="conv_fwd"):
+            act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag="conv_fwd", want_stats=False):
     """Tap-list implicit GEMM on tcgen05 (see include/sos_b200.h: sos_conv2d_tc).
 
     x (N, H, W, Cin) NHWC; wk (Cout, ntaps*Cin); y (N, YH, YW, Cy) is allocated when None (dense, Cy = Cout
@@ -341,6 +348,11 @@ def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lat
     a.force_plan = force_plan
     po = (_I32 * 8)() if plan_out is not None else None
     a.plan_out = po
+    partial, rows = None, None
+    if want_stats:                                   # BatchNorm partial sums of the raw outputs, written by the epilogue
+        partial = torch.empty(lib().sos_conv_stats_rows(), 2, y.shape[3], device=x.device, dtype=torch.float32)
+        rows = (_I32 * 1)()
+        a.stats_partial, a.stats_channels, a.stats_rows_out = partial.data_ptr(), y.shape[3], rows
     assert x.is_contiguous() and wk.is_contiguous() and y.is_contiguous()
     e0 = _pb()
     check(lib().sos_conv2d_tc(C.byref(a), _stream()), "sos_conv2d_tc")
@@ -348,6 +360,8 @@ def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lat
     _count()
     if plan_out is not None:
         plan_out[:] = list(po)
+    if want_stats:
+        return y, partial[:rows[0]]
     return y
 
 
