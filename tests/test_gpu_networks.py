@@ -219,3 +219,65 @@ def test_joint_matches_reference(cuda, gold, mode, tag):
         with torch.no_grad():
             n2, m2 = joint(x, n)                               # inference path (fused epilogues)
         assert float((m2 - ref["mask"]).abs().mean()) < MASK_L1_TOL and _rel(n2, ref["npred"]) < OUT_TOL
+
+
+@pytest.mark.parametrize("L", [28000, 32000])
+def test_full_size_training_step(cuda, L):
+    """Reference-native (14 kHz x 2 s, T = 178) and benchmark (16 kHz x 2 s, T = 203) clip sizes through the agents' public
+    surface: shapes of every output (M1/networks.py:158-169 smoke, M2 item contract), finite losses, a parameter update, and the
+    checkpoint dict keys of M2/agent.py:65-77."""
+    from sos_b200 import agent as ag, transform
+    from oracle import synth
+    B, T = 2, 1 + L // 158
+    clips = synth.make_batch(B, length=L)
+    dev = cuda
+    wave = {k: torch.tensor(clips[k], device=dev) for k in ("mixed", "clean", "full_noise", "noise")}
+    spec = {k: transform.stft_batch(v) for k, v in wave.items()}
+    assert spec["mixed"].shape == (B, 2, 256, T)
+    torch.manual_seed(0)
+    sid = ag.get_agent(ag.default_config(model="sid"))
+    torch.manual_seed(1)
+    joint = ag.get_agent(ag.default_config(model="joint"))
+    w0 = joint.net.stage2.fc[4].weight.detach().clone()
+    logits, l_sid = sid.train_func({"audio": spec["mixed"], "label": torch.tensor(clips["label"], device=dev)})
+    (n_pred, mask), l_jt = joint.train_func({k: spec[k] for k in ("mixed", "noise", "clean", "full_noise")})
+    assert logits.shape == (B, clips["label"].shape[1]) and n_pred.shape == mask.shape == (B, 2, 256, T)
+    vals = {**sid.loss_values(), **joint.loss_values()}
+    assert set(vals) == {"bce", "stage1", "stage2"} and all(np.isfinite(v) for v in vals.values()), vals
+    assert float(mask.min()) > 0 and float(mask.max()) < 1
+    assert not torch.equal(joint.net.stage2.fc[4].weight.detach(), w0), "Adam did not update the parameters"
+    # eval / inference surface
+    _, lv = joint.val_func({k: spec[k] for k in ("mixed", "noise", "clean", "full_noise")})
+    assert np.isfinite(float(lv["stage2"]))
+    sd = joint.net.state_dict()
+    assert len(sd) == 322 and sd["stage1.mid.8.block.0.weight"].shape == (256, 128, 3, 3) and sd["stage2.lstm.weight_ih_l0_reverse"].shape == (800, 3072)
+    assert len(sid.net.state_dict()) == 84
+
+
+def test_checkpoint_roundtrip(cuda, tmp_path):
+    """save_ckpt / load_ckpt keep the reference's file names and dict keys (M2/agent.py:57-95); a restored agent reproduces the
+    forward pass bit for bit and the next update up to the summation order of the weight-gradient atomics."""
+    from sos_b200 import agent as ag
+    cfg = ag.default_config(model="sid", model_dir=str(tmp_path))
+    torch.manual_seed(0)
+    a = ag.get_agent(cfg)
+    g = torch.Generator().manual_seed(4)
+    data = {"audio": (torch.randn(2, 2, 256, 71, generator=g) * 0.3).to(cuda), "label": (torch.rand(2, 21, generator=g) > 0.5).float().to(cuda)}
+    a.train_func(data)
+    a.clock.tick()
+    path = a.save_ckpt()
+    ck = torch.load(path, map_location="cpu")
+    assert path.endswith("ckpt_epoch1.pth") and set(ck) == {"clock", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict"}
+    assert list(ck["model_state_dict"])[0] == "encoder_audio.0.block.0.weight"
+    torch.manual_seed(123)
+    b = ag.get_agent(cfg)
+    b.load_ckpt(1)
+    assert b.clock.step == 1 and b.optimizer.step_count == 1
+    out_a, _ = a.train_func(data)
+    out_b, _ = b.train_func(data)
+    assert torch.equal(out_a, out_b)
+    for (k, p), (_, q) in zip(a.net.state_dict().items(), b.net.state_dict().items()):
+        if p.is_floating_point():       # wgrad merges its pixel slices with fp32 atomics: the last bits of a gradient depend on their order
+            assert float((p - q).abs().max()) < 2e-4, k
+        else:
+            assert torch.equal(p, q), k
