@@ -554,24 +554,25 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, View iv, float
 
 // dst(view, H x W) = src(view, Hs x Ws) with PyTorch 'nearest' index map; C channels copied.
 // accumulate: dst += src (used for gradient fan-in)
-__global__ void copy_view_kernel(const float* __restrict__ src, View sv, float* __restrict__ dst, View dv, int C, long long Pd,
-                                 int accumulate) {
+// One block per destination row (n, h): the row-level index arithmetic (nearest source row, view offsets) is done once per
+// block; threads run over the row's W * C/4 float4 elements.
+__global__ void __launch_bounds__(kThreads) copy_view_kernel(const float* __restrict__ src, View sv, float* __restrict__ dst, View dv, int C,
+                                                              int accumulate) {
   const int cg = C >> 2;
-  const long long total = Pd * cg;
-  const float sh = (float)sv.H / (float)dv.H, sw = (float)sv.W / (float)dv.W;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long p = e / cg;
-    const int c = (int)(e - p * cg) * 4;
-    const int w = (int)(p % dv.W);
-    const long long t = p / dv.W;
-    const int h = (int)(t % dv.H);
-    const long long n = t / dv.H;
-    int hs = h, ws = w;
-    if (sv.H != dv.H) hs = min((int)floorf(h * sh), sv.H - 1);
-    if (sv.W != dv.W) ws = min((int)floorf(w * sw), sv.W - 1);
-    const long long ps = (n * sv.H + hs) * sv.W + ws;
-    float4 v = *reinterpret_cast<const float4*>(src + view_pix(sv, ps) + c);
-    float* d = dst + view_pix(dv, p) + c;
+  const int h = blockIdx.x, n = blockIdx.y;
+  int hs = h;
+  if (sv.H != dv.H) hs = min((int)floorf(h * ((float)sv.H / (float)dv.H)), sv.H - 1);
+  const float sw = (float)sv.W / (float)dv.W;
+  const bool same_w = sv.W == dv.W;
+  const float* srow = src + (((long long)n * sv.Hp + hs + sv.ph) * sv.Wp + sv.pw) * (long long)sv.ld + sv.coff;
+  float* drow = dst + (((long long)n * dv.Hp + h + dv.ph) * dv.Wp + dv.pw) * (long long)dv.ld + dv.coff;
+  const int total = dv.W * cg;
+  for (int e = threadIdx.x; e < total; e += kThreads) {
+    const int w = e / cg;
+    const int c = (e - w * cg) * 4;
+    const int ws = same_w ? w : min((int)floorf(w * sw), sv.W - 1);
+    float4 v = *reinterpret_cast<const float4*>(srow + (long long)ws * sv.ld + c);
+    float* d = drow + (long long)w * dv.ld + c;
     if (accumulate) {
       const float4 o = *reinterpret_cast<const float4*>(d);
       v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
@@ -606,50 +607,52 @@ __device__ __forceinline__ int reflect_coord(int i, int n) {
 }
 
 // Fill the border of a padded NHWC buffer (B,Hp,Wp,C) by reflection of its interior (H x W at offset p).
-__global__ void reflect_fill_kernel(float* __restrict__ buf, int B, int H, int W, int pad, int C) {
+// One block per buffer row (n, hp): border rows copy a whole mirrored row, interior rows only their 2*pad border columns.
+__global__ void __launch_bounds__(kThreads) reflect_fill_kernel(float* __restrict__ buf, int H, int W, int pad, int C) {
   const int Hp = H + 2 * pad, Wp = W + 2 * pad, cg = C >> 2;
-  const long long total = (long long)B * Hp * Wp * cg;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(e % cg) * 4;
-    long long t = e / cg;
-    const int wp = (int)(t % Wp); t /= Wp;
-    const int hp = (int)(t % Hp);
-    const long long n = t / Hp;
-    const int h = hp - pad, w = wp - pad;
-    if (h >= 0 && h < H && w >= 0 && w < W) continue;
-    const int hs = reflect_coord(h, H) + pad, ws = reflect_coord(w, W) + pad;
-    *reinterpret_cast<float4*>(buf + ((n * Hp + hp) * Wp + wp) * (long long)C + c) =
-        *reinterpret_cast<const float4*>(buf + ((n * Hp + hs) * Wp + ws) * (long long)C + c);
+  const int hp = blockIdx.x, n = blockIdx.y;
+  const int h = hp - pad;
+  const bool border_row = h < 0 || h >= H;
+  const int hs = reflect_coord(h, H) + pad;
+  float* drow = buf + ((long long)n * Hp + hp) * Wp * (long long)C;
+  const float* srow = buf + ((long long)n * Hp + hs) * Wp * (long long)C;
+  const int ncols = border_row ? Wp : 2 * pad;               // columns of this row that need filling
+  const int total = ncols * cg;
+  for (int e = threadIdx.x; e < total; e += kThreads) {
+    int col = e / cg;
+    const int c = (e - col * cg) * 4;
+    const int wp = border_row ? col : (col < pad ? col : W + col);          // interior rows: left pad, then right pad
+    const int ws = reflect_coord(wp - pad, W) + pad;
+    *reinterpret_cast<float4*>(drow + (long long)wp * C + c) = *reinterpret_cast<const float4*>(srow + (long long)ws * C + c);
   }
 }
 
 // Adjoint: fold border gradients back into the interior (in place).  One thread per interior element gathers
-// the (up to 8) border positions that mirror onto it, so no atomics are needed.
-__global__ void reflect_fold_kernel(float* __restrict__ g, int B, int H, int W, int pad, int C) {
+// the (up to 8) border positions that mirror onto it, so no atomics are needed.  One block per interior row (n, h).
+__global__ void __launch_bounds__(kThreads) reflect_fold_kernel(float* __restrict__ g, int H, int W, int pad, int C) {
   const int Hp = H + 2 * pad, Wp = W + 2 * pad, cg = C >> 2;
-  const long long total = (long long)B * H * W * cg;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(e % cg) * 4;
-    long long t = e / cg;
-    const int w = (int)(t % W); t /= W;
-    const int h = (int)(t % H);
-    const long long n = t / H;
-    // rows that map to h: h itself, -h (if 1<=h<=pad), 2(H-1)-h (if H-1-pad <= h <= H-2)
-    int hs[3], nh = 0, ws[3], nw = 0;
-    hs[nh++] = h;
-    if (h >= 1 && h <= pad) hs[nh++] = -h;
-    if (h <= H - 2 && h >= H - 1 - pad) hs[nh++] = 2 * (H - 1) - h;
+  const int h = blockIdx.x, n = blockIdx.y;
+  // rows that map to h: h itself, -h (if 1<=h<=pad), 2(H-1)-h (if H-1-pad <= h <= H-2)
+  int hs[3], nh = 0;
+  hs[nh++] = h;
+  if (h >= 1 && h <= pad) hs[nh++] = -h;
+  if (h <= H - 2 && h >= H - 1 - pad) hs[nh++] = 2 * (H - 1) - h;
+  float* base = g + (long long)n * Hp * Wp * (long long)C;
+  const int total = W * cg;
+  for (int e = threadIdx.x; e < total; e += kThreads) {
+    const int w = e / cg;
+    const int c = (e - w * cg) * 4;
+    int ws[3], nw = 0;
     ws[nw++] = w;
     if (w >= 1 && w <= pad) ws[nw++] = -w;
     if (w <= W - 2 && w >= W - 1 - pad) ws[nw++] = 2 * (W - 1) - w;
     float4 acc = {0, 0, 0, 0};
     for (int i = 0; i < nh; ++i)
       for (int j = 0; j < nw; ++j) {
-        const float4 v = *reinterpret_cast<const float4*>(g + ((n * Hp + hs[i] + pad) * Wp + ws[j] + pad) * (long long)C + c);
+        const float4 v = *reinterpret_cast<const float4*>(base + ((long long)(hs[i] + pad) * Wp + ws[j] + pad) * C + c);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
-    __syncwarp();
-    *reinterpret_cast<float4*>(g + ((n * Hp + h + pad) * Wp + w + pad) * (long long)C + c) = acc;
+    *reinterpret_cast<float4*>(base + ((long long)(h + pad) * Wp + w + pad) * C + c) = acc;
   }
 }
 
@@ -970,8 +973,8 @@ int sos_copy_view(const float* src, const int32_t* src_view, float* dst, const i
   SOS_CHECK_ARG(src && dst && src_view && dst_view && batch > 0 && channels >= 4 && channels % 4 == 0, "sos_copy_view: bad arguments");
   const View sv = mk_view(src_view), dv = mk_view(dst_view);
   SOS_CHECK_ARG(view_ok(sv, (int)channels) && view_ok(dv, (int)channels), "sos_copy_view: inconsistent view");
-  const long long Pd = batch * dv.H * dv.W;
-  copy_view_kernel<<<grid_for(Pd * (channels / 4)), kThreads, 0, stream>>>(src, sv, dst, dv, (int)channels, Pd, accumulate);
+  SOS_CHECK_ARG(batch <= 65535, "sos_copy_view: batch > 65535");
+  copy_view_kernel<<<dim3((unsigned)dv.H, (unsigned)batch), kThreads, 0, stream>>>(src, sv, dst, dv, (int)channels, accumulate);
   SOS_CHECK_LAUNCH("sos_copy_view");
   return SOS_OK;
 }
@@ -989,8 +992,8 @@ int sos_copy_view_backward(const float* grad_dst, const int32_t* dst_view, float
 int sos_reflect_fill(float* buf, int64_t batch, int64_t H, int64_t W, int64_t pad, int64_t channels, cudaStream_t stream) {
   SOS_CHECK_ARG(buf && batch > 0 && pad >= 0 && pad < H && pad < W && channels % 4 == 0, "sos_reflect_fill: bad arguments (pad must be < H, W)");
   if (pad == 0) return SOS_OK;
-  const long long total = batch * (H + 2 * pad) * (W + 2 * pad) * (channels / 4);
-  reflect_fill_kernel<<<grid_for(total), kThreads, 0, stream>>>(buf, (int)batch, (int)H, (int)W, (int)pad, (int)channels);
+  SOS_CHECK_ARG(batch <= 65535, "sos_reflect_fill: batch > 65535");
+  reflect_fill_kernel<<<dim3((unsigned)(H + 2 * pad), (unsigned)batch), kThreads, 0, stream>>>(buf, (int)H, (int)W, (int)pad, (int)channels);
   SOS_CHECK_LAUNCH("sos_reflect_fill");
   return SOS_OK;
 }
@@ -999,8 +1002,8 @@ int sos_reflect_fold(float* grad_buf, int64_t batch, int64_t H, int64_t W, int64
   SOS_CHECK_ARG(grad_buf && batch > 0 && pad >= 0 && pad < H && pad < W && channels % 4 == 0, "sos_reflect_fold: bad arguments");
   if (pad == 0) return SOS_OK;
   // every interior element only reads border cells and itself, and writes itself -> safe in place
-  reflect_fold_kernel<<<grid_for(batch * H * W * (channels / 4)), kThreads, 0, stream>>>(grad_buf, (int)batch, (int)H, (int)W, (int)pad,
-                                                                                          (int)channels);
+  SOS_CHECK_ARG(batch <= 65535, "sos_reflect_fold: batch > 65535");
+  reflect_fold_kernel<<<dim3((unsigned)H, (unsigned)batch), kThreads, 0, stream>>>(grad_buf, (int)H, (int)W, (int)pad, (int)channels);
   SOS_CHECK_LAUNCH("sos_reflect_fold");
   return SOS_OK;
 }
