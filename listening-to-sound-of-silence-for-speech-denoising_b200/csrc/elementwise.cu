@@ -581,22 +581,34 @@ __global__ void __launch_bounds__(kThreads) copy_view_kernel(const float* __rest
   }
 }
 
-// Adjoint of copy_view with resize: gsrc(view) += gdst(view) through the nearest map (atomic when many-to-one).
-__global__ void copy_view_bwd_kernel(const float* __restrict__ gdst, View dv, float* __restrict__ gsrc, View sv, int C, long long Pd) {
-  const long long total = Pd * C;
-  const float sh = (float)sv.H / (float)dv.H, sw = (float)sv.W / (float)dv.W;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long p = e / C;
-    const int c = (int)(e - p * C);
-    const int w = (int)(p % dv.W);
-    const long long t = p / dv.W;
-    const int h = (int)(t % dv.H);
-    const long long n = t / dv.H;
-    int hs = h, ws = w;
-    if (sv.H != dv.H) hs = min((int)floorf(h * sh), sv.H - 1);
-    if (sv.W != dv.W) ws = min((int)floorf(w * sw), sv.W - 1);
-    const long long ps = (n * sv.H + hs) * sv.W + ws;
-    atomicAdd(gsrc + view_pix(sv, ps) + c, gdst[view_pix(dv, p) + c]);
+// Adjoint of copy_view with resize: gsrc(view) += gdst(view) through the nearest map.  One block per destination row.  When the
+// destination is not larger than the source in either axis the map is one-to-one (plain read-modify-write); otherwise several
+// destination pixels hit the same source pixel and the adds are atomic.
+__global__ void __launch_bounds__(kThreads) copy_view_bwd_kernel(const float* __restrict__ gdst, View dv, float* __restrict__ gsrc, View sv,
+                                                                  int C) {
+  const int cg = C >> 2;
+  const int h = blockIdx.x, n = blockIdx.y;
+  int hs = h;
+  if (sv.H != dv.H) hs = min((int)floorf(h * ((float)sv.H / (float)dv.H)), sv.H - 1);
+  const float sw = (float)sv.W / (float)dv.W;
+  const bool same_w = sv.W == dv.W;
+  const bool many_to_one = dv.H > sv.H || dv.W > sv.W;
+  float* srow = gsrc + (((long long)n * sv.Hp + hs + sv.ph) * sv.Wp + sv.pw) * (long long)sv.ld + sv.coff;
+  const float* drow = gdst + (((long long)n * dv.Hp + h + dv.ph) * dv.Wp + dv.pw) * (long long)dv.ld + dv.coff;
+  const int total = dv.W * cg;
+  for (int e = threadIdx.x; e < total; e += kThreads) {
+    const int w = e / cg;
+    const int c = (e - w * cg) * 4;
+    const int ws = same_w ? w : min((int)floorf(w * sw), sv.W - 1);
+    const float4 v = *reinterpret_cast<const float4*>(drow + (long long)w * dv.ld + c);
+    float* d = srow + (long long)ws * sv.ld + c;
+    if (many_to_one) {
+      atomicAdd(d, v.x); atomicAdd(d + 1, v.y); atomicAdd(d + 2, v.z); atomicAdd(d + 3, v.w);
+    } else {
+      float4 o = *reinterpret_cast<float4*>(d);
+      o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+      *reinterpret_cast<float4*>(d) = o;
+    }
   }
 }
 
@@ -981,10 +993,11 @@ int sos_copy_view(const float* src, const int32_t* src_view, float* dst, const i
 
 int sos_copy_view_backward(const float* grad_dst, const int32_t* dst_view, float* grad_src, const int32_t* src_view, int64_t batch,
                            int64_t channels, cudaStream_t stream) {
-  SOS_CHECK_ARG(grad_dst && grad_src && src_view && dst_view && batch > 0 && channels > 0, "sos_copy_view_backward: bad arguments");
+  SOS_CHECK_ARG(grad_dst && grad_src && src_view && dst_view && batch > 0 && batch <= 65535 && channels >= 4 && channels % 4 == 0,
+                "sos_copy_view_backward: bad arguments");
   const View sv = mk_view(src_view), dv = mk_view(dst_view);
-  const long long Pd = batch * dv.H * dv.W;
-  copy_view_bwd_kernel<<<grid_for(Pd * channels), kThreads, 0, stream>>>(grad_dst, dv, grad_src, sv, (int)channels, Pd);
+  SOS_CHECK_ARG(view_ok(sv, (int)channels) && view_ok(dv, (int)channels), "sos_copy_view_backward: inconsistent view");
+  copy_view_bwd_kernel<<<dim3((unsigned)dv.H, (unsigned)batch), kThreads, 0, stream>>>(grad_dst, dv, grad_src, sv, (int)channels);
   SOS_CHECK_LAUNCH("sos_copy_view_backward");
   return SOS_OK;
 }
