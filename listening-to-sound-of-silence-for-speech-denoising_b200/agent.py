@@ -217,7 +217,11 @@ class BaseAgent(object):
     def update_network(self, loss_dict):
         loss = sum(loss_dict.values())
         self.optimizer.zero_grad()
-        loss.backward()
+        if os.environ.get("SOS_SYNC_WGRAD"):
+            loss.backward()
+        else:
+            with L.async_wgrad():                              # conv weight gradients on a side stream, joined on exit
+                loss.backward()
         self.optimizer.step()
 
     def update_learning_rate(self):

@@ -248,7 +248,10 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __
                                                                   const float* __restrict__ invstd, int act,
                                                                   const float* __restrict__ slope_ptr,
                                                                   float* __restrict__ partial /*[grid][3][C]*/) {
-  extern __shared__ float sm[];                 // [rows][3][C]
+  extern __shared__ float sm[];                 // [3][C] block totals (shared-memory atomics: a small footprint lets this
+                                                // HBM-bound kernel share an SM with a tensor-core kernel of another stream)
+  for (int i = threadIdx.x; i < 3 * C; i += kThreads) sm[i] = 0.f;
+  __syncthreads();
   const int cg = C >> 2;
   const int rows = kThreads / cg;
   const int r = threadIdx.x / cg, c4 = threadIdx.x - r * cg;
@@ -287,16 +290,15 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __
         }
       }
     }
-    float* d = sm + (size_t)r * 3 * C;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { d[c + i] = s1[i]; d[C + c + i] = s2[i]; d[2 * C + c + i] = s3[i]; }
+    for (int i = 0; i < 4; ++i) {
+      atomicAdd(sm + c + i, s1[i]);
+      atomicAdd(sm + C + c + i, s2[i]);
+      atomicAdd(sm + 2 * C + c + i, s3[i]);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * C; i += kThreads) {
-    float a = 0.f;
-    for (int rr = 0; rr < rows; ++rr) a += sm[(size_t)rr * 3 * C + i];
-    partial[(size_t)blockIdx.x * 3 * C + i] = a;
-  }
+  for (int i = threadIdx.x; i < 3 * C; i += kThreads) partial[(size_t)blockIdx.x * 3 * C + i] = sm[i];
 }
 
 // Backward finalize: dgamma, dbeta, dslope (atomically accumulated; zeroed by the caller) and the two per-channel means
@@ -898,9 +900,7 @@ int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y,
   const int C = (int)channels;
   SOS_CHECK_ARG(view_ok(dv, C) && rows % ((long long)dv.H * dv.W) == 0, "sos_bn_act_backward: inconsistent view");
   SOS_CHECK_ARG((act & SOS_ACT_MASK) != 2 || (slope && dslope), "sos_bn_act_backward: PReLU needs slope and dslope");
-  const int rpb = kThreads / (C / 4);
-  const size_t smem = (size_t)rpb * 3 * C * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)3 * C * sizeof(float);
   bn_bwd_reduce_kernel<<<G, kThreads, smem, stream>>>(dz, dv, y, rows, C, scale, shift, mean, invstd, act, slope, partial);
   SOS_CHECK_LAUNCH("sos_bn_act_backward(reduce)");
   bn_bwd_finalize_kernel<<<ceil_div(C, 32), 256, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta, (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2);

@@ -35,6 +35,37 @@ def precise():
     return _PRECISE
 
 
+# Weight gradients are off the backward critical path (only the optimiser needs them): inside `async_wgrad()` TapConv.backward
+# enqueues them on a side stream and adds them straight into the parameter's .grad (a view of the agent's flat gradient buffer),
+# so the tensor-bound wgrad kernels overlap the HBM-bound BatchNorm passes of the following layers.  The caller joins the
+# streams (`join_wgrad()`) before it reads any gradient.
+_ASYNC_WGRAD = False
+_SIDE = None
+
+
+def _side_stream():
+    global _SIDE
+    if _SIDE is None:
+        _SIDE = torch.cuda.Stream()
+    return _SIDE
+
+
+class async_wgrad(object):
+    def __enter__(self):
+        global _ASYNC_WGRAD
+        self.old, _ASYNC_WGRAD = _ASYNC_WGRAD, True
+
+    def __exit__(self, *a):
+        global _ASYNC_WGRAD
+        _ASYNC_WGRAD = self.old
+        join_wgrad()
+
+
+def join_wgrad():
+    if _SIDE is not None:
+        torch.cuda.current_stream().wait_stream(_SIDE)
+
+
 def _split(t):
     hi = ops.round_tf32_(t.detach().clone().contiguous())
     lo = ops.round_tf32_((t.detach() - hi).contiguous())
@@ -181,8 +212,17 @@ class TapConv(torch.autograd.Function):
             return dx, dw, None, None
         if g.round_dy:
             dy = ops.round_tf32_(dy.clone())
+        dw = None
+        if ctx.needs_input_grad[1] and _ASYNC_WGRAD and w.grad is not None:
+            side, main = _side_stream(), torch.cuda.current_stream()
+            side.wait_stream(main)                                     # x, dy (and the zeroed .grad) are ready
+            with torch.cuda.stream(side):
+                w.grad.add_(_conv_wgrad(x, dy, w, g))
+            x.record_stream(side)
+            dy.record_stream(side)
+        elif ctx.needs_input_grad[1]:
+            dw = _conv_wgrad(x, dy, w, g)
         dx = _conv_dgrad(dy, w, g, x.shape) if ctx.needs_input_grad[0] else None
-        dw = _conv_wgrad(x, dy, w, g) if ctx.needs_input_grad[1] else None
         return dx, dw, None, None
 
 
