@@ -13,7 +13,7 @@ def _gather(x, dh, dw, OH, OW, stride):
 
 
 def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lattice=(1, 1, 0, 0), epi_scale=None, epi_shift=None,
-            act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag=None):
+            act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag=None, want_stats=False):
     N, H, W, Cin = x.shape
     osh, osw, oph, opw = lattice
     if y is None:
@@ -31,10 +31,19 @@ def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lat
     return y
 
 
-def conv_wgrad(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_plan=-1, plan_out=None, real=None):
+def conv_wgrad(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_plan=-1, plan_out=None, real=None, **_):
     N, H, W, Cin = x.shape
     dw_ = torch.zeros(len(tap_dh), Cout, Cin)
     d = dy[..., dy_coff:dy_coff + Cout].reshape(-1, Cout)
     for t, (dh, dwo) in enumerate(zip(tap_dh, tap_dw)):
         dw_[t] = d.t() @ _gather(x, dh, dwo, OH, OW, stride).reshape(-1, Cin)
     return dw_
+
+
+def pack_taps(w, taps, k_padded, round_tf32=True):
+    """sos_pack_taps semantics: out[r, t*k_padded + k] = w[r, k, taps[t][0], taps[t][1]], zero padded (no rounding here)."""
+    R, K = w.shape[0], w.shape[1]
+    out = torch.zeros(R, len(taps) * k_padded)
+    for t, (a, b) in enumerate(taps):
+        out[:, t * k_padded:t * k_padded + K] = w[:, :, a, b]
+    return out

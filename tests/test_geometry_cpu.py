@@ -25,6 +25,7 @@ CASES = [
 def emulated(monkeypatch):
     monkeypatch.setattr(ops, "conv_tc", _emul.conv_tc)
     monkeypatch.setattr(ops, "conv_wgrad", _emul.conv_wgrad)
+    monkeypatch.setattr(ops, "pack_taps", _emul.pack_taps)
     monkeypatch.setattr(ops, "round_tf32_", lambda t: t)          # operand rounding is a device kernel; geometry only here
 
 
