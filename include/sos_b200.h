@@ -103,6 +103,21 @@ int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y,
                         const float* scale, const float* shift, const float* mean, const float* invstd, int act,
                         const float* slope, float* partial, float* dgamma, float* dbeta, float* dslope, float* m1, float* m2,
                         cudaStream_t stream);
+/* Half-precision operand producers (the tensor-core GEMMs run kind::f16 on them).
+ * sos_bn_act_half: as sos_bn_act with a dense half output z (rows, channels), channels % 8 == 0.
+ * sos_bn_act_backward_half: as sos_bn_act_backward (dense dz) with dy written as half(dy * s), s the power of two that brings
+ *   the tensor's RMS to ~1 (fp16 keeps 11 significant bits from 6e-5 to 65504 only; gradient maps live near 1e-8).
+ *   scal (3 floats, scal[2] zeroed by the caller): out scal[0] = s, scal[1] = 1/s (the out_scale of the consuming GEMMs),
+ *   scal[2] = sum of dy^2.  partial: sos_bn_partial_blocks(rows, C) * 4 * C floats.
+ * sos_to_half: out (rows, cd) half = x (rows, cs) fp32 zero-padded to cd channels; with scal != NULL (3 floats, scal[2]
+ *   zeroed by the caller) the values are scaled as above. */
+int sos_bn_act_half(const float* y, void* z_half, int64_t rows, int64_t channels, const float* scale, const float* shift,
+                    int act, const float* slope, cudaStream_t stream);
+int sos_bn_act_backward_half(const float* dz, const float* y, void* dy_half, int64_t rows, int64_t channels, const float* scale,
+                             const float* shift, const float* mean, const float* invstd, int act, const float* slope,
+                             float* partial, float* dgamma, float* dbeta, float* dslope, float* m1, float* m2, float* scal,
+                             cudaStream_t stream);
+int sos_to_half(const float* x, int64_t rows, int64_t cs, void* out_half, int64_t cd, float* scal, cudaStream_t stream);
 /* eval-mode backward of z = act(y*scale+shift): dy = dz*act'(pre)*scale (no batch statistics). */
 int sos_affine_act_backward(const float* dz, const int32_t* dz_view, const float* y, float* dy, int64_t rows,
                             int64_t channels, const float* scale, const float* shift, int act, const float* slope,
@@ -146,6 +161,9 @@ int sos_pack_conv_weight(const float* w, int64_t Cout, int64_t Cin, int64_t kh, 
  *   rounded to TF32.  tap_off: host array, ntaps <= 49 entries. */
 int sos_pack_taps(const float* w, int64_t rows, int64_t K, int64_t KP, int64_t row_stride, int64_t k_stride, int64_t ntaps,
                   const int32_t* tap_off, int round_tf32, float* out, cudaStream_t stream);
+/* Same gather with a half output (operand of the kind::f16 GEMMs). */
+int sos_pack_taps_half(const float* w, int64_t rows, int64_t K, int64_t KP, int64_t row_stride, int64_t k_stride, int64_t ntaps,
+                       const int32_t* tap_off, void* out_half, cudaStream_t stream);
 /* wgrad buffer [tap][CoutP][CinP] -> PyTorch (Cout, Cin, kh, kw) (transposed=0) or ConvTranspose (Cin, Cout, kh, kw)
  * (transposed=1, in which case src is [tap][CinP'][CoutP'] with the roles swapped by the caller). */
 int sos_unpack_wgrad(const float* src, int64_t Cout, int64_t Cin, int64_t ntaps, int64_t CinP, float* dst, int accumulate,
@@ -187,7 +205,16 @@ typedef struct sos_conv_args {
   float* stats_partial;    /* device, or NULL */
   int64_t stats_channels;
   int32_t* stats_rows_out; /* host */
+  /* Operand type: SOS_DTYPE_TF32 (default, 0) = fp32 storage read as TF32 (kind::tf32); SOS_DTYPE_F16 = x and wk are IEEE
+   * half arrays (same 11-bit significand as TF32, half the bytes, twice the tensor rate: kind::f16), Cin % 16 == 0.  The
+   * accumulators and y stay fp32 unless y_dtype == SOS_DTYPE_F16 (y is then a half array; Cy and y_coff in halfs, % 8 == 0). */
+  int64_t x_dtype, y_dtype;
+  /* Optional device scalar multiplied into every output before the affine / activation: undoes the power-of-two scale a
+   * half-precision gradient operand carries (sos_bn_act_backward_half, sos_to_half). */
+  const float* out_scale;
 } sos_conv_args;
+#define SOS_DTYPE_TF32 0
+#define SOS_DTYPE_F16 1
 int sos_conv_stats_rows(void);   /* upper bound of *stats_rows_out (4 x SM count) */
 int sos_conv2d_tc(const sos_conv_args* args, cudaStream_t stream);
 
@@ -206,6 +233,8 @@ typedef struct sos_wgrad_args {
   int64_t ntaps, stride;
   int64_t force_plan;
   int32_t* plan_out;
+  int64_t dtype;            /* SOS_DTYPE_TF32 (x, dy fp32) or SOS_DTYPE_F16 (x, dy half; Cdy and dy_coff % 8 == 0) */
+  const float* out_scale;   /* optional device scalar multiplied into the sums before they are added to dw */
 } sos_wgrad_args;
 int sos_conv2d_wgrad(const sos_wgrad_args* args, cudaStream_t stream);
 

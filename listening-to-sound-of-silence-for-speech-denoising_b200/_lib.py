@@ -26,7 +26,8 @@ class ConvArgs(C.Structure):
                 ("epi_scale", C.c_void_p), ("epi_shift", C.c_void_p),
                 ("act", i64), ("slope", C.c_void_p),
                 ("force_plan", i64), ("plan_out", C.POINTER(C.c_int32)),
-                ("stats_partial", C.c_void_p), ("stats_channels", i64), ("stats_rows_out", C.POINTER(C.c_int32))]
+                ("stats_partial", C.c_void_p), ("stats_channels", i64), ("stats_rows_out", C.POINTER(C.c_int32)),
+                ("x_dtype", i64), ("y_dtype", i64), ("out_scale", C.c_void_p)]
 
 
 class WgradArgs(C.Structure):
@@ -35,7 +36,8 @@ class WgradArgs(C.Structure):
                 ("N", i64), ("H", i64), ("W", i64), ("Cin", i64),
                 ("Cout", i64), ("OH", i64), ("OW", i64), ("Cdy", i64), ("dy_coff", i64),
                 ("ntaps", i64), ("stride", i64),
-                ("force_plan", i64), ("plan_out", C.POINTER(C.c_int32))]
+                ("force_plan", i64), ("plan_out", C.POINTER(C.c_int32)),
+                ("dtype", i64), ("out_scale", C.c_void_p)]
 
 
 S = C.c_void_p  # cudaStream_t
@@ -60,6 +62,9 @@ _SIGS = {
     "sos_bn_eval_coeffs": (C.c_int, [i64, c_f, c_f, c_f, c_f, C.c_float, c_f, c_f, S]),
     "sos_bn_act": (C.c_int, [c_f, c_f, i32p, i64, i64, c_f, c_f, C.c_int, c_f, S]),
     "sos_bn_act_backward": (C.c_int, [c_f, i32p, c_f, c_f, i64, i64, c_f, c_f, c_f, c_f, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, S]),
+    "sos_bn_act_half": (C.c_int, [c_f, c_f, i64, i64, c_f, c_f, C.c_int, c_f, S]),
+    "sos_bn_act_backward_half": (C.c_int, [c_f, c_f, c_f, i64, i64, c_f, c_f, c_f, c_f, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f, S]),
+    "sos_to_half": (C.c_int, [c_f, i64, i64, c_f, i64, c_f, S]),
     "sos_affine_act_backward": (C.c_int, [c_f, i32p, c_f, c_f, i64, i64, c_f, c_f, C.c_int, c_f, S]),
     "sos_nchw_to_nhwc": (C.c_int, [c_f, i64, i64, c_f, i32p, i64, S]),
     "sos_nhwc_to_nchw": (C.c_int, [c_f, i32p, i64, i64, c_f, S]),
@@ -74,6 +79,7 @@ _SIGS = {
     "sos_bias_act_backward": (C.c_int, [c_f, c_f, c_f, i64, i64, i64, C.c_int, c_f, S]),
     "sos_pack_conv_weight": (C.c_int, [c_f, i64, i64, i64, i64, i64, i64, C.c_int, c_f, S]),
     "sos_pack_taps": (C.c_int, [c_f, i64, i64, i64, i64, i64, i64, C.POINTER(C.c_int32), C.c_int, c_f, S]),
+    "sos_pack_taps_half": (C.c_int, [c_f, i64, i64, i64, i64, i64, i64, C.POINTER(C.c_int32), c_f, S]),
     "sos_unpack_wgrad": (C.c_int, [c_f, i64, i64, i64, i64, c_f, C.c_int, S]),
     "sos_conv2d_tc": (C.c_int, [C.POINTER(ConvArgs), S]),
     "sos_conv2d_wgrad": (C.c_int, [C.POINTER(WgradArgs), S]),

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -50,6 +51,19 @@ __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
+}
+// Half-precision operand scaling: the power of two s that brings a tensor's RMS to ~1 (fp16 keeps its 11 significant bits
+// between 6.1e-5 and 65504; max <= sqrt(n) * RMS, so n < 2^32 elements cannot overflow).  Returns the exponent e, s = 2^e.
+__device__ __forceinline__ int half_scale_exp(float sumsq, float count) {
+  const float ms = sumsq / count;
+  if (!(ms > 0.f) || !(ms < 3e38f)) return 0;
+  int e = (int)rintf(-0.5f * log2f(ms));
+  return max(-100, min(100, e));
+}
+__device__ __forceinline__ float pow2i(int e) { return __int_as_float((e + 127) << 23); }
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 #define SOS_ACT_MASK 15
 #define SOS_ACT_ROUND_TF32 16

@@ -47,6 +47,10 @@ struct alignas(64) TcParams {
   const float* shift;
   int act;                       // 0 none, 1 relu, 2 prelu
   const float* slope;
+  int esz;                       // operand element size: 4 (TF32 in fp32 storage) or 2 (half)
+  int b_tile_bytes;              // bytes of one staged weight box
+  int y_half;                    // outputs are stored as half (staging rows of ec * 2 bytes)
+  const float* out_scale;        // optional device scalar multiplied into every output
   float* stats;                  // optional BatchNorm partial sums [4 * grid][2][stats_c] of the RAW outputs (sum, sum of squares)
   int stats_c, out_fast, lat_slow;
   TapGroup groups[kMaxGroups];
@@ -69,7 +73,8 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
   return c;
 }
 
-__global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __grid_constant__ TcParams p) {
+template <int KIND>
+__device__ __forceinline__ void tapgemm_body(const TcParams& p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
       for (int g = 0; g < p.n_groups; ++g) {
         const TapGroup& grp = p.groups[g];
         const int n_sub = grp.n_sub;
-        const uint32_t tx_bytes = (uint32_t)p.S * p.a_box_bytes + (uint32_t)n_sub * (p.N * p.cbe * 4);
+        const uint32_t tx_bytes = (uint32_t)p.S * p.a_box_bytes + (uint32_t)n_sub * p.b_tile_bytes;
         const int fast0 = fast_t + grp.d_fast, slow0 = slow_t + grp.d_slow;
         for (int c = 0; c < p.n_chunks; ++c) {
           mbar_wait(empty_bar(stage), phase ^ 1, 100);
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
               const uint4 e = p.prog[m];
               const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + e.x);
               const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + e.y);
-              umma_tf32(d_base + e.z, ad, bd, idesc, (e.w & first_mask) == 0u);
+              umma<KIND>(d_base + e.z, ad, bd, idesc, (e.w & first_mask) == 0u);
             }
             umma_commit(empty_bar(stage));                 // frees the smem stage when these MMAs retire
             if (l == loads_per_tile - 1) umma_commit(tfull_bar(acc));
@@ -195,7 +200,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
     uint32_t acc_phase = 0;
     int buf = 0;
     const float slope = ((p.act & SOS_ACT_MASK) == 2 && p.slope) ? *p.slope : 0.f;
+    const float oscale = p.out_scale ? *p.out_scale : 1.f;
     const int n_ec = p.N / p.ec;
+    const int erow = p.ec * (p.y_half ? 2 : 4);          // bytes of one staging row
     float* my_stats = stats_s + q * 512;                 // this warp's [2][256]
     if (p.stats) {
       for (int i = lane; i < 512; i += 32) my_stats[i] = 0.f;
@@ -241,13 +248,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
               my_stats[256 + cc * p.ec + lane] += w[0];
             }
           }
-          if (p.scale || p.act) {
+          if (p.scale || p.act || p.out_scale) {
             const int act = p.act & SOS_ACT_MASK;
             const bool rnd = (p.act & SOS_ACT_ROUND_TF32) != 0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               if (i < p.ec) {
-                float v = __uint_as_float(r[i]);
+                float v = __uint_as_float(r[i]) * oscale;
                 if (p.scale) v = fmaf(v, __ldg(p.scale + ch0 + i), __ldg(p.shift + ch0 + i));
                 if (act == 1) v = fmaxf(v, 0.f);
                 else if (act == 2) v = v > 0.f ? v : v * slope;
@@ -259,17 +266,34 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
           // make sure the TMA store that last read this staging buffer has drained
           if (ethread == 0) bulk_wait_read<1>();
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          const uint32_t sbuf = staging_base + (uint32_t)buf * (128 * p.ec * 4);
-          const uint32_t srow = sbuf + (uint32_t)row * (p.ec * 4);
+          const uint32_t sbuf = staging_base + (uint32_t)buf * (128 * erow);
+          const uint32_t srow = sbuf + (uint32_t)row * erow;
           // staging rows are written in the TMA store's swizzle (128B rows: 16-byte chunk ^= row & 7; 64B rows: chunk ^=
-          // (row >> 1) & 3), which is also bank-conflict free for a quarter-warp of consecutive rows
-          const int xr = p.ec == 32 ? (row & 7) : ((row >> 1) & 3);
+          // (row >> 1) & 3; 32B rows: chunk ^= (row >> 2) & 1), which is also bank-conflict free for a quarter-warp of
+          // consecutive rows
+          const int xr = erow == 128 ? (row & 7) : (erow == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+          if (p.y_half) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (j < p.ec / 4)
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ xr) << 4)), "r"(r[4 * j]), "r"(r[4 * j + 1]),
-                           "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
-                           : "memory");
+            for (int j = 0; j < 4; ++j) {
+              if (j < p.ec / 8) {
+                uint32_t h[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const __half2 hv = __floats2half2_rn(__uint_as_float(r[8 * j + 2 * k]), __uint_as_float(r[8 * j + 2 * k + 1]));
+                  h[k] = *reinterpret_cast<const uint32_t*>(&hv);
+                }
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ xr) << 4)), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3])
+                             : "memory");
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (j < p.ec / 4)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ xr) << 4)), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                             "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                             : "memory");
+            }
           }
           fence_proxy_async_smem();
           asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -304,23 +328,33 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __gri
   }
 }
 
+__global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __grid_constant__ TcParams p) { tapgemm_body<0>(p); }
+__global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_f16_kernel(const __grid_constant__ TcParams p) { tapgemm_body<1>(p); }
+
 }  // namespace
 
 extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG(ap != nullptr, "sos_conv2d_tc: null args");
   const sos_conv_args& a = *ap;
   SOS_CHECK_ARG(a.x && a.wk && a.y && a.tap_dh && a.tap_dw, "sos_conv2d_tc: null pointer");
+  SOS_CHECK_ARG((a.x_dtype == SOS_DTYPE_TF32 || a.x_dtype == SOS_DTYPE_F16) && (a.y_dtype == SOS_DTYPE_TF32 || a.y_dtype == SOS_DTYPE_F16),
+                "sos_conv2d_tc: unknown operand / output type");
+  const int esz = a.x_dtype == SOS_DTYPE_F16 ? 2 : 4;       // operand element size
+  const int kpe = 32 / esz;                                // K elements per MMA
+  const int ysz = a.y_dtype == SOS_DTYPE_F16 ? 2 : 4;
+  // (a half map of 8 channels is legal: the 16-channel TMA boxes read the missing K half as zeros)
   SOS_CHECK_ARG(a.N > 0 && a.H > 0 && a.W > 0 && a.Cin >= 8 && a.Cin % 8 == 0, "sos_conv2d_tc: Cin must be a positive multiple of 8 (got %lld)",
                 (long long)a.Cin);
   SOS_CHECK_ARG(a.Cout > 0 && a.OH > 0 && a.OW > 0 && a.ntaps > 0 && a.ntaps <= 49, "sos_conv2d_tc: bad output shape / taps");
   SOS_CHECK_ARG(a.stride == 1 || a.stride == 2, "sos_conv2d_tc: stride must be 1 or 2");
   SOS_CHECK_ARG(a.osh >= 1 && a.osw >= 1 && a.oph >= 0 && a.opw >= 0 && a.oph < a.osh && a.opw < a.osw, "sos_conv2d_tc: bad output lattice");
-  SOS_CHECK_ARG(a.Cy % 4 == 0 && a.y_coff % 4 == 0 && a.y_coff < a.Cy, "sos_conv2d_tc: output channels / offset must be multiples of 4");
+  SOS_CHECK_ARG(a.Cy % (16 / ysz) == 0 && a.y_coff % (16 / ysz) == 0 && a.y_coff < a.Cy, "sos_conv2d_tc: output channels / offset must be multiples of 16 bytes");
   SOS_CHECK_ARG(((uintptr_t)a.x % 16) == 0 && ((uintptr_t)a.y % 16) == 0 && ((uintptr_t)a.wk % 16) == 0, "sos_conv2d_tc: pointers must be 16-byte aligned");
   SOS_CHECK_ARG((a.OH - 1) * a.osh + a.oph < a.YH && (a.OW - 1) * a.osw + a.opw < a.YW, "sos_conv2d_tc: output lattice exceeds the output buffer");
 
   // ---- output-channel blocking
   const int Cin = (int)a.Cin, Cout = (int)a.Cout;
+  const int CinK = round_up(Cin, kpe);                      // K extent per tap as the MMAs see it
   const int Ntot = round_up(Cout, 16);
   int N = Ntot, n_nblk = 1;
   if (Ntot > 256) {
@@ -331,18 +365,18 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
     }
   }
   const int ec = (N % 32 == 0) ? 32 : 16;
-  const int staging_bytes = 2 * 128 * ec * 4;
+  const int staging_bytes = 2 * 128 * ec * 4;               // (half outputs use the first half of each buffer)
   const int avail = kSmemLimit - 1024 - staging_bytes - 512 - kStatsSmem;
 
   // ---- choose orientation / box sharing / taps per box / channel chunk / sub-tiles: the cheapest candidate (tensor time vs
   //      L2->smem feed time per output pixel) whose pipeline stage fits at least twice (three times preferred) in shared memory
   Geometry geo{(int)a.ntaps, a.tap_dh, a.tap_dw, (int)a.H, (int)a.W, (int)a.OH, (int)a.OW, (int)a.stride, Cin, Cout,
-               a.osh == 1 && a.osw == 1 && a.oph == 0 && a.opw == 0, kMaxSub, true};
+               a.osh == 1 && a.osw == 1 && a.oph == 0 && a.opw == 0, kMaxSub, true, esz};
   struct Cand { Plan pl; int cbe = 0, S = 0, n_stages = 0, stage_bytes = 0, a_box_bytes = 0; double cost = 1e300; };
   Cand best;
   auto consider = [&](const Plan& pl, int cbe, int S) {
     if (n_nblk > 1 || S * N > 256) S = 1;
-    const int cb = cbe * 4;
+    const int cb = cbe * esz;
     const int a_box = (pl.SB + pl.halo) * pl.FB * cb;
     int max_sub = 1;
     for (auto& g : pl.groups) max_sub = std::max(max_sub, (int)g.n_sub);
@@ -351,8 +385,8 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
     if (n_stages < 2) return;
     const int out_fast = pl.fast_is_w ? (int)a.OW : (int)a.OH, out_slow = pl.fast_is_w ? (int)a.OH : (int)a.OW;
     const int tiles_fast = ceil_div(out_fast, pl.FB);
-    const double mma = (double)a.ntaps * (Cin / 8) * S * (128.0 * N / 256.0);
-    const double bytes = ((double)pl.groups.size() * S * (pl.SB + pl.halo) * pl.FB + (double)a.ntaps * N) * Cin * 4.0;
+    const double mma = (double)a.ntaps * (CinK / kpe) * S * (128.0 * N / 256.0);
+    const double bytes = ((double)pl.groups.size() * S * (pl.SB + pl.halo) * pl.FB + (double)a.ntaps * N) * Cin * (double)esz;
     const int lat_slow = out_slow / pl.g;
     const double util = ((double)lat_slow / (ceil_div(lat_slow, pl.SB) * pl.SB)) * ((double)out_fast / (ceil_div(tiles_fast, S) * S * pl.FB));
     double cost = std::max(mma, bytes / 40.0) / (util * S);
@@ -366,8 +400,8 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
       Plan pl;
       if (!build_plan(geo, fw, sh, pl)) continue;
       any = true;
-      for (int cbe = 32; cbe >= 8; cbe >>= 1) {
-        if (Cin % cbe) continue;
+      for (int cbe = 4 * kpe; cbe >= kpe; cbe >>= 1) {
+        if (CinK % cbe) continue;
         consider(pl, cbe, 2);
         consider(pl, cbe, 1);
       }
@@ -388,7 +422,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   p.N = N;
   p.n_nblk = n_nblk;
   p.cbe = best.cbe;
-  p.n_chunks = Cin / p.cbe;
+  p.n_chunks = CinK / p.cbe;
   p.cin = Cin;
   p.ec = ec;
   p.FB = pl.FB;
@@ -398,10 +432,14 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   p.stride = (int)a.stride;
   p.n_groups = (int)pl.groups.size();
   for (int i = 0; i < p.n_groups; ++i) p.groups[i] = pl.groups[i];
-  const int cb = p.cbe * 4;
+  const int cb = p.cbe * esz;
+  p.esz = esz;
+  p.b_tile_bytes = N * cb;
+  p.y_half = ysz == 2;
+  p.out_scale = a.out_scale;
   p.layout_type = cb == 128 ? 2 : (cb == 64 ? 4 : 6);
   p.sbo = 8 * cb;
-  p.idesc = make_idesc_tf32(128, N, 0, 0);
+  p.idesc = esz == 2 ? make_idesc_f16(128, N, 0, 0) : make_idesc_tf32(128, N, 0, 0);
   const int box_slow = pl.SB + pl.halo;
   p.a_box_bytes = best.a_box_bytes;
   p.a_box_stride = round_up(p.a_box_bytes, 1024);
@@ -411,7 +449,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   p.staging_bytes = staging_bytes;
   {
     int n = 0;
-    const int kk_per_chunk = p.cbe / 8;
+    const int kk_per_chunk = p.cbe / kpe;
     for (int gi = 0; gi < p.n_groups; ++gi) {
       const TapGroup& grp = p.groups[gi];
       int same = -1;                                      // an earlier group with the same sub-tap structure shares its program
@@ -422,7 +460,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
       for (int s2 = 0; s2 < p.S; ++s2)
         for (int j = 0; j < grp.n_sub; ++j)
           for (int kk = 0; kk < kk_per_chunk; ++kk) {
-            const uint32_t a_delta = (uint32_t)s2 * p.a_box_stride + (uint32_t)grp.a_off[j] * (p.FB * p.cbe * 4) + kk * 32;
+            const uint32_t a_delta = (uint32_t)s2 * p.a_box_stride + (uint32_t)grp.a_off[j] * (p.FB * cb) + kk * 32;
             const uint32_t b_delta = (uint32_t)j * p.b_tile_stride + kk * 32;
             SOS_CHECK_ARG(n < kMaxProg, "sos_conv2d_tc: MMA program of %d entries is too long", n);
             p.prog[n++] = make_uint4(a_delta >> 4, b_delta >> 4, (uint32_t)s2 * N, (j == 0 && kk == 0) ? 1u : 0u);
@@ -437,45 +475,48 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG((a.epi_scale == nullptr) == (a.epi_shift == nullptr), "sos_conv2d_tc: epi_scale and epi_shift go together");
   p.stats = a.stats_partial;
   p.stats_c = (int)a.stats_channels;
-  SOS_CHECK_ARG(a.stats_partial == nullptr || (n_nblk == 1 && a.stats_channels > 0 && a.stats_channels <= 256 && a.stats_channels <= a.Cy - a.y_coff &&
+  SOS_CHECK_ARG(a.stats_partial == nullptr || (ysz == 4 && n_nblk == 1 && a.stats_channels > 0 && a.stats_channels <= 256 && a.stats_channels <= a.Cy - a.y_coff &&
                                                a.epi_scale == nullptr && (a.act & SOS_ACT_MASK) == 0),
                 "sos_conv2d_tc: fused BatchNorm statistics need raw outputs of at most 256 channels in one channel block");
 
   // ---- tensor maps.  Dim order: (channel, fast, slow/g, phase(g), image)
   const bool fw = pl.fast_is_w;
   const int g = pl.g;
-  const uint64_t pixA = (uint64_t)Cin * 4;
+  const uint64_t pixA = (uint64_t)Cin * esz;
+  const CUtensorMapDataType dtA = esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
   const uint64_t in_fast = fw ? a.W : a.H, in_slow = fw ? a.H : a.W;
   const uint64_t sA_fast = fw ? pixA : pixA * a.W, sA_slow = fw ? pixA * a.W : pixA;
   {
     uint64_t dims[5] = {(uint64_t)Cin, in_fast, in_slow / g, (uint64_t)g, (uint64_t)a.N};
-    uint64_t str[5] = {4, sA_fast, sA_slow * g, sA_slow, pixA * a.H * a.W};
+    uint64_t str[5] = {(uint64_t)esz, sA_fast, sA_slow * g, sA_slow, pixA * a.H * a.W};
     uint32_t box[5] = {(uint32_t)p.cbe, (uint32_t)(pl.FB * a.stride), (uint32_t)(box_slow * a.stride), 1, 1};
     uint32_t es[5] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1, 1};
     SOS_CHECK_ARG(box[1] <= 256 && box[2] <= 256, "sos_conv2d_tc: activation box too large");
     const CUtensorMapSwizzle sw = cb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (cb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    if (int e = encode_map(&p.mapA, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, a.x, dims, str, box, es, sw, "activations")) return e;
+    if (int e = encode_map(&p.mapA, dtA, 5, a.x, dims, str, box, es, sw, "activations")) return e;
     uint64_t bd[2] = {(uint64_t)a.ntaps * Cin, (uint64_t)Cout};
-    uint64_t bs[2] = {4, (uint64_t)a.ntaps * Cin * 4};
+    uint64_t bs[2] = {(uint64_t)esz, (uint64_t)a.ntaps * Cin * esz};
     uint32_t bb[2] = {(uint32_t)p.cbe, (uint32_t)N};
     uint32_t be[2] = {1, 1};
-    if (int e = encode_map(&p.mapB, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, a.wk, bd, bs, bb, be, sw, "weights")) return e;
+    if (int e = encode_map(&p.mapB, dtA, 2, a.wk, bd, bs, bb, be, sw, "weights")) return e;
   }
   const int out_fast = fw ? (int)a.OW : (int)a.OH, out_slow = fw ? (int)a.OH : (int)a.OW;
   {
-    const uint64_t pixY = (uint64_t)a.Cy * 4;
+    const uint64_t pixY = (uint64_t)a.Cy * ysz;
     const uint64_t rowY = pixY * a.YW;
     // output pixel (oh, ow) lives at (oh*osh + oph, ow*osw + opw)
     const uint64_t sY_h = rowY * a.osh, sY_w = pixY * a.osw;
-    const float* base = a.y + a.y_coff + ((uint64_t)a.oph * a.YW + a.opw) * a.Cy;
-    const int cstore = std::min(round_up(Cout, 4), (int)(a.Cy - a.y_coff));
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(a.y) + (a.y_coff + ((uint64_t)a.oph * a.YW + a.opw) * a.Cy) * ysz;
+    const int cstore = std::min(round_up(Cout, 16 / ysz), (int)(a.Cy - a.y_coff));
     const uint64_t sY_fast = fw ? sY_w : sY_h, sY_slow = fw ? sY_h : sY_w;
     uint64_t dims[5] = {(uint64_t)cstore, (uint64_t)out_fast, (uint64_t)(out_slow / g), (uint64_t)g, (uint64_t)a.N};
-    uint64_t str[5] = {4, sY_fast, sY_slow * g, sY_slow, pixY * a.YH * a.YW};
+    uint64_t str[5] = {(uint64_t)ysz, sY_fast, sY_slow * g, sY_slow, pixY * a.YH * a.YW};
     uint32_t box[5] = {(uint32_t)p.ec, (uint32_t)pl.FB, (uint32_t)pl.SB, 1, 1};
     uint32_t es[5] = {1, 1, 1, 1, 1};
-    if (int e = encode_map(&p.mapD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, str, box, es,
-                            ec == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, "output")) return e;
+    const int erow = ec * ysz;
+    if (int e = encode_map(&p.mapD, ysz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, str, box, es,
+                            erow == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (erow == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
+                            "output")) return e;
   }
   const int tiles_fast = ceil_div(out_fast, pl.FB);
   p.out_fast = out_fast;
@@ -490,14 +531,16 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   const int smem = 1024 + p.n_stages * p.stage_bytes + staging_bytes + 512 + kStatsSmem;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(tapgemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess) {
+    if (cudaFuncSetAttribute(tapgemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess ||
+        cudaFuncSetAttribute(tapgemm_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess) {
       sos_set_error("sos_conv2d_tc: cannot raise dynamic shared memory to %d bytes: %s", kSmemLimit, cudaGetErrorString(cudaGetLastError()));
       return SOS_ERR_CUDA;
     }
     attr_set = true;
   }
   const int grid = (int)std::min<long long>(total, sos_num_sms());
-  tapgemm_tf32_kernel<<<grid, kThreadsTc, smem, stream>>>(p);
+  if (esz == 2) tapgemm_f16_kernel<<<grid, kThreadsTc, smem, stream>>>(p);
+  else tapgemm_tf32_kernel<<<grid, kThreadsTc, smem, stream>>>(p);
   SOS_CHECK_LAUNCH("sos_conv2d_tc");
   if (a.stats_rows_out) *a.stats_rows_out = 4 * grid;
   if (a.plan_out) {

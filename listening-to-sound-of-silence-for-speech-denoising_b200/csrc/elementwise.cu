@@ -242,22 +242,23 @@ __global__ void __launch_bounds__(kThreads) bn_act_kernel(const float* __restric
 
 // Backward pass 1: per-channel sums of dpre and dpre*xhat (+ PReLU slope grad).
 //   pre = y*scale+shift, dpre = dz * act'(pre), xhat = (y-mean)*invstd
+template <int NQ>   // 3 sums, or 4 with the sum of dpre^2 (half-precision gradient scaling)
 __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __restrict__ dz, View dzv, const float* __restrict__ y,
                                                                   long long P, int C, const float* __restrict__ scale,
                                                                   const float* __restrict__ shift, const float* __restrict__ mean,
                                                                   const float* __restrict__ invstd, int act,
                                                                   const float* __restrict__ slope_ptr,
-                                                                  float* __restrict__ partial /*[grid][3][C]*/) {
-  extern __shared__ float sm[];                 // [3][C] block totals (shared-memory atomics: a small footprint lets this
+                                                                  float* __restrict__ partial /*[grid][NQ][C]*/) {
+  extern __shared__ float sm[];                 // [NQ][C] block totals (shared-memory atomics: a small footprint lets this
                                                 // HBM-bound kernel share an SM with a tensor-core kernel of another stream)
-  for (int i = threadIdx.x; i < 3 * C; i += kThreads) sm[i] = 0.f;
+  for (int i = threadIdx.x; i < NQ * C; i += kThreads) sm[i] = 0.f;
   __syncthreads();
   const int cg = C >> 2;
   const int rows = kThreads / cg;
   const int r = threadIdx.x / cg, c4 = threadIdx.x - r * cg;
   const float slope = slope_ptr ? *slope_ptr : 0.f;
   act &= SOS_ACT_MASK;
-  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, s3[4] = {0, 0, 0, 0};
+  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, s3[4] = {0, 0, 0, 0}, s4[4] = {0, 0, 0, 0};
   if (r < rows) {
     const int c = c4 * 4;
     float sc[4], sh[4], mu[4], is[4];
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __
           else if (act == 2) { if (pre <= 0.f) { s3[i] = fmaf(dv[i], pre, s3[i]); dpre *= slope; } }
           s1[i] += dpre;
           s2[i] = fmaf(dpre, (yv[i] - mu[i]) * is[i], s2[i]);
+          if (NQ == 4) s4[i] = fmaf(dpre, dpre, s4[i]);
         }
       }
     }
@@ -295,21 +297,24 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __
       atomicAdd(sm + c + i, s1[i]);
       atomicAdd(sm + C + c + i, s2[i]);
       atomicAdd(sm + 2 * C + c + i, s3[i]);
+      if (NQ == 4) atomicAdd(sm + 3 * C + c + i, s4[i]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * C; i += kThreads) partial[(size_t)blockIdx.x * 3 * C + i] = sm[i];
+  for (int i = threadIdx.x; i < NQ * C; i += kThreads) partial[(size_t)blockIdx.x * NQ * C + i] = sm[i];
 }
 
 // Backward finalize: dgamma, dbeta, dslope (atomically accumulated; zeroed by the caller) and the two per-channel means
 // used by pass 2.  Same 32-channel blocks as bn_finalize_kernel.
+template <int NQ>
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int G, int C, double count,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                              float* __restrict__ dslope, float* __restrict__ m1, float* __restrict__ m2) {
-  __shared__ double sm[8][3][32];
+                                                              float* __restrict__ dslope, float* __restrict__ m1, float* __restrict__ m2,
+                                                              const float* __restrict__ scale, float* __restrict__ dy_sumsq) {
+  __shared__ double sm[8][NQ][32];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), gl = threadIdx.x >> 5;
-  double r[3];
-  reduce_partials<3>(partial, G, C, c, gl, r, sm);
+  double r[NQ];
+  reduce_partials<NQ>(partial, G, C, c, gl, r, sm);
   if (gl != 0) return;
   float s3 = 0.f;
   if (c < C) {
@@ -318,6 +323,17 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
     m1[c] = (float)(r[0] / count);
     m2[c] = (float)(r[1] / count);
     s3 = (float)r[2];
+  }
+  if (NQ == 4) {
+    // sum over pixels of dy^2 with dy = scale (dpre - m1 - xhat m2):  scale^2 (sum dpre^2 - P m1^2 - P m2^2)
+    float q = 0.f;
+    if (c < C) {
+      const double a = r[0] / count, b = r[1] / count, sc = (double)scale[c];
+      const double v = sc * sc * (r[NQ - 1] - count * a * a - count * b * b);
+      q = v > 0 ? (float)v : 0.f;
+    }
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) atomicAdd(dy_sumsq, q);
   }
   if (dslope) {
     s3 = warp_sum(s3);
@@ -442,6 +458,127 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_dense_kernel(const floa
       }
       *reinterpret_cast<float4*>(dy + (size_t)e * 4) = make_float4(o[0], o[1], o[2], o[3]);
     }
+  }
+}
+
+// ----------------------------------------------------------------------------- half-precision operand producers
+// z half dense [P][C] = act(y * scale + shift): a thread owns 8 channels (two 16-byte loads, one 16-byte store).
+__global__ void __launch_bounds__(kThreads) bn_act_half_kernel(const float* __restrict__ y, uint4* __restrict__ z, unsigned total, unsigned cg8,
+                                                                const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                                                const float* __restrict__ slope_ptr) {
+  const float slope = slope_ptr ? *slope_ptr : 0.f;
+  act &= SOS_ACT_MASK;
+  const unsigned span = gridDim.x * blockDim.x;
+  for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += span * 2) {
+    float4 v[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const unsigned e = e0 + i * span;
+      if (e < total) {
+        v[i][0] = ld_stream(y + (size_t)e * 8);
+        v[i][1] = ld_stream(y + (size_t)e * 8 + 4);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const unsigned e = e0 + i * span;
+      if (e >= total) break;
+      const unsigned c = (e % cg8) * 8;
+      const float in[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = act_fwd(fmaf(in[k], __ldg(scale + c + k), __ldg(shift + c + k)), act, slope);
+      z[e] = make_uint4(pack_half2(o[0], o[1]), pack_half2(o[2], o[3]), pack_half2(o[4], o[5]), pack_half2(o[6], o[7]));
+    }
+  }
+}
+
+// BatchNorm backward pass 2 with a scaled half output: dy = half(s * scale (dpre - m1 - xhat m2)), s = 2^e from the tensor's
+// sum of squares (scal[2], written by the finalize kernel).  Block 0 publishes scal[0] = s, scal[1] = 1/s.
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_half_kernel(const float* __restrict__ dz, const float* __restrict__ y,
+                                                                      uint4* __restrict__ dy, unsigned total, unsigned cg8,
+                                                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                      const float* __restrict__ m1, const float* __restrict__ m2, int act,
+                                                                      const float* __restrict__ slope_ptr, float* __restrict__ scal, float count) {
+  const float slope = slope_ptr ? *slope_ptr : 0.f;
+  act &= SOS_ACT_MASK;
+  const int ex = half_scale_exp(scal[2], count);
+  const float s = pow2i(ex);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    scal[0] = s;
+    scal[1] = pow2i(-ex);
+  }
+  const unsigned span = gridDim.x * blockDim.x;
+  for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += span * 2) {
+    float4 yv4[2][2], dz4[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const unsigned e = e0 + i * span;
+      if (e < total) {
+        yv4[i][0] = ld_stream(y + (size_t)e * 8);
+        yv4[i][1] = ld_stream(y + (size_t)e * 8 + 4);
+        dz4[i][0] = ld_stream(dz + (size_t)e * 8);
+        dz4[i][1] = ld_stream(dz + (size_t)e * 8 + 4);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const unsigned e = e0 + i * span;
+      if (e >= total) break;
+      const unsigned c = (e % cg8) * 8;
+      const float yv[8] = {yv4[i][0].x, yv4[i][0].y, yv4[i][0].z, yv4[i][0].w, yv4[i][1].x, yv4[i][1].y, yv4[i][1].z, yv4[i][1].w};
+      const float dv[8] = {dz4[i][0].x, dz4[i][0].y, dz4[i][0].z, dz4[i][0].w, dz4[i][1].x, dz4[i][1].y, dz4[i][1].z, dz4[i][1].w};
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float sc = __ldg(scale + c + k);
+        const float pre = fmaf(yv[k], sc, __ldg(shift + c + k));
+        float dpre = dv[k];
+        if (act == 1) dpre = pre > 0.f ? dpre : 0.f;
+        else if (act == 2) dpre = pre > 0.f ? dpre : dpre * slope;
+        const float xhat = (yv[k] - __ldg(mean + c + k)) * __ldg(invstd + c + k);
+        o[k] = s * (sc * (dpre - __ldg(m1 + c + k) - xhat * __ldg(m2 + c + k)));
+      }
+      dy[e] = make_uint4(pack_half2(o[0], o[1]), pack_half2(o[2], o[3]), pack_half2(o[4], o[5]), pack_half2(o[6], o[7]));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) acc = fmaf(x[e], x[e], acc);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+// out half [P][cd] = s * x [P][cs] (zero for channels >= cs); one thread per 8 output channels.
+__global__ void __launch_bounds__(kThreads) to_half_kernel(const float* __restrict__ x, long long P, int cs, uint4* __restrict__ out, int cd,
+                                                            float* __restrict__ scal, float count) {
+  float s = 1.f;
+  if (scal) {
+    const int ex = half_scale_exp(scal[2], count);
+    s = pow2i(ex);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      scal[0] = s;
+      scal[1] = pow2i(-ex);
+    }
+  }
+  const int g8 = cd >> 3;
+  const long long total = P * g8;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / g8;
+    const int c = (int)(e - p * g8) * 8;
+    float v[8];
+    if (c + 8 <= cs && (cs & 3) == 0) {
+      const float4 a = *reinterpret_cast<const float4*>(x + p * cs + c), b = *reinterpret_cast<const float4*>(x + p * cs + c + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = c + k < cs ? x[p * cs + c + k] : 0.f;
+    }
+    out[e] = make_uint4(pack_half2(s * v[0], s * v[1]), pack_half2(s * v[2], s * v[3]), pack_half2(s * v[4], s * v[5]), pack_half2(s * v[6], s * v[7]));
   }
 }
 
@@ -745,6 +882,18 @@ __global__ void pack_taps_kernel(const float* __restrict__ w, int R, int K, int 
   }
 }
 
+__global__ void pack_taps_half_kernel(const float* __restrict__ w, int R, int K, int KP, long long sr, long long sk, int ntaps, TapOffsets taps,
+                                      __half* __restrict__ out) {
+  const long long total = (long long)R * ntaps * KP;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % KP);
+    const long long t2 = e / KP;
+    const int t = (int)(t2 % ntaps);
+    const int r = (int)(t2 / ntaps);
+    out[e] = __float2half_rn(k < K ? w[r * sr + k * sk + taps.off[t]] : 0.f);
+  }
+}
+
 // wgrad result [taps][CoutP?]... -> PyTorch layout.  src is [tap][Cout][CinP] (tap-major), dst (Cout,Cin,kh,kw).
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, int Cout, int Cin, int ntaps, int CinP, float* __restrict__ dst,
                                     int accumulate) {
@@ -901,9 +1050,10 @@ int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y,
   SOS_CHECK_ARG(view_ok(dv, C) && rows % ((long long)dv.H * dv.W) == 0, "sos_bn_act_backward: inconsistent view");
   SOS_CHECK_ARG((act & SOS_ACT_MASK) != 2 || (slope && dslope), "sos_bn_act_backward: PReLU needs slope and dslope");
   const size_t smem = (size_t)3 * C * sizeof(float);
-  bn_bwd_reduce_kernel<<<G, kThreads, smem, stream>>>(dz, dv, y, rows, C, scale, shift, mean, invstd, act, slope, partial);
+  bn_bwd_reduce_kernel<3><<<G, kThreads, smem, stream>>>(dz, dv, y, rows, C, scale, shift, mean, invstd, act, slope, partial);
   SOS_CHECK_LAUNCH("sos_bn_act_backward(reduce)");
-  bn_bwd_finalize_kernel<<<ceil_div(C, 32), 256, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta, (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2);
+  bn_bwd_finalize_kernel<3><<<ceil_div(C, 32), 256, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta, (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2,
+                                                                 nullptr, nullptr);
   SOS_CHECK_LAUNCH("sos_bn_act_backward(finalize)");
   const long long tot4 = rows * (channels / 4);
   if (view_dense(dv, C) && tot4 < (1ll << 32))
@@ -912,6 +1062,56 @@ int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y,
   else
     bn_bwd_apply_kernel<<<grid_for(tot4), kThreads, 0, stream>>>(dz, dv, y, dy, rows, C, scale, shift, mean, invstd, m1, m2, act, slope);
   SOS_CHECK_LAUNCH("sos_bn_act_backward(apply)");
+  return SOS_OK;
+}
+
+int sos_bn_act_half(const float* y, void* z_half, int64_t rows, int64_t channels, const float* scale, const float* shift, int act,
+                    const float* slope, cudaStream_t stream) {
+  SOS_CHECK_ARG(y && z_half && scale && shift && rows > 0 && channels >= 8 && channels % 8 == 0, "sos_bn_act_half: bad arguments (channels % 8)");
+  SOS_CHECK_ARG((act & SOS_ACT_MASK) != 2 || slope, "sos_bn_act_half: PReLU needs a slope pointer");
+  const long long tot8 = rows * (channels / 8);
+  SOS_CHECK_ARG(tot8 < (1ll << 32), "sos_bn_act_half: too many elements");
+  bn_act_half_kernel<<<grid_for(tot8, kThreads * 2, 148 * 8), kThreads, 0, stream>>>(y, reinterpret_cast<uint4*>(z_half), (unsigned)tot8,
+                                                                                     (unsigned)(channels / 8), scale, shift, act, slope);
+  SOS_CHECK_LAUNCH("sos_bn_act_half");
+  return SOS_OK;
+}
+
+int sos_bn_act_backward_half(const float* dz, const float* y, void* dy_half, int64_t rows, int64_t channels, const float* scale,
+                             const float* shift, const float* mean, const float* invstd, int act, const float* slope, float* partial,
+                             float* dgamma, float* dbeta, float* dslope, float* m1, float* m2, float* scal, cudaStream_t stream) {
+  const int G = sos_bn_partial_blocks(rows, channels);
+  SOS_CHECK_ARG(dz && y && dy_half && scale && shift && mean && invstd && partial && dgamma && dbeta && m1 && m2 && scal && G > 0 &&
+                    channels % 8 == 0,
+                "sos_bn_act_backward_half: bad arguments");
+  SOS_CHECK_ARG((act & SOS_ACT_MASK) != 2 || (slope && dslope), "sos_bn_act_backward_half: PReLU needs slope and dslope");
+  const int C = (int)channels;
+  const View dv{1, (int)rows, 1, (int)rows, 0, 0, C, 0};      // dense rows (the reduce kernel only tests for density)
+  SOS_CHECK_ARG(rows < (1ll << 31), "sos_bn_act_backward_half: too many rows");
+  const size_t smem = (size_t)4 * C * sizeof(float);
+  bn_bwd_reduce_kernel<4><<<G, kThreads, smem, stream>>>(dz, dv, y, rows, C, scale, shift, mean, invstd, act, slope, partial);
+  SOS_CHECK_LAUNCH("sos_bn_act_backward_half(reduce)");
+  bn_bwd_finalize_kernel<4><<<ceil_div(C, 32), 256, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta,
+                                                                 (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2, scale, scal + 2);
+  SOS_CHECK_LAUNCH("sos_bn_act_backward_half(finalize)");
+  const long long tot8 = rows * (channels / 8);
+  SOS_CHECK_ARG(tot8 < (1ll << 32), "sos_bn_act_backward_half: too many elements");
+  bn_bwd_apply_half_kernel<<<grid_for(tot8, kThreads * 2, 148 * 8), kThreads, 0, stream>>>(
+      dz, y, reinterpret_cast<uint4*>(dy_half), (unsigned)tot8, (unsigned)(channels / 8), scale, shift, mean, invstd, m1, m2, act, slope, scal,
+      (float)((double)rows * (double)channels));
+  SOS_CHECK_LAUNCH("sos_bn_act_backward_half(apply)");
+  return SOS_OK;
+}
+
+int sos_to_half(const float* x, int64_t rows, int64_t cs, void* out_half, int64_t cd, float* scal, cudaStream_t stream) {
+  SOS_CHECK_ARG(x && out_half && rows > 0 && cs > 0 && cd >= cs && cd % 8 == 0, "sos_to_half: bad arguments (cd must be a multiple of 8, >= cs)");
+  if (scal) {
+    sumsq_kernel<<<grid_for(rows * cs, kThreads, 148 * 4), kThreads, 0, stream>>>(x, rows * cs, scal + 2);
+    SOS_CHECK_LAUNCH("sos_to_half(sumsq)");
+  }
+  to_half_kernel<<<grid_for(rows * (cd / 8)), kThreads, 0, stream>>>(x, rows, (int)cs, reinterpret_cast<uint4*>(out_half), (int)cd, scal,
+                                                                     (float)((double)rows * (double)cs));
+  SOS_CHECK_LAUNCH("sos_to_half");
   return SOS_OK;
 }
 
@@ -1056,6 +1256,17 @@ int sos_pack_taps(const float* w, int64_t rows, int64_t K, int64_t KP, int64_t r
   pack_taps_kernel<<<grid_for(rows * ntaps * KP), kThreads, 0, stream>>>(w, (int)rows, (int)K, (int)KP, row_stride, k_stride, (int)ntaps, t,
                                                                          round_tf32, out);
   SOS_CHECK_LAUNCH("sos_pack_taps");
+  return SOS_OK;
+}
+
+int sos_pack_taps_half(const float* w, int64_t rows, int64_t K, int64_t KP, int64_t row_stride, int64_t k_stride, int64_t ntaps,
+                       const int32_t* tap_off, void* out_half, cudaStream_t stream) {
+  SOS_CHECK_ARG(w && out_half && tap_off && rows > 0 && K > 0 && KP >= K && ntaps > 0 && ntaps <= 49, "sos_pack_taps_half: bad arguments");
+  TapOffsets t;
+  for (int i = 0; i < (int)ntaps; ++i) t.off[i] = tap_off[i];
+  pack_taps_half_kernel<<<grid_for(rows * ntaps * KP), kThreads, 0, stream>>>(w, (int)rows, (int)K, (int)KP, row_stride, k_stride, (int)ntaps, t,
+                                                                              reinterpret_cast<__half*>(out_half));
+  SOS_CHECK_LAUNCH("sos_pack_taps_half");
   return SOS_OK;
 }
 

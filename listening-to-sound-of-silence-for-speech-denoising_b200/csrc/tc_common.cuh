@@ -29,6 +29,7 @@ struct Geometry {
   bool lattice_out;            // output addressed densely (no sub-pixel scatter) -> dilation lattices allowed
   int max_sub;                 // most taps one staged box may serve (<= kMaxSub)
   bool allow_wide = false;     // 16 x 8 (fast x slow) tiles for short dilation lattices (forward / dgrad kernel only)
+  int esz = 4;                 // operand element size in bytes: 4 (TF32 in fp32 storage) or 2 (half)
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -158,10 +159,11 @@ inline bool build_plan(const Geometry& a, bool fast_is_w, bool share, Plan& pl) 
   const int tiles_fast = ceil_div(out_fast, pl.FB);
   pl.S = (2 * N <= 256 && tiles_fast >= 2) ? 2 : 1;
   // cost model: per output pixel, max(tensor time, L2 feed time), divided by tile utilisation
-  const int cbe = a.Cin % 32 == 0 ? 32 : (a.Cin % 16 == 0 ? 16 : 8);
+  const int kpe = 32 / a.esz;   // K elements per MMA (32 operand bytes per row)
+  const int cbe = a.Cin % (4 * kpe) == 0 ? 4 * kpe : (a.Cin % (2 * kpe) == 0 ? 2 * kpe : kpe);
   const int n_chunks = (int)a.Cin / cbe;
-  const double mma = (double)nt * n_chunks * (cbe / 8) * pl.S * (128.0 * N / 256.0);
-  const double bytes = ((double)pl.groups.size() * pl.S * (pl.SB + pl.halo) * pl.FB + (double)nt * N) * cbe * 4.0 * n_chunks;
+  const double mma = (double)nt * n_chunks * (cbe / kpe) * pl.S * (128.0 * N / 256.0);
+  const double bytes = ((double)pl.groups.size() * pl.S * (pl.SB + pl.halo) * pl.FB + (double)nt * N) * cbe * (double)a.esz * n_chunks;
   const double t = std::max(mma, bytes / 40.0);
   const int lat_slow = out_slow / pl.g;
   const double util = ((double)lat_slow / (ceil_div(lat_slow, pl.SB) * pl.SB)) *

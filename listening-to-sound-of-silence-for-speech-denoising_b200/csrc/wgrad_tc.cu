@@ -52,7 +52,12 @@ struct alignas(64) WgParams {
   int x_box_bytes, x_box_stride, dy_chunk_bytes, dy_chunk_stride, x_off;
   int stage_bytes, n_stages;
   int layout_a, layout_b;
+  int kstep_bytes;                  // operand bytes of one k step: (8 | 16 pixels) x 128-byte rows
+  int row_bytes;                    // bytes of one slow row of a staged box (FB pixels x 128)
+  int m_half_chunks;                // channel chunks per 64 accumulator rows (stacked mode stages the shifted box there)
+  uint32_t desc_hi;                 // descriptor high word: SBO | version | layout
   uint32_t idesc;
+  const float* out_scale;           // optional device scalar multiplied into the sums
   float* dw;
   int16_t job_coblk[kMaxJobs], job_g0[kMaxJobs], job_ng[kMaxJobs], job_s0[kMaxJobs], job_ns[kMaxJobs];
   int16_t job_group[kMaxJobs * 4];   // tap groups whose x boxes a job stages (job_g0 = first index, job_ng = count)
@@ -70,11 +75,8 @@ __device__ __forceinline__ WgTile decode_wg_tile(const WgParams& p, int t) {
   return c;
 }
 
-__device__ __forceinline__ void umma_tf32_wg(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  umma_tf32(d_tmem, adesc, bdesc, idesc, accumulate);
-}
-
-__global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_constant__ WgParams p) {
+template <int KIND>
+__device__ __forceinline__ void wgrad_body(const WgParams& p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
                         tc.ts * p.SB, tc.ph, tc.n);
           if (p.stacked)
             for (int cc = 0; cc < n_co_chunks; ++cc)     // M chunks 2, 3: the same channels, `delta` pixels further along the fast axis
-              tma_load_5d(sbase + (uint32_t)(2 + cc) * p.dy_chunk_stride, &p.mapDY, full_bar(stage), cc * p.cbo, tc.tf * p.FB + p.delta,
+              tma_load_5d(sbase + (uint32_t)(p.m_half_chunks + cc) * p.dy_chunk_stride, &p.mapDY, full_bar(stage), cc * p.cbo, tc.tf * p.FB + p.delta,
                           tc.ts * p.SB, tc.ph, tc.n);
           for (int gi = 0; gi < ng; ++gi) {
             const TapGroup& grp = p.groups[p.job_group[g0 + gi]];
@@ -149,9 +151,8 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
     // ===================================================================== MMA issuer
     int stage = 0;
     uint32_t phase = 0, acc_phase = 0;
-    const uint32_t a_kstep = 8u * p.cbo * 4u, b_kstep = 8u * p.cbi * 4u;     // 8 pixels (one k step) of one chunk
-    const uint32_t a_inc = a_kstep >> 4, b_inc = b_kstep >> 4;
-    const uint32_t desc_hi = (512u >> 4) | (1u << 14) | (1u << 29);
+    const uint32_t a_inc = (uint32_t)p.kstep_bytes >> 4, b_inc = a_inc;        // one k step (8 or 16 pixels) of one chunk
+    const uint32_t desc_hi = p.desc_hi;
     const uint32_t x_lbo_bits = ((uint32_t)p.x_box_stride >> 4) << 16;
     const uint32_t idesc = p.idesc;
     const int ksteps = p.ksteps;
@@ -176,10 +177,10 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
             const uint32_t d = tmem_base + (uint32_t)i * p.N;
             const uint32_t xb = xbase + (uint32_t)sl.x_idx * p.n_ci_chunks * p.x_box_stride;
             uint32_t a_lo = a_lo0;
-            uint32_t b_lo = ((xb + (uint32_t)(sl.shift * p.shift_mul) * b_kstep) >> 4) | x_lbo_bits;
+            uint32_t b_lo = ((xb + (uint32_t)sl.shift * (uint32_t)p.row_bytes) >> 4) | x_lbo_bits;
 #pragma unroll 4
             for (int ks = 0; ks < ksteps; ++ks) {
-              umma_tf32_wg(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, first | (uint32_t)ks);
+              umma<KIND>(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, first | (uint32_t)ks);
               a_lo += a_inc;
               b_lo += b_inc;
             }
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
     // ===================================================================== drain (warps 2..5)
     const int q = warp & 3;
     uint32_t acc_phase = 0;
+    const float oscale = p.out_scale ? *p.out_scale : 1.f;
     for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
       const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
       const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
           if (co < p.Cout && tap >= 0) {
 #pragma unroll
             for (int k = 0; k < 16; ++k)
-              if (c0 + k < p.Cin) atomicAdd(dst + c0 + k, __uint_as_float(r[k]));
+              if (c0 + k < p.Cin) atomicAdd(dst + c0 + k, __uint_as_float(r[k]) * oscale);
           }
         }
       }
@@ -235,6 +237,9 @@ __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_
   }
 }
 
+__global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_constant__ WgParams p) { wgrad_body<0>(p); }
+__global__ void __launch_bounds__(kThreadsWg, 1) wgrad_f16_kernel(const __grid_constant__ WgParams p) { wgrad_body<1>(p); }
+
 }  // namespace
 
 extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
@@ -242,16 +247,20 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   const sos_wgrad_args& a = *ap;
   SOS_CHECK_ARG(a.x && a.dy && a.dw && a.tap_dh && a.tap_dw, "sos_conv2d_wgrad: null pointer");
   SOS_CHECK_ARG(a.N > 0 && a.H > 0 && a.W > 0 && a.OH > 0 && a.OW > 0 && a.ntaps > 0 && a.ntaps <= 49, "sos_conv2d_wgrad: bad shape");
+  SOS_CHECK_ARG(a.dtype == SOS_DTYPE_TF32 || a.dtype == SOS_DTYPE_F16, "sos_conv2d_wgrad: unknown operand type");
+  const int esz = a.dtype == SOS_DTYPE_F16 ? 2 : 4;
+  const int kpix = 32 / esz;                 // pixels (K) per MMA
+  const int cchunk = 128 / esz;              // channels per 128-byte row of a staged box
   SOS_CHECK_ARG(a.Cin >= 8 && a.Cin % 8 == 0 && a.Cin <= 256, "sos_conv2d_wgrad: Cin must be a multiple of 8 in [8, 256] (got %lld)",
                 (long long)a.Cin);
   SOS_CHECK_ARG(a.Cout >= 8 && a.Cout % 8 == 0 && a.Cout <= 1024, "sos_conv2d_wgrad: Cout must be a multiple of 8 in [8, 1024] (got %lld)",
                 (long long)a.Cout);
-  SOS_CHECK_ARG(a.Cdy % 4 == 0 && a.dy_coff % 4 == 0 && a.dy_coff + a.Cout <= a.Cdy, "sos_conv2d_wgrad: bad dy channel slice");
+  SOS_CHECK_ARG(a.Cdy % (16 / esz) == 0 && a.dy_coff % (16 / esz) == 0 && a.dy_coff + a.Cout <= a.Cdy, "sos_conv2d_wgrad: bad dy channel slice");
   SOS_CHECK_ARG(a.stride == 1 || a.stride == 2, "sos_conv2d_wgrad: stride must be 1 or 2");
   SOS_CHECK_ARG(((uintptr_t)a.x % 16) == 0 && ((uintptr_t)a.dy % 16) == 0, "sos_conv2d_wgrad: pointers must be 16-byte aligned");
 
   Geometry geo{(int)a.ntaps, a.tap_dh, a.tap_dw, (int)a.H, (int)a.W, (int)a.OH, (int)a.OW, (int)a.stride, (int)a.Cin, (int)a.Cout, true,
-               std::min(kMaxSub, 512 / round_up((int)a.Cin, 16)), true};
+               std::min(kMaxSub, 512 / round_up((int)a.Cin, 16)), true, esz};
   Plan best;
   for (int fw = 1; fw >= 0; --fw)
     for (int sh = 1; sh >= 0; --sh) {
@@ -273,15 +282,20 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   p.Cin = Cin;
   p.Cout = Cout;
   p.N = round_up(Cin, 16);
-  p.cbi = 32;
-  p.n_ci_chunks = ceil_div(Cin, 32);
-  p.cbo = 32;
+  p.cbi = cchunk;
+  p.n_ci_chunks = ceil_div(Cin, cchunk);
+  p.cbo = cchunk;
+  p.out_scale = a.out_scale;
   p.FB = pl.FB;                      // 8, or 16 for short dilation lattices (then SB <= 8)
-  const int fbm = pl.FB / 8;         // k steps (8 pixels) per slow row
   p.stride = (int)a.stride;
   p.dw = a.dw;
-  p.layout_a = p.layout_b = 1;
-  p.idesc = make_idesc_tf32(128, p.N, 1, 1);
+  // TF32: 128-byte swizzle with 32-byte atoms (4 k rows per atom, SBO 512); half: plain 128-byte swizzle (8 k rows, SBO 1024)
+  p.layout_a = p.layout_b = esz == 2 ? 2 : 1;
+  p.desc_hi = ((esz == 2 ? 1024u : 512u) >> 4) | (1u << 14) | ((uint32_t)p.layout_a << 29);
+  p.kstep_bytes = kpix * 128;
+  p.row_bytes = p.FB * 128;
+  p.m_half_chunks = 64 / cchunk;
+  p.idesc = esz == 2 ? make_idesc_f16(128, p.N, 1, 1) : make_idesc_tf32(128, p.N, 1, 1);
 
   // ---- jobs: tap groups packed into TMEM (512 columns) per output-channel block; at most kMaxJobGroups boxes per stage
   const int n_acc = 512 / p.N;
@@ -342,11 +356,11 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   // choose SB (pixels per tile = FB*SB) and groups per job so that at least 2 stages fit
   int SB = pl.SB, groups_per_job = 1;
   const int avail = kSmemLimit - 2048;
-  const int dy_chunks_staged = stacked ? 4 : n_co_chunks_max;
+  const int dy_chunks_staged = stacked ? 128 / cchunk : n_co_chunks_max;
   auto stage_bytes_for = [&](int sb, int ng, int* x_off_out, int* reach_out) {
-    const int dy_chunk = sb * p.FB * p.cbo * 4;
+    const int dy_chunk = sb * p.FB * 128;
     const int dy_stride = round_up(dy_chunk, 1024);
-    const int x_box = (sb + pl.halo) * p.FB * p.cbi * 4;
+    const int x_box = (sb + pl.halo) * p.FB * 128;
     const int x_stride = round_up(x_box, 1024);
     const int x_off = dy_chunks_staged * dy_stride;
     const int used = x_off + ng * p.n_ci_chunks * x_stride;
@@ -375,11 +389,12 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   int reach = 0;
   const int used = stage_bytes_for(SB, groups_per_job, &p.x_off, &reach);
   p.SB = SB;
-  p.dy_chunk_bytes = SB * p.FB * p.cbo * 4;
+  p.dy_chunk_bytes = SB * p.FB * 128;
   p.dy_chunk_stride = round_up(p.dy_chunk_bytes, 1024);
-  p.x_box_bytes = (SB + pl.halo) * p.FB * p.cbi * 4;
-  p.ksteps = SB * fbm;
-  p.shift_mul = fbm;
+  p.x_box_bytes = (SB + pl.halo) * p.FB * 128;
+  SOS_CHECK_ARG((SB * p.FB) % kpix == 0, "sos_conv2d_wgrad: tile of %d x %d pixels is not a multiple of the k step", SB, p.FB);
+  p.ksteps = SB * p.FB / kpix;
+  p.shift_mul = p.FB / 8;
   p.x_box_stride = round_up(p.x_box_bytes, 1024);
   p.stage_bytes = used;
   const int tail = std::max(0, reach - used);
@@ -419,27 +434,29 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   const bool fw = pl.fast_is_w;
   const int g = pl.g;
   {
-    const uint64_t pix = (uint64_t)Cin * 4;
+    const uint64_t pix = (uint64_t)Cin * esz;
     const uint64_t in_fast = fw ? a.W : a.H, in_slow = fw ? a.H : a.W;
     const uint64_t s_fast = fw ? pix : pix * a.W, s_slow = fw ? pix * a.W : pix;
     uint64_t dims[5] = {(uint64_t)Cin, in_fast, in_slow / g, (uint64_t)g, (uint64_t)a.N};
-    uint64_t str[5] = {4, s_fast, s_slow * g, s_slow, pix * a.H * a.W};
+    uint64_t str[5] = {(uint64_t)esz, s_fast, s_slow * g, s_slow, pix * a.H * a.W};
     uint32_t box[5] = {(uint32_t)p.cbi, (uint32_t)(p.FB * a.stride), (uint32_t)((SB + pl.halo) * a.stride), 1, 1};
     uint32_t es[5] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1, 1};
     SOS_CHECK_ARG(box[2] <= 256, "sos_conv2d_wgrad: activation box too large");
-    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    if (int e = encode_map(&p.mapX, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, a.x, dims, str, box, es, sw, "wgrad activations")) return e;
+    const CUtensorMapSwizzle sw = esz == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (int e = encode_map(&p.mapX, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, a.x, dims, str, box, es, sw,
+                           "wgrad activations")) return e;
   }
   const int out_fast = fw ? (int)a.OW : (int)a.OH, out_slow = fw ? (int)a.OH : (int)a.OW;
   {
-    const uint64_t pix = (uint64_t)a.Cdy * 4;
+    const uint64_t pix = (uint64_t)a.Cdy * esz;
     const uint64_t s_fast = fw ? pix : pix * a.OW, s_slow = fw ? pix * a.OW : pix;
     uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)out_fast, (uint64_t)(out_slow / g), (uint64_t)g, (uint64_t)a.N};
-    uint64_t str[5] = {4, s_fast, s_slow * g, s_slow, pix * a.OH * a.OW};
+    uint64_t str[5] = {(uint64_t)esz, s_fast, s_slow * g, s_slow, pix * a.OH * a.OW};
     uint32_t box[5] = {(uint32_t)p.cbo, (uint32_t)p.FB, (uint32_t)SB, 1, 1};
     uint32_t es[5] = {1, 1, 1, 1, 1};
-    const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    if (int e = encode_map(&p.mapDY, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, a.dy + a.dy_coff, dims, str, box, es, sw, "wgrad output grads"))
+    const CUtensorMapSwizzle sw = esz == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (int e = encode_map(&p.mapDY, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5,
+                           reinterpret_cast<const uint8_t*>(a.dy) + a.dy_coff * esz, dims, str, box, es, sw, "wgrad output grads"))
       return e;
   }
   p.tiles_fast = ceil_div(out_fast, p.FB) + p.tf_extra;
@@ -456,14 +473,16 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   const int smem = 2048 + p.n_stages * p.stage_bytes + tail;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess) {
+    if (cudaFuncSetAttribute(wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess ||
+        cudaFuncSetAttribute(wgrad_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess) {
       sos_set_error("sos_conv2d_wgrad: cannot raise dynamic shared memory: %s", cudaGetErrorString(cudaGetLastError()));
       return SOS_ERR_CUDA;
     }
     attr_set = true;
   }
   const int grid = std::min(p.n_jobs * p.n_slices, sms);
-  wgrad_tf32_kernel<<<grid, kThreadsWg, smem, stream>>>(p);
+  if (esz == 2) wgrad_f16_kernel<<<grid, kThreadsWg, smem, stream>>>(p);
+  else wgrad_tf32_kernel<<<grid, kThreadsWg, smem, stream>>>(p);
   SOS_CHECK_LAUNCH("sos_conv2d_wgrad");
   if (a.plan_out) {
     a.plan_out[0] = pl.fast_is_w;

@@ -35,6 +35,22 @@ def precise():
     return _PRECISE
 
 
+# Operand storage of the default (one-pass) mode: IEEE half (True; tcgen05 kind::f16 -- the same 11-bit significand as TF32 at
+# half the bytes and twice the tensor rate; gradient operands carry a per-tensor power-of-two scale) or TF32 in fp32 storage
+# (False; kind::tf32, the first implementation, kept for A/B measurements).  Precise mode always runs on the TF32 kernels.
+_HALF = True
+
+
+def set_half(flag):
+    global _HALF
+    old, _HALF = _HALF, bool(flag)
+    return old
+
+
+def half_mode():
+    return _HALF and not _PRECISE
+
+
 # Weight gradients are off the backward critical path (only the optimiser needs them): inside `async_wgrad()` TapConv.backward
 # enqueues them on a side stream and adds them straight into the parameter's .grad (a view of the agent's flat gradient buffer),
 # so the tensor-bound wgrad kernels overlap the HBM-bound BatchNorm passes of the following layers.  The caller joins the
@@ -100,34 +116,39 @@ class ConvGeom:
         return 2 * H, 2 * W
 
 
-def _pack_fwd(w, taps, cin_p):
-    """(Cout, Cin, kh, kw) view -> (Cout, len(taps)*cin_p), k = t*cin_p + ci, TF32-rounded (one gather kernel)."""
+def _pack_fwd(w, taps, cin_p, half=False):
+    """(Cout, Cin, kh, kw) view -> (Cout, len(taps)*cin_p), k = t*cin_p + ci, TF32-rounded fp32 or half (one gather kernel)."""
+    if half:
+        return ops.pack_taps_half(w.detach(), taps, cin_p)
     return ops.pack_taps(w.detach(), taps, cin_p, round_tf32=True)
 
 
-def _conv_forward(x, w, g, epi=None, want_stats=False):
+def _conv_forward(x, w, g, epi=None, want_stats=False, y_half=False, y_out=None):
     """x NHWC (N,H,W,Cin_p); w PyTorch layout.  Returns y NHWC (N,OH,OW,round8(Cout)); with want_stats also the BatchNorm
     partial sums (G, 2, C) of y computed by the epilogue (the four sub-pixel launches of a transposed conv stack theirs)."""
     N, H, W, cin_p = x.shape
     OH, OW = g.out_size(H, W)
     kw = dict(epi_scale=epi[0], epi_shift=epi[1], act=epi[2], slope=epi[3]) if epi else {}
+    half = x.dtype == torch.float16
+    kw["y_half"] = y_half
     if g.kind != "convT":
         Cout = w.shape[0]
-        wk = _pack_fwd(w, g.taps, cin_p)
+        wk = _pack_fwd(w, g.taps, cin_p, half)
         return ops.conv_tc(x, wk, [o[0] for o in g.off], [o[1] for o in g.off], Cout, OH, OW, g.stride, k_real=w.shape[1],
-                           want_stats=want_stats, **kw)
+                           want_stats=want_stats, y=y_out, **kw)
     # ConvTranspose2d(k3, s2, p1, output_padding=1): oy = 2*iy - 1 + ky  ->  four sub-pixel convolutions
     Cout = w.shape[1]
     wc = w.permute(1, 0, 2, 3)                                             # (Cout, Cin, ky, kx)
     Cy = _round8(Cout)
-    y = (torch.zeros if Cy != Cout else torch.empty)(N, OH, OW, Cy, device=x.device, dtype=torch.float32)
+    y = y_out if y_out is not None else (torch.zeros if Cy != Cout else torch.empty)(N, OH, OW, Cy, device=x.device,
+                                                                                     dtype=torch.float16 if y_half else torch.float32)
     ph_taps = {0: [(1, 0)], 1: [(0, 1), (2, 0)]}                          # phase -> [(k, input offset)]
     parts = []
     for py in (0, 1):
         for px in (0, 1):
             taps = [(ky, kx) for ky, _ in ph_taps[py] for kx, _ in ph_taps[px]]
             offs = [(oy, ox) for _, oy in ph_taps[py] for _, ox in ph_taps[px]]
-            wk = _pack_fwd(wc, taps, cin_p)
+            wk = _pack_fwd(wc, taps, cin_p, half)
             r = ops.conv_tc(x, wk, [o[0] for o in offs], [o[1] for o in offs], Cout, H, W, 1, y=y, lattice=(2, 2, py, px), k_real=w.shape[0],
                             want_stats=want_stats, **kw)
             if want_stats:
@@ -135,20 +156,31 @@ def _conv_forward(x, w, g, epi=None, want_stats=False):
     return (y, torch.cat(parts)) if want_stats else y
 
 
-def _conv_dgrad(dy, w, g, x_shape):
-    """Gradient w.r.t. the (possibly reflect-padded) NHWC input buffer."""
+def _conv_dgrad(dy, w, g, x_shape, out_scale=None):
+    dx = _conv_dgrad_raw(dy, w, g, x_shape, out_scale)
+    if dx.shape[3] != x_shape[3]:                        # x carries more zero channels than round8(Cin) (2 -> 16 in half mode)
+        dx = torch.nn.functional.pad(dx, (0, x_shape[3] - dx.shape[3]))
+    return dx
+
+
+def _conv_dgrad_raw(dy, w, g, x_shape, out_scale=None):
+    """Gradient w.r.t. the (possibly reflect-padded) NHWC input buffer (fp32).  dy: fp32 (TF32) or half with its inverse
+    scale `out_scale`."""
     N, H, W, cin_p = x_shape
     cout_p = dy.shape[3]
+    half = dy.dtype == torch.float16
     if g.kind == "convT":
         # dx[iy] = sum_k dy[2*iy - 1 + ky] w[ci][co][ky]: a stride-2 tap conv over dy
         Cin = w.shape[0]
-        wk = _pack_fwd(w, g.taps, cout_p)                                  # rows ci, k = t*cout_p + co
-        return ops.conv_tc(dy, wk, [o[0] for o in g.off], [o[1] for o in g.off], Cin, H, W, 2, k_real=w.shape[1], tag="conv_dgrad")
+        wk = _pack_fwd(w, g.taps, cout_p, half)                            # rows ci, k = t*cout_p + co
+        return ops.conv_tc(dy, wk, [o[0] for o in g.off], [o[1] for o in g.off], Cin, H, W, 2, k_real=w.shape[1], tag="conv_dgrad",
+                           out_scale=out_scale)
     Cin = w.shape[1]
     wt = w.permute(1, 0, 2, 3)                                             # (Cin, Cout, kh, kw)
     if g.stride == 1:
-        wk = _pack_fwd(wt, g.taps, cout_p)
-        return ops.conv_tc(dy, wk, [-o[0] for o in g.off], [-o[1] for o in g.off], Cin, H, W, 1, k_real=w.shape[0], tag="conv_dgrad")
+        wk = _pack_fwd(wt, g.taps, cout_p, half)
+        return ops.conv_tc(dy, wk, [-o[0] for o in g.off], [-o[1] for o in g.off], Cin, H, W, 1, k_real=w.shape[0], tag="conv_dgrad",
+                           out_scale=out_scale)
     # stride 2: four output phases of the input lattice
     dx = torch.empty(N, H, W, _round8(Cin), device=dy.device, dtype=torch.float32)
     assert _round8(Cin) == Cin
@@ -159,23 +191,25 @@ def _conv_dgrad(dy, w, g, x_shape):
             if not sel:
                 dx[:, py::2, px::2].zero_()
                 continue
-            wk = _pack_fwd(wt, [t for t, _ in sel], cout_p)
+            wk = _pack_fwd(wt, [t for t, _ in sel], cout_p, half)
             ops.conv_tc(dy, wk, [(py - o[0]) // 2 for _, o in sel], [(px - o[1]) // 2 for _, o in sel], Cin, oh, ow, 1, y=dx,
-                        lattice=(2, 2, py, px), k_real=w.shape[0], tag="conv_dgrad")
+                        lattice=(2, 2, py, px), k_real=w.shape[0], tag="conv_dgrad", out_scale=out_scale)
     return dx
 
 
-def _conv_wgrad(x, dy, w, g):
+def _conv_wgrad(x, dy, w, g, out_scale=None):
     """Returns the gradient in w's own layout."""
     if g.kind == "convT":
         Cin, Cout = w.shape[0], w.shape[1]
         # roles swapped: "input" = dy (2H x 2W), "output grad" = x (H x W), stride 2
-        dwt = ops.conv_wgrad(dy, x, [o[0] for o in g.off], [o[1] for o in g.off], x.shape[3], x.shape[1], x.shape[2], 2, real=(Cout, Cin))
+        dwt = ops.conv_wgrad(dy, x, [o[0] for o in g.off], [o[1] for o in g.off], x.shape[3], x.shape[1], x.shape[2], 2, real=(Cout, Cin),
+                             out_scale=out_scale)
         # dwt (ntaps, Cin_p, Cout_p) -> (Cin, Cout, kh, kw)
         return dwt[:, :Cin, :Cout].permute(1, 2, 0).reshape(Cin, Cout, g.kh, g.kw).contiguous()
     Cout, Cin = w.shape[0], w.shape[1]
     OH, OW = dy.shape[1], dy.shape[2]
-    dwt = ops.conv_wgrad(x, dy, [o[0] for o in g.off], [o[1] for o in g.off], dy.shape[3], OH, OW, g.stride, real=(Cin, Cout))
+    dwt = ops.conv_wgrad(x, dy, [o[0] for o in g.off], [o[1] for o in g.off], dy.shape[3], OH, OW, g.stride, real=(Cin, Cout),
+                         out_scale=out_scale)
     return dwt[:, :Cout, :Cin].permute(1, 2, 0).reshape(Cout, Cin, g.kh, g.kw).contiguous()
 
 
@@ -227,8 +261,114 @@ class TapConv(torch.autograd.Function):
 
 
 def conv_fused_eval(x, w, g, scale, shift, act, slope, round_out=True):
-    """Inference path: BN (running stats) + activation folded into the GEMM epilogue."""
+    """Inference path: BN (running stats) + activation folded into the GEMM epilogue.  Half mode: x is a half-map handle and
+    the epilogue stores half (round_out) or fp32 (the map feeds the LSTM projection)."""
+    if ops.is_half_handle(x):
+        if not round_out:
+            return _conv_forward(ops.hv(x), w, g, epi=(scale, shift, act, slope))
+        Cout = w.shape[1] if g.kind == "convT" else w.shape[0]
+        assert Cout % 8 == 0
+        OH, OW = g.out_size(x.shape[1], x.shape[2])
+        z = ops.new_half((x.shape[0], OH, OW, Cout), x.device)
+        _conv_forward(ops.hv(x), w, g, epi=(scale, shift, act, slope), y_half=True, y_out=ops.hv(z))
+        return z
     return _conv_forward(x, w, g, epi=(scale, shift, act | (ops.ACT_ROUND_TF32 if round_out else 0), slope))
+
+
+def _wgrad_into(w, x, dy, g, out_scale):
+    """Weight gradient: on the side stream straight into w.grad inside async_wgrad(), else returned."""
+    if _ASYNC_WGRAD and w.grad is not None:
+        side, main = _side_stream(), torch.cuda.current_stream()
+        side.wait_stream(main)                                     # x, dy, the scale (and the zeroed .grad) are ready
+        with torch.cuda.stream(side):
+            w.grad.add_(_conv_wgrad(x, dy, w, g, out_scale))
+        x.record_stream(side)
+        dy.record_stream(side)
+        if out_scale is not None:
+            out_scale.record_stream(side)
+        return None
+    return _conv_wgrad(x, dy, w, g, out_scale)
+
+
+class ConvBNActH(torch.autograd.Function):
+    """Training-mode conv -> BatchNorm (batch statistics from the GEMM epilogue) -> ReLU / PReLU over HALF maps, as ONE autograd
+    node: the gradient w.r.t. the conv output is a scaled half operand that never leaves this node.
+    x: half-map handle; returns a half-map handle (or a dense fp32 map with out_f32)."""
+
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, slope, running_mean, running_var, eps, momentum, act, g, out_f32):
+        xh = ops.hv(x)
+        y, partial = _conv_forward(xh, w, g, want_stats=True)
+        Cp, Cn = y.shape[3], gamma.numel()
+        gm, bt, rm, rv = gamma.detach(), beta.detach(), running_mean, running_var
+        if Cp != Cn:                                                      # padded channels: gamma = beta = 0 -> z = 0
+            pad = (0, Cp - Cn)
+            gm, bt, rm = (torch.nn.functional.pad(t, pad) for t in (gm, bt, rm))
+            rv = torch.nn.functional.pad(rv, pad, value=1.0)
+        stats = ops.bn_finalize_partial(partial, y.numel() // Cp, gm.contiguous(), bt.contiguous(), rm, rv, eps, momentum)
+        if Cp != Cn:
+            running_mean.copy_(rm[:Cn])
+            running_var.copy_(rv[:Cn])
+        z = ops.bn_act_apply(y, stats, act, slope, half=not out_f32)
+        ctx.g, ctx.act, ctx.Cn = g, act, Cn
+        ctx.save_for_backward(x, w, y, stats, slope if slope is not None else torch.empty(0))
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, w, y, stats, slope = ctx.saved_tensors
+        slope = slope if slope.numel() else None
+        g, Cn = ctx.g, ctx.Cn
+        dy, dgamma, dbeta, dslope, scal = ops.bn_train_backward_half(dz.contiguous(), y, stats, ctx.act, slope)
+        inv = scal[1:2]
+        xh = ops.hv(x)
+        dw = _wgrad_into(w, xh, dy, g, inv) if ctx.needs_input_grad[1] else None
+        dx = _conv_dgrad(dy, w, g, xh.shape, inv) if ctx.needs_input_grad[0] else None
+        return dx, dw, dgamma[:Cn], dbeta[:Cn], dslope, None, None, None, None, None, None, None
+
+
+class TapConvH(torch.autograd.Function):
+    """Convolution of a half map with an fp32 output and no normalisation after it (the last InpaintNet layer, and the
+    eval-with-autograd path): forward(x handle, w, geometry) -> y fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w, g):
+        ctx.g = g
+        ctx.save_for_backward(x, w)
+        return _conv_forward(ops.hv(x), w, g)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        g = ctx.g
+        dyh, scal = ops.to_half(dy.contiguous(), scaled=True)
+        inv = scal[1:2]
+        xh = ops.hv(x)
+        dw = _wgrad_into(w, xh, dyh, g, inv) if ctx.needs_input_grad[1] else None
+        dx = _conv_dgrad(dyh, w, g, xh.shape, inv) if ctx.needs_input_grad[0] else None
+        return dx, dw, None
+
+
+class ToHalf(torch.autograd.Function):
+    """fp32 NHWC map -> half-map handle with the channels zero-padded to `cd` (straight-through gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, cd):
+        ctx.cs = x.shape[3]
+        z = ops.new_half((*x.shape[:3], cd), x.device)
+        ops.to_half(x.detach().contiguous(), cd, out=ops.hv(z))
+        return z
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g if g.shape[3] == ctx.cs else g[..., :ctx.cs].contiguous()), None
+
+
+def to_operand(x, cd=None):
+    """Marks an fp32 NHWC map produced by a plain tensor expression as the input of a tensor-core GEMM."""
+    if half_mode():
+        return ToHalf.apply(x, cd or (x.shape[3] + 15) // 16 * 16)
+    return RoundTF32.apply(x)
 
 
 class RoundTF32(torch.autograd.Function):
@@ -292,7 +432,7 @@ def bn_act(y, bn, act, slope, training, round_out=True, round_grad=True, conv_pa
         pre = torch.relu(pre)
     elif act == ops.ACT_PRELU:
         pre = torch.where(pre > 0, pre, pre * slope)
-    return RoundTF32.apply(pre) if round_out else pre
+    return to_operand(pre) if round_out else pre
 
 
 # ----------------------------------------------------------------------------------------------- pad + concat
@@ -337,6 +477,32 @@ class PadCat(torch.autograd.Function):
                 ops.copy_view_backward(g, dv, gs, ops.view8(Hs, Ws, ld=Cs), N, Cs)
             grads.append(gs)
         return (None, None, None, *grads)
+
+
+class PadCatH(torch.autograd.Function):
+    """PadCat over half-map handles: the copies move 16-byte pixel groups, so they run on the fp32-pair view of the same bytes
+    (channel counts halved); gradients are ordinary fp32 maps."""
+
+    @staticmethod
+    def forward(ctx, pad, H, W, *srcs):
+        N = srcs[0].shape[0]
+        Ct = sum(s.shape[3] for s in srcs)
+        buf = ops.new_half((N, H + 2 * pad, W + 2 * pad, Ct), srcs[0].device)
+        bf = ops.fv(buf)
+        coff = 0
+        meta = []
+        for s in srcs:
+            _, Hs, Ws, Cs = s.shape
+            ops.copy_view(ops.fv(s), ops.view8(Hs, Ws, ld=Cs // 2), bf, ops.view8(H, W, H + 2 * pad, W + 2 * pad, pad, pad, Ct // 2, coff // 2),
+                          N, Cs // 2)
+            meta.append((Hs, Ws, Cs, coff))
+            coff += Cs
+        if pad:
+            ops.reflect_fill(bf, H, W, pad)
+        ctx.meta, ctx.pad, ctx.H, ctx.W, ctx.N, ctx.Ct = meta, pad, H, W, N, Ct
+        return buf
+
+    backward = staticmethod(PadCat.backward)
 
 
 # ----------------------------------------------------------------------------------------------- layout changes

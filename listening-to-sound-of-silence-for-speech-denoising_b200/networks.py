@@ -32,8 +32,9 @@ class _Block(nn.Module):
 
     def _run(self, x, conv, bn, act, slope_mod, geom):
         slope = slope_mod.weight if slope_mod is not None else None
+        half = ops.is_half_handle(x)                                     # half-map handle (default mode) or fp32 / TF32 map
         if bn is None:                                                   # last InpaintNet conv: bias, no norm, no act
-            y = L.TapConv.apply(x, conv.weight, geom)
+            y = (L.TapConvH if half else L.TapConv).apply(x, conv.weight, geom)
             Cp, Cn = y.shape[3], conv.out_channels
             b = conv.bias if Cp == Cn else torch.nn.functional.pad(conv.bias, (0, Cp - Cn))
             return y + b
@@ -47,10 +48,16 @@ class _Block(nn.Module):
             scale, shift = ops.bn_eval_coeffs(gamma.detach().contiguous(), beta.detach().contiguous(), rm.contiguous(), rv.contiguous(), bn.eps)
             return L.conv_fused_eval(x, conv.weight.detach(), geom, scale, shift, act, slope.detach() if slope is not None else None,
                                      self.round_out)
+        if self.training and half:                                       # conv + batch-stat BN + activation as one autograd node
+            z = L.ConvBNActH.apply(x, conv.weight, bn.weight, bn.bias, slope, bn.running_mean, bn.running_var, bn.eps, bn.momentum,
+                                   act, geom, not self.round_out)
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
+            return z
         if self.training:                                                # batch statistics come out of the conv epilogue
             y, partial = L.TapConv.apply(x, conv.weight, geom, True)
             return L.bn_act(y, bn, act, slope, True, self.round_out, conv_partial=partial)
-        y = L.TapConv.apply(x, conv.weight, geom)
+        y = (L.TapConvH if half else L.TapConv).apply(x, conv.weight, geom)
         return L.bn_act(y, bn, act, slope, False, self.round_out)
 
 
@@ -92,7 +99,7 @@ class DownConvBlock(_Block):
         H, W = size if size is not None else (srcs[0].shape[1], srcs[0].shape[2])
         if self.pad >= min(H, W):
             raise RuntimeError(f"ReflectionPad2d({self.pad}) needs an input larger than the padding, got {H}x{W}")
-        xp = L.PadCat.apply(self.pad, H, W, *srcs)
+        xp = (L.PadCatH if ops.is_half_handle(srcs[0]) else L.PadCat).apply(self.pad, H, W, *srcs)
         if self.has_norm:
             return self._run(xp, self.block[1], self.block[2], ops.ACT_PRELU, self.block[3], self.geom)
         return self._run(xp, self.block[1], None, ops.ACT_NONE, None, self.geom)
@@ -115,7 +122,13 @@ class UpConvBlock(_Block):
 
 
 def _to_nhwc(x):
-    """(B, 2, 256, T) NCHW -> NHWC with channels zero-padded to 8."""
+    """(B, 2, 256, T) NCHW -> NHWC operand of the first convolutions: a half map with 16 channels (one K = 16 MMA step) in the
+    default mode, else fp32 with channels zero-padded to 8 (TF32-rounded unless precise)."""
+    if L.half_mode():
+        y = ops.nchw_to_nhwc(x.contiguous().float(), 16)
+        z = ops.new_half(y.shape, y.device)
+        ops.to_half(y, 16, out=ops.hv(z))
+        return z
     y = ops.nchw_to_nhwc(x.contiguous().float(), 8)
     return y if L.precise() else ops.round_tf32_(y)
 
@@ -241,7 +254,7 @@ class JointModel(nn.Module):
     def forward(self, x, n):
         xh, nh = _nhwc_in(x), _nhwc_in(n)
         n_pred_nhwc = self.stage1.forward_nhwc(nh, xh)
-        out = self.stage2.forward_nhwc(xh, L.RoundTF32.apply(n_pred_nhwc))
+        out = self.stage2.forward_nhwc(xh, L.to_operand(n_pred_nhwc))
         return L.ToNCHW.apply(n_pred_nhwc, 2), out
 
 

@@ -20,7 +20,7 @@ def _stream():
 def _p(t):
     if t is None:
         return None
-    assert t.is_cuda and t.dtype in (torch.float32, torch.uint8, torch.int32), (t.device, t.dtype)
+    assert t.is_cuda and t.dtype in (torch.float32, torch.float16, torch.uint8, torch.int32), (t.device, t.dtype)
     assert t.is_contiguous(), "sos_b200 ops need contiguous tensors"
     return C.c_void_p(t.data_ptr())
 
@@ -80,6 +80,48 @@ def view8(H, W, Hp=None, Wp=None, ph=0, pw=0, ld=0, coff=0):
     Hp = H if Hp is None else Hp
     Wp = W if Wp is None else Wp
     return (_I32 * 8)(H, W, Hp, Wp, ph, pw, ld, coff)
+
+
+# ----------------------------------------------------------------------------------------------- half-precision maps
+# Activations between the tensor-core GEMMs are IEEE half NHWC arrays (same 11-bit significand as TF32, half the bytes, twice the
+# MMA rate).  Autograd would cast a gradient to the dtype of the tensor it belongs to, and the gradients of these maps must stay
+# fp32, so a half map travels through the graph behind an fp32-typed HANDLE of the same logical shape (N, H, W, C): strides
+# (HWC/2, WC/2, C/2, 1) over a storage of N*H*W*C/2 + C/2 floats, i.e. exactly the half array's bytes.  Only the kernels below
+# touch its memory, through `hv` (the real contiguous half tensor) or `fv` (the same bytes as fp32 pairs, for the copy kernels).
+def new_half(shape, device):
+    N, H, W, Cn = shape
+    assert Cn % 8 == 0, "half maps need a multiple of 8 channels (16-byte pixels)"
+    store = torch.empty(N * H * W * Cn // 2 + Cn // 2, device=device, dtype=torch.float32)
+    return store.as_strided((N, H, W, Cn), (H * W * Cn // 2, W * Cn // 2, Cn // 2, 1))
+
+
+def is_half_handle(t):
+    return t.dtype == torch.float32 and t.dim() == 4 and t.shape[3] > 1 and t.stride(3) == 1 and t.stride(2) * 2 == t.shape[3]
+
+
+def hv(h):
+    assert is_half_handle(h), "expected a half-map handle (ops.new_half)"
+    return torch.empty(0, device=h.device, dtype=torch.float16).set_(h.untyped_storage(), h.storage_offset() * 2, tuple(h.shape))
+
+
+def fv(h):
+    assert is_half_handle(h), "expected a half-map handle (ops.new_half)"
+    N, H, W, Cn = h.shape
+    return torch.empty(0, device=h.device, dtype=torch.float32).set_(h.untyped_storage(), h.storage_offset(), (N, H, W, Cn // 2))
+
+
+def to_half(x, cd=None, scaled=False, out=None):
+    """x (..., cs) fp32 -> real half tensor (..., cd) zero-padded; scaled: multiplied by the power of two that brings the RMS
+    to ~1, returned as scal = [s, 1/s, sum x^2] (device floats; scal[1:2] is the out_scale of the consuming GEMMs)."""
+    cs = x.shape[-1]
+    cd = cs if cd is None else cd
+    rows = x.numel() // cs
+    if out is None:
+        out = torch.empty(*x.shape[:-1], cd, device=x.device, dtype=torch.float16)
+    scal = torch.zeros(3, device=x.device, dtype=torch.float32) if scaled else None
+    check(lib().sos_to_half(_p(x), rows, cs, _p(out), cd, _p(scal), _stream()), "sos_to_half")
+    _count(2 if scaled else 1)
+    return (out, scal) if scaled else out
 
 
 # ----------------------------------------------------------------------------------------------- transforms
@@ -217,6 +259,52 @@ def bn_train_forward(y, gamma, beta, running_mean, running_var, eps, momentum, a
     return z, stats
 
 
+def bn_finalize_partial(conv_partial, rows, gamma, beta, running_mean, running_var, eps, momentum):
+    """Batch statistics from the convolution epilogue's partial sums (G, 2, C) -> stats (4, C) = mean, invstd, scale, shift."""
+    Cn = gamma.numel()
+    assert conv_partial.shape[1:] == (2, Cn) and conv_partial.is_contiguous()
+    stats = torch.empty(4, Cn, device=gamma.device, dtype=torch.float32)
+    sp = [C.c_void_p(stats[i].data_ptr()) for i in range(4)]
+    check(lib().sos_bn_finalize_partial(_p(conv_partial), conv_partial.shape[0], rows, Cn, _p(gamma), _p(beta), eps, momentum,
+                                        _p(running_mean), _p(running_var), sp[0], sp[1], sp[2], sp[3], _stream()), "sos_bn_finalize_partial")
+    _count()
+    return stats
+
+
+def bn_act_apply(y, stats, act, slope, half):
+    """z = act(y * scale + shift) with the finalized stats: a half-map handle (half=True) or a dense fp32 map."""
+    Cn = y.shape[-1]
+    rows = y.numel() // Cn
+    sc, sh = C.c_void_p(stats[2].data_ptr()), C.c_void_p(stats[3].data_ptr())
+    if half:
+        z = new_half(y.shape, y.device)
+        check(lib().sos_bn_act_half(_p(y), _p(hv(z)), rows, Cn, sc, sh, act & 15, _p(slope), _stream()), "sos_bn_act_half")
+    else:
+        z = torch.empty_like(y)
+        check(lib().sos_bn_act(_p(y), _p(z), view8(y.shape[-3], y.shape[-2], ld=Cn), rows, Cn, sc, sh, act & 15, _p(slope), _stream()), "sos_bn_act")
+    _count()
+    return z
+
+
+def bn_train_backward_half(dz, y, stats, act, slope):
+    """BatchNorm + activation backward with the gradient w.r.t. the conv output written as a scaled half operand.
+    -> dy (real half tensor), dgamma, dbeta, dslope, scal [s, 1/s, sum dy^2]."""
+    Cn = y.shape[-1]
+    rows = y.numel() // Cn
+    G = lib().sos_bn_partial_blocks(rows, Cn)
+    partial = torch.empty(G * 4 * Cn, device=y.device, dtype=torch.float32)
+    dy = torch.empty(y.shape, device=y.device, dtype=torch.float16)
+    out = torch.empty(4, Cn, device=y.device, dtype=torch.float32)             # dgamma, dbeta, m1, m2
+    dslope = torch.zeros(1, device=y.device, dtype=torch.float32) if (act & 15) == ACT_PRELU else None
+    scal = torch.zeros(3, device=y.device, dtype=torch.float32)
+    sp = lambda i: C.c_void_p(stats[i].data_ptr())
+    op = lambda i: C.c_void_p(out[i].data_ptr())
+    check(lib().sos_bn_act_backward_half(_p(dz), _p(y), _p(dy), rows, Cn, sp(2), sp(3), sp(0), sp(1), act & 15, _p(slope), _p(partial),
+                                         op(0), op(1), _p(dslope), op(2), op(3), _p(scal), _stream()), "sos_bn_act_backward_half")
+    _count(3)
+    return dy, out[0], out[1], dslope, scal
+
+
 def bn_train_backward(dz, y, stats, act, slope):
     Cn = y.shape[-1]
     rows = y.numel() // Cn
@@ -318,12 +406,26 @@ def pack_taps(w, taps, k_padded, round_tf32=True):
     return out
 
 
+def pack_taps_half(w, taps, k_padded):
+    """pack_taps with a half output (operand of the kind::f16 GEMMs)."""
+    assert w.dim() == 4 and w.is_cuda and w.dtype == torch.float32
+    R, K = w.shape[0], w.shape[1]
+    st = w.stride()
+    out = torch.empty(R, len(taps) * k_padded, device=w.device, dtype=torch.float16)
+    offs = _i32arr([a * st[2] + b * st[3] for a, b in taps])
+    check(lib().sos_pack_taps_half(C.c_void_p(w.data_ptr()), R, K, k_padded, st[0], st[1], len(taps), offs, _p(out), _stream()),
+          "sos_pack_taps_half")
+    _count()
+    return out
+
+
 def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lattice=(1, 1, 0, 0), epi_scale=None, epi_shift=None,
-            act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag="conv_fwd", want_stats=False):
+            act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag="conv_fwd", want_stats=False, y_half=False, out_scale=None):
     """Tap-list implicit GEMM on tcgen05 (see include/sos_b200.h: sos_conv2d_tc).
 
     x (N, H, W, Cin) NHWC; wk (Cout, ntaps*Cin); y (N, YH, YW, Cy) is allocated when None (dense, Cy = Cout
-    rounded up to 8, zero filled if padded)."""
+    rounded up to 8, zero filled if padded).  x and wk are both fp32 (read as TF32) or both half (kind::f16); y is fp32, or a
+    real half tensor with y_half.  out_scale: device scalar multiplied into the outputs."""
     N, H, W, Cin = x.shape
     ntaps = len(tap_dh)
     assert wk.shape == (Cout, ntaps * Cin), (wk.shape, Cout, ntaps, Cin)
@@ -331,8 +433,12 @@ def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lat
         Cy = (Cout + 7) // 8 * 8
         osh, osw, _, _ = lattice
         alloc = torch.zeros if (Cy != Cout) else torch.empty
-        y = alloc(N, OH * osh, OW * osw, Cy, device=x.device, dtype=torch.float32)
+        y = alloc(N, OH * osh, OW * osw, Cy, device=x.device, dtype=torch.float16 if y_half else torch.float32)
+    assert x.dtype == wk.dtype and x.dtype in (torch.float32, torch.float16)
     a = ConvArgs()
+    a.x_dtype = 1 if x.dtype == torch.float16 else 0
+    a.y_dtype = 1 if y.dtype == torch.float16 else 0
+    a.out_scale = out_scale.data_ptr() if out_scale is not None else None
     a.x, a.wk, a.y = x.data_ptr(), wk.data_ptr(), y.data_ptr()
     dh, dw = _i32arr(tap_dh), _i32arr(tap_dw)
     a.tap_dh, a.tap_dw = dh, dw
@@ -365,13 +471,16 @@ def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lat
     return y
 
 
-def conv_wgrad(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_plan=-1, plan_out=None, real=None):
+def conv_wgrad(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_plan=-1, plan_out=None, real=None, out_scale=None):
     """dw[t][co][ci] = sum_pixels dy[p][dy_coff+co] * x[p*stride + off_t][ci]  ->  (ntaps, Cout, Cin)."""
     N, H, W, Cin = x.shape
     ntaps = len(tap_dh)
     assert dy.shape[0] == N and dy.shape[1] == OH and dy.shape[2] == OW, (dy.shape, N, OH, OW)
     dw = torch.zeros(ntaps, Cout, Cin, device=x.device, dtype=torch.float32)
+    assert x.dtype == dy.dtype and x.dtype in (torch.float32, torch.float16)
     a = WgradArgs()
+    a.dtype = 1 if x.dtype == torch.float16 else 0
+    a.out_scale = out_scale.data_ptr() if out_scale is not None else None
     a.x, a.dy, a.dw = x.data_ptr(), dy.data_ptr(), dw.data_ptr()
     dh, dwv = _i32arr(tap_dh), _i32arr(tap_dw)
     a.tap_dh, a.tap_dw = dh, dwv

@@ -29,8 +29,13 @@ BN_EPS, BN_MOM = 1e-5, 0.1
 #                  see the rounded output gradient).  This is what the tcgen05
 #                  kind::tf32 kernels compute, and what PyTorch's own cuDNN path does
 #                  for the reference's nn.Conv2d on Ampere+ GPUs (allow_tf32 = True).
+#   half_contract: the same contract with round-to-nearest-EVEN (what cvt.rn.f16.f32 does):
+#                  the tcgen05 kind::f16 kernels multiply IEEE half operands, which carry the
+#                  same 11-bit significand as TF32; gradient operands travel scaled by a
+#                  power of two, so the rounding is range-free here.
 # ---------------------------------------------------------------------------
 TF32 = False
+RNE = False
 
 
 class tf32_contract(object):
@@ -43,9 +48,22 @@ class tf32_contract(object):
         TF32 = self.old
 
 
+class half_contract(object):
+    def __enter__(self):
+        global TF32, RNE
+        self.old, TF32, RNE = (TF32, RNE), True, True
+
+    def __exit__(self, *a):
+        global TF32, RNE
+        TF32, RNE = self.old
+
+
 def round_tf32(t):
-    """fp32 -> nearest TF32 (ties away from zero), kept in fp32."""
+    """fp32 -> nearest value with a 10-bit mantissa, kept in fp32: ties away from zero (TF32, cvt.rna), or ties to even
+    under half_contract (cvt.rn.f16 inside half's normal range)."""
     i = t.detach().contiguous().view(torch.int32)
+    if RNE:
+        return ((i + 0xFFF + ((i >> 13) & 1)) & ~0x1FFF).view(torch.float32)
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 

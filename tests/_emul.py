@@ -13,7 +13,7 @@ def _gather(x, dh, dw, OH, OW, stride):
 
 
 def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lattice=(1, 1, 0, 0), epi_scale=None, epi_shift=None,
-            act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag=None, want_stats=False):
+            act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag=None, want_stats=False, y_half=False, out_scale=None):
     N, H, W, Cin = x.shape
     osh, osw, oph, opw = lattice
     if y is None:

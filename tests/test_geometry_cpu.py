@@ -57,3 +57,19 @@ def test_tap_geometry(emulated, case):
     assert torch.allclose(dx[..., :Cin].permute(0, 3, 1, 2), x.grad, atol=1e-4)
     dw = L._conv_wgrad(xh, gy, w.detach(), geom)
     assert torch.allclose(dw, w.grad, atol=1e-3)
+
+
+def test_half_map_handles():
+    """A half map travels through autograd behind an fp32-typed handle of the same logical shape over exactly its own bytes."""
+    h = ops.new_half((2, 3, 5, 16), torch.device("cpu"))
+    assert ops.is_half_handle(h) and h.dtype == torch.float32 and tuple(h.shape) == (2, 3, 5, 16)
+    assert h.untyped_storage().nbytes() == 2 * 3 * 5 * 16 * 2 + 16 * 2          # the half array + one pixel of slack
+    v = ops.hv(h)
+    assert v.dtype == torch.float16 and v.is_contiguous() and tuple(v.shape) == (2, 3, 5, 16)
+    ref = torch.randn(2, 3, 5, 16).half()
+    v.copy_(ref)
+    assert torch.equal(ops.hv(h), ref)                                          # same bytes
+    f = ops.fv(h)
+    assert f.dtype == torch.float32 and tuple(f.shape) == (2, 3, 5, 8) and f.data_ptr() == v.data_ptr()
+    assert torch.equal(f.view(torch.float16).view(2, 3, 5, 16), ref)
+    assert not ops.is_half_handle(torch.zeros(2, 3, 5, 16))

@@ -136,3 +136,75 @@ def test_conv_fused_epilogue(cuda):
         torch.cuda.synchronize()
         e = _rel(ops.nhwc_to_nchw(y, Cout).cpu(), ref)
         assert e < TOL, (act, e)
+
+
+# ------------------------------------------------------------------------------------------------ half operands (kind::f16)
+# IEEE half has the same 11-bit significand as TF32, so (inside its exponent range) the half path obeys the same arithmetic
+# contract up to the tie rule (cvt.rn.f16 rounds ties to even, cvt.rna.tf32 away from zero): oracle.nets.half_contract.  Gradient operands are far below
+# half's normal range; they travel scaled by a per-tensor power of two (exact), which the tiny-gradient case exercises.
+HALF_TOL = TOL             # vs the oracle's half contract (round-to-nearest-even operands, fp32 accumulate)
+HALF_CASES = [c for c in CASES if c[1] % 16 == 0 or c[1] == 2]
+
+
+@pytest.mark.parametrize("gscale", [1.0, 3e-9])
+@pytest.mark.parametrize("case", HALF_CASES, ids=lambda c: f"{c[0]}-{c[1]}to{c[2]}-k{c[3][0]}x{c[3][1]}-d{c[4][0]}x{c[4][1]}-s{c[5]}")
+def test_tapconv_half_fwd_bwd(cuda, case, gscale):
+    from sos_b200 import layers as L, ops
+    from oracle import nets
+    kind, Cin, Cout, k, d, stride, N, H, W = case
+    if gscale != 1.0 and (Cin, Cout) not in ((96, 96), (48, 48), (64, 128), (128, 64)):
+        pytest.skip("tiny-gradient scaling is checked on a subset")
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    if kind == "convT":
+        w = torch.randn(Cin, Cout, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    else:
+        w = torch.randn(Cout, Cin, k[0], k[1], generator=g) / (Cin * k[0] * k[1]) ** 0.5
+    x.requires_grad_(True)
+    w.requires_grad_(True)
+    with nets.half_contract():
+        y_ref = _ref_conv(x, w, kind, k, d, stride)
+        gy = torch.randn(y_ref.shape, generator=g) * gscale
+        y_ref.backward(gy)
+
+    geom = L.ConvGeom(kind, k[0], k[1], d[0], d[1], stride, round_dy=True)
+    cin_p = (Cin + 15) // 16 * 16
+    x32 = ops.nchw_to_nhwc(x.detach().to(cuda), cin_p).requires_grad_(True)
+    xd = L.ToHalf.apply(x32, cin_p)
+    assert ops.is_half_handle(xd) and ops.hv(xd).dtype == torch.float16
+    wd = w.detach().to(cuda).requires_grad_(True)
+    y = L.TapConvH.apply(xd, wd, geom)
+    torch.cuda.synchronize()
+    y_nchw = ops.nhwc_to_nchw(y, Cout).cpu()
+    assert y_nchw.shape == y_ref.shape
+    e_f = _rel(y_nchw, y_ref.detach())
+    y.backward(ops.nchw_to_nhwc(gy.to(cuda), y.shape[3]))
+    torch.cuda.synchronize()
+    e_w = _rel(wd.grad.cpu(), w.grad)
+    e_x = _rel(ops.nhwc_to_nchw(x32.grad, Cin).cpu(), x.grad)
+    print(f"\nhalf {case} gscale {gscale}: fwd {e_f:.2e} dgrad {e_x:.2e} wgrad {e_w:.2e}")
+    assert e_f < HALF_TOL and e_x < HALF_TOL and e_w < HALF_TOL, f"rel err: forward {e_f:.2e} dgrad {e_x:.2e} wgrad {e_w:.2e}"
+
+
+def test_conv_half_fused_epilogue(cuda):
+    """Inference epilogue with half outputs written straight into the next layer's operand map."""
+    from sos_b200 import layers as L, ops
+    from oracle import nets
+    g = torch.Generator().manual_seed(11)
+    for Cin, Cout, kind, k in ((96, 96, "zero", 5), (48, 48, "zero", 5), (64, 128, "valid", 5), (256, 128, "convT", 3)):
+        N, H, W = 2, 32, 27
+        x = torch.randn(N, Cin, H, W, generator=g)
+        w = (torch.randn(Cin, Cout, 3, 3, generator=g) if kind == "convT" else torch.randn(Cout, Cin, k, k, generator=g)) / (Cin * k * k) ** 0.5
+        sc, sh = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g) * 0.1
+        with nets.half_contract():
+            y_ref = _ref_conv(x, w, kind, (k, k), (1, 1), 1) * sc[None, :, None, None] + sh[None, :, None, None]
+            ref = nets.round_tf32(torch.relu(y_ref))
+        geom = L.ConvGeom(kind, k, k, 1, 1, 2 if kind == "convT" else 1)
+        xd = L.ToHalf.apply(ops.nchw_to_nhwc(x.to(cuda), Cin), Cin)
+        z = L.conv_fused_eval(xd, w.to(cuda), geom, sc.to(cuda), sh.to(cuda), 1, None, round_out=True)
+        torch.cuda.synchronize()
+        assert ops.is_half_handle(z)
+        got = ops.hv(z).float().permute(0, 3, 1, 2).cpu()
+        e = _rel(got, ref)
+        print(f"\nhalf epilogue {kind} {Cin}->{Cout}: {e:.2e}")
+        assert e < 1.1e-3, (kind, Cin, Cout, e)        # one ulp of the half output (<= 2^-10 of its value) on top of the GEMM tolerance
