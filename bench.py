@@ -223,14 +223,18 @@ def run_gpu(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        h0 = time.perf_counter()
         for _ in range(steps):
             step(src, e2e)
         e1.record()
+        host_ms[0] = 1e3 * (time.perf_counter() - h0) / steps          # host time to ENQUEUE a step (no synchronisation inside)
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
+
+    host_ms = [0.0]
 
     for _ in range(max(args.warmup, 3)):
         step(resident, False)
@@ -240,6 +244,7 @@ def run_gpu(args):
     ops.profile_start()
     n0 = _lib.launch_count
     ms = timed(resident, False, args.steps)
+    enqueue_ms = host_ms[0]
     launches = _lib.launch_count - n0
     prof = ops.profile_stop()
     clocks = sampler.summary() if sampler else None
@@ -256,10 +261,9 @@ def run_gpu(args):
         bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json, sustained bf16 cuBLAS)" if peaks else "fallback (B200_PROFILING.md)"
-        # cuBLAS TF32 on the same box, for scale: the conv kernels issue tcgen05 kind::tf32, whose hardware peak is half of bf16
-        torch.backends.cuda.matmul.allow_tf32 = True
-        a = torch.randn(8192, 8192, device=dev)
-        b = torch.randn(8192, 8192, device=dev)
+        # cuBLAS fp16 (fp32 accumulate) on the same box, for scale: the conv kernels issue tcgen05 kind::f16 like it does
+        a = torch.randn(8192, 8192, device=dev).half()
+        b = torch.randn(8192, 8192, device=dev).half()
         for _ in range(3):
             a @ b
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -268,8 +272,7 @@ def run_gpu(args):
             a @ b
         t1.record()
         torch.cuda.synchronize()
-        tf32_peak = 10 * 2 * 8192 ** 3 / (t0.elapsed_time(t1) * 1e-3) / 1e12
-        torch.backends.cuda.matmul.allow_tf32 = False
+        f16_peak = 10 * 2 * 8192 ** 3 / (t0.elapsed_time(t1) * 1e-3) / 1e12
         del a, b
         kern = {}
         for name, rec in prof.items():
@@ -277,9 +280,11 @@ def run_gpu(args):
                 kern[name] = {"launches": rec["n"], "ms_per_step": rec["ms"] / args.steps, "avg_launch_us": 1e3 * rec["ms"] / max(rec["n"], 1),
                               "tflops": rec["flops"] / (rec["ms"] * 1e-3) / 1e12 if rec["flops"] else None,
                               "gbs": rec["bytes"] / (rec["ms"] * 1e-3) / 1e9 if rec["bytes"] else None}
-        # the dominant kernel: tapgemm_tf32_kernel serves the forward convolutions AND their data gradients (same kernel, flipped
-        # taps); wgrad_tf32_kernel is the other tensor-core kernel
-        fams = {"tapgemm_tf32_kernel (conv forward + data gradient)": ("conv_fwd", "conv_dgrad"), "wgrad_tf32_kernel (conv weight gradient)": ("conv_wgrad",)}
+        # the dominant kernel: tapgemm_f16_kernel serves the forward convolutions AND their data gradients (same kernel, flipped
+        # taps); wgrad_f16_kernel is the other tensor-core kernel.  The weight gradients run on a second stream next to the data
+        # gradients / BatchNorm backward, so the event time of a backward launch includes waiting for the other stream's kernel:
+        # the roofline is quoted on the kernel's FORWARD launches (nothing else runs then); `kernels` lists every family.
+        fams = {"tapgemm_f16_kernel (conv forward + data gradient), forward launches": ("conv_fwd",)}
         roofline, best_ms = None, -1.0
         ncu = {}
         try:
@@ -298,9 +303,10 @@ def run_gpu(args):
                             "traffic": ncu.get(fam.split(" ")[0], {}).get("dram_bytes_per_launch"),
                             "traffic_note": ncu.get(fam.split(" ")[0], {}).get("note"),
                             "launches": nl, "avg_launch_us": 1e3 * tms / nl, "flops_per_launch": fl / nl,
-                            "peak_source": peak_src + "; the kernel issues tcgen05 kind::tf32, whose hardware peak is half of bf16",
-                            "tf32_cublas_tflops_measured_here": tf32_peak, "frac_of_tf32_cublas": ach / tf32_peak,
-                            "share_of_step": tms / ms}
+                            "peak_source": peak_src + "; the kernel issues tcgen05 kind::f16 (same rate as bf16)",
+                            "f16_cublas_tflops_measured_here": f16_peak, "frac_of_f16_cublas": ach / f16_peak,
+                            "share_of_step": sum(prof[n]["ms"] for n in ("conv_fwd", "conv_dgrad") if n in prof) / ms,
+                            "share_note": "forward + data-gradient launches of this kernel (event time) over the step"}
         if "stft" in kern and kern["stft"]["gbs"]:
             kern["stft"]["hbm_frac"] = kern["stft"]["gbs"] / hbm_peak
         cpu = None
@@ -315,8 +321,9 @@ def run_gpu(args):
                    "sample": f"{n}-clip steps of the same workload (BatchNorm over {n} clips), 1 warm-up + 3 timed, {dt:.2f} s per step"}
         print(json.dumps({
             "metric": METRIC, "value": clips / (ms * 1e-3), "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)",
-            "data": "synthetic",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 conv operands (11-bit significand, as TF32), fp32 accumulate; fp32 elsewhere",
+            "data": "synthetic", "host_enqueue_ms_per_step": enqueue_ms,
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": world * B, "samples_per_clip": LENGTH, "frames": 1 + LENGTH // 158,
                        "parallelism": f"dp{world} (NCCL all-reduce of the flat gradient buffers)" if world > 1 else "single GPU",
                        "l2": "no explicit flush: the step's activation working set (tens of GB) is far larger than the 126 MB L2"},
@@ -374,7 +381,7 @@ def run_infer(args):
     print(json.dumps({
         "metric": "clips/sec forward-only inference", "value": clips / (ms * 1e-3), "unit": "clips/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
+        "dtype": "f16 conv operands (11-bit significand, as TF32), fp32 accumulate; fp32 elsewhere", "data": "synthetic",
         "config": {"workload": f"batch={B} clips of {L} samples @16 kHz, STFT->SID->gate->STFT->JointModel->cRM+iSTFT, forward only "
                                "(BASELINE configs[0]/[3]/[4])", "batch": B, "samples_per_clip": L, "frames": 1 + L // 158,
                    "chunked_transforms": bool(fpc)},

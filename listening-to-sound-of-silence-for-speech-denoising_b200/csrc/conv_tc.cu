@@ -391,6 +391,8 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
     const double util = ((double)lat_slow / (ceil_div(lat_slow, pl.SB) * pl.SB)) * ((double)out_fast / (ceil_div(tiles_fast, S) * S * pl.FB));
     double cost = std::max(mma, bytes / 40.0) / (util * S);
     if (n_stages < 3) cost *= 1.3;
+    if (cb == 32) cost *= 1.4;                   // 32-byte operand rows: one L2 sector per TMA row, 32B swizzle
+    else if (cb == 64) cost *= 1.05;
     if (cost < best.cost) { best.pl = pl; best.cbe = cbe; best.S = S; best.n_stages = n_stages; best.stage_bytes = stage; best.a_box_bytes = a_box; best.cost = cost; }
   };
   auto sweep = [&](bool fw, bool sh) -> bool {
@@ -401,7 +403,9 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
       if (!build_plan(geo, fw, sh, pl)) continue;
       any = true;
       for (int cbe = 4 * kpe; cbe >= kpe; cbe >>= 1) {
-        if (CinK % cbe) continue;
+        // a chunk wider than the whole K extent is legal: ONE chunk whose box tail is zero-filled by TMA (activations) or
+        // never multiplied (weights); the MMA program then stops after CinK / kpe steps
+        if (CinK % cbe && cbe < CinK) continue;
         consider(pl, cbe, 2);
         consider(pl, cbe, 1);
       }
@@ -422,7 +426,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   p.N = N;
   p.n_nblk = n_nblk;
   p.cbe = best.cbe;
-  p.n_chunks = CinK / p.cbe;
+  p.n_chunks = ceil_div(CinK, p.cbe);
   p.cin = Cin;
   p.ec = ec;
   p.FB = pl.FB;
@@ -449,7 +453,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   p.staging_bytes = staging_bytes;
   {
     int n = 0;
-    const int kk_per_chunk = p.cbe / kpe;
+    const int kk_per_chunk = std::min(p.cbe, CinK) / kpe;
     for (int gi = 0; gi < p.n_groups; ++gi) {
       const TapGroup& grp = p.groups[gi];
       int same = -1;                                      // an earlier group with the same sub-tap structure shares its program

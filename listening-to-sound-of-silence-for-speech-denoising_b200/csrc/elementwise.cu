@@ -16,6 +16,14 @@ inline int grid_for(long long n, int per_block = kThreads, int max_blocks = 148 
   return (int)g;
 }
 
+// Smallest grid >= g for which g * kThreads is a multiple of `groups` (a thread then keeps one channel group for the whole run).
+inline int grid_mult(int g, int groups) {
+  int a = groups, b = kThreads;
+  while (b) { const int t = a % b; a = b; b = t; }
+  const int m = groups / a;
+  return (g + m - 1) / m * m;
+}
+
 // ----------------------------------------------------------------------------- cRM
 __device__ __forceinline__ float crm_to_m(float c, float inv_a, float b) {
   return inv_a * (logf(c / (1.f - c + 1e-8f) + 1e-10f) + b);
@@ -462,17 +470,24 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_dense_kernel(const floa
 }
 
 // ----------------------------------------------------------------------------- half-precision operand producers
-// z half dense [P][C] = act(y * scale + shift): a thread owns 8 channels (two 16-byte loads, one 16-byte store).
+// z half dense [P][C] = act(y * scale + shift): a thread owns 8 channels (two 16-byte loads, one 16-byte store).  The grid is
+// sized so that gridDim * blockDim is a multiple of C/8: a thread then meets the same 8 channels in every iteration and keeps
+// their coefficients in registers.
 __global__ void __launch_bounds__(kThreads) bn_act_half_kernel(const float* __restrict__ y, uint4* __restrict__ z, unsigned total, unsigned cg8,
                                                                 const float* __restrict__ scale, const float* __restrict__ shift, int act,
                                                                 const float* __restrict__ slope_ptr) {
   const float slope = slope_ptr ? *slope_ptr : 0.f;
   act &= SOS_ACT_MASK;
   const unsigned span = gridDim.x * blockDim.x;
-  for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += span * 2) {
-    float4 v[2][2];
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned c = (tid % cg8) * 8;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+  for (int k = 0; k < 8; ++k) { sc[k] = __ldg(scale + c + k); sh[k] = __ldg(shift + c + k); }
+  for (unsigned e0 = tid; e0 < total; e0 += span * 4) {
+    float4 v[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
       const unsigned e = e0 + i * span;
       if (e < total) {
         v[i][0] = ld_stream(y + (size_t)e * 8);
@@ -480,21 +495,21 @@ __global__ void __launch_bounds__(kThreads) bn_act_half_kernel(const float* __re
       }
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       const unsigned e = e0 + i * span;
       if (e >= total) break;
-      const unsigned c = (e % cg8) * 8;
       const float in[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
       float o[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = act_fwd(fmaf(in[k], __ldg(scale + c + k), __ldg(shift + c + k)), act, slope);
+      for (int k = 0; k < 8; ++k) o[k] = act_fwd(fmaf(in[k], sc[k], sh[k]), act, slope);
       z[e] = make_uint4(pack_half2(o[0], o[1]), pack_half2(o[2], o[3]), pack_half2(o[4], o[5]), pack_half2(o[6], o[7]));
     }
   }
 }
 
 // BatchNorm backward pass 2 with a scaled half output: dy = half(s * scale (dpre - m1 - xhat m2)), s = 2^e from the tensor's
-// sum of squares (scal[2], written by the finalize kernel).  Block 0 publishes scal[0] = s, scal[1] = 1/s.
+// sum of squares (scal[2], written by the finalize kernel).  Block 0 publishes scal[0] = s, scal[1] = 1/s.  Same thread ->
+// channel-group mapping as bn_act_half_kernel.
 __global__ void __launch_bounds__(kThreads) bn_bwd_apply_half_kernel(const float* __restrict__ dz, const float* __restrict__ y,
                                                                       uint4* __restrict__ dy, unsigned total, unsigned cg8,
                                                                       const float* __restrict__ scale, const float* __restrict__ shift,
@@ -510,7 +525,15 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_half_kernel(const float
     scal[1] = pow2i(-ex);
   }
   const unsigned span = gridDim.x * blockDim.x;
-  for (unsigned e0 = blockIdx.x * blockDim.x + threadIdx.x; e0 < total; e0 += span * 2) {
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned c = (tid % cg8) * 8;
+  float sc[8], sh[8], mu[8], is[8], a1[8], a2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = __ldg(scale + c + k); sh[k] = __ldg(shift + c + k); mu[k] = __ldg(mean + c + k); is[k] = __ldg(invstd + c + k);
+    a1[k] = __ldg(m1 + c + k); a2[k] = __ldg(m2 + c + k);
+  }
+  for (unsigned e0 = tid; e0 < total; e0 += span * 2) {
     float4 yv4[2][2], dz4[2][2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -526,19 +549,17 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_half_kernel(const float
     for (int i = 0; i < 2; ++i) {
       const unsigned e = e0 + i * span;
       if (e >= total) break;
-      const unsigned c = (e % cg8) * 8;
       const float yv[8] = {yv4[i][0].x, yv4[i][0].y, yv4[i][0].z, yv4[i][0].w, yv4[i][1].x, yv4[i][1].y, yv4[i][1].z, yv4[i][1].w};
       const float dv[8] = {dz4[i][0].x, dz4[i][0].y, dz4[i][0].z, dz4[i][0].w, dz4[i][1].x, dz4[i][1].y, dz4[i][1].z, dz4[i][1].w};
       float o[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float sc = __ldg(scale + c + k);
-        const float pre = fmaf(yv[k], sc, __ldg(shift + c + k));
+        const float pre = fmaf(yv[k], sc[k], sh[k]);
         float dpre = dv[k];
         if (act == 1) dpre = pre > 0.f ? dpre : 0.f;
         else if (act == 2) dpre = pre > 0.f ? dpre : dpre * slope;
-        const float xhat = (yv[k] - __ldg(mean + c + k)) * __ldg(invstd + c + k);
-        o[k] = s * (sc * (dpre - __ldg(m1 + c + k) - xhat * __ldg(m2 + c + k)));
+        const float xhat = (yv[k] - mu[k]) * is[k];
+        o[k] = s * (sc[k] * (dpre - a1[k] - xhat * a2[k]));
       }
       dy[e] = make_uint4(pack_half2(o[0], o[1]), pack_half2(o[2], o[3]), pack_half2(o[4], o[5]), pack_half2(o[6], o[7]));
     }
@@ -1071,7 +1092,7 @@ int sos_bn_act_half(const float* y, void* z_half, int64_t rows, int64_t channels
   SOS_CHECK_ARG((act & SOS_ACT_MASK) != 2 || slope, "sos_bn_act_half: PReLU needs a slope pointer");
   const long long tot8 = rows * (channels / 8);
   SOS_CHECK_ARG(tot8 < (1ll << 32), "sos_bn_act_half: too many elements");
-  bn_act_half_kernel<<<grid_for(tot8, kThreads * 2, 148 * 8), kThreads, 0, stream>>>(y, reinterpret_cast<uint4*>(z_half), (unsigned)tot8,
+  bn_act_half_kernel<<<grid_mult(grid_for(tot8, kThreads * 4, 148 * 8), (int)(channels / 8)), kThreads, 0, stream>>>(y, reinterpret_cast<uint4*>(z_half), (unsigned)tot8,
                                                                                      (unsigned)(channels / 8), scale, shift, act, slope);
   SOS_CHECK_LAUNCH("sos_bn_act_half");
   return SOS_OK;
@@ -1096,7 +1117,7 @@ int sos_bn_act_backward_half(const float* dz, const float* y, void* dy_half, int
   SOS_CHECK_LAUNCH("sos_bn_act_backward_half(finalize)");
   const long long tot8 = rows * (channels / 8);
   SOS_CHECK_ARG(tot8 < (1ll << 32), "sos_bn_act_backward_half: too many elements");
-  bn_bwd_apply_half_kernel<<<grid_for(tot8, kThreads * 2, 148 * 8), kThreads, 0, stream>>>(
+  bn_bwd_apply_half_kernel<<<grid_mult(grid_for(tot8, kThreads * 2, 148 * 8), (int)(channels / 8)), kThreads, 0, stream>>>(
       dz, y, reinterpret_cast<uint4*>(dy_half), (unsigned)tot8, (unsigned)(channels / 8), scale, shift, mean, invstd, m1, m2, act, slope, scal,
       (float)((double)rows * (double)channels));
   SOS_CHECK_LAUNCH("sos_bn_act_backward_half(apply)");

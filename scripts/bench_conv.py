@@ -1,6 +1,6 @@
 """Per-layer timing of the tcgen05 tap GEMM in its three roles (forward / data gradient / weight gradient) on the distinct
 convolution shapes of the two networks at the benchmark size (B clips, T = 203).  Prints TFLOP/s (algorithmic 2*MACs) and
-the planner's choice per layer.  usage: python scripts/bench_conv.py [B] [filter-substring]"""
+the planner's choice per layer.  usage: python scripts/bench_conv.py [B] [filter-substring] [tf32]   (default: half operands)"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -11,6 +11,9 @@ ops.init()
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 flt = sys.argv[2] if len(sys.argv) > 2 else ""
+HALF = not (len(sys.argv) > 3 and sys.argv[3] == "tf32")
+if flt == "all":
+    flt = ""
 T = 203
 # name, kind, Cin, Cout, k, d, stride, H, W (input, already padded for "valid"), count in the step
 LAYERS = [
@@ -50,12 +53,15 @@ for name, kind, Cin, Cout, k, d, stride, H, W, cnt in LAYERS:
     if flt and flt not in name:
         continue
     g = L.ConvGeom(kind, k[0], k[1], d[0], d[1], stride)
-    x = ops.round_tf32_(torch.randn(B, H, W, Cin, device=dev))
+    if HALF and Cin == 8:
+        Cin = 16
+    x = torch.randn(B, H, W, Cin, device=dev).relu_()
+    x = ops.to_half(x) if HALF else ops.round_tf32_(x)
     w = torch.randn((Cin, Cout, 3, 3) if kind == "convT" else (Cout, Cin, k[0], k[1]), device=dev) * 0.05
     OH, OW = g.out_size(H, W)
     y = L._conv_forward(x, w, g)
-    dy = ops.round_tf32_(torch.randn_like(y))
-    flops = 2.0 * B * OH * OW * Cout * Cin * k[0] * k[1] / (4 if kind == "convT" else 1)
+    dy = ops.to_half(torch.randn_like(y)) if HALF else ops.round_tf32_(torch.randn_like(y))
+    flops = 2.0 * B * OH * OW * Cout * (2 if Cin == 16 and Cout in (96, 64) else Cin) * k[0] * k[1] / (4 if kind == "convT" else 1)
     t_f = timeit(lambda: L._conv_forward(x, w, g))
     t_d = timeit(lambda: L._conv_dgrad(dy, w, g, x.shape))
     t_w = timeit(lambda: L._conv_wgrad(x, dy, w, g))
