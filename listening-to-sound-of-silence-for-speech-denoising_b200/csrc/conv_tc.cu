@@ -249,19 +249,39 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
             }
           }
           if (p.scale || p.act || p.out_scale) {
+            // branch-free over the 32 accumulator columns (columns >= ec hold don't-care values that are never stored); every
+            // condition is uniform and tested once per chunk, not once per element
             const int act = p.act & SOS_ACT_MASK;
-            const bool rnd = (p.act & SOS_ACT_ROUND_TF32) != 0;
+            float v[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (i < p.ec) {
-                float v = __uint_as_float(r[i]) * oscale;
-                if (p.scale) v = fmaf(v, __ldg(p.scale + ch0 + i), __ldg(p.shift + ch0 + i));
-                if (act == 1) v = fmaxf(v, 0.f);
-                else if (act == 2) v = v > 0.f ? v : v * slope;
-                if (rnd) v = tf32_rna(v);
-                r[i] = __float_as_uint(v);
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * oscale;
+            if (p.scale) {
+              const float4* sc4 = reinterpret_cast<const float4*>(p.scale + ch0);
+              const float4* sh4 = reinterpret_cast<const float4*>(p.shift + ch0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (4 * j < p.ec) {
+                  const float4 a = __ldg(sc4 + j), b = __ldg(sh4 + j);
+                  v[4 * j] = fmaf(v[4 * j], a.x, b.x);
+                  v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, b.y);
+                  v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, b.z);
+                  v[4 * j + 3] = fmaf(v[4 * j + 3], a.w, b.w);
+                }
               }
             }
+            if (act == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (act == 2) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * slope;
+            }
+            if ((p.act & SOS_ACT_ROUND_TF32) != 0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = tf32_rna(v[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
           }
           // make sure the TMA store that last read this staging buffer has drained
           if (ethread == 0) bulk_wait_read<1>();
