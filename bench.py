@@ -171,7 +171,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     import sos_b200
-    from sos_b200 import _lib, agent as ag, ops, transform
+    from sos_b200 import _lib, agent as ag, ops, tools, transform
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -200,10 +200,10 @@ def run_gpu(args):
 
     def step(src, e2e):
         d = {k: v.to(dev, non_blocking=True) for k, v in src.items()} if e2e else src
-        mixed = transform.stft_batch(d["mixed"])
-        noise = transform.stft_batch(d["mixed"], d["bits"], ratio, 1)
-        clean = transform.stft_batch(d["clean"])
-        full = transform.stft_batch(d["full_noise"])
+        # the four transforms of a training item (M2/dataset.py:234-237) as ONE launch over the 4 x B waveforms
+        gated = tools.gate_noise(d["mixed"], ratio, d["bits"])
+        spec = transform.stft_batch(torch.cat([d["mixed"], gated, d["clean"], d["full_noise"]]))
+        mixed, noise, clean, full = spec[:B], spec[B:2 * B], spec[2 * B:3 * B], spec[3 * B:]
         _, l_sid = sid.train_func({"audio": mixed, "label": d["label"]})
         _, l_jt = joint.train_func({"mixed": mixed, "noise": noise, "clean": clean, "full_noise": full})
         wave = transform.istft_batch(joint.last_rec.detach())

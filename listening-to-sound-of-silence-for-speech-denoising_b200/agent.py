@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import layers as L
-from . import ops, transform
+from . import ops, tools, transform
 from .networks import get_network
 
 PHASE_TRAINING, PHASE_TESTING = "train", "test"
@@ -268,11 +268,11 @@ class MyAgent(BaseAgent):
         mixed_w = _dev(data["mixed_wave"], d)
         bits = _dev(data["bits"], d)
         ratio = getattr(self.config, "sr", 16000) / getattr(self.config, "fps", 30.0)
-        mixed = transform.stft_batch(mixed_w)
-        noise = transform.stft_batch(mixed_w, bits, ratio, 1)                 # noise_sig = mixed * mask, gate fused
-        clean = transform.stft_batch(_dev(data["clean_wave"], d))
-        full = transform.stft_batch(_dev(data["full_noise_wave"], d))
-        return mixed, noise, clean, full
+        # the item's four transforms (M2/dataset.py:234-237) as ONE launch over the 4 x B waveforms: more than one wave of CTAs
+        B = mixed_w.shape[0]
+        gated = tools.gate_noise(mixed_w, ratio, bits)                        # noise_sig = mixed * mask  (M2/dataset.py:229)
+        spec = transform.stft_batch(torch.cat([mixed_w, gated, _dev(data["clean_wave"], d), _dev(data["full_noise_wave"], d)]))
+        return spec[:B], spec[B:2 * B], spec[2 * B:3 * B], spec[3 * B:]
 
     def forward(self, data):
         mixed, noise, clean, full_noise = self.spectrograms(data)

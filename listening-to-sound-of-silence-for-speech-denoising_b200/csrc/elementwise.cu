@@ -156,26 +156,36 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const float* __restr
   }
 }
 
-// Reduction of the per-block partial sums: a block owns 32 channels; 8 thread rows stride over the G partial blocks
-// (coalesced 128-byte reads), then combine through shared memory.  NQ quantities per channel ([g][NQ][C] layout).
+// Reduction of the per-block partial sums: a block owns kFinCh = 8 channels (one 32-byte sector per partial row); kFinRows = 32
+// thread rows stride over the G partial blocks (G is ~600: ~19 dependent loads per thread), then combine through shared
+// memory.  NQ quantities per channel ([g][NQ][C] layout).  Thread t: channel t & 7, row t >> 3; the channel totals end up in
+// the threads of row 0 (lanes 0..7 of warp 0).
+constexpr int kFinCh = 8, kFinRows = 32;
+__device__ __forceinline__ float sum8(float v) {       // over lanes 0..7 (only they call it)
+  v += __shfl_xor_sync(0xffu, v, 4);
+  v += __shfl_xor_sync(0xffu, v, 2);
+  v += __shfl_xor_sync(0xffu, v, 1);
+  return v;
+}
 template <int NQ>
 __device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int G, int C, int c, int gl, double (&out)[NQ],
-                                                double (*sm)[NQ][32]) {
+                                                double (*sm)[NQ][kFinCh]) {
   double a[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) a[q] = 0;
   if (c < C)
-    for (int g = gl; g < G; g += 8) {
+    for (int g = gl; g < G; g += kFinRows) {
 #pragma unroll
       for (int q = 0; q < NQ; ++q) a[q] += partial[((size_t)g * NQ + q) * C + c];
     }
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) sm[gl][q][threadIdx.x & 31] = a[q];
+  for (int q = 0; q < NQ; ++q) sm[gl][q][threadIdx.x & (kFinCh - 1)] = a[q];
   __syncthreads();
+  if (gl != 0) return;
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     double t = 0;
-    for (int r = 0; r < 8; ++r) t += sm[r][q][threadIdx.x & 31];
+    for (int r = 0; r < kFinRows; ++r) t += sm[r][q][threadIdx.x & (kFinCh - 1)];
     out[q] = t;
   }
 }
@@ -186,8 +196,8 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restric
                                                           float* __restrict__ running_var, float* __restrict__ mean_out,
                                                           float* __restrict__ invstd_out, float* __restrict__ scale_out,
                                                           float* __restrict__ shift_out) {
-  __shared__ double sm[8][2][32];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), gl = threadIdx.x >> 5;
+  __shared__ double sm[kFinRows][2][kFinCh];
+  const int c = blockIdx.x * kFinCh + (threadIdx.x & (kFinCh - 1)), gl = threadIdx.x / kFinCh;
   double r[2];
   reduce_partials<2>(partial, G, C, c, gl, r, sm);
   if (gl != 0 || c >= C) return;
@@ -319,8 +329,8 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                               float* __restrict__ dslope, float* __restrict__ m1, float* __restrict__ m2,
                                                               const float* __restrict__ scale, float* __restrict__ dy_sumsq) {
-  __shared__ double sm[8][NQ][32];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), gl = threadIdx.x >> 5;
+  __shared__ double sm[kFinRows][NQ][kFinCh];
+  const int c = blockIdx.x * kFinCh + (threadIdx.x & (kFinCh - 1)), gl = threadIdx.x / kFinCh;
   double r[NQ];
   reduce_partials<NQ>(partial, G, C, c, gl, r, sm);
   if (gl != 0) return;
@@ -340,12 +350,12 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
       const double v = sc * sc * (r[NQ - 1] - count * a * a - count * b * b);
       q = v > 0 ? (float)v : 0.f;
     }
-    q = warp_sum(q);
-    if ((threadIdx.x & 31) == 0) atomicAdd(dy_sumsq, q);
+    q = sum8(q);
+    if (threadIdx.x == 0) atomicAdd(dy_sumsq, q);
   }
   if (dslope) {
-    s3 = warp_sum(s3);
-    if ((threadIdx.x & 31) == 0) atomicAdd(dslope, s3);
+    s3 = sum8(s3);
+    if (threadIdx.x == 0) atomicAdd(dslope, s3);
   }
 }
 
@@ -1018,7 +1028,7 @@ int sos_bn_finalize(const float* partial, int64_t rows, int64_t channels, const 
                     cudaStream_t stream) {
   const int G = sos_bn_partial_blocks(rows, channels);
   SOS_CHECK_ARG(partial && gamma && beta && mean && invstd && scale && shift && G > 0, "sos_bn_finalize: bad arguments");
-  bn_finalize_kernel<<<ceil_div((int)channels, 32), 256, 0, stream>>>(partial, G, (int)channels, (double)rows, gamma, beta, eps, momentum,
+  bn_finalize_kernel<<<ceil_div((int)channels, kFinCh), kFinCh * kFinRows, 0, stream>>>(partial, G, (int)channels, (double)rows, gamma, beta, eps, momentum,
                                                                       running_mean, running_var, mean, invstd, scale, shift);
   SOS_CHECK_LAUNCH("sos_bn_finalize");
   return SOS_OK;
@@ -1029,7 +1039,7 @@ int sos_bn_finalize_partial(const float* partial, int64_t g_rows, int64_t rows, 
                             float* shift, cudaStream_t stream) {
   SOS_CHECK_ARG(partial && gamma && beta && mean && invstd && scale && shift && g_rows > 0 && rows > 0 && channels > 0,
                 "sos_bn_finalize_partial: bad arguments");
-  bn_finalize_kernel<<<ceil_div((int)channels, 32), 256, 0, stream>>>(partial, (int)g_rows, (int)channels, (double)rows, gamma, beta, eps, momentum,
+  bn_finalize_kernel<<<ceil_div((int)channels, kFinCh), kFinCh * kFinRows, 0, stream>>>(partial, (int)g_rows, (int)channels, (double)rows, gamma, beta, eps, momentum,
                                                                      running_mean, running_var, mean, invstd, scale, shift);
   SOS_CHECK_LAUNCH("sos_bn_finalize_partial");
   return SOS_OK;
@@ -1073,7 +1083,7 @@ int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y,
   const size_t smem = (size_t)3 * C * sizeof(float);
   bn_bwd_reduce_kernel<3><<<G, kThreads, smem, stream>>>(dz, dv, y, rows, C, scale, shift, mean, invstd, act, slope, partial);
   SOS_CHECK_LAUNCH("sos_bn_act_backward(reduce)");
-  bn_bwd_finalize_kernel<3><<<ceil_div(C, 32), 256, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta, (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2,
+  bn_bwd_finalize_kernel<3><<<ceil_div(C, kFinCh), kFinCh * kFinRows, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta, (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2,
                                                                  nullptr, nullptr);
   SOS_CHECK_LAUNCH("sos_bn_act_backward(finalize)");
   const long long tot4 = rows * (channels / 4);
@@ -1112,7 +1122,7 @@ int sos_bn_act_backward_half(const float* dz, const float* y, void* dy_half, int
   const size_t smem = (size_t)4 * C * sizeof(float);
   bn_bwd_reduce_kernel<4><<<G, kThreads, smem, stream>>>(dz, dv, y, rows, C, scale, shift, mean, invstd, act, slope, partial);
   SOS_CHECK_LAUNCH("sos_bn_act_backward_half(reduce)");
-  bn_bwd_finalize_kernel<4><<<ceil_div(C, 32), 256, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta,
+  bn_bwd_finalize_kernel<4><<<ceil_div(C, kFinCh), kFinCh * kFinRows, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta,
                                                                  (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2, scale, scal + 2);
   SOS_CHECK_LAUNCH("sos_bn_act_backward_half(finalize)");
   const long long tot8 = rows * (channels / 8);

@@ -4,7 +4,7 @@ import sys
 import torch
 sys.path.insert(0, ".")
 import sos_b200  # noqa
-from sos_b200 import agent as ag, ops, transform
+from sos_b200 import agent as ag, ops, tools, transform
 import bench
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
@@ -19,10 +19,9 @@ ratio = bench.SR / bench.FPS
 
 
 def step():
-    mixed = transform.stft_batch(d["mixed"])
-    noise = transform.stft_batch(d["mixed"], d["bits"], ratio, 1)
-    clean = transform.stft_batch(d["clean"])
-    full = transform.stft_batch(d["full_noise"])
+    gated = tools.gate_noise(d["mixed"], ratio, d["bits"])
+    spec = transform.stft_batch(torch.cat([d["mixed"], gated, d["clean"], d["full_noise"]]))
+    mixed, noise, clean, full = spec[:B], spec[B:2 * B], spec[2 * B:3 * B], spec[3 * B:]
     sid.train_func({"audio": mixed, "label": d["label"]})
     joint.train_func({"mixed": mixed, "noise": noise, "clean": clean, "full_noise": full})
     return transform.istft_batch(joint.last_rec.detach())
