@@ -353,10 +353,11 @@ def run_infer(args):
     resident = host.to(dev)
     out_host = torch.empty(B, 158 * (L // 158), dtype=torch.float32).pin_memory()
     fpc = 256 if L > 64000 else None
+    graphed = pipeline.GraphedDenoiser(sid, joint, B, L, SR, FPS, frames_per_chunk=fpc) if args.graph else None
 
     def step(e2e):
         w = host.to(dev, non_blocking=True) if e2e else resident
-        out = pipeline.denoise(w, sid, joint, SR, FPS, frames_per_chunk=fpc)
+        out = graphed(w) if graphed else pipeline.denoise(w, sid, joint, SR, FPS, frames_per_chunk=fpc)
         if e2e:
             out_host.copy_(out["denoised"], non_blocking=True)
             torch.cuda.current_stream().synchronize()
@@ -384,7 +385,7 @@ def run_infer(args):
         "dtype": "f16 conv operands (11-bit significand, as TF32), fp32 accumulate; fp32 elsewhere", "data": "synthetic",
         "config": {"workload": f"batch={B} clips of {L} samples @16 kHz, STFT->SID->gate->STFT->JointModel->cRM+iSTFT, forward only "
                                "(BASELINE configs[0]/[3]/[4])", "batch": B, "samples_per_clip": L, "frames": 1 + L // 158,
-                   "chunked_transforms": bool(fpc)},
+                   "chunked_transforms": bool(fpc), "cuda_graph": bool(graphed)},
         "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": "clips/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4},
         "gpu_launches": launches}))
@@ -402,6 +403,7 @@ def main():
     ap.add_argument("--workload", default="train", choices=["train", "infer"], help="train = BASELINE configs[1] (default, the metric); "
                     "infer = forward-only inference at --batch / --length")
     ap.add_argument("--length", type=int, default=LENGTH, help="samples per clip (infer workload)")
+    ap.add_argument("--graph", type=int, default=1, help="infer workload: replay the forward pass as one CUDA graph (pipeline.GraphedDenoiser)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

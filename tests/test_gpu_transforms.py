@@ -269,3 +269,22 @@ def test_denoise_pipeline_matches_oracle(cuda):
     print(f"denoise pipeline: mask L1 {e_mask:.2e}, waveform L1 {e_wave:.2e} (|wave| mean {np.abs(den).mean():.3f})")
     assert e_mask < 1e-3                                            # north_star bar
     assert e_wave < 2e-2 * float(np.abs(den).mean()) + 1e-4         # cRM recovery amplifies mask error x40 at crm = 0.5
+
+
+def test_graphed_denoiser_matches_eager(cuda):
+    """The CUDA-graph replay of the inference pipeline returns what the eager call returns, for changing inputs."""
+    from sos_b200 import networks, pipeline
+    from oracle import synth
+    torch.manual_seed(0)
+    sid = networks.get_network().to(cuda).eval()
+    torch.manual_seed(1)
+    joint = networks.get_network(object()).to(cuda).eval()
+    L = 16000
+    g = pipeline.GraphedDenoiser(sid, joint, 2, L, 16000, 30.0)
+    for seed in (0, 5):
+        wave = torch.tensor(synth.make_batch(2, length=L, start=seed)["mixed"], device=cuda)
+        ref = pipeline.denoise(wave, sid, joint, 16000, 30.0)
+        out = g(wave)
+        torch.cuda.synchronize()
+        assert torch.equal(out["bits"], ref["bits"])
+        assert torch.equal(out["denoised"], ref["denoised"]) and torch.equal(out["mask"], ref["mask"])
