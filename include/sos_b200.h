@@ -64,6 +64,18 @@ int sos_icrm_forward(const float* Y, const float* crm, float* rec, int64_t batch
 int sos_icrm_backward(const float* Y, const float* crm, const float* grad_rec, float* grad_crm, int64_t batch,
                       int64_t plane, float a, cudaStream_t stream);
 
+/* ------------------------------------------------------------------------------------------------ training-item construction
+ * sos_add_signals   M2/tools.py:217-303 add_signals / add_noise_to_audio (one noise track), called from M2/dataset.py:217:
+ *   new_noise = noise / ratio with ratio = sqrt(P_noise) / sqrt(P_signal / 10^(snr/10)) (noise unchanged when P_signal == 0 or
+ *   ratio == 0), mixed = signal + new_noise, then all three divided by max|mixed| / norm (norm == 0: no normalisation).
+ *   signal, noise (the already cropped interval), outputs: (B, L); snr_db: (B) device floats.
+ * sos_crm_forward   M2/transform.py:130-138 fast_cRM_sigmoid (the Dataset's "mask" entry, M2/dataset.py:239):
+ *   crm = sigmoid(a * M - b), M = clean / mixed as a complex ratio; (B, 2, plane) layout, a = 0.1, b = 0 in the reference. */
+int sos_add_signals(const float* signal, const float* noise, const float* snr_db, int64_t batch, int64_t length, float norm,
+                    float* mixed, float* clean, float* full_noise, cudaStream_t stream);
+int sos_crm_forward(const float* clean_spec, const float* mixed_spec, float* crm, int64_t batch, int64_t plane, float a, float b,
+                    cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------------------ losses / optimiser
  * nn.MSELoss / nn.BCEWithLogitsLoss (M2/agent.py:172-190, M1/agent.py:185-202): *loss_sum += sum of
  * element losses (caller divides by n); grad = dloss/dpred * grad_scale when grad != NULL. */

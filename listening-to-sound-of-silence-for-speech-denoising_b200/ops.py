@@ -208,6 +208,28 @@ def icrm_backward(Y, crm, grad_rec, a=0.1):
     return g
 
 
+# ----------------------------------------------------------------------------------------------- training-item construction
+def add_signals(signal, noise, snr_db, norm=0.5):
+    """M2/tools.py:217-276 on the device: signal, noise (B, L), snr_db (B,) -> mixed, clean, full_noise (B, L)."""
+    B, L = signal.shape
+    assert noise.shape == signal.shape and snr_db.numel() == B
+    mixed, clean, full = torch.empty_like(signal), torch.empty_like(signal), torch.empty_like(signal)
+    check(lib().sos_add_signals(_p(signal), _p(noise), _p(snr_db), B, L, float(norm or 0.0), _p(mixed), _p(clean), _p(full), _stream()),
+          "sos_add_signals")
+    _count()
+    return mixed, clean, full
+
+
+def crm_forward(clean_spec, mixed_spec, a=0.1, b=0.0):
+    """fast_cRM_sigmoid (M2/transform.py:130-138) on (B, 2, 256, T) spectrograms."""
+    B = clean_spec.shape[0]
+    plane = clean_spec[0, 0].numel()
+    out = torch.empty_like(clean_spec)
+    check(lib().sos_crm_forward(_p(clean_spec), _p(mixed_spec), _p(out), B, plane, a, b, _stream()), "sos_crm_forward")
+    _count()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- losses / optimiser
 def mse_fwd_bwd(pred, target, want_grad, grad_scale=1.0):
     n = pred.numel()

@@ -288,3 +288,43 @@ def test_graphed_denoiser_matches_eager(cuda):
         torch.cuda.synchronize()
         assert torch.equal(out["bits"], ref["bits"])
         assert torch.equal(out["denoised"], ref["denoised"]) and torch.equal(out["mask"], ref["mask"])
+
+
+def test_device_item_builder_matches_reference_recipe(cuda):
+    """the stage-2 training item built on the device (gate, add_signals at an SNR, gate, 4 x STFT, cRM target) against
+    the oracle's restatement of M2/dataset.py:167-259 / M2/tools.py:217-276, incl. a silent clip and norm = 0."""
+    from sos_b200 import datapipe, ops
+    from oracle import synth, transform as otf
+    from oracle.gating import bits_to_sample_mask
+    rng = np.random.default_rng(7)
+    B, L, sr, fps = 4, 16000, 16000, 30.0
+    n_bits = int(L / (sr / fps))
+    audio = (rng.standard_normal((B, L)) * 0.1).astype(np.float32)
+    noise = (rng.standard_normal((B, L)) * 0.3).astype(np.float32)
+    audio[2] = 0                                                   # signal_power == 0: the noise is added as it is
+    bits = ["".join(rng.choice(["0", "1"], p=[0.4, 0.6]) for _ in range(n_bits)) for _ in range(B)]
+    snrs = [-7.0, 3.0, 0.0, 10.0]
+    for norm in (0.5, 0.0):
+        item = datapipe.make_joint_items(torch.tensor(audio, device=cuda), torch.tensor(noise, device=cuda), snrs, bits, sr, fps, norm=norm,
+                                         want_waves=True)
+        torch.cuda.synchronize()
+        for i in range(B):
+            mask = bits_to_sample_mask(L, sr / fps, bits[i]).astype(np.float32)
+            mixed, clean, full = synth.add_signals(audio[i] * (1 - mask), noise[i], snrs[i], norm=norm)
+            gated = mixed * mask
+            for name, ref in (("mixed", mixed), ("clean", clean), ("full_noise", full), ("noise", gated)):
+                got = item["waves"][name][i].cpu().numpy()
+                assert np.abs(got - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), (norm, i, name, np.abs(got - ref).max())
+                spec = item[name][i].cpu().numpy()
+                assert np.abs(spec - otf.fast_stft(ref).transpose(2, 0, 1)).max() < 3e-4, (norm, i, name)
+            crm = otf.fast_cRM_sigmoid(otf.fast_stft(clean), otf.fast_stft(mixed)).transpose(2, 0, 1)
+            # the target divides by |Y|^2 + 1e-8: compare where the mixture bin is not vanishing (elsewhere the ratio amplifies
+            # the 1e-4 transform tolerance without bound)
+            Y = otf.fast_stft(mixed)
+            ok = (Y[..., 0] ** 2 + Y[..., 1] ** 2) > 1e-2
+            err = np.abs(item["mask"][i].cpu().numpy() - crm)[:, ok]
+            assert err.max() < 2e-3, (norm, i, err.max())
+    sid_item = datapipe.make_sid_items(torch.tensor(audio, device=cuda), torch.tensor(noise, device=cuda), snrs, bits, sr, fps)
+    assert sid_item["label"].shape == (B, n_bits) and sid_item["audio"].shape == (B, 2, 256, 1 + L // 158)
+    assert torch.equal(sid_item["audio"], datapipe.make_joint_items(torch.tensor(audio, device=cuda), torch.tensor(noise, device=cuda), snrs,
+                                                                   bits, sr, fps)["mixed"])
