@@ -61,3 +61,96 @@ class GraphedDenoiser(object):
         self.wave.copy_(wave, non_blocking=True)
         self.graph.replay()
         return self.out
+
+
+# ----------------------------------------------------------------------------------------------- predict.py-compatible driver
+def _read_wav(path):
+    """-> (float32 mono waveform in [-1, 1], sample rate).  (librosa.load's resampling, SURVEY 8f-3, is not built: the file must
+    already be at the model's sample rate.)"""
+    import numpy as np
+    from scipy.io import wavfile
+    sr, x = wavfile.read(path)
+    if x.dtype.kind == "i":
+        x = x.astype(np.float32) / float(np.iinfo(x.dtype).max + 1)
+    elif x.dtype.kind == "u":
+        x = (x.astype(np.float32) - 128.0) / 128.0
+    x = x.astype(np.float32)
+    if x.ndim == 2:
+        x = x.mean(axis=1)                                          # librosa.load(mono=True)
+    return x, int(sr)
+
+
+def _write_wav(path, x, sr):
+    import numpy as np
+    from scipy.io import wavfile
+    wavfile.write(path, int(sr), np.asarray(x, dtype=np.float32))   # librosa.output.write_wav writes float32 WAV too
+
+
+def predict_files(files, sid, joint, out_dir, sr=16000, fps=30.0, threshold=0.5, bit_streams=None, snr=None, save_audio=True):
+    """What the reference does with three programs and JSON / WAV hand-offs (M1/predict.py:107-233 -> M1/create_data_from_pred.py:60-270
+    -> M2/predict.py:395-530), per file and fully on the device: silent-interval prediction for the WHOLE file
+    (v_num_frames = number of video frames it covers), gating, denoising, and the same artefacts:
+
+      out_dir/pred_data.json              the hierarchy create_data_from_pred.py writes (dataset_path, num_videos, data_total_frames,
+                                          data_center_frames, sigmoid_threshold, snr, prediction_statistics, files[...])
+      out_dir/<k>/{noisy_input,noise_intervals,predicted_full_noise,denoised_output}.wav      (M2/predict.py:510-522)
+
+    files: list of WAV paths or (name, waveform ndarray) pairs, each at `sr`; clips may have different lengths.
+    bit_streams: optional ground-truth strings ('0' = silent) per file -> prediction_statistics (accuracy / precision / recall of
+    the silent class).  Returns the hierarchy dict."""
+    import json
+    import os
+    from collections import OrderedDict
+    import numpy as np
+    os.makedirs(out_dir, exist_ok=True)
+    dev = next(joint.parameters()).device
+    ratio = sr / fps
+    groups, labels, preds = [], [], []
+    for k, f in enumerate(files):
+        if isinstance(f, (tuple, list)):
+            name, x = f[0], np.asarray(f[1], dtype=np.float32)
+        else:
+            name = f
+            x, file_sr = _read_wav(f)
+            if file_sr != sr:
+                raise ValueError(f"{f}: sample rate {file_sr} != {sr} (resample first; librosa.load's resampler is not part of this path)")
+        n_frames = int(len(x) / ratio)
+        if n_frames < 1 or 1 + len(x) // 158 < 68:                  # ReflectionPad2d(16) on the T/4 axis (M2/networks.py:176)
+            raise RuntimeError(f"{name}: clip of {len(x)} samples is too short for the networks (needs at least 68 STFT frames)")
+        wave = torch.from_numpy(x).to(dev)[None]
+        out = denoise(wave, sid, joint, sr, fps, threshold)
+        bits = out["bits"][0].cpu().numpy()
+        pred = "".join(str(int(b)) for b in bits)
+        item = OrderedDict([("path", str(name)), ("num_frames", n_frames), ("framerate", fps), ("audio_sample_rate", sr),
+                            ("audio_samples", int(len(x))), ("duration", len(x) / sr),
+                            ("bit_stream", bit_streams[k] if bit_streams else None), ("predicted_bit_stream", pred),
+                            ("recovered_prediction", pred)])
+        if bit_streams:
+            gt = bit_streams[k][:n_frames]
+            labels += [int(c) for c in gt]
+            preds += [int(c) for c in pred[:len(gt)]]
+        if save_audio:
+            d = os.path.join(out_dir, str(k))
+            os.makedirs(d, exist_ok=True)
+            T = out["mask"].shape[3]
+            n = 158 * (T - 1)
+            gated = tools.gate_noise(wave, ratio, out["bits"])[0, :n].cpu().numpy()
+            pred_noise = transform.istft_batch(out["noise_pred"])[0].cpu().numpy()
+            for fname, sig in (("noisy_input", x[:n]), ("noise_intervals", gated), ("predicted_full_noise", pred_noise),
+                               ("denoised_output", out["denoised"][0].cpu().numpy())):
+                _write_wav(os.path.join(d, fname + ".wav"), sig, sr)
+            item["mixed_audio"] = os.path.join(str(k), "noisy_input.wav")
+            item["denoised_output"] = os.path.join(str(k), "denoised_output.wav")
+        groups.append(item)
+    stats = None
+    if labels:                                                     # silent frames ('0') are the positive class, as in show_metrics
+        l, p = np.array(labels), np.array(preds)
+        tp, fp, fn = int(((l == 0) & (p == 0)).sum()), int(((l == 1) & (p == 0)).sum()), int(((l == 0) & (p == 1)).sum())
+        stats = OrderedDict([("accuracy", float((l == p).mean())), ("precision", tp / max(tp + fp, 1)), ("recall", tp / max(tp + fn, 1))])
+    paths = [g["path"] for g in groups]
+    hierarchy = OrderedDict([("dataset_path", os.path.commonpath(paths) if all(os.path.isabs(p) for p in paths) else ""),
+                             ("num_videos", len(groups)), ("data_total_frames", None), ("data_center_frames", None),
+                             ("sigmoid_threshold", threshold), ("snr", snr), ("prediction_statistics", stats), ("files", groups)])
+    with open(os.path.join(out_dir, "pred_data.json"), "w") as fp_:
+        json.dump(hierarchy, fp_, indent=2)
+    return hierarchy

@@ -328,3 +328,35 @@ def test_device_item_builder_matches_reference_recipe(cuda):
     assert sid_item["label"].shape == (B, n_bits) and sid_item["audio"].shape == (B, 2, 256, 1 + L // 158)
     assert torch.equal(sid_item["audio"], datapipe.make_joint_items(torch.tensor(audio, device=cuda), torch.tensor(noise, device=cuda), snrs,
                                                                    bits, sr, fps)["mixed"])
+
+
+def test_predict_files_driver(cuda, tmp_path):
+    """the predict.py-shaped driver on two clips of different lengths: pred_data.json keys, bit strings of the right
+    length, and denoised_output.wav equal to the in-memory pipeline's waveform."""
+    import json
+    from scipy.io import wavfile
+    from sos_b200 import networks, pipeline
+    from oracle import synth
+    torch.manual_seed(0)
+    sid = networks.get_network().to(cuda).eval()
+    torch.manual_seed(1)
+    joint = networks.get_network(object()).to(cuda).eval()
+    clips = [synth.make_clip(0, 32000), synth.make_clip(1, 48000)]
+    paths = []
+    for i, c in enumerate(clips):
+        p = str(tmp_path / f"clip{i}.wav")
+        wavfile.write(p, 16000, c["mixed"].astype(np.float32))
+        paths.append(p)
+    h = pipeline.predict_files(paths, sid, joint, str(tmp_path / "out"), 16000, 30.0, bit_streams=[c["bits"] for c in clips])
+    saved = json.load(open(tmp_path / "out" / "pred_data.json"))
+    assert list(saved) == ["dataset_path", "num_videos", "data_total_frames", "data_center_frames", "sigmoid_threshold", "snr",
+                           "prediction_statistics", "files"]
+    assert saved["num_videos"] == 2 and set(saved["prediction_statistics"]) == {"accuracy", "precision", "recall"}
+    for i, (c, f) in enumerate(zip(clips, saved["files"])):
+        n = int(len(c["mixed"]) / (16000 / 30.0))
+        assert f["num_frames"] == n and len(f["predicted_bit_stream"]) == n and f["recovered_prediction"] == f["predicted_bit_stream"]
+        assert set(f["predicted_bit_stream"]) <= {"0", "1"}
+        sr, den = wavfile.read(tmp_path / "out" / str(i) / "denoised_output.wav")
+        ref = pipeline.denoise(torch.tensor(c["mixed"], device=cuda)[None], sid, joint, 16000, 30.0)["denoised"][0].cpu().numpy()
+        assert sr == 16000 and den.shape == ref.shape and np.array_equal(den, ref)
+    assert h["files"][0]["path"] == paths[0]
