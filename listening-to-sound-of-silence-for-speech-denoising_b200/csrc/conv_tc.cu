@@ -23,6 +23,7 @@
 #include "ptx.cuh"
 #include "sos_b200.h"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -413,8 +414,11 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
     if (n_stages < 3) cost *= 1.3;
     if (cb == 32) cost *= 1.4;                   // 32-byte operand rows: one L2 sector per TMA row, 32B swizzle
     else if (cb == 64) cost *= 1.05;
+    if (cbe > CinK) cost *= 1.0 + 0.5 * (cbe - CinK) / CinK;   // zero-filled box tail: shared-memory fill without payload (measured:
+                                                               // pays off at 48 of 64 channels, loses at 16 of 64)
     if (cost < best.cost) { best.pl = pl; best.cbe = cbe; best.S = S; best.n_stages = n_stages; best.stage_bytes = stage; best.a_box_bytes = a_box; best.cost = cost; }
   };
+  static const int force_cbe = getenv("SOS_FORCE_CBE") ? atoi(getenv("SOS_FORCE_CBE")) : 0;     // debugging aid
   auto sweep = [&](bool fw, bool sh) -> bool {
     bool any = false;
     for (int ms = sh ? kMaxSub : 1; ms >= 1; --ms) {
@@ -426,6 +430,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
         // a chunk wider than the whole K extent is legal: ONE chunk whose box tail is zero-filled by TMA (activations) or
         // never multiplied (weights); the MMA program then stops after CinK / kpe steps
         if (CinK % cbe && cbe < CinK) continue;
+        if (force_cbe > 0 && cbe != force_cbe) continue;
         consider(pl, cbe, 2);
         consider(pl, cbe, 1);
       }
