@@ -277,7 +277,9 @@ def test_checkpoint_roundtrip(cuda, tmp_path):
     out_b, _ = b.train_func(data)
     assert torch.equal(out_a, out_b)
     for (k, p), (_, q) in zip(a.net.state_dict().items(), b.net.state_dict().items()):
-        if p.is_floating_point():       # wgrad merges its pixel slices with fp32 atomics: the last bits of a gradient depend on their order
-            assert float((p - q).abs().max()) < 2e-4, k
+        if p.is_floating_point():       # wgrad merges its pixel slices with fp32 atomics: the last bits of a gradient depend on their
+            # order, and Adam's normalised update (lr 1e-3) turns a last-bit difference of a near-zero gradient into up to 2 lr
+            assert float((p - q).abs().max()) < 1e-3, k
+            assert float((p - q).abs().mean()) < 1e-5, k
         else:
             assert torch.equal(p, q), k
