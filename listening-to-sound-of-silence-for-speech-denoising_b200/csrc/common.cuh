@@ -61,9 +61,12 @@ __device__ __forceinline__ int half_scale_exp(float sumsq, float count) {
   return max(-100, min(100, e));
 }
 __device__ __forceinline__ float pow2i(int e) { return __int_as_float((e + 127) << 23); }
+// Two floats -> packed half2, round to nearest even, SATURATING at +-65504: an out-of-range activation must not turn into an
+// infinity (and then NaNs) inside a tensor-core operand.
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // first source operand -> upper half
+  return r;
 }
 #define SOS_ACT_MASK 15
 #define SOS_ACT_ROUND_TF32 16

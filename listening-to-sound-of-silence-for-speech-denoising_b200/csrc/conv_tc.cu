@@ -299,10 +299,7 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
               if (j < p.ec / 8) {
                 uint32_t h[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const __half2 hv = __floats2half2_rn(__uint_as_float(r[8 * j + 2 * k]), __uint_as_float(r[8 * j + 2 * k + 1]));
-                  h[k] = *reinterpret_cast<const uint32_t*>(&hv);
-                }
+                for (int k = 0; k < 4; ++k) h[k] = pack_half2(__uint_as_float(r[8 * j + 2 * k]), __uint_as_float(r[8 * j + 2 * k + 1]));
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ xr) << 4)), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3])
                              : "memory");
               }

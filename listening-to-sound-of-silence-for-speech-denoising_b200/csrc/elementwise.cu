@@ -921,7 +921,7 @@ __global__ void pack_taps_half_kernel(const float* __restrict__ w, int R, int K,
     const long long t2 = e / KP;
     const int t = (int)(t2 % ntaps);
     const int r = (int)(t2 / ntaps);
-    out[e] = __float2half_rn(k < K ? w[r * sr + k * sk + taps.off[t]] : 0.f);
+    out[e] = __float2half_rn(k < K ? fminf(fmaxf(w[r * sr + k * sk + taps.off[t]], -65504.f), 65504.f) : 0.f);
   }
 }
 

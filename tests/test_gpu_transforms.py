@@ -360,3 +360,22 @@ def test_predict_files_driver(cuda, tmp_path):
         ref = pipeline.denoise(torch.tensor(c["mixed"], device=cuda)[None], sid, joint, 16000, 30.0)["denoised"][0].cpu().numpy()
         assert sr == 16000 and den.shape == ref.shape and np.array_equal(den, ref)
     assert h["files"][0]["path"] == paths[0]
+
+
+def test_to_half_saturates_and_scales(cuda):
+    """Half operand producers: round to nearest even, zero-padded channels, saturation at +-65504 (no infinities inside a GEMM
+    operand), and the power-of-two scale of gradient-sized values (exact, RMS brought to ~1)."""
+    from sos_b200 import ops
+    x = torch.tensor([[1e6, -1e6, 65504.0, 1.0, 0.1, -3.0e-5, 0.0, 2049.0]], device=cuda)
+    h = ops.to_half(x, 16)
+    assert h.shape == (1, 16) and h.dtype == torch.float16
+    want = torch.tensor([65504.0, -65504.0, 65504.0, 1.0, 0.1, -3.0e-5, 0.0, 2049.0]).half()      # 2049 -> 2048 (ties to even)
+    assert torch.equal(h[0, :8].cpu(), want) and float(h[0, 8:].abs().max()) == 0
+    g = torch.randn(4096, 8, device=cuda) * 3e-9
+    gh, scal = ops.to_half(g, scaled=True)
+    s, inv = float(scal[0]), float(scal[1])
+    assert s * inv == 1.0 and abs(np.log2(s) - round(np.log2(s))) < 1e-12                           # an exact power of two
+    rms = float((gh.float() ** 2).mean().sqrt())
+    assert 0.5 < rms < 2.0
+    back = gh.float() * inv
+    assert float((back - g).abs().max()) <= 2.0 ** -11 * float(g.abs().max())                       # 11-bit significand kept
