@@ -270,9 +270,15 @@ static unsigned int* next_sync_slot(cudaStream_t stream) {
   return p;
 }
 
+int sos_lstm_forward_cluster(const float* gx, const float* w_hh, int64_t T, int64_t B, int64_t H, float* out, float* gates_ws, float* cell_ws,
+                             cudaStream_t stream);
+int sos_lstm_backward_cluster(const float* dout, const float* w_hh, const float* gates_ws, const float* cell_ws, int64_t T, int64_t B, int64_t H,
+                              float* dgx, cudaStream_t stream);
+
 extern "C" int sos_lstm_forward(const float* gx, const float* w_hh, int64_t T, int64_t B, int64_t H, float* out, float* gates_ws,
                                 float* cell_ws, cudaStream_t stream) {
   SOS_CHECK_ARG(gx && w_hh && out && gates_ws && cell_ws && T > 0 && B > 0 && H > 0 && H <= 512, "sos_lstm_forward: bad arguments");
+  if (int c = sos_lstm_forward_cluster(gx, w_hh, T, B, H, out, gates_ws, cell_ws, stream)) return c < 0 ? c : SOS_OK;   // cluster + DSMEM path
   const size_t smem = ((size_t)H * kHsPitch + (size_t)32 * (H + 1) + 32 * (kBt + 1)) * sizeof(float);
   SOS_CHECK_ARG(smem <= 200 * 1024, "sos_lstm_forward: hidden size too large for shared memory");
   static size_t attr = 0;
@@ -300,6 +306,7 @@ extern "C" int sos_lstm_backward(const float* dout, const float* w_hh, const flo
   (void)dh_ws;
   SOS_CHECK_ARG(dout && w_hh && gates_ws && cell_ws && dgx && dc_ws && T > 0 && B > 0 && H > 0 && H <= 512,
                 "sos_lstm_backward: bad arguments");
+  if (int c = sos_lstm_backward_cluster(dout, w_hh, gates_ws, cell_ws, T, B, H, dgx, stream)) return c < 0 ? c : SOS_OK;
   const size_t smem = ((size_t)kUnits * 4 * H + (size_t)std::min<int64_t>(4 * H, kBwdChunk) * kGsPitch + 8 * kUnits * kBt) * sizeof(float);
   SOS_CHECK_ARG(smem <= 200 * 1024, "sos_lstm_backward: hidden size too large for shared memory");
   static size_t attr = 0;

@@ -187,10 +187,11 @@ def test_padcat_reflect_resize(cuda):
     assert float((ops.nhwc_to_nchw(bd.grad, 64).cpu() - b.grad).abs().max()) < 1e-5
 
 
-@pytest.mark.parametrize("I,H,T,B", [(96, 40, 13, 5), (64, 200, 37, 40), (32, 100, 60, 3)])
+@pytest.mark.parametrize("I,H,T,B", [(96, 40, 13, 5), (64, 200, 37, 40), (32, 100, 60, 3), (48, 200, 29, 32), (16, 100, 17, 1), (24, 250, 9, 7)])
 def test_bilstm_matches_torch(cuda, I, H, T, B):
-    """nn.LSTM(bidirectional) forward / backward; the larger cases run the persistent kernels over several blocks per
-    direction (the inter-step barrier) and more than one 32-clip batch tile."""
+    """nn.LSTM(bidirectional) forward / backward.  Batches of at most 32 clips run the cluster kernels (one thread-block cluster per
+    direction, h / dh exchanged through distributed shared memory: 3, 7, 13 and 16 CTAs here); B = 40 runs the global-barrier
+    kernels over two batch tiles."""
     from sos_b200 import networks
     torch.manual_seed(2)
     ref = torch.nn.LSTM(I, H, bidirectional=True)
