@@ -15,4 +15,4 @@ void sos_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* sos_last_error(void) { return g_err; }
-extern "C" int sos_version(void) { return 100; }
+extern "C" int sos_version(void) { return 110; }

@@ -443,7 +443,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG(best.cost < 1e299, "sos_conv2d_tc: no feasible plan (Cin %d Cout %d taps %d)", Cin, Cout, (int)a.ntaps);
   const Plan& pl = best.pl;
 
-  static TcParams p;                  // kernel parameter block (copied at launch)
+  static thread_local TcParams p;     // kernel parameter block (copied at launch; one per host thread)
   memset(&p, 0, sizeof(p));
   p.N = N;
   p.n_nblk = n_nblk;

@@ -283,7 +283,7 @@ int sos_stft_tc_init() { return init_stft_tc(); }
 int sos_stft_tc_launch(const float* wave, int64_t batch, int64_t length, float* spec_out, const uint8_t* bits, int64_t n_bits,
                        const int32_t* frame_lo, double ratio, int gate_mode, cudaStream_t stream) {
   if (int e = init_stft_tc()) return e;
-  static StftParams p;
+  static thread_local StftParams p;
   p.tab = g_tab_map;
   p.wave = wave;
   p.out = spec_out;

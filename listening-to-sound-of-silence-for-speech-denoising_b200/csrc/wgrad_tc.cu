@@ -276,7 +276,7 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG(best.cost < 1e299, "sos_conv2d_wgrad: no feasible plan");
   const Plan& pl = best;
 
-  static WgParams p;
+  static thread_local WgParams p;
   memset(&p, 0, sizeof(p));
   const int Cin = (int)a.Cin, Cout = (int)a.Cout;
   p.Cin = Cin;

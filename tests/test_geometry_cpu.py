@@ -73,3 +73,17 @@ def test_half_map_handles():
     assert f.dtype == torch.float32 and tuple(f.shape) == (2, 3, 5, 8) and f.data_ptr() == v.data_ptr()
     assert torch.equal(f.view(torch.float16).view(2, 3, 5, 16), ref)
     assert not ops.is_half_handle(torch.zeros(2, 3, 5, 16))
+
+
+def test_crop_noise_host_logic():
+    """datapipe.crop_noise: a random interval of a random noise track per clip (M2/tools.py:279-292), errors on short tracks."""
+    import random
+    from sos_b200 import datapipe
+    noises = [torch.arange(1000, dtype=torch.float32), torch.arange(5000, 7000, dtype=torch.float32)]
+    out = datapipe.crop_noise(noises, 400, 6, torch.device("cpu"), rng=random.Random(3))
+    assert out.shape == (6, 400)
+    for row in out:
+        assert torch.equal(row[1:] - row[:-1], torch.ones(399))            # a contiguous interval of one track
+        assert 0 <= float(row[0]) <= 600 or 5000 <= float(row[0]) <= 6600
+    with pytest.raises(ValueError):
+        datapipe.crop_noise([torch.zeros(100)], 400, 1, torch.device("cpu"))
