@@ -76,6 +76,12 @@ int sos_add_signals(const float* signal, const float* noise, const float* snr_db
 int sos_crm_forward(const float* clean_spec, const float* mixed_spec, float* crm, int64_t batch, int64_t plane, float a, float b,
                     cudaStream_t stream);
 
+/* sos_ssnr           M2/metrics.py:86-129 metrics_ssnr (shift = 0) and :132-175 metrics_ssnr_shift (shift = 1), the evaluation
+ *   step's segmental SNR (30 ms Hann-windowed frames, quarter-frame hop, each clamped to [min_snr, max_snr]) and overall SNR,
+ *   for a batch of equally long waveform pairs: ref, deg (B, L) -> overall_out, segmental_out (B). */
+int sos_ssnr(const float* ref, const float* deg, int64_t batch, int64_t length, int64_t srate, double win_len_ms, float min_snr,
+             float max_snr, double eps, int shift, float* overall_out, float* segmental_out, cudaStream_t stream);
+
 /* ------------------------------------------------------------------------------------------------ losses / optimiser
  * nn.MSELoss / nn.BCEWithLogitsLoss (M2/agent.py:172-190, M1/agent.py:185-202): *loss_sum += sum of
  * element losses (caller divides by n); grad = dloss/dpred * grad_scale when grad != NULL. */

@@ -3,6 +3,7 @@
 //   fast_cRM_sigmoid                   M2/transform.py:36-54,92-94,130-138   (the Dataset's "mask" target, M2/dataset.py:239)
 #include "common.cuh"
 #include "sos_b200.h"
+#include <math.h>
 
 namespace {
 
@@ -95,7 +96,64 @@ __global__ void crm_fwd_kernel(const float* __restrict__ S, const float* __restr
   }
 }
 
+// Segmental SNR (M2/metrics.py:86-175).  One block per clip, a warp per frame: frame f covers samples [f * skip, f * skip + win)
+// under the Hann-like window 0.5 (1 - cos(2 pi (n + 1) / (win + 1))); each frame's 10 log10(Es / (En + eps) + off) is clamped to
+// [min_snr, max_snr] and the frames are averaged; the overall SNR uses the unwindowed sums.  Sums in double.
+__global__ void __launch_bounds__(256) ssnr_kernel(const float* __restrict__ ref, const float* __restrict__ deg, int L, int win, int skip,
+                                                   int n_frames, float min_snr, float max_snr, double eps, double off,
+                                                   float* __restrict__ overall, float* __restrict__ segmental) {
+  __shared__ double smd[32];
+  const float* r = ref + (size_t)blockIdx.x * L;
+  const float* g = deg + (size_t)blockIdx.x * L;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double ps = 0.0, pd = 0.0;
+  for (int i = threadIdx.x; i < L; i += 256) {
+    const double a = r[i], d = (double)r[i] - (double)g[i];
+    ps += a * a;
+    pd += d * d;
+  }
+  ps = block_sum_d(ps, smd);
+  pd = block_sum_d(pd, smd);
+  double seg = 0.0;
+  for (int f = warp; f < n_frames; f += 8) {
+    double se = 0.0, ne = 0.0;
+    for (int n = lane; n < win; n += 32) {
+      const double w = 0.5 * (1.0 - cos(6.283185307179586476925286766559 * (double)(n + 1) / (double)(win + 1)));
+      const double c = (double)r[f * skip + n] * w, p = (double)g[f * skip + n] * w;
+      se += c * c;
+      ne += (c - p) * (c - p);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      se += __shfl_xor_sync(0xffffffffu, se, o);
+      ne += __shfl_xor_sync(0xffffffffu, ne, o);
+    }
+    double v = 10.0 * log10(se / (ne + eps) + off);
+    v = fmin(fmax(v, (double)min_snr), (double)max_snr);
+    if (lane == 0) seg += v;
+  }
+  seg = block_sum_d(seg, smd);
+  if (threadIdx.x == 0) {
+    overall[blockIdx.x] = (float)(10.0 * log10(ps / (pd + eps)));
+    segmental[blockIdx.x] = n_frames > 0 ? (float)(seg / n_frames) : nanf("");
+  }
+}
+
 }  // namespace
+
+extern "C" int sos_ssnr(const float* ref, const float* deg, int64_t batch, int64_t length, int64_t srate, double win_len_ms, float min_snr,
+                        float max_snr, double eps, int shift, float* overall_out, float* segmental_out, cudaStream_t stream) {
+  SOS_CHECK_ARG(ref && deg && overall_out && segmental_out && batch > 0 && length > 0 && length < (1ll << 31) && srate > 0 && win_len_ms > 0,
+                "sos_ssnr: bad arguments");
+  const int win = (int)nearbyint(win_len_ms * (double)srate / 1000.0);          // int(np.round(win_len * srate / 1000)): half to even
+  const int skip = win / 4;
+  SOS_CHECK_ARG(win >= 4, "sos_ssnr: window of %d samples is too short", win);
+  const int n_frames = (int)((double)length / skip - ((double)win / skip));    // int(clean_length / skiprate - winlength / skiprate)
+  ssnr_kernel<<<(unsigned)batch, 256, 0, stream>>>(ref, deg, (int)length, win, skip, n_frames < 0 ? 0 : n_frames, min_snr, max_snr, eps,
+                                                   shift ? 1.0 : eps, overall_out, segmental_out);
+  SOS_CHECK_LAUNCH("sos_ssnr");
+  return SOS_OK;
+}
 
 extern "C" int sos_add_signals(const float* signal, const float* noise, const float* snr_db, int64_t batch, int64_t length, float norm,
                                float* mixed, float* clean, float* full_noise, cudaStream_t stream) {

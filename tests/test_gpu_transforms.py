@@ -380,3 +380,24 @@ def test_to_half_saturates_and_scales(cuda):
     assert 0.5 < rms < 2.0
     back = gh.float() * inv
     assert float((back - g).abs().max()) <= 2.0 ** -11 * float(g.abs().max())                       # 11-bit significand kept
+
+
+def test_ssnr_metrics_match_reference(cuda, golden_dir):
+    """segmental / overall SNR on the device vs the golden values from the reference's own source and vs the oracle,
+    single waveforms and a batch, clips of three lengths."""
+    import os
+    from sos_b200 import metrics
+    from oracle import metrics as om, synth
+    rows = np.load(os.path.join(golden_dir, "metrics.npz"))["rows"]
+    for index, length, eps, ov, seg, ov_s, seg_s in rows:
+        c = synth.make_clip(int(index), int(length))
+        a = metrics.metrics_ssnr(c["clean"], c["mixed"], eps=eps)
+        b = metrics.metrics_ssnr_shift(c["clean"], c["mixed"], eps=eps)
+        assert abs(a[0] - ov) < 2e-4 and abs(a[1] - seg) < 2e-4 and abs(b[0] - ov_s) < 2e-4 and abs(b[1] - seg_s) < 2e-4, (index, a, b)
+    batch = synth.make_batch(3, length=24000)
+    ov, seg = metrics.metrics_ssnr(torch.tensor(batch["clean"], device=cuda), torch.tensor(batch["mixed"], device=cuda))
+    for i in range(3):
+        want = om.metrics_ssnr(batch["clean"][i], batch["mixed"][i])
+        assert abs(float(ov[i]) - want[0]) < 2e-4 and abs(float(seg[i]) - want[1]) < 2e-4
+    l1 = metrics.metrics_L1(batch["mixed"][0], batch["clean"][0])
+    assert abs(l1 - float(np.mean(np.abs(batch["mixed"][0] - batch["clean"][0])))) < 1e-7

@@ -1,6 +1,7 @@
 """CPU: the oracle (oracle/*.py) against the golden vectors generated FROM THE REFERENCE ITSELF (oracle/make_golden.py ran
 the reference's own networks.py / transform.py / tools.py functions in the build container; see tests/golden/).
 This is what pins the oracle; the GPU parity tests then compare the CUDA path with the oracle and with the same goldens."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -136,3 +137,15 @@ def test_state_dict_keys_match_reference_counts():
     assert len(sid) == 84 and len(joint) == 322
     count = lambda sh: sum(int(np.prod(s)) for k, s in sh.items() if "running" not in k and "num_batches" not in k)
     assert count(sid) == 2276857 and count(joint) == 16389372
+
+
+def test_ssnr_oracle_matches_reference(golden_dir):
+    """oracle.metrics vs values produced by the reference's own metrics_ssnr / metrics_ssnr_shift source (M2/metrics.py:86-175)."""
+    from oracle import metrics as om, synth
+    rows = np.load(os.path.join(golden_dir, "metrics.npz"))["rows"]
+    assert len(rows) == 8
+    for index, length, eps, ov, seg, ov_s, seg_s in rows:
+        c = synth.make_clip(int(index), int(length))
+        a = om.metrics_ssnr(c["clean"], c["mixed"], eps=eps)
+        b = om.metrics_ssnr_shift(c["clean"], c["mixed"], eps=eps)
+        assert abs(a[0] - ov) < 1e-9 and abs(a[1] - seg) < 1e-9 and abs(b[0] - ov_s) < 1e-9 and abs(b[1] - seg_s) < 1e-9
