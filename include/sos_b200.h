@@ -126,7 +126,8 @@ int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y,
  * sos_bn_act_backward_half: as sos_bn_act_backward (dense dz) with dy written as half(dy * s), s the power of two that brings
  *   the tensor's RMS to ~1 (fp16 keeps 11 significant bits from 6e-5 to 65504 only; gradient maps live near 1e-8).
  *   scal (3 floats, scal[2] zeroed by the caller): out scal[0] = s, scal[1] = 1/s (the out_scale of the consuming GEMMs),
- *   scal[2] = sum of dy^2.  partial: sos_bn_partial_blocks(rows, C) * 4 * C floats.
+ *   scal[2] = sum of dy^2.  partial: sos_bn_partial_blocks(rows, C) * 4 * C floats.  accumulate_param_grads: dgamma / dbeta
+ *   (first real_channels entries; 0 = all) are ADDED to (they are the parameters' .grad) instead of written.
  * sos_to_half: out (rows, cd) half = x (rows, cs) fp32 zero-padded to cd channels; with scal != NULL (3 floats, scal[2]
  *   zeroed by the caller) the values are scaled as above. */
 int sos_bn_act_half(const float* y, void* z_half, int64_t rows, int64_t channels, const float* scale, const float* shift,
@@ -134,7 +135,7 @@ int sos_bn_act_half(const float* y, void* z_half, int64_t rows, int64_t channels
 int sos_bn_act_backward_half(const float* dz, const float* y, void* dy_half, int64_t rows, int64_t channels, const float* scale,
                              const float* shift, const float* mean, const float* invstd, int act, const float* slope,
                              float* partial, float* dgamma, float* dbeta, float* dslope, float* m1, float* m2, float* scal,
-                             cudaStream_t stream);
+                             int accumulate_param_grads, int64_t real_channels, cudaStream_t stream);
 int sos_to_half(const float* x, int64_t rows, int64_t cs, void* out_half, int64_t cd, float* scal, cudaStream_t stream);
 /* eval-mode backward of z = act(y*scale+shift): dy = dz*act'(pre)*scale (no batch statistics). */
 int sos_affine_act_backward(const float* dz, const int32_t* dz_view, const float* y, float* dy, int64_t rows,
@@ -149,6 +150,9 @@ int sos_nchw_to_nhwc(const float* x, int64_t batch, int64_t channels, float* out
                      int64_t slice_channels, cudaStream_t stream);
 int sos_nhwc_to_nchw(const float* in, const int32_t* in_view, int64_t batch, int64_t channels, float* out,
                      cudaStream_t stream);
+/* (B, C, H, W) fp32 -> dense NHWC half (B, H, W, padded_channels), zero padded: the network inputs of the half path. */
+int sos_nchw_to_nhwc_half(const float* x, int64_t batch, int64_t channels, int64_t H, int64_t W, void* out_half,
+                          int64_t padded_channels, cudaStream_t stream);
 int sos_copy_view(const float* src, const int32_t* src_view, float* dst, const int32_t* dst_view, int64_t batch,
                   int64_t channels, int accumulate, cudaStream_t stream);
 int sos_copy_view_backward(const float* grad_dst, const int32_t* dst_view, float* grad_src, const int32_t* src_view,
@@ -186,6 +190,10 @@ int sos_pack_taps_half(const float* w, int64_t rows, int64_t K, int64_t KP, int6
  * (transposed=1, in which case src is [tap][CinP'][CoutP'] with the roles swapped by the caller). */
 int sos_unpack_wgrad(const float* src, int64_t Cout, int64_t Cin, int64_t ntaps, int64_t CinP, float* dst, int accumulate,
                      cudaStream_t stream);
+/* dst (rows, cols, taps) += src [tap][rows_padded][cols_padded]: the weight-gradient buffer added straight into a parameter's
+ * .grad (Conv2d: rows = Cout, cols = Cin; ConvTranspose2d: rows = Cin, cols = Cout with the roles swapped by the caller). */
+int sos_accumulate_wgrad(const float* src, int64_t ntaps, int64_t rows_padded, int64_t cols_padded, int64_t rows, int64_t cols,
+                         float* dst, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ tensor-core tap GEMM
  * One kernel family (tcgen05 kind::tf32, fp32 accumulate in TMEM, TMA-staged operands) serves

@@ -328,7 +328,8 @@ template <int NQ>
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int G, int C, double count,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                               float* __restrict__ dslope, float* __restrict__ m1, float* __restrict__ m2,
-                                                              const float* __restrict__ scale, float* __restrict__ dy_sumsq) {
+                                                              const float* __restrict__ scale, float* __restrict__ dy_sumsq, int accumulate,
+                                                              int c_real) {
   __shared__ double sm[kFinRows][NQ][kFinCh];
   const int c = blockIdx.x * kFinCh + (threadIdx.x & (kFinCh - 1)), gl = threadIdx.x / kFinCh;
   double r[NQ];
@@ -336,8 +337,15 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __res
   if (gl != 0) return;
   float s3 = 0.f;
   if (c < C) {
-    dbeta[c] = (float)r[0];
-    dgamma[c] = (float)r[1];
+    if (c < c_real) {                                // (channels >= c_real are zero padding of the map, not parameters)
+      if (accumulate) {                              // straight into the parameters' .grad
+        dbeta[c] += (float)r[0];
+        dgamma[c] += (float)r[1];
+      } else {
+        dbeta[c] = (float)r[0];
+        dgamma[c] = (float)r[1];
+      }
+    }
     m1[c] = (float)(r[0] / count);
     m2[c] = (float)(r[1] / count);
     s3 = (float)r[2];
@@ -710,6 +718,21 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, float* _
   }
 }
 
+// NCHW fp32 (B,C,H,W) -> dense NHWC half (B,H,W,Cw), channels >= C zero filled: a thread writes 8 channels of one pixel.
+__global__ void nchw_to_nhwc_half_kernel(const float* __restrict__ x, int C, uint4* __restrict__ out, int Cw, long long plane, long long P) {
+  const int g8 = Cw >> 3;
+  const long long total = P * g8;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long p = e / g8;
+    const int c0 = (int)(e - p * g8) * 8;
+    const long long n = p / plane, r = p - n * plane;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = c0 + k < C ? __ldg(x + (n * C + c0 + k) * plane + r) : 0.f;
+    out[e] = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]), pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+  }
+}
+
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, View iv, float* __restrict__ out, int C, long long P) {
   const long long plane = (long long)iv.H * iv.W;
   const long long total = P * C;
@@ -939,6 +962,18 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, int Cout, int
   }
 }
 
+// wgrad buffer [tap][RP][CP] (padded rows / columns) -> += parameter gradient (R, Cc, taps) in PyTorch's layout.
+__global__ void accumulate_wgrad_kernel(const float* __restrict__ src, int ntaps, int RP, int CP, int R, int Cc, float* __restrict__ dst) {
+  const long long total = (long long)R * Cc * ntaps;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(e % ntaps);
+    const long long t = e / ntaps;
+    const int c = (int)(t % Cc);
+    const int r = (int)(t / Cc);
+    dst[e] += src[((long long)tap * RP + r) * CP + c];
+  }
+}
+
 }  // namespace
 
 // ============================================================================= C ABI
@@ -1084,7 +1119,7 @@ int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y,
   bn_bwd_reduce_kernel<3><<<G, kThreads, smem, stream>>>(dz, dv, y, rows, C, scale, shift, mean, invstd, act, slope, partial);
   SOS_CHECK_LAUNCH("sos_bn_act_backward(reduce)");
   bn_bwd_finalize_kernel<3><<<ceil_div(C, kFinCh), kFinCh * kFinRows, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta, (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2,
-                                                                 nullptr, nullptr);
+                                                                 nullptr, nullptr, 0, C);
   SOS_CHECK_LAUNCH("sos_bn_act_backward(finalize)");
   const long long tot4 = rows * (channels / 4);
   if (view_dense(dv, C) && tot4 < (1ll << 32))
@@ -1110,7 +1145,8 @@ int sos_bn_act_half(const float* y, void* z_half, int64_t rows, int64_t channels
 
 int sos_bn_act_backward_half(const float* dz, const float* y, void* dy_half, int64_t rows, int64_t channels, const float* scale,
                              const float* shift, const float* mean, const float* invstd, int act, const float* slope, float* partial,
-                             float* dgamma, float* dbeta, float* dslope, float* m1, float* m2, float* scal, cudaStream_t stream) {
+                             float* dgamma, float* dbeta, float* dslope, float* m1, float* m2, float* scal, int accumulate_param_grads,
+                             int64_t real_channels, cudaStream_t stream) {
   const int G = sos_bn_partial_blocks(rows, channels);
   SOS_CHECK_ARG(dz && y && dy_half && scale && shift && mean && invstd && partial && dgamma && dbeta && m1 && m2 && scal && G > 0 &&
                     channels % 8 == 0,
@@ -1123,7 +1159,8 @@ int sos_bn_act_backward_half(const float* dz, const float* y, void* dy_half, int
   bn_bwd_reduce_kernel<4><<<G, kThreads, smem, stream>>>(dz, dv, y, rows, C, scale, shift, mean, invstd, act, slope, partial);
   SOS_CHECK_LAUNCH("sos_bn_act_backward_half(reduce)");
   bn_bwd_finalize_kernel<4><<<ceil_div(C, kFinCh), kFinCh * kFinRows, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta,
-                                                                 (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2, scale, scal + 2);
+                                                                 (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2, scale, scal + 2,
+                                                                 accumulate_param_grads, (int)(real_channels > 0 ? real_channels : channels));
   SOS_CHECK_LAUNCH("sos_bn_act_backward_half(finalize)");
   const long long tot8 = rows * (channels / 8);
   SOS_CHECK_ARG(tot8 < (1ll << 32), "sos_bn_act_backward_half: too many elements");
@@ -1198,6 +1235,26 @@ int sos_nchw_to_nhwc(const float* x, int64_t batch, int64_t channels, float* out
   const long long P = batch * ov.H * ov.W;
   nchw_to_nhwc_kernel<<<grid_for(P * slice_channels), kThreads, 0, stream>>>(x, (int)channels, out, ov, (int)slice_channels, P);
   SOS_CHECK_LAUNCH("sos_nchw_to_nhwc");
+  return SOS_OK;
+}
+
+int sos_nchw_to_nhwc_half(const float* x, int64_t batch, int64_t channels, int64_t H, int64_t W, void* out_half, int64_t padded_channels,
+                          cudaStream_t stream) {
+  SOS_CHECK_ARG(x && out_half && batch > 0 && channels > 0 && H > 0 && W > 0 && padded_channels >= channels && padded_channels % 8 == 0,
+                "sos_nchw_to_nhwc_half: bad arguments (padded_channels must be a multiple of 8, >= channels)");
+  const long long plane = H * W, P = batch * plane;
+  nchw_to_nhwc_half_kernel<<<grid_for(P * (padded_channels / 8)), kThreads, 0, stream>>>(x, (int)channels, reinterpret_cast<uint4*>(out_half),
+                                                                                        (int)padded_channels, plane, P);
+  SOS_CHECK_LAUNCH("sos_nchw_to_nhwc_half");
+  return SOS_OK;
+}
+
+int sos_accumulate_wgrad(const float* src, int64_t ntaps, int64_t rows_padded, int64_t cols_padded, int64_t rows, int64_t cols, float* dst,
+                         cudaStream_t stream) {
+  SOS_CHECK_ARG(src && dst && ntaps > 0 && rows > 0 && cols > 0 && rows_padded >= rows && cols_padded >= cols, "sos_accumulate_wgrad: bad arguments");
+  accumulate_wgrad_kernel<<<grid_for(rows * cols * ntaps), kThreads, 0, stream>>>(src, (int)ntaps, (int)rows_padded, (int)cols_padded, (int)rows,
+                                                                                 (int)cols, dst);
+  SOS_CHECK_LAUNCH("sos_accumulate_wgrad");
   return SOS_OK;
 }
 

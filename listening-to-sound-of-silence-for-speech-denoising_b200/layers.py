@@ -8,6 +8,8 @@ records the graph.  Reference semantics:
   FeatToSeq     view/interpolate/permute before the LSTMs (M1/networks.py:131-135, M2/networks.py:83-86)
   BiLSTM        nn.LSTM(bidirectional=True) (M1/networks.py:95, M2/networks.py:64)
 """
+import os
+
 import torch
 
 from . import ops
@@ -57,6 +59,7 @@ def half_mode():
 # streams (`join_wgrad()`) before it reads any gradient.
 _ASYNC_WGRAD = False
 _SIDE = None
+_DIRECT_GRADS = os.environ.get("SOS_DIRECT_GRADS", "1") != "0"      # A/B switch: parameter gradients added straight into .grad
 
 
 def _side_stream():
@@ -197,20 +200,24 @@ def _conv_dgrad_raw(dy, w, g, x_shape, out_scale=None):
     return dx
 
 
-def _conv_wgrad(x, dy, w, g, out_scale=None):
-    """Returns the gradient in w's own layout."""
+def _conv_wgrad_raw(x, dy, w, g, out_scale=None):
+    """The weight-gradient kernel's tap-major buffer (ntaps, RP, CP): rows / columns are w's first two axes, zero padded."""
     if g.kind == "convT":
         Cin, Cout = w.shape[0], w.shape[1]
-        # roles swapped: "input" = dy (2H x 2W), "output grad" = x (H x W), stride 2
-        dwt = ops.conv_wgrad(dy, x, [o[0] for o in g.off], [o[1] for o in g.off], x.shape[3], x.shape[1], x.shape[2], 2, real=(Cout, Cin),
-                             out_scale=out_scale)
-        # dwt (ntaps, Cin_p, Cout_p) -> (Cin, Cout, kh, kw)
-        return dwt[:, :Cin, :Cout].permute(1, 2, 0).reshape(Cin, Cout, g.kh, g.kw).contiguous()
+        # roles swapped: "input" = dy (2H x 2W), "output grad" = x (H x W), stride 2  ->  (ntaps, Cin_p, Cout_p)
+        return ops.conv_wgrad(dy, x, [o[0] for o in g.off], [o[1] for o in g.off], x.shape[3], x.shape[1], x.shape[2], 2, real=(Cout, Cin),
+                              out_scale=out_scale)
     Cout, Cin = w.shape[0], w.shape[1]
     OH, OW = dy.shape[1], dy.shape[2]
-    dwt = ops.conv_wgrad(x, dy, [o[0] for o in g.off], [o[1] for o in g.off], dy.shape[3], OH, OW, g.stride, real=(Cin, Cout),
-                         out_scale=out_scale)
-    return dwt[:, :Cout, :Cin].permute(1, 2, 0).reshape(Cout, Cin, g.kh, g.kw).contiguous()
+    return ops.conv_wgrad(x, dy, [o[0] for o in g.off], [o[1] for o in g.off], dy.shape[3], OH, OW, g.stride, real=(Cin, Cout),
+                          out_scale=out_scale)
+
+
+def _conv_wgrad(x, dy, w, g, out_scale=None):
+    """Returns the gradient in w's own layout."""
+    dwt = _conv_wgrad_raw(x, dy, w, g, out_scale)
+    R, Cc = w.shape[0], w.shape[1]
+    return dwt[:, :R, :Cc].permute(1, 2, 0).reshape(R, Cc, g.kh, g.kw).contiguous()
 
 
 class TapConv(torch.autograd.Function):
@@ -281,7 +288,10 @@ def _wgrad_into(w, x, dy, g, out_scale):
         side, main = _side_stream(), torch.cuda.current_stream()
         side.wait_stream(main)                                     # x, dy, the scale (and the zeroed .grad) are ready
         with torch.cuda.stream(side):
-            w.grad.add_(_conv_wgrad(x, dy, w, g, out_scale))
+            if _DIRECT_GRADS and w.grad.is_contiguous():
+                ops.accumulate_wgrad(_conv_wgrad_raw(x, dy, w, g, out_scale), w.grad)     # one pass: un-pad, re-layout, add
+            else:
+                w.grad.add_(_conv_wgrad(x, dy, w, g, out_scale))
         x.record_stream(side)
         dy.record_stream(side)
         if out_scale is not None:
@@ -311,19 +321,26 @@ class ConvBNActH(torch.autograd.Function):
             running_var.copy_(rv[:Cn])
         z = ops.bn_act_apply(y, stats, act, slope, half=not out_f32)
         ctx.g, ctx.act, ctx.Cn = g, act, Cn
-        ctx.save_for_backward(x, w, y, stats, slope if slope is not None else torch.empty(0))
+        ctx.save_for_backward(x, w, y, stats, slope if slope is not None else torch.empty(0), gamma, beta)
         return z
 
     @staticmethod
     def backward(ctx, dz):
-        x, w, y, stats, slope = ctx.saved_tensors
+        x, w, y, stats, slope, gamma, beta = ctx.saved_tensors
         slope = slope if slope.numel() else None
         g, Cn = ctx.g, ctx.Cn
-        dy, dgamma, dbeta, dslope, scal = ops.bn_train_backward_half(dz.contiguous(), y, stats, ctx.act, slope)
+        # inside async_wgrad() (the agents' update_network) the BatchNorm parameter gradients are added straight into .grad (views
+        # of the flat gradient buffer) by the finalize kernel: no gradient tensors for autograd to accumulate
+        direct = (_ASYNC_WGRAD and _DIRECT_GRADS and gamma.grad is not None and beta.grad is not None and (slope is None or slope.grad is not None)
+                  and gamma.grad.is_contiguous() and beta.grad.is_contiguous())
+        into = (gamma.grad, beta.grad, slope.grad if slope is not None else None) if direct else None
+        dy, dgamma, dbeta, dslope, scal = ops.bn_train_backward_half(dz.contiguous(), y, stats, ctx.act, slope, grad_into=into)
         inv = scal[1:2]
         xh = ops.hv(x)
         dw = _wgrad_into(w, xh, dy, g, inv) if ctx.needs_input_grad[1] else None
         dx = _conv_dgrad(dy, w, g, xh.shape, inv) if ctx.needs_input_grad[0] else None
+        if direct:
+            return dx, dw, None, None, None, None, None, None, None, None, None, None
         return dx, dw, dgamma[:Cn], dbeta[:Cn], dslope, None, None, None, None, None, None, None
 
 

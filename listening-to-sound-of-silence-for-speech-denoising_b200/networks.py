@@ -125,10 +125,7 @@ def _to_nhwc(x):
     """(B, 2, 256, T) NCHW -> NHWC operand of the first convolutions: a half map with 16 channels (one K = 16 MMA step) in the
     default mode, else fp32 with channels zero-padded to 8 (TF32-rounded unless precise)."""
     if L.half_mode():
-        y = ops.nchw_to_nhwc(x.contiguous().float(), 16)
-        z = ops.new_half(y.shape, y.device)
-        ops.to_half(y, 16, out=ops.hv(z))
-        return z
+        return ops.nchw_to_nhwc_half(x.contiguous().float(), 16)
     y = ops.nchw_to_nhwc(x.contiguous().float(), 8)
     return y if L.precise() else ops.round_tf32_(y)
 

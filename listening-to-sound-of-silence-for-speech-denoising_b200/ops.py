@@ -322,21 +322,32 @@ def bn_act_apply(y, stats, act, slope, half):
     return z
 
 
-def bn_train_backward_half(dz, y, stats, act, slope):
+def bn_train_backward_half(dz, y, stats, act, slope, grad_into=None):
     """BatchNorm + activation backward with the gradient w.r.t. the conv output written as a scaled half operand.
-    -> dy (real half tensor), dgamma, dbeta, dslope, scal [s, 1/s, sum dy^2]."""
+    -> dy (real half tensor), dgamma, dbeta, dslope, scal [s, 1/s, sum dy^2].
+    grad_into = (gamma.grad, beta.grad, slope.grad or None): the parameter gradients are ADDED straight into these (their first
+    gamma.grad.numel() channels; the map may carry zero-padded channels) and None is returned in their place."""
     Cn = y.shape[-1]
     rows = y.numel() // Cn
     G = lib().sos_bn_partial_blocks(rows, Cn)
     partial = torch.empty(G * 4 * Cn, device=y.device, dtype=torch.float32)
     dy = torch.empty(y.shape, device=y.device, dtype=torch.float16)
     out = torch.empty(4, Cn, device=y.device, dtype=torch.float32)             # dgamma, dbeta, m1, m2
-    dslope = torch.zeros(1, device=y.device, dtype=torch.float32) if (act & 15) == ACT_PRELU else None
+    prelu = (act & 15) == ACT_PRELU
     scal = torch.zeros(3, device=y.device, dtype=torch.float32)
     sp = lambda i: C.c_void_p(stats[i].data_ptr())
     op = lambda i: C.c_void_p(out[i].data_ptr())
+    if grad_into is not None:
+        gg, gb, gs = grad_into
+        assert gg.is_contiguous() and gb.is_contiguous() and gg.numel() == gb.numel() <= Cn and (not prelu or gs is not None)
+        check(lib().sos_bn_act_backward_half(_p(dz), _p(y), _p(dy), rows, Cn, sp(2), sp(3), sp(0), sp(1), act & 15, _p(slope), _p(partial),
+                                             _p(gg), _p(gb), _p(gs) if prelu else None, op(2), op(3), _p(scal), 1, gg.numel(), _stream()),
+              "sos_bn_act_backward_half")
+        _count(3)
+        return dy, None, None, None, scal
+    dslope = torch.zeros(1, device=y.device, dtype=torch.float32) if prelu else None
     check(lib().sos_bn_act_backward_half(_p(dz), _p(y), _p(dy), rows, Cn, sp(2), sp(3), sp(0), sp(1), act & 15, _p(slope), _p(partial),
-                                         op(0), op(1), _p(dslope), op(2), op(3), _p(scal), _stream()), "sos_bn_act_backward_half")
+                                         op(0), op(1), _p(dslope), op(2), op(3), _p(scal), 0, 0, _stream()), "sos_bn_act_backward_half")
     _count(3)
     return dy, out[0], out[1], dslope, scal
 
@@ -375,6 +386,24 @@ def nchw_to_nhwc(x, channels_padded):
     check(lib().sos_nchw_to_nhwc(_p(x), B, Cc, _p(out), view8(H, W, ld=channels_padded), channels_padded, _stream()), "sos_nchw_to_nhwc")
     _count()
     return out
+
+
+def nchw_to_nhwc_half(x, channels_padded):
+    """(B, C, H, W) fp32 -> half-map handle (B, H, W, Cp) with zero padded channels, one pass."""
+    B, Cc, H, W = x.shape
+    z = new_half((B, H, W, channels_padded), x.device)
+    check(lib().sos_nchw_to_nhwc_half(_p(x), B, Cc, H, W, _p(hv(z)), channels_padded, _stream()), "sos_nchw_to_nhwc_half")
+    _count()
+    return z
+
+
+def accumulate_wgrad(dwt, grad):
+    """grad (R, Cc, kh, kw) += dwt (ntaps, RP, CP) (the weight-gradient kernel's tap-major buffer, padded rows / columns)."""
+    ntaps, RP, CP = dwt.shape
+    R, Cc = grad.shape[0], grad.shape[1]
+    assert grad.is_contiguous() and grad.shape[2] * grad.shape[3] == ntaps and R <= RP and Cc <= CP
+    check(lib().sos_accumulate_wgrad(_p(dwt), ntaps, RP, CP, R, Cc, _p(grad), _stream()), "sos_accumulate_wgrad")
+    _count()
 
 
 def nhwc_to_nchw(x, channels):
