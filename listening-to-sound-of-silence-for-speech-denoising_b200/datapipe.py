@@ -62,3 +62,52 @@ def make_sid_items(audio, noise, snr_db, bits, sr=16000, fps=30.0, norm=0.5, cle
         audio = ops.gate_wave(audio.contiguous(), bits.contiguous(), ratio, 2)
         audio, _, _ = ops.add_signals(audio, noise.contiguous(), torch.as_tensor(snr_db, dtype=torch.float32, device=dev), norm)
     return {"label": bits.float(), "audio": transform.stft_batch(audio)}
+
+
+class WaveformDataset(torch.utils.data.Dataset):
+    """The waveform-only Dataset of SURVEY.md 8f-2: items are RAW crops (what the reference's `__getitem__` has after
+    `librosa.load` and slicing, M2/dataset.py:160-163,203-206), everything else happens in `collate` for the whole batch on the
+    device.  `clips`: list of dicts {"audio": 1-D float array at `sr`, "bitstream": '0101..' ('0' = silent)}; `noises`: list of 1-D
+    float arrays, each at least as long as a clip; `snrs` / `snr_idx` as in the reference (random choice per item when snr_idx is
+    None, M2/dataset.py:198-201).  Clips of one dataset have equal length (the reference slices `data_len_sec`)."""
+
+    def __init__(self, clips, noises, sr=16000, fps=30.0, snrs=SNRS, snr_idx=None, norm=0.5, seed=None):
+        if not clips:
+            raise ValueError("WaveformDataset needs at least one clip")
+        n = len(clips[0]["audio"])
+        for c in clips:
+            if len(c["audio"]) != n:
+                raise RuntimeError("clips of one dataset must have equal length")        # (dataset errors are RuntimeError, M2/dataset.py:307-309)
+            if set(c["bitstream"]) - {"0", "1"}:
+                raise RuntimeError("Invalid bit?")
+        self.clips, self.noises = clips, [torch.as_tensor(x, dtype=torch.float32) for x in noises]
+        self.sr, self.fps, self.snrs, self.snr_idx, self.norm = sr, fps, list(snrs), snr_idx, norm
+        self.rng = random.Random(seed)
+
+    def __len__(self):
+        return len(self.clips)
+
+    def __getitem__(self, i):
+        c = self.clips[i]
+        n = len(c["audio"])
+        noise = self.rng.choice(self.noises)
+        if noise.numel() < n:
+            raise RuntimeError(f"noise track of {noise.numel()} samples is shorter than the {n}-sample clip")
+        start = self.rng.randint(0, noise.numel() - n)
+        snr = self.rng.choice(self.snrs) if self.snr_idx is None else self.snrs[self.snr_idx]
+        return {"audio": torch.as_tensor(c["audio"], dtype=torch.float32), "noise": noise[start:start + n], "snr": float(snr),
+                "bitstream": c["bitstream"], "start": 0}
+
+    def collate(self, batch, device=None, model="joint"):
+        """list of raw items -> the reference's item dict for the whole batch, built on the device (pinned staging, async copies)."""
+        device = device or torch.device("cuda", torch.cuda.current_device())
+        audio = torch.stack([b["audio"] for b in batch]).pin_memory().to(device, non_blocking=True)
+        noise = torch.stack([b["noise"] for b in batch]).pin_memory().to(device, non_blocking=True)
+        snr = [b["snr"] for b in batch]
+        bits = [b["bitstream"] for b in batch]
+        if model == "sid":
+            return make_sid_items(audio, noise, snr, bits, self.sr, self.fps, self.norm)
+        item = make_joint_items(audio, noise, snr, bits, self.sr, self.fps, self.norm)
+        item["bitstream"] = bits
+        item["start"] = [b["start"] for b in batch]
+        return item

@@ -87,3 +87,41 @@ def test_crop_noise_host_logic():
         assert 0 <= float(row[0]) <= 600 or 5000 <= float(row[0]) <= 6600
     with pytest.raises(ValueError):
         datapipe.crop_noise([torch.zeros(100)], 400, 1, torch.device("cpu"))
+
+
+def test_waveform_dataset_host_logic():
+    """datapipe.WaveformDataset: raw crops per item (noise interval, SNR choice), reference-style RuntimeErrors (no GPU needed)."""
+    import numpy as np
+    from sos_b200 import datapipe
+    clips = [{"audio": np.arange(800, dtype=np.float32) + 1000 * i, "bitstream": "0110"} for i in range(3)]
+    noises = [np.arange(5000, dtype=np.float32)]
+    ds = datapipe.WaveformDataset(clips, noises, snr_idx=2, seed=1)
+    assert len(ds) == 3
+    it = ds[1]
+    assert it["snr"] == datapipe.SNRS[2] and it["bitstream"] == "0110" and it["audio"].shape == (800,) and it["noise"].shape == (800,)
+    assert float(it["audio"][0]) == 1000.0 and torch.equal(it["noise"][1:] - it["noise"][:-1], torch.ones(799))
+    ds2 = datapipe.WaveformDataset(clips, noises, seed=5)
+    assert {ds2[0]["snr"] for _ in range(40)} <= set(datapipe.SNRS) and len({ds2[0]["snr"] for _ in range(40)}) > 1
+    with pytest.raises(RuntimeError):
+        datapipe.WaveformDataset(clips + [{"audio": np.zeros(10, np.float32), "bitstream": "0"}], noises)
+    with pytest.raises(RuntimeError):
+        datapipe.WaveformDataset([{"audio": np.zeros(800, np.float32), "bitstream": "01x"}], noises)
+    with pytest.raises(RuntimeError):
+        datapipe.WaveformDataset(clips, [np.zeros(100, np.float32)])[0]
+
+
+def test_wav_io_roundtrip(tmp_path):
+    """pipeline._read_wav / _write_wav: float32 WAV round trip, int16 scaling, stereo -> mono."""
+    import numpy as np
+    from scipy.io import wavfile
+    from sos_b200 import pipeline
+    x = (np.random.default_rng(0).standard_normal(1000) * 0.1).astype(np.float32)
+    p = str(tmp_path / "a.wav")
+    pipeline._write_wav(p, x, 16000)
+    y, sr = pipeline._read_wav(p)
+    assert sr == 16000 and np.array_equal(x, y)
+    wavfile.write(str(tmp_path / "b.wav"), 8000, np.stack([np.full(10, 16384, np.int16), np.full(10, -16384, np.int16)], axis=1))
+    y, sr = pipeline._read_wav(str(tmp_path / "b.wav"))
+    assert sr == 8000 and y.shape == (10,) and np.allclose(y, 0.0)
+    wavfile.write(str(tmp_path / "c.wav"), 8000, np.full(10, 16384, np.int16))
+    assert np.allclose(pipeline._read_wav(str(tmp_path / "c.wav"))[0], 0.5)

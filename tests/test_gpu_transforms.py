@@ -401,3 +401,25 @@ def test_ssnr_metrics_match_reference(cuda, golden_dir):
         assert abs(float(ov[i]) - want[0]) < 2e-4 and abs(float(seg[i]) - want[1]) < 2e-4
     l1 = metrics.metrics_L1(batch["mixed"][0], batch["clean"][0])
     assert abs(l1 - float(np.mean(np.abs(batch["mixed"][0] - batch["clean"][0])))) < 1e-7
+
+
+def test_waveform_dataset_collate(cuda):
+    """WaveformDataset.collate: raw crops -> the reference's item dict on the device; the joint agent trains on it unchanged."""
+    from sos_b200 import agent as ag, datapipe
+    from oracle import synth
+    clips = []
+    for i in range(2):
+        c = synth.make_clip(i, 16000)
+        clips.append({"audio": c["clean"], "bitstream": c["bits"]})
+    noises = [np.random.default_rng(1).standard_normal(40000).astype(np.float32) * 0.2]
+    ds = datapipe.WaveformDataset(clips, noises, seed=0)
+    item = ds.collate([ds[0], ds[1]])
+    assert set(item) == {"mixed", "clean", "noise", "full_noise", "mask", "start", "bitstream"}
+    assert item["mixed"].shape == (2, 2, 256, 1 + 16000 // 158) and item["mask"].shape == item["mixed"].shape
+    assert float(item["mask"].min()) > 0 and float(item["mask"].max()) < 1
+    torch.manual_seed(1)
+    joint = ag.MyAgent(ag.default_config(model="joint", sr=16000, fps=30.0))
+    _, losses = joint.train_func(item)
+    assert all(torch.isfinite(v) for v in losses.values())
+    sid_item = ds.collate([ds[0], ds[1]], model="sid")
+    assert sid_item["label"].shape == (2, 30) and sid_item["audio"].shape == item["mixed"].shape
