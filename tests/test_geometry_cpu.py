@@ -125,3 +125,70 @@ def test_wav_io_roundtrip(tmp_path):
     assert sr == 8000 and y.shape == (10,) and np.allclose(y, 0.0)
     wavfile.write(str(tmp_path / "c.wav"), 8000, np.full(10, 16384, np.int16))
     assert np.allclose(pipeline._read_wav(str(tmp_path / "c.wav"))[0], 0.5)
+
+
+@pytest.fixture()
+def emulated_half(monkeypatch):
+    for name, fn in (("conv_tc", _emul.conv_tc_any), ("conv_wgrad", _emul.conv_wgrad_any), ("pack_taps", _emul.pack_taps),
+                     ("pack_taps_half", _emul.pack_taps_half), ("to_half", _emul.to_half), ("bn_finalize_partial", _emul.bn_finalize_partial),
+                     ("bn_act_apply", _emul.bn_act_apply), ("bn_train_backward_half", _emul.bn_train_backward_half),
+                     ("copy_view", _emul.copy_view), ("reflect_fill", _emul.reflect_fill), ("reflect_fold", _emul.reflect_fold),
+                     ("copy_view_backward", _emul.copy_view_backward), ("init", lambda: None)):
+        monkeypatch.setattr(ops, name, fn)
+
+
+def test_half_path_wiring_cpu(emulated_half):
+    """Host-side wiring of the half-operand path with every kernel replaced by a CPU emulation of its documented semantics:
+    ToHalf -> ConvBNActH (zero-padded dilated conv, padded channel tail 8 -> 16) -> PadCatH (concat + nearest resize + reflect pad)
+    -> ConvBNActH (strided valid conv, PReLU) against nn.Conv2d / BatchNorm2d / PReLU autograd.  Checks handle plumbing, channel
+    padding, the gradient scale (out_scale) and which gradients each node returns; tolerances are those of 11-bit operands."""
+    torch.manual_seed(0)
+    N, H, W = 2, 12, 10
+    x = torch.randn(N, 8, H, W)
+    skip = torch.randn(N, 16, H // 2, W // 2)
+    c1 = torch.nn.Conv2d(8, 16, 3, 1, 2, 2, bias=False)
+    b1 = torch.nn.BatchNorm2d(16)
+    c2 = torch.nn.Conv2d(32, 8, 3, 2, 0, 1, bias=False)
+    b2 = torch.nn.BatchNorm2d(8)
+    pr = torch.nn.PReLU()
+    for m in (b1, b2):
+        m.weight.data.uniform_(0.5, 1.5)
+        m.bias.data.uniform_(-0.3, 0.3)
+    # ---- reference: plain PyTorch
+    xr, sr = x.clone().requires_grad_(True), skip.clone().requires_grad_(True)
+    z1 = torch.relu(b1(c1(xr)))
+    cat = torch.cat([z1, F.interpolate(sr, size=(H, W))], 1)
+    z2 = pr(b2(c2(F.pad(cat, (1, 1, 1, 1), mode="reflect"))))
+    go = torch.randn(z2.shape) * 1e-6                                   # gradient-sized values: exercises the power-of-two scale
+    z2.backward(go)
+    ref = {"x": xr.grad, "skip": sr.grad, "w1": c1.weight.grad, "w2": c2.weight.grad, "g1": b1.weight.grad, "be1": b1.bias.grad,
+           "g2": b2.weight.grad, "be2": b2.bias.grad, "slope": pr.weight.grad}
+    rm1 = b1.running_mean.clone()
+    for p in (c1.weight, c2.weight, b1.weight, b1.bias, b2.weight, b2.bias, pr.weight):
+        p.grad = None
+    for m in (b1, b2):
+        m.reset_running_stats()
+    # ---- half path over the emulated kernels
+    to_nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    xh32, sh32 = to_nhwc(x).requires_grad_(True), to_nhwc(skip).requires_grad_(True)
+    xh, sh = L.ToHalf.apply(xh32, 16), L.ToHalf.apply(sh32, 16)        # channel tail 8 -> 16 zero padded
+    assert ops.is_half_handle(xh) and tuple(xh.shape) == (N, H, W, 16)
+    g1 = L.ConvGeom("zero", 3, 3, 2, 2, 1)
+    h1 = L.ConvBNActH.apply(xh, c1.weight, b1.weight, b1.bias, None, b1.running_mean, b1.running_var, b1.eps, b1.momentum, ops.ACT_RELU, g1, False)
+    assert ops.is_half_handle(h1) and tuple(h1.shape) == (N, H, W, 16)
+    cat_h = L.PadCatH.apply(1, H, W, h1, sh)
+    assert ops.is_half_handle(cat_h) and tuple(cat_h.shape) == (N, H + 2, W + 2, 32)
+    g2 = L.ConvGeom("valid", 3, 3, 1, 1, 2)
+    z = L.ConvBNActH.apply(cat_h, c2.weight, b2.weight, b2.bias, pr.weight, b2.running_mean, b2.running_var, b2.eps, b2.momentum,
+                           ops.ACT_PRELU, g2, True)                     # out_f32: a plain fp32 map
+    assert z.dtype == torch.float32 and not ops.is_half_handle(z) and tuple(z.shape) == (N, z2.shape[2], z2.shape[3], 8)
+    rel = lambda a, b: float((a - b).abs().max() / (b.abs().max() + 1e-30))
+    assert rel(z.permute(0, 3, 1, 2), z2.detach()) < 5e-3
+    assert rel(b1.running_mean, rm1) < 5e-3
+    z.backward(to_nhwc(go))
+    got = {"x": xh32.grad.permute(0, 3, 1, 2), "skip": sh32.grad.permute(0, 3, 1, 2), "w1": c1.weight.grad, "w2": c2.weight.grad,
+           "g1": b1.weight.grad, "be1": b1.bias.grad, "g2": b2.weight.grad, "be2": b2.bias.grad, "slope": pr.weight.grad}
+    errs = {k: rel(got[k], ref[k]) for k in ref}
+    for k in ref:
+        assert got[k] is not None and got[k].shape == ref[k].shape, k
+        assert errs[k] < 2e-2, errs
