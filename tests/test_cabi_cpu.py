@@ -47,6 +47,41 @@ def test_argument_errors_are_reported(built):
     assert rc == -1 and b"null" in lib.sos_last_error()
 
 
+def test_argument_errors_of_the_newer_entry_points(built):
+    """Host-side validation of the half-operand producers, the item builder and the metrics: bad arguments give -1 and a
+    message naming the entry point, before any CUDA call."""
+    lib = built.lib()
+    one = ctypes.c_void_p(16)                                            # a non-null dummy pointer (never dereferenced on these paths)
+    assert lib.sos_to_half(one, 10, 8, one, 12, None, None) == -1 and b"sos_to_half" in lib.sos_last_error()          # cd % 8
+    assert lib.sos_to_half(one, 10, 16, one, 8, None, None) == -1                                                      # cd < cs
+    assert lib.sos_bn_act_half(one, one, 10, 12, one, one, 1, None, None) == -1 and b"channels % 8" in lib.sos_last_error()
+    assert lib.sos_bn_act_half(one, one, 10, 16, one, one, 2, None, None) == -1 and b"PReLU" in lib.sos_last_error()  # slope missing
+    assert lib.sos_add_signals(one, one, None, 4, 100, 0.5, one, one, one, None) == -1 and b"sos_add_signals" in lib.sos_last_error()
+    assert lib.sos_add_signals(one, one, one, 0, 100, 0.5, one, one, one, None) == -1                                  # empty batch
+    assert lib.sos_crm_forward(one, one, one, 2, 0, 0.1, 0.0, None) == -1 and b"sos_crm_forward" in lib.sos_last_error()
+    assert lib.sos_ssnr(one, one, 1, 100, 16000, 0.0, -10.0, 35.0, 1e-10, 0, one, one, None) == -1 and b"sos_ssnr" in lib.sos_last_error()
+    assert lib.sos_ssnr(one, one, 1, 100, 100, 30.0, -10.0, 35.0, 1e-10, 0, one, one, None) == -1 and b"too short" in lib.sos_last_error()
+    assert lib.sos_nchw_to_nhwc_half(one, 1, 2, 4, 4, one, 12, None) == -1 and b"multiple of 8" in lib.sos_last_error()
+    assert lib.sos_accumulate_wgrad(one, 9, 8, 8, 16, 8, one, None) == -1                                              # rows > rows_padded
+    assert lib.sos_pack_taps_half(one, 4, 4, 8, 36, 9, 50, (ctypes.c_int32 * 50)(), one, None) == -1                   # > 49 taps
+    a = built._lib.ConvArgs()
+    a.x, a.wk, a.y = 16, 16, 16
+    dh = (ctypes.c_int32 * 1)(0)
+    a.tap_dh, a.tap_dw = dh, dh
+    a.N, a.H, a.W, a.Cin, a.Cout, a.OH, a.OW, a.ntaps, a.stride = 1, 8, 8, 12, 16, 8, 8, 1, 1
+    a.YH, a.YW, a.Cy, a.osh, a.osw = 8, 8, 16, 1, 1
+    a.force_plan = -1
+    assert lib.sos_conv2d_tc(ctypes.byref(a), None) == -1 and b"multiple of 8" in lib.sos_last_error()                # Cin = 12
+    a.Cin, a.x_dtype = 16, 7
+    assert lib.sos_conv2d_tc(ctypes.byref(a), None) == -1 and b"unknown operand" in lib.sos_last_error()
+    g = built._lib.WgradArgs()
+    g.x, g.dy, g.dw = 16, 16, 16
+    g.tap_dh, g.tap_dw = dh, dh
+    g.N, g.H, g.W, g.Cin, g.Cout, g.OH, g.OW, g.Cdy, g.ntaps, g.stride, g.dtype = 1, 8, 8, 16, 16, 8, 8, 12, 1, 1, 1
+    g.force_plan = -1
+    assert lib.sos_conv2d_wgrad(ctypes.byref(g), None) == -1 and b"dy channel slice" in lib.sos_last_error()           # half: Cdy % 8
+
+
 def test_no_cpu_fallback(built):
     import torch
     if torch.cuda.is_available():
