@@ -26,6 +26,13 @@ constexpr int kHPitch = kCB + 4;   // h_s row pitch (floats): 16-byte aligned ro
 
 __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
 
+// The per-step cluster barrier as an explicit release / acquire pair.  cooperative_groups' cluster.sync() puts a GPU-scope
+// MEMBAR + ERRBAR in front of the barrier (18 % of the forward kernel's stall samples, profiles/r01b_lstm_fwd_cluster_ncu.txt):
+// the exchange only needs the distributed-shared-memory stores ordered at cluster scope, and the split lets the step's global
+// stores (cell, h, gates: nobody in the cluster reads them) be issued between arrive and wait.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // Two IEEE fp32 FMAs in one instruction (sm_100 FFMA2): (d0, d1) += w * (b0, b1).  The recurrent products are issue bound
 // (one SM does 410 k FMAs per time step), so halving the FMA instruction count is what shortens a step.
 __device__ __forceinline__ void ffma2(float& d0, float& d1, float w, float b0, float b1) {
@@ -104,33 +111,23 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_fwd_cluster_kernel(const 
 #pragma unroll
       for (int i = 0; i < 8; ++i) g_s[(ks * kCRows + rg * 4 + a) * (kCB + 1) + bg * 8 + i] = acc[a][i];
     __syncthreads();
-    {
-      float h = 0.f;
-      if (cell_live) {
-        float pre[4];
+    float h = 0.f, ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f;
+    if (cell_live) {
+      float pre[4];
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
-          float v = gxv[qq];
+      for (int qq = 0; qq < 4; ++qq) {
+        float v = gxv[qq];
 #pragma unroll
-          for (int s2 = 0; s2 < kKSplit; ++s2) v += g_s[(s2 * kCRows + qq * kCU + ju) * (kCB + 1) + bu];
-          pre[qq] = v;
-        }
-        const float ig = sigm(pre[0]), fg = sigm(pre[1]), gg = tanhf(pre[2]), og = sigm(pre[3]);
-        const float c = fg * c_reg + ig * gg;
-        c_reg = c;
-        h = og * tanhf(c);
-        cell[(((size_t)t * B + bu) * 2 + d) * H + ju_g] = c;
-        out[((size_t)t * B + bu) * 2 * H + (size_t)d * H + ju_g] = h;
-        float* gp = gates + (((size_t)t * B + bu) * 2 + d) * 4 * H + ju_g;
-        gp[0] = ig;
-        gp[H] = fg;
-        gp[2 * H] = gg;
-        gp[3 * H] = og;
+        for (int s2 = 0; s2 < kKSplit; ++s2) v += g_s[(s2 * kCRows + qq * kCU + ju) * (kCB + 1) + bu];
+        pre[qq] = v;
       }
-      o_s[ju * kCB + bu] = h;
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) gxv[qq] = gxn[qq];
+      ig = sigm(pre[0]); fg = sigm(pre[1]); gg = tanhf(pre[2]); og = sigm(pre[3]);
+      c_reg = fg * c_reg + ig * gg;
+      h = og * tanhf(c_reg);
     }
+    o_s[ju * kCB + bu] = h;
+#pragma unroll
+    for (int qq = 0; qq < 4; ++qq) gxv[qq] = gxn[qq];
     __syncthreads();
     if (step + 1 < T) {
       // broadcast the slice into the "next" h buffer of every CTA of the direction: 16 rows x 8 float4 per destination
@@ -142,8 +139,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) lstm_fwd_cluster_kernel(const 
           *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(o_s + row * kCB + v * 4);
         }
       }
-      cluster.sync();                                // release / acquire: the slices are visible cluster-wide
+      cluster_arrive();                              // release: this thread's slice stores are ordered before the barrier
     }
+    if (cell_live) {                                 // the step's outputs: global stores issued under the barrier's latency
+      cell[(((size_t)t * B + bu) * 2 + d) * H + ju_g] = c_reg;
+      out[((size_t)t * B + bu) * 2 * H + (size_t)d * H + ju_g] = h;
+      float* gp = gates + (((size_t)t * B + bu) * 2 + d) * 4 * H + ju_g;
+      gp[0] = ig;
+      gp[H] = fg;
+      gp[2 * H] = gg;
+      gp[3 * H] = og;
+    }
+    if (step + 1 < T) cluster_wait();                // acquire: every CTA's slice of the next h is in this CTA's buffer
   }
 }
 
@@ -241,7 +248,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) lstm_bwd_cluster_kernel(const 
           }
         }
       }
-      cluster.sync();                                // every CTA's partial slices have arrived
+      cluster_arrive();
+      cluster_wait();                                // every CTA's partial slices have arrived
     }
 #pragma unroll
     for (int half = 0; half < kPairs; ++half) {
