@@ -77,7 +77,12 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.begin = index, [], False, 0
+
+    def mark_begin(self):
+        """Only samples taken from now on count (the sampler itself is started BEFORE the warm-up steps: spawning nvidia-smi from
+        a large process holds the interpreter for ~0.1 s, which must not fall into the timed region)."""
+        self.begin = len(self.samples)
 
     def run(self):
         try:
@@ -96,6 +101,7 @@ class ClockSampler(threading.Thread):
         self.stop_flag = True
         if hasattr(self, "proc"):
             self.proc.kill()
+        self.samples = self.samples[self.begin:] or self.samples
         sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
@@ -220,6 +226,9 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def timed(src, e2e, steps):
+        import gc
+        gc.collect()
+        gc.disable()                  # no collector pauses while the host feeds the GPU (the step keeps ~10^4 tensors alive)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -229,6 +238,7 @@ def run_gpu(args):
         e1.record()
         host_ms[0] = 1e3 * (time.perf_counter() - h0) / steps          # host time to ENQUEUE a step (no synchronisation inside)
         barrier()
+        gc.enable()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -236,11 +246,13 @@ def run_gpu(args):
 
     host_ms = [0.0]
 
-    for _ in range(max(args.warmup, 3)):
-        step(resident, False)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step(resident, False)
+    if sampler:
+        sampler.mark_begin()
     ops.profile_start()
     n0 = _lib.launch_count
     ms = timed(resident, False, args.steps)

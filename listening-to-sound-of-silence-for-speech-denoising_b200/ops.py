@@ -32,18 +32,33 @@ def _count(n=1):
 
 # ----------------------------------------------------------------------------------------------- per-kernel timing (bench.py)
 _prof = None
+_pool, _pool_next = [], 0
 
 
-def profile_start():
-    """Start recording a CUDA event pair (on the launching stream) around every tensor-core / transform launch."""
-    global _prof
+def profile_start(max_events=16384):
+    """Start recording a CUDA event pair (on the launching stream) around every tensor-core / transform launch.  The events come
+    from a pool created here, outside the timed region: constructing ~1000 event objects per step on the fly costs the host
+    several ms per step, enough to make a GPU-bound step host-bound."""
+    global _prof, _pool_next
+    while len(_pool) < max_events:
+        _pool.append(torch.cuda.Event(enable_timing=True))
+    _pool_next = 0
     _prof = []
+
+
+def _event():
+    global _pool_next
+    if _pool_next < len(_pool):
+        e = _pool[_pool_next]
+        _pool_next += 1
+        return e
+    return torch.cuda.Event(enable_timing=True)
 
 
 def _pb():
     if _prof is None:
         return None
-    e = torch.cuda.Event(enable_timing=True)
+    e = _event()
     e.record()
     return e
 
@@ -51,7 +66,7 @@ def _pb():
 def _pe(name, e0, flops=0.0, nbytes=0.0):
     if e0 is None:
         return
-    e1 = torch.cuda.Event(enable_timing=True)
+    e1 = _event()
     e1.record()
     _prof.append((name, e0, e1, flops, nbytes))
 
