@@ -26,3 +26,16 @@ def cuda():
     from sos_b200 import ops
     ops.init()
     return torch.device("cuda:0")
+
+
+def record(name, **values):
+    """Parity numbers of the GPU tests, captured (not only printed): one JSON line per call appended to
+    gpurun_out/parity.jsonl (copied to profiles/parity_rNN.txt when a round's numbers are committed)."""
+    import json
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity.jsonl"), "a") as f:
+            f.write(json.dumps({"test": name, **{k: (float(v) if hasattr(v, "__float__") else v) for k, v in values.items()}}) + "\n")
+    except OSError:
+        pass

@@ -149,3 +149,52 @@ def test_ssnr_oracle_matches_reference(golden_dir):
         a = om.metrics_ssnr(c["clean"], c["mixed"], eps=eps)
         b = om.metrics_ssnr_shift(c["clean"], c["mixed"], eps=eps)
         assert abs(a[0] - ov) < 1e-9 and abs(a[1] - seg) < 1e-9 and abs(b[0] - ov_s) < 1e-9 and abs(b[1] - seg_s) < 1e-9
+
+
+def full_size_inputs(L):
+    """The inputs oracle/make_golden_full.py fed to the reference, rebuilt from the same seeds (deterministic numpy)."""
+    from oracle import synth, transform as otf
+    clips = synth.make_batch(2, length=L, sr=16000 if L == 32000 else 14000, start=40)
+    spec = {k: torch.tensor(np.ascontiguousarray(otf.stft_batch(clips[k]))) for k in ("mixed", "noise", "clean", "full_noise")}
+    return spec, torch.tensor(clips["label"])
+
+
+def test_oracle_matches_reference_at_benchmark_size(golden_dir):
+    """oracle.nets at the BENCHMARKED clip size (T = 203: 2 s @ 16 kHz, BASELINE configs[1]) against tests/golden/nets_full.npz
+    (written by oracle/make_golden_full.py running the reference's own M1 / M2 networks.py, training mode, fp32): logits, losses,
+    n_pred, mask and the stored gradient slices -- including the dilation-32 layers, which a T = 71 map never exercises."""
+    from oracle import nets, transform as otf
+    from oracle.make_golden_full import grad_slice
+    g = np.load(golden_dir + "/nets_full.npz")
+    spec, lab = full_size_inputs(32000)
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in nets.synth_state_dict(nets.sid_shapes(), 3).items()}
+    logits = nets.sid_forward(sd, spec["mixed"], lab.shape[1], training=True)
+    loss = F.binary_cross_entropy_with_logits(logits, lab)
+    loss.backward()
+    assert float((logits.detach() - torch.tensor(g["T203_sid_logits"])).abs().max()) < 2e-4
+    assert abs(float(loss.detach()) - float(g["T203_sid_loss"])) < 1e-5
+    n = 0
+    for key in g.files:
+        if key.startswith("T203_sid_grad:"):
+            want = torch.tensor(g[key])
+            got = torch.tensor(grad_slice(sd[key.split(":", 1)[1]].grad.numpy()))
+            assert float((got - want).abs().max()) < 5e-3 * float(want.abs().max()) + 1e-8, key
+            n += 1
+    assert n >= 9
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in nets.synth_state_dict(nets.joint_shapes(), 4).items()}
+    n_pred, mask = nets.joint_forward(sd, spec["mixed"], spec["noise"], training=True)
+    rec = otf.batch_fast_icRM_sigmoid(spec["mixed"], mask)
+    l1, l2 = F.mse_loss(n_pred, spec["full_noise"]), F.mse_loss(rec, spec["clean"])
+    (l1 + l2).backward()
+    assert float((mask.detach()[..., ::2] - torch.tensor(g["T203_joint_plain_mask"])).abs().mean()) < 1e-5
+    assert float((n_pred.detach()[..., ::2] - torch.tensor(g["T203_joint_plain_npred"])).abs().max()) < 1e-3 * float(np.abs(g["T203_joint_plain_npred"]).max())
+    assert abs(float(l1.detach()) - float(g["T203_joint_plain_loss1"])) < 1e-4 and abs(float(l2.detach()) - float(g["T203_joint_plain_loss2"])) < 1e-3
+    n = 0
+    for key in g.files:
+        if key.startswith("T203_joint_plain_grad:"):
+            want = torch.tensor(g[key])
+            got = torch.tensor(grad_slice(sd[key.split(":", 1)[1]].grad.numpy()))
+            assert float((got - want).abs().max()) < 2e-2 * float(want.abs().max()) + 1e-8, key
+            n += 1
+    assert n >= 18
