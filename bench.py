@@ -173,6 +173,33 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------- this repo's arm (GPU)
+def cpu_forward_b1():
+    """BASELINE configs[0]: ONE 2 s clip, SID + JointModel forward only, eval mode, on the host cores (oracle port)."""
+    import torch
+    from oracle import nets, transform as otf
+    torch.set_num_threads(os.cpu_count() or 1)
+    data = synth_batch(1)
+    sid_sd, jt_sd = nets.synth_state_dict(nets.sid_shapes(), 3), nets.synth_state_dict(nets.joint_shapes(), 4)
+    ratio = SR / FPS
+
+    def fwd():
+        with torch.no_grad():
+            mixed = torch.tensor(np.ascontiguousarray(otf.stft_batch(data["mixed"])))
+            logits = nets.sid_forward(sid_sd, mixed, data["label"].shape[1], training=False)
+            bits = (torch.sigmoid(logits) >= 0.5).numpy().astype(np.uint8)
+            from oracle.gating import bits_to_sample_mask
+            mask = bits_to_sample_mask(LENGTH, ratio, "".join(str(int(b)) for b in bits[0])).astype(np.float32)
+            noise = torch.tensor(np.ascontiguousarray(otf.stft_batch(data["mixed"] * mask[None])))
+            _, m = nets.joint_forward(jt_sd, mixed, noise, training=False)
+            rec = otf.batch_fast_icRM_sigmoid(mixed, m)
+            otf.istft_batch(rec.numpy())
+    fwd()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        fwd()
+    return (time.perf_counter() - t0) / 3
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -203,9 +230,9 @@ def run_gpu(args):
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
     out_host = {"wave": torch.empty(B, 158 * (LENGTH // 158), dtype=torch.float32).pin_memory(), "loss": torch.empty(3, dtype=torch.float32).pin_memory()}
     d2h_bytes = sum(v.numel() * v.element_size() for v in out_host.values())
+    trainer = ag.GraphedTrainStep(sid, joint, B, LENGTH, SR, FPS, warmup=2) if args.graph else None
 
-    def step(src, e2e):
-        d = {k: v.to(dev, non_blocking=True) for k, v in src.items()} if e2e else src
+    def eager_step(d):
         # the four transforms of a training item (M2/dataset.py:234-237) as ONE launch over the 4 x B waveforms
         gated = tools.gate_noise(d["mixed"], ratio, d["bits"])
         spec = transform.stft_batch(torch.cat([d["mixed"], gated, d["clean"], d["full_noise"]]))
@@ -213,11 +240,16 @@ def run_gpu(args):
         _, l_sid = sid.train_func({"audio": mixed, "label": d["label"]})
         _, l_jt = joint.train_func({"mixed": mixed, "noise": noise, "clean": clean, "full_noise": full})
         wave = transform.istft_batch(joint.last_rec.detach())
+        return {"losses": torch.stack([l_sid["bce"].detach(), l_jt["stage1"].detach(), l_jt["stage2"].detach()]), "wave": wave}
+
+    def step(src, e2e):
+        d = {k: v.to(dev, non_blocking=True) for k, v in src.items()} if e2e else src
+        out = trainer(d["mixed"], d["clean"], d["full_noise"], d["bits"], d["label"]) if trainer else eager_step(d)
         if e2e:
-            out_host["loss"].copy_(torch.stack([l_sid["bce"].detach(), l_jt["stage1"].detach(), l_jt["stage2"].detach()]), non_blocking=True)
-            out_host["wave"].copy_(wave, non_blocking=True)
+            out_host["loss"].copy_(out["losses"], non_blocking=True)
+            out_host["wave"].copy_(out["wave"], non_blocking=True)
             torch.cuda.current_stream().synchronize()          # the user holds the step's result before the next step
-        return wave
+        return out
 
     def barrier():
         torch.cuda.synchronize()
@@ -228,7 +260,7 @@ def run_gpu(args):
     def timed(src, e2e, steps):
         import gc
         gc.collect()
-        gc.disable()                  # no collector pauses while the host feeds the GPU (the step keeps ~10^4 tensors alive)
+        gc.disable()                  # no collector pauses while the host feeds the GPU
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -249,20 +281,35 @@ def run_gpu(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    n0 = _lib.launch_count
+    for _ in range(max(args.warmup, 3) + (1 if trainer else 0)):       # (graph mode: 2 eager steps, the capture, then replays)
         step(resident, False)
+    warm_launches = _lib.launch_count - n0
     if sampler:
         sampler.mark_begin()
-    ops.profile_start()
+    # ---- the metric: NO per-launch instrumentation inside this region
     n0 = _lib.launch_count
     ms = timed(resident, False, args.steps)
     enqueue_ms = host_ms[0]
     launches = _lib.launch_count - n0
-    prof = ops.profile_stop()
+    if trainer:                       # replays do not pass through the Python binding: count what the captured graphs hold
+        launches = (trainer.launches_per_step + 4) * args.steps
     clocks = sampler.summary() if sampler else None
     step(pinned, True)
     ms_e2e = timed(pinned, True, args.steps)
     clips = world * B * args.steps
+
+    # ---- per-kernel breakdown in a SEPARATE eager pass (CUDA-event pair around every tensor-core / transform launch, weight
+    #      gradients on the main stream so that an event pair brackets exactly one kernel)
+    os.environ["SOS_SYNC_WGRAD"] = "1"
+    eager_step(resident)
+    ops.profile_start()
+    prof_steps = 2
+    for _ in range(prof_steps):
+        eager_step(resident)
+    prof = ops.profile_stop()
+    del os.environ["SOS_SYNC_WGRAD"]
+    barrier()
 
     if rank == 0:
         peaks = {}
@@ -273,76 +320,109 @@ def run_gpu(args):
         bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         peak_src = "measured (MEASURED_PEAKS.json, sustained bf16 cuBLAS)" if peaks else "fallback (B200_PROFILING.md)"
-        # cuBLAS fp16 (fp32 accumulate) on the same box, for scale: the conv kernels issue tcgen05 kind::f16 like it does
-        a = torch.randn(8192, 8192, device=dev).half()
-        b = torch.randn(8192, 8192, device=dev).half()
-        for _ in range(3):
-            a @ b
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
-        for _ in range(10):
-            a @ b
-        t1.record()
-        torch.cuda.synchronize()
-        f16_peak = 10 * 2 * 8192 ** 3 / (t0.elapsed_time(t1) * 1e-3) / 1e12
-        del a, b
         kern = {}
         for name, rec in prof.items():
             if rec["ms"] > 0:
-                kern[name] = {"launches": rec["n"], "ms_per_step": rec["ms"] / args.steps, "avg_launch_us": 1e3 * rec["ms"] / max(rec["n"], 1),
+                kern[name] = {"launches_per_step": rec["n"] / prof_steps, "ms_per_step": rec["ms"] / prof_steps, "avg_launch_us": 1e3 * rec["ms"] / max(rec["n"], 1),
                               "tflops": rec["flops"] / (rec["ms"] * 1e-3) / 1e12 if rec["flops"] else None,
                               "gbs": rec["bytes"] / (rec["ms"] * 1e-3) / 1e9 if rec["bytes"] else None}
-        # the dominant kernel: tapgemm_f16_kernel serves the forward convolutions AND their data gradients (same kernel, flipped
-        # taps); wgrad_f16_kernel is the other tensor-core kernel.  The weight gradients run on a second stream next to the data
-        # gradients / BatchNorm backward, so the event time of a backward launch includes waiting for the other stream's kernel:
-        # the roofline is quoted on the kernel's FORWARD launches (nothing else runs then); `kernels` lists every family.
-        fams = {"tapgemm_f16_kernel (conv forward + data gradient), forward launches": ("conv_fwd",)}
-        roofline, best_ms = None, -1.0
+        for name in ("stft", "istft"):
+            if name in kern and kern[name]["gbs"]:
+                kern[name]["hbm_frac"] = kern[name]["gbs"] / hbm_peak
+        # the dominant kernel: tapgemm_f16_kernel = every convolution's forward AND data gradient (same kernel, flipped taps).
+        # roofline = ALL its launches of a step (algorithmic FLOPs / summed launch durations)
         ncu = {}
         try:
             ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         except (OSError, ValueError):
             pass
-        for fam, names in fams.items():
-            recs = [prof[n] for n in names if n in prof and prof[n]["ms"] > 0]
-            if not recs:
-                continue
+        recs = [prof[n] for n in ("conv_fwd", "conv_dgrad") if n in prof and prof[n]["ms"] > 0]
+        roofline = None
+        if recs:
             fl, tms, nl = sum(r["flops"] for r in recs), sum(r["ms"] for r in recs), sum(r["n"] for r in recs)
-            if tms > best_ms:
-                best_ms = tms
-                ach = fl / (tms * 1e-3) / 1e12
-                roofline = {"bound": "tensor", "kernel": fam, "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
-                            "traffic": ncu.get(fam.split(" ")[0], {}).get("dram_bytes_per_launch"),
-                            "traffic_note": ncu.get(fam.split(" ")[0], {}).get("note"),
-                            "launches": nl, "avg_launch_us": 1e3 * tms / nl, "flops_per_launch": fl / nl,
-                            "peak_source": peak_src + "; the kernel issues tcgen05 kind::f16 (same rate as bf16)",
-                            "f16_cublas_tflops_measured_here": f16_peak, "frac_of_f16_cublas": ach / f16_peak,
-                            "share_of_step": sum(prof[n]["ms"] for n in ("conv_fwd", "conv_dgrad") if n in prof) / ms,
-                            "share_note": "forward + data-gradient launches of this kernel (event time) over the step"}
-        if "stft" in kern and kern["stft"]["gbs"]:
-            kern["stft"]["hbm_frac"] = kern["stft"]["gbs"] / hbm_peak
-        cpu = None
+            ach = fl / (tms * 1e-3) / 1e12
+            tr = ncu.get("tapgemm_f16_kernel", {})
+            roofline = {"bound": "tensor", "kernel": "tapgemm_f16_kernel (all launches of a step: conv forward + data gradient)",
+                        "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
+                        "traffic": tr.get("dram_bytes_per_launch"), "traffic_note": tr.get("note"),
+                        "launches_per_step": nl / prof_steps, "avg_launch_us": 1e3 * tms / nl, "flops_per_launch": fl / nl,
+                        "peak_source": peak_src + "; the kernel issues tcgen05 kind::f16 (same rate as bf16)",
+                        "ms_per_step": tms / prof_steps, "share_of_step": (tms / prof_steps) / (ms / args.steps),
+                        "measured": "CUDA events around every launch in a separate eager pass (not inside the timed `value` region)"}
+        # whole-step conv fraction: ALL algorithmic conv FLOPs of the step (fwd + dgrad + wgrad = 3 x 506.45 GFLOP per clip,
+        # SURVEY 8d) over the step time, against the same peak
+        conv_tflop_per_clip = 3 * 506.45e-3
+        step_conv_frac = B * conv_tflop_per_clip / (ms / args.steps * 1e-3) / bf16_peak
+        cpu, extra = None, None
         if world == 1 and not args.no_cpu_baseline:
             cstep, n = cpu_step_factory(args.ref_batch)
             cstep()                                        # warm-up (thread pools, allocator)
             t0 = time.perf_counter()
-            for _ in range(3):
+            reps = 2
+            for _ in range(reps):
                 cstep()
-            dt = (time.perf_counter() - t0) / 3
-            cpu = {"value": n / dt, "unit": "clips/s", "cores": os.cpu_count() or 1, "kind": "port",
-                   "sample": f"{n}-clip steps of the same workload (BatchNorm over {n} clips), 1 warm-up + 3 timed, {dt:.2f} s per step"}
+            dt = (time.perf_counter() - t0) / reps
+            cpu = {"value": n / dt, "unit": "clips/s", "cores": os.cpu_count() or 1, "kind": "port", "same_config": n == B,
+                   "sample": f"{n}-clip steps of the same workload (BatchNorm over {n} clips; {B} clips would need ~2 GB of host memory per clip "
+                             f"for the fp32 autograd graph), 1 warm-up + {reps} timed, {dt:.2f} s per step"}
+        if world == 1 and not args.no_extra:
+            extra = run_extra(dev, sid.net, joint.net, not args.no_cpu_baseline)
         print(json.dumps({
             "metric": METRIC, "value": clips / (ms * 1e-3), "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 conv operands (11-bit significand, as TF32), fp32 accumulate; fp32 elsewhere",
             "data": "synthetic", "host_enqueue_ms_per_step": enqueue_ms,
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": world * B, "samples_per_clip": LENGTH, "frames": 1 + LENGTH // 158,
-                       "parallelism": f"dp{world} (NCCL all-reduce of the flat gradient buffers)" if world > 1 else "single GPU",
+                       "parallelism": f"dp{world} (NCCL all-reduce of the flat gradient buffers, SID's overlapped with the Joint step)" if world > 1 else "single GPU",
+                       "cuda_graph": bool(trainer),
                        "l2": "no explicit flush: the step's activation working set (tens of GB) is far larger than the 126 MB L2"},
             "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": "clips/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kern, "cpu_baseline": cpu}))
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "step_conv_frac": step_conv_frac,
+            "step_conv_frac_note": f"{B} clips x 1.519 TFLOP (conv fwd + dgrad + wgrad) / ms_per_step / {bf16_peak:.1f} TFLOP/s",
+            "kernels": kern, "cpu_baseline": cpu, "extra": extra}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_extra(dev, sid_net, joint_net, with_cpu):
+    """The other BASELINE configs, measured in the same run (parity-test cases, not the headline): configs[0] one clip forward
+    (GPU latency + the CPU port's), configs[3] forward-only sweep, configs[4] 10 s clips x 16 with chunked STFT / streaming OLA."""
+    import torch
+    from sos_b200 import pipeline
+    sid_net.eval()
+    joint_net.eval()
+    res = {"infer_sweep": []}
+
+    def run(B, L, fpc=None, steps=5, graph=True):
+        wave = torch.from_numpy(synth_batch(min(B, 32), L)["mixed"]).repeat((B + 31) // 32, 1)[:B].contiguous().to(dev)
+        fn = pipeline.GraphedDenoiser(sid_net, joint_net, B, L, SR, FPS, frames_per_chunk=fpc) if graph else \
+            (lambda w: pipeline.denoise(w, sid_net, joint_net, SR, FPS, frames_per_chunk=fpc))
+        for _ in range(3):
+            fn(wave)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn(wave)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        del fn
+        torch.cuda.empty_cache()
+        return {"batch": B, "samples_per_clip": L, "ms_per_batch": ms, "clips_per_s": B / (ms * 1e-3), "cuda_graph": graph}
+
+    with torch.no_grad():
+        for B in (1, 8, 32, 128, 512):
+            res["infer_sweep"].append(run(B, LENGTH, steps=10 if B <= 32 else 3))
+        res["config0_single_clip_forward"] = dict(res["infer_sweep"][0])
+        res["config4_longform_10s_x16"] = run(16, 160000, fpc=256, steps=3)
+    if with_cpu:
+        dt = cpu_forward_b1()
+        res["config0_single_clip_forward"]["cpu_port_ms"] = 1e3 * dt
+        res["config0_single_clip_forward"]["cpu_cores"] = os.cpu_count() or 1
+    sid_net.train()
+    joint_net.train()
+    return res
 
 
 def run_infer(args):
@@ -410,12 +490,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sos_b200", choices=["sos_b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="clips per GPU")
-    ap.add_argument("--ref-batch", type=int, default=2, help="clips per step of the CPU arm (a bounded sample of the workload)")
+    ap.add_argument("--ref-batch", type=int, default=8, help="clips per step of the CPU arm (a bounded sample of the workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[0]/[3]/[4] forward-only measurements")
     ap.add_argument("--workload", default="train", choices=["train", "infer"], help="train = BASELINE configs[1] (default, the metric); "
                     "infer = forward-only inference at --batch / --length")
     ap.add_argument("--length", type=int, default=LENGTH, help="samples per clip (infer workload)")
-    ap.add_argument("--graph", type=int, default=1, help="infer workload: replay the forward pass as one CUDA graph (pipeline.GraphedDenoiser)")
+    ap.add_argument("--graph", type=int, default=1, help="replay the step as CUDA graphs (train: agent.GraphedTrainStep; infer: pipeline.GraphedDenoiser)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

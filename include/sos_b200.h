@@ -92,6 +92,12 @@ int sos_bce_logits_fwd_bwd(const float* logits, const float* labels, int64_t n, 
 /* optim.Adam(lr) defaults (M2/agent.py:167-170, M1/agent.py:175-183) over one flat buffer; step >= 1. */
 int sos_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, int64_t step, float grad_scale, cudaStream_t stream);
+/* The same update with the optimiser clock in device memory, so that a captured CUDA graph of the training step (agent.py:
+ * GraphedTrainStep) replays correctly: state = float[4] {lr, step, lr / (1 - beta1^step), 1 / sqrt(1 - beta2^step)}; the call
+ * advances state[1] by one and refreshes state[2..3] before the update.  The host sets state[0] (StepLR, M2/agent.py:108-111)
+ * and state[1] (checkpoint restore).  n % 4 == 0, buffers 16-byte aligned. */
+int sos_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float* state, float beta1,
+                      float beta2, float eps, float grad_scale, cudaStream_t stream);
 
 /* In-place round-to-nearest of fp32 values to TF32 (10-bit mantissa).  The tensor-core GEMMs below read TF32 operands by
  * TRUNCATING fp32; every producer of such an operand (packed weights, network inputs, BatchNorm outputs, gradient maps)
@@ -242,6 +248,9 @@ typedef struct sos_conv_args {
 #define SOS_DTYPE_TF32 0
 #define SOS_DTYPE_F16 1
 int sos_conv_stats_rows(void);   /* upper bound of *stats_rows_out (4 x SM count) */
+/* Plan cache (SURVEY 8b sos_plan_*): the planner result, MMA program and tensor-map geometry of sos_conv2d_tc are computed once
+ * per distinct (shapes, taps, types) key and reused; tensor maps are re-encoded only when a base pointer changes. */
+void sos_plan_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries);
 int sos_conv2d_tc(const sos_conv_args* args, cudaStream_t stream);
 
 /* Weight gradient of the same operator (split over pixels, accumulated with fp32 atomics):

@@ -57,6 +57,8 @@ _SIGS = {
     "sos_bce_logits_fwd_bwd": (C.c_int, [c_f, c_f, i64, c_f, c_f, C.c_float, S]),
     "sos_round_tf32": (C.c_int, [c_f, i64, S]),
     "sos_adam_step": (C.c_int, [c_f, c_f, c_f, c_f, i64, C.c_float, C.c_float, C.c_float, C.c_float, i64, C.c_float, S]),
+    "sos_adam_step_dev": (C.c_int, [c_f, c_f, c_f, c_f, i64, c_f, C.c_float, C.c_float, C.c_float, C.c_float, S]),
+    "sos_plan_cache_stats": (None, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "sos_bn_partial_blocks": (C.c_int, [i64, i64]),
     "sos_bn_stats": (C.c_int, [c_f, i64, i64, c_f, S]),
     "sos_bn_finalize": (C.c_int, [c_f, i64, i64, c_f, c_f, C.c_float, C.c_float, c_f, c_f, c_f, c_f, c_f, c_f, S]),

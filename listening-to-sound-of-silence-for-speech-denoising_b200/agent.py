@@ -77,9 +77,32 @@ class FlatAdam(object):
         self.step_count = 0
         self.group = process_group
         self.n_real = n
+        # the optimiser clock lives on the device (sos_adam_step_dev): [lr, step, lr / (1 - b1^step), 1 / sqrt(1 - b2^step)], so a
+        # captured CUDA graph of the step replays with the right bias correction; the host mirrors step_count for checkpoints
+        self.state = torch.tensor([lr, 0.0, 0.0, 0.0], device=dev, dtype=torch.float32)
+        self._state_lr = lr
+        self.broadcast()
+
+    def broadcast(self):
+        """Data parallelism needs bit-identical replicas: rank 0's parameters (and optimiser moments) overwrite every other
+        rank's, at construction and after a checkpoint is loaded (no reliance on identical seeds)."""
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(self.group) > 1:
+            for t in (self.flat_param, self.exp_avg, self.exp_avg_sq, self.state):
+                torch.distributed.broadcast(t, 0, group=self.group)
+
+    def sync_clock(self):
+        """Push a host-side change of the learning rate (StepLR) or of the step count (checkpoint restore) to the device clock.
+        Called OUTSIDE captured regions; a no-op (no launch) when nothing changed."""
+        lr = self.param_groups[0]["lr"]
+        if lr != self._state_lr:
+            self.state[0:1].fill_(lr)
+            self._state_lr = lr
 
     def zero_grad(self, set_to_none=False):
         self.flat_grad.zero_()
+        self.zero_grad_views()
+
+    def zero_grad_views(self):
         for p, o in zip(self.params, self.offsets):            # autograd may have replaced .grad; re-attach the views
             if p.grad is None or p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * o:
                 p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
@@ -94,12 +117,22 @@ class FlatAdam(object):
                 torch.distributed.all_reduce(self.flat_grad, group=self.group)        # ncclAllReduce(sum) over NVLink
         return world
 
-    def step(self):
-        world = self.exchange()
+    def step(self, exchange=True, world=None):
+        """exchange=False: the caller has already all-reduced the flat gradient (or captured this call in a CUDA graph, where
+        the collective stays outside) and passes the world size."""
+        if exchange:
+            world = self.exchange()
+        elif world is None:
+            world = 1
+        self.sync_clock()
+        self.apply(world)
+
+    def apply(self, world=1):
+        """The update itself: two launches (clock tick + fused Adam over the flat buffers); graph-capturable."""
         self.step_count += 1
         g = self.param_groups[0]
-        ops.adam_step(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, g["lr"], self.step_count, g["betas"][0],
-                      g["betas"][1], g["eps"], grad_scale=1.0 / world)
+        ops.adam_step_dev(self.flat_param, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.state, g["betas"][0], g["betas"][1], g["eps"],
+                          grad_scale=1.0 / world)
 
     # torch.optim-shaped checkpoint: {"state": {i: {step, exp_avg, exp_avg_sq}}, "param_groups": [...]}
     def state_dict(self):
@@ -124,6 +157,9 @@ class FlatAdam(object):
             self.step_count = int(float(st["step"]))
             self.exp_avg[o:o + p.numel()].copy_(st["exp_avg"].reshape(-1))
             self.exp_avg_sq[o:o + p.numel()].copy_(st["exp_avg_sq"].reshape(-1))
+        self.state[0:1].fill_(self.param_groups[0]["lr"])
+        self.state[1:2].fill_(float(self.step_count))
+        self._state_lr = self.param_groups[0]["lr"]
 
 
 class StepLR(object):
@@ -176,6 +212,9 @@ class BaseAgent(object):
         self.set_loss_function()
         self.set_optimizer(config)
         self.last_losses = {}
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            for b in self.net.buffers():                        # BatchNorm running statistics start identical on every rank as well
+                torch.distributed.broadcast(b, 0)
 
     # -- reference: nn.DataParallel(net.cuda()) when several GPUs are visible.  Here: this process owns ONE GPU; when
     #    torch.distributed is initialised every rank builds the same net (same seed) and FlatAdam all-reduces gradients.
@@ -191,6 +230,8 @@ class BaseAgent(object):
 
     def save_ckpt(self, name=None):
         path = os.path.join(self.model_dir, ("ckpt_epoch{}.pth".format(self.clock.epoch)) if name is None else "{}.pth".format(name))
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_rank() != 0:
+            return path                                         # replicas are identical: rank 0 writes the file
         torch.save({"clock": self.clock.make_checkpoint(),
                     "model_state_dict": {k: v.detach().cpu().clone() for k, v in self.net.state_dict().items()},
                     "optimizer_state_dict": self.optimizer.state_dict(),
@@ -205,16 +246,22 @@ class BaseAgent(object):
         ck = torch.load(path, map_location="cpu")
         with torch.no_grad():                                   # copy INTO the flat views (keeps the optimiser's aliasing)
             own = self.net.state_dict()
+            missing, unexpected = sorted(set(own) - set(ck["model_state_dict"])), sorted(set(ck["model_state_dict"]) - set(own))
+            if missing or unexpected:                           # strict, like the reference's load_state_dict (M2/agent.py:89)
+                raise RuntimeError("Error(s) in loading state_dict: missing keys {}, unexpected keys {}".format(missing, unexpected))
             for k, v in ck["model_state_dict"].items():
                 own[k].copy_(v)
+        L.weights_changed()
         self.optimizer.load_state_dict(ck["optimizer_state_dict"])
+        self.optimizer.broadcast()
         self.scheduler.load_state_dict(ck["scheduler_state_dict"])
         self.clock.restore_checkpoint(ck["clock"])
 
     def forward(self, data):
         raise NotImplementedError
 
-    def update_network(self, loss_dict):
+    def backward(self, loss_dict):
+        """zero_grad + backward of the summed losses (M2/agent.py:101-105) into the flat gradient buffer; graph-capturable."""
         loss = sum(loss_dict.values())
         self.optimizer.zero_grad()
         if os.environ.get("SOS_SYNC_WGRAD"):
@@ -222,7 +269,11 @@ class BaseAgent(object):
         else:
             with L.async_wgrad():                              # conv weight gradients on a side stream, joined on exit
                 loss.backward()
+
+    def update_network(self, loss_dict):
+        self.backward(loss_dict)
         self.optimizer.step()
+        L.weights_changed()
 
     def update_learning_rate(self):
         self.scheduler.step(self.clock.epoch)
@@ -321,6 +372,105 @@ class SIDAgent(BaseAgent):
                 ok += int((pred == _dev(data["label"], self.device)).sum())
                 n += pred.numel()
         return ok / max(n, 1)
+
+
+class GraphedTrainStep(object):
+    """BASELINE configs[1] -- one training step of BOTH models on a batch of waveforms -- as CUDA-graph replays.
+
+        step = GraphedTrainStep(sid_agent, joint_agent, batch, length, sr, fps)
+        out = step(mixed, clean, full_noise, bits, label)     # (B, L) fp32 x 3, (B, n_bits) uint8, (B, n_bits) fp32 device tensors
+        out["losses"] (3,) = bce, stage1, stage2;  out["wave"] (B, 158 (T-1)) = iSTFT of the recovered spectrogram
+
+    The eager step enqueues ~1000 kernels from Python (tens of ms of host time: the GPU would wait for the host on a slower CPU,
+    and data-parallel ranks would wait for the slowest host).  Here the work is captured once, after `warmup` eager steps, into
+    two graphs and replayed with one launch each:
+        graph 1: silent-interval gate -> 4 x STFT (one launch) -> SID forward, BCE, backward (M1/agent.py:185-206)
+        graph 2: JointModel forward, cRM recovery, 2 x MSE, backward (M2/agent.py:176-190, 101-105) -> iSTFT of the recovery
+    The data-parallel exchange stays outside the graphs: SID's flat gradient is all-reduced (NCCL, its own stream) WHILE graph 2
+    runs; the Joint gradient follows; then the two fused Adam updates (device-resident step clock, FlatAdam.apply).
+    The returned tensors are static buffers of the graphs: consume (or copy) them before the next call."""
+
+    def __init__(self, sid_agent, joint_agent, batch, length, sr=16000, fps=30.0, n_bits=None, warmup=3):
+        self.sid, self.joint = sid_agent, joint_agent
+        dev = sid_agent.device
+        self.ratio = sr / fps
+        n_bits = int(round(length / sr * fps)) if n_bits is None else n_bits
+        self.inp = {"mixed": torch.zeros(batch, length, device=dev), "clean": torch.zeros(batch, length, device=dev),
+                    "full_noise": torch.zeros(batch, length, device=dev), "bits": torch.ones(batch, n_bits, device=dev, dtype=torch.uint8),
+                    "label": torch.zeros(batch, n_bits, device=dev)}
+        self.batch, self.warmup, self.calls = batch, warmup, 0
+        self.g1 = self.g2 = None
+        self.out = None
+        self.launches_per_step = 0
+        self.world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+
+    def _part1(self):
+        d, B = self.inp, self.batch
+        gated = tools.gate_noise(d["mixed"], self.ratio, d["bits"])
+        spec = transform.stft_batch(torch.cat([d["mixed"], gated, d["clean"], d["full_noise"]]))
+        self.spec = spec
+        self.sid.net.train()
+        _, l_sid = self.sid.forward({"audio": spec[:B], "label": d["label"]})
+        self.sid.backward(l_sid)
+        return l_sid["bce"].detach()
+
+    def _part2(self):
+        B, spec = self.batch, self.spec
+        self.joint.net.train()
+        _, l_jt = self.joint.forward({"mixed": spec[:B], "noise": spec[B:2 * B], "clean": spec[2 * B:3 * B], "full_noise": spec[3 * B:]})
+        self.joint.backward(l_jt)
+        wave = transform.istft_batch(self.joint.last_rec.detach())
+        return l_jt["stage1"].detach(), l_jt["stage2"].detach(), wave
+
+    def _finish(self, bce, l1, l2, wave):
+        return {"losses": torch.stack([bce, l1, l2]), "wave": wave}
+
+    def _exchange_and_update(self, h_sid=None):
+        sid_o, jt_o = self.sid.optimizer, self.joint.optimizer
+        if self.world > 1:
+            h_jt = torch.distributed.all_reduce(jt_o.flat_grad, async_op=True)
+            if h_sid is not None:
+                h_sid.wait()
+            h_jt.wait()
+        sid_o.sync_clock()
+        jt_o.sync_clock()
+        sid_o.apply(self.world)
+        jt_o.apply(self.world)
+        L.weights_changed()
+        for a in (self.sid, self.joint):
+            a.clock.tick()
+
+    def __call__(self, mixed, clean, full_noise, bits, label):
+        for k, v in (("mixed", mixed), ("clean", clean), ("full_noise", full_noise), ("bits", bits), ("label", label)):
+            self.inp[k].copy_(v, non_blocking=True)
+        self.calls += 1
+        if self.calls <= self.warmup:                           # eager warm-up: allocator pools, plan cache, lazily built tables
+            bce = self._part1()
+            h = torch.distributed.all_reduce(self.sid.optimizer.flat_grad, async_op=True) if self.world > 1 else None
+            l1, l2, wave = self._part2()
+            out = self._finish(bce, l1, l2, wave)
+            self._exchange_and_update(h)
+            return out
+        if self.g1 is None:
+            torch.cuda.synchronize()
+            self.g1, self.g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            pool = torch.cuda.graph_pool_handle()
+            from . import _lib
+            n0 = _lib.launch_count
+            # (thread_local: NCCL's watchdog thread polls CUDA events while we capture)
+            with torch.cuda.graph(self.g1, pool=pool, capture_error_mode="thread_local"):
+                bce = self._part1()
+            with torch.cuda.graph(self.g2, pool=pool, capture_error_mode="thread_local"):
+                l1, l2, wave = self._part2()
+                self.out = self._finish(bce, l1, l2, wave)
+            self.launches_per_step = _lib.launch_count - n0    # this library's kernels inside the two graphs
+            for a in (self.sid, self.joint):                    # autograd replaced .grad views? re-attach (host only)
+                a.optimizer.zero_grad_views()
+        self.g1.replay()
+        h = torch.distributed.all_reduce(self.sid.optimizer.flat_grad, async_op=True) if self.world > 1 else None
+        self.g2.replay()
+        self._exchange_and_update(h)
+        return self.out
 
 
 def get_agent(config):

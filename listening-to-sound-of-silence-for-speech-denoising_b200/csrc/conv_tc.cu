@@ -24,6 +24,8 @@
 #include "sos_b200.h"
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <map>
+#include <mutex>
 
 namespace {
 
@@ -349,26 +351,28 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
 __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __grid_constant__ TcParams p) { tapgemm_body<0>(p); }
 __global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_f16_kernel(const __grid_constant__ TcParams p) { tapgemm_body<1>(p); }
 
-}  // namespace
+// ---- plan cache (SURVEY 8b `sos_plan_*`): the planner sweep, the MMA program and the tensor-map geometry depend only on the
+// call's shapes / taps / types, never on its pointers.  They are computed once per distinct geometry (~200 per training step,
+// identical from step to step) and kept for the life of the process; a call then patches the pointers and re-encodes a tensor
+// map only when its base address differs from the one the cached map was encoded for.
+struct TcPlan {
+  TcParams p;
+  MapSpec specA, specB, specD;
+  const void *baseA = nullptr, *baseB = nullptr, *baseD = nullptr;
+  long long d_offset = 0;          // byte offset of the output map's origin inside y (channel slice + lattice phase)
+  int smem = 0, grid = 0, esz = 4;
+  int32_t plan_out[8] = {0};
+};
+std::mutex g_plan_mutex;
+std::map<std::vector<int32_t>, TcPlan*> g_plans;
+long long g_plan_hits = 0, g_plan_misses = 0;
 
-extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
-  SOS_CHECK_ARG(ap != nullptr, "sos_conv2d_tc: null args");
-  const sos_conv_args& a = *ap;
-  SOS_CHECK_ARG(a.x && a.wk && a.y && a.tap_dh && a.tap_dw, "sos_conv2d_tc: null pointer");
-  SOS_CHECK_ARG((a.x_dtype == SOS_DTYPE_TF32 || a.x_dtype == SOS_DTYPE_F16) && (a.y_dtype == SOS_DTYPE_TF32 || a.y_dtype == SOS_DTYPE_F16),
-                "sos_conv2d_tc: unknown operand / output type");
+// Everything that does not depend on the call's pointers: blocking, plan sweep, MMA program, tensor-map geometry, grid.
+int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
   const int esz = a.x_dtype == SOS_DTYPE_F16 ? 2 : 4;       // operand element size
   const int kpe = 32 / esz;                                // K elements per MMA
   const int ysz = a.y_dtype == SOS_DTYPE_F16 ? 2 : 4;
-  // (a half map of 8 channels is legal: the 16-channel TMA boxes read the missing K half as zeros)
-  SOS_CHECK_ARG(a.N > 0 && a.H > 0 && a.W > 0 && a.Cin >= 8 && a.Cin % 8 == 0, "sos_conv2d_tc: Cin must be a positive multiple of 8 (got %lld)",
-                (long long)a.Cin);
-  SOS_CHECK_ARG(a.Cout > 0 && a.OH > 0 && a.OW > 0 && a.ntaps > 0 && a.ntaps <= 49, "sos_conv2d_tc: bad output shape / taps");
-  SOS_CHECK_ARG(a.stride == 1 || a.stride == 2, "sos_conv2d_tc: stride must be 1 or 2");
-  SOS_CHECK_ARG(a.osh >= 1 && a.osw >= 1 && a.oph >= 0 && a.opw >= 0 && a.oph < a.osh && a.opw < a.osw, "sos_conv2d_tc: bad output lattice");
-  SOS_CHECK_ARG(a.Cy % (16 / ysz) == 0 && a.y_coff % (16 / ysz) == 0 && a.y_coff < a.Cy, "sos_conv2d_tc: output channels / offset must be multiples of 16 bytes");
-  SOS_CHECK_ARG(((uintptr_t)a.x % 16) == 0 && ((uintptr_t)a.y % 16) == 0 && ((uintptr_t)a.wk % 16) == 0, "sos_conv2d_tc: pointers must be 16-byte aligned");
-  SOS_CHECK_ARG((a.OH - 1) * a.osh + a.oph < a.YH && (a.OW - 1) * a.osw + a.opw < a.YW, "sos_conv2d_tc: output lattice exceeds the output buffer");
+  out.esz = esz;
 
   // ---- output-channel blocking
   const int Cin = (int)a.Cin, Cout = (int)a.Cout;
@@ -443,7 +447,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG(best.cost < 1e299, "sos_conv2d_tc: no feasible plan (Cin %d Cout %d taps %d)", Cin, Cout, (int)a.ntaps);
   const Plan& pl = best.pl;
 
-  static thread_local TcParams p;     // kernel parameter block (copied at launch; one per host thread)
+  TcParams& p = out.p;
   memset(&p, 0, sizeof(p));
   p.N = N;
   p.n_nblk = n_nblk;
@@ -462,7 +466,6 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   p.esz = esz;
   p.b_tile_bytes = N * cb;
   p.y_half = ysz == 2;
-  p.out_scale = a.out_scale;
   p.layout_type = cb == 128 ? 2 : (cb == 64 ? 4 : 6);
   p.sbo = 8 * cb;
   p.idesc = esz == 2 ? make_idesc_f16(128, N, 0, 0) : make_idesc_tf32(128, N, 0, 0);
@@ -494,37 +497,30 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
       p.prog_n[gi] = (int16_t)(n - p.prog0[gi]);
     }
   }
-  p.scale = a.epi_scale;
-  p.shift = a.epi_shift;
-  p.act = (int)a.act;
-  p.slope = a.slope;
-  SOS_CHECK_ARG((a.epi_scale == nullptr) == (a.epi_shift == nullptr), "sos_conv2d_tc: epi_scale and epi_shift go together");
-  p.stats = a.stats_partial;
   p.stats_c = (int)a.stats_channels;
-  SOS_CHECK_ARG(a.stats_partial == nullptr || (ysz == 4 && n_nblk == 1 && a.stats_channels > 0 && a.stats_channels <= 256 && a.stats_channels <= a.Cy - a.y_coff &&
-                                               a.epi_scale == nullptr && (a.act & SOS_ACT_MASK) == 0),
+  SOS_CHECK_ARG(a.stats_partial == nullptr || (n_nblk == 1 && a.stats_channels > 0 && a.stats_channels <= 256 && a.stats_channels <= a.Cy - a.y_coff),
                 "sos_conv2d_tc: fused BatchNorm statistics need raw outputs of at most 256 channels in one channel block");
 
-  // ---- tensor maps.  Dim order: (channel, fast, slow/g, phase(g), image)
+  // ---- tensor-map geometry.  Dim order: (channel, fast, slow/g, phase(g), image)
   const bool fw = pl.fast_is_w;
   const int g = pl.g;
   const uint64_t pixA = (uint64_t)Cin * esz;
   const CUtensorMapDataType dtA = esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32;
   const uint64_t in_fast = fw ? a.W : a.H, in_slow = fw ? a.H : a.W;
   const uint64_t sA_fast = fw ? pixA : pixA * a.W, sA_slow = fw ? pixA * a.W : pixA;
+  const CUtensorMapSwizzle sw = cb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (cb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   {
     uint64_t dims[5] = {(uint64_t)Cin, in_fast, in_slow / g, (uint64_t)g, (uint64_t)a.N};
     uint64_t str[5] = {(uint64_t)esz, sA_fast, sA_slow * g, sA_slow, pixA * a.H * a.W};
     uint32_t box[5] = {(uint32_t)p.cbe, (uint32_t)(pl.FB * a.stride), (uint32_t)(box_slow * a.stride), 1, 1};
     uint32_t es[5] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1, 1};
     SOS_CHECK_ARG(box[1] <= 256 && box[2] <= 256, "sos_conv2d_tc: activation box too large");
-    const CUtensorMapSwizzle sw = cb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (cb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    if (int e = encode_map(&p.mapA, dtA, 5, a.x, dims, str, box, es, sw, "activations")) return e;
+    out.specA = make_spec(dtA, 5, dims, str, box, es, sw, "activations");
     uint64_t bd[2] = {(uint64_t)a.ntaps * Cin, (uint64_t)Cout};
     uint64_t bs[2] = {(uint64_t)esz, (uint64_t)a.ntaps * Cin * esz};
     uint32_t bb[2] = {(uint32_t)p.cbe, (uint32_t)N};
     uint32_t be[2] = {1, 1};
-    if (int e = encode_map(&p.mapB, dtA, 2, a.wk, bd, bs, bb, be, sw, "weights")) return e;
+    out.specB = make_spec(dtA, 2, bd, bs, bb, be, sw, "weights");
   }
   const int out_fast = fw ? (int)a.OW : (int)a.OH, out_slow = fw ? (int)a.OH : (int)a.OW;
   {
@@ -532,7 +528,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
     const uint64_t rowY = pixY * a.YW;
     // output pixel (oh, ow) lives at (oh*osh + oph, ow*osw + opw)
     const uint64_t sY_h = rowY * a.osh, sY_w = pixY * a.osw;
-    const uint8_t* base = reinterpret_cast<const uint8_t*>(a.y) + (a.y_coff + ((uint64_t)a.oph * a.YW + a.opw) * a.Cy) * ysz;
+    out.d_offset = (long long)((a.y_coff + ((uint64_t)a.oph * a.YW + a.opw) * a.Cy) * ysz);
     const int cstore = std::min(round_up(Cout, 16 / ysz), (int)(a.Cy - a.y_coff));
     const uint64_t sY_fast = fw ? sY_w : sY_h, sY_slow = fw ? sY_h : sY_w;
     uint64_t dims[5] = {(uint64_t)cstore, (uint64_t)out_fast, (uint64_t)(out_slow / g), (uint64_t)g, (uint64_t)a.N};
@@ -540,9 +536,8 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
     uint32_t box[5] = {(uint32_t)p.ec, (uint32_t)pl.FB, (uint32_t)pl.SB, 1, 1};
     uint32_t es[5] = {1, 1, 1, 1, 1};
     const int erow = ec * ysz;
-    if (int e = encode_map(&p.mapD, ysz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, dims, str, box, es,
-                            erow == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (erow == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
-                            "output")) return e;
+    out.specD = make_spec(ysz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, dims, str, box, es,
+                          erow == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (erow == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B), "output");
   }
   const int tiles_fast = ceil_div(out_fast, pl.FB);
   p.out_fast = out_fast;
@@ -554,7 +549,79 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG(total < (1ll << 31), "sos_conv2d_tc: too many tiles");
   p.total_ctiles = (int)total;
 
-  const int smem = 1024 + p.n_stages * p.stage_bytes + staging_bytes + 512 + kStatsSmem;
+  out.smem = 1024 + p.n_stages * p.stage_bytes + staging_bytes + 512 + kStatsSmem;
+  out.grid = (int)std::min<long long>(total, sos_num_sms());
+  out.plan_out[0] = pl.fast_is_w;
+  out.plan_out[1] = pl.share;
+  out.plan_out[2] = pl.g;
+  out.plan_out[3] = p.S;
+  out.plan_out[4] = p.n_groups;
+  out.plan_out[5] = p.n_stages;
+  out.plan_out[6] = p.stage_bytes;
+  out.plan_out[7] = out.grid;
+  return SOS_OK;
+}
+
+}  // namespace
+
+extern "C" void sos_plan_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries) {
+  std::lock_guard<std::mutex> lock(g_plan_mutex);
+  if (hits) *hits = g_plan_hits;
+  if (misses) *misses = g_plan_misses;
+  if (entries) *entries = (int64_t)g_plans.size();
+}
+
+extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
+  SOS_CHECK_ARG(ap != nullptr, "sos_conv2d_tc: null args");
+  const sos_conv_args& a = *ap;
+  SOS_CHECK_ARG(a.x && a.wk && a.y && a.tap_dh && a.tap_dw, "sos_conv2d_tc: null pointer");
+  SOS_CHECK_ARG((a.x_dtype == SOS_DTYPE_TF32 || a.x_dtype == SOS_DTYPE_F16) && (a.y_dtype == SOS_DTYPE_TF32 || a.y_dtype == SOS_DTYPE_F16),
+                "sos_conv2d_tc: unknown operand / output type");
+  const int ysz = a.y_dtype == SOS_DTYPE_F16 ? 2 : 4;
+  // (a half map of 8 channels is legal: the 16-channel TMA boxes read the missing K half as zeros)
+  SOS_CHECK_ARG(a.N > 0 && a.H > 0 && a.W > 0 && a.Cin >= 8 && a.Cin % 8 == 0, "sos_conv2d_tc: Cin must be a positive multiple of 8 (got %lld)",
+                (long long)a.Cin);
+  SOS_CHECK_ARG(a.Cout > 0 && a.OH > 0 && a.OW > 0 && a.ntaps > 0 && a.ntaps <= 49, "sos_conv2d_tc: bad output shape / taps");
+  SOS_CHECK_ARG(a.stride == 1 || a.stride == 2, "sos_conv2d_tc: stride must be 1 or 2");
+  SOS_CHECK_ARG(a.osh >= 1 && a.osw >= 1 && a.oph >= 0 && a.opw >= 0 && a.oph < a.osh && a.opw < a.osw, "sos_conv2d_tc: bad output lattice");
+  SOS_CHECK_ARG(a.Cy % (16 / ysz) == 0 && a.y_coff % (16 / ysz) == 0 && a.y_coff < a.Cy, "sos_conv2d_tc: output channels / offset must be multiples of 16 bytes");
+  SOS_CHECK_ARG(((uintptr_t)a.x % 16) == 0 && ((uintptr_t)a.y % 16) == 0 && ((uintptr_t)a.wk % 16) == 0, "sos_conv2d_tc: pointers must be 16-byte aligned");
+  SOS_CHECK_ARG((a.OH - 1) * a.osh + a.oph < a.YH && (a.OW - 1) * a.osw + a.opw < a.YW, "sos_conv2d_tc: output lattice exceeds the output buffer");
+  SOS_CHECK_ARG((a.epi_scale == nullptr) == (a.epi_shift == nullptr), "sos_conv2d_tc: epi_scale and epi_shift go together");
+  SOS_CHECK_ARG(a.stats_partial == nullptr || (a.epi_scale == nullptr && (a.act & SOS_ACT_MASK) == 0),
+                "sos_conv2d_tc: fused BatchNorm statistics are taken of the RAW outputs (no affine / activation in the same call)");
+
+  std::vector<int32_t> key;
+  key.reserve(24 + 2 * (size_t)a.ntaps);
+  const int64_t fields[] = {a.N, a.H, a.W, a.Cin, a.Cout, a.OH, a.OW, a.ntaps, a.stride, a.YH, a.YW, a.Cy, a.y_coff, a.osh, a.osw, a.oph, a.opw,
+                            a.x_dtype, a.y_dtype, a.force_plan, a.stats_partial ? a.stats_channels : -1};
+  for (int64_t f : fields) key.push_back((int32_t)f);
+  for (int t = 0; t < a.ntaps; ++t) { key.push_back(a.tap_dh[t]); key.push_back(a.tap_dw[t]); }
+
+  std::lock_guard<std::mutex> lock(g_plan_mutex);     // (held through the launch: the cached parameter block is patched in place)
+  TcPlan* plan;
+  auto it = g_plans.find(key);
+  if (it != g_plans.end()) {
+    plan = it->second;
+    ++g_plan_hits;
+  } else {
+    plan = new TcPlan();
+    if (int e = plan_conv2d_tc(a, *plan)) { delete plan; return e; }
+    g_plans.emplace(std::move(key), plan);
+    ++g_plan_misses;
+  }
+  TcParams& p = plan->p;
+  p.out_scale = a.out_scale;
+  p.scale = a.epi_scale;
+  p.shift = a.epi_shift;
+  p.act = (int)a.act;
+  p.slope = a.slope;
+  p.stats = a.stats_partial;
+  const void* baseD = reinterpret_cast<const uint8_t*>(a.y) + plan->d_offset;
+  if (plan->baseA != a.x) { if (int e = encode_spec(&p.mapA, plan->specA, a.x)) return e; plan->baseA = a.x; }
+  if (plan->baseB != a.wk) { if (int e = encode_spec(&p.mapB, plan->specB, a.wk)) return e; plan->baseB = a.wk; }
+  if (plan->baseD != baseD) { if (int e = encode_spec(&p.mapD, plan->specD, baseD)) return e; plan->baseD = baseD; }
+
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(tapgemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess ||
@@ -564,21 +631,11 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
     }
     attr_set = true;
   }
-  const int grid = (int)std::min<long long>(total, sos_num_sms());
-  if (esz == 2) tapgemm_f16_kernel<<<grid, kThreadsTc, smem, stream>>>(p);
-  else tapgemm_tf32_kernel<<<grid, kThreadsTc, smem, stream>>>(p);
+  if (plan->esz == 2) tapgemm_f16_kernel<<<plan->grid, kThreadsTc, plan->smem, stream>>>(p);
+  else tapgemm_tf32_kernel<<<plan->grid, kThreadsTc, plan->smem, stream>>>(p);
   SOS_CHECK_LAUNCH("sos_conv2d_tc");
-  if (a.stats_rows_out) *a.stats_rows_out = 4 * grid;
-  if (a.plan_out) {
-    a.plan_out[0] = pl.fast_is_w;
-    a.plan_out[1] = pl.share;
-    a.plan_out[2] = pl.g;
-    a.plan_out[3] = p.S;
-    a.plan_out[4] = p.n_groups;
-    a.plan_out[5] = p.n_stages;
-    a.plan_out[6] = p.stage_bytes;
-    a.plan_out[7] = grid;
-  }
+  if (a.stats_rows_out) *a.stats_rows_out = 4 * plan->grid;
+  if (a.plan_out) memcpy(a.plan_out, plan->plan_out, sizeof(plan->plan_out));
   return SOS_OK;
 }
 

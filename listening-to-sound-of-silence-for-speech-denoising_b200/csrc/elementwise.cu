@@ -102,6 +102,32 @@ __global__ void round_tf32_kernel(float* __restrict__ x, long long n) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) x[e] = tf32_rna(x[e]);
 }
 
+// Device-resident optimiser clock (CUDA-graph friendly: a replayed graph must not bake the step count or the learning rate in
+// as kernel arguments).  state = [lr, step, lr / (1 - b1^step), 1 / sqrt(1 - b2^step)]; the tick kernel advances the step.
+__global__ void adam_tick_kernel(float* __restrict__ state, float b1, float b2) {
+  const double step = (double)state[1] + 1.0;
+  state[1] = (float)step;
+  state[2] = (float)((double)state[0] / (1.0 - pow((double)b1, step)));
+  state[3] = (float)(1.0 / sqrt(1.0 - pow((double)b2, step)));
+}
+__global__ void adam_dev_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                                long long n4, const float* __restrict__ state, float b1, float b2, float eps, float gscale) {
+  const float lr_over_bc1 = state[2], inv_sqrt_bc2 = state[3];
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+    const float4 g4 = g[e];
+    float4 p4 = p[e], m4 = m[e], v4 = v[e];
+    const float gr[4] = {g4.x * gscale, g4.y * gscale, g4.z * gscale, g4.w * gscale};
+    float* pp = &p4.x; float* mm = &m4.x; float* vv = &v4.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mm[i] = b1 * mm[i] + (1.f - b1) * gr[i];
+      vv[i] = b2 * vv[i] + (1.f - b2) * gr[i] * gr[i];
+      pp[i] -= lr_over_bc1 * mm[i] / (sqrtf(vv[i]) * inv_sqrt_bc2 + eps);
+    }
+    p[e] = p4; m[e] = m4; v[e] = v4;
+  }
+}
+
 // ----------------------------------------------------------------------------- views
 struct View {
   int H, W;     // logical extent
@@ -1027,6 +1053,19 @@ int sos_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
   adam_kernel<<<grid_for(n), kThreads, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, (float)(lr / bc1), beta1, beta2, eps,
                                                     (float)(1.0 / sqrt(bc2)), grad_scale);
   SOS_CHECK_LAUNCH("sos_adam_step");
+  return SOS_OK;
+}
+
+int sos_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float* state, float beta1,
+                      float beta2, float eps, float grad_scale, cudaStream_t stream) {
+  SOS_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && state && n > 0 && n % 4 == 0, "sos_adam_step_dev: bad arguments (n must be a multiple of 4)");
+  SOS_CHECK_ARG(((uintptr_t)param % 16) == 0 && ((uintptr_t)grad % 16) == 0 && ((uintptr_t)exp_avg % 16) == 0 && ((uintptr_t)exp_avg_sq % 16) == 0,
+                "sos_adam_step_dev: buffers must be 16-byte aligned");
+  adam_tick_kernel<<<1, 1, 0, stream>>>(state, beta1, beta2);
+  adam_dev_kernel<<<grid_for(n / 4), kThreads, 0, stream>>>(reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad),
+                                                            reinterpret_cast<float4*>(exp_avg), reinterpret_cast<float4*>(exp_avg_sq), n / 4, state,
+                                                            beta1, beta2, eps, grad_scale);
+  SOS_CHECK_LAUNCH("sos_adam_step_dev");
   return SOS_OK;
 }
 

@@ -72,6 +72,26 @@ inline int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, const vo
   return SOS_OK;
 }
 
+// Geometry of a tensor map without its base address: cached per plan, encoded again only when the base pointer changes.
+struct MapSpec {
+  CUtensorMapDataType dt;
+  int rank;
+  uint64_t dims[5], strides[5];
+  uint32_t box[5], es[5];
+  CUtensorMapSwizzle sw;
+  const char* what;
+};
+inline MapSpec make_spec(CUtensorMapDataType dt, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                         const uint32_t* estr, CUtensorMapSwizzle sw, const char* what) {
+  MapSpec s{};
+  s.dt = dt; s.rank = rank; s.sw = sw; s.what = what;
+  for (int i = 0; i < rank; ++i) { s.dims[i] = dims[i]; s.strides[i] = strides_bytes[i]; s.box[i] = box[i]; s.es[i] = estr[i]; }
+  return s;
+}
+inline int encode_spec(CUtensorMap* m, const MapSpec& s, const void* base) {
+  return encode_map(m, s.dt, s.rank, base, s.dims, s.strides, s.box, s.es, s.sw, s.what);
+}
+
 inline int gcd_i(int a, int b) { a = a < 0 ? -a : a; b = b < 0 ? -b : b; while (b) { int t = a % b; a = b; b = t; } return a; }
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 

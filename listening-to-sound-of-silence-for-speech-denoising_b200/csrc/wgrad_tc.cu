@@ -26,6 +26,8 @@
 #include "ptx.cuh"
 #include "sos_b200.h"
 #include "tc_common.cuh"
+#include <map>
+#include <mutex>
 
 namespace {
 
@@ -240,25 +242,22 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
 __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_tf32_kernel(const __grid_constant__ WgParams p) { wgrad_body<0>(p); }
 __global__ void __launch_bounds__(kThreadsWg, 1) wgrad_f16_kernel(const __grid_constant__ WgParams p) { wgrad_body<1>(p); }
 
-}  // namespace
+struct WgPlan {
+  WgParams p;
+  MapSpec specX, specDY;
+  const void *baseX = nullptr, *baseDY = nullptr;
+  int smem = 0, grid = 0, esz = 4;
+  int32_t plan_out[8] = {0};
+};
+std::mutex g_wg_mutex;
+std::map<std::vector<int32_t>, WgPlan*> g_wg_plans;
 
-extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
-  SOS_CHECK_ARG(ap != nullptr, "sos_conv2d_wgrad: null args");
-  const sos_wgrad_args& a = *ap;
-  SOS_CHECK_ARG(a.x && a.dy && a.dw && a.tap_dh && a.tap_dw, "sos_conv2d_wgrad: null pointer");
-  SOS_CHECK_ARG(a.N > 0 && a.H > 0 && a.W > 0 && a.OH > 0 && a.OW > 0 && a.ntaps > 0 && a.ntaps <= 49, "sos_conv2d_wgrad: bad shape");
-  SOS_CHECK_ARG(a.dtype == SOS_DTYPE_TF32 || a.dtype == SOS_DTYPE_F16, "sos_conv2d_wgrad: unknown operand type");
+// Everything that does not depend on the call's pointers (see conv_tc.cu: plan cache).
+int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
   const int esz = a.dtype == SOS_DTYPE_F16 ? 2 : 4;
   const int kpix = 32 / esz;                 // pixels (K) per MMA
   const int cchunk = 128 / esz;              // channels per 128-byte row of a staged box
-  SOS_CHECK_ARG(a.Cin >= 8 && a.Cin % 8 == 0 && a.Cin <= 256, "sos_conv2d_wgrad: Cin must be a multiple of 8 in [8, 256] (got %lld)",
-                (long long)a.Cin);
-  SOS_CHECK_ARG(a.Cout >= 8 && a.Cout % 8 == 0 && a.Cout <= 1024, "sos_conv2d_wgrad: Cout must be a multiple of 8 in [8, 1024] (got %lld)",
-                (long long)a.Cout);
-  SOS_CHECK_ARG(a.Cdy % (16 / esz) == 0 && a.dy_coff % (16 / esz) == 0 && a.dy_coff + a.Cout <= a.Cdy, "sos_conv2d_wgrad: bad dy channel slice");
-  SOS_CHECK_ARG(a.stride == 1 || a.stride == 2, "sos_conv2d_wgrad: stride must be 1 or 2");
-  SOS_CHECK_ARG(((uintptr_t)a.x % 16) == 0 && ((uintptr_t)a.dy % 16) == 0, "sos_conv2d_wgrad: pointers must be 16-byte aligned");
-
+  out.esz = esz;
   Geometry geo{(int)a.ntaps, a.tap_dh, a.tap_dw, (int)a.H, (int)a.W, (int)a.OH, (int)a.OW, (int)a.stride, (int)a.Cin, (int)a.Cout, true,
                std::min(kMaxSub, 512 / round_up((int)a.Cin, 16)), true, esz};
   Plan best;
@@ -276,7 +275,7 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG(best.cost < 1e299, "sos_conv2d_wgrad: no feasible plan");
   const Plan& pl = best;
 
-  static thread_local WgParams p;
+  WgParams& p = out.p;
   memset(&p, 0, sizeof(p));
   const int Cin = (int)a.Cin, Cout = (int)a.Cout;
   p.Cin = Cin;
@@ -285,10 +284,8 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   p.cbi = cchunk;
   p.n_ci_chunks = ceil_div(Cin, cchunk);
   p.cbo = cchunk;
-  p.out_scale = a.out_scale;
   p.FB = pl.FB;                      // 8, or 16 for short dilation lattices (then SB <= 8)
   p.stride = (int)a.stride;
-  p.dw = a.dw;
   // TF32: 128-byte swizzle with 32-byte atoms (4 k rows per atom, SBO 512); half: plain 128-byte swizzle (8 k rows, SBO 1024)
   p.layout_a = p.layout_b = esz == 2 ? 2 : 1;
   p.desc_hi = ((esz == 2 ? 1024u : 512u) >> 4) | (1u << 14) | ((uint32_t)p.layout_a << 29);
@@ -443,8 +440,7 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
     uint32_t es[5] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1, 1};
     SOS_CHECK_ARG(box[2] <= 256, "sos_conv2d_wgrad: activation box too large");
     const CUtensorMapSwizzle sw = esz == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    if (int e = encode_map(&p.mapX, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, a.x, dims, str, box, es, sw,
-                           "wgrad activations")) return e;
+    out.specX = make_spec(esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, dims, str, box, es, sw, "wgrad activations");
   }
   const int out_fast = fw ? (int)a.OW : (int)a.OH, out_slow = fw ? (int)a.OH : (int)a.OW;
   {
@@ -455,9 +451,7 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
     uint32_t box[5] = {(uint32_t)p.cbo, (uint32_t)p.FB, (uint32_t)SB, 1, 1};
     uint32_t es[5] = {1, 1, 1, 1, 1};
     const CUtensorMapSwizzle sw = esz == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
-    if (int e = encode_map(&p.mapDY, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5,
-                           reinterpret_cast<const uint8_t*>(a.dy) + a.dy_coff * esz, dims, str, box, es, sw, "wgrad output grads"))
-      return e;
+    out.specDY = make_spec(esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, dims, str, box, es, sw, "wgrad output grads");
   }
   p.tiles_fast = ceil_div(out_fast, p.FB) + p.tf_extra;
   p.tiles_slow = ceil_div(out_slow / g, SB);
@@ -470,7 +464,59 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   p.tiles_per_slice = ceil_div((int)total, p.n_slices);
   p.n_slices = ceil_div((int)total, p.tiles_per_slice);
 
-  const int smem = 2048 + p.n_stages * p.stage_bytes + tail;
+  out.smem = 2048 + p.n_stages * p.stage_bytes + tail;
+  out.grid = std::min(p.n_jobs * p.n_slices, sms);
+  out.plan_out[0] = pl.fast_is_w;
+  out.plan_out[1] = pl.share;
+  out.plan_out[2] = pl.g;
+  out.plan_out[3] = SB;
+  out.plan_out[4] = n_jobs;
+  out.plan_out[5] = p.n_stages;
+  out.plan_out[6] = p.stage_bytes;
+  out.plan_out[7] = p.n_slices + (stacked ? 1000 : 0);
+  return SOS_OK;
+}
+
+}  // namespace
+
+extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
+  SOS_CHECK_ARG(ap != nullptr, "sos_conv2d_wgrad: null args");
+  const sos_wgrad_args& a = *ap;
+  SOS_CHECK_ARG(a.x && a.dy && a.dw && a.tap_dh && a.tap_dw, "sos_conv2d_wgrad: null pointer");
+  SOS_CHECK_ARG(a.N > 0 && a.H > 0 && a.W > 0 && a.OH > 0 && a.OW > 0 && a.ntaps > 0 && a.ntaps <= 49, "sos_conv2d_wgrad: bad shape");
+  SOS_CHECK_ARG(a.dtype == SOS_DTYPE_TF32 || a.dtype == SOS_DTYPE_F16, "sos_conv2d_wgrad: unknown operand type");
+  const int esz = a.dtype == SOS_DTYPE_F16 ? 2 : 4;
+  SOS_CHECK_ARG(a.Cin >= 8 && a.Cin % 8 == 0 && a.Cin <= 256, "sos_conv2d_wgrad: Cin must be a multiple of 8 in [8, 256] (got %lld)",
+                (long long)a.Cin);
+  SOS_CHECK_ARG(a.Cout >= 8 && a.Cout % 8 == 0 && a.Cout <= 1024, "sos_conv2d_wgrad: Cout must be a multiple of 8 in [8, 1024] (got %lld)",
+                (long long)a.Cout);
+  SOS_CHECK_ARG(a.Cdy % (16 / esz) == 0 && a.dy_coff % (16 / esz) == 0 && a.dy_coff + a.Cout <= a.Cdy, "sos_conv2d_wgrad: bad dy channel slice");
+  SOS_CHECK_ARG(a.stride == 1 || a.stride == 2, "sos_conv2d_wgrad: stride must be 1 or 2");
+  SOS_CHECK_ARG(((uintptr_t)a.x % 16) == 0 && ((uintptr_t)a.dy % 16) == 0, "sos_conv2d_wgrad: pointers must be 16-byte aligned");
+
+  std::vector<int32_t> key;
+  key.reserve(16 + 2 * (size_t)a.ntaps);
+  const int64_t fields[] = {a.N, a.H, a.W, a.Cin, a.Cout, a.OH, a.OW, a.Cdy, a.dy_coff, a.ntaps, a.stride, a.force_plan, a.dtype};
+  for (int64_t f : fields) key.push_back((int32_t)f);
+  for (int t = 0; t < a.ntaps; ++t) { key.push_back(a.tap_dh[t]); key.push_back(a.tap_dw[t]); }
+
+  std::lock_guard<std::mutex> lock(g_wg_mutex);
+  WgPlan* plan;
+  auto it = g_wg_plans.find(key);
+  if (it != g_wg_plans.end()) {
+    plan = it->second;
+  } else {
+    plan = new WgPlan();
+    if (int e = plan_conv2d_wgrad(a, *plan)) { delete plan; return e; }
+    g_wg_plans.emplace(std::move(key), plan);
+  }
+  WgParams& p = plan->p;
+  p.out_scale = a.out_scale;
+  p.dw = a.dw;
+  const void* baseDY = reinterpret_cast<const uint8_t*>(a.dy) + a.dy_coff * esz;
+  if (plan->baseX != a.x) { if (int e = encode_spec(&p.mapX, plan->specX, a.x)) return e; plan->baseX = a.x; }
+  if (plan->baseDY != baseDY) { if (int e = encode_spec(&p.mapDY, plan->specDY, baseDY)) return e; plan->baseDY = baseDY; }
+
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess ||
@@ -480,19 +526,9 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
     }
     attr_set = true;
   }
-  const int grid = std::min(p.n_jobs * p.n_slices, sms);
-  if (esz == 2) wgrad_f16_kernel<<<grid, kThreadsWg, smem, stream>>>(p);
-  else wgrad_tf32_kernel<<<grid, kThreadsWg, smem, stream>>>(p);
+  if (plan->esz == 2) wgrad_f16_kernel<<<plan->grid, kThreadsWg, plan->smem, stream>>>(p);
+  else wgrad_tf32_kernel<<<plan->grid, kThreadsWg, plan->smem, stream>>>(p);
   SOS_CHECK_LAUNCH("sos_conv2d_wgrad");
-  if (a.plan_out) {
-    a.plan_out[0] = pl.fast_is_w;
-    a.plan_out[1] = pl.share;
-    a.plan_out[2] = pl.g;
-    a.plan_out[3] = SB;
-    a.plan_out[4] = n_jobs;
-    a.plan_out[5] = p.n_stages;
-    a.plan_out[6] = p.stage_bytes;
-    a.plan_out[7] = p.n_slices + (stacked ? 1000 : 0);
-  }
+  if (a.plan_out) memcpy(a.plan_out, plan->plan_out, sizeof(plan->plan_out));
   return SOS_OK;
 }

@@ -119,11 +119,35 @@ class ConvGeom:
         return 2 * H, 2 * W
 
 
+# Packed GEMM operands of the weights are cached per (weight storage, view, tap list): inference packs every weight ONCE, not once
+# per call.  An entry is valid while the weight's version counter and the global weight epoch are unchanged -- the optimiser
+# updates parameters through the flat buffer behind autograd's back, so FlatAdam / load_ckpt bump the epoch (`weights_changed`).
+# The entry holds the weight's storage, so its address cannot be recycled for another tensor while the entry lives.  Nothing is
+# cached (or served from the cache) while a CUDA graph is being captured: a replay must re-pack the updated weights itself.
+_WEIGHT_EPOCH = 0
+_PACKS = {}
+
+
+def weights_changed():
+    global _WEIGHT_EPOCH
+    _WEIGHT_EPOCH += 1
+
+
 def _pack_fwd(w, taps, cin_p, half=False):
     """(Cout, Cin, kh, kw) view -> (Cout, len(taps)*cin_p), k = t*cin_p + ci, TF32-rounded fp32 or half (one gather kernel)."""
-    if half:
+    if not half:
+        return ops.pack_taps(w.detach(), taps, cin_p, round_tf32=True)
+    if w.is_cuda and torch.cuda.is_current_stream_capturing():
         return ops.pack_taps_half(w.detach(), taps, cin_p)
-    return ops.pack_taps(w.detach(), taps, cin_p, round_tf32=True)
+    st = w.untyped_storage()
+    key = (st.data_ptr(), w.storage_offset(), tuple(w.shape), tuple(w.stride()), tuple(taps), cin_p)
+    ver = (w._version, _WEIGHT_EPOCH)
+    ent = _PACKS.get(key)
+    if ent is not None and ent[0] == ver:
+        return ent[1]
+    wk = ops.pack_taps_half(w.detach(), taps, cin_p)
+    _PACKS[key] = (ver, wk, st)
+    return wk
 
 
 def _conv_forward(x, w, g, epi=None, want_stats=False, y_half=False, y_out=None):

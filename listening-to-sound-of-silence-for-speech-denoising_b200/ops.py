@@ -270,6 +270,13 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999
     _count()
 
 
+def adam_step_dev(param, grad, exp_avg, exp_avg_sq, state, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """Adam with the optimiser clock in device memory (state = [lr, step, ...]); advances the step by one."""
+    check(lib().sos_adam_step_dev(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), _p(state), beta1, beta2, eps, grad_scale,
+                                  _stream()), "sos_adam_step_dev")
+    _count(2)
+
+
 # ----------------------------------------------------------------------------------------------- BatchNorm + activation
 ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
 ACT_ROUND_TF32 = 16          # OR into `act`: round the output to TF32 (it feeds a tensor-core GEMM)
