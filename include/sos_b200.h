@@ -134,14 +134,20 @@ int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y,
  *   scal (3 floats, scal[2] zeroed by the caller): out scal[0] = s, scal[1] = 1/s (the out_scale of the consuming GEMMs),
  *   scal[2] = sum of dy^2.  partial: sos_bn_partial_blocks(rows, C) * 4 * C floats.  accumulate_param_grads: dgamma / dbeta
  *   (first real_channels entries; 0 = all) are ADDED to (they are the parameters' .grad) instead of written.
+ *   y_dtype / dz_dtype (SOS_DTYPE_TF32 = fp32 storage, SOS_DTYPE_F16 = half storage): the raw conv output y may be the half
+ *   array sos_conv2d_tc writes with y_dtype = F16 (its batch statistics still come from the fp32 accumulators), and dz may be the
+ *   half array a data-gradient call writes WITHOUT out_scale, i.e. still multiplied by the operand scale of the layer above;
+ *   dz_inv_scale (device scalar or NULL = 1) is that scale's inverse: parameter gradients are multiplied by it and the published
+ *   scal[0..1] compose it, so the chain needs no pass to unscale.  Per element: 4 B forward, 10 B backward (fp32 storage: 6 / 18).
  * sos_to_half: out (rows, cd) half = x (rows, cs) fp32 zero-padded to cd channels; with scal != NULL (3 floats, scal[2]
  *   zeroed by the caller) the values are scaled as above. */
-int sos_bn_act_half(const float* y, void* z_half, int64_t rows, int64_t channels, const float* scale, const float* shift,
+int sos_bn_act_half(const void* y, int y_dtype, void* z_half, int64_t rows, int64_t channels, const float* scale, const float* shift,
                     int act, const float* slope, cudaStream_t stream);
-int sos_bn_act_backward_half(const float* dz, const float* y, void* dy_half, int64_t rows, int64_t channels, const float* scale,
-                             const float* shift, const float* mean, const float* invstd, int act, const float* slope,
-                             float* partial, float* dgamma, float* dbeta, float* dslope, float* m1, float* m2, float* scal,
-                             int accumulate_param_grads, int64_t real_channels, cudaStream_t stream);
+int sos_bn_act_backward_half(const void* dz, int dz_dtype, const float* dz_inv_scale, const void* y, int y_dtype, void* dy_half,
+                             int64_t rows, int64_t channels, const float* scale, const float* shift, const float* mean,
+                             const float* invstd, int act, const float* slope, float* partial, float* dgamma, float* dbeta,
+                             float* dslope, float* m1, float* m2, float* scal, int accumulate_param_grads, int64_t real_channels,
+                             cudaStream_t stream);
 int sos_to_half(const float* x, int64_t rows, int64_t cs, void* out_half, int64_t cd, float* scal, cudaStream_t stream);
 /* eval-mode backward of z = act(y*scale+shift): dy = dz*act'(pre)*scale (no batch statistics). */
 int sos_affine_act_backward(const float* dz, const int32_t* dz_view, const float* y, float* dy, int64_t rows,

@@ -67,9 +67,9 @@ _SIGS = {
     "sos_bn_eval_coeffs": (C.c_int, [i64, c_f, c_f, c_f, c_f, C.c_float, c_f, c_f, S]),
     "sos_bn_act": (C.c_int, [c_f, c_f, i32p, i64, i64, c_f, c_f, C.c_int, c_f, S]),
     "sos_bn_act_backward": (C.c_int, [c_f, i32p, c_f, c_f, i64, i64, c_f, c_f, c_f, c_f, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, S]),
-    "sos_bn_act_half": (C.c_int, [c_f, c_f, i64, i64, c_f, c_f, C.c_int, c_f, S]),
-    "sos_bn_act_backward_half": (C.c_int, [c_f, c_f, c_f, i64, i64, c_f, c_f, c_f, c_f, C.c_int, c_f, c_f, c_f, c_f, c_f, c_f, c_f, c_f,
-                                           C.c_int, i64, S]),
+    "sos_bn_act_half": (C.c_int, [c_f, C.c_int, c_f, i64, i64, c_f, c_f, C.c_int, c_f, S]),
+    "sos_bn_act_backward_half": (C.c_int, [c_f, C.c_int, c_f, c_f, C.c_int, c_f, i64, i64, c_f, c_f, c_f, c_f, C.c_int, c_f, c_f, c_f, c_f, c_f,
+                                           c_f, c_f, c_f, C.c_int, i64, S]),
     "sos_nchw_to_nhwc_half": (C.c_int, [c_f, i64, i64, i64, i64, c_f, i64, S]),
     "sos_accumulate_wgrad": (C.c_int, [c_f, i64, i64, i64, i64, i64, c_f, S]),
     "sos_to_half": (C.c_int, [c_f, i64, i64, c_f, i64, c_f, S]),

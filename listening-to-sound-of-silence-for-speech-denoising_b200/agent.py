@@ -329,7 +329,7 @@ class MyAgent(BaseAgent):
         mixed, noise, clean, full_noise = self.spectrograms(data)
         pred_noise, mask = self.net(mixed, noise)
         rec = transform.batch_fast_icRM_sigmoid(mixed, mask)
-        self.last_rec = rec
+        self.last_rec = rec.detach()                           # (detached: a kept graph would pin last step's AccumulateGrad nodes)
         l1 = self.criterion(pred_noise, full_noise)
         l2 = self.criterion(rec, clean)
         return (pred_noise, mask), {"stage1": l1, "stage2": l2}
@@ -402,6 +402,7 @@ class GraphedTrainStep(object):
         self.g1 = self.g2 = None
         self.out = None
         self.launches_per_step = 0
+        self.stream = torch.cuda.Stream()
         self.world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
 
     def _part1(self):
@@ -444,12 +445,18 @@ class GraphedTrainStep(object):
         for k, v in (("mixed", mixed), ("clean", clean), ("full_noise", full_noise), ("bits", bits), ("label", label)):
             self.inp[k].copy_(v, non_blocking=True)
         self.calls += 1
-        if self.calls <= self.warmup:                           # eager warm-up: allocator pools, plan cache, lazily built tables
-            bce = self._part1()
-            h = torch.distributed.all_reduce(self.sid.optimizer.flat_grad, async_op=True) if self.world > 1 else None
-            l1, l2, wave = self._part2()
-            out = self._finish(bce, l1, l2, wave)
-            self._exchange_and_update(h)
+        if self.calls <= self.warmup:
+            # eager warm-up (allocator pools, plan cache, lazily built tables) on a side stream: autograd's AccumulateGrad nodes must
+            # not be born on the legacy default stream, or the capture below could not include them
+            cur = torch.cuda.current_stream()
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                bce = self._part1()
+                h = torch.distributed.all_reduce(self.sid.optimizer.flat_grad, async_op=True) if self.world > 1 else None
+                l1, l2, wave = self._part2()
+                out = self._finish(bce, l1, l2, wave)
+                self._exchange_and_update(h)
+            cur.wait_stream(self.stream)
             return out
         if self.g1 is None:
             torch.cuda.synchronize()

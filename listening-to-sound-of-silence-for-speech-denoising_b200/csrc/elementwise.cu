@@ -5,6 +5,7 @@
 //   BatchNorm (train/eval) + ReLU/PReLU fwd/bwd over NHWC activations
 //   layout changes (NCHW <-> NHWC, reflect borders, nearest resize, concat slices)
 #include "common.cuh"
+#include "sos_b200.h"
 
 namespace {
 
@@ -610,6 +611,229 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_half_kernel(const float
   }
 }
 
+// ----------------------------------------------------------------------------- half-STORAGE BatchNorm passes
+// Second generation of the three kernels above: the raw conv output y and the incoming gradient dz may themselves be stored as
+// half (y: the conv epilogue rounds its fp32 accumulators once, AFTER taking the batch statistics from them; dz: the data-gradient
+// epilogue of the next layer stores its accumulators unscaled, i.e. still multiplied by that layer's power-of-two operand scale,
+// whose inverse arrives as the device scalar `in_inv`).  Per element a layer then moves 4 B forward (was 6) and 10 B backward
+// (was 18).  BatchNorm backward is linear in dz, so the kernels work on the stored (scaled) values throughout: m1, m2 and the
+// new operand scale are in those units, the parameter gradients are multiplied by in_inv when they are written, and the
+// published scale of dy composes both (scal[0] = s * s_in, scal[1] = 1/s * in_inv).
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p, size_t e) { a = ld_stream(p + e * 8); b = ld_stream(p + e * 8 + 4); }
+  __device__ __forceinline__ void get(float (&v)[8]) const { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+};
+template <> struct Raw8<__half> {
+  uint4 u;
+  __device__ __forceinline__ void load(const __half* p, size_t e) { u = __ldcs(reinterpret_cast<const uint4*>(p) + e); }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+      v[2 * k] = f.x; v[2 * k + 1] = f.y;
+    }
+  }
+};
+
+template <typename TY>
+__global__ void __launch_bounds__(kThreads) bn_act_h_kernel(const TY* __restrict__ y, uint4* __restrict__ z, unsigned total, unsigned cg8,
+                                                            const float* __restrict__ scale, const float* __restrict__ shift, int act,
+                                                            const float* __restrict__ slope_ptr) {
+  const float slope = slope_ptr ? *slope_ptr : 0.f;
+  act &= SOS_ACT_MASK;
+  const unsigned span = gridDim.x * blockDim.x;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned c = (tid % cg8) * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sc[k] = __ldg(scale + c + k); sh[k] = __ldg(shift + c + k); }
+  constexpr int U = 8;
+  for (unsigned e0 = tid; e0 < total; e0 += span * U) {
+    Raw8<TY> v[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const unsigned e = e0 + i * span;
+      if (e < total) v[i].load(y, e);
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const unsigned e = e0 + i * span;
+      if (e >= total) break;
+      float in[8], o[8];
+      v[i].get(in);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = act_fwd(fmaf(in[k], sc[k], sh[k]), act, slope);
+      z[e] = make_uint4(pack_half2(o[0], o[1]), pack_half2(o[2], o[3]), pack_half2(o[4], o[5]), pack_half2(o[6], o[7]));
+    }
+  }
+}
+
+// Backward pass 1 (sums of dpre, dpre * xhat, PReLU slope term, dpre^2).  Block-local mapping: thread t owns channel group
+// t % cg8 for rows (t / cg8) + k * rows_per_block (threads beyond rows_per_block * cg8 idle: 4 of 256 for 48 / 96 channels).
+template <typename TY, typename TDZ>
+__global__ void __launch_bounds__(kThreads) bn_bwd_reduce_h_kernel(const TDZ* __restrict__ dz, const TY* __restrict__ y, long long P, int C,
+                                                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                   const float* __restrict__ mean, const float* __restrict__ invstd, int act,
+                                                                   const float* __restrict__ slope_ptr, float* __restrict__ partial /*[grid][4][C]*/) {
+  extern __shared__ float sm[];                 // [4][C] block totals
+  for (int i = threadIdx.x; i < 4 * C; i += kThreads) sm[i] = 0.f;
+  __syncthreads();
+  const int cg8 = C >> 3;
+  const int rpb = kThreads / cg8;
+  const int r = threadIdx.x / cg8, cgi = threadIdx.x - r * cg8;
+  const float slope = slope_ptr ? *slope_ptr : 0.f;
+  act &= SOS_ACT_MASK;
+  if (r < rpb) {
+    const int c = cgi * 8;
+    float sc[8], sh[8], mu[8], is[8];
+    float s1[8], s2[8], s3[8], s4[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sc[k] = __ldg(scale + c + k); sh[k] = __ldg(shift + c + k); mu[k] = __ldg(mean + c + k); is[k] = __ldg(invstd + c + k);
+      s1[k] = s2[k] = s3[k] = s4[k] = 0.f;
+    }
+    const long long stride = (long long)gridDim.x * rpb;
+    constexpr int U = 4;
+    for (long long p0 = (long long)blockIdx.x * rpb + r; p0 < P; p0 += stride * U) {
+      Raw8<TY> yr[U];
+      Raw8<TDZ> dr[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long pp = p0 + u * stride;
+        if (pp < P) {
+          yr[u].load(y, (size_t)pp * cg8 + cgi);
+          dr[u].load(dz, (size_t)pp * cg8 + cgi);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (p0 + u * stride >= P) break;
+        float yv[8], dv[8];
+        yr[u].get(yv);
+        dr[u].get(dv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float pre = fmaf(yv[k], sc[k], sh[k]);
+          float dpre = dv[k];
+          if (act == 1) dpre = pre > 0.f ? dpre : 0.f;
+          else if (act == 2) { if (pre <= 0.f) { s3[k] = fmaf(dv[k], pre, s3[k]); dpre *= slope; } }
+          s1[k] += dpre;
+          s2[k] = fmaf(dpre, (yv[k] - mu[k]) * is[k], s2[k]);
+          s4[k] = fmaf(dpre, dpre, s4[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(sm + c + k, s1[k]);
+      atomicAdd(sm + C + c + k, s2[k]);
+      atomicAdd(sm + 2 * C + c + k, s3[k]);
+      atomicAdd(sm + 3 * C + c + k, s4[k]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * C; i += kThreads) partial[(size_t)blockIdx.x * 4 * C + i] = sm[i];
+}
+
+// Backward finalize for the kernels of this section: like bn_bwd_finalize_kernel<4>, with the incoming gradient's inverse scale.
+__global__ void __launch_bounds__(256) bn_bwd_finalize_h_kernel(const float* __restrict__ partial, int G, int C, double count,
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dslope,
+                                                                float* __restrict__ m1, float* __restrict__ m2, const float* __restrict__ scale,
+                                                                float* __restrict__ dy_sumsq, int accumulate, int c_real,
+                                                                const float* __restrict__ in_inv_ptr) {
+  __shared__ double sm[kFinRows][4][kFinCh];
+  const int c = blockIdx.x * kFinCh + (threadIdx.x & (kFinCh - 1)), gl = threadIdx.x / kFinCh;
+  double r[4];
+  reduce_partials<4>(partial, G, C, c, gl, r, sm);
+  if (gl != 0) return;
+  const float in_inv = in_inv_ptr ? *in_inv_ptr : 1.f;
+  float s3 = 0.f, q = 0.f;
+  if (c < C) {
+    if (c < c_real) {
+      if (accumulate) {
+        dbeta[c] += (float)r[0] * in_inv;
+        dgamma[c] += (float)r[1] * in_inv;
+      } else {
+        dbeta[c] = (float)r[0] * in_inv;
+        dgamma[c] = (float)r[1] * in_inv;
+      }
+    }
+    m1[c] = (float)(r[0] / count);
+    m2[c] = (float)(r[1] / count);
+    s3 = (float)r[2] * in_inv;
+    const double a = r[0] / count, b = r[1] / count, sc = (double)scale[c];
+    const double v = sc * sc * (r[3] - count * a * a - count * b * b);
+    q = v > 0 ? (float)v : 0.f;
+  }
+  q = sum8(q);
+  if (threadIdx.x == 0) atomicAdd(dy_sumsq, q);
+  if (dslope) {
+    s3 = sum8(s3);
+    if (threadIdx.x == 0) atomicAdd(dslope, s3);
+  }
+}
+
+template <typename TY, typename TDZ>
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_h_kernel(const TDZ* __restrict__ dz, const TY* __restrict__ y, uint4* __restrict__ dy,
+                                                                  unsigned total, unsigned cg8, const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift, const float* __restrict__ mean,
+                                                                  const float* __restrict__ invstd, const float* __restrict__ m1,
+                                                                  const float* __restrict__ m2, int act, const float* __restrict__ slope_ptr,
+                                                                  float* __restrict__ scal, float count, const float* __restrict__ in_inv_ptr) {
+  const float slope = slope_ptr ? *slope_ptr : 0.f;
+  act &= SOS_ACT_MASK;
+  const int ex = half_scale_exp(scal[2], count);
+  const float s = pow2i(ex);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const float in_inv = in_inv_ptr ? *in_inv_ptr : 1.f;
+    scal[0] = s / in_inv;                              // (powers of two: exact)
+    scal[1] = pow2i(-ex) * in_inv;
+  }
+  const unsigned span = gridDim.x * blockDim.x;
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned c = (tid % cg8) * 8;
+  float sc[8], sh[8], mu[8], is[8], a1[8], a2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = __ldg(scale + c + k); sh[k] = __ldg(shift + c + k); mu[k] = __ldg(mean + c + k); is[k] = __ldg(invstd + c + k);
+    a1[k] = __ldg(m1 + c + k); a2[k] = __ldg(m2 + c + k);
+  }
+  constexpr int U = 4;
+  for (unsigned e0 = tid; e0 < total; e0 += span * U) {
+    Raw8<TY> yr[U];
+    Raw8<TDZ> dr[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const unsigned e = e0 + i * span;
+      if (e < total) {
+        yr[i].load(y, e);
+        dr[i].load(dz, e);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const unsigned e = e0 + i * span;
+      if (e >= total) break;
+      float yv[8], dv[8], o[8];
+      yr[i].get(yv);
+      dr[i].get(dv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float pre = fmaf(yv[k], sc[k], sh[k]);
+        float dpre = dv[k];
+        if (act == 1) dpre = pre > 0.f ? dpre : 0.f;
+        else if (act == 2) dpre = pre > 0.f ? dpre : dpre * slope;
+        const float xhat = (yv[k] - mu[k]) * is[k];
+        o[k] = s * (sc[k] * (dpre - a1[k] - xhat * a2[k]));
+      }
+      dy[e] = make_uint4(pack_half2(o[0], o[1]), pack_half2(o[2], o[3]), pack_half2(o[4], o[5]), pack_half2(o[6], o[7]));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) sumsq_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
   __shared__ float red[32];
   float acc = 0.f;
@@ -1003,6 +1227,27 @@ __global__ void accumulate_wgrad_kernel(const float* __restrict__ src, int ntaps
 }  // namespace
 
 // ============================================================================= C ABI
+template <typename TY, typename TDZ>
+static int bn_backward_h(const void* dz, const void* y, void* dy_half, long long rows, int C, const float* scale, const float* shift,
+                         const float* mean, const float* invstd, int act, const float* slope, float* partial, float* dgamma, float* dbeta,
+                         float* dslope, float* m1, float* m2, float* scal, int accumulate, int c_real, const float* in_inv, int G,
+                         cudaStream_t stream) {
+  const size_t smem = (size_t)4 * C * sizeof(float);
+  bn_bwd_reduce_h_kernel<TY, TDZ><<<G, kThreads, smem, stream>>>(reinterpret_cast<const TDZ*>(dz), reinterpret_cast<const TY*>(y), rows, C, scale, shift,
+                                                                 mean, invstd, act, slope, partial);
+  SOS_CHECK_LAUNCH("sos_bn_act_backward_half(reduce)");
+  bn_bwd_finalize_h_kernel<<<ceil_div(C, kFinCh), kFinCh * kFinRows, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta,
+                                                                                (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2, scale, scal + 2,
+                                                                                accumulate, c_real, in_inv);
+  SOS_CHECK_LAUNCH("sos_bn_act_backward_half(finalize)");
+  const long long tot8 = rows * (C / 8);
+  bn_bwd_apply_h_kernel<TY, TDZ><<<grid_mult(grid_for(tot8, kThreads * 4, 148 * 8), C / 8), kThreads, 0, stream>>>(
+      reinterpret_cast<const TDZ*>(dz), reinterpret_cast<const TY*>(y), reinterpret_cast<uint4*>(dy_half), (unsigned)tot8, (unsigned)(C / 8), scale, shift,
+      mean, invstd, m1, m2, act, slope, scal, (float)((double)rows * (double)C), in_inv);
+  SOS_CHECK_LAUNCH("sos_bn_act_backward_half(apply)");
+  return SOS_OK;
+}
+
 extern "C" {
 
 int sos_icrm_forward(const float* Y, const float* crm, float* rec, int64_t batch, int64_t plane, float a, float b,
@@ -1170,44 +1415,47 @@ int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y,
   return SOS_OK;
 }
 
-int sos_bn_act_half(const float* y, void* z_half, int64_t rows, int64_t channels, const float* scale, const float* shift, int act,
+int sos_bn_act_half(const void* y, int y_dtype, void* z_half, int64_t rows, int64_t channels, const float* scale, const float* shift, int act,
                     const float* slope, cudaStream_t stream) {
   SOS_CHECK_ARG(y && z_half && scale && shift && rows > 0 && channels >= 8 && channels % 8 == 0, "sos_bn_act_half: bad arguments (channels % 8)");
+  SOS_CHECK_ARG(y_dtype == SOS_DTYPE_TF32 || y_dtype == SOS_DTYPE_F16, "sos_bn_act_half: unknown y type");
   SOS_CHECK_ARG((act & SOS_ACT_MASK) != 2 || slope, "sos_bn_act_half: PReLU needs a slope pointer");
   const long long tot8 = rows * (channels / 8);
   SOS_CHECK_ARG(tot8 < (1ll << 32), "sos_bn_act_half: too many elements");
-  bn_act_half_kernel<<<grid_mult(grid_for(tot8, kThreads * 4, 148 * 8), (int)(channels / 8)), kThreads, 0, stream>>>(y, reinterpret_cast<uint4*>(z_half), (unsigned)tot8,
-                                                                                     (unsigned)(channels / 8), scale, shift, act, slope);
+  const int grid = grid_mult(grid_for(tot8, kThreads * 8, 148 * 8), (int)(channels / 8));
+  if (y_dtype == SOS_DTYPE_F16)
+    bn_act_h_kernel<__half><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const __half*>(y), reinterpret_cast<uint4*>(z_half), (unsigned)tot8,
+                                                           (unsigned)(channels / 8), scale, shift, act, slope);
+  else
+    bn_act_h_kernel<float><<<grid, kThreads, 0, stream>>>(reinterpret_cast<const float*>(y), reinterpret_cast<uint4*>(z_half), (unsigned)tot8,
+                                                          (unsigned)(channels / 8), scale, shift, act, slope);
   SOS_CHECK_LAUNCH("sos_bn_act_half");
   return SOS_OK;
 }
 
-int sos_bn_act_backward_half(const float* dz, const float* y, void* dy_half, int64_t rows, int64_t channels, const float* scale,
-                             const float* shift, const float* mean, const float* invstd, int act, const float* slope, float* partial,
-                             float* dgamma, float* dbeta, float* dslope, float* m1, float* m2, float* scal, int accumulate_param_grads,
-                             int64_t real_channels, cudaStream_t stream) {
+int sos_bn_act_backward_half(const void* dz, int dz_dtype, const float* dz_inv_scale, const void* y, int y_dtype, void* dy_half, int64_t rows,
+                             int64_t channels, const float* scale, const float* shift, const float* mean, const float* invstd, int act,
+                             const float* slope, float* partial, float* dgamma, float* dbeta, float* dslope, float* m1, float* m2, float* scal,
+                             int accumulate_param_grads, int64_t real_channels, cudaStream_t stream) {
   const int G = sos_bn_partial_blocks(rows, channels);
   SOS_CHECK_ARG(dz && y && dy_half && scale && shift && mean && invstd && partial && dgamma && dbeta && m1 && m2 && scal && G > 0 &&
-                    channels % 8 == 0,
+                    channels % 8 == 0 && channels <= 256,
                 "sos_bn_act_backward_half: bad arguments");
+  SOS_CHECK_ARG((dz_dtype == SOS_DTYPE_TF32 || dz_dtype == SOS_DTYPE_F16) && (y_dtype == SOS_DTYPE_TF32 || y_dtype == SOS_DTYPE_F16),
+                "sos_bn_act_backward_half: unknown dz / y type");
   SOS_CHECK_ARG((act & SOS_ACT_MASK) != 2 || (slope && dslope), "sos_bn_act_backward_half: PReLU needs slope and dslope");
-  const int C = (int)channels;
-  const View dv{1, (int)rows, 1, (int)rows, 0, 0, C, 0};      // dense rows (the reduce kernel only tests for density)
-  SOS_CHECK_ARG(rows < (1ll << 31), "sos_bn_act_backward_half: too many rows");
-  const size_t smem = (size_t)4 * C * sizeof(float);
-  bn_bwd_reduce_kernel<4><<<G, kThreads, smem, stream>>>(dz, dv, y, rows, C, scale, shift, mean, invstd, act, slope, partial);
-  SOS_CHECK_LAUNCH("sos_bn_act_backward_half(reduce)");
-  bn_bwd_finalize_kernel<4><<<ceil_div(C, kFinCh), kFinCh * kFinRows, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta,
-                                                                 (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2, scale, scal + 2,
-                                                                 accumulate_param_grads, (int)(real_channels > 0 ? real_channels : channels));
-  SOS_CHECK_LAUNCH("sos_bn_act_backward_half(finalize)");
-  const long long tot8 = rows * (channels / 8);
-  SOS_CHECK_ARG(tot8 < (1ll << 32), "sos_bn_act_backward_half: too many elements");
-  bn_bwd_apply_half_kernel<<<grid_mult(grid_for(tot8, kThreads * 2, 148 * 8), (int)(channels / 8)), kThreads, 0, stream>>>(
-      dz, y, reinterpret_cast<uint4*>(dy_half), (unsigned)tot8, (unsigned)(channels / 8), scale, shift, mean, invstd, m1, m2, act, slope, scal,
-      (float)((double)rows * (double)channels));
-  SOS_CHECK_LAUNCH("sos_bn_act_backward_half(apply)");
-  return SOS_OK;
+  SOS_CHECK_ARG(rows * (channels / 8) < (1ll << 32), "sos_bn_act_backward_half: too many elements");
+  const int C = (int)channels, cr = (int)(real_channels > 0 ? real_channels : channels);
+#define SOS_BN_BWD(TY, TDZ) \
+  return bn_backward_h<TY, TDZ>(dz, y, dy_half, rows, C, scale, shift, mean, invstd, act, slope, partial, dgamma, dbeta, dslope, m1, m2, scal, \
+                                accumulate_param_grads, cr, dz_inv_scale, G, stream)
+  if (y_dtype == SOS_DTYPE_F16) {
+    if (dz_dtype == SOS_DTYPE_F16) SOS_BN_BWD(__half, __half);
+    SOS_BN_BWD(__half, float);
+  }
+  if (dz_dtype == SOS_DTYPE_F16) SOS_BN_BWD(float, __half);
+  SOS_BN_BWD(float, float);
+#undef SOS_BN_BWD
 }
 
 int sos_to_half(const float* x, int64_t rows, int64_t cs, void* out_half, int64_t cd, float* scal, cudaStream_t stream) {

@@ -190,12 +190,14 @@ def _conv_dgrad(dy, w, g, x_shape, out_scale=None):
     return dx
 
 
-def _conv_dgrad_raw(dy, w, g, x_shape, out_scale=None):
+def _conv_dgrad_raw(dy, w, g, x_shape, out_scale=None, y_half=False):
     """Gradient w.r.t. the (possibly reflect-padded) NHWC input buffer (fp32).  dy: fp32 (TF32) or half with its inverse
-    scale `out_scale`."""
+    scale `out_scale`.  y_half (stride-1 convolutions only): the result is stored as half -- pass out_scale=None then, so that it
+    keeps dy's power-of-two scale (see EncoderChainH)."""
     N, H, W, cin_p = x_shape
     cout_p = dy.shape[3]
     half = dy.dtype == torch.float16
+    assert not y_half or (g.kind != "convT" and g.stride == 1)
     if g.kind == "convT":
         # dx[iy] = sum_k dy[2*iy - 1 + ky] w[ci][co][ky]: a stride-2 tap conv over dy
         Cin = w.shape[0]
@@ -207,7 +209,7 @@ def _conv_dgrad_raw(dy, w, g, x_shape, out_scale=None):
     if g.stride == 1:
         wk = _pack_fwd(wt, g.taps, cout_p, half)
         return ops.conv_tc(dy, wk, [-o[0] for o in g.off], [-o[1] for o in g.off], Cin, H, W, 1, k_real=w.shape[0], tag="conv_dgrad",
-                           out_scale=out_scale)
+                           out_scale=out_scale, y_half=y_half)
     # stride 2: four output phases of the input lattice
     dx = torch.empty(N, H, W, _round8(Cin), device=dy.device, dtype=torch.float32)
     assert _round8(Cin) == Cin
@@ -324,6 +326,86 @@ def _wgrad_into(w, x, dy, g, out_scale):
     return _conv_wgrad(x, dy, w, g, out_scale)
 
 
+_Y_HALF = os.environ.get("SOS_Y_HALF", "1") != "0"                 # A/B switch: raw conv outputs (BatchNorm inputs) stored as half
+
+
+def _bn_pad(gamma, beta, rm, rv, Cp):
+    """BatchNorm parameter vectors zero-padded to the map's channel count (gamma = beta = 0 -> z = 0 in the padded channels)."""
+    Cn = gamma.numel()
+    gm, bt = gamma.detach(), beta.detach()
+    if Cp != Cn:
+        pad = (0, Cp - Cn)
+        gm, bt, rm = (torch.nn.functional.pad(t, pad) for t in (gm, bt, rm))
+        rv = torch.nn.functional.pad(rv, pad, value=1.0)
+    return gm.contiguous(), bt.contiguous(), rm, rv
+
+
+class EncoderChainH(torch.autograd.Function):
+    """A whole encoder -- a chain of Conv2d(bias=False, zero 'same' padding, dilation) + BatchNorm2d(batch statistics) + ReLU blocks
+    (`encoder_audio` M1/networks.py:91-93, `encoder_x` / `encoder_n` M2/networks.py:72-80) -- as ONE autograd node over half maps.
+
+    Inside the node nothing travels in fp32: a block's raw conv output y and its activation z are half maps, and in backward the
+    data gradient of block i + 1 is stored by its GEMM epilogue as half WITHOUT undoing the operand scale of dy_{i+1}; block i's
+    BatchNorm backward (linear in dz) reads it together with that scale's inverse.  Per element and block: 4 B forward + 10 B
+    backward of BatchNorm traffic instead of 6 + 18.  The last block (-> 8 / 4 channels, feeds the LSTM) keeps fp32 y and z.
+
+    forward(x handle, geoms, eps, momentum, *[w, gamma, beta, running_mean, running_var] per block) -> z_last fp32 dense."""
+
+    @staticmethod
+    def forward(ctx, x, geoms, eps, momentum, *params):
+        n = len(geoms)
+        assert len(params) == 5 * n
+        saved, cur = [], x
+        for i in range(n):
+            w, gamma, beta, rm, rv = params[5 * i:5 * i + 5]
+            last = i == n - 1
+            xh = ops.hv(cur)
+            y, partial = _conv_forward(xh, w, geoms[i], want_stats=True, y_half=not last)
+            Cp, Cn = y.shape[3], gamma.numel()
+            gm, bt, rmp, rvp = _bn_pad(gamma, beta, rm, rv, Cp)
+            stats = ops.bn_finalize_partial(partial, y.numel() // Cp, gm, bt, rmp, rvp, eps, momentum)
+            if Cp != Cn:
+                rm.copy_(rmp[:Cn])
+                rv.copy_(rvp[:Cn])
+            z = ops.bn_act_apply(y, stats, ops.ACT_RELU, None, half=not last)
+            saved += [cur, y, stats]
+            cur = z
+        ctx.geoms, ctx.n = geoms, n
+        ctx.save_for_backward(*saved, *[params[5 * i + k] for i in range(n) for k in range(3)])
+        return cur
+
+    @staticmethod
+    def backward(ctx, dz):
+        n, geoms = ctx.n, ctx.geoms
+        t = ctx.saved_tensors
+        acts, prm = t[:3 * n], t[3 * n:]
+        grads = [None] * (5 * n)
+        dz, dz_inv = dz.contiguous(), None
+        dx = None
+        for i in reversed(range(n)):
+            x, y, stats = acts[3 * i:3 * i + 3]
+            w, gamma, beta = prm[3 * i:3 * i + 3]
+            g, Cn = geoms[i], gamma.numel()
+            direct = (_ASYNC_WGRAD and _DIRECT_GRADS and gamma.grad is not None and beta.grad is not None and gamma.grad.is_contiguous()
+                      and beta.grad.is_contiguous())
+            dy, dgamma, dbeta, _, scal = ops.bn_train_backward_half(dz, y, stats, ops.ACT_RELU, None, grad_into=(gamma.grad, beta.grad, None) if direct else None,
+                                                                    dz_inv=dz_inv)
+            inv = scal[1:2]
+            xh = ops.hv(x)
+            need_w = ctx.needs_input_grad[4 + 5 * i]
+            dw = _wgrad_into(w, xh, dy, g, inv) if need_w else None
+            grads[5 * i] = dw
+            if not direct:
+                grads[5 * i + 1], grads[5 * i + 2] = dgamma[:Cn], dbeta[:Cn]
+            if i > 0:
+                # data gradient stored as half, still carrying dy's scale (no out_scale): the next block's dz
+                dz = _conv_dgrad_raw(dy, w, g, xh.shape, None, y_half=True)
+                dz_inv = inv
+            elif ctx.needs_input_grad[0]:
+                dx = _conv_dgrad(dy, w, g, xh.shape, inv)
+        return (dx, None, None, None, *grads)
+
+
 class ConvBNActH(torch.autograd.Function):
     """Training-mode conv -> BatchNorm (batch statistics from the GEMM epilogue) -> ReLU / PReLU over HALF maps, as ONE autograd
     node: the gradient w.r.t. the conv output is a scaled half operand that never leaves this node.
@@ -332,7 +414,8 @@ class ConvBNActH(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, gamma, beta, slope, running_mean, running_var, eps, momentum, act, g, out_f32):
         xh = ops.hv(x)
-        y, partial = _conv_forward(xh, w, g, want_stats=True)
+        # raw conv output stored as half unless the block's output stays fp32 (statistics always come from the fp32 accumulators)
+        y, partial = _conv_forward(xh, w, g, want_stats=True, y_half=not out_f32 and _Y_HALF)
         Cp, Cn = y.shape[3], gamma.numel()
         gm, bt, rm, rv = gamma.detach(), beta.detach(), running_mean, running_var
         if Cp != Cn:                                                      # padded channels: gamma = beta = 0 -> z = 0

@@ -160,6 +160,26 @@ def _make_enc(kernel_sizes, dilations, nf, outf):
     return nn.Sequential(*enc)
 
 
+_CHAIN = True                 # A/B switch: run training-mode encoders as one EncoderChainH node (half dz between the blocks)
+
+
+def _run_encoder(enc, x):
+    """An encoder Sequential of ConvBlocks on an NHWC operand map.  Training in the default (half) mode: the whole chain is one
+    autograd node (layers.EncoderChainH); every other mode runs the blocks one by one."""
+    if not (_CHAIN and enc.training and torch.is_grad_enabled() and ops.is_half_handle(x) and L.half_mode()):
+        return enc(x)
+    params = []
+    for blk in enc:
+        conv, bn = blk.block[0], blk.block[1]
+        params += [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+    bn0 = enc[0].block[1]
+    z = L.EncoderChainH.apply(x, tuple(blk.geom for blk in enc), bn0.eps, bn0.momentum, *params)
+    with torch.no_grad():
+        for blk in enc:
+            blk.block[1].num_batches_tracked += 1
+    return z
+
+
 class AudioVisualNet(nn.Module):
     """Silent-interval detector (M1/networks.py:80-155).  forward(s (B,2,256,T), v_num_frames) -> logits (B, v)."""
 
@@ -170,7 +190,7 @@ class AudioVisualNet(nn.Module):
         self.fc1 = nn.Sequential(nn.Linear(200, 100), nn.ReLU(True), nn.Linear(100, 1))
 
     def forward(self, s, v_num_frames=60):
-        f = self.encoder_audio(_nhwc_in(s))                               # (B, 256, T, 8)
+        f = _run_encoder(self.encoder_audio, _nhwc_in(s))                               # (B, 256, T, 8)
         seq = L.FeatToSeq.apply(int(v_num_frames), (8,), f)               # (v, B, 2048)
         m = self.lstm(seq).permute(1, 0, 2)                               # (B, v, 200)
         return self.fc1(m).squeeze(2)
@@ -192,8 +212,8 @@ class ContextAggNet(nn.Module):
 
     def forward_nhwc(self, x, n):
         """x, n: NHWC (B,256,T,8) maps whose first two channels are real/imag."""
-        fx = self.encoder_x(x)
-        fn = self.encoder_n(n)
+        fx = _run_encoder(self.encoder_x, x)
+        fn = _run_encoder(self.encoder_n, n)
         T = fx.shape[2]
         seq = L.FeatToSeq.apply(T, (8, 4), fx, fn)                        # (T, B, 3072)
         h = self.lstm(seq).permute(1, 0, 2)                               # (B, T, 400)

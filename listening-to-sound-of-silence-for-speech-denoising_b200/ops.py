@@ -329,24 +329,32 @@ def bn_finalize_partial(conv_partial, rows, gamma, beta, running_mean, running_v
     return stats
 
 
+def _dt(t):
+    return 1 if t.dtype == torch.float16 else 0
+
+
 def bn_act_apply(y, stats, act, slope, half):
-    """z = act(y * scale + shift) with the finalized stats: a half-map handle (half=True) or a dense fp32 map."""
+    """z = act(y * scale + shift) with the finalized stats: a half-map handle (half=True; y fp32 or half storage) or a dense fp32 map."""
     Cn = y.shape[-1]
     rows = y.numel() // Cn
     sc, sh = C.c_void_p(stats[2].data_ptr()), C.c_void_p(stats[3].data_ptr())
     if half:
         z = new_half(y.shape, y.device)
-        check(lib().sos_bn_act_half(_p(y), _p(hv(z)), rows, Cn, sc, sh, act & 15, _p(slope), _stream()), "sos_bn_act_half")
+        e0 = _pb()
+        check(lib().sos_bn_act_half(_p(y), _dt(y), _p(hv(z)), rows, Cn, sc, sh, act & 15, _p(slope), _stream()), "sos_bn_act_half")
+        _pe("bn_fwd", e0, 0.0, y.numel() * (y.element_size() + 2.0))
     else:
+        assert y.dtype == torch.float32
         z = torch.empty_like(y)
         check(lib().sos_bn_act(_p(y), _p(z), view8(y.shape[-3], y.shape[-2], ld=Cn), rows, Cn, sc, sh, act & 15, _p(slope), _stream()), "sos_bn_act")
     _count()
     return z
 
 
-def bn_train_backward_half(dz, y, stats, act, slope, grad_into=None):
+def bn_train_backward_half(dz, y, stats, act, slope, grad_into=None, dz_inv=None):
     """BatchNorm + activation backward with the gradient w.r.t. the conv output written as a scaled half operand.
     -> dy (real half tensor), dgamma, dbeta, dslope, scal [s, 1/s, sum dy^2].
+    dz, y: fp32 or half storage; dz_inv: device scalar, the inverse of the power-of-two scale a half dz still carries.
     grad_into = (gamma.grad, beta.grad, slope.grad or None): the parameter gradients are ADDED straight into these (their first
     gamma.grad.numel() channels; the map may carry zero-padded channels) and None is returned in their place."""
     Cn = y.shape[-1]
@@ -359,17 +367,22 @@ def bn_train_backward_half(dz, y, stats, act, slope, grad_into=None):
     scal = torch.zeros(3, device=y.device, dtype=torch.float32)
     sp = lambda i: C.c_void_p(stats[i].data_ptr())
     op = lambda i: C.c_void_p(out[i].data_ptr())
+    nbytes = y.numel() * (2.0 * dz.element_size() + 2.0 * y.element_size() + 2.0)
+    e0 = _pb()
     if grad_into is not None:
         gg, gb, gs = grad_into
         assert gg.is_contiguous() and gb.is_contiguous() and gg.numel() == gb.numel() <= Cn and (not prelu or gs is not None)
-        check(lib().sos_bn_act_backward_half(_p(dz), _p(y), _p(dy), rows, Cn, sp(2), sp(3), sp(0), sp(1), act & 15, _p(slope), _p(partial),
-                                             _p(gg), _p(gb), _p(gs) if prelu else None, op(2), op(3), _p(scal), 1, gg.numel(), _stream()),
-              "sos_bn_act_backward_half")
+        check(lib().sos_bn_act_backward_half(_p(dz), _dt(dz), _p(dz_inv), _p(y), _dt(y), _p(dy), rows, Cn, sp(2), sp(3), sp(0), sp(1), act & 15,
+                                             _p(slope), _p(partial), _p(gg), _p(gb), _p(gs) if prelu else None, op(2), op(3), _p(scal), 1,
+                                             gg.numel(), _stream()), "sos_bn_act_backward_half")
+        _pe("bn_bwd", e0, 0.0, nbytes)
         _count(3)
         return dy, None, None, None, scal
     dslope = torch.zeros(1, device=y.device, dtype=torch.float32) if prelu else None
-    check(lib().sos_bn_act_backward_half(_p(dz), _p(y), _p(dy), rows, Cn, sp(2), sp(3), sp(0), sp(1), act & 15, _p(slope), _p(partial),
-                                         op(0), op(1), _p(dslope), op(2), op(3), _p(scal), 0, 0, _stream()), "sos_bn_act_backward_half")
+    check(lib().sos_bn_act_backward_half(_p(dz), _dt(dz), _p(dz_inv), _p(y), _dt(y), _p(dy), rows, Cn, sp(2), sp(3), sp(0), sp(1), act & 15,
+                                         _p(slope), _p(partial), op(0), op(1), _p(dslope), op(2), op(3), _p(scal), 0, 0, _stream()),
+          "sos_bn_act_backward_half")
+    _pe("bn_bwd", e0, 0.0, nbytes)
     _count(3)
     return dy, out[0], out[1], dslope, scal
 

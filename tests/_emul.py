@@ -129,6 +129,7 @@ def _act(pre, act, slope):
 
 def bn_act_apply(y, stats, act, slope, half):
     from sos_b200 import ops
+    y = _f(y)                                             # (the raw conv output may be stored as half)
     z = _act(y * stats[2] + stats[3], act, slope)
     if not half:
         return z
@@ -137,7 +138,11 @@ def bn_act_apply(y, stats, act, slope, half):
     return h
 
 
-def bn_train_backward_half(dz, y, stats, act, slope, grad_into=None):
+def bn_train_backward_half(dz, y, stats, act, slope, grad_into=None, dz_inv=None):
+    """dz / y may be stored as half; a half dz still carries the power-of-two scale of the layer above (inverse = dz_inv): the
+    kernels work on the stored values, scale the parameter gradients by dz_inv and publish the COMPOSED scale of dy."""
+    dz, y = _f(dz), _f(y)
+    inv_in = float(dz_inv) if dz_inv is not None else 1.0
     mean, invstd, scale, shift = stats
     pre = y * scale + shift
     a = act & 15
@@ -154,6 +159,10 @@ def bn_train_backward_half(dz, y, stats, act, slope, grad_into=None):
     n = flat(dpre).shape[0]
     dy = scale * (dpre - dbeta / n - xhat * (dgamma / n))
     dyh, scal = to_half(dy, scaled=True)
+    scal = torch.tensor([float(scal[0]) / inv_in, float(scal[1]) * inv_in, float(scal[2])], dtype=torch.float32)
+    dgamma, dbeta = dgamma * inv_in, dbeta * inv_in
+    if dslope is not None:
+        dslope = dslope * inv_in
     if grad_into is not None:
         gg, gb, gs = grad_into
         gg += dgamma[:gg.numel()]

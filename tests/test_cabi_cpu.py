@@ -54,8 +54,12 @@ def test_argument_errors_of_the_newer_entry_points(built):
     one = ctypes.c_void_p(16)                                            # a non-null dummy pointer (never dereferenced on these paths)
     assert lib.sos_to_half(one, 10, 8, one, 12, None, None) == -1 and b"sos_to_half" in lib.sos_last_error()          # cd % 8
     assert lib.sos_to_half(one, 10, 16, one, 8, None, None) == -1                                                      # cd < cs
-    assert lib.sos_bn_act_half(one, one, 10, 12, one, one, 1, None, None) == -1 and b"channels % 8" in lib.sos_last_error()
-    assert lib.sos_bn_act_half(one, one, 10, 16, one, one, 2, None, None) == -1 and b"PReLU" in lib.sos_last_error()  # slope missing
+    assert lib.sos_bn_act_half(one, 0, one, 10, 12, one, one, 1, None, None) == -1 and b"channels % 8" in lib.sos_last_error()
+    assert lib.sos_bn_act_half(one, 1, one, 10, 16, one, one, 2, None, None) == -1 and b"PReLU" in lib.sos_last_error()  # slope missing
+    assert lib.sos_bn_act_half(one, 5, one, 10, 16, one, one, 1, None, None) == -1 and b"unknown y type" in lib.sos_last_error()
+    assert lib.sos_bn_act_backward_half(one, 3, None, one, 0, one, 100, 16, one, one, one, one, 1, None, one, one, one, None, one, one, one, 0, 0,
+                                        None) == -1 and b"unknown dz" in lib.sos_last_error()
+    assert lib.sos_adam_step_dev(one, one, one, one, 10, one, 0.9, 0.999, 1e-8, 1.0, None) == -1 and b"multiple of 4" in lib.sos_last_error()
     assert lib.sos_add_signals(one, one, None, 4, 100, 0.5, one, one, one, None) == -1 and b"sos_add_signals" in lib.sos_last_error()
     assert lib.sos_add_signals(one, one, one, 0, 100, 0.5, one, one, one, None) == -1                                  # empty batch
     assert lib.sos_crm_forward(one, one, one, 2, 0, 0.1, 0.0, None) == -1 and b"sos_crm_forward" in lib.sos_last_error()

@@ -192,3 +192,66 @@ def test_half_path_wiring_cpu(emulated_half):
     for k in ref:
         assert got[k] is not None and got[k].shape == ref[k].shape, k
         assert errs[k] < 2e-2, errs
+
+
+def test_encoder_chain_wiring_cpu(emulated_half):
+    """layers.EncoderChainH (a whole Conv + BatchNorm + ReLU encoder as one autograd node: half y, half UNSCALED data gradients
+    between the blocks, composed power-of-two scales) over the emulated kernels: forward against nn.Conv2d / BatchNorm2d, and the
+    input gradient + every parameter gradient of a 3-block chain (dilated 3x3, (1,3), 1x1 -> 8 channels) against the same blocks
+    run one by one as ConvBNActH nodes with fp32 y and fp32 gradients between them (that path is pinned against PyTorch autograd by
+    test_half_path_wiring_cpu and, on the GPU, against the reference goldens).  Block-by-block vs PyTorch is not asserted on this
+    240-pixel map: one ReLU flip of a near-zero activation moves a random-signed gradient sum by several per cent."""
+    torch.manual_seed(1)
+    N, H, W = 2, 10, 12
+    x = torch.randn(N, 16, H, W)
+    convs = [torch.nn.Conv2d(16, 16, 3, 1, 2, 2, bias=False), torch.nn.Conv2d(16, 16, (1, 3), 1, (0, 1), 1, bias=False),
+             torch.nn.Conv2d(16, 8, 1, 1, 0, 1, bias=False)]
+    bns = [torch.nn.BatchNorm2d(16), torch.nn.BatchNorm2d(16), torch.nn.BatchNorm2d(8)]
+    for m in bns:
+        m.weight.data.uniform_(0.5, 1.5)
+        m.bias.data.uniform_(-0.3, 0.3)
+    with torch.no_grad():
+        h = x
+        for c, b in zip(convs, bns):
+            h = torch.relu(b(c(h)))
+    rv2 = bns[2].running_var.clone()
+    geoms = (L.ConvGeom("zero", 3, 3, 2, 2, 1), L.ConvGeom("zero", 1, 3, 1, 1, 1), L.ConvGeom("zero", 1, 1, 1, 1, 1))
+    go = (torch.randn(N, H, W, 8) * 1e-7)                               # gradient-sized values: exercises the composed scales
+
+    def run(chain):
+        for c, b in zip(convs, bns):
+            c.weight.grad = b.weight.grad = b.bias.grad = None
+            b.reset_running_stats()
+        x32 = x.permute(0, 2, 3, 1).contiguous().requires_grad_(True)
+        xh = L.ToHalf.apply(x32, 16)
+        if chain:
+            params = []
+            for c, b in zip(convs, bns):
+                params += [c.weight, b.weight, b.bias, b.running_mean, b.running_var]
+            z = L.EncoderChainH.apply(xh, geoms, bns[0].eps, bns[0].momentum, *params)
+        else:
+            z = xh
+            for i, (c, b) in enumerate(zip(convs, bns)):
+                z = L.ConvBNActH.apply(z, c.weight, b.weight, b.bias, None, b.running_mean, b.running_var, b.eps, b.momentum, ops.ACT_RELU, geoms[i], i == 2)
+        z.backward(go)
+        out = {"z": z.detach(), "x": x32.grad}
+        for i, (c, b) in enumerate(zip(convs, bns)):
+            out[f"w{i}"], out[f"g{i}"], out[f"b{i}"] = c.weight.grad.clone(), b.weight.grad.clone(), b.bias.grad.clone()
+        return out
+
+    old = L._Y_HALF
+    L._Y_HALF = False
+    try:
+        ref = run(False)
+    finally:
+        L._Y_HALF = old
+    got = run(True)
+    z = got["z"]
+    assert z.dtype == torch.float32 and not ops.is_half_handle(z) and tuple(z.shape) == (N, H, W, 8)
+    rel = lambda a, b: float((a - b).abs().max() / (b.abs().max() + 1e-30))
+    assert rel(z.permute(0, 3, 1, 2), h) < 5e-3
+    assert rel(bns[2].running_var, rv2) < 5e-3
+    errs = {k: rel(got[k], ref[k]) for k in ref}
+    for k in ref:
+        assert got[k].shape == ref[k].shape, k
+        assert errs[k] < 3e-2, errs        # (half y flips a few near-zero ReLU decisions on this 240-pixel map; wiring errors are O(1))

@@ -1,0 +1,58 @@
+"""agent.GraphedTrainStep (the whole training step of both models as two CUDA-graph replays, device-resident Adam clock) must do
+what the eager agents do: same losses step by step on changing data, the same parameters afterwards, a working learning-rate
+change, and a checkpoint step count that follows the replays."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _agents():
+    from sos_b200 import agent as ag
+    torch.manual_seed(0)
+    sid = ag.SIDAgent(ag.default_config(model="sid"))
+    torch.manual_seed(1)
+    joint = ag.MyAgent(ag.default_config(model="joint"))
+    return sid, joint
+
+
+def test_graphed_step_matches_eager(cuda):
+    from sos_b200 import agent as ag, tools, transform
+    from oracle import synth
+    B, L, STEPS = 2, 16000, 6
+    ratio = 16000 / 30.0
+    sid_e, joint_e = _agents()
+    sid_g, joint_g = _agents()
+    step = ag.GraphedTrainStep(sid_g, joint_g, B, L, 16000, 30.0, warmup=2)
+    rows = []
+    for i in range(STEPS):
+        clips = synth.make_batch(B, length=L, start=10 * i)
+        w = {k: torch.tensor(clips[k], device=cuda) for k in ("mixed", "clean", "full_noise")}
+        bits = torch.tensor(np.array([[int(c) for c in b] for b in clips["bits"]], dtype=np.uint8), device=cuda)
+        lab = torch.tensor(clips["label"], device=cuda)
+        if i == 4:                                        # a learning-rate change between replays (StepLR) must reach the device clock
+            for a in (sid_e, joint_e, sid_g, joint_g):
+                a.optimizer.param_groups[0]["lr"] = 2.5e-4
+        out = step(w["mixed"], w["clean"], w["full_noise"], bits, lab)
+        got = out["losses"].cpu().numpy().copy()
+        wave_g = out["wave"].clone()
+        gated = tools.gate_noise(w["mixed"], ratio, bits)
+        spec = transform.stft_batch(torch.cat([w["mixed"], gated, w["clean"], w["full_noise"]]))
+        _, ls = sid_e.train_func({"audio": spec[:B], "label": lab})
+        _, lj = joint_e.train_func({"mixed": spec[:B], "noise": spec[B:2 * B], "clean": spec[2 * B:3 * B], "full_noise": spec[3 * B:]})
+        want = np.array([float(ls["bce"].detach()), float(lj["stage1"].detach()), float(lj["stage2"].detach())])
+        wave_e = transform.istft_batch(joint_e.last_rec)
+        rows.append((got, want))
+        assert np.allclose(got, want, rtol=2e-3, atol=1e-6), (i, got, want)          # (fp32 atomics order differs run to run)
+        assert float((wave_g - wave_e).abs().max()) < 2e-3 * float(wave_e.abs().max()) + 1e-6, i
+    assert step.g1 is not None and step.launches_per_step > 100
+    assert sid_g.optimizer.step_count == STEPS and abs(float(sid_g.optimizer.state[1]) - STEPS) < 1e-6
+    assert abs(float(joint_g.optimizer.state[0]) - 2.5e-4) < 1e-10
+    for (k, p), (_, q) in zip(joint_e.net.state_dict().items(), joint_g.net.state_dict().items()):
+        if p.is_floating_point():
+            assert float((p - q).abs().max()) < 5e-3, k                                 # Adam turns last-bit gradient noise into <= 2 lr per step
+            assert float((p - q).abs().mean()) < 5e-5, k
+        else:
+            assert torch.equal(p, q), k
+    assert rows[-1][1][1] < rows[0][1][1], "stage-1 loss did not fall"
