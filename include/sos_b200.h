@@ -179,6 +179,17 @@ int sos_feat_to_seq_backward(const float* grad_out, int64_t B, int64_t F, int64_
 /* out (cols, rows) = in (rows, cols)^T */
 int sos_transpose(const float* in, int64_t rows, int64_t cols, float* out, cudaStream_t stream);
 /* y[r][c] = act(y[r][c] + bias[c]) in place; act 0 none, 1 ReLU, 3 sigmoid.  ld = row pitch (floats). */
+/* fp32-grade GEMM operands for the tap GEMM (see the kernel comment in csrc/elementwise.cu): x = hi + lo with hi = tf32(x),
+ * lo = tf32(x - hi); out[s * slot_stride + r * ld_out + k] = part_s(src[r * stride_r + (k + k_shift) * stride_k]) for r < R,
+ * k < KP, zero where k >= K or the shifted index leaves [0, K).  n_slots = 2: {hi, lo} (activation stack); 3: {hi, hi, lo}
+ * (weight slots along K).  One of the strides must be 1 (the kernel transposes through shared memory when stride_k != 1). */
+int sos_split_tf32(const float* src, int64_t R, int64_t K, int64_t KP, int64_t stride_r, int64_t stride_k, int64_t k_shift, float* out,
+                   int64_t ld_out, int64_t slot_stride, int n_slots, cudaStream_t stream);
+/* dst = (base ? base : dst) + alpha * src (parameter gradients of the LSTM / Linear layers added into the flat gradient buffer;
+ * b_ih + b_hh of the LSTM). */
+int sos_axpy(float* dst, const float* src, int64_t n, float alpha, const float* base_or_null, cudaStream_t stream);
+/* (T, B, ld)[..., :C] sequence rows <-> (B, C, T) maps: `permute(0, 2, 1).view(B, 2, 256, T)` of M2/networks.py:92-93 and its adjoint. */
+int sos_seq_map(const float* in, float* out, int64_t T, int64_t B, int64_t C, int64_t ld, int to_map, cudaStream_t stream);
 int sos_bias_act(float* y, int64_t rows, int64_t cols, int64_t ld, const float* bias, int act, cudaStream_t stream);
 /* dpre = dy * act'(y) (y = saved OUTPUT of the activation); dbias[c] += sum_r dpre (dbias zeroed by caller). */
 int sos_bias_act_backward(const float* dy, const float* y, float* dpre, int64_t rows, int64_t cols, int64_t ld, int act,

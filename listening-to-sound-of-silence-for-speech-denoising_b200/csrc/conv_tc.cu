@@ -56,6 +56,7 @@ struct alignas(64) TcParams {
   const float* out_scale;        // optional device scalar multiplied into every output
   float* stats;                  // optional BatchNorm partial sums [4 * grid][2][stats_c] of the RAW outputs (sum, sum of squares)
   int stats_c, out_fast, lat_slow;
+  int n_out;                     // real output channels: the per-channel epilogue vectors hold this many entries
   TapGroup groups[kMaxGroups];
   // MMA program: one entry per tcgen05.mma of a pipeline stage (same for every tile / channel chunk; tap groups with the
   // same structure share one program): x = A descriptor address delta (16-byte units), y = B delta, z = accumulator column
@@ -251,20 +252,29 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
               my_stats[256 + cc * p.ec + lane] += w[0];
             }
           }
-          if (p.scale || p.act || p.out_scale) {
+          if (p.shift || p.act || p.out_scale) {
             // branch-free over the 32 accumulator columns (columns >= ec hold don't-care values that are never stored); every
             // condition is uniform and tested once per chunk, not once per element
             const int act = p.act & SOS_ACT_MASK;
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * oscale;
-            if (p.scale) {
-              const float4* sc4 = reinterpret_cast<const float4*>(p.scale + ch0);
-              const float4* sh4 = reinterpret_cast<const float4*>(p.shift + ch0);
+            if (p.shift) {
+              // per-channel affine (eval-mode BatchNorm) or bias only (scale == NULL); the vectors hold n_out entries
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 if (4 * j < p.ec) {
-                  const float4 a = __ldg(sc4 + j), b = __ldg(sh4 + j);
+                  const int cj = ch0 + 4 * j;
+                  float4 a = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (cj + 4 <= p.n_out && (p.n_out & 3) == 0) {
+                    b = __ldg(reinterpret_cast<const float4*>(p.shift + cj));
+                    if (p.scale) a = __ldg(reinterpret_cast<const float4*>(p.scale + cj));
+                  } else {
+                    float* af = &a.x; float* bf = &b.x;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      if (cj + k < p.n_out) { bf[k] = __ldg(p.shift + cj + k); if (p.scale) af[k] = __ldg(p.scale + cj + k); }
+                  }
                   v[4 * j] = fmaf(v[4 * j], a.x, b.x);
                   v[4 * j + 1] = fmaf(v[4 * j + 1], a.y, b.y);
                   v[4 * j + 2] = fmaf(v[4 * j + 2], a.z, b.z);
@@ -278,6 +288,9 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
             } else if (act == 2) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * slope;
+            } else if (act == 3) {                       // sigmoid (mask head, M2/networks.py:70)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 1.f / (1.f + expf(-v[i]));
             }
             if ((p.act & SOS_ACT_ROUND_TF32) != 0) {
 #pragma unroll
@@ -498,6 +511,7 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
     }
   }
   p.stats_c = (int)a.stats_channels;
+  p.n_out = Cout;
   SOS_CHECK_ARG(a.stats_partial == nullptr || (n_nblk == 1 && a.stats_channels > 0 && a.stats_channels <= 256 && a.stats_channels <= a.Cy - a.y_coff),
                 "sos_conv2d_tc: fused BatchNorm statistics need raw outputs of at most 256 channels in one channel block");
 
@@ -587,8 +601,8 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG(a.Cy % (16 / ysz) == 0 && a.y_coff % (16 / ysz) == 0 && a.y_coff < a.Cy, "sos_conv2d_tc: output channels / offset must be multiples of 16 bytes");
   SOS_CHECK_ARG(((uintptr_t)a.x % 16) == 0 && ((uintptr_t)a.y % 16) == 0 && ((uintptr_t)a.wk % 16) == 0, "sos_conv2d_tc: pointers must be 16-byte aligned");
   SOS_CHECK_ARG((a.OH - 1) * a.osh + a.oph < a.YH && (a.OW - 1) * a.osw + a.opw < a.YW, "sos_conv2d_tc: output lattice exceeds the output buffer");
-  SOS_CHECK_ARG((a.epi_scale == nullptr) == (a.epi_shift == nullptr), "sos_conv2d_tc: epi_scale and epi_shift go together");
-  SOS_CHECK_ARG(a.stats_partial == nullptr || (a.epi_scale == nullptr && (a.act & SOS_ACT_MASK) == 0),
+  SOS_CHECK_ARG(a.epi_scale == nullptr || a.epi_shift != nullptr, "sos_conv2d_tc: epi_scale needs epi_shift (a shift alone is a bias)");
+  SOS_CHECK_ARG(a.stats_partial == nullptr || (a.epi_shift == nullptr && (a.act & SOS_ACT_MASK) == 0),
                 "sos_conv2d_tc: fused BatchNorm statistics are taken of the RAW outputs (no affine / activation in the same call)");
 
   std::vector<int32_t> key;

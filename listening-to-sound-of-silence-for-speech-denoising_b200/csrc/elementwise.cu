@@ -673,11 +673,12 @@ __global__ void __launch_bounds__(kThreads) bn_act_h_kernel(const TY* __restrict
 
 // Backward pass 1 (sums of dpre, dpre * xhat, PReLU slope term, dpre^2).  Block-local mapping: thread t owns channel group
 // t % cg8 for rows (t / cg8) + k * rows_per_block (threads beyond rows_per_block * cg8 idle: 4 of 256 for 48 / 96 channels).
-template <typename TY, typename TDZ>
-__global__ void __launch_bounds__(kThreads) bn_bwd_reduce_h_kernel(const TDZ* __restrict__ dz, const TY* __restrict__ y, long long P, int C,
-                                                                   const float* __restrict__ scale, const float* __restrict__ shift,
-                                                                   const float* __restrict__ mean, const float* __restrict__ invstd, int act,
-                                                                   const float* __restrict__ slope_ptr, float* __restrict__ partial /*[grid][4][C]*/) {
+// (two blocks per SM: <= 128 registers, so that ~64 KB of loads are in flight per SM; PRELU = false drops the slope sums)
+template <typename TY, typename TDZ, bool PRELU>
+__global__ void __launch_bounds__(kThreads, 2) bn_bwd_reduce_h_kernel(const TDZ* __restrict__ dz, const TY* __restrict__ y, long long P, int C,
+                                                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                      const float* __restrict__ mean, const float* __restrict__ invstd, int act,
+                                                                      const float* __restrict__ slope_ptr, float* __restrict__ partial /*[grid][4][C]*/) {
   extern __shared__ float sm[];                 // [4][C] block totals
   for (int i = threadIdx.x; i < 4 * C; i += kThreads) sm[i] = 0.f;
   __syncthreads();
@@ -696,7 +697,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_h_kernel(const TDZ* __
       s1[k] = s2[k] = s3[k] = s4[k] = 0.f;
     }
     const long long stride = (long long)gridDim.x * rpb;
-    constexpr int U = 4;
+    constexpr int U = (sizeof(TY) + sizeof(TDZ) > 4) ? 2 : 4;       // 16-byte loads in flight per array and thread
     for (long long p0 = (long long)blockIdx.x * rpb + r; p0 < P; p0 += stride * U) {
       Raw8<TY> yr[U];
       Raw8<TDZ> dr[U];
@@ -718,8 +719,8 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_h_kernel(const TDZ* __
         for (int k = 0; k < 8; ++k) {
           const float pre = fmaf(yv[k], sc[k], sh[k]);
           float dpre = dv[k];
-          if (act == 1) dpre = pre > 0.f ? dpre : 0.f;
-          else if (act == 2) { if (pre <= 0.f) { s3[k] = fmaf(dv[k], pre, s3[k]); dpre *= slope; } }
+          if (PRELU) { if (pre <= 0.f) { s3[k] = fmaf(dv[k], pre, s3[k]); dpre *= slope; } }
+          else if (act == 1) dpre = pre > 0.f ? dpre : 0.f;
           s1[k] += dpre;
           s2[k] = fmaf(dpre, (yv[k] - mu[k]) * is[k], s2[k]);
           s4[k] = fmaf(dpre, dpre, s4[k]);
@@ -730,7 +731,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_h_kernel(const TDZ* __
     for (int k = 0; k < 8; ++k) {
       atomicAdd(sm + c + k, s1[k]);
       atomicAdd(sm + C + c + k, s2[k]);
-      atomicAdd(sm + 2 * C + c + k, s3[k]);
+      if (PRELU) atomicAdd(sm + 2 * C + c + k, s3[k]);
       atomicAdd(sm + 3 * C + c + k, s4[k]);
     }
   }
@@ -777,7 +778,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_h_kernel(const float* __r
 }
 
 template <typename TY, typename TDZ>
-__global__ void __launch_bounds__(kThreads) bn_bwd_apply_h_kernel(const TDZ* __restrict__ dz, const TY* __restrict__ y, uint4* __restrict__ dy,
+__global__ void __launch_bounds__(kThreads, 2) bn_bwd_apply_h_kernel(const TDZ* __restrict__ dz, const TY* __restrict__ y, uint4* __restrict__ dy,
                                                                   unsigned total, unsigned cg8, const float* __restrict__ scale,
                                                                   const float* __restrict__ shift, const float* __restrict__ mean,
                                                                   const float* __restrict__ invstd, const float* __restrict__ m1,
@@ -801,7 +802,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_h_kernel(const TDZ* __r
     sc[k] = __ldg(scale + c + k); sh[k] = __ldg(shift + c + k); mu[k] = __ldg(mean + c + k); is[k] = __ldg(invstd + c + k);
     a1[k] = __ldg(m1 + c + k); a2[k] = __ldg(m2 + c + k);
   }
-  constexpr int U = 4;
+  constexpr int U = (sizeof(TY) + sizeof(TDZ) > 4) ? 2 : 4;
   for (unsigned e0 = tid; e0 < total; e0 += span * U) {
     Raw8<TY> yr[U];
     Raw8<TDZ> dr[U];
@@ -917,6 +918,79 @@ __global__ void transpose_kernel(const float* __restrict__ in, long long rows, l
   }
 }
 
+// Split operands of the fp32-grade tensor-core GEMMs (LSTM input projections, MLP heads: M1/networks.py:95-98, M2/networks.py:64-70).
+// A value x is written as hi = tf32(x) and lo = tf32(x - hi) (both exactly representable, so the TF32 products are exact) and
+// a @ b = hi@hi + lo@hi + hi@lo runs as ONE 3-tap launch of the tap GEMM: the activation operand is the stack [hi; lo] (tap t reads
+// stack row {0, 1, 0}[t]) and the weight operand carries the slots [hi | hi | lo] along K.
+//   out[s * slot_stride + r * ld_out + k] = part_s(src[r * sr + (k + k_shift) * sk]),  r < R, k < KP  (zero where k >= K or the
+//   shifted source index leaves [0, K)); n_slots = 2: parts {hi, lo}; n_slots = 3: {hi, hi, lo}.
+// One of sr / sk is 1: the 32 x 32 tile is read along that axis and written along k, i.e. the kernel also transposes.
+__global__ void split_tf32_kernel(const float* __restrict__ src, long long R, long long K, long long KP, long long sr, long long sk,
+                                  long long k_shift, float* __restrict__ out, long long ld_out, long long slot_stride, int n_slots) {
+  __shared__ float tile[32][33];
+  const long long k0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+  if (sk == 1) {
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const long long r = r0 + i, k = k0 + threadIdx.x, ks = k + k_shift;
+      tile[i][threadIdx.x] = (r < R && k < K && ks >= 0 && ks < K) ? src[r * sr + ks] : 0.f;
+    }
+  } else {
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const long long k = k0 + i, r = r0 + threadIdx.x, ks = k + k_shift;
+      tile[threadIdx.x][i] = (r < R && k < K && ks >= 0 && ks < K) ? src[r * sr + ks * sk] : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const long long r = r0 + i, k = k0 + threadIdx.x;
+    if (r >= R || k >= KP) continue;
+    const float v = tile[i][threadIdx.x];
+    const float hi = tf32_rna(v), lo = tf32_rna(v - hi);
+    float* o = out + r * ld_out + k;
+    o[0] = hi;
+    if (n_slots == 2) {
+      o[slot_stride] = lo;
+    } else {
+      o[slot_stride] = hi;
+      o[2 * slot_stride] = lo;
+    }
+  }
+}
+
+// dst[i] += alpha * src[i]  (parameter gradients added straight into the flat gradient buffer)
+__global__ void axpy_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n, float alpha, const float* __restrict__ base) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    dst[e] = fmaf(alpha, src[e], base ? base[e] : dst[e]);
+}
+
+// Sequence-major rows (T, B, C) <-> per-clip maps (B, C, T): the mask head's `h.permute(0, 2, 1).view(B, 2, 256, T)` (M2/networks.py:92-93)
+// and its adjoint.  to_map = 1: out (B, C, T) = in (T, B, ld)[..., :C]; to_map = 0: out (T, B, C) = in (B, C, T).  Tiled over (t, c).
+__global__ void seq_map_kernel(const float* __restrict__ in, float* __restrict__ out, int T, int B, int C, int ld, int to_map) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  if (to_map) {
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int t = t0 + i, c = c0 + threadIdx.x;
+      tile[i][threadIdx.x] = (t < T && c < C) ? in[((long long)t * B + b) * ld + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int c = c0 + i, t = t0 + threadIdx.x;
+      if (c < C && t < T) out[((long long)b * C + c) * T + t] = tile[threadIdx.x][i];
+    }
+  } else {
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int c = c0 + i, t = t0 + threadIdx.x;
+      tile[i][threadIdx.x] = (t < T && c < C) ? in[((long long)b * C + c) * T + t] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int t = t0 + i, c = c0 + threadIdx.x;
+      if (c < C && t < T) out[((long long)t * B + b) * ld + c] = tile[threadIdx.x][i];
+    }
+  }
+}
+
 // y[r][c] = act(y[r][c] + bias[c]);  act 0 none, 1 relu, 3 sigmoid
 __global__ void bias_act_kernel(float* __restrict__ y, long long rows, int cols, long long ld, const float* __restrict__ bias, int act) {
   const long long total = rows * cols;
@@ -942,7 +1016,7 @@ __global__ void bias_act_bwd_kernel(const float* __restrict__ dy, const float* _
       const float o = y[r * ld + c];
       if (act == 1) g = o > 0.f ? g : 0.f;
       else if (act == 3) g = g * o * (1.f - o);
-      dpre[r * ld + c] = g;
+      if (dpre) dpre[r * ld + c] = g;
       acc += g;
     }
   }
@@ -1233,15 +1307,19 @@ static int bn_backward_h(const void* dz, const void* y, void* dy_half, long long
                          float* dslope, float* m1, float* m2, float* scal, int accumulate, int c_real, const float* in_inv, int G,
                          cudaStream_t stream) {
   const size_t smem = (size_t)4 * C * sizeof(float);
-  bn_bwd_reduce_h_kernel<TY, TDZ><<<G, kThreads, smem, stream>>>(reinterpret_cast<const TDZ*>(dz), reinterpret_cast<const TY*>(y), rows, C, scale, shift,
-                                                                 mean, invstd, act, slope, partial);
+  if ((act & SOS_ACT_MASK) == 2)
+    bn_bwd_reduce_h_kernel<TY, TDZ, true><<<G, kThreads, smem, stream>>>(reinterpret_cast<const TDZ*>(dz), reinterpret_cast<const TY*>(y), rows, C, scale,
+                                                                         shift, mean, invstd, act, slope, partial);
+  else
+    bn_bwd_reduce_h_kernel<TY, TDZ, false><<<G, kThreads, smem, stream>>>(reinterpret_cast<const TDZ*>(dz), reinterpret_cast<const TY*>(y), rows, C, scale,
+                                                                          shift, mean, invstd, act, slope, partial);
   SOS_CHECK_LAUNCH("sos_bn_act_backward_half(reduce)");
   bn_bwd_finalize_h_kernel<<<ceil_div(C, kFinCh), kFinCh * kFinRows, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta,
                                                                                 (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2, scale, scal + 2,
                                                                                 accumulate, c_real, in_inv);
   SOS_CHECK_LAUNCH("sos_bn_act_backward_half(finalize)");
   const long long tot8 = rows * (C / 8);
-  bn_bwd_apply_h_kernel<TY, TDZ><<<grid_mult(grid_for(tot8, kThreads * 4, 148 * 8), C / 8), kThreads, 0, stream>>>(
+  bn_bwd_apply_h_kernel<TY, TDZ><<<grid_mult(grid_for(tot8, kThreads * 2, 148 * 8), C / 8), kThreads, 0, stream>>>(
       reinterpret_cast<const TDZ*>(dz), reinterpret_cast<const TY*>(y), reinterpret_cast<uint4*>(dy_half), (unsigned)tot8, (unsigned)(C / 8), scale, shift,
       mean, invstd, m1, m2, act, slope, scal, (float)((double)rows * (double)C), in_inv);
   SOS_CHECK_LAUNCH("sos_bn_act_backward_half(apply)");
@@ -1495,6 +1573,32 @@ int sos_transpose(const float* in, int64_t rows, int64_t cols, float* out, cudaS
   return SOS_OK;
 }
 
+int sos_split_tf32(const float* src, int64_t R, int64_t K, int64_t KP, int64_t stride_r, int64_t stride_k, int64_t k_shift, float* out,
+                   int64_t ld_out, int64_t slot_stride, int n_slots, cudaStream_t stream) {
+  SOS_CHECK_ARG(src && out && R > 0 && K > 0 && KP >= K && (n_slots == 2 || n_slots == 3), "sos_split_tf32: bad arguments");
+  SOS_CHECK_ARG(stride_r == 1 || stride_k == 1, "sos_split_tf32: one of the source strides must be 1");
+  SOS_CHECK_ARG(ceil_div_ll(R, 32) <= 65535, "sos_split_tf32: too many rows");
+  dim3 grid((unsigned)ceil_div_ll(KP, 32), (unsigned)ceil_div_ll(R, 32));
+  split_tf32_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, R, K, KP, stride_r, stride_k, k_shift, out, ld_out, slot_stride, n_slots);
+  SOS_CHECK_LAUNCH("sos_split_tf32");
+  return SOS_OK;
+}
+
+int sos_axpy(float* dst, const float* src, int64_t n, float alpha, const float* base_or_null, cudaStream_t stream) {
+  SOS_CHECK_ARG(dst && src && n > 0, "sos_axpy: bad arguments");
+  axpy_kernel<<<grid_for(n), kThreads, 0, stream>>>(dst, src, n, alpha, base_or_null);
+  SOS_CHECK_LAUNCH("sos_axpy");
+  return SOS_OK;
+}
+
+int sos_seq_map(const float* in, float* out, int64_t T, int64_t B, int64_t C, int64_t ld, int to_map, cudaStream_t stream) {
+  SOS_CHECK_ARG(in && out && T > 0 && B > 0 && B <= 65535 && C > 0 && ld >= C, "sos_seq_map: bad arguments");
+  dim3 grid((unsigned)ceil_div_ll(T, 32), (unsigned)ceil_div_ll(C, 32), (unsigned)B);
+  seq_map_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, out, (int)T, (int)B, (int)C, (int)ld, to_map);
+  SOS_CHECK_LAUNCH("sos_seq_map");
+  return SOS_OK;
+}
+
 int sos_bias_act(float* y, int64_t rows, int64_t cols, int64_t ld, const float* bias, int act, cudaStream_t stream) {
   SOS_CHECK_ARG(y && rows > 0 && cols > 0 && ld >= cols && (act == 0 || act == 1 || act == 3), "sos_bias_act: bad arguments");
   bias_act_kernel<<<grid_for(rows * cols), kThreads, 0, stream>>>(y, rows, (int)cols, ld, bias, act);
@@ -1504,7 +1608,7 @@ int sos_bias_act(float* y, int64_t rows, int64_t cols, int64_t ld, const float* 
 
 int sos_bias_act_backward(const float* dy, const float* y, float* dpre, int64_t rows, int64_t cols, int64_t ld, int act,
                           float* dbias_or_null, cudaStream_t stream) {
-  SOS_CHECK_ARG(dy && y && dpre && rows > 0 && cols > 0 && ld >= cols && (act == 0 || act == 1 || act == 3),
+  SOS_CHECK_ARG(dy && y && (dpre || dbias_or_null) && rows > 0 && cols > 0 && ld >= cols && (act == 0 || act == 1 || act == 3),
                 "sos_bias_act_backward: bad arguments");
   long long gy = ceil_div_ll(rows, 8 * 16);
   if (gy > 64) gy = 64;

@@ -673,56 +673,123 @@ class FeatToSeq(torch.autograd.Function):
         return (None, None, *grads)
 
 
-# ----------------------------------------------------------------------------------------------- LSTM
-def _mm3(a, b):
-    """a @ b for the large LSTM GEMMs as a plain library GEMM (cuBLAS) at fp32-grade accuracy on the tensor cores: both operands
-    are split x = hi + lo with hi = tf32(x), lo = tf32(x - hi) (exactly representable, so the TF32 products are exact) and
-    a @ b = hi@hi + lo@hi + hi@lo (error ~2^-21 relative) -- 3 tensor-core GEMMs instead of one fp32 SIMT GEMM (~4x faster)."""
-    (ah, al), (bh, bl) = _split(a), _split(b)
-    old = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    try:
-        out = ah @ bh
-        out.addmm_(al, bh)
-        out.addmm_(ah, bl)
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = old
-    return out
+# ----------------------------------------------------------------------------------------------- Linear / LSTM
+def _direct(p):
+    """Inside the agents' backward (async_wgrad) a parameter gradient is added straight into p.grad (a view of the flat gradient
+    buffer) by this library's kernels and autograd gets None."""
+    return _ASYNC_WGRAD and _DIRECT_GRADS and p.grad is not None and p.grad.is_contiguous()
+
+
+def _grad_out(p, g):
+    if _direct(p):
+        ops.axpy_(p.grad, g.contiguous() if not g.is_contiguous() else g)
+        return None
+    return g
+
+
+class LinearAct(torch.autograd.Function):
+    """act(x @ W^T + b) over the rows of x -- nn.Linear + ReLU / Sigmoid of the heads (M1/networks.py:96-98, M2/networks.py:65-70)
+    at fp32-grade accuracy on the tensor cores (ops.gemm3: one 3-tap TF32 tap-GEMM launch over split operands; bias and activation
+    in its epilogue).  Backward: dpre = dy act'(y) with the bias gradient in the same pass, then two more gemm3 launches."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act):
+        x2 = x.reshape(-1, x.shape[-1])
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        y = ops.gemm3(ops.split_act(x2), ops.split_weight(W.detach()), W.shape[0], b.detach(), act, tag="linear")
+        if not y.is_contiguous():
+            y = y.contiguous()
+        ctx.act = act
+        ctx.save_for_backward(x2, W, b, y)
+        return y.view(*x.shape[:-1], W.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, W, b, y = ctx.saved_tensors
+        n_out, K = W.shape
+        dy2 = dy.reshape(-1, n_out)
+        dy2 = dy2 if dy2.is_contiguous() else dy2.contiguous()
+        direct_b = _direct(b)
+        db = b.grad if direct_b else torch.zeros(n_out, device=dy.device, dtype=torch.float32)
+        dpre = ops.bias_act_backward(dy2, y, ctx.act, db)
+        dx = dW = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm3(ops.split_act(dpre), ops.split_weight(W.detach(), transpose=True), K, tag="linear_dgrad")
+            dx = (dx if dx.is_contiguous() else dx.contiguous()).view(*dy.shape[:-1], K)
+        if ctx.needs_input_grad[1]:
+            dW = ops.gemm3(ops.split_act(dpre, transpose=True), ops.split_weight(x2, transpose=True), K, tag="linear_wgrad")
+            dW = _grad_out(W, dW)
+        return dx, dW, (None if direct_b else db), None
+
+
+class SeqToMap(torch.autograd.Function):
+    """(T, B, C) sequence rows -> (B, C, T): `h.permute(0, 2, 1).view(B, 2, 256, T)` of M2/networks.py:92-93 on (T, B)-ordered rows."""
+
+    @staticmethod
+    def forward(ctx, h):
+        ctx.shape = h.shape
+        return ops.seq_to_map(h.contiguous(), h.shape[2])
+
+    @staticmethod
+    def backward(ctx, g):
+        T, B, Cn = ctx.shape
+        return ops.map_to_seq(g.contiguous(), T, B, Cn)
 
 
 class BiLSTMFn(torch.autograd.Function):
-    """Single-layer bidirectional LSTM.  Input projection / weight gradients are plain library GEMMs
-    (cuBLAS, split-TF32 for the large ones); the recurrence runs in the sos_lstm_* kernels."""
+    """Single-layer bidirectional LSTM (nn.LSTM(bidirectional=True), M1/networks.py:95, M2/networks.py:64).  The input projection and
+    every weight gradient are fp32-grade tensor-core GEMMs of this library (ops.gemm3); the recurrence runs in the sos_lstm_* kernels."""
 
     @staticmethod
     def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
         T, B, I = x.shape
         H = w_hh.shape[1]
-        W = torch.cat([w_ih, w_ih_r], dim=0)                                # (8H, I)
-        bias = torch.cat([b_ih + b_hh, b_ih_r + b_hh_r])
-        gx = (_mm3(x.reshape(T * B, I), W.t()) + bias).view(T, B, 2, 4 * H)
-        whh = torch.stack([w_hh, w_hh_r]).contiguous()
-        out, gates, cell = ops.lstm_forward(gx, whh)
-        ctx.save_for_backward(x, W, whh, out, gates, cell)
+        x2 = x.reshape(T * B, I)
+        a2 = ops.split_act(x2)
+        gx = torch.empty(T * B, 8 * H, device=x.device, dtype=torch.float32)
+        for d, (w, bi, bh) in enumerate(((w_ih, b_ih, b_hh), (w_ih_r, b_ih_r, b_hh_r))):
+            bias = ops.axpy_(torch.empty(4 * H, device=x.device, dtype=torch.float32), bh.detach(), 1.0, base=bi.detach())
+            ops.gemm3(a2, ops.split_weight(w.detach()), 4 * H, bias, 0, tag="lstm_proj", out=gx, col=d * 4 * H)
+        whh = torch.empty(2, 4 * H, H, device=x.device, dtype=torch.float32)
+        ops.axpy_(whh[0], w_hh.detach(), 0.0, base=w_hh.detach())               # (copies: whh = stack([w_hh, w_hh_r]))
+        ops.axpy_(whh[1], w_hh_r.detach(), 0.0, base=w_hh_r.detach())
+        out, gates, cell = ops.lstm_forward(gx.view(T, B, 2, 4 * H), whh)
+        ctx.save_for_backward(x2, w_ih, w_ih_r, whh, out, gates, cell, w_hh, w_hh_r, b_ih, b_hh, b_ih_r, b_hh_r)
+        ctx.dims = (T, B, I, H)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, W, whh, out, gates, cell = ctx.saved_tensors
-        T, B, I = x.shape
-        H = whh.shape[2]
+        x2, w_ih, w_ih_r, whh, out, gates, cell, w_hh, w_hh_r, b_ih, b_hh, b_ih_r, b_hh_r = ctx.saved_tensors
+        T, B, I, H = ctx.dims
+        M = T * B
         dgx = ops.lstm_backward(dout.contiguous(), whh, out, gates, cell)   # (T,B,2,4H)
-        flat = dgx.view(T * B, 8 * H)
-        dx = _mm3(flat, W).view(T, B, I) if ctx.needs_input_grad[0] else None
-        dW = _mm3(flat.t(), x.reshape(T * B, I))                            # (8H, I)
-        db = flat.sum(0)
-        hprev_f = torch.zeros(T, B, H, device=x.device, dtype=torch.float32)
-        hprev_f[1:] = out[:-1, :, :H]
-        hprev_r = torch.zeros(T, B, H, device=x.device, dtype=torch.float32)
-        hprev_r[:-1] = out[1:, :, H:]
-        dwhh_f = dgx[:, :, 0].reshape(T * B, 4 * H).t() @ hprev_f.view(T * B, H)
-        dwhh_r = dgx[:, :, 1].reshape(T * B, 4 * H).t() @ hprev_r.view(T * B, H)
-        return (dx, dW[:4 * H], dwhh_f, db[:4 * H], db[:4 * H], dW[4 * H:], dwhh_r, db[4 * H:], db[4 * H:])
+        flat = dgx.view(M, 8 * H)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            # dx = dg_f @ w_ih + dg_r @ w_ih_r: ONE GEMM over K = 8H against [w_ih; w_ih_r]^T
+            dx = ops.gemm3(ops.split_act(flat), ops.split_weight_cat_t([w_ih.detach(), w_ih_r.detach()]), I, tag="lstm_dgrad").view(T, B, I)
+        xT = ops.split_weight(x2, transpose=True)                           # (I, 3 * MP): shared by both directions
+        out2 = out.view(M, 2 * H)
+        grads = []
+        for d, (wi, wh, bi, bh) in enumerate(((w_ih, w_hh, b_ih, b_hh), (w_ih_r, w_hh_r, b_ih_r, b_hh_r))):
+            dg = flat[:, d * 4 * H:(d + 1) * 4 * H]                         # (M, 4H), row stride 8H
+            dgT = ops.split_act(dg, transpose=True)                         # (2, 4H, MP)
+            dW = _grad_out(wi, ops.gemm3(dgT, xT, I, tag="lstm_wgrad"))
+            # h_{t-1} of the forward direction is out[t-1, :, :H] (rows shifted by -B); of the reverse direction out[t+1, :, H:]
+            hprevT = ops.split_weight(out2[:, d * H:(d + 1) * H], transpose=True, k_shift=(-B if d == 0 else B))
+            dWhh = ops.gemm3(dgT, hprevT, H, tag="lstm_wgrad")
+            dWhh = _grad_out(wh, dWhh if dWhh.is_contiguous() else dWhh.contiguous())
+            if _direct(bi) and _direct(bh):
+                ops.bias_act_backward(dg, dg, 0, bi.grad, want_dpre=False)
+                ops.bias_act_backward(dg, dg, 0, bh.grad, want_dpre=False)
+                db_i = db_h = None
+            else:
+                db_i = torch.zeros(4 * H, device=dg.device, dtype=torch.float32)
+                ops.bias_act_backward(dg, dg, 0, db_i, want_dpre=False)
+                db_h = db_i
+            grads += [dW, dWhh, db_i, db_h]
+        return (dx, *grads)
 
 
 # ----------------------------------------------------------------------------------------------- cRM + losses

@@ -192,8 +192,10 @@ class AudioVisualNet(nn.Module):
     def forward(self, s, v_num_frames=60):
         f = _run_encoder(self.encoder_audio, _nhwc_in(s))                               # (B, 256, T, 8)
         seq = L.FeatToSeq.apply(int(v_num_frames), (8,), f)               # (v, B, 2048)
-        m = self.lstm(seq).permute(1, 0, 2)                               # (B, v, 200)
-        return self.fc1(m).squeeze(2)
+        m = self.lstm(seq)                                                # (v, B, 200); the head acts per row: keep (v, B) order
+        m = L.LinearAct.apply(m, self.fc1[0].weight, self.fc1[0].bias, ops.ACT_RELU)
+        m = L.LinearAct.apply(m, self.fc1[2].weight, self.fc1[2].bias, ops.ACT_NONE)
+        return m.squeeze(2).t()                                           # (B, v)
 
 
 class ContextAggNet(nn.Module):
@@ -216,9 +218,12 @@ class ContextAggNet(nn.Module):
         fn = _run_encoder(self.encoder_n, n)
         T = fx.shape[2]
         seq = L.FeatToSeq.apply(T, (8, 4), fx, fn)                        # (T, B, 3072)
-        h = self.lstm(seq).permute(1, 0, 2)                               # (B, T, 400)
-        h = self.fc(h)                                                    # (B, T, 512)
-        return h.permute(0, 2, 1).reshape(h.size(0), 2, -1, h.size(1))
+        h = self.lstm(seq)                                                # (T, B, 400); the head acts per row: keep (T, B) order
+        h = L.LinearAct.apply(h, self.fc[0].weight, self.fc[0].bias, ops.ACT_RELU)
+        h = L.LinearAct.apply(h, self.fc[2].weight, self.fc[2].bias, ops.ACT_RELU)
+        h = L.LinearAct.apply(h, self.fc[4].weight, self.fc[4].bias, ops.ACT_SIGMOID)       # (T, B, 512)
+        m = L.SeqToMap.apply(h)                                           # (B, 512, T) = h.permute(1, 2, 0)
+        return m.view(m.size(0), 2, -1, m.size(2))
 
 
 class InpaintNet(nn.Module):

@@ -278,7 +278,7 @@ def adam_step_dev(param, grad, exp_avg, exp_avg_sq, state, beta1=0.9, beta2=0.99
 
 
 # ----------------------------------------------------------------------------------------------- BatchNorm + activation
-ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_PRELU, ACT_SIGMOID = 0, 1, 2, 3
 ACT_ROUND_TF32 = 16          # OR into `act`: round the output to TF32 (it feeds a tensor-core GEMM)
 
 
@@ -599,6 +599,120 @@ def conv_wgrad(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_p
     if plan_out is not None:
         plan_out[:] = list(po)
     return dw
+
+
+# ----------------------------------------------------------------------------------------------- fp32-grade GEMMs on the tap GEMM
+# The LSTM input projections and the MLP heads (M1/networks.py:95-98, M2/networks.py:64-70) are contractions over 200..6500 fp32
+# values whose results feed a sigmoid mask: they run at fp32-grade accuracy on the tensor cores as ONE 3-tap launch of the TF32 tap
+# GEMM over split operands (x = hi + lo, both TF32-exact; a @ b^T = hi hi + lo hi + hi lo, error ~2^-21): the activation operand is
+# the stack [hi; lo] (N = 1, H = 2, W = rows, C = K), tap t reads stack row {0, 1, 0}[t], and the weight operand carries the slots
+# [hi | hi | lo] along K.
+def _r8(n):
+    return (n + 7) // 8 * 8
+
+
+def _split_into(src, transpose, k_shift, out, ld_out, slot_stride, n_slots, col_offset=0):
+    """Rows of the operand = rows of src (or its columns with `transpose`), K axis = the other one; writes slots of width KP = K
+    rounded up to 8 at column `col_offset` of rows of length ld_out."""
+    assert src.dim() == 2 and src.stride(1) == 1 and src.dtype == torch.float32 and src.is_cuda
+    R, K = src.shape
+    dst = C.c_void_p(out.data_ptr() + 4 * col_offset)
+    if not transpose:
+        check(lib().sos_split_tf32(_p_any(src), R, K, _r8(K), src.stride(0), 1, 0, dst, ld_out, slot_stride, n_slots, _stream()), "sos_split_tf32")
+    else:
+        check(lib().sos_split_tf32(_p_any(src), K, R, _r8(R), 1, src.stride(0), k_shift, dst, ld_out, slot_stride, n_slots, _stream()), "sos_split_tf32")
+    _count()
+
+
+def split_act(x, transpose=False, k_shift=0):
+    """x (R, K) fp32 (any row stride, unit column stride) -> activation stack (2, R, KP) [hi; lo], KP = K rounded up to 8.
+    transpose: the operand is x^T, i.e. the stack is (2, K, RP) (RP = R rounded up to 8); k_shift then shifts along R:
+    element [k][r] = x[r + k_shift][k] (zero outside), which expresses h_{t-1} / h_{t+1} of an LSTM output."""
+    R, K = x.shape
+    rows, kp = (K, _r8(R)) if transpose else (R, _r8(K))
+    out = torch.empty(2, rows, kp, device=x.device, dtype=torch.float32)
+    _split_into(x, transpose, k_shift, out, kp, rows * kp, 2)
+    return out
+
+
+def split_weight(w, transpose=False, k_shift=0):
+    """w (Cout, K) fp32 (unit column stride) -> weight operand (Cout, 3 * KP) [hi | hi | lo]; transpose: the operand is w^T
+    (K, 3 * RP) with the same k_shift semantics as split_act."""
+    R, K = w.shape
+    rows, kp = (K, _r8(R)) if transpose else (R, _r8(K))
+    out = torch.empty(rows, 3 * kp, device=w.device, dtype=torch.float32)
+    _split_into(w, transpose, k_shift, out, 3 * kp, kp, 3)
+    return out
+
+
+def split_weight_cat_t(ws):
+    """Weight operand of x @ [w_0; w_1; ...] (the w_i (R_i, K) stacked along their rows, which is the contraction axis here):
+    (K, 3 * sum RP_i) with slot s holding [w_0^T | w_1^T | ...]."""
+    K = ws[0].shape[1]
+    kp = sum(_r8(w.shape[0]) for w in ws)
+    out = torch.empty(K, 3 * kp, device=ws[0].device, dtype=torch.float32)
+    off = 0
+    for w in ws:
+        _split_into(w, True, 0, out, 3 * kp, kp, 3, col_offset=off)
+        off += _r8(w.shape[0])
+    return out
+
+
+def _p_any(t):
+    assert t.is_cuda and t.dtype == torch.float32
+    return C.c_void_p(t.data_ptr())
+
+
+def gemm3(a2, w3, n_out, bias=None, act=0, tag="gemm", out=None, col=0):
+    """a2 (2, M, KP) activation stack, w3 (n_out, 3 * KP) weight operand -> (M, n_out) fp32 = act(a @ w^T + bias); act 0 / 1 relu /
+    3 sigmoid.  out (M, ld) + col: write into columns [col, col + n_out) of an existing buffer (col, ld multiples of 4).  A fresh
+    output is padded to a multiple of 4 columns; the returned view drops the padding."""
+    _, M, KP = a2.shape
+    assert w3.shape == (n_out, 3 * KP), (w3.shape, n_out, KP)
+    if out is None:
+        Cy = (n_out + 3) // 4 * 4
+        out = torch.empty(M, Cy, device=a2.device, dtype=torch.float32)
+    Cy = out.shape[1]
+    conv_tc(a2.view(1, 2, M, KP), w3, [0, 1, 0], [0, 0, 0], n_out, 1, M, 1, y=out.view(1, 1, M, Cy), y_coff=col, epi_shift=bias, act=act,
+            force_plan=1, tag=tag, k_real=KP)
+    return out if (Cy == n_out and col == 0) else out[:, col:col + n_out]
+
+
+def axpy_(dst, src, alpha=1.0, base=None):
+    """dst = (base if given else dst) + alpha * src."""
+    assert dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel() and (base is None or base.is_contiguous())
+    check(lib().sos_axpy(_p(dst), _p(src), dst.numel(), alpha, _p(base), _stream()), "sos_axpy")
+    _count()
+    return dst
+
+
+def seq_to_map(h, channels):
+    """h (T, B, ld) sequence rows -> (B, channels, T) maps (the mask head's permute + view, M2/networks.py:92-93)."""
+    T, B, ld = h.shape
+    out = torch.empty(B, channels, T, device=h.device, dtype=torch.float32)
+    check(lib().sos_seq_map(_p(h), _p(out), T, B, channels, ld, 1, _stream()), "sos_seq_map")
+    _count()
+    return out
+
+
+def map_to_seq(g, T, B, channels):
+    """adjoint of seq_to_map: g (B, channels, T) -> (T, B, channels)."""
+    out = torch.empty(T, B, channels, device=g.device, dtype=torch.float32)
+    check(lib().sos_seq_map(_p(g), _p(out), T, B, channels, channels, 0, _stream()), "sos_seq_map")
+    _count()
+    return out
+
+
+def bias_act_backward(dy, y, act, dbias=None, want_dpre=True):
+    """dpre = dy * act'(y) for y = act(pre) (act 0 / 1 relu / 3 sigmoid), dbias += column sums of dpre.  dy, y (rows, cols), unit
+    column stride, same row stride; want_dpre=False: only the column sums."""
+    rows, cols = dy.shape
+    assert dy.stride(1) == 1 and y.stride(1) == 1 and dy.stride(0) == y.stride(0)
+    dpre = torch.empty_strided(dy.shape, dy.stride(), device=dy.device, dtype=torch.float32) if want_dpre else None
+    check(lib().sos_bias_act_backward(_p_any(dy), _p_any(y), _p_any(dpre) if want_dpre else None, rows, cols, dy.stride(0), act, _p(dbias),
+                                      _stream()), "sos_bias_act_backward")
+    _count()
+    return dpre
 
 
 # ----------------------------------------------------------------------------------------------- LSTM recurrence

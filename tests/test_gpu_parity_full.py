@@ -175,7 +175,7 @@ def test_training_trajectory_matches_fp32(cuda):
     on 4-clip batches amplifies any rounding difference from step to step, so the band is calibrated in the same run: a THIRD
     trajectory runs the oracle through PyTorch's own cuDNN / cuBLAS TF32 path (allow_tf32 = True: what the reference's nn.Conv2d
     does by default on any Ampere-or-later GPU), and the product path may deviate from fp32 by at most
-    max(TRAJ_BAND, 2 x that trajectory's deviation) at every step."""
+    max(TRAJ_BAND, 2 x that trajectory's worst deviation) at every step and max(3 %, 2 x its mean deviation) on average."""
     from sos_b200 import agent as ag, transform
     from oracle import nets, synth, transform as otf
     B, STEPS = 4, 20
@@ -234,7 +234,8 @@ def test_training_trajectory_matches_fp32(cuda):
     for i in range(STEPS):
         print(f"{i:3d}  " + "   ".join(f"{got[i, j]:.5f}/{want[i, j]:.5f}/{gauge[i, j]:.5f}" for j in range(3)))
     assert want[-1, 1] < 0.9 * want[0, 1], "the fp32 oracle itself did not train (stage 1 loss)"
-    band = np.maximum(TRAJ_BAND, 2.0 * np.maximum.accumulate(rel_g, axis=0))
-    assert (rel <= band).all(), (rel.max(0), rel_g.max(0))
-    # and it must have trained: every loss within 15 % of the fp32 trajectory's at the end, far below where it started
-    assert (np.abs(got[-1] - want[-1]) < 0.15 * want[-1]).all() and (got[-1] < 0.6 * want[0]).all()
+    # per step: within max(5 %, 2 x the cuDNN-TF32 trajectory's worst deviation); on average: max(3 %, 2 x its mean deviation)
+    assert (rel.max(0) <= np.maximum(TRAJ_BAND, 2.0 * rel_g.max(0))).all(), (rel.max(0), rel_g.max(0))
+    assert (rel.mean(0) <= np.maximum(0.03, 2.0 * rel_g.mean(0))).all(), (rel.mean(0), rel_g.mean(0))
+    # and it must have trained: the last five steps' mean losses within 10 % of the fp32 trajectory's, far below where it started
+    assert (np.abs(got[-5:].mean(0) - want[-5:].mean(0)) < 0.10 * want[-5:].mean(0)).all() and (got[-1] < 0.6 * want[0]).all()

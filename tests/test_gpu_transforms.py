@@ -135,6 +135,63 @@ def test_losses_and_adam(cuda):
     assert float((pd.cpu() - pr.detach()).abs().max()) < 1e-6
 
 
+def test_adam_device_clock(cuda):
+    """sos_adam_step_dev (optimiser clock in device memory, CUDA-graph friendly): 4 steps with a learning-rate change against
+    torch.optim.Adam."""
+    from sos_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    p = torch.randn(1000, generator=g)
+    grads = [torch.randn(1000, generator=g) * 10 ** (-i) for i in range(4)]
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=1e-3)
+    pd, m, v = p.to(cuda), torch.zeros(1000, device=cuda), torch.zeros(1000, device=cuda)
+    state = torch.tensor([1e-3, 0, 0, 0], device=cuda)
+    for i, gr in enumerate(grads):
+        if i == 2:
+            opt.param_groups[0]["lr"] = 1e-4
+            state[0:1].fill_(1e-4)
+        pr.grad = gr.clone()
+        opt.step()
+        ops.adam_step_dev(pd, gr.to(cuda), m, v, state)
+    assert float((pd.cpu() - pr.detach()).abs().max()) < 1e-6
+    assert float(state[1]) == 4.0
+
+
+@pytest.mark.parametrize("rows,K,n_out,act", [(203 * 3, 400, 600, 1), (65, 600, 512, 3), (1920, 200, 100, 1), (77, 100, 1, 0), (130, 2048, 96, 0)])
+def test_linear_act_matches_fp64(cuda, rows, K, n_out, act):
+    """layers.LinearAct (nn.Linear + ReLU / Sigmoid of the heads, M1/networks.py:96-98, M2/networks.py:65-70) = one 3-tap TF32 tap-GEMM
+    launch over split operands: fp32-grade.  Forward, input gradient, weight and bias gradients against float64."""
+    from sos_b200 import layers as L
+    g = torch.Generator().manual_seed(rows + K)
+    x = torch.randn(rows, K, generator=g, dtype=torch.float64)
+    W = torch.randn(n_out, K, generator=g, dtype=torch.float64) / K ** 0.5
+    b = torch.randn(n_out, generator=g, dtype=torch.float64) * 0.1
+    go = torch.randn(rows, n_out, generator=g, dtype=torch.float64)
+    xr, Wr, br = (t.clone().requires_grad_(True) for t in (x, W, b))
+    pre = xr @ Wr.t() + br
+    y = torch.relu(pre) if act == 1 else (torch.sigmoid(pre) if act == 3 else pre)
+    y.backward(go)
+    xd, Wd, bd = (t.float().to(cuda).requires_grad_(True) for t in (x, W, b))
+    got = L.LinearAct.apply(xd.view(rows, 1, K), Wd, bd, act)
+    assert got.shape == (rows, 1, n_out)
+    got.backward(go.float().to(cuda).view(rows, 1, n_out))
+    rel = lambda a, r: float((a.double().cpu() - r).abs().max() / (r.abs().max() + 1e-30))
+    tol = 2e-5 * max(1.0, K / 400)           # (the tensor core truncates its fp32 accumulation: ~2^-24 per K step; plain TF32 would be ~1e-3)
+    errs = (rel(got.detach().view(rows, n_out), y.detach()), rel(xd.grad, xr.grad), rel(Wd.grad, Wr.grad), rel(bd.grad, br.grad))
+    print("linear_act", rows, K, n_out, act, ["%.2e" % e for e in errs])
+    assert errs[0] < tol and errs[1] < 2.5 * tol and errs[2] < 2.5 * tol * max(1.0, rows / K) and errs[3] < 2.5 * tol, errs
+
+
+def test_seq_map_roundtrip(cuda):
+    from sos_b200 import layers as L
+    h = torch.randn(37, 5, 70, device=cuda, requires_grad=True)
+    m = L.SeqToMap.apply(h)
+    assert torch.equal(m.detach(), h.detach().permute(1, 2, 0).contiguous())
+    go = torch.randn_like(m)
+    m.backward(go)
+    assert torch.equal(h.grad, go.permute(2, 0, 1).contiguous())
+
+
 @pytest.mark.parametrize("act", [1, 2])
 @pytest.mark.parametrize("C", [48, 96, 8, 256])
 def test_bn_act_train(cuda, act, C):
@@ -205,8 +262,10 @@ def test_bilstm_matches_torch(cuda, I, H, T, B):
     xd = x.detach().to(cuda).requires_grad_(True)
     got = mine(xd)
     got.backward(go.to(cuda))
-    assert float((got.cpu() - out.detach()).abs().max()) < 1e-5
-    assert float((xd.grad.cpu() - x.grad).abs().max()) < 1e-5
+    # (the projections and weight gradients are split-TF32 tensor-core GEMMs: exact products, but the tensor core's fp32 accumulation
+    #  truncates instead of rounding, ~2^-24 per K step: 1e-5 relative at K = 1600, vs 5e-4 for plain TF32)
+    assert float((got.cpu() - out.detach()).abs().max()) < 2e-5
+    assert float((xd.grad.cpu() - x.grad).abs().max()) < 5e-5 * float(x.grad.abs().max() + 1)
     for (k, p), (_, q) in zip(ref.named_parameters(), mine.named_parameters()):
         assert float((q.grad.cpu() - p.grad).abs().max()) < 1e-4 * float(p.grad.abs().max() + 1), k
 
