@@ -153,12 +153,16 @@ __global__ void gate_wave_kernel(const float* __restrict__ wave, int L, const ui
 
 }  // namespace
 
+int sos_stft_f16_init();
+int sos_stft_f16_launch(const float* wave, int64_t batch, int64_t length, float* spec_out, const uint8_t* bits, int64_t n_bits,
+                        const int32_t* frame_lo, double ratio, int gate_mode, cudaStream_t stream);
 int sos_stft_tc_init();
 int sos_stft_tc_launch(const float* wave, int64_t batch, int64_t length, float* spec_out, const uint8_t* bits, int64_t n_bits,
                        const int32_t* frame_lo, double ratio, int gate_mode, cudaStream_t stream);
 
 extern "C" int sos_init(void) {
   if (int e = init_tables()) return e;
+  if (int e = sos_stft_f16_init()) return e;
   return sos_stft_tc_init();
 }
 
@@ -167,6 +171,13 @@ extern "C" int sos_stft_forward(const float* wave, int64_t batch, int64_t length
   SOS_CHECK_ARG(wave && spec_out && batch > 0 && length > kNfft / 2, "sos_stft_forward: bad arguments (need length > 255)");
   SOS_CHECK_ARG(gate_mode == 0 || (bits && frame_lo && n_bits > 0 && ratio > 0), "sos_stft_forward: gating needs bits/frame_lo/ratio");
   SOS_CHECK_ARG(batch <= 65535, "sos_stft_forward: batch > 65535");
+  // default: the persistent half-split kernel (stft_f16.cu); clips too short for its tiling (< 43 frames), or SOS_STFT_TF32=1
+  // (A/B measurements, tests), run the one-tile-per-CTA TF32 kernel (stft_tc.cu)
+  static const bool force_tf32 = getenv("SOS_STFT_TF32") && atoi(getenv("SOS_STFT_TF32")) != 0;
+  if (!force_tf32) {
+    const int e = sos_stft_f16_launch(wave, batch, length, spec_out, bits, n_bits, frame_lo, ratio, gate_mode, stream);
+    if (e != SOS_ERR_UNSUPPORTED) return e;
+  }
   return sos_stft_tc_launch(wave, batch, length, spec_out, bits, n_bits, frame_lo, ratio, gate_mode, stream);
 }
 
