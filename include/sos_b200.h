@@ -54,6 +54,10 @@ int sos_stft_forward(const float* wave, int64_t batch, int64_t length, float* sp
 int sos_istft_forward(const float* spec, const float* crm_or_null, int64_t batch, int64_t n_frames, float* frames_ws,
                       float* wave_out, cudaStream_t stream);
 /* sos_gate_wave      M2/tools.py:340-362 + the gating multiplies; mode as gate_mode above (1 or 2). */
+/* The inverse transform's second stage alone: gather overlap-add of windowed inverse-DFT frames (batch * n_frames, 400) + division by
+ * the window-sum-square envelope + trim (librosa.istft, M2/transform.py:196-202).  The frames come from sos_istft_forward's own
+ * first stage or from a tensor-core GEMM (ops.istft: spectrogram rows x the windowed inverse-DFT table through ops.gemm3). */
+int sos_istft_ola(const float* frames, int64_t batch, int64_t n_frames, float* wave_out, cudaStream_t stream);
 int sos_gate_wave(const float* wave, int64_t batch, int64_t length, const uint8_t* bits, int64_t n_bits,
                   const int32_t* frame_lo, double ratio, int mode, float* out_or_null, float* mask_or_null,
                   cudaStream_t stream);
@@ -182,9 +186,12 @@ int sos_transpose(const float* in, int64_t rows, int64_t cols, float* out, cudaS
 /* fp32-grade GEMM operands for the tap GEMM (see the kernel comment in csrc/elementwise.cu): x = hi + lo with hi = tf32(x),
  * lo = tf32(x - hi); out[s * slot_stride + r * ld_out + k] = part_s(src[r * stride_r + (k + k_shift) * stride_k]) for r < R,
  * k < KP, zero where k >= K or the shifted index leaves [0, K).  n_slots = 2: {hi, lo} (activation stack); 3: {hi, hi, lo}
- * (weight slots along K).  One of the strides must be 1 (the kernel transposes through shared memory when stride_k != 1). */
+ * (weight slots along K).  One of the strides must be 1 (the kernel transposes through shared memory when stride_k != 1).
+ * batch > 1: that many independent (R, K) operands src + i * src_batch_stride -> out + i * out_batch_stride (e.g. the spectrogram of
+ * clip i, (512, T) with T contiguous, becoming rows i*T .. i*T + T - 1 of the inverse transform's activation operand). */
 int sos_split_tf32(const float* src, int64_t R, int64_t K, int64_t KP, int64_t stride_r, int64_t stride_k, int64_t k_shift, float* out,
-                   int64_t ld_out, int64_t slot_stride, int n_slots, cudaStream_t stream);
+                   int64_t ld_out, int64_t slot_stride, int n_slots, int64_t batch, int64_t src_batch_stride, int64_t out_batch_stride,
+                   cudaStream_t stream);
 /* dst = (base ? base : dst) + alpha * src (parameter gradients of the LSTM / Linear layers added into the flat gradient buffer;
  * b_ih + b_hh of the LSTM). */
 int sos_axpy(float* dst, const float* src, int64_t n, float alpha, const float* base_or_null, cudaStream_t stream);

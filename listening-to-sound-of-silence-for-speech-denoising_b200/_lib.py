@@ -83,7 +83,8 @@ _SIGS = {
     "sos_feat_to_seq": (C.c_int, [c_f, i64, i64, i64, i64, c_f, i64, i64, i64, S]),
     "sos_feat_to_seq_backward": (C.c_int, [c_f, i64, i64, i64, i64, c_f, i64, i64, i64, S]),
     "sos_transpose": (C.c_int, [c_f, i64, i64, c_f, S]),
-    "sos_split_tf32": (C.c_int, [c_f, i64, i64, i64, i64, i64, i64, c_f, i64, i64, C.c_int, S]),
+    "sos_split_tf32": (C.c_int, [c_f, i64, i64, i64, i64, i64, i64, c_f, i64, i64, C.c_int, i64, i64, i64, S]),
+    "sos_istft_ola": (C.c_int, [c_f, i64, i64, c_f, S]),
     "sos_axpy": (C.c_int, [c_f, c_f, i64, C.c_float, c_f, S]),
     "sos_seq_map": (C.c_int, [c_f, c_f, i64, i64, i64, i64, C.c_int, S]),
     "sos_bias_act": (C.c_int, [c_f, i64, i64, i64, c_f, C.c_int, S]),

@@ -926,9 +926,12 @@ __global__ void transpose_kernel(const float* __restrict__ in, long long rows, l
 //   shifted source index leaves [0, K)); n_slots = 2: parts {hi, lo}; n_slots = 3: {hi, hi, lo}.
 // One of sr / sk is 1: the 32 x 32 tile is read along that axis and written along k, i.e. the kernel also transposes.
 __global__ void split_tf32_kernel(const float* __restrict__ src, long long R, long long K, long long KP, long long sr, long long sk,
-                                  long long k_shift, float* __restrict__ out, long long ld_out, long long slot_stride, int n_slots) {
+                                  long long k_shift, float* __restrict__ out, long long ld_out, long long slot_stride, int n_slots,
+                                  long long src_batch_stride, long long out_batch_stride) {
   __shared__ float tile[32][33];
   const long long k0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+  src += blockIdx.z * src_batch_stride;                // (batched: grid.z independent (R, K) operands, e.g. one per clip)
+  out += blockIdx.z * out_batch_stride;
   if (sk == 1) {
     for (int i = threadIdx.y; i < 32; i += 8) {
       const long long r = r0 + i, k = k0 + threadIdx.x, ks = k + k_shift;
@@ -1574,12 +1577,14 @@ int sos_transpose(const float* in, int64_t rows, int64_t cols, float* out, cudaS
 }
 
 int sos_split_tf32(const float* src, int64_t R, int64_t K, int64_t KP, int64_t stride_r, int64_t stride_k, int64_t k_shift, float* out,
-                   int64_t ld_out, int64_t slot_stride, int n_slots, cudaStream_t stream) {
+                   int64_t ld_out, int64_t slot_stride, int n_slots, int64_t batch, int64_t src_batch_stride, int64_t out_batch_stride,
+                   cudaStream_t stream) {
   SOS_CHECK_ARG(src && out && R > 0 && K > 0 && KP >= K && (n_slots == 2 || n_slots == 3), "sos_split_tf32: bad arguments");
   SOS_CHECK_ARG(stride_r == 1 || stride_k == 1, "sos_split_tf32: one of the source strides must be 1");
-  SOS_CHECK_ARG(ceil_div_ll(R, 32) <= 65535, "sos_split_tf32: too many rows");
-  dim3 grid((unsigned)ceil_div_ll(KP, 32), (unsigned)ceil_div_ll(R, 32));
-  split_tf32_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, R, K, KP, stride_r, stride_k, k_shift, out, ld_out, slot_stride, n_slots);
+  SOS_CHECK_ARG(ceil_div_ll(R, 32) <= 65535 && batch >= 1 && batch <= 65535, "sos_split_tf32: too many rows / batches");
+  dim3 grid((unsigned)ceil_div_ll(KP, 32), (unsigned)ceil_div_ll(R, 32), (unsigned)batch);
+  split_tf32_kernel<<<grid, dim3(32, 8), 0, stream>>>(src, R, K, KP, stride_r, stride_k, k_shift, out, ld_out, slot_stride, n_slots,
+                                                      src_batch_stride, out_batch_stride);
   SOS_CHECK_LAUNCH("sos_split_tf32");
   return SOS_OK;
 }

@@ -197,6 +197,16 @@ extern "C" int sos_istft_forward(const float* spec, const float* crm_or_null, in
   return SOS_OK;
 }
 
+extern "C" int sos_istft_ola(const float* frames, int64_t batch, int64_t n_frames, float* wave_out, cudaStream_t stream) {
+  SOS_CHECK_ARG(frames && wave_out && batch > 0 && batch <= 65535 && n_frames > 1, "sos_istft_ola: bad arguments");
+  if (int e = init_tables()) return e;
+  const int T = (int)n_frames, out_len = kHop * (T - 1);
+  dim3 g2(ceil_div(out_len, 256), (unsigned)batch);
+  istft_ola_kernel<<<g2, 256, 0, stream>>>(frames, T, g_w2, wave_out, out_len);
+  SOS_CHECK_LAUNCH("sos_istft_ola");
+  return SOS_OK;
+}
+
 extern "C" int sos_gate_wave(const float* wave, int64_t batch, int64_t length, const uint8_t* bits, int64_t n_bits,
                              const int32_t* frame_lo, double ratio, int mode, float* out_or_null, float* mask_or_null,
                              cudaStream_t stream) {

