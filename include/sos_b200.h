@@ -83,6 +83,20 @@ int sos_crm_forward(const float* clean_spec, const float* mixed_spec, float* crm
 /* sos_ssnr           M2/metrics.py:86-129 metrics_ssnr (shift = 0) and :132-175 metrics_ssnr_shift (shift = 1), the evaluation
  *   step's segmental SNR (30 ms Hann-windowed frames, quarter-frame hop, each clamped to [min_snr, max_snr]) and overall SNR,
  *   for a batch of equally long waveform pairs: ref, deg (B, L) -> overall_out, segmental_out (B). */
+/* librosa.load's resampler (M2/predict.py:303, M1/dataset.py:226) = resampy.resample(filter='kaiser_best'): x (batch, n_in) ->
+ * y (batch, n_out), n_out = int(n_in * ratio).  interp_win / interp_delta: the half filter table and its forward differences
+ * (doubles, n_win entries, num_table samples per zero crossing; scaled by the ratio when down-sampling), time_register[t] = the
+ * reference's repeatedly-added input time of output sample t.  Built by ops.resample. */
+int sos_resample(const float* x, int64_t batch, int64_t n_in, float* y, int64_t n_out, const double* interp_win,
+                 const double* interp_delta, int64_t n_win, int64_t num_table, double sample_ratio, const double* time_register,
+                 cudaStream_t stream);
+/* Frame-wise objective measures of M2/metrics.py on (batch, length) waveform pairs: 30 ms Hann frames every 7.5 ms,
+ * sos_metric_frames(length, srate) of them per clip.  sos_wss: weighted spectral slope distance per frame (:404-558);
+ * sos_llr: log-likelihood ratio per frame from order-16 (10 below 10 kHz) LPC (:561-681).  dist_out (batch, frames) doubles. */
+int sos_metric_frames(int64_t length, int64_t srate);
+int sos_wss(const float* ref, const float* deg, int64_t batch, int64_t length, int64_t srate, double eps, double* dist_out,
+            cudaStream_t stream);
+int sos_llr(const float* ref, const float* deg, int64_t batch, int64_t length, int64_t srate, double* dist_out, cudaStream_t stream);
 int sos_ssnr(const float* ref, const float* deg, int64_t batch, int64_t length, int64_t srate, double win_len_ms, float min_snr,
              float max_snr, double eps, int shift, float* overall_out, float* segmental_out, cudaStream_t stream);
 

@@ -52,6 +52,10 @@ _SIGS = {
     "sos_icrm_backward": (C.c_int, [c_f, c_f, c_f, c_f, i64, i64, C.c_float, S]),
     "sos_add_signals": (C.c_int, [c_f, c_f, c_f, i64, i64, C.c_float, c_f, c_f, c_f, S]),
     "sos_crm_forward": (C.c_int, [c_f, c_f, c_f, i64, i64, C.c_float, C.c_float, S]),
+    "sos_resample": (C.c_int, [c_f, i64, i64, c_f, i64, c_f, c_f, i64, i64, C.c_double, c_f, S]),
+    "sos_metric_frames": (C.c_int, [i64, i64]),
+    "sos_wss": (C.c_int, [c_f, c_f, i64, i64, i64, C.c_double, c_f, S]),
+    "sos_llr": (C.c_int, [c_f, c_f, i64, i64, i64, c_f, S]),
     "sos_ssnr": (C.c_int, [c_f, c_f, i64, i64, i64, C.c_double, C.c_float, C.c_float, C.c_double, C.c_int, c_f, c_f, S]),
     "sos_mse_fwd_bwd": (C.c_int, [c_f, c_f, i64, c_f, c_f, C.c_float, S]),
     "sos_bce_logits_fwd_bwd": (C.c_int, [c_f, c_f, i64, c_f, c_f, C.c_float, S]),

@@ -232,6 +232,48 @@ def istft(spec, crm=None, tensor_core=True):
     return out
 
 
+# ----------------------------------------------------------------------------------------------- audio loading (librosa.load)
+_RESAMPLE_FILTERS = {}
+
+
+def _kaiser_best(ratio, device):
+    """resampy's 'kaiser_best' interpolation table (64 zero crossings x 512 samples, rolloff 0.9475937167399596, Kaiser beta
+    14.769656459379492; resampy/filters.py sinc_window), scaled by the ratio when down-sampling, and its forward differences."""
+    import numpy as np
+    from scipy.signal.windows import kaiser
+    key = (float(ratio), str(device))
+    if key not in _RESAMPLE_FILTERS:
+        num_bits, num_zeros = 512, 64
+        n = num_bits * num_zeros
+        win = kaiser(2 * n + 1, 14.769656459379492)[n:] * 0.9475937167399596 * np.sinc(0.9475937167399596 * np.linspace(0, num_zeros, num=n + 1, endpoint=True))
+        if ratio < 1:
+            win = win * ratio
+        delta = np.zeros_like(win)
+        delta[:-1] = np.diff(win)
+        _RESAMPLE_FILTERS[key] = (torch.tensor(win, dtype=torch.float64, device=device), torch.tensor(delta, dtype=torch.float64, device=device), num_bits)
+    return _RESAMPLE_FILTERS[key]
+
+
+def resample(wave, sr_orig, sr_new):
+    """wave (B, n) fp32 -> (B, int(n * sr_new / sr_orig)): resampy.resample(filter='kaiser_best'), the resampler behind
+    librosa.load(path, sr=...) (M2/predict.py:303, M1/dataset.py:226)."""
+    import numpy as np
+    B, n = wave.shape
+    ratio = float(sr_new) / float(sr_orig)
+    n_out = int(n * ratio)
+    if n_out < 1:
+        raise _lib.SosError(f"resample: input of {n} samples is too short for the ratio {ratio}")
+    win, delta, num_table = _kaiser_best(ratio, wave.device)
+    # the reference advances its time register by repeated addition of 1 / ratio (float64): the same cumulative sum here
+    treg = np.concatenate([[0.0], np.cumsum(np.full(n_out - 1, 1.0 / ratio))]) if n_out > 1 else np.zeros(1)
+    treg = torch.tensor(treg, dtype=torch.float64, device=wave.device)
+    out = torch.empty(B, n_out, device=wave.device, dtype=torch.float32)
+    pd = lambda a: C.c_void_p(a.data_ptr())
+    check(lib().sos_resample(_p(wave), B, n, _p(out), n_out, pd(win), pd(delta), win.numel(), num_table, ratio, pd(treg), _stream()), "sos_resample")
+    _count()
+    return out
+
+
 def gate_wave(wave, bits, ratio, mode=1, want_mask=False):
     B, L = wave.shape
     nb = bits.shape[1]

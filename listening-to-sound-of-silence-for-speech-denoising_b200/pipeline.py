@@ -65,8 +65,7 @@ class GraphedDenoiser(object):
 
 # ----------------------------------------------------------------------------------------------- predict.py-compatible driver
 def _read_wav(path):
-    """-> (float32 mono waveform in [-1, 1], sample rate).  (librosa.load's resampling, SURVEY 8f-3, is not built: the file must
-    already be at the model's sample rate.)"""
+    """-> (float32 mono waveform in [-1, 1], sample rate) without resampling."""
     import numpy as np
     from scipy.io import wavfile
     sr, x = wavfile.read(path)
@@ -88,16 +87,24 @@ def _write_wav(path, x, sr):
 
 def predict_files(files, sid, joint, out_dir, sr=16000, fps=30.0, threshold=0.5, bit_streams=None, snr=None, save_audio=True):
     """What the reference does with three programs and JSON / WAV hand-offs (M1/predict.py:107-233 -> M1/create_data_from_pred.py:60-270
-    -> M2/predict.py:395-530), per file and fully on the device: silent-interval prediction for the WHOLE file
-    (v_num_frames = number of video frames it covers), gating, denoising, and the same artefacts:
+    -> M2/predict.py:395-530), per file and fully on the device.  Like the reference's prediction phase, the detector sees the WHOLE
+    file in one pass (M1/tools.py:328-330 builds ONE item per file with its whole bit stream when pred=True and M1/dataset.py:225-233
+    feeds `audio = snd`, so v_num_frames = the number of video frames the file covers, M1/predict.py:117); then gating, denoising,
+    and the same artefacts:
 
+      out_dir/eval_results.json           M1/predict.py:185-233: data_total_frames, data_center_frames, sigmoid_threshold, snr,
+                                          prediction_statistics {"all": show_metrics}, data[...] (id, path, full_bit_stream, num_frames,
+                                          framerate, audio_sample_rate, audio_samples, duration, frame_start_idx, label, pred_label,
+                                          match, confidence), sorted by mean confidence, descending
       out_dir/pred_data.json              the hierarchy create_data_from_pred.py writes (dataset_path, num_videos, data_total_frames,
                                           data_center_frames, sigmoid_threshold, snr, prediction_statistics, files[...])
       out_dir/<k>/{noisy_input,noise_intervals,predicted_full_noise,denoised_output}.wav      (M2/predict.py:510-522)
 
-    files: list of WAV paths or (name, waveform ndarray) pairs, each at `sr`; clips may have different lengths.
-    bit_streams: optional ground-truth strings ('0' = silent) per file -> prediction_statistics (accuracy / precision / recall of
-    the silent class).  Returns the hierarchy dict."""
+    files: list of WAV paths or (name, waveform ndarray at `sr`) pairs; clips may have different lengths.  WAV files at another
+    sample rate (or stereo) go through tools.load_audio = librosa.load(path, sr=sr) (M2/predict.py:303: kaiser_best resampling on the
+    device).  bit_streams: optional ground-truth strings ('0' = silent) per file -> prediction_statistics.  The reference's own
+    models run at sr = 14000 (DATA_REQUIRED_SR, M1/dataset.py:38); BASELINE.json's configurations at 16000 (the default here).
+    Returns the pred_data hierarchy dict."""
     import json
     import os
     from collections import OrderedDict
@@ -105,28 +112,34 @@ def predict_files(files, sid, joint, out_dir, sr=16000, fps=30.0, threshold=0.5,
     os.makedirs(out_dir, exist_ok=True)
     dev = next(joint.parameters()).device
     ratio = sr / fps
-    groups, labels, preds = [], [], []
+    groups, labels, preds, stat = [], [], [], []
     for k, f in enumerate(files):
         if isinstance(f, (tuple, list)):
             name, x = f[0], np.asarray(f[1], dtype=np.float32)
+            wave = torch.from_numpy(x).to(dev)[None]
         else:
             name = f
-            x, file_sr = _read_wav(f)
-            if file_sr != sr:
-                raise ValueError(f"{f}: sample rate {file_sr} != {sr} (resample first; librosa.load's resampler is not part of this path)")
+            w, _ = tools.load_audio(f, sr=sr, device=dev)           # librosa.load(path, sr=sr)
+            wave = w[None]
+            x = w.cpu().numpy()
         n_frames = int(len(x) / ratio)
         if n_frames < 1 or 1 + len(x) // 158 < 68:                  # ReflectionPad2d(16) on the T/4 axis (M2/networks.py:176)
             raise RuntimeError(f"{name}: clip of {len(x)} samples is too short for the networks (needs at least 68 STFT frames)")
-        wave = torch.from_numpy(x).to(dev)[None]
         out = denoise(wave, sid, joint, sr, fps, threshold)
         bits = out["bits"][0].cpu().numpy()
+        conf = out["confidence"][0].cpu().numpy()
         pred = "".join(str(int(b)) for b in bits)
+        gt = (bit_streams[k][:n_frames] if bit_streams else None)
         item = OrderedDict([("path", str(name)), ("num_frames", n_frames), ("framerate", fps), ("audio_sample_rate", sr),
                             ("audio_samples", int(len(x))), ("duration", len(x) / sr),
                             ("bit_stream", bit_streams[k] if bit_streams else None), ("predicted_bit_stream", pred),
                             ("recovered_prediction", pred)])
-        if bit_streams:
-            gt = bit_streams[k][:n_frames]
+        label = list(gt) if gt else None
+        stat.append(OrderedDict([("id", k), ("path", str(name)), ("full_bit_stream", bit_streams[k] if bit_streams else None),
+                                 ("num_frames", n_frames), ("framerate", fps), ("audio_sample_rate", sr), ("audio_samples", int(len(x))),
+                                 ("duration", len(x) / sr), ("frame_start_idx", 0), ("label", label), ("pred_label", list(pred)),
+                                 ("match", label == list(pred) if label else None), ("confidence", [str(c) for c in conf.astype(np.float32)])]))
+        if gt:
             labels += [int(c) for c in gt]
             preds += [int(c) for c in pred[:len(gt)]]
         if save_audio:
@@ -142,11 +155,14 @@ def predict_files(files, sid, joint, out_dir, sr=16000, fps=30.0, threshold=0.5,
             item["mixed_audio"] = os.path.join(str(k), "noisy_input.wav")
             item["denoised_output"] = os.path.join(str(k), "denoised_output.wav")
         groups.append(item)
-    stats = None
-    if labels:                                                     # silent frames ('0') are the positive class, as in show_metrics
-        l, p = np.array(labels), np.array(preds)
-        tp, fp, fn = int(((l == 0) & (p == 0)).sum()), int(((l == 1) & (p == 0)).sum()), int(((l == 0) & (p == 1)).sum())
-        stats = OrderedDict([("accuracy", float((l == p).mean())), ("precision", tp / max(tp + fp, 1)), ("recall", tp / max(tp + fn, 1))])
+    stats = tools.show_metrics(labels, preds) if labels else None
+    # ---- eval_results.json (M1/predict.py:185-233)
+    stat = sorted(stat, key=lambda it: float(np.mean([float(c) for c in it["confidence"]])), reverse=True)
+    eval_results = OrderedDict([("data_total_frames", None), ("data_center_frames", None), ("sigmoid_threshold", threshold), ("snr", snr),
+                                ("prediction_statistics", OrderedDict([("all", stats)])), ("data", stat)])
+    with open(os.path.join(out_dir, "eval_results.json"), "w") as fp_:
+        json.dump(eval_results, fp_, indent=2)
+    # ---- pred_data.json (M1/create_data_from_pred.py:212-270)
     paths = [g["path"] for g in groups]
     hierarchy = OrderedDict([("dataset_path", os.path.commonpath(paths) if all(os.path.isabs(p) for p in paths) else ""),
                              ("num_videos", len(groups)), ("data_total_frames", None), ("data_center_frames", None),

@@ -30,7 +30,48 @@ def cases():
     return out
 
 
+def reference_lpc_functions():
+    """wss / llr / lpcoeff of M2/metrics.py, exec'd unmodified (they need numpy and scipy.linalg.toeplitz only)."""
+    from scipy.linalg import toeplitz
+    src = open(REF).read()
+    ns = {"np": np, "toeplitz": toeplitz}
+    for name in ("wss", "llr", "lpcoeff"):
+        m = re.search(r"^def %s\(.*?(?=^(def |#@nb))" % name, src, flags=re.S | re.M) or re.search(r"^def %s\(.*" % name, src, flags=re.S | re.M)
+        exec(m.group(0), ns)
+    return ns["wss"], ns["llr"]
+
+
+def lpc_cases():
+    sys.path.insert(0, ROOT)
+    from oracle import synth
+    out = []
+    for index, length, srate in ((0, 16000, 16000), (3, 14000, 14000), (6, 8000, 8000)):
+        out.append((index, length, srate) + lpc_pair(index, length, srate))
+    return out
+
+
+def lpc_pair(index, length, srate):
+    """Reference / degraded waveforms of the WSS / LLR fixtures: the synthetic clean speech (a sum of five harmonics, which an order-16
+    predictor would fit almost perfectly and leave float32 cancellation noise in the LLR's quadratic forms) plus white noise at
+    -26 dB, against the same speech plus a stronger, coloured noise."""
+    sys.path.insert(0, ROOT)
+    from oracle import synth
+    c = synth.make_clip(index, length, srate)
+    rng = np.random.default_rng(9000 + index)
+    ref = c["clean"].astype(np.float64) + 0.01 * rng.standard_normal(length)
+    deg = 0.9 * c["clean"].astype(np.float64) + 0.15 * c["full_noise"] + 0.02 * rng.standard_normal(length)
+    return ref.astype(np.float32).astype(np.float64), deg.astype(np.float32).astype(np.float64)
+
+
 if __name__ == "__main__":
+    wss_ref, llr_ref = reference_lpc_functions()
+    lpc = {}
+    for index, length, srate, ref_w, deg_w in lpc_cases():
+        lpc[f"wss:{index}:{length}:{srate}"] = np.array(wss_ref(ref_w, deg_w, srate), dtype=np.float64)
+        lpc[f"llr:{index}:{length}:{srate}"] = np.array(llr_ref(ref_w, deg_w, srate), dtype=np.float64)
+        print(index, srate, "wss frames", len(lpc[f"wss:{index}:{length}:{srate}"]), "mean", lpc[f"wss:{index}:{length}:{srate}"].mean(),
+              "llr mean", np.nanmean(lpc[f"llr:{index}:{length}:{srate}"]))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "metrics_lpc.npz"), **lpc)
     ssnr, ssnr_shift = reference_functions()
     rows = []
     for index, length, clean, mixed in cases():
