@@ -7,6 +7,8 @@
 // product instead of a kernel launch.  The grid (2 * ceil(H / kUnits) blocks, <= 128 for H <= 512) must be co-resident:
 // it is launched with one block per SM's worth of shared memory and the host checks it against the SM count.
 #include "common.cuh"
+#include <atomic>
+#include <mutex>
 #include "sos_b200.h"
 #include <algorithm>
 
@@ -258,14 +260,18 @@ __global__ void __launch_bounds__(kLstmThreads) lstm_bwd_step_kernel(const float
 
 // Barrier counters: a ring of slots so that launches on different streams do not share one (2 counters per launch).
 static unsigned int* g_sync = nullptr;
-static int g_sync_next = 0;
-constexpr int kSyncSlots = 64;
+static std::atomic<unsigned> g_sync_next{0};
+static std::mutex g_sync_mutex;
+constexpr int kSyncSlots = 256;
 static unsigned int* next_sync_slot(cudaStream_t stream) {
-  if (!g_sync && cudaMalloc(&g_sync, kSyncSlots * 2 * sizeof(unsigned int)) != cudaSuccess) {
-    g_sync = nullptr;
-    return nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_sync_mutex);
+    if (!g_sync && cudaMalloc(&g_sync, kSyncSlots * 2 * sizeof(unsigned int)) != cudaSuccess) {
+      g_sync = nullptr;
+      return nullptr;
+    }
   }
-  unsigned int* p = g_sync + 2 * (g_sync_next++ % kSyncSlots);
+  unsigned int* p = g_sync + 2 * (g_sync_next.fetch_add(1) % kSyncSlots);
   if (cudaMemsetAsync(p, 0, 2 * sizeof(unsigned int), stream) != cudaSuccess) return nullptr;
   return p;
 }
@@ -294,8 +300,14 @@ extern "C" int sos_lstm_forward(const float* gx, const float* w_hh, int64_t T, i
     sos_set_error("sos_lstm_forward: cannot allocate the barrier counters");
     return SOS_ERR_CUDA;
   }
-  lstm_fwd_step_kernel<<<grid, kLstmThreads, smem, stream>>>(gx, w_hh, (int)T, (int)B, (int)H, out, gates_ws, cell_ws, sync);
-  SOS_CHECK_LAUNCH("sos_lstm_forward");
+  // the kernel's blocks meet at a global-memory barrier between time steps: a COOPERATIVE launch, so that the driver guarantees
+  // their co-residency (or refuses) whatever else runs on the device (another stream's weight gradients, NCCL, the other agent)
+  int Ti = (int)T, Bi = (int)B, Hi = (int)H;
+  void* args[] = {(void*)&gx, (void*)&w_hh, (void*)&Ti, (void*)&Bi, (void*)&Hi, (void*)&out, (void*)&gates_ws, (void*)&cell_ws, (void*)&sync};
+  if (cudaLaunchCooperativeKernel((const void*)lstm_fwd_step_kernel, grid, dim3(kLstmThreads), args, smem, stream) != cudaSuccess) {
+    sos_set_error("sos_lstm_forward: cooperative launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return SOS_ERR_CUDA;
+  }
   return SOS_OK;
 }
 
@@ -322,7 +334,11 @@ extern "C" int sos_lstm_backward(const float* dout, const float* w_hh, const flo
     sos_set_error("sos_lstm_backward: cannot allocate the barrier counters");
     return SOS_ERR_CUDA;
   }
-  lstm_bwd_step_kernel<<<grid, kLstmThreads, smem, stream>>>(dout, w_hh, gates_ws, cell_ws, (int)T, (int)B, (int)H, dgx, dc_ws, sync);
-  SOS_CHECK_LAUNCH("sos_lstm_backward");
+  int Ti = (int)T, Bi = (int)B, Hi = (int)H;
+  void* args[] = {(void*)&dout, (void*)&w_hh, (void*)&gates_ws, (void*)&cell_ws, (void*)&Ti, (void*)&Bi, (void*)&Hi, (void*)&dgx, (void*)&dc_ws, (void*)&sync};
+  if (cudaLaunchCooperativeKernel((const void*)lstm_bwd_step_kernel, grid, dim3(kLstmThreads), args, smem, stream) != cudaSuccess) {
+    sos_set_error("sos_lstm_backward: cooperative launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return SOS_ERR_CUDA;
+  }
   return SOS_OK;
 }

@@ -292,8 +292,10 @@ bool g_cluster_broken = false;     // a failed cluster launch (e.g. no GPC can h
 
 template <typename... Args>
 cudaError_t launch_cluster(void (*kernel)(Args...), int nblk, int threads, size_t smem, cudaStream_t stream, Args... args) {
-  static size_t smem_set[2] = {0, 0};             // per kernel instantiation: attributes are set outside any stream capture
-  size_t& cur = smem_set[0];
+  static size_t smem_set[64] = {0};               // per kernel instantiation AND device: function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  size_t& cur = smem_set[dev & 63];
   if (smem > cur) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
