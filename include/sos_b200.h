@@ -290,6 +290,10 @@ int sos_conv_stats_rows(void);   /* upper bound of *stats_rows_out (4 x SM count
  * per distinct (shapes, taps, types) key and reused; tensor maps are re-encoded only when a base pointer changes. */
 void sos_plan_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries);
 int sos_conv2d_tc(const sos_conv_args* args, cudaStream_t stream);
+/* Host-only planner query (no CUDA call, pointers other than the tap arrays are ignored): info[16] = {fast_is_w, share, lattice g,
+ * sub-tiles S, tap groups, pipeline stages, stage bytes, grid, K chunk (elements), K chunks, N, epilogue chunk, FB, SB, tiles,
+ * dynamic shared memory}. */
+int sos_conv2d_plan(const sos_conv_args* args, int32_t* info);
 
 /* Weight gradient of the same operator (split over pixels, accumulated with fp32 atomics):
  *   dw[t][co][ci] += sum_{n,oh,ow} dy[n, oh, ow, dy_coff + co] * x[n, oh*stride + tap_dh[t], ow*stride + tap_dw[t], ci]

@@ -98,6 +98,7 @@ _SIGS = {
     "sos_pack_taps_half": (C.c_int, [c_f, i64, i64, i64, i64, i64, i64, C.POINTER(C.c_int32), c_f, S]),
     "sos_unpack_wgrad": (C.c_int, [c_f, i64, i64, i64, i64, c_f, C.c_int, S]),
     "sos_conv2d_tc": (C.c_int, [C.POINTER(ConvArgs), S]),
+    "sos_conv2d_plan": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(C.c_int32)]),
     "sos_conv2d_wgrad": (C.c_int, [C.POINTER(WgradArgs), S]),
     "sos_lstm_forward": (C.c_int, [c_f, c_f, i64, i64, i64, c_f, c_f, c_f, S]),
     "sos_lstm_backward": (C.c_int, [c_f, c_f, c_f, c_f, c_f, i64, i64, i64, c_f, c_f, c_f, S]),

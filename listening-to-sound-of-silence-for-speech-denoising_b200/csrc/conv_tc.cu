@@ -153,32 +153,36 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
   } else if (warp == 1 || warp == 6) {
     // ===================================================================== MMA issuer(s)
     const int issuer = warp == 1 ? 0 : 1;
-    if (issuer < p.n_issuers) {
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    // descriptor words: hi = SBO | version | layout (constant); lo = (address >> 4) | LBO, advanced by the program's deltas
-    const uint32_t desc_hi = (uint32_t)((p.sbo >> 4) & 0x3FFF) | (1u << 14) | ((uint32_t)(p.layout_type & 7) << 29);
-    const uint32_t lbo_bits = (16u >> 4) << 16;
-    const uint32_t idesc = p.idesc;
-    const uint32_t b_off = (uint32_t)p.S * p.a_box_stride;
-    for (int ct = blockIdx.x; ct < p.total_ctiles; ct += gridDim.x) {
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1, 200);
-      tc_fence_after();
-      const uint32_t d_base = tmem_base + (uint32_t)acc * 256;
-      int l = 0;
-      for (int g = 0; g < p.n_groups; ++g) {
-        const int per = p.prog_n[g] / p.n_issuers;          // the program lists sub-tile 0's MMAs first, then sub-tile 1's
-        const int m0 = p.prog0[g] + issuer * per, m1 = m0 + per;
-        for (int c = 0; c < p.n_chunks; ++c, ++l) {
-          mbar_wait(full_bar(stage), phase, 201);
-          tc_fence_after();
-          if (elect_one_sync()) {
-            const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
-            const uint32_t a_lo = (sbase >> 4) | lbo_bits, b_lo = ((sbase + b_off) >> 4) | lbo_bits;
-            const uint32_t first_mask = l == 0 ? 1u : 0u;
-#pragma unroll 4
+    // ONE thread runs the whole issue loop (elected once, outside every loop: per pipeline stage the thread then executes a
+    // barrier poll, two address adds, its MMAs and one commit -- no per-stage elect / reconvergence, no integer division).
+    // An N = 48 MMA lasts 24 cycles and a stage holds only 5-15 of them, so every instruction of this loop is on the kernel's
+    // critical path (ncu r02: 124 instructions / 965 cycles per 5-MMA stage before this form).
+    if (issuer < p.n_issuers && elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      // descriptor words: hi = SBO | version | layout (constant); lo = (address >> 4) | LBO, advanced by the program's deltas
+      const uint32_t desc_hi = (uint32_t)((p.sbo >> 4) & 0x3FFF) | (1u << 14) | ((uint32_t)(p.layout_type & 7) << 29);
+      const uint32_t lbo_bits = (16u >> 4) << 16;
+      const uint32_t idesc = p.idesc;
+      const uint32_t a_lo0 = (stages_base >> 4) | lbo_bits;
+      const uint32_t b_lo0 = ((stages_base + (uint32_t)p.S * p.a_box_stride) >> 4) | lbo_bits;
+      const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
+      const int n_groups = p.n_groups, n_chunks = p.n_chunks, n_stages = p.n_stages;
+      for (int ct = blockIdx.x; ct < p.total_ctiles; ct += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1, 200);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)acc * 256;
+        uint32_t first_mask = 1u;
+        for (int g = 0; g < n_groups; ++g) {
+          const int per = p.prog_n[g];                         // MMAs per issuer and stage; the program lists sub-tile 0's first
+          const int m0 = p.prog0[g] + issuer * per, m1 = m0 + per;
+          for (int c = 0; c < n_chunks; ++c) {
+            mbar_wait(full_bar(stage), phase, 201);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_step, b_lo = b_lo0 + (uint32_t)stage * stage_step;
+#pragma unroll 5
             for (int m = m0; m < m1; ++m) {
               const uint4 e = p.prog[m];
               const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + e.x);
@@ -186,14 +190,13 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
               umma<KIND>(d_base + e.z, ad, bd, idesc, (e.w & first_mask) == 0u);
             }
             umma_commit(empty_bar(stage));                 // frees the smem stage when these MMAs retire
-            if (l == loads_per_tile - 1) umma_commit(tfull_bar(acc));
+            first_mask = 0u;
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
-          __syncwarp();
-          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
         }
+        umma_commit(tfull_bar(acc));                       // (tracks every MMA this thread issued before it)
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
@@ -507,7 +510,7 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
             SOS_CHECK_ARG(n < kMaxProg, "sos_conv2d_tc: MMA program of %d entries is too long", n);
             p.prog[n++] = make_uint4(a_delta >> 4, b_delta >> 4, (uint32_t)s2 * N, (j == 0 && kk == 0) ? 1u : 0u);
           }
-      p.prog_n[gi] = (int16_t)(n - p.prog0[gi]);
+      p.prog_n[gi] = (int16_t)((n - p.prog0[gi]) / p.n_issuers);   // per issuer (sub-tile)
     }
   }
   p.stats_c = (int)a.stats_channels;
@@ -654,3 +657,16 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
 }
 
 extern "C" int sos_conv_stats_rows(void) { return 4 * sos_num_sms(); }
+
+// Host-only planner query (no CUDA call): what sos_conv2d_tc would choose for these shapes / taps / types.
+extern "C" int sos_conv2d_plan(const sos_conv_args* ap, int32_t* info) {
+  SOS_CHECK_ARG(ap != nullptr && info != nullptr && ap->tap_dh && ap->tap_dw, "sos_conv2d_plan: null pointer");
+  SOS_CHECK_ARG(ap->ntaps > 0 && ap->ntaps <= 49 && ap->Cin >= 8 && ap->Cin % 8 == 0 && ap->Cout > 0, "sos_conv2d_plan: bad shapes");
+  TcPlan plan;
+  if (int e = plan_conv2d_tc(*ap, plan)) return e;
+  const TcParams& p = plan.p;
+  const int32_t v[16] = {plan.plan_out[0], plan.plan_out[1], plan.plan_out[2], p.S, p.n_groups, p.n_stages, p.stage_bytes, plan.grid,
+                         p.cbe, p.n_chunks, p.N, p.ec, p.FB, p.SB, p.total_ctiles, plan.smem};
+  memcpy(info, v, sizeof(v));
+  return SOS_OK;
+}

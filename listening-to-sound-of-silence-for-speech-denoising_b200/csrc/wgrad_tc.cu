@@ -40,7 +40,7 @@ constexpr int kMaxSlots = 64;
 
 // One TMEM accumulator of a job: x box `x_idx` of the stage shifted by `shift` slow rows; accumulator rows 0..63 (all 128
 // when not stacked) receive tap `tap_lo`, rows 64..127 tap `tap_hi` (-1: unused).
-struct WgSlot { int16_t x_idx, shift, tap_lo, tap_hi; };
+struct WgSlot { int16_t x_idx, shift, tap_lo, tap_hi; uint32_t b_off16; };   // b_off16: byte offset of the slot's x operand inside the stage's x area, >> 4
 
 struct alignas(64) WgParams {
   CUtensorMap mapX, mapDY;
@@ -151,36 +151,37 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    int stage = 0;
-    uint32_t phase = 0, acc_phase = 0;
-    const uint32_t a_inc = (uint32_t)p.kstep_bytes >> 4, b_inc = a_inc;        // one k step (8 or 16 pixels) of one chunk
-    const uint32_t desc_hi = p.desc_hi;
-    const uint32_t x_lbo_bits = ((uint32_t)p.x_box_stride >> 4) << 16;
-    const uint32_t idesc = p.idesc;
-    const int ksteps = p.ksteps;
-    for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
-      const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
-      const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
-      if (t0 >= t1) continue;
-      const int s0 = p.job_s0[job], ns = p.job_ns[job];
-      mbar_wait(tempty_bar, acc_phase ^ 1, 600);
-      tc_fence_after();
-      for (int tile = t0; tile < t1; ++tile) {
-        mbar_wait(full_bar(stage), phase, 601);
+    // ONE elected thread runs the whole issue loop (see conv_tc.cu): per stage a barrier poll, per accumulator slot two adds,
+    // per MMA two adds -- the 24/48-cycle MMAs leave no room for per-stage elect / reconvergence or address arithmetic.
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint32_t a_inc = (uint32_t)p.kstep_bytes >> 4, b_inc = a_inc;        // one k step (8 or 16 pixels) of one chunk
+      const uint32_t desc_hi = p.desc_hi;
+      const uint32_t idesc = p.idesc;
+      const int ksteps = p.ksteps, n_stages = p.n_stages;
+      const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
+      // descriptor words: hi = SBO | version | layout; lo = (address >> 4) | LBO (chunk pitch); one k step = 8 / 16 pixels
+      const uint32_t a_lo_base = (stages_base >> 4) | (((uint32_t)p.dy_chunk_stride >> 4) << 16);
+      const uint32_t b_lo_base = ((stages_base + (uint32_t)p.x_off) >> 4) | (((uint32_t)p.x_box_stride >> 4) << 16);
+      const uint32_t N = (uint32_t)p.N;
+      for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
+        const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
+        const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
+        if (t0 >= t1) continue;
+        const int s0 = p.job_s0[job], ns = p.job_ns[job];
+        mbar_wait(tempty_bar, acc_phase ^ 1, 600);
         tc_fence_after();
-        if (elect_one_sync()) {
-          // descriptor words: hi = SBO (512) | version | layout 1; lo = (address >> 4) | LBO (chunk pitch); one k step = 8 pixels
-          const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
-          const uint32_t a_lo0 = (sbase >> 4) | (((uint32_t)p.dy_chunk_stride >> 4) << 16);
-          const uint32_t xbase = sbase + p.x_off;
-          const uint32_t first = tile != t0 ? 1u : 0u;
-          for (int i = 0; i < ns; ++i) {
-            const WgSlot sl = p.slots[s0 + i];
-            const uint32_t d = tmem_base + (uint32_t)i * p.N;
-            const uint32_t xb = xbase + (uint32_t)sl.x_idx * p.n_ci_chunks * p.x_box_stride;
+        uint32_t first = 0u;
+        for (int tile = t0; tile < t1; ++tile) {
+          mbar_wait(full_bar(stage), phase, 601);
+          tc_fence_after();
+          const uint32_t a_lo0 = a_lo_base + (uint32_t)stage * stage_step, b_lo0 = b_lo_base + (uint32_t)stage * stage_step;
+          uint32_t d = tmem_base;
+          for (int i = 0; i < ns; ++i, d += N) {
             uint32_t a_lo = a_lo0;
-            uint32_t b_lo = ((xb + (uint32_t)sl.shift * (uint32_t)p.row_bytes) >> 4) | x_lbo_bits;
-#pragma unroll 4
+            uint32_t b_lo = b_lo0 + p.slots[s0 + i].b_off16;
+#pragma unroll 8
             for (int ks = 0; ks < ksteps; ++ks) {
               umma<KIND>(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, first | (uint32_t)ks);
               a_lo += a_inc;
@@ -188,12 +189,12 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
             }
           }
           umma_commit(empty_bar(stage));
-          if (tile == t1 - 1) umma_commit(tfull_bar);
+          first = 1u;
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+        umma_commit(tfull_bar);
+        acc_phase ^= 1;
       }
-      acc_phase ^= 1;
     }
   } else {
     // ===================================================================== drain (warps 2..5)
@@ -419,7 +420,8 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
         const TapGroup& ga = pl.groups[A];
         p.job_group[n_jg++] = (int16_t)A;
         for (int j = 0; j < ga.n_sub; ++j)
-          p.slots[n_slots++] = WgSlot{(int16_t)gi, (int16_t)ga.a_off[j], ga.tap[j], (int16_t)(partner[A] >= 0 ? pl.groups[partner[A]].tap[j] : -1)};
+          p.slots[n_slots++] = WgSlot{(int16_t)gi, (int16_t)ga.a_off[j], ga.tap[j], (int16_t)(partner[A] >= 0 ? pl.groups[partner[A]].tap[j] : -1),
+                                      ((uint32_t)gi * p.n_ci_chunks * p.x_box_stride + (uint32_t)ga.a_off[j] * (uint32_t)p.row_bytes) >> 4};
       }
       ++n_jobs;
       li += ng;
