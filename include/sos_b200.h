@@ -285,13 +285,13 @@ typedef struct sos_conv_args {
 } sos_conv_args;
 #define SOS_DTYPE_TF32 0
 #define SOS_DTYPE_F16 1
-int sos_conv_stats_rows(void);   /* upper bound of *stats_rows_out (4 x SM count) */
+int sos_conv_stats_rows(void);   /* upper bound of *stats_rows_out (8 epilogue warps x SM count) */
 /* Plan cache (SURVEY 8b sos_plan_*): the planner result, MMA program and tensor-map geometry of sos_conv2d_tc are computed once
  * per distinct (shapes, taps, types) key and reused; tensor maps are re-encoded only when a base pointer changes. */
 void sos_plan_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries);
 int sos_conv2d_tc(const sos_conv_args* args, cudaStream_t stream);
 /* Host-only planner query (no CUDA call, pointers other than the tap arrays are ignored): info[16] = {fast_is_w, share, lattice g,
- * sub-tiles S, tap groups, pipeline stages, stage bytes, grid, K chunk (elements), K chunks, N, epilogue chunk, FB, SB, tiles,
+ * sub-tiles S, tap groups, pipeline stages, stage bytes, grid, K chunk (elements), K chunks, N, epilogue chunk, FB, SB, output staging buffers,
  * dynamic shared memory}. */
 int sos_conv2d_plan(const sos_conv_args* args, int32_t* info);
 

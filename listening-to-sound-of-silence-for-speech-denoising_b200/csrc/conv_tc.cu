@@ -32,8 +32,9 @@ namespace {
 using namespace ptx;
 using namespace tc;
 
-constexpr int kThreadsTc = 224;
-constexpr int kStatsSmem = 4 * 512 * 4;    // BatchNorm partial sums of the epilogue warps
+constexpr int kThreadsTc = 352;            // warp 0 producer, 1 and 6 MMA issuers, 2-5 and 7-10 the two epilogue groups
+constexpr int kEpiWarps = 8;
+// (BatchNorm partial sums of the epilogue warps: [8 warps][2][N] floats of shared memory, only when statistics are requested)
 constexpr int kMaxProg = 144;             // entries of the deduplicated MMA programs
 struct alignas(64) TcParams {
   CUtensorMap mapA, mapB, mapD;
@@ -44,6 +45,8 @@ struct alignas(64) TcParams {
   int cin;                       // K elements per tap in the weight matrix
   int ec;                        // epilogue / store chunk width (16 or 32 channels)
   int n_stages, stage_bytes, a_box_bytes, a_box_stride, b_tile_stride, staging_bytes;
+  int n_stg;                     // output staging buffers per epilogue group (2..8)
+  int n_egroups;                 // epilogue groups in use: 2, or 1 (A/B switch SOS_EPI_GROUPS=1: warps 7-10 idle)
   int layout_type, sbo;
   uint32_t idesc;
   const float* scale;            // optional per-output-channel affine (eval-mode BN / bias) ...
@@ -119,8 +122,6 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-
-  const int loads_per_tile = p.n_groups * p.n_chunks;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -199,25 +200,34 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 2..5 = group 0, 7..10 = group 1)
+    // Two groups of four warps: group e drains accumulator buffer e, i.e. every other tile of this CTA, with its own staging
+    // buffers, named barrier and store queue -- the drains of consecutive tiles overlap.  (With one group, layers with few taps /
+    // channels were bound by the latency chain tcgen05.ld -> st.shared -> fence -> barrier -> TMA store of a single chunk.)
+    const int eg = warp >= 7 ? 1 : 0;
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;                // accumulator row = pixel within the tile
-    const int ethread = threadIdx.x - 64;         // 0..127
-    int acc = 0;
+    const int ethread = threadIdx.x - (eg ? 224 : 64);         // 0..127 within the group
+    const int ewarp = eg * 4 + (ethread >> 5);    // 0..7: statistics row of this warp
+    const int neg = p.n_egroups;
+    int acc = neg == 2 ? eg : 0;
     uint32_t acc_phase = 0;
     int buf = 0;
+    const int n_stg = neg == 2 ? p.n_stg : 2 * p.n_stg;
+    const uint32_t my_staging = staging_base + (neg == 2 ? (uint32_t)eg * (uint32_t)(p.staging_bytes >> 1) : 0u);
+    const int bar_id = 1 + eg;
     const float slope = ((p.act & SOS_ACT_MASK) == 2 && p.slope) ? *p.slope : 0.f;
     const float oscale = p.out_scale ? *p.out_scale : 1.f;
     const int n_ec = p.N / p.ec;
     const int erow = p.ec * (p.y_half ? 2 : 4);          // bytes of one staging row
-    float* my_stats = stats_s + q * 512;                 // this warp's [2][256]
+    float* my_stats = stats_s + ewarp * 2 * p.N;         // this warp's [2][N]
     if (p.stats) {
-      for (int i = lane; i < 512; i += 32) my_stats[i] = 0.f;
+      for (int i = lane; i < 2 * p.N; i += 32) my_stats[i] = 0.f;
       __syncwarp();
     }
     // pixel of this thread's accumulator row inside the tile (rows are [slow][fast])
     const int row_f = row % p.FB, row_s = row / p.FB;
-    for (int ct = blockIdx.x; ct < p.total_ctiles; ct += gridDim.x) {
+    for (int ct = blockIdx.x + eg * gridDim.x; ct < p.total_ctiles && eg < neg; ct += neg * gridDim.x) {
       const TileCoord tc = decode_tile(p, ct);
       mbar_wait(tfull_bar(acc), acc_phase, 300);
       tc_fence_after();
@@ -234,25 +244,50 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
             // after which lane i holds the total of channel ch0 + i; rows outside the image (ragged tiles) count as zero
             const bool in_img = (tc.tfg * p.S + s) * p.FB + row_f < p.out_fast && tc.ts * p.SB + row_s < p.lat_slow;
             float v[32], w[32];
+            if (p.ec == 32) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              v[i] = (in_img && i < p.ec) ? __uint_as_float(r[i]) : 0.f;
-              w[i] = v[i] * v[i];
-            }
-#pragma unroll
-            for (int st = 16; st >= 1; st >>= 1) {
-              const bool up = (lane & st) != 0;
-#pragma unroll
-              for (int i = 0; i < st; ++i) {
-                const float send_v = up ? v[i] : v[i + st], keep_v = up ? v[i + st] : v[i];
-                const float send_w = up ? w[i] : w[i + st], keep_w = up ? w[i + st] : w[i];
-                v[i] = keep_v + __shfl_xor_sync(0xffffffffu, send_v, st);
-                w[i] = keep_w + __shfl_xor_sync(0xffffffffu, send_w, st);
+              for (int i = 0; i < 32; ++i) {
+                v[i] = in_img ? __uint_as_float(r[i]) : 0.f;
+                w[i] = v[i] * v[i];
               }
-            }
-            if (lane < p.ec) {                           // (for ec = 16 lanes 16..31 hold zeros)
-              my_stats[cc * p.ec + lane] += v[0];
-              my_stats[256 + cc * p.ec + lane] += w[0];
+#pragma unroll
+              for (int st = 16; st >= 1; st >>= 1) {
+                const bool up = (lane & st) != 0;
+#pragma unroll
+                for (int i = 0; i < st; ++i) {
+                  const float send_v = up ? v[i] : v[i + st], keep_v = up ? v[i + st] : v[i];
+                  const float send_w = up ? w[i] : w[i + st], keep_w = up ? w[i + st] : w[i];
+                  v[i] = keep_v + __shfl_xor_sync(0xffffffffu, send_v, st);
+                  w[i] = keep_w + __shfl_xor_sync(0xffffffffu, send_w, st);
+                }
+              }
+              my_stats[cc * 32 + lane] += v[0];
+              my_stats[p.N + cc * 32 + lane] += w[0];
+            } else {
+              // 16 channels: 15 shuffles per quantity bring lane i the sum of channel (i & 15) over its half-warp's rows, one more
+              // adds the two half-warps
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                v[i] = in_img ? __uint_as_float(r[i]) : 0.f;
+                w[i] = v[i] * v[i];
+              }
+#pragma unroll
+              for (int st = 8; st >= 1; st >>= 1) {
+                const bool up = (lane & st) != 0;
+#pragma unroll
+                for (int i = 0; i < st; ++i) {
+                  const float send_v = up ? v[i] : v[i + st], keep_v = up ? v[i + st] : v[i];
+                  const float send_w = up ? w[i] : w[i + st], keep_w = up ? w[i + st] : w[i];
+                  v[i] = keep_v + __shfl_xor_sync(0xffffffffu, send_v, st);
+                  w[i] = keep_w + __shfl_xor_sync(0xffffffffu, send_w, st);
+                }
+              }
+              v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+              w[0] += __shfl_xor_sync(0xffffffffu, w[0], 16);
+              if (lane < 16) {
+                my_stats[cc * 16 + lane] += v[0];
+                my_stats[p.N + cc * 16 + lane] += w[0];
+              }
             }
           }
           if (p.shift || p.act || p.out_scale) {
@@ -302,10 +337,8 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
           }
-          // make sure the TMA store that last read this staging buffer has drained
-          if (ethread == 0) bulk_wait_read<1>();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          const uint32_t sbuf = staging_base + (uint32_t)buf * (128 * erow);
+          // (this buffer is free: thread 0 waited for the store that last read it before the previous chunk's barrier)
+          const uint32_t sbuf = my_staging + (uint32_t)buf * (128 * erow);     // (128 * erow == the plan's stg_bytes)
           const uint32_t srow = sbuf + (uint32_t)row * erow;
           // staging rows are written in the TMA store's swizzle (128B rows: 16-byte chunk ^= row & 7; 64B rows: chunk ^=
           // (row >> 1) & 3; 32B rows: chunk ^= (row >> 2) & 1), which is also bank-conflict free for a quarter-warp of
@@ -332,26 +365,41 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
             }
           }
           fence_proxy_async_smem();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          // ONE barrier per chunk: before it thread 0 makes sure that at most n_stg - 2 earlier stores still read their
+          // buffers, i.e. the buffer of the NEXT chunk is free by the time anybody passes the barrier
+          if (ethread == 0) {
+            switch (n_stg) {                              // (the wait count is an immediate)
+              case 2: bulk_wait_read<0>(); break;
+              case 3: bulk_wait_read<1>(); break;
+              case 4: bulk_wait_read<2>(); break;
+              case 5: bulk_wait_read<3>(); break;
+              case 6: bulk_wait_read<4>(); break;
+              case 7: bulk_wait_read<5>(); break;
+              case 8: bulk_wait_read<6>(); break;
+              default: bulk_wait_read<7>(); break;
+            }
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
           if (ethread == 0) {
             tma_store_5d(&p.mapD, sbuf, ch0, (tc.tfg * p.S + s) * p.FB, tc.ts * p.SB, tc.ph, tc.n);
             bulk_commit();
           }
-          buf ^= 1;
+          if (++buf == n_stg) buf = 0;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (neg == 2) acc_phase ^= 1;
+      else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (ethread == 0) bulk_wait<0>();
     if (p.stats) {
       __syncwarp();
-      float* dst = p.stats + (size_t)(blockIdx.x * 4 + q) * 2 * p.stats_c;
+      float* dst = p.stats + (size_t)(blockIdx.x * kEpiWarps + ewarp) * 2 * p.stats_c;
       for (int c = lane; c < p.stats_c; c += 32) {
         dst[c] = c < p.N ? my_stats[c] : 0.f;
-        dst[p.stats_c + c] = c < p.N ? my_stats[256 + c] : 0.f;
+        dst[p.stats_c + c] = c < p.N ? my_stats[p.N + c] : 0.f;
       }
     }
   }
@@ -403,14 +451,15 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
     }
   }
   const int ec = (N % 32 == 0) ? 32 : 16;
-  const int staging_bytes = 2 * 128 * ec * 4;               // (half outputs use the first half of each buffer)
-  const int avail = kSmemLimit - 1024 - staging_bytes - 512 - kStatsSmem;
+  const int stg_bytes = 128 * ec * ysz;                     // one output staging buffer (a multiple of 1024: swizzle-aligned)
+  const int stats_smem = a.stats_partial ? kEpiWarps * 2 * N * 4 : 0;
+  const int avail = kSmemLimit - 1024 - 2 * 2 * stg_bytes - 512 - stats_smem;   // (two epilogue groups x at least 2 staging buffers)
 
   // ---- choose orientation / box sharing / taps per box / channel chunk / sub-tiles: the cheapest candidate (tensor time vs
   //      L2->smem feed time per output pixel) whose pipeline stage fits at least twice (three times preferred) in shared memory
   Geometry geo{(int)a.ntaps, a.tap_dh, a.tap_dw, (int)a.H, (int)a.W, (int)a.OH, (int)a.OW, (int)a.stride, Cin, Cout,
                a.osh == 1 && a.osw == 1 && a.oph == 0 && a.opw == 0, kMaxSub, true, esz};
-  struct Cand { Plan pl; int cbe = 0, S = 0, n_stages = 0, stage_bytes = 0, a_box_bytes = 0; double cost = 1e300; };
+  struct Cand { Plan pl; int cbe = 0, S = 0, n_stages = 0, stage_bytes = 0, a_box_bytes = 0; double cost = 1e300, tile_cycles = 0; };
   Cand best;
   auto consider = [&](const Plan& pl, int cbe, int S) {
     if (n_nblk > 1 || S * N > 256) S = 1;
@@ -429,11 +478,18 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
     const double util = ((double)lat_slow / (ceil_div(lat_slow, pl.SB) * pl.SB)) * ((double)out_fast / (ceil_div(tiles_fast, S) * S * pl.FB));
     double cost = std::max(mma, bytes / 40.0) / (util * S);
     if (n_stages < 3) cost *= 1.3;
-    if (cb == 32) cost *= 1.4;                   // 32-byte operand rows: one L2 sector per TMA row, 32B swizzle
+    // Measured (r02, scripts/bench_conv.py): 32-byte operand rows (one L2 sector per TMA row, 32B swizzle) cost ~1.4x, more when
+    // several such chunks make up K (48 -> 48 5x5 as 3 x 16 channels: 0.33 ms against 0.25 ms as ONE zero-tailed 64-wide chunk);
+    // TMA's out-of-bounds zero fill is cheap for a quarter of the box (48 of 64 channels) but not for half or more of it
+    // (16 -> 64 as a half-empty 32-wide chunk: 0.20 ms against 0.15 ms with 16-wide rows; 8 of 32 channels: 0.35-0.5 against 0.2).
+    const int n_chunks = ceil_div(CinK, cbe);
+    if (cb == 32) cost *= 1.4 + 0.2 * (n_chunks - 1);
     else if (cb == 64) cost *= 1.05;
-    if (cbe > CinK) cost *= 1.0 + 0.5 * (cbe - CinK) / CinK;   // zero-filled box tail: shared-memory fill without payload (measured:
-                                                               // pays off at 48 of 64 channels, loses at 16 of 64)
-    if (cost < best.cost) { best.pl = pl; best.cbe = cbe; best.S = S; best.n_stages = n_stages; best.stage_bytes = stage; best.a_box_bytes = a_box; best.cost = cost; }
+    if (cbe * n_chunks > Cin) {
+      const double oob = 1.0 - (double)Cin / (cbe * n_chunks);
+      cost *= 1.0 + 2.0 * oob * oob;
+    }
+    if (cost < best.cost) { best.pl = pl; best.cbe = cbe; best.S = S; best.n_stages = n_stages; best.stage_bytes = stage; best.a_box_bytes = a_box; best.cost = cost; best.tile_cycles = std::max(mma, bytes / 40.0); }
   };
   static const int force_cbe = getenv("SOS_FORCE_CBE") ? atoi(getenv("SOS_FORCE_CBE")) : 0;     // debugging aid
   auto sweep = [&](bool fw, bool sh) -> bool {
@@ -491,7 +547,23 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
   p.b_tile_stride = round_up(N * cb, 1024);
   p.stage_bytes = best.stage_bytes;
   p.n_stages = best.n_stages;
-  p.staging_bytes = staging_bytes;
+  {
+    // A TMA store holds its staging buffer for ~2000 cycles (issue -> shared memory read), so a CTA tile of S * N / ec chunk
+    // stores needs enough buffers in flight to hide that behind its MMA / load time: layers with few taps or channels (2 -> 96,
+    // 64 -> 2 and their gradients) are otherwise bound by the store latency (ncu r02: 1.3 TB/s of stores with 2 buffers).  Extra
+    // buffers are taken from the operand pipeline, which keeps at least 2 (3 if it had them) stages.
+    const double per_tile = (double)best.S * (N / ec) * 2000.0 / std::max(1.0, best.tile_cycles);
+    int n_stg = std::min(8, std::max(3, (int)std::ceil(per_tile / 2) + 1));      // per epilogue group (2 only when shared memory is short:
+                                                                                 // consecutive stores of a group then serialise)
+    const int budget = kSmemLimit - 1024 - 512 - stats_smem;
+    const int keep = per_tile >= 3.0 ? std::min(p.n_stages, 2) : p.n_stages;   // (a third buffer never costs a tensor-bound layer a pipeline stage)
+    while (n_stg > 2 && (budget - 2 * n_stg * stg_bytes) / p.stage_bytes < keep) --n_stg;
+    p.n_stages = std::min(p.n_stages, (budget - 2 * n_stg * stg_bytes) / p.stage_bytes);
+    p.n_stg = n_stg;
+    p.staging_bytes = 2 * n_stg * stg_bytes;
+    static const int one_group = getenv("SOS_EPI_GROUPS") && atoi(getenv("SOS_EPI_GROUPS")) == 1;     // A/B aid
+    p.n_egroups = one_group ? 1 : 2;
+  }
   {
     int n = 0;
     const int kk_per_chunk = std::min(p.cbe, CinK) / kpe;
@@ -566,7 +638,7 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
   SOS_CHECK_ARG(total < (1ll << 31), "sos_conv2d_tc: too many tiles");
   p.total_ctiles = (int)total;
 
-  out.smem = 1024 + p.n_stages * p.stage_bytes + staging_bytes + 512 + kStatsSmem;
+  out.smem = 1024 + p.n_stages * p.stage_bytes + p.staging_bytes + 512 + stats_smem;
   out.grid = (int)std::min<long long>(total, sos_num_sms());
   out.plan_out[0] = pl.fast_is_w;
   out.plan_out[1] = pl.share;
@@ -651,12 +723,12 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   if (plan->esz == 2) tapgemm_f16_kernel<<<plan->grid, kThreadsTc, plan->smem, stream>>>(p);
   else tapgemm_tf32_kernel<<<plan->grid, kThreadsTc, plan->smem, stream>>>(p);
   SOS_CHECK_LAUNCH("sos_conv2d_tc");
-  if (a.stats_rows_out) *a.stats_rows_out = 4 * plan->grid;
+  if (a.stats_rows_out) *a.stats_rows_out = kEpiWarps * plan->grid;
   if (a.plan_out) memcpy(a.plan_out, plan->plan_out, sizeof(plan->plan_out));
   return SOS_OK;
 }
 
-extern "C" int sos_conv_stats_rows(void) { return 4 * sos_num_sms(); }
+extern "C" int sos_conv_stats_rows(void) { return kEpiWarps * sos_num_sms(); }
 
 // Host-only planner query (no CUDA call): what sos_conv2d_tc would choose for these shapes / taps / types.
 extern "C" int sos_conv2d_plan(const sos_conv_args* ap, int32_t* info) {
@@ -666,7 +738,7 @@ extern "C" int sos_conv2d_plan(const sos_conv_args* ap, int32_t* info) {
   if (int e = plan_conv2d_tc(*ap, plan)) return e;
   const TcParams& p = plan.p;
   const int32_t v[16] = {plan.plan_out[0], plan.plan_out[1], plan.plan_out[2], p.S, p.n_groups, p.n_stages, p.stage_bytes, plan.grid,
-                         p.cbe, p.n_chunks, p.N, p.ec, p.FB, p.SB, p.total_ctiles, plan.smem};
+                         p.cbe, p.n_chunks, p.N, p.ec, p.FB, p.SB, p.n_stg, plan.smem};
   memcpy(info, v, sizeof(v));
   return SOS_OK;
 }

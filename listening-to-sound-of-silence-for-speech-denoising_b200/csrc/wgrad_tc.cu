@@ -21,7 +21,8 @@
 // 15 accumulators instead of 25).  The shifted half sees dy columns [delta, W + delta), so the tile grid is extended to
 // negative fast coordinates (zero-filled) to cover columns [0, delta) as well.
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 drain TMEM at the end of each work item.
+// CTA = 192 threads: warp 0 TMA producer, warps 1-5 MMA issuers (one elected thread each, accumulator slots dealt round-robin),
+// warps 2-5 also drain TMEM at the end of each work item.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "sos_b200.h"
@@ -35,8 +36,10 @@ using namespace ptx;
 using namespace tc;
 
 constexpr int kThreadsWg = 192;
+constexpr int kIssuers = 5;                // warps 1..5 each elect one MMA-issuing thread
 constexpr int kMaxJobs = 100;
 constexpr int kMaxSlots = 64;
+constexpr int kMaxItems = 512;
 
 // One TMEM accumulator of a job: x box `x_idx` of the stage shifted by `shift` slow rows; accumulator rows 0..63 (all 128
 // when not stacked) receive tap `tap_lo`, rows 64..127 tap `tap_hi` (-1: unused).
@@ -45,7 +48,7 @@ struct WgSlot { int16_t x_idx, shift, tap_lo, tap_hi; uint32_t b_off16; };   // 
 struct alignas(64) WgParams {
   CUtensorMap mapX, mapDY;
   int stacked, delta, tf_extra;      // delta: fast-axis shift of the stacked dy box; tf_extra: tile columns added at negative fast coordinates
-  int n_jobs, n_slices, tiles_per_slice, total_tiles;
+  int n_jobs, n_items, total_tiles;
   int tiles_fast, tiles_slow, n_phase;
   int FB, SB, stride;
   int Cin, Cout, N;
@@ -62,6 +65,12 @@ struct alignas(64) WgParams {
   const float* out_scale;           // optional device scalar multiplied into the sums
   float* dw;
   int16_t job_coblk[kMaxJobs], job_g0[kMaxJobs], job_ng[kMaxJobs], job_s0[kMaxJobs], job_ns[kMaxJobs];
+  // a job's pixel tiles are split into job_nsl[j] slices of job_tps[j] tiles; the slice counts are proportional to the jobs' MMA
+  // counts, so that every work item (job, slice) costs about the same.  Items are ordered by their relative position in the
+  // tile stream, so that the jobs working on the same pixels run at the same time (their operand boxes then hit in L2).
+  int16_t job_nsl[kMaxJobs];
+  int32_t job_tps[kMaxJobs];
+  int16_t item_job[kMaxItems], item_slice[kMaxItems];
   int16_t job_group[kMaxJobs * 4];   // tap groups whose x boxes a job stages (job_g0 = first index, job_ng = count)
   WgSlot slots[kMaxSlots];
   TapGroup groups[kMaxGroups];
@@ -75,6 +84,16 @@ __device__ __forceinline__ WgTile decode_wg_tile(const WgParams& p, int t) {
   c.ph = t % p.n_phase;
   c.n = t / p.n_phase;
   return c;
+}
+
+struct WgItem { int job, t0, t1; };
+__device__ __forceinline__ WgItem decode_wg_item(const WgParams& p, int wi) {
+  const int j = p.item_job[wi], slice = p.item_slice[wi];
+  WgItem it;
+  it.job = j;
+  it.t0 = slice * p.job_tps[j];
+  it.t1 = min(p.total_tiles, it.t0 + p.job_tps[j]);
+  return it;
 }
 
 template <int KIND>
@@ -97,9 +116,9 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
     prefetch_tmap(&p.mapDY);
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), kIssuers);
     }
-    mbar_init(tfull_bar, 1);
+    mbar_init(tfull_bar, kIssuers);
     mbar_init(tempty_bar, 4);
     fence_barrier_init();
   }
@@ -111,15 +130,15 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const int n_items = p.n_jobs * p.n_slices;
+  const int n_items = p.n_items;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
     for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
-      const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
-      const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
+      const WgItem it = decode_wg_item(p, wi);
+      const int job = it.job, t0 = it.t0, t1 = it.t1;
       const int coblk = p.job_coblk[job], g0 = p.job_g0[job], ng = p.job_ng[job];
       const int co_here = min(128, p.Cout - coblk * 128);
       const int n_co_chunks = (co_here + p.cbo - 1) / p.cbo;
@@ -149,36 +168,43 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    // ONE elected thread runs the whole issue loop (see conv_tc.cu): per stage a barrier poll, per accumulator slot two adds,
-    // per MMA two adds -- the 24/48-cycle MMAs leave no room for per-stage elect / reconvergence or address arithmetic.
-    if (elect_one_sync()) {
-      int stage = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      const uint32_t a_inc = (uint32_t)p.kstep_bytes >> 4, b_inc = a_inc;        // one k step (8 or 16 pixels) of one chunk
-      const uint32_t desc_hi = p.desc_hi;
-      const uint32_t idesc = p.idesc;
-      const int ksteps = p.ksteps, n_stages = p.n_stages;
-      const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
-      // descriptor words: hi = SBO | version | layout; lo = (address >> 4) | LBO (chunk pitch); one k step = 8 / 16 pixels
-      const uint32_t a_lo_base = (stages_base >> 4) | (((uint32_t)p.dy_chunk_stride >> 4) << 16);
-      const uint32_t b_lo_base = ((stages_base + (uint32_t)p.x_off) >> 4) | (((uint32_t)p.x_box_stride >> 4) << 16);
-      const uint32_t N = (uint32_t)p.N;
-      for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
-        const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
-        const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
-        if (t0 >= t1) continue;
-        const int s0 = p.job_s0[job], ns = p.job_ns[job];
+  } else {
+    // ===================================================================== MMA issuers (warps 1..5) + drain (warps 2..5)
+    // The accumulator slots of a job are independent, so they are dealt round-robin to kIssuers elected threads (one per warp):
+    // an N = 48 MMA lasts 24 cycles but costs one thread ~75 cycles of uniform-datapath instructions (ncu r02: the single
+    // issuer of the 48-channel layers ran at 620 cycles per 8-MMA slot against 192 cycles of tensor time).  The drain warps are
+    // idle while a work item's tiles stream through, so they issue as well.
+    const int issuer = warp - 1;                  // 0..4
+    const int q = warp & 3;                       // TMEM lane quadrant (drain)
+    int stage = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const uint32_t a_inc = (uint32_t)p.kstep_bytes >> 4, b_inc = a_inc;        // one k step (8 or 16 pixels) of one chunk
+    const uint32_t desc_hi = p.desc_hi;
+    const uint32_t idesc = p.idesc;
+    const int ksteps = p.ksteps, n_stages = p.n_stages;
+    const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
+    // descriptor words: hi = SBO | version | layout; lo = (address >> 4) | LBO (chunk pitch); one k step = 8 / 16 pixels
+    const uint32_t a_lo_base = (stages_base >> 4) | (((uint32_t)p.dy_chunk_stride >> 4) << 16);
+    const uint32_t b_lo_base = ((stages_base + (uint32_t)p.x_off) >> 4) | (((uint32_t)p.x_box_stride >> 4) << 16);
+    const uint32_t N = (uint32_t)p.N;
+    const float oscale = p.out_scale ? *p.out_scale : 1.f;
+    for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
+      const WgItem it = decode_wg_item(p, wi);
+      const int job = it.job, t0 = it.t0, t1 = it.t1;
+      if (t0 >= t1) continue;
+      const int coblk = p.job_coblk[job], s0 = p.job_s0[job], ns = p.job_ns[job];
+      if (elect_one_sync()) {
         mbar_wait(tempty_bar, acc_phase ^ 1, 600);
         tc_fence_after();
         uint32_t first = 0u;
+        int st = stage;
+        uint32_t ph = phase;
         for (int tile = t0; tile < t1; ++tile) {
-          mbar_wait(full_bar(stage), phase, 601);
+          mbar_wait(full_bar(st), ph, 601);
           tc_fence_after();
-          const uint32_t a_lo0 = a_lo_base + (uint32_t)stage * stage_step, b_lo0 = b_lo_base + (uint32_t)stage * stage_step;
-          uint32_t d = tmem_base;
-          for (int i = 0; i < ns; ++i, d += N) {
+          const uint32_t a_lo0 = a_lo_base + (uint32_t)st * stage_step, b_lo0 = b_lo_base + (uint32_t)st * stage_step;
+          for (int i = issuer; i < ns; i += kIssuers) {
+            const uint32_t d = tmem_base + (uint32_t)i * N;
             uint32_t a_lo = a_lo0;
             uint32_t b_lo = b_lo0 + p.slots[s0 + i].b_off16;
 #pragma unroll 8
@@ -188,46 +214,44 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
               b_lo += b_inc;
             }
           }
-          umma_commit(empty_bar(stage));
+          umma_commit(empty_bar(st));               // (an issuer without slots in this job still arrives)
           first = 1u;
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          if (++st == n_stages) { st = 0; ph ^= 1; }
         }
         umma_commit(tfull_bar);
-        acc_phase ^= 1;
       }
-    }
-  } else {
-    // ===================================================================== drain (warps 2..5)
-    const int q = warp & 3;
-    uint32_t acc_phase = 0;
-    const float oscale = p.out_scale ? *p.out_scale : 1.f;
-    for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
-      const int job = wi % p.n_jobs, slice = wi / p.n_jobs;
-      const int t0 = slice * p.tiles_per_slice, t1 = min(p.total_tiles, t0 + p.tiles_per_slice);
-      if (t0 >= t1) continue;
-      const int coblk = p.job_coblk[job], s0 = p.job_s0[job], ns = p.job_ns[job];
-      // accumulator row q*32 + lane: output channel, and (stacked) which of the slot's two taps
-      const int co = p.stacked ? (q & 1) * 32 + lane : coblk * 128 + q * 32 + lane;
-      mbar_wait(tfull_bar, acc_phase, 700);
-      tc_fence_after();
-      for (int i = 0; i < ns; ++i) {
-        const WgSlot sl = p.slots[s0 + i];
-        const int tap = (p.stacked && (q >> 1)) ? sl.tap_hi : sl.tap_lo;
-        float* dst = p.dw + ((size_t)(tap < 0 ? 0 : tap) * p.Cout + co) * p.Cin;
-        for (int c0 = 0; c0 < p.N; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * p.N + c0), r);
-          tmem_ld_wait();
-          if (co < p.Cout && tap >= 0) {
+      __syncwarp();
+      // every lane tracks the pipeline position the elected lane advanced through
+      {
+        const int adv = t1 - t0;
+        const int tot = stage + adv;
+        phase ^= (uint32_t)((tot / n_stages) & 1);
+        stage = tot % n_stages;
+      }
+      if (warp >= 2) {
+        // ---- drain: accumulator row q*32 + lane = output channel, and (stacked) which of the slot's two taps
+        const int co = p.stacked ? (q & 1) * 32 + lane : coblk * 128 + q * 32 + lane;
+        mbar_wait(tfull_bar, acc_phase, 700);
+        tc_fence_after();
+        for (int i = 0; i < ns; ++i) {
+          const WgSlot sl = p.slots[s0 + i];
+          const int tap = (p.stacked && (q >> 1)) ? sl.tap_hi : sl.tap_lo;
+          float* dst = p.dw + ((size_t)(tap < 0 ? 0 : tap) * p.Cout + co) * p.Cin;
+          for (int c0 = 0; c0 < p.N; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * p.N + c0), r);
+            tmem_ld_wait();
+            if (co < p.Cout && tap >= 0) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-              if (c0 + k < p.Cin) atomicAdd(dst + c0 + k, __uint_as_float(r[k]) * oscale);
+              for (int k = 0; k < 16; ++k)
+                if (c0 + k < p.Cin) atomicAdd(dst + c0 + k, __uint_as_float(r[k]) * oscale);
+            }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar);
       acc_phase ^= 1;
     }
   }
@@ -462,12 +486,41 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
   SOS_CHECK_ARG(total < (1ll << 30), "sos_conv2d_wgrad: too many tiles");
   p.total_tiles = (int)total;
   const int sms = sos_num_sms();
-  p.n_slices = std::max(1, std::min((int)total, sms / std::max(1, n_jobs)));
-  p.tiles_per_slice = ceil_div((int)total, p.n_slices);
-  p.n_slices = ceil_div((int)total, p.tiles_per_slice);
+  {
+    // slices per job proportional to its cost per tile = max(tensor / shared-memory time of its MMAs, L2 -> smem time of its
+    // boxes), at least one, about one work item per SM in total.  Jobs of (nearly) equal cost get the same slice count, which
+    // keeps the items of one slice -- the jobs that read the same pixels -- exactly in step.
+    std::vector<double> wgt(n_jobs);
+    double total_wd = 0, wmin = 1e300, wmax = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+      const int co_here = std::min(128, Cout - p.job_coblk[j] * 128);
+      const double mma_cyc = std::max(p.N / 2.0, (4096.0 + 32.0 * round_up(p.N, 64)) / 128.0);
+      const double bytes = (double)ceil_div(co_here, p.cbo) * (stacked ? 2 : 1) * p.dy_chunk_bytes + (double)p.job_ng[j] * p.n_ci_chunks * p.x_box_bytes;
+      wgt[j] = std::max((double)p.job_ns[j] * p.ksteps * mma_cyc, bytes / 48.0);
+      total_wd += wgt[j];
+      wmin = std::min(wmin, wgt[j]);
+      wmax = std::max(wmax, wgt[j]);
+    }
+    if (wmax <= 1.15 * wmin) { for (int j = 0; j < n_jobs; ++j) wgt[j] = 1.0; total_wd = n_jobs; }
+    int items = 0;
+    std::vector<std::pair<double, std::pair<int, int>>> order;
+    for (int j = 0; j < n_jobs; ++j) {
+      int nsl = std::max(1, std::min((int)total, (int)(sms * wgt[j] / total_wd)));
+      const int tps = ceil_div((int)total, nsl);
+      nsl = ceil_div((int)total, tps);
+      SOS_CHECK_ARG(items + nsl <= kMaxItems, "sos_conv2d_wgrad: too many work items");
+      p.job_nsl[j] = (int16_t)nsl;
+      p.job_tps[j] = tps;
+      for (int sl = 0; sl < nsl; ++sl) order.push_back({(double)sl / nsl, {j, sl}});
+      items += nsl;
+    }
+    std::stable_sort(order.begin(), order.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+    for (int i = 0; i < items; ++i) { p.item_job[i] = (int16_t)order[i].second.first; p.item_slice[i] = (int16_t)order[i].second.second; }
+    p.n_items = items;
+  }
 
   out.smem = 2048 + p.n_stages * p.stage_bytes + tail;
-  out.grid = std::min(p.n_jobs * p.n_slices, sms);
+  out.grid = std::min(p.n_items, sms);
   out.plan_out[0] = pl.fast_is_w;
   out.plan_out[1] = pl.share;
   out.plan_out[2] = pl.g;
@@ -475,7 +528,7 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
   out.plan_out[4] = n_jobs;
   out.plan_out[5] = p.n_stages;
   out.plan_out[6] = p.stage_bytes;
-  out.plan_out[7] = p.n_slices + (stacked ? 1000 : 0);
+  out.plan_out[7] = p.job_nsl[0] + (stacked ? 1000 : 0);
   return SOS_OK;
 }
 

@@ -30,6 +30,9 @@ LAYERS = [
     ("in_256_k3d16", "valid", 256, 256, (3, 3), (16, 16), 1, 96, 83, 1), ("in_T256to128", "convT", 256, 128, (3, 3), (1, 1), 2, 64, 51, 1),
     ("in_256to128_k3", "valid", 256, 128, (3, 3), (1, 1), 1, 130, 104, 1), ("in_T128to64", "convT", 128, 64, (3, 3), (1, 1), 2, 128, 102, 1),
     ("in_128to64_k3", "valid", 128, 64, (3, 3), (1, 1), 1, 258, T + 2, 1), ("in_64to2_k3", "valid", 64, 2, (3, 3), (1, 1), 1, 258, T + 2, 1),
+    # probes (count 0: not part of the step): the same small layers with their few channels stored as 16 / 32
+    ("probe_64to16_k3", "valid", 64, 16, (3, 3), (1, 1), 1, 258, T + 2, 0), ("probe_64to32_k3", "valid", 64, 32, (3, 3), (1, 1), 1, 258, T + 2, 0),
+    ("probe_96to32_k1", "zero", 96, 32, (1, 1), (1, 1), 1, 256, T, 0), ("probe_32to96_k1x7", "zero", 32, 96, (1, 7), (1, 1), 1, 256, T, 0),
 ]
 
 
@@ -62,9 +65,19 @@ for name, kind, Cin, Cout, k, d, stride, H, W, cnt in LAYERS:
     y = L._conv_forward(x, w, g)
     dy = ops.to_half(torch.randn_like(y)) if HALF else ops.round_tf32_(torch.randn_like(y))
     flops = 2.0 * B * OH * OW * Cout * (2 if Cin == 16 and Cout in (96, 64) else Cin) * k[0] * k[1] / (4 if kind == "convT" else 1)
-    t_f = timeit(lambda: L._conv_forward(x, w, g))
-    t_d = timeit(lambda: L._conv_dgrad(dy, w, g, x.shape))
-    t_w = timeit(lambda: L._conv_wgrad(x, dy, w, g))
+    if HALF:
+        # the calls of a training step: forward with the BatchNorm statistics in the epilogue and a half output; data gradient
+        # stored as half inside the encoder chains ("zero" layers), fp32 with the operand's inverse scale elsewhere
+        inv = torch.ones(1, device=dev)
+        t_f = timeit(lambda: L._conv_forward(x, w, g, want_stats=True, y_half=True))
+        if kind == "zero":
+            t_d = timeit(lambda: L._conv_dgrad_raw(dy, w, g, x.shape, None, y_half=True))
+        else:
+            t_d = timeit(lambda: L._conv_dgrad(dy, w, g, x.shape, inv))
+    else:
+        t_f = timeit(lambda: L._conv_forward(x, w, g))
+        t_d = timeit(lambda: L._conv_dgrad(dy, w, g, x.shape))
+    t_w = timeit(lambda: L._conv_wgrad_raw(x, dy, w, g, inv if HALF else None))
     tot["fwd"] += cnt * t_f; tot["dgrad"] += cnt * t_d; tot["wgrad"] += cnt * t_w; totf += cnt * flops
     print(f"      {name:16s} {flops/1e9:8.1f} | {t_f:8.3f} {flops/t_f/1e9:6.0f} | {t_d:8.3f} {flops/t_d/1e9:6.0f} | {t_w:8.3f} {flops/t_w/1e9:6.0f}  x{cnt}", flush=True)
     del x, w, y, dy

@@ -281,7 +281,7 @@ def test_checkpoint_roundtrip(cuda, tmp_path):
     for (k, p), (_, q) in zip(a.net.state_dict().items(), b.net.state_dict().items()):
         if p.is_floating_point():       # wgrad merges its pixel slices with fp32 atomics: the last bits of a gradient depend on their
             # order, and Adam's normalised update (lr 1e-3) turns a last-bit difference of a near-zero gradient into up to 2 lr
-            assert float((p - q).abs().max()) < 1e-3, k
+            assert float((p - q).abs().max()) < 2.1e-3, k        # 2 lr: one element whose near-zero gradient changed sign
             assert float((p - q).abs().mean()) < 1e-5, k
         else:
             assert torch.equal(p, q), k
