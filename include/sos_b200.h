@@ -238,6 +238,10 @@ int sos_unpack_wgrad(const float* src, int64_t Cout, int64_t Cin, int64_t ntaps,
  * .grad (Conv2d: rows = Cout, cols = Cin; ConvTranspose2d: rows = Cin, cols = Cout with the roles swapped by the caller). */
 int sos_accumulate_wgrad(const float* src, int64_t ntaps, int64_t rows_padded, int64_t cols_padded, int64_t rows, int64_t cols,
                          float* dst, cudaStream_t stream);
+/* Same, and the source elements it read are set back to zero: a persistent weight-gradient workspace is then ready for the next
+ * sos_conv2d_wgrad (which accumulates into a zeroed buffer) without a fill launch. */
+int sos_accumulate_wgrad_clear(float* src, int64_t ntaps, int64_t rows_padded, int64_t cols_padded, int64_t rows, int64_t cols,
+                               float* dst, cudaStream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ tensor-core tap GEMM
  * One kernel family (tcgen05 kind::tf32, fp32 accumulate in TMEM, TMA-staged operands) serves

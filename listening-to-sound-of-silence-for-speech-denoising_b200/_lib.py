@@ -76,6 +76,7 @@ _SIGS = {
                                            c_f, c_f, c_f, C.c_int, i64, S]),
     "sos_nchw_to_nhwc_half": (C.c_int, [c_f, i64, i64, i64, i64, c_f, i64, S]),
     "sos_accumulate_wgrad": (C.c_int, [c_f, i64, i64, i64, i64, i64, c_f, S]),
+    "sos_accumulate_wgrad_clear": (C.c_int, [c_f, i64, i64, i64, i64, i64, c_f, S]),
     "sos_to_half": (C.c_int, [c_f, i64, i64, c_f, i64, c_f, S]),
     "sos_affine_act_backward": (C.c_int, [c_f, i32p, c_f, c_f, i64, i64, c_f, c_f, C.c_int, c_f, S]),
     "sos_nchw_to_nhwc": (C.c_int, [c_f, i64, i64, c_f, i32p, i64, S]),

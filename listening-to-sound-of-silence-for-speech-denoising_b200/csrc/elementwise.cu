@@ -1290,14 +1290,19 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, int Cout, int
 }
 
 // wgrad buffer [tap][RP][CP] (padded rows / columns) -> += parameter gradient (R, Cc, taps) in PyTorch's layout.
-__global__ void accumulate_wgrad_kernel(const float* __restrict__ src, int ntaps, int RP, int CP, int R, int Cc, float* __restrict__ dst) {
+// CLEAR: the visited source elements are zeroed after they are read (the padded ones are never written by the weight-gradient
+// kernel), which leaves the buffer ready for the next weight gradient without a fill launch.
+template <bool CLEAR>
+__global__ void accumulate_wgrad_kernel(float* __restrict__ src, int ntaps, int RP, int CP, int R, int Cc, float* __restrict__ dst) {
   const long long total = (long long)R * Cc * ntaps;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int tap = (int)(e % ntaps);
     const long long t = e / ntaps;
     const int c = (int)(t % Cc);
     const int r = (int)(t / Cc);
-    dst[e] += src[((long long)tap * RP + r) * CP + c];
+    const long long si = ((long long)tap * RP + r) * CP + c;
+    dst[e] += src[si];
+    if (CLEAR) src[si] = 0.f;
   }
 }
 
@@ -1648,9 +1653,18 @@ int sos_nchw_to_nhwc_half(const float* x, int64_t batch, int64_t channels, int64
 int sos_accumulate_wgrad(const float* src, int64_t ntaps, int64_t rows_padded, int64_t cols_padded, int64_t rows, int64_t cols, float* dst,
                          cudaStream_t stream) {
   SOS_CHECK_ARG(src && dst && ntaps > 0 && rows > 0 && cols > 0 && rows_padded >= rows && cols_padded >= cols, "sos_accumulate_wgrad: bad arguments");
-  accumulate_wgrad_kernel<<<grid_for(rows * cols * ntaps), kThreads, 0, stream>>>(src, (int)ntaps, (int)rows_padded, (int)cols_padded, (int)rows,
-                                                                                 (int)cols, dst);
+  accumulate_wgrad_kernel<false><<<grid_for(rows * cols * ntaps), kThreads, 0, stream>>>(const_cast<float*>(src), (int)ntaps, (int)rows_padded,
+                                                                                        (int)cols_padded, (int)rows, (int)cols, dst);
   SOS_CHECK_LAUNCH("sos_accumulate_wgrad");
+  return SOS_OK;
+}
+
+int sos_accumulate_wgrad_clear(float* src, int64_t ntaps, int64_t rows_padded, int64_t cols_padded, int64_t rows, int64_t cols, float* dst,
+                               cudaStream_t stream) {
+  SOS_CHECK_ARG(src && dst && ntaps > 0 && rows > 0 && cols > 0 && rows_padded >= rows && cols_padded >= cols, "sos_accumulate_wgrad_clear: bad arguments");
+  accumulate_wgrad_kernel<true><<<grid_for(rows * cols * ntaps), kThreads, 0, stream>>>(src, (int)ntaps, (int)rows_padded, (int)cols_padded, (int)rows,
+                                                                                       (int)cols, dst);
+  SOS_CHECK_LAUNCH("sos_accumulate_wgrad_clear");
   return SOS_OK;
 }
 

@@ -226,17 +226,17 @@ def _conv_dgrad_raw(dy, w, g, x_shape, out_scale=None, y_half=False):
     return dx
 
 
-def _conv_wgrad_raw(x, dy, w, g, out_scale=None):
+def _conv_wgrad_raw(x, dy, w, g, out_scale=None, workspace=False):
     """The weight-gradient kernel's tap-major buffer (ntaps, RP, CP): rows / columns are w's first two axes, zero padded."""
     if g.kind == "convT":
         Cin, Cout = w.shape[0], w.shape[1]
         # roles swapped: "input" = dy (2H x 2W), "output grad" = x (H x W), stride 2  ->  (ntaps, Cin_p, Cout_p)
         return ops.conv_wgrad(dy, x, [o[0] for o in g.off], [o[1] for o in g.off], x.shape[3], x.shape[1], x.shape[2], 2, real=(Cout, Cin),
-                              out_scale=out_scale)
+                              out_scale=out_scale, workspace=workspace)
     Cout, Cin = w.shape[0], w.shape[1]
     OH, OW = dy.shape[1], dy.shape[2]
     return ops.conv_wgrad(x, dy, [o[0] for o in g.off], [o[1] for o in g.off], dy.shape[3], OH, OW, g.stride, real=(Cin, Cout),
-                          out_scale=out_scale)
+                          out_scale=out_scale, workspace=workspace)
 
 
 def _conv_wgrad(x, dy, w, g, out_scale=None):
@@ -315,7 +315,8 @@ def _wgrad_into(w, x, dy, g, out_scale):
         side.wait_stream(main)                                     # x, dy, the scale (and the zeroed .grad) are ready
         with torch.cuda.stream(side):
             if _DIRECT_GRADS and w.grad.is_contiguous():
-                ops.accumulate_wgrad(_conv_wgrad_raw(x, dy, w, g, out_scale), w.grad)     # one pass: un-pad, re-layout, add
+                # one pass: un-pad, re-layout, add -- out of the side stream's shared workspace, which it leaves zeroed (no fill launch)
+                ops.accumulate_wgrad(_conv_wgrad_raw(x, dy, w, g, out_scale, workspace=True), w.grad, clear=True)
             else:
                 w.grad.add_(_conv_wgrad(x, dy, w, g, out_scale))
         x.record_stream(side)

@@ -512,13 +512,29 @@ def nchw_to_nhwc_half(x, channels_padded):
     return z
 
 
-def accumulate_wgrad(dwt, grad):
-    """grad (R, Cc, kh, kw) += dwt (ntaps, RP, CP) (the weight-gradient kernel's tap-major buffer, padded rows / columns)."""
+def accumulate_wgrad(dwt, grad, clear=False):
+    """grad (R, Cc, kh, kw) += dwt (ntaps, RP, CP) (the weight-gradient kernel's tap-major buffer, padded rows / columns);
+    clear: dwt is zeroed again on the way (a `wgrad_workspace`)."""
     ntaps, RP, CP = dwt.shape
     R, Cc = grad.shape[0], grad.shape[1]
     assert grad.is_contiguous() and grad.shape[2] * grad.shape[3] == ntaps and R <= RP and Cc <= CP
-    check(lib().sos_accumulate_wgrad(_p(dwt), ntaps, RP, CP, R, Cc, _p(grad), _stream()), "sos_accumulate_wgrad")
+    fn = lib().sos_accumulate_wgrad_clear if clear else lib().sos_accumulate_wgrad
+    check(fn(_p(dwt), ntaps, RP, CP, R, Cc, _p(grad), _stream()), "sos_accumulate_wgrad")
     _count()
+
+
+_WGRAD_WS = {}
+
+
+def wgrad_workspace(ntaps, rows, cols, device):
+    """A persistent zeroed (ntaps, rows, cols) fp32 buffer for conv_wgrad(dw=...) + accumulate_wgrad(clear=True): every user leaves it
+    zeroed, all users run in order on one stream (the weight-gradient side stream), so one buffer per shape serves every layer and a
+    training step needs no fill launches for its weight gradients."""
+    key = (str(device), ntaps, rows, cols)
+    ws = _WGRAD_WS.get(key)
+    if ws is None:
+        ws = _WGRAD_WS[key] = torch.zeros(ntaps, rows, cols, device=device, dtype=torch.float32)
+    return ws
 
 
 def nhwc_to_nchw(x, channels):
@@ -651,12 +667,13 @@ def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lat
     return y
 
 
-def conv_wgrad(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_plan=-1, plan_out=None, real=None, out_scale=None):
-    """dw[t][co][ci] = sum_pixels dy[p][dy_coff+co] * x[p*stride + off_t][ci]  ->  (ntaps, Cout, Cin)."""
+def conv_wgrad(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_plan=-1, plan_out=None, real=None, out_scale=None, workspace=False):
+    """dw[t][co][ci] = sum_pixels dy[p][dy_coff+co] * x[p*stride + off_t][ci]  ->  (ntaps, Cout, Cin); workspace: the sums go into the
+    shared `wgrad_workspace` of that shape (which the caller must empty with accumulate_wgrad(clear=True))."""
     N, H, W, Cin = x.shape
     ntaps = len(tap_dh)
     assert dy.shape[0] == N and dy.shape[1] == OH and dy.shape[2] == OW, (dy.shape, N, OH, OW)
-    dw = torch.zeros(ntaps, Cout, Cin, device=x.device, dtype=torch.float32)
+    dw = wgrad_workspace(ntaps, Cout, Cin, x.device) if workspace else torch.zeros(ntaps, Cout, Cin, device=x.device, dtype=torch.float32)
     assert x.dtype == dy.dtype and x.dtype in (torch.float32, torch.float16)
     a = WgradArgs()
     a.dtype = 1 if x.dtype == torch.float16 else 0
