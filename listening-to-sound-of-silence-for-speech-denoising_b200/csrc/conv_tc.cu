@@ -660,6 +660,10 @@ extern "C" void sos_plan_cache_stats(int64_t* hits, int64_t* misses, int64_t* en
   if (entries) *entries = (int64_t)g_plans.size();
 }
 
+// conv_row.cu: the row-streaming stacked-tap kernel for the narrow dilated k x k layers
+bool sos_rowconv_eligible(const sos_conv_args& a);
+int sos_rowconv_launch(const sos_conv_args& a, cudaStream_t stream);
+
 extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG(ap != nullptr, "sos_conv2d_tc: null args");
   const sos_conv_args& a = *ap;
@@ -679,6 +683,8 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   SOS_CHECK_ARG(a.epi_scale == nullptr || a.epi_shift != nullptr, "sos_conv2d_tc: epi_scale needs epi_shift (a shift alone is a bias)");
   SOS_CHECK_ARG(a.stats_partial == nullptr || (a.epi_shift == nullptr && (a.act & SOS_ACT_MASK) == 0),
                 "sos_conv2d_tc: fused BatchNorm statistics are taken of the RAW outputs (no affine / activation in the same call)");
+
+  if (sos_rowconv_eligible(a)) return sos_rowconv_launch(a, stream);
 
   std::vector<int32_t> key;
   key.reserve(24 + 2 * (size_t)a.ntaps);
