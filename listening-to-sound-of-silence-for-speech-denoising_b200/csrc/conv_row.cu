@@ -23,7 +23,8 @@
 // the newest one (o = i + half), which gets its own N = Cout MMA for the first (f, k-step).  Ranges that wrap around the ring
 // end are issued as two MMAs.
 //
-// CTA = 352 threads: warp 0 TMA producer, warp 1 MMA issuer (one elected thread), warps 2-5 / 7-10 two epilogue groups (even /
+// CTA = 352 threads: warp 0 TMA producer, warps 1 and 6 MMA issuers (one elected thread each, alternating input columns), warps
+// 2-5 / 7-10 two epilogue groups (even /
 // odd output columns): tcgen05.ld -> BatchNorm statistics | scale / affine / activation -> half -> dense staging -> TMA store.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -53,6 +54,7 @@ struct alignas(64) RowParams {
   int b_tile_bytes;              // one (f, b) weight tile: Cout x 128 B
   int R;                         // ring slots
   int ksteps;                    // K steps of 16 channels
+  int n_issuers;                 // 2, or 1 (A/B switch SOS_ROW_ISSUERS=1)
   uint32_t idesc[8];             // instruction descriptor for N = nb * Cout, nb = 1..KW
   int16_t tapsel[kMaxTaps];      // weight tap index (column block of wk) of smem tile (f, b)
   const float* scale;
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(kThreadsRow, 1) rowconv_f16_kernel(const __gri
   auto tfull_bar = [&](int s) { return bar_base + 8u * (16 + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (32 + s); };
   const uint32_t bfull_bar = bar_base + 8u * 48;
+  auto turn_bar = [&](int t) { return bar_base + 8u * (50 + t); };
   const uint32_t tmem_slot = bar_base + 8u * 49;
   float* stats_s = reinterpret_cast<float*>(smem_raw + (bar_base + 512u - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -129,6 +132,8 @@ __global__ void __launch_bounds__(kThreadsRow, 1) rowconv_f16_kernel(const __gri
       mbar_init(tempty_bar(s), 4);
     }
     mbar_init(bfull_bar, 1);
+    mbar_init(turn_bar(0), 1);
+    mbar_init(turn_bar(1), 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -159,15 +164,22 @@ __global__ void __launch_bounds__(kThreadsRow, 1) rowconv_f16_kernel(const __gri
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+  } else if (warp == 1 || warp == 6) {
+    // ===================================================================== MMA issuers
     // One elected thread.  Per input column it first works out the (at most three) accumulator ranges ("pieces") its MMAs write --
     // slot, width, weight block, overwrite flag -- and then issues KH * ksteps * pieces MMAs with two adds each; the ring size is
     // a compile-time constant so that slot / phase arithmetic has no integer division (the first version of this loop spent ~390
     // cycles of address arithmetic per 120-cycle MMA).
-    if (elect_one_sync()) {
-      int stage = 0;
-      uint32_t phase = 0;
+    // Two issuers take the input columns in turn (warp 1 the even, warp 6 the odd ones of this CTA's column sequence): one thread
+    // needs ~1500 cycles of barrier polls and bookkeeping per column on top of ~1700 to issue its MMAs, during which the tensor
+    // pipe (1800 cycles of work per column) would drain.  The MMAs of consecutive columns accumulate into the same TMEM slots and
+    // must enter the tensor pipe in column order: a thread issues only after the other one has issued the previous column (`turn`
+    // barriers); each commit then also covers the other thread's earlier MMAs, because the pipe retires in issue order.
+    const int T = warp == 1 ? 0 : 1;
+    if (T < p.n_issuers && elect_one_sync()) {
+      const int n_iss = p.n_issuers;
+      int g = 0;                                      // index of the input column in this CTA's sequence
+      uint32_t turn_phase = 0;
       int c_base = 0;                                 // output counter of the current stream's first output column
       constexpr int R = kRing;
       const int Cout = p.Cout, KW = p.KW, KH = p.KH, half_w = p.half_w, ksteps = p.ksteps;
@@ -182,7 +194,10 @@ __global__ void __launch_bounds__(kThreadsRow, 1) rowconv_f16_kernel(const __gri
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
         const RowItem r = decode_row_item(p, it);
         if (r.k0 >= r.k1) continue;
-        for (int i = r.i0; i < r.i1; ++i) {
+        for (int i = r.i0; i < r.i1; ++i, ++g) {
+          if (n_iss == 2 && (g & 1) != T) continue;
+          const int stage = g % p.n_stages;
+          const uint32_t phase = (uint32_t)(g / p.n_stages) & 1u;
           // outputs fed by this input column, as lattice indices [oa, ob]; their weight blocks b = o - (i - half)
           const int oa = max(r.k0, i - half_w), ob = min(r.k1 - 1, i + half_w);
           const bool all_fresh = i == r.i0;
@@ -207,6 +222,10 @@ __global__ void __launch_bounds__(kThreadsRow, 1) rowconv_f16_kernel(const __gri
             tc_fence_after();
           }
           mbar_wait(full_bar(stage), phase, 201);
+          if (n_iss == 2) {                                   // my turn: the other issuer has issued the previous column
+            mbar_wait(turn_bar(T), turn_phase ^ (T == 0 ? 1u : 0u), 202);
+            turn_phase ^= 1u;
+          }
           tc_fence_after();
           const uint32_t a_col = a_lo0 + (uint32_t)stage * stage16;
           {
@@ -242,12 +261,12 @@ __global__ void __launch_bounds__(kThreadsRow, 1) rowconv_f16_kernel(const __gri
             const int da = max(i - half_w, r.k0), db = last_in ? r.k1 - 1 : i - half_w;
             for (int o = da; o <= db; ++o) umma_commit(tfull_bar((c_base + (o - r.k0)) % R));
           }
-          if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+          if (n_iss == 2) mbar_arrive(turn_bar(1 - T));
         }
         c_base += r.k1 - r.k0;
       }
     }
-  } else if (warp != 6) {
+  } else {
     // ===================================================================== epilogue (warps 2..5 = group 0, 7..10 = group 1)
     const int eg = warp >= 7 ? 1 : 0;
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
@@ -465,6 +484,8 @@ int plan_rowconv(const sos_conv_args& a, RowPlan& out) {
   p.stage_bytes = round_up(p.box_bytes, 1024);
   p.b_tile_bytes = Cout * 128;
   p.R = kRing;
+  static const int one_iss = getenv("SOS_ROW_ISSUERS") && atoi(getenv("SOS_ROW_ISSUERS")) == 1;
+  p.n_issuers = one_iss ? 1 : 2;
   p.ksteps = round_up(Cin, 16) / 16;
   for (int nb = 1; nb <= KW; ++nb) p.idesc[nb] = make_idesc_f16(128, nb * Cout, 0, 0);
   // smem tile (f, b) holds the tap with dh = (f - (KH-1)/2) * dh and W offset s' - half with s' = KW - 1 - b: input column i feeds
@@ -499,7 +520,8 @@ int plan_rowconv(const sos_conv_args& a, RowPlan& out) {
     const int sl = ceil_div(Lmax, ns);
     const int nsr = ceil_div(Lmax, sl);
     const double waves = (double)streams * nsr / sms;
-    const double eff = waves / std::ceil(waves) * ((double)sl / (sl + (nsr > 1 ? 2 * p.half_w : 0)));
+    // (a segment's 2 * half halo columns cost A traffic and issue slots, not tensor time: about half a column each)
+    const double eff = waves / std::ceil(waves) * ((double)sl / (sl + (nsr > 1 ? p.half_w : 0)));
     if (eff > best_eff + 1e-9) { best_eff = eff; best_seg = nsr; }
   }
   p.seg_len = ceil_div(Lmax, best_seg);

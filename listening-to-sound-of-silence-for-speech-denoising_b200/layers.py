@@ -316,7 +316,7 @@ def _wgrad_into(w, x, dy, g, out_scale):
         with torch.cuda.stream(side):
             if _DIRECT_GRADS and w.grad.is_contiguous():
                 # one pass: un-pad, re-layout, add -- out of the side stream's shared workspace, which it leaves zeroed (no fill launch)
-                ops.accumulate_wgrad(_conv_wgrad_raw(x, dy, w, g, out_scale, workspace=True), w.grad, clear=True)
+                ops.accumulate_wgrad(_conv_wgrad_raw(x, dy, w, g, out_scale, workspace=_WGRAD_WS), w.grad, clear=_WGRAD_WS)
             else:
                 w.grad.add_(_conv_wgrad(x, dy, w, g, out_scale))
         x.record_stream(side)
@@ -327,6 +327,7 @@ def _wgrad_into(w, x, dy, g, out_scale):
     return _conv_wgrad(x, dy, w, g, out_scale)
 
 
+_WGRAD_WS = os.environ.get("SOS_WGRAD_WS", "1") != "0"           # A/B switch: weight gradients through the shared zeroed workspace
 _Y_HALF = os.environ.get("SOS_Y_HALF", "1") != "0"                 # A/B switch: raw conv outputs (BatchNorm inputs) stored as half
 
 
