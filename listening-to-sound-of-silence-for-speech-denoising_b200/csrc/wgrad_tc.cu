@@ -41,9 +41,18 @@ constexpr int kMaxJobs = 100;
 constexpr int kMaxSlots = 64;
 constexpr int kMaxItems = 512;
 
-// One TMEM accumulator of a job: x box `x_idx` of the stage shifted by `shift` slow rows; accumulator rows 0..63 (all 128
-// when not stacked) receive tap `tap_lo`, rows 64..127 tap `tap_hi` (-1: unused).
-struct WgSlot { int16_t x_idx, shift, tap_lo, tap_hi; uint32_t b_off16; };   // b_off16: byte offset of the slot's x operand inside the stage's x area, >> 4
+// One TMEM accumulator of a job.  Narrow slot: one tap, N = round16(Cin) columns.  Wide slot (Cin <= 64, half operands): up to four
+// taps of ONE tap group that differ by equally spaced slow-axis shifts share the MMA -- the x operand of tap j0 + c is N chunk c (64
+// channels) of the same staged box, `lbo` bytes further on, so the descriptor's chunk stride addresses all of them: N = 64 * ntaps,
+// the dy operand (4 KB per MMA) is read once for four taps (ncu r02: the 48-channel weight gradients were shared-memory bound at
+// 48 wavefronts per 24-cycle N = 48 MMA).  Accumulator rows 0..63 (all 128 when not stacked) receive taps tap_lo[], rows 64..127
+// taps tap_hi[] (-1: unused).
+struct WgSlot {
+  int16_t x_idx, ntaps, col0, n_cols;
+  uint32_t b_desc;               // ((byte offset of the x operand inside the stage's x area) >> 4) | (chunk stride >> 4) << 16
+  uint32_t idesc;
+  int16_t tap_lo[4], tap_hi[4];
+};
 
 struct alignas(64) WgParams {
   CUtensorMap mapX, mapDY;
@@ -61,7 +70,6 @@ struct alignas(64) WgParams {
   int row_bytes;                    // bytes of one slow row of a staged box (FB pixels x 128)
   int m_half_chunks;                // channel chunks per 64 accumulator rows (stacked mode stages the shifted box there)
   uint32_t desc_hi;                 // descriptor high word: SBO | version | layout
-  uint32_t idesc;
   const float* out_scale;           // optional device scalar multiplied into the sums
   float* dw;
   int16_t job_coblk[kMaxJobs], job_g0[kMaxJobs], job_ng[kMaxJobs], job_s0[kMaxJobs], job_ns[kMaxJobs];
@@ -180,13 +188,11 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
     uint32_t phase = 0, acc_phase = 0;
     const uint32_t a_inc = (uint32_t)p.kstep_bytes >> 4, b_inc = a_inc;        // one k step (8 or 16 pixels) of one chunk
     const uint32_t desc_hi = p.desc_hi;
-    const uint32_t idesc = p.idesc;
     const int ksteps = p.ksteps, n_stages = p.n_stages;
     const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
     // descriptor words: hi = SBO | version | layout; lo = (address >> 4) | LBO (chunk pitch); one k step = 8 / 16 pixels
     const uint32_t a_lo_base = (stages_base >> 4) | (((uint32_t)p.dy_chunk_stride >> 4) << 16);
-    const uint32_t b_lo_base = ((stages_base + (uint32_t)p.x_off) >> 4) | (((uint32_t)p.x_box_stride >> 4) << 16);
-    const uint32_t N = (uint32_t)p.N;
+    const uint32_t b_lo_base = (stages_base + (uint32_t)p.x_off) >> 4;      // (+ the slot's offset and chunk stride)
     const float oscale = p.out_scale ? *p.out_scale : 1.f;
     for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
       const WgItem it = decode_wg_item(p, wi);
@@ -204,9 +210,10 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
           tc_fence_after();
           const uint32_t a_lo0 = a_lo_base + (uint32_t)st * stage_step, b_lo0 = b_lo_base + (uint32_t)st * stage_step;
           for (int i = issuer; i < ns; i += kIssuers) {
-            const uint32_t d = tmem_base + (uint32_t)i * N;
+            const uint32_t d = tmem_base + (uint32_t)p.slots[s0 + i].col0;
+            const uint32_t idesc = p.slots[s0 + i].idesc;
             uint32_t a_lo = a_lo0;
-            uint32_t b_lo = b_lo0 + p.slots[s0 + i].b_off16;
+            uint32_t b_lo = b_lo0 + p.slots[s0 + i].b_desc;
 #pragma unroll 8
             for (int ks = 0; ks < ksteps; ++ks) {
               umma<KIND>(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, first | (uint32_t)ks);
@@ -234,17 +241,20 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
         mbar_wait(tfull_bar, acc_phase, 700);
         tc_fence_after();
         for (int i = 0; i < ns; ++i) {
-          const WgSlot sl = p.slots[s0 + i];
-          const int tap = (p.stacked && (q >> 1)) ? sl.tap_hi : sl.tap_lo;
-          float* dst = p.dw + ((size_t)(tap < 0 ? 0 : tap) * p.Cout + co) * p.Cin;
-          for (int c0 = 0; c0 < p.N; c0 += 16) {
+          const WgSlot& sl = p.slots[s0 + i];
+          const bool wide = sl.ntaps > 1;
+          for (int c0 = 0; c0 < sl.n_cols; c0 += 16) {
+            const int sub = wide ? (c0 >> 6) : 0, ci0 = wide ? (c0 & 63) : c0;
+            const int tap = (p.stacked && (q >> 1)) ? sl.tap_hi[sub] : sl.tap_lo[sub];
+            if (ci0 >= p.Cin) continue;                                  // (padding columns of a 64-wide chunk)
             uint32_t r[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(i * p.N + c0), r);
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sl.col0 + c0), r);
             tmem_ld_wait();
             if (co < p.Cout && tap >= 0) {
+              float* dst = p.dw + ((size_t)tap * p.Cout + co) * p.Cin + ci0;
 #pragma unroll
               for (int k = 0; k < 16; ++k)
-                if (c0 + k < p.Cin) atomicAdd(dst + c0 + k, __uint_as_float(r[k]) * oscale);
+                if (ci0 + k < p.Cin) atomicAdd(dst + k, __uint_as_float(r[k]) * oscale);
             }
           }
         }
@@ -317,10 +327,8 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
   p.kstep_bytes = kpix * 128;
   p.row_bytes = p.FB * 128;
   p.m_half_chunks = 64 / cchunk;
-  p.idesc = esz == 2 ? make_idesc_f16(128, p.N, 1, 1) : make_idesc_tf32(128, p.N, 1, 1);
 
   // ---- jobs: tap groups packed into TMEM (512 columns) per output-channel block; at most kMaxJobGroups boxes per stage
-  const int n_acc = 512 / p.N;
   const int n_coblk = ceil_div(Cout, 128);
   const int n_groups = (int)pl.groups.size();
   SOS_CHECK_ARG(n_groups <= kMaxGroups, "sos_conv2d_wgrad: too many tap groups");
@@ -373,10 +381,33 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
   for (int i = 0; i < n_groups; ++i)
     if (!is_upper[i]) leads.push_back(i);
   const int n_leads = (int)leads.size();
-  auto slots_of = [&](int li) { return (int)pl.groups[leads[li]].n_sub; };
-  for (int li = 0; li < n_leads; ++li) SOS_CHECK_ARG(slots_of(li) <= n_acc, "sos_conv2d_wgrad: tap group does not fit in TMEM");
-  // choose SB (pixels per tile = FB*SB) and groups per job so that at least 2 stages fit
-  int SB = pl.SB, groups_per_job = 1;
+  // accumulator slots of every lead group: wide slots (up to four equally spaced taps per MMA) where the operands allow
+  struct SlotDesc { int li, j0, nt, cols; };
+  std::vector<SlotDesc> sd;
+  static const int narrow_only = getenv("SOS_WGRAD_NARROW") && atoi(getenv("SOS_WGRAD_NARROW")) == 1;     // A/B aid
+  const bool can_wide = esz == 2 && p.n_ci_chunks == 1 && !narrow_only && a.force_plan < 0;
+  bool any_wide = false;
+  std::vector<int> spacing(n_leads, 0);
+  for (int li = 0; li < n_leads; ++li) {
+    const TapGroup& ga = pl.groups[leads[li]];
+    bool eq = can_wide && ga.n_sub > 1;
+    const int da = ga.n_sub > 1 ? ga.a_off[1] - ga.a_off[0] : 0;
+    for (int j = 1; j < ga.n_sub && eq; ++j) eq = (ga.a_off[j] - ga.a_off[j - 1]) == da && da > 0;
+    spacing[li] = eq ? da : 0;
+    if (eq) {
+      for (int j = 0; j < ga.n_sub;) {
+        const int nt = std::min(4, ga.n_sub - j);
+        sd.push_back({li, j, nt, nt == 1 ? p.N : 64 * nt});
+        any_wide |= nt > 1;
+        j += nt;
+      }
+    } else {
+      for (int j = 0; j < ga.n_sub; ++j) sd.push_back({li, j, 1, p.N});
+    }
+  }
+  for (const SlotDesc& d : sd) SOS_CHECK_ARG(d.cols <= 512, "sos_conv2d_wgrad: accumulator does not fit in TMEM");
+  // choose SB (pixels per tile = FB*SB) so that at least 2 stages fit, then how many groups' boxes a stage may hold
+  int SB = pl.SB;
   const int avail = kSmemLimit - 2048;
   const int dy_chunks_staged = stacked ? 128 / cchunk : n_co_chunks_max;
   auto stage_bytes_for = [&](int sb, int ng, int* x_off_out, int* reach_out) {
@@ -399,17 +430,40 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
     if (2 * used + std::max(0, reach - used) <= avail || SB == 2) break;
     SB /= 2;
   }
-  // more groups per job (sharing the staged dy tile) while TMEM and 3 stages allow
+  int gcap = 1;                                              // groups per job (sharing the staged dy tile) while 3 stages fit
   for (int ng = 2; ng <= std::min(n_leads, 4); ++ng) {
-    int slots_in = 0;
-    for (int i = 0; i < ng; ++i) slots_in += slots_of(i);
     int reach = 0;
     const int used = stage_bytes_for(SB, ng, nullptr, &reach);
-    if (slots_in > n_acc || 3 * used + std::max(0, reach - used) > avail) break;
-    groups_per_job = ng;
+    if ((any_wide ? 2 : 3) * used + std::max(0, reach - used) > avail) break;
+    gcap = ng;
   }
+  // jobs: bins of slots with at most 512 TMEM columns and gcap distinct groups.  Narrow plans keep whole groups together in tap
+  // order (as the first implementation did); wide plans are packed first-fit by decreasing width
+  struct JobDesc { std::vector<int> groups; std::vector<int> slots; int cols = 0; };
+  std::vector<JobDesc> jd;
+  {
+    std::vector<int> order(sd.size());
+    for (size_t i = 0; i < sd.size(); ++i) order[i] = (int)i;
+    if (any_wide) std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return sd[x].cols > sd[y].cols; });
+    for (int si : order) {
+      const SlotDesc& d = sd[si];
+      int placed = -1;
+      const int first = any_wide ? 0 : std::max(0, (int)jd.size() - 1);      // narrow: only the open (last) job
+      for (int j = first; j < (int)jd.size() && placed < 0; ++j) {
+        const bool has = std::find(jd[j].groups.begin(), jd[j].groups.end(), d.li) != jd[j].groups.end();
+        if (jd[j].cols + d.cols <= 512 && (has || (int)jd[j].groups.size() < gcap)) placed = j;
+      }
+      if (placed < 0) { jd.emplace_back(); placed = (int)jd.size() - 1; }
+      JobDesc& J = jd[placed];
+      if (std::find(J.groups.begin(), J.groups.end(), d.li) == J.groups.end()) J.groups.push_back(d.li);
+      J.slots.push_back(si);
+      J.cols += d.cols;
+    }
+  }
+  int max_ng = 1;
+  for (const JobDesc& J : jd) max_ng = std::max(max_ng, (int)J.groups.size());
   int reach = 0;
-  const int used = stage_bytes_for(SB, groups_per_job, &p.x_off, &reach);
+  const int used = stage_bytes_for(SB, max_ng, &p.x_off, &reach);
   p.SB = SB;
   p.dy_chunk_bytes = SB * p.FB * 128;
   p.dy_chunk_stride = round_up(p.dy_chunk_bytes, 1024);
@@ -424,31 +478,44 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
   SOS_CHECK_ARG(p.n_stages >= 1, "sos_conv2d_wgrad: stage of %d bytes does not fit in shared memory", used);
 
   int n_jobs = 0, n_slots = 0, n_jg = 0;
+  std::vector<double> job_cost;
   for (int cb = 0; cb < n_coblk; ++cb) {
-    int li = 0;
-    while (li < n_leads) {
-      int ng = 0, slots_in = 0;
-      while (li + ng < n_leads && ng < groups_per_job && slots_in + slots_of(li + ng) <= n_acc) {
-        slots_in += slots_of(li + ng);
-        ++ng;
-      }
-      SOS_CHECK_ARG(ng > 0 && n_jobs < kMaxJobs && n_slots + slots_in <= kMaxSlots && n_jg + ng <= kMaxJobs * 4,
-                    "sos_conv2d_wgrad: too many jobs / accumulators");
+    for (const JobDesc& J : jd) {
+      const int ng = (int)J.groups.size(), nsl = (int)J.slots.size();
+      SOS_CHECK_ARG(n_jobs < kMaxJobs && n_slots + nsl <= kMaxSlots && n_jg + ng <= kMaxJobs * 4, "sos_conv2d_wgrad: too many jobs / accumulators");
       p.job_coblk[n_jobs] = (int16_t)cb;
       p.job_g0[n_jobs] = (int16_t)n_jg;
       p.job_ng[n_jobs] = (int16_t)ng;
       p.job_s0[n_jobs] = (int16_t)n_slots;
-      p.job_ns[n_jobs] = (int16_t)slots_in;
-      for (int gi = 0; gi < ng; ++gi) {
-        const int A = leads[li + gi];
+      p.job_ns[n_jobs] = (int16_t)nsl;
+      for (int gi = 0; gi < ng; ++gi) p.job_group[n_jg++] = (int16_t)leads[J.groups[gi]];
+      int col = 0;
+      double cost = 0;
+      for (int si : J.slots) {
+        const SlotDesc& d = sd[si];
+        const int A = leads[d.li];
         const TapGroup& ga = pl.groups[A];
-        p.job_group[n_jg++] = (int16_t)A;
-        for (int j = 0; j < ga.n_sub; ++j)
-          p.slots[n_slots++] = WgSlot{(int16_t)gi, (int16_t)ga.a_off[j], ga.tap[j], (int16_t)(partner[A] >= 0 ? pl.groups[partner[A]].tap[j] : -1),
-                                      ((uint32_t)gi * p.n_ci_chunks * p.x_box_stride + (uint32_t)ga.a_off[j] * (uint32_t)p.row_bytes) >> 4};
+        const int gi = (int)(std::find(J.groups.begin(), J.groups.end(), d.li) - J.groups.begin());
+        WgSlot ws{};
+        ws.x_idx = (int16_t)gi;
+        ws.ntaps = (int16_t)d.nt;
+        ws.col0 = (int16_t)col;
+        ws.n_cols = (int16_t)d.cols;
+        const uint32_t off = (uint32_t)gi * p.n_ci_chunks * p.x_box_stride + (uint32_t)ga.a_off[d.j0] * (uint32_t)p.row_bytes;
+        const uint32_t lbo = d.nt > 1 ? (uint32_t)spacing[d.li] * (uint32_t)p.row_bytes : (uint32_t)p.x_box_stride;
+        SOS_CHECK_ARG((lbo >> 4) < (1u << 14), "sos_conv2d_wgrad: chunk stride too large for the descriptor");
+        ws.b_desc = (off >> 4) | ((lbo >> 4) << 16);
+        ws.idesc = esz == 2 ? make_idesc_f16(128, d.cols, 1, 1) : make_idesc_tf32(128, d.cols, 1, 1);
+        for (int c = 0; c < 4; ++c) {
+          ws.tap_lo[c] = (int16_t)(c < d.nt ? ga.tap[d.j0 + c] : -1);
+          ws.tap_hi[c] = (int16_t)((c < d.nt && partner[A] >= 0) ? pl.groups[partner[A]].tap[d.j0 + c] : -1);
+        }
+        p.slots[n_slots++] = ws;
+        col += d.cols;
+        cost += p.ksteps * std::max(d.cols / 2.0, (4096.0 + 32.0 * round_up(d.cols, 64)) / 128.0);
       }
+      job_cost.push_back(cost);
       ++n_jobs;
-      li += ng;
     }
   }
   p.n_jobs = n_jobs;
@@ -494,9 +561,8 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
     double total_wd = 0, wmin = 1e300, wmax = 0;
     for (int j = 0; j < n_jobs; ++j) {
       const int co_here = std::min(128, Cout - p.job_coblk[j] * 128);
-      const double mma_cyc = std::max(p.N / 2.0, (4096.0 + 32.0 * round_up(p.N, 64)) / 128.0);
       const double bytes = (double)ceil_div(co_here, p.cbo) * (stacked ? 2 : 1) * p.dy_chunk_bytes + (double)p.job_ng[j] * p.n_ci_chunks * p.x_box_bytes;
-      wgt[j] = std::max((double)p.job_ns[j] * p.ksteps * mma_cyc, bytes / 48.0);
+      wgt[j] = std::max(job_cost[j], bytes / 48.0);
       total_wd += wgt[j];
       wmin = std::min(wmin, wgt[j]);
       wmax = std::max(wmax, wgt[j]);
