@@ -289,7 +289,7 @@ typedef struct sos_conv_args {
 } sos_conv_args;
 #define SOS_DTYPE_TF32 0
 #define SOS_DTYPE_F16 1
-int sos_conv_stats_rows(void);   /* upper bound of *stats_rows_out (8 epilogue warps x SM count) */
+int sos_conv_stats_rows(void);   /* upper bound of *stats_rows_out (one row per CTA: the SM count) */
 /* Plan cache (SURVEY 8b sos_plan_*): the planner result, MMA program and tensor-map geometry of sos_conv2d_tc are computed once
  * per distinct (shapes, taps, types) key and reused; tensor maps are re-encoded only when a base pointer changes. */
 void sos_plan_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries);

@@ -385,18 +385,22 @@ __global__ void __launch_bounds__(kThreadsRow, 1) rowconv_f16_kernel(const __gri
       c_base += r.k1 - r.k0;
     }
     if (ethread == 0) bulk_wait<0>();
-    if (p.stats) {
-      __syncwarp();
-      float* dst = p.stats + (size_t)(blockIdx.x * kRowEpiWarps + ewarp) * 2 * p.stats_c;
-      for (int c = lane; c < p.stats_c; c += 32) {
-        dst[c] = c < Cout ? my_stats[c] : 0.f;
-        dst[p.stats_c + c] = c < Cout ? my_stats[Cout + c] : 0.f;
-      }
-    }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.stats) {
+    // one row of BatchNorm partial sums per CTA: the eight epilogue warps' running sums, added up in a fixed order
+    const int N = p.Cout;
+    float* dst = p.stats + (size_t)blockIdx.x * 2 * p.stats_c;
+    for (int c = threadIdx.x; c < 2 * p.stats_c; c += blockDim.x) {
+      const int half = c >= p.stats_c ? 1 : 0, ch = c - half * p.stats_c;
+      float sum = 0.f;
+      if (ch < N)
+        for (int w = 0; w < kRowEpiWarps; ++w) sum += stats_s[w * 2 * N + half * N + ch];
+      dst[c] = sum;
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -600,7 +604,7 @@ int sos_rowconv_launch(const sos_conv_args& a, cudaStream_t stream) {
   }
   rowconv_f16_kernel<<<plan->grid, kThreadsRow, plan->smem, stream>>>(p);
   SOS_CHECK_LAUNCH("sos_conv2d_tc (row kernel)");
-  if (a.stats_rows_out) *a.stats_rows_out = kRowEpiWarps * plan->grid;
+  if (a.stats_rows_out) *a.stats_rows_out = plan->grid;
   if (a.plan_out) {
     const int32_t po[8] = {2, 1, p.dwl, 1, p.KH, p.n_stages, p.stage_bytes, plan->grid};      // [0] = 2: row-streaming kernel
     memcpy(a.plan_out, po, sizeof(po));

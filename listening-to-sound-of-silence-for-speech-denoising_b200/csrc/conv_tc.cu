@@ -394,18 +394,22 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (ethread == 0) bulk_wait<0>();
-    if (p.stats) {
-      __syncwarp();
-      float* dst = p.stats + (size_t)(blockIdx.x * kEpiWarps + ewarp) * 2 * p.stats_c;
-      for (int c = lane; c < p.stats_c; c += 32) {
-        dst[c] = c < p.N ? my_stats[c] : 0.f;
-        dst[p.stats_c + c] = c < p.N ? my_stats[p.N + c] : 0.f;
-      }
-    }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.stats) {
+    // one row of BatchNorm partial sums per CTA: the eight epilogue warps' running sums, added up in a fixed order
+    const int N = p.N;
+    float* dst = p.stats + (size_t)blockIdx.x * 2 * p.stats_c;
+    for (int c = threadIdx.x; c < 2 * p.stats_c; c += blockDim.x) {
+      const int half = c >= p.stats_c ? 1 : 0, ch = c - half * p.stats_c;
+      float sum = 0.f;
+      if (ch < N)
+        for (int w = 0; w < kEpiWarps; ++w) sum += stats_s[w * 2 * N + half * N + ch];
+      dst[c] = sum;
+    }
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -729,12 +733,12 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
   if (plan->esz == 2) tapgemm_f16_kernel<<<plan->grid, kThreadsTc, plan->smem, stream>>>(p);
   else tapgemm_tf32_kernel<<<plan->grid, kThreadsTc, plan->smem, stream>>>(p);
   SOS_CHECK_LAUNCH("sos_conv2d_tc");
-  if (a.stats_rows_out) *a.stats_rows_out = kEpiWarps * plan->grid;
+  if (a.stats_rows_out) *a.stats_rows_out = plan->grid;
   if (a.plan_out) memcpy(a.plan_out, plan->plan_out, sizeof(plan->plan_out));
   return SOS_OK;
 }
 
-extern "C" int sos_conv_stats_rows(void) { return kEpiWarps * sos_num_sms(); }
+extern "C" int sos_conv_stats_rows(void) { return sos_num_sms(); }
 
 // Host-only planner query (no CUDA call): what sos_conv2d_tc would choose for these shapes / taps / types.
 extern "C" int sos_conv2d_plan(const sos_conv_args* ap, int32_t* info) {

@@ -331,6 +331,22 @@ _WGRAD_WS = os.environ.get("SOS_WGRAD_WS", "1") != "0"           # A/B switch: w
 _Y_HALF = os.environ.get("SOS_Y_HALF", "1") != "0"                 # A/B switch: raw conv outputs (BatchNorm inputs) stored as half
 
 
+# nn.BatchNorm2d.num_batches_tracked += 1 in training mode (M2/networks.py:37; nobody reads it, but it is part of the state_dict):
+# the blocks note their counters here and the networks bump them all with ONE multi-tensor launch per forward instead of 60.
+_BN_PENDING = []
+
+
+def note_bn_step(bn):
+    _BN_PENDING.append(bn.num_batches_tracked)
+
+
+def flush_bn_steps():
+    if _BN_PENDING:
+        with torch.no_grad():
+            torch._foreach_add_(_BN_PENDING, 1)
+        _BN_PENDING.clear()
+
+
 def _bn_pad(gamma, beta, rm, rv, Cp):
     """BatchNorm parameter vectors zero-padded to the map's channel count (gamma = beta = 0 -> z = 0 in the padded channels)."""
     Cn = gamma.numel()
@@ -548,8 +564,7 @@ def bn_act(y, bn, act, slope, training, round_out=True, round_grad=True, conv_pa
             with torch.no_grad():
                 rm.copy_(rm_p[:Cn])
                 rv.copy_(rv_p[:Cn])
-        with torch.no_grad():
-            bn.num_batches_tracked += 1
+        note_bn_step(bn)
         return z
     # eval with autograd: plain tensor expression (not a hot path; inference uses conv_fused_eval)
     scale = gamma * torch.rsqrt(rv_p + bn.eps)

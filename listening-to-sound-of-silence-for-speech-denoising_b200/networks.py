@@ -51,8 +51,7 @@ class _Block(nn.Module):
         if self.training and half:                                       # conv + batch-stat BN + activation as one autograd node
             z = L.ConvBNActH.apply(x, conv.weight, bn.weight, bn.bias, slope, bn.running_mean, bn.running_var, bn.eps, bn.momentum,
                                    act, geom, not self.round_out)
-            with torch.no_grad():
-                bn.num_batches_tracked += 1
+            L.note_bn_step(bn)
             return z
         if self.training:                                                # batch statistics come out of the conv epilogue
             y, partial = L.TapConv.apply(x, conv.weight, geom, True)
@@ -174,9 +173,8 @@ def _run_encoder(enc, x):
         params += [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
     bn0 = enc[0].block[1]
     z = L.EncoderChainH.apply(x, tuple(blk.geom for blk in enc), bn0.eps, bn0.momentum, *params)
-    with torch.no_grad():
-        for blk in enc:
-            blk.block[1].num_batches_tracked += 1
+    for blk in enc:
+        L.note_bn_step(blk.block[1])
     return z
 
 
@@ -195,6 +193,7 @@ class AudioVisualNet(nn.Module):
         m = self.lstm(seq)                                                # (v, B, 200); the head acts per row: keep (v, B) order
         m = L.LinearAct.apply(m, self.fc1[0].weight, self.fc1[0].bias, ops.ACT_RELU)
         m = L.LinearAct.apply(m, self.fc1[2].weight, self.fc1[2].bias, ops.ACT_NONE)
+        L.flush_bn_steps()
         return m.squeeze(2).t()                                           # (B, v)
 
 
@@ -223,6 +222,7 @@ class ContextAggNet(nn.Module):
         h = L.LinearAct.apply(h, self.fc[2].weight, self.fc[2].bias, ops.ACT_RELU)
         h = L.LinearAct.apply(h, self.fc[4].weight, self.fc[4].bias, ops.ACT_SIGMOID)       # (T, B, 512)
         m = L.SeqToMap.apply(h)                                           # (B, 512, T) = h.permute(1, 2, 0)
+        L.flush_bn_steps()
         return m.view(m.size(0), 2, -1, m.size(2))
 
 
@@ -257,7 +257,9 @@ class InpaintNet(nn.Module):
         o = self.up1[0](o, d4, size=d4.shape[1:3])
         o = self.up1[1](o)
         o = self.up2[0](o, d3, size=d3.shape[1:3])
-        return self.up2[1](o)
+        o = self.up2[1](o)
+        L.flush_bn_steps()
+        return o
 
     def forward(self, x, y):
         return L.ToNCHW.apply(self.forward_nhwc(_nhwc_in(x), _nhwc_in(y)), 2)
