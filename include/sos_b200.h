@@ -199,7 +199,8 @@ int sos_transpose(const float* in, int64_t rows, int64_t cols, float* out, cudaS
 /* y[r][c] = act(y[r][c] + bias[c]) in place; act 0 none, 1 ReLU, 3 sigmoid.  ld = row pitch (floats). */
 /* fp32-grade GEMM operands for the tap GEMM (see the kernel comment in csrc/elementwise.cu): x = hi + lo with hi = tf32(x),
  * lo = tf32(x - hi); out[s * slot_stride + r * ld_out + k] = part_s(src[r * stride_r + (k + k_shift) * stride_k]) for r < R,
- * k < KP, zero where k >= K or the shifted index leaves [0, K).  n_slots = 2: {hi, lo} (activation stack); 3: {hi, hi, lo}
+ * k < KP, zero where k >= K or the shifted index leaves [0, K).  n_slots = 1: {hi} (single-pass TF32 operand); 2: {hi, lo}
+ * (activation stack); 3: {hi, hi, lo}
  * (weight slots along K).  One of the strides must be 1 (the kernel transposes through shared memory when stride_k != 1).
  * batch > 1: that many independent (R, K) operands src + i * src_batch_stride -> out + i * out_batch_stride (e.g. the spectrogram of
  * clip i, (512, T) with T contiguous, becoming rows i*T .. i*T + T - 1 of the inverse transform's activation operand). */

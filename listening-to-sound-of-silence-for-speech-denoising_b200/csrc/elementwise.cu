@@ -923,7 +923,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, long long rows, l
 // a @ b = hi@hi + lo@hi + hi@lo runs as ONE 3-tap launch of the tap GEMM: the activation operand is the stack [hi; lo] (tap t reads
 // stack row {0, 1, 0}[t]) and the weight operand carries the slots [hi | hi | lo] along K.
 //   out[s * slot_stride + r * ld_out + k] = part_s(src[r * sr + (k + k_shift) * sk]),  r < R, k < KP  (zero where k >= K or the
-//   shifted source index leaves [0, K)); n_slots = 2: parts {hi, lo}; n_slots = 3: {hi, hi, lo}.
+//   shifted source index leaves [0, K)); n_slots = 1: {hi} (a plain TF32 operand); 2: parts {hi, lo}; 3: {hi, hi, lo}.
 // One of sr / sk is 1: the 32 x 32 tile is read along that axis and written along k, i.e. the kernel also transposes.
 __global__ void split_tf32_kernel(const float* __restrict__ src, long long R, long long K, long long KP, long long sr, long long sk,
                                   long long k_shift, float* __restrict__ out, long long ld_out, long long slot_stride, int n_slots,
@@ -953,7 +953,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, long long R, lo
     o[0] = hi;
     if (n_slots == 2) {
       o[slot_stride] = lo;
-    } else {
+    } else if (n_slots == 3) {
       o[slot_stride] = hi;
       o[2 * slot_stride] = lo;
     }
@@ -1584,7 +1584,7 @@ int sos_transpose(const float* in, int64_t rows, int64_t cols, float* out, cudaS
 int sos_split_tf32(const float* src, int64_t R, int64_t K, int64_t KP, int64_t stride_r, int64_t stride_k, int64_t k_shift, float* out,
                    int64_t ld_out, int64_t slot_stride, int n_slots, int64_t batch, int64_t src_batch_stride, int64_t out_batch_stride,
                    cudaStream_t stream) {
-  SOS_CHECK_ARG(src && out && R > 0 && K > 0 && KP >= K && (n_slots == 2 || n_slots == 3), "sos_split_tf32: bad arguments");
+  SOS_CHECK_ARG(src && out && R > 0 && K > 0 && KP >= K && (n_slots >= 1 && n_slots <= 3), "sos_split_tf32: bad arguments");
   SOS_CHECK_ARG(stride_r == 1 || stride_k == 1, "sos_split_tf32: one of the source strides must be 1");
   SOS_CHECK_ARG(ceil_div_ll(R, 32) <= 65535 && batch >= 1 && batch <= 65535, "sos_split_tf32: too many rows / batches");
   dim3 grid((unsigned)ceil_div_ll(KP, 32), (unsigned)ceil_div_ll(R, 32), (unsigned)batch);

@@ -408,6 +408,8 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
   for (const SlotDesc& d : sd) SOS_CHECK_ARG(d.cols <= 512, "sos_conv2d_wgrad: accumulator does not fit in TMEM");
   // choose SB (pixels per tile = FB*SB) so that at least 2 stages fit, then how many groups' boxes a stage may hold
   int SB = pl.SB;
+  static const int force_sb = getenv("SOS_WGRAD_SB") ? atoi(getenv("SOS_WGRAD_SB")) : 0;     // experiment aid
+  if (force_sb > 0 && any_wide && force_sb < SB) SB = force_sb;
   const int avail = kSmemLimit - 2048;
   const int dy_chunks_staged = stacked ? 128 / cchunk : n_co_chunks_max;
   auto stage_bytes_for = [&](int sb, int ng, int* x_off_out, int* reach_out) {

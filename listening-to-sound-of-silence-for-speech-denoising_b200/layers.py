@@ -704,6 +704,16 @@ def _grad_out(p, g):
     return g
 
 
+_GRAD_3PASS = os.environ.get("SOS_GRAD_3PASS", "0") == "1"      # A/B switch: fp32-grade (3-pass) gradient GEMMs of the LSTM / MLP head
+
+
+def _bw_passes():
+    """Passes of the split-TF32 GEMMs in BACKWARD: the forward projections feed the sigmoid mask and stay fp32-grade (three passes);
+    their data and weight gradients run as one TF32 pass in the default (half) mode -- the 11-bit-significand contract every
+    convolution gradient of this mode already has (cuDNN's own default for the reference's LSTM) -- and as three in precise mode."""
+    return 3 if (precise() or not half_mode() or _GRAD_3PASS) else 1
+
+
 class LinearAct(torch.autograd.Function):
     """act(x @ W^T + b) over the rows of x -- nn.Linear + ReLU / Sigmoid of the heads (M1/networks.py:96-98, M2/networks.py:65-70)
     at fp32-grade accuracy on the tensor cores (ops.gemm3: one 3-tap TF32 tap-GEMM launch over split operands; bias and activation
@@ -730,11 +740,12 @@ class LinearAct(torch.autograd.Function):
         db = b.grad if direct_b else torch.zeros(n_out, device=dy.device, dtype=torch.float32)
         dpre = ops.bias_act_backward(dy2, y, ctx.act, db)
         dx = dW = None
+        np_ = _bw_passes()
         if ctx.needs_input_grad[0]:
-            dx = ops.gemm3(ops.split_act(dpre), ops.split_weight(W.detach(), transpose=True), K, tag="linear_dgrad")
+            dx = ops.gemm3(ops.split_act(dpre, passes=np_), ops.split_weight(W.detach(), transpose=True, passes=np_), K, tag="linear_dgrad")
             dx = (dx if dx.is_contiguous() else dx.contiguous()).view(*dy.shape[:-1], K)
         if ctx.needs_input_grad[1]:
-            dW = ops.gemm3(ops.split_act(dpre, transpose=True), ops.split_weight(x2, transpose=True), K, tag="linear_wgrad")
+            dW = ops.gemm3(ops.split_act(dpre, transpose=True, passes=np_), ops.split_weight(x2, transpose=True, passes=np_), K, tag="linear_wgrad")
             dW = _grad_out(W, dW)
         return dx, dW, (None if direct_b else db), None
 
@@ -783,18 +794,20 @@ class BiLSTMFn(torch.autograd.Function):
         dgx = ops.lstm_backward(dout.contiguous(), whh, out, gates, cell)   # (T,B,2,4H)
         flat = dgx.view(M, 8 * H)
         dx = None
+        np_ = _bw_passes()
         if ctx.needs_input_grad[0]:
             # dx = dg_f @ w_ih + dg_r @ w_ih_r: ONE GEMM over K = 8H against [w_ih; w_ih_r]^T
-            dx = ops.gemm3(ops.split_act(flat), ops.split_weight_cat_t([w_ih.detach(), w_ih_r.detach()]), I, tag="lstm_dgrad").view(T, B, I)
-        xT = ops.split_weight(x2, transpose=True)                           # (I, 3 * MP): shared by both directions
+            dx = ops.gemm3(ops.split_act(flat, passes=np_), ops.split_weight_cat_t([w_ih.detach(), w_ih_r.detach()], passes=np_), I,
+                           tag="lstm_dgrad").view(T, B, I)
+        xT = ops.split_weight(x2, transpose=True, passes=np_)               # (I, passes * MP): shared by both directions
         out2 = out.view(M, 2 * H)
         grads = []
         for d, (wi, wh, bi, bh) in enumerate(((w_ih, w_hh, b_ih, b_hh), (w_ih_r, w_hh_r, b_ih_r, b_hh_r))):
             dg = flat[:, d * 4 * H:(d + 1) * 4 * H]                         # (M, 4H), row stride 8H
-            dgT = ops.split_act(dg, transpose=True)                         # (2, 4H, MP)
+            dgT = ops.split_act(dg, transpose=True, passes=np_)             # (2 | 1, 4H, MP)
             dW = _grad_out(wi, ops.gemm3(dgT, xT, I, tag="lstm_wgrad"))
             # h_{t-1} of the forward direction is out[t-1, :, :H] (rows shifted by -B); of the reverse direction out[t+1, :, H:]
-            hprevT = ops.split_weight(out2[:, d * H:(d + 1) * H], transpose=True, k_shift=(-B if d == 0 else B))
+            hprevT = ops.split_weight(out2[:, d * H:(d + 1) * H], transpose=True, k_shift=(-B if d == 0 else B), passes=np_)
             dWhh = ops.gemm3(dgT, hprevT, H, tag="lstm_wgrad")
             dWhh = _grad_out(wh, dWhh if dWhh.is_contiguous() else dWhh.contiguous())
             if _direct(bi) and _direct(bh):

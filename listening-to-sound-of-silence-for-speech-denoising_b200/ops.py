@@ -722,36 +722,38 @@ def _split_into(src, transpose, k_shift, out, ld_out, slot_stride, n_slots, col_
     _count()
 
 
-def split_act(x, transpose=False, k_shift=0):
+def split_act(x, transpose=False, k_shift=0, passes=3):
     """x (R, K) fp32 (any row stride, unit column stride) -> activation stack (2, R, KP) [hi; lo], KP = K rounded up to 8.
     transpose: the operand is x^T, i.e. the stack is (2, K, RP) (RP = R rounded up to 8); k_shift then shifts along R:
-    element [k][r] = x[r + k_shift][k] (zero outside), which expresses h_{t-1} / h_{t+1} of an LSTM output."""
+    element [k][r] = x[r + k_shift][k] (zero outside), which expresses h_{t-1} / h_{t+1} of an LSTM output.
+    passes = 1: only the TF32-rounded part, (1, rows, KP): the operand of a single-pass TF32 GEMM (gradient GEMMs of the half mode)."""
     R, K = x.shape
     rows, kp = (K, _r8(R)) if transpose else (R, _r8(K))
-    out = torch.empty(2, rows, kp, device=x.device, dtype=torch.float32)
-    _split_into(x, transpose, k_shift, out, kp, rows * kp, 2)
+    ns = 2 if passes == 3 else 1
+    out = torch.empty(ns, rows, kp, device=x.device, dtype=torch.float32)
+    _split_into(x, transpose, k_shift, out, kp, rows * kp, ns)
     return out
 
 
-def split_weight(w, transpose=False, k_shift=0):
+def split_weight(w, transpose=False, k_shift=0, passes=3):
     """w (Cout, K) fp32 (unit column stride) -> weight operand (Cout, 3 * KP) [hi | hi | lo]; transpose: the operand is w^T
-    (K, 3 * RP) with the same k_shift semantics as split_act."""
+    (K, 3 * RP) with the same k_shift semantics as split_act.  passes = 1: (rows, KP), the TF32-rounded part only."""
     R, K = w.shape
     rows, kp = (K, _r8(R)) if transpose else (R, _r8(K))
-    out = torch.empty(rows, 3 * kp, device=w.device, dtype=torch.float32)
-    _split_into(w, transpose, k_shift, out, 3 * kp, kp, 3)
+    out = torch.empty(rows, passes * kp, device=w.device, dtype=torch.float32)
+    _split_into(w, transpose, k_shift, out, passes * kp, kp, passes)
     return out
 
 
-def split_weight_cat_t(ws):
+def split_weight_cat_t(ws, passes=3):
     """Weight operand of x @ [w_0; w_1; ...] (the w_i (R_i, K) stacked along their rows, which is the contraction axis here):
-    (K, 3 * sum RP_i) with slot s holding [w_0^T | w_1^T | ...]."""
+    (K, 3 * sum RP_i) with slot s holding [w_0^T | w_1^T | ...] (passes = 1: one slot)."""
     K = ws[0].shape[1]
     kp = sum(_r8(w.shape[0]) for w in ws)
-    out = torch.empty(K, 3 * kp, device=ws[0].device, dtype=torch.float32)
+    out = torch.empty(K, passes * kp, device=ws[0].device, dtype=torch.float32)
     off = 0
     for w in ws:
-        _split_into(w, True, 0, out, 3 * kp, kp, 3, col_offset=off)
+        _split_into(w, True, 0, out, passes * kp, kp, passes, col_offset=off)
         off += _r8(w.shape[0])
     return out
 
@@ -765,14 +767,15 @@ def gemm3(a2, w3, n_out, bias=None, act=0, tag="gemm", out=None, col=0):
     """a2 (2, M, KP) activation stack, w3 (n_out, 3 * KP) weight operand -> (M, n_out) fp32 = act(a @ w^T + bias); act 0 / 1 relu /
     3 sigmoid.  out (M, ld) + col: write into columns [col, col + n_out) of an existing buffer (col, ld multiples of 4).  A fresh
     output is padded to a multiple of 4 columns; the returned view drops the padding."""
-    _, M, KP = a2.shape
-    assert w3.shape == (n_out, 3 * KP), (w3.shape, n_out, KP)
+    ns, M, KP = a2.shape
+    one = ns == 1                                     # single-pass TF32 (hi . hi): one tap over the TF32-rounded operands
+    assert w3.shape == (n_out, (1 if one else 3) * KP), (w3.shape, n_out, KP)
     if out is None:
         Cy = (n_out + 3) // 4 * 4
         out = torch.empty(M, Cy, device=a2.device, dtype=torch.float32)
     Cy = out.shape[1]
-    conv_tc(a2.view(1, 2, M, KP), w3, [0, 1, 0], [0, 0, 0], n_out, 1, M, 1, y=out.view(1, 1, M, Cy), y_coff=col, epi_shift=bias, act=act,
-            force_plan=1, tag=tag, k_real=KP)
+    conv_tc(a2.view(1, ns, M, KP), w3, [0] if one else [0, 1, 0], [0] if one else [0, 0, 0], n_out, 1, M, 1, y=out.view(1, 1, M, Cy), y_coff=col,
+            epi_shift=bias, act=act, force_plan=1, tag=tag, k_real=KP)
     return out if (Cy == n_out and col == 0) else out[:, col:col + n_out]
 
 

@@ -81,7 +81,8 @@ def conv_tc_any(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0,
     return y
 
 
-def conv_wgrad_any(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_plan=-1, plan_out=None, real=None, out_scale=None):
+def conv_wgrad_any(x, dy, tap_dh, tap_dw, Cout, OH, OW, stride=1, dy_coff=0, force_plan=-1, plan_out=None, real=None, out_scale=None,
+                   workspace=False):
     dw = conv_wgrad(_f(x), _f(dy), tap_dh, tap_dw, Cout, OH, OW, stride, dy_coff)
     return dw * out_scale if out_scale is not None else dw
 

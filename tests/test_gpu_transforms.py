@@ -171,15 +171,23 @@ def test_linear_act_matches_fp64(cuda, rows, K, n_out, act):
     pre = xr @ Wr.t() + br
     y = torch.relu(pre) if act == 1 else (torch.sigmoid(pre) if act == 3 else pre)
     y.backward(go)
-    xd, Wd, bd = (t.float().to(cuda).requires_grad_(True) for t in (x, W, b))
-    got = L.LinearAct.apply(xd.view(rows, 1, K), Wd, bd, act)
-    assert got.shape == (rows, 1, n_out)
-    got.backward(go.float().to(cuda).view(rows, 1, n_out))
     rel = lambda a, r: float((a.double().cpu() - r).abs().max() / (r.abs().max() + 1e-30))
     tol = 2e-5 * max(1.0, K / 400)           # (the tensor core truncates its fp32 accumulation: ~2^-24 per K step; plain TF32 would be ~1e-3)
-    errs = (rel(got.detach().view(rows, n_out), y.detach()), rel(xd.grad, xr.grad), rel(Wd.grad, Wr.grad), rel(bd.grad, br.grad))
-    print("linear_act", rows, K, n_out, act, ["%.2e" % e for e in errs])
-    assert errs[0] < tol and errs[1] < 2.5 * tol and errs[2] < 2.5 * tol * max(1.0, rows / K) and errs[3] < 2.5 * tol, errs
+    # default mode: fp32-grade forward, ONE TF32 pass for the data / weight gradients (layers._bw_passes; operands rounded to 11 bits:
+    # ~1e-3 of scale); precise mode: three passes everywhere
+    for precise in (False, True):
+        old = L.set_precise(precise)
+        try:
+            xd, Wd, bd = (t.float().to(cuda).requires_grad_(True) for t in (x, W, b))
+            got = L.LinearAct.apply(xd.view(rows, 1, K), Wd, bd, act)
+            assert got.shape == (rows, 1, n_out)
+            got.backward(go.float().to(cuda).view(rows, 1, n_out))
+        finally:
+            L.set_precise(old)
+        errs = (rel(got.detach().view(rows, n_out), y.detach()), rel(xd.grad, xr.grad), rel(Wd.grad, Wr.grad), rel(bd.grad, br.grad))
+        print("linear_act", "precise" if precise else "default", rows, K, n_out, act, ["%.2e" % e for e in errs])
+        gtol = 2.5 * tol if precise else 1.5e-3
+        assert errs[0] < tol and errs[1] < gtol and errs[2] < gtol * (max(1.0, rows / K) if precise else 1.0) and errs[3] < 2.5 * tol, errs
 
 
 def test_seq_map_roundtrip(cuda):
@@ -259,15 +267,25 @@ def test_bilstm_matches_torch(cuda, I, H, T, B):
     out, _ = ref(x)
     go = torch.randn(out.shape)
     out.backward(go)
-    xd = x.detach().to(cuda).requires_grad_(True)
-    got = mine(xd)
-    got.backward(go.to(cuda))
-    # (the projections and weight gradients are split-TF32 tensor-core GEMMs: exact products, but the tensor core's fp32 accumulation
-    #  truncates instead of rounding, ~2^-24 per K step: 1e-5 relative at K = 1600, vs 5e-4 for plain TF32)
-    assert float((got.cpu() - out.detach()).abs().max()) < 2e-5
-    assert float((xd.grad.cpu() - x.grad).abs().max()) < 5e-5 * float(x.grad.abs().max() + 1)
-    for (k, p), (_, q) in zip(ref.named_parameters(), mine.named_parameters()):
-        assert float((q.grad.cpu() - p.grad).abs().max()) < 1e-4 * float(p.grad.abs().max() + 1), k
+    from sos_b200 import layers as L
+    # (the projections are split-TF32 tensor-core GEMMs: exact products, but the tensor core's fp32 accumulation truncates instead of
+    #  rounding, ~2^-24 per K step: 1e-5 relative at K = 1600.  The data / weight gradients take ONE TF32 pass in the default mode
+    #  (layers._bw_passes: ~1e-3 of scale) and three in precise mode)
+    for precise in (False, True):
+        old = L.set_precise(precise)
+        try:
+            for q in mine.parameters():
+                q.grad = None
+            xd = x.detach().to(cuda).requires_grad_(True)
+            got = mine(xd)
+            got.backward(go.to(cuda))
+        finally:
+            L.set_precise(old)
+        assert float((got.cpu() - out.detach()).abs().max()) < 2e-5
+        gx, gw = (5e-5, 1e-4) if precise else (2e-3, 2e-3)
+        assert float((xd.grad.cpu() - x.grad).abs().max()) < gx * float(x.grad.abs().max() + 1)
+        for (k, p), (_, q) in zip(ref.named_parameters(), mine.named_parameters()):
+            assert float((q.grad.cpu() - p.grad).abs().max()) < gw * float(p.grad.abs().max() + 1), (k, precise)
 
 
 def test_longform_chunked_equals_unchunked(cuda):
