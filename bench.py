@@ -337,6 +337,18 @@ def run_gpu(args):
         except (OSError, ValueError):
             pass
         recs = [prof[n] for n in ("conv_fwd", "conv_dgrad") if n in prof and prof[n]["ms"] > 0]
+        # the other tensor-bound kernel families of the step, same accounting (algorithmic FLOPs of their launches / summed durations)
+        fam = {"rowconv_f16_kernel (48-channel dilated 5x5 layers: forward + data gradient)": ("conv_fwd_row", "conv_dgrad_row"),
+               "wgrad_f16_kernel (all weight gradients)": ("conv_wgrad",)}
+        other = []
+        for label, names in fam.items():
+            rr = [prof[n] for n in names if n in prof and prof[n]["ms"] > 0]
+            if rr:
+                fl, tms, nl = sum(r["flops"] for r in rr), sum(r["ms"] for r in rr), sum(r["n"] for r in rr)
+                tr = ncu.get(label.split(" ")[0], {})
+                other.append({"bound": "tensor", "kernel": label, "achieved": fl / (tms * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
+                              "frac": fl / (tms * 1e-3) / 1e12 / bf16_peak, "traffic": tr.get("dram_bytes_per_launch"), "traffic_note": tr.get("note"),
+                              "launches_per_step": nl / prof_steps, "ms_per_step": tms / prof_steps})
         roofline = None
         if recs:
             fl, tms, nl = sum(r["flops"] for r in recs), sum(r["ms"] for r in recs), sum(r["n"] for r in recs)
@@ -377,7 +389,7 @@ def run_gpu(args):
                        "cuda_graph": bool(trainer),
                        "l2": "no explicit flush: the step's activation working set (tens of GB) is far larger than the 126 MB L2"},
             "e2e": {"value": clips / (ms_e2e * 1e-3), "unit": "clips/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "step_conv_frac": step_conv_frac,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_other_kernels": other, "step_conv_frac": step_conv_frac,
             "step_conv_frac_note": f"{B} clips x 1.519 TFLOP (conv fwd + dgrad + wgrad) / ms_per_step / {bf16_peak:.1f} TFLOP/s",
             "kernels": kern, "cpu_baseline": cpu, "extra": extra}))
     if world > 1:

@@ -648,7 +648,7 @@ def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lat
     a.act = act
     a.slope = slope.data_ptr() if slope is not None else None
     a.force_plan = force_plan
-    po = (_I32 * 8)() if plan_out is not None else None
+    po = (_I32 * 8)() if (plan_out is not None or _prof is not None) else None
     a.plan_out = po
     partial, rows = None, None
     if want_stats:                                   # BatchNorm partial sums of the raw outputs, written by the epilogue
@@ -658,7 +658,8 @@ def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lat
     assert x.is_contiguous() and wk.is_contiguous() and y.is_contiguous()
     e0 = _pb()
     check(lib().sos_conv2d_tc(C.byref(a), _stream()), "sos_conv2d_tc")
-    _pe(tag, e0, 2.0 * N * OH * OW * Cout * (k_real or Cin) * ntaps)
+    # (profiling: launches served by the row-streaming kernel -- plan_out[0] == 2 -- are booked as their own family)
+    _pe(tag + ("_row" if (po is not None and po[0] == 2 and e0 is not None) else ""), e0, 2.0 * N * OH * OW * Cout * (k_real or Cin) * ntaps)
     _count()
     if plan_out is not None:
         plan_out[:] = list(po)
