@@ -38,6 +38,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kMaxProg = 144;             // entries of the deduplicated MMA programs
 struct alignas(64) TcParams {
   CUtensorMap mapA, mapB, mapD;
+  int pair;                      // CTA-pair mode (cta_group::2): mapB's box holds N / 2 weight rows, tiles are dealt to pairs
   int total_ctiles, n_nblk, tiles_fast_g, tiles_slow, n_phase;
   int S, N, cbe, n_chunks, n_groups;
   int FB, SB, stride;
@@ -80,7 +81,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
   return c;
 }
 
-template <int KIND>
+template <int KIND, int PAIR>
 __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -100,6 +101,15 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
+  // CTA pairs (PAIR): the two CTAs of a cluster work on two tiles at once.  Each stages its own activation boxes and HALF the rows
+  // of every weight tile; the even CTA ("leader") issues M = 256 MMAs (cta_group::2) that read both CTAs' shared memory and write
+  // both CTAs' TMEM -- the B operand bytes per FLOP, the part of the shared-memory traffic that bounds the wide layers, halve.
+  // Loads of both CTAs complete on the leader's `full` barriers; MMA commits arrive on both CTAs' `empty` / `tfull` barriers
+  // (multicast); both CTAs' epilogue warps arrive on the leader's `tempty` barriers.
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int grid_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;          // CTAs, or CTA pairs
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = PAIR ? (p.total_ctiles + 1) >> 1 : p.total_ctiles;        // tiles, or tile pairs (an odd last tile gets a dummy partner)
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.mapA);
     prefetch_tmap(&p.mapB);
@@ -110,16 +120,17 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), p.n_issuers);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), PAIR ? 8 : 4);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -127,24 +138,35 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
     // ===================================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int ct = blockIdx.x; ct < p.total_ctiles; ct += gridDim.x) {
-      const TileCoord tc = decode_tile(p, ct);
+    for (int cu = unit0; cu < n_units; cu += grid_units) {
+      const int ct = PAIR ? 2 * cu + (int)rank : cu;                 // (ct == total_ctiles: the dummy partner -- image index out of range,
+      const TileCoord tc = decode_tile(p, ct);                       //  every box zero-filled, every store clipped)
       const int fast_t = tc.tfg * p.S * p.FB * p.stride, slow_t = tc.ts * p.SB * p.stride, wrow = tc.nb * p.N;
       for (int g = 0; g < p.n_groups; ++g) {
         const TapGroup& grp = p.groups[g];
         const int n_sub = grp.n_sub;
-        const uint32_t tx_bytes = (uint32_t)p.S * p.a_box_bytes + (uint32_t)n_sub * p.b_tile_bytes;
+        // bytes that land per stage: this CTA's boxes, or (PAIR, counted on the leader's barrier) both CTAs' activation boxes and weight halves
+        const uint32_t tx_bytes = (PAIR ? 2u : 1u) * (uint32_t)p.S * p.a_box_bytes + (uint32_t)n_sub * p.b_tile_bytes;
         const int fast0 = fast_t + grp.d_fast, slow0 = slow_t + grp.d_slow;
         for (int c = 0; c < p.n_chunks; ++c) {
           mbar_wait(empty_bar(stage), phase ^ 1, 100);
           if (elect_one_sync()) {
-            mbar_expect_tx(full_bar(stage), tx_bytes);
             const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
-            for (int s = 0; s < p.S; ++s)
-              tma_load_5d(sbase + (uint32_t)s * p.a_box_stride, &p.mapA, full_bar(stage), c * p.cbe, fast0 + s * p.FB * p.stride, slow0, tc.ph, tc.n);
             const uint32_t bbase = sbase + (uint32_t)p.S * p.a_box_stride;
-            for (int j = 0; j < n_sub; ++j)
-              tma_load_2d(bbase + (uint32_t)j * p.b_tile_stride, &p.mapB, full_bar(stage), grp.tap[j] * p.cin + c * p.cbe, wrow);
+            if (PAIR) {
+              const uint32_t fb = leader_addr(full_bar(stage));
+              if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
+              for (int s = 0; s < p.S; ++s)
+                tma_load_5d_pair(sbase + (uint32_t)s * p.a_box_stride, &p.mapA, fb, c * p.cbe, fast0 + s * p.FB * p.stride, slow0, tc.ph, tc.n);
+              for (int j = 0; j < n_sub; ++j)           // this CTA's half of the weight rows
+                tma_load_2d_pair(bbase + (uint32_t)j * p.b_tile_stride, &p.mapB, fb, grp.tap[j] * p.cin + c * p.cbe, wrow + (int)rank * (p.N >> 1));
+            } else {
+              mbar_expect_tx(full_bar(stage), tx_bytes);
+              for (int s = 0; s < p.S; ++s)
+                tma_load_5d(sbase + (uint32_t)s * p.a_box_stride, &p.mapA, full_bar(stage), c * p.cbe, fast0 + s * p.FB * p.stride, slow0, tc.ph, tc.n);
+              for (int j = 0; j < n_sub; ++j)
+                tma_load_2d(bbase + (uint32_t)j * p.b_tile_stride, &p.mapB, full_bar(stage), grp.tap[j] * p.cin + c * p.cbe, wrow);
+            }
           }
           __syncwarp();
           if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
@@ -158,7 +180,7 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
     // barrier poll, two address adds, its MMAs and one commit -- no per-stage elect / reconvergence, no integer division).
     // An N = 48 MMA lasts 24 cycles and a stage holds only 5-15 of them, so every instruction of this loop is on the kernel's
     // critical path (ncu r02: 124 instructions / 965 cycles per 5-MMA stage before this form).
-    if (issuer < p.n_issuers && elect_one_sync()) {
+    if (issuer < p.n_issuers && rank == 0 && elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -171,7 +193,7 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
       const uint32_t b_lo0 = ((stages_base + (uint32_t)p.S * p.a_box_stride) >> 4) | lbo_bits;
       const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
       const int n_groups = p.n_groups, n_chunks = p.n_chunks, n_stages = p.n_stages;
-      for (int ct = blockIdx.x; ct < p.total_ctiles; ct += gridDim.x) {
+      for (int cu = unit0; cu < n_units; cu += grid_units) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1, 200);
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)acc * 256;
@@ -188,14 +210,17 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
               const uint4 e = p.prog[m];
               const uint64_t ad = ((uint64_t)desc_hi << 32) | (a_lo + e.x);
               const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + e.y);
-              umma<KIND>(d_base + e.z, ad, bd, idesc, (e.w & first_mask) == 0u);
+              if (PAIR) umma_f16_pair(d_base + e.z, ad, bd, idesc, (e.w & first_mask) == 0u);
+              else umma<KIND>(d_base + e.z, ad, bd, idesc, (e.w & first_mask) == 0u);
             }
-            umma_commit(empty_bar(stage));                 // frees the smem stage when these MMAs retire
+            if (PAIR) umma_commit_pair(empty_bar(stage));
+            else umma_commit(empty_bar(stage));            // frees the smem stage when these MMAs retire
             first_mask = 0u;
             if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
         }
-        umma_commit(tfull_bar(acc));                       // (tracks every MMA this thread issued before it)
+        if (PAIR) umma_commit_pair(tfull_bar(acc));
+        else umma_commit(tfull_bar(acc));                  // (tracks every MMA this thread issued before it)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -227,7 +252,8 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
     }
     // pixel of this thread's accumulator row inside the tile (rows are [slow][fast])
     const int row_f = row % p.FB, row_s = row / p.FB;
-    for (int ct = blockIdx.x + eg * gridDim.x; ct < p.total_ctiles && eg < neg; ct += neg * gridDim.x) {
+    for (int cu = unit0 + eg * grid_units; cu < n_units && eg < neg; cu += neg * grid_units) {
+      const int ct = PAIR ? 2 * cu + (int)rank : cu;
       const TileCoord tc = decode_tile(p, ct);
       mbar_wait(tfull_bar(acc), acc_phase, 300);
       tc_fence_after();
@@ -389,7 +415,10 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_leader(tempty_bar(acc));
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (neg == 2) acc_phase ^= 1;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -397,7 +426,8 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();                // (the peer's MMAs read this CTA's shared memory and write its TMEM until the very end)
+  else __syncthreads();
   if (p.stats) {
     // one row of BatchNorm partial sums per CTA: the eight epilogue warps' running sums, added up in a fixed order
     const int N = p.N;
@@ -412,12 +442,16 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
   }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
-__global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __grid_constant__ TcParams p) { tapgemm_body<0>(p); }
-__global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_f16_kernel(const __grid_constant__ TcParams p) { tapgemm_body<1>(p); }
+__global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_tf32_kernel(const __grid_constant__ TcParams p) { tapgemm_body<0, 0>(p); }
+__global__ void __launch_bounds__(kThreadsTc, 1) tapgemm_f16_kernel(const __grid_constant__ TcParams p) { tapgemm_body<1, 0>(p); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsTc, 1) tapgemm_f16_pair_kernel(const __grid_constant__ TcParams p) {
+  tapgemm_body<1, 1>(p);
+}
 
 // ---- plan cache (SURVEY 8b `sos_plan_*`): the planner sweep, the MMA program and the tensor-map geometry depend only on the
 // call's shapes / taps / types, never on its pointers.  They are computed once per distinct geometry (~200 per training step,
@@ -454,6 +488,13 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
       if (n <= 256 && n * nb - Ntot < best_waste) { best_waste = n * nb - Ntot; N = n; n_nblk = nb; }
     }
   }
+  // CTA pairs (cta_group::2, M = 256 per MMA): for the wide layers, whose N = Cout-wide B operand dominates the shared-memory traffic
+  static const int pair_env = getenv("SOS_PAIR") ? atoi(getenv("SOS_PAIR")) : 1;     // (A/B switch: SOS_PAIR=0 turns the pair kernel off)
+  // (only where a tile carries enough MMA work: layers with few taps / channels are bound by their epilogue and stores, and pairing
+  //  costs them 5-15 % -- measured: 7x1 96->96, 1x7 2->96, the transposed convolutions)
+  const double tile_mma = (double)a.ntaps * (CinK / kpe) * (N / 2.0) * (2 * N <= 256 ? 2 : 1);
+  const int pair = (pair_env == 1 && esz == 2 && n_nblk == 1 && N % 16 == 0 && N >= 48 && tile_mma >= 6000.0 && a.force_plan < 0) ? 1 : 0;
+  const int Nb = pair ? N / 2 : N;                           // weight rows a CTA stages per tap
   const int ec = (N % 32 == 0) ? 32 : 16;
   const int stg_bytes = 128 * ec * ysz;                     // one output staging buffer (a multiple of 1024: swizzle-aligned)
   const int stats_smem = a.stats_partial ? kEpiWarps * 2 * N * 4 : 0;
@@ -471,13 +512,13 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
     const int a_box = (pl.SB + pl.halo) * pl.FB * cb;
     int max_sub = 1;
     for (auto& g : pl.groups) max_sub = std::max(max_sub, (int)g.n_sub);
-    const int stage = S * round_up(a_box, 1024) + max_sub * round_up(N * cb, 1024);
+    const int stage = S * round_up(a_box, 1024) + max_sub * round_up(Nb * cb, 1024);
     const int n_stages = std::min(8, avail / stage);
     if (n_stages < 2) return;
     const int out_fast = pl.fast_is_w ? (int)a.OW : (int)a.OH, out_slow = pl.fast_is_w ? (int)a.OH : (int)a.OW;
     const int tiles_fast = ceil_div(out_fast, pl.FB);
     const double mma = (double)a.ntaps * (CinK / kpe) * S * (128.0 * N / 256.0);
-    const double bytes = ((double)pl.groups.size() * S * (pl.SB + pl.halo) * pl.FB + (double)a.ntaps * N) * Cin * (double)esz;
+    const double bytes = ((double)pl.groups.size() * S * (pl.SB + pl.halo) * pl.FB + (double)a.ntaps * Nb) * Cin * (double)esz;
     const int lat_slow = out_slow / pl.g;
     const double util = ((double)lat_slow / (ceil_div(lat_slow, pl.SB) * pl.SB)) * ((double)out_fast / (ceil_div(tiles_fast, S) * S * pl.FB));
     double cost = std::max(mma, bytes / 40.0) / (util * S);
@@ -544,11 +585,12 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
   p.y_half = ysz == 2;
   p.layout_type = cb == 128 ? 2 : (cb == 64 ? 4 : 6);
   p.sbo = 8 * cb;
-  p.idesc = esz == 2 ? make_idesc_f16(128, N, 0, 0) : make_idesc_tf32(128, N, 0, 0);
+  p.pair = pair;
+  p.idesc = esz == 2 ? make_idesc_f16(p.pair ? 256 : 128, N, 0, 0) : make_idesc_tf32(128, N, 0, 0);
   const int box_slow = pl.SB + pl.halo;
   p.a_box_bytes = best.a_box_bytes;
   p.a_box_stride = round_up(p.a_box_bytes, 1024);
-  p.b_tile_stride = round_up(N * cb, 1024);
+  p.b_tile_stride = round_up(Nb * cb, 1024);
   p.stage_bytes = best.stage_bytes;
   p.n_stages = best.n_stages;
   {
@@ -611,7 +653,7 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
     out.specA = make_spec(dtA, 5, dims, str, box, es, sw, "activations");
     uint64_t bd[2] = {(uint64_t)a.ntaps * Cin, (uint64_t)Cout};
     uint64_t bs[2] = {(uint64_t)esz, (uint64_t)a.ntaps * Cin * esz};
-    uint32_t bb[2] = {(uint32_t)p.cbe, (uint32_t)N};
+    uint32_t bb[2] = {(uint32_t)p.cbe, (uint32_t)(p.pair ? N / 2 : N)};      // (a CTA of a pair stages half the weight rows)
     uint32_t be[2] = {1, 1};
     out.specB = make_spec(dtA, 2, bd, bs, bb, be, sw, "weights");
   }
@@ -644,6 +686,7 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
 
   out.smem = 1024 + p.n_stages * p.stage_bytes + p.staging_bytes + 512 + stats_smem;
   out.grid = (int)std::min<long long>(total, sos_num_sms());
+  if (p.pair) out.grid = -1;                      // (sized at the first launch: whole clusters that are co-resident)
   out.plan_out[0] = pl.fast_is_w;
   out.plan_out[1] = pl.share;
   out.plan_out[2] = pl.g;
@@ -730,7 +773,32 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
     }
     attr_set = true;
   }
-  if (plan->esz == 2) tapgemm_f16_kernel<<<plan->grid, kThreadsTc, plan->smem, stream>>>(p);
+  if (p.pair) {
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      if (cudaFuncSetAttribute(tapgemm_f16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit) != cudaSuccess) {
+        sos_set_error("sos_conv2d_tc: cannot raise dynamic shared memory of the pair kernel: %s", cudaGetErrorString(cudaGetLastError()));
+        return SOS_ERR_CUDA;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * sos_num_sms());
+      cfg.blockDim = dim3(kThreadsTc);
+      cfg.dynamicSmemBytes = kSmemLimit;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, tapgemm_f16_pair_kernel, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = sos_num_sms() / 2;
+      }
+      max_clusters = n;
+    }
+    if (plan->grid < 0) plan->grid = 2 * (int)std::min<long long>((p.total_ctiles + 1) / 2, max_clusters);
+    tapgemm_f16_pair_kernel<<<plan->grid, kThreadsTc, plan->smem, stream>>>(p);
+  } else if (plan->esz == 2) tapgemm_f16_kernel<<<plan->grid, kThreadsTc, plan->smem, stream>>>(p);
   else tapgemm_tf32_kernel<<<plan->grid, kThreadsTc, plan->smem, stream>>>(p);
   SOS_CHECK_LAUNCH("sos_conv2d_tc");
   if (a.stats_rows_out) *a.stats_rows_out = plan->grid;
