@@ -353,8 +353,9 @@ def run_gpu(args):
         if recs:
             fl, tms, nl = sum(r["flops"] for r in recs), sum(r["ms"] for r in recs), sum(r["n"] for r in recs)
             ach = fl / (tms * 1e-3) / 1e12
-            tr = ncu.get("tapgemm_f16_kernel", {})
-            roofline = {"bound": "tensor", "kernel": "tapgemm_f16_kernel (all launches of a step: conv forward + data gradient)",
+            tr = ncu.get("tapgemm_f16_pair_kernel", ncu.get("tapgemm_f16_kernel", {}))
+            roofline = {"bound": "tensor", "kernel": "tapgemm_f16_pair_kernel / tapgemm_f16_kernel (all launches of a step: conv forward + data gradient "
+                                                     "of every layer the row-streaming kernel does not serve)",
                         "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
                         "traffic": tr.get("dram_bytes_per_launch"), "traffic_note": tr.get("note"),
                         "launches_per_step": nl / prof_steps, "avg_launch_us": 1e3 * tms / nl, "flops_per_launch": fl / nl,

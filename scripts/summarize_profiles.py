@@ -44,8 +44,17 @@ KEYS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active_realtime.avg.pc
         "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "smsp__inst_executed.sum", "sm__inst_executed_pipe_uniform.sum", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed"]
+        "smsp__inst_executed.sum", "sm__inst_executed_pipe_uniform.sum", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+        # shared-memory pipe: wavefronts read by the tensor core, data-bank reads / writes (TMA fills, staging), bytes TMA loaded
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
+        "l1tex__m_l1tex2xbar_write_bytes_mem_global_op_tma_st.sum"]
 traffic = {}
+try:                                   # keep the entries of kernels that were not captured again this time
+    traffic = json.load(open("profiles/ncu_traffic.json"))
+except (OSError, ValueError):
+    pass
+fresh = set()
 for rep in sorted(f for f in os.listdir("gpurun_out") if f.endswith(".ncu-rep")):
     name = rep[:-len(".ncu-rep")].replace("prof_", "")
     raw = subprocess.run(["ncu", "-i", os.path.join("gpurun_out", rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -68,7 +77,8 @@ for rep in sorted(f for f in os.listdir("gpurun_out") if f.endswith(".ncu-rep"))
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
             if "dram__bytes_read.sum" in d:
                 t = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
-                if kn not in traffic or t > traffic[kn]["dram_bytes_per_launch"]:
+                if kn not in fresh or t > traffic[kn]["dram_bytes_per_launch"]:
+                    fresh.add(kn)
                     traffic[kn] = {"dram_bytes_per_launch": t, "duration_ms": float(d["gpu__time_duration.sum"][0].replace(",", "")),
                                    "note": f"largest captured launch of {kn} ({tag}, ncu --set full, profiles/{tag}_{name}_ncu.txt)"}
     print("wrote", f"profiles/{tag}_{name}_ncu.txt")
