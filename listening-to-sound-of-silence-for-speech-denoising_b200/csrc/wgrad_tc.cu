@@ -69,7 +69,16 @@ struct alignas(64) WgParams {
   int kstep_bytes;                  // operand bytes of one k step: (8 | 16 pixels) x 128-byte rows
   int row_bytes;                    // bytes of one slow row of a staged box (FB pixels x 128)
   int m_half_chunks;                // channel chunks per 64 accumulator rows (stacked mode stages the shifted box there)
-  uint32_t desc_hi;                 // descriptor high word: SBO | version | layout
+  uint32_t desc_hi;                 // descriptor high word of the dy operand: SBO | version | layout
+  uint32_t desc_hi_b;               // ... of the x operand (union mode: its SBO is the union box's row pitch)
+  uint32_t a_inc16, b_inc16;        // descriptor advance per k step (16-byte units)
+  uint32_t a_lbo16;                 // chunk stride of the dy operand (16-byte units)
+  // Union mode (Cin <= 64, 8-pixel tiles, fast-axis tap span < 32 pixels): ONE x box of FB + span pixels per slow row serves every
+  // fast offset -- a tap's operand starts `d_fast` pixels (128-byte rows) into it, an address that is not swizzle-atom aligned, which
+  // the tensor core handles (it XORs the absolute address bits TMA used; see conv_row.cu) -- and, stacked, ONE dy box of FB + delta
+  // pixels serves both the plain and the shifted half of the M rows.  L2 -> shared-memory traffic per tile: 164 -> 96 KB on the
+  // 48-channel 5x5 layers.
+  int uni, fbu_x, fbu_dy, xmin_fast, xmin_slow, dy_box_bytes;
   const float* out_scale;           // optional device scalar multiplied into the sums
   float* dw;
   int16_t job_coblk[kMaxJobs], job_g0[kMaxJobs], job_ng[kMaxJobs], job_s0[kMaxJobs], job_ns[kMaxJobs];
@@ -150,13 +159,21 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
       const int coblk = p.job_coblk[job], g0 = p.job_g0[job], ng = p.job_ng[job];
       const int co_here = min(128, p.Cout - coblk * 128);
       const int n_co_chunks = (co_here + p.cbo - 1) / p.cbo;
-      const uint32_t tx = (uint32_t)n_co_chunks * (p.stacked ? 2 : 1) * p.dy_chunk_bytes + (uint32_t)ng * p.n_ci_chunks * p.x_box_bytes;
+      const uint32_t tx = p.uni ? (uint32_t)n_co_chunks * p.dy_box_bytes + (uint32_t)p.x_box_bytes
+                                : (uint32_t)n_co_chunks * (p.stacked ? 2 : 1) * p.dy_chunk_bytes + (uint32_t)ng * p.n_ci_chunks * p.x_box_bytes;
       for (int tile = t0; tile < t1; ++tile) {
         const WgTile tc = decode_wg_tile(p, tile);
         mbar_wait(empty_bar(stage), phase ^ 1, 500);
         if (elect_one_sync()) {
           mbar_expect_tx(full_bar(stage), tx);
           const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
+          if (p.uni) {
+            for (int cc = 0; cc < n_co_chunks; ++cc)
+              tma_load_5d(sbase + (uint32_t)cc * p.dy_chunk_stride, &p.mapDY, full_bar(stage), coblk * 128 + cc * p.cbo, tc.tf * p.FB, tc.ts * p.SB, tc.ph,
+                          tc.n);
+            tma_load_5d(sbase + p.x_off, &p.mapX, full_bar(stage), 0, tc.tf * p.FB + p.xmin_fast, tc.ts * p.SB + p.xmin_slow, tc.ph, tc.n);
+            goto loaded;
+          }
           for (int cc = 0; cc < n_co_chunks; ++cc)
             tma_load_5d(sbase + (uint32_t)cc * p.dy_chunk_stride, &p.mapDY, full_bar(stage), coblk * 128 + cc * p.cbo, tc.tf * p.FB,
                         tc.ts * p.SB, tc.ph, tc.n);
@@ -171,6 +188,7 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
               tma_load_5d(xb + (uint32_t)c * p.x_box_stride, &p.mapX, full_bar(stage), c * p.cbi, tc.tf * p.FB * p.stride + grp.d_fast,
                           tc.ts * p.SB * p.stride + grp.d_slow, tc.ph, tc.n);
           }
+        loaded:;
         }
         __syncwarp();
         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
@@ -186,12 +204,12 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
     const int q = warp & 3;                       // TMEM lane quadrant (drain)
     int stage = 0;
     uint32_t phase = 0, acc_phase = 0;
-    const uint32_t a_inc = (uint32_t)p.kstep_bytes >> 4, b_inc = a_inc;        // one k step (8 or 16 pixels) of one chunk
-    const uint32_t desc_hi = p.desc_hi;
+    const uint32_t a_inc = p.a_inc16, b_inc = p.b_inc16;                       // one k step (8 or 16 pixels) of one chunk
+    const uint32_t desc_hi = p.desc_hi, desc_hi_b = p.desc_hi_b;
     const int ksteps = p.ksteps, n_stages = p.n_stages;
     const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
     // descriptor words: hi = SBO | version | layout; lo = (address >> 4) | LBO (chunk pitch); one k step = 8 / 16 pixels
-    const uint32_t a_lo_base = (stages_base >> 4) | (((uint32_t)p.dy_chunk_stride >> 4) << 16);
+    const uint32_t a_lo_base = (stages_base >> 4) | (p.a_lbo16 << 16);
     const uint32_t b_lo_base = (stages_base + (uint32_t)p.x_off) >> 4;      // (+ the slot's offset and chunk stride)
     const float oscale = p.out_scale ? *p.out_scale : 1.f;
     for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
@@ -216,7 +234,7 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
             uint32_t b_lo = b_lo0 + p.slots[s0 + i].b_desc;
 #pragma unroll 8
             for (int ks = 0; ks < ksteps; ++ks) {
-              umma<KIND>(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, first | (uint32_t)ks);
+              umma<KIND>(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi_b << 32) | b_lo, idesc, first | (uint32_t)ks);
               a_lo += a_inc;
               b_lo += b_inc;
             }
@@ -323,7 +341,6 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
   p.stride = (int)a.stride;
   // TF32: 128-byte swizzle with 32-byte atoms (4 k rows per atom, SBO 512); half: plain 128-byte swizzle (8 k rows, SBO 1024)
   p.layout_a = p.layout_b = esz == 2 ? 2 : 1;
-  p.desc_hi = ((esz == 2 ? 1024u : 512u) >> 4) | (1u << 14) | ((uint32_t)p.layout_a << 29);
   p.kstep_bytes = kpix * 128;
   p.row_bytes = p.FB * 128;
   p.m_half_chunks = 64 / cchunk;
@@ -386,6 +403,21 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
   std::vector<SlotDesc> sd;
   static const int narrow_only = getenv("SOS_WGRAD_NARROW") && atoi(getenv("SOS_WGRAD_NARROW")) == 1;     // A/B aid
   const bool can_wide = esz == 2 && p.n_ci_chunks == 1 && !narrow_only && a.force_plan < 0;
+  // union boxes: one x box spanning every group's fast offset (and, stacked, one dy box spanning the shift) -- see WgParams::uni
+  int xmin_fast = 0, xmax_fast = 0, xmin_slow = 0, halo_u = 0;
+  for (int i = 0; i < n_groups; ++i) {
+    xmin_fast = i ? std::min(xmin_fast, (int)pl.groups[i].d_fast) : (int)pl.groups[i].d_fast;
+    xmax_fast = i ? std::max(xmax_fast, (int)pl.groups[i].d_fast) : (int)pl.groups[i].d_fast;
+    xmin_slow = i ? std::min(xmin_slow, (int)pl.groups[i].d_slow) : (int)pl.groups[i].d_slow;
+  }
+  for (int i = 0; i < n_groups; ++i)
+    for (int j = 0; j < pl.groups[i].n_sub; ++j) halo_u = std::max(halo_u, pl.groups[i].d_slow - xmin_slow + pl.groups[i].a_off[j]);
+  static const int no_union = getenv("SOS_WGRAD_NO_UNION") && atoi(getenv("SOS_WGRAD_NO_UNION")) == 1;      // A/B aid
+  const int fbu_x = p.FB + (xmax_fast - xmin_fast), fbu_dy = p.FB + (stacked ? delta : 0);
+  const bool uni = can_wide && !no_union && pl.share && a.stride == 1 && p.FB == 8 && n_groups > 1 && fbu_x < n_groups * p.FB && fbu_x <= 256 &&
+                   (!stacked || n_co_chunks_max == 1);
+  p.uni = uni;
+  p.fbu_x = fbu_x; p.fbu_dy = fbu_dy; p.xmin_fast = xmin_fast; p.xmin_slow = xmin_slow;
   bool any_wide = false;
   std::vector<int> spacing(n_leads, 0);
   for (int li = 0; li < n_leads; ++li) {
@@ -413,6 +445,16 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
   const int avail = kSmemLimit - 2048;
   const int dy_chunks_staged = stacked ? 128 / cchunk : n_co_chunks_max;
   auto stage_bytes_for = [&](int sb, int ng, int* x_off_out, int* reach_out) {
+    if (uni) {
+      const int dy_stride = round_up(sb * fbu_dy * 128, 1024);
+      const int x_off = (stacked ? 1 : n_co_chunks_max) * dy_stride;
+      const int used = x_off + round_up((sb + halo_u) * fbu_x * 128, 1024);
+      // (the M = 128 rows of a non-stacked dy operand with fewer than 128 channels read one chunk pitch past the staged chunks)
+      const int reach_a = stacked ? x_off : (128 / p.cbo) * dy_stride;
+      if (x_off_out) *x_off_out = x_off;
+      if (reach_out) *reach_out = std::max(reach_a, used);
+      return used;
+    }
     const int dy_chunk = sb * p.FB * 128;
     const int dy_stride = round_up(dy_chunk, 1024);
     const int x_box = (sb + pl.halo) * p.FB * 128;
@@ -432,8 +474,8 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
     if (2 * used + std::max(0, reach - used) <= avail || SB == 2) break;
     SB /= 2;
   }
-  int gcap = 1;                                              // groups per job (sharing the staged dy tile) while 3 stages fit
-  for (int ng = 2; ng <= std::min(n_leads, 4); ++ng) {
+  int gcap = uni ? n_leads : 1;                              // groups per job (sharing the staged dy tile) while 3 stages fit
+  for (int ng = 2; ng <= std::min(n_leads, 4) && !uni; ++ng) {
     int reach = 0;
     const int used = stage_bytes_for(SB, ng, nullptr, &reach);
     if ((any_wide ? 2 : 3) * used + std::max(0, reach - used) > avail) break;
@@ -468,8 +510,20 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
   const int used = stage_bytes_for(SB, max_ng, &p.x_off, &reach);
   p.SB = SB;
   p.dy_chunk_bytes = SB * p.FB * 128;
-  p.dy_chunk_stride = round_up(p.dy_chunk_bytes, 1024);
-  p.x_box_bytes = (SB + pl.halo) * p.FB * 128;
+  p.dy_chunk_stride = round_up(uni ? SB * fbu_dy * 128 : p.dy_chunk_bytes, 1024);
+  p.dy_box_bytes = SB * fbu_dy * 128;
+  p.x_box_bytes = uni ? (SB + halo_u) * fbu_x * 128 : (SB + pl.halo) * p.FB * 128;
+  // descriptors: SBO = stride between the 8-pixel atoms along K (the next slow row of an 8-pixel-wide tile: the box's row pitch in
+  // union mode), advance per k step = kpix pixels
+  {
+    const uint32_t sbo_plain = esz == 2 ? 1024u : 512u;
+    const uint32_t sbo_a = uni ? (uint32_t)fbu_dy * 128u : sbo_plain, sbo_b = uni ? (uint32_t)fbu_x * 128u : sbo_plain;
+    p.desc_hi = (sbo_a >> 4) | (1u << 14) | ((uint32_t)p.layout_a << 29);
+    p.desc_hi_b = (sbo_b >> 4) | (1u << 14) | ((uint32_t)p.layout_b << 29);
+    p.a_inc16 = (uni ? (uint32_t)(kpix / 8) * fbu_dy * 128u : (uint32_t)p.kstep_bytes) >> 4;
+    p.b_inc16 = (uni ? (uint32_t)(kpix / 8) * fbu_x * 128u : (uint32_t)p.kstep_bytes) >> 4;
+    p.a_lbo16 = ((uni && stacked) ? (uint32_t)delta * 128u : (uint32_t)p.dy_chunk_stride) >> 4;
+  }
   SOS_CHECK_ARG((SB * p.FB) % kpix == 0, "sos_conv2d_wgrad: tile of %d x %d pixels is not a multiple of the k step", SB, p.FB);
   p.ksteps = SB * p.FB / kpix;
   p.shift_mul = p.FB / 8;
@@ -503,8 +557,10 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
         ws.ntaps = (int16_t)d.nt;
         ws.col0 = (int16_t)col;
         ws.n_cols = (int16_t)d.cols;
-        const uint32_t off = (uint32_t)gi * p.n_ci_chunks * p.x_box_stride + (uint32_t)ga.a_off[d.j0] * (uint32_t)p.row_bytes;
-        const uint32_t lbo = d.nt > 1 ? (uint32_t)spacing[d.li] * (uint32_t)p.row_bytes : (uint32_t)p.x_box_stride;
+        const uint32_t urow = (uint32_t)fbu_x * 128u;        // union mode: bytes per slow row of the x box
+        const uint32_t off = uni ? (uint32_t)(ga.d_slow - xmin_slow + ga.a_off[d.j0]) * urow + (uint32_t)(ga.d_fast - xmin_fast) * 128u
+                                 : (uint32_t)gi * p.n_ci_chunks * p.x_box_stride + (uint32_t)ga.a_off[d.j0] * (uint32_t)p.row_bytes;
+        const uint32_t lbo = d.nt > 1 ? (uint32_t)spacing[d.li] * (uni ? urow : (uint32_t)p.row_bytes) : (uint32_t)p.x_box_stride;
         SOS_CHECK_ARG((lbo >> 4) < (1u << 14), "sos_conv2d_wgrad: chunk stride too large for the descriptor");
         ws.b_desc = (off >> 4) | ((lbo >> 4) << 16);
         ws.idesc = esz == 2 ? make_idesc_f16(128, d.cols, 1, 1) : make_idesc_tf32(128, d.cols, 1, 1);
@@ -531,7 +587,7 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
     const uint64_t s_fast = fw ? pix : pix * a.W, s_slow = fw ? pix * a.W : pix;
     uint64_t dims[5] = {(uint64_t)Cin, in_fast, in_slow / g, (uint64_t)g, (uint64_t)a.N};
     uint64_t str[5] = {(uint64_t)esz, s_fast, s_slow * g, s_slow, pix * a.H * a.W};
-    uint32_t box[5] = {(uint32_t)p.cbi, (uint32_t)(p.FB * a.stride), (uint32_t)((SB + pl.halo) * a.stride), 1, 1};
+    uint32_t box[5] = {(uint32_t)p.cbi, (uint32_t)(uni ? fbu_x : p.FB * a.stride), (uint32_t)(uni ? SB + halo_u : (SB + pl.halo) * a.stride), 1, 1};
     uint32_t es[5] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1, 1};
     SOS_CHECK_ARG(box[2] <= 256, "sos_conv2d_wgrad: activation box too large");
     const CUtensorMapSwizzle sw = esz == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
@@ -543,7 +599,7 @@ int plan_conv2d_wgrad(const sos_wgrad_args& a, WgPlan& out) {
     const uint64_t s_fast = fw ? pix : pix * a.OW, s_slow = fw ? pix * a.OW : pix;
     uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)out_fast, (uint64_t)(out_slow / g), (uint64_t)g, (uint64_t)a.N};
     uint64_t str[5] = {(uint64_t)esz, s_fast, s_slow * g, s_slow, pix * a.OH * a.OW};
-    uint32_t box[5] = {(uint32_t)p.cbo, (uint32_t)p.FB, (uint32_t)SB, 1, 1};
+    uint32_t box[5] = {(uint32_t)p.cbo, (uint32_t)(uni ? fbu_dy : p.FB), (uint32_t)SB, 1, 1};
     uint32_t es[5] = {1, 1, 1, 1, 1};
     const CUtensorMapSwizzle sw = esz == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
     out.specDY = make_spec(esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 5, dims, str, box, es, sw, "wgrad output grads");
