@@ -813,11 +813,17 @@ extern "C" int sos_conv_stats_rows(void) { return sos_num_sms(); }
 extern "C" int sos_conv2d_plan(const sos_conv_args* ap, int32_t* info) {
   SOS_CHECK_ARG(ap != nullptr && info != nullptr && ap->tap_dh && ap->tap_dw, "sos_conv2d_plan: null pointer");
   SOS_CHECK_ARG(ap->ntaps > 0 && ap->ntaps <= 49 && ap->Cin >= 8 && ap->Cin % 8 == 0 && ap->Cout > 0, "sos_conv2d_plan: bad shapes");
+  if (ap->N > 0 && ap->H > 0 && ap->W > 0 && sos_rowconv_eligible(*ap)) {      // served by the row-streaming kernel (conv_row.cu)
+    memset(info, 0, 16 * sizeof(int32_t));
+    info[0] = 2;
+    info[10] = (int32_t)ap->Cout;
+    return SOS_OK;
+  }
   TcPlan plan;
   if (int e = plan_conv2d_tc(*ap, plan)) return e;
   const TcParams& p = plan.p;
   const int32_t v[16] = {plan.plan_out[0], plan.plan_out[1], plan.plan_out[2], p.S, p.n_groups, p.n_stages, p.stage_bytes, plan.grid,
-                         p.cbe, p.n_chunks, p.N, p.ec, p.FB, p.SB, p.n_stg, plan.smem};
+                         p.cbe, p.n_chunks, p.N, p.ec, p.FB, p.SB, p.n_stg + 100 * p.pair, plan.smem};
   memcpy(info, v, sizeof(v));
   return SOS_OK;
 }
