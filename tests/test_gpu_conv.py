@@ -34,6 +34,7 @@ CASES = [
     ("zero", 32, 32, (1, 1), (1, 1), 1, 1, 16, 24),
     ("zero", 48, 48, (5, 5), (1, 1), 1, 2, 32, 27),
     ("zero", 96, 96, (5, 5), (2, 2), 1, 1, 32, 43),
+    ("zero", 96, 96, (5, 5), (1, 1), 1, 3, 16, 16),          # three tiles: the CTA-pair kernel's odd last tile gets a dummy partner
     ("zero", 96, 96, (5, 5), (8, 1), 1, 1, 64, 19),
     ("zero", 48, 48, (5, 5), (16, 16), 1, 1, 64, 37),
     ("zero", 2, 96, (1, 7), (1, 1), 1, 2, 16, 29),
