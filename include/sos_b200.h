@@ -161,9 +161,16 @@ int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y,
  *   zeroed by the caller) the values are scaled as above. */
 int sos_bn_act_half(const void* y, int y_dtype, void* z_half, int64_t rows, int64_t channels, const float* scale, const float* shift,
                     int act, const float* slope, cudaStream_t stream);
+/* sos_bn_act_backward_half_pre: the same with pass 1 (the reduction over dz, y) already done by the producer of dz: `partial` is an
+ * INPUT of partial_rows x 4 x channels floats (sos_conv_args::bnr_partial). */
 int sos_bn_act_backward_half(const void* dz, int dz_dtype, const float* dz_inv_scale, const void* y, int y_dtype, void* dy_half,
                              int64_t rows, int64_t channels, const float* scale, const float* shift, const float* mean,
                              const float* invstd, int act, const float* slope, float* partial, float* dgamma, float* dbeta,
+                             float* dslope, float* m1, float* m2, float* scal, int accumulate_param_grads, int64_t real_channels,
+                             cudaStream_t stream);
+int sos_bn_act_backward_half_pre(const void* dz, int dz_dtype, const float* dz_inv_scale, const void* y, int y_dtype, void* dy_half,
+                             int64_t rows, int64_t channels, const float* scale, const float* shift, const float* mean,
+                             const float* invstd, int act, const float* slope, const float* partial, int64_t partial_rows, float* dgamma, float* dbeta,
                              float* dslope, float* m1, float* m2, float* scal, int accumulate_param_grads, int64_t real_channels,
                              cudaStream_t stream);
 int sos_to_half(const float* x, int64_t rows, int64_t cs, void* out_half, int64_t cd, float* scal, cudaStream_t stream);
@@ -287,6 +294,21 @@ typedef struct sos_conv_args {
   /* Optional device scalar multiplied into every output before the affine / activation: undoes the power-of-two scale a
    * half-precision gradient operand carries (sos_bn_act_backward_half, sos_to_half). */
   const float* out_scale;
+  /* Optional fused BatchNorm-backward REDUCTION of the layer below (a data-gradient call inside an encoder chain, whose output is
+   * that layer's dz): given that layer's raw conv output bnr_y (half map with this call's output geometry, Cy channels, y_coff = 0)
+   * and its BatchNorm coefficients (scale = gamma*invstd, shift = beta - mean*scale, mean, invstd; >= Cout entries), the epilogue
+   * also writes per-CTA partial sums [*bnr_rows_out][4][bnr_channels] -- sum g, sum g*xhat, 0, sum g^2 with g = the stored output
+   * value where that layer's ReLU was active -- i.e. what pass 1 of sos_bn_act_backward_half computes from dz and y, ready for
+   * sos_bn_act_backward_half_pre.  *bnr_rows_out = 0 when the kernel serving this call does not support it (then run the plain
+   * sos_bn_act_backward_half). */
+  const void* bnr_y;
+  const float* bnr_scale;
+  const float* bnr_shift;
+  const float* bnr_mean;
+  const float* bnr_invstd;
+  float* bnr_partial;       /* device, sos_conv_stats_rows() * 4 * bnr_channels floats */
+  int64_t bnr_channels;
+  int32_t* bnr_rows_out;    /* host */
 } sos_conv_args;
 #define SOS_DTYPE_TF32 0
 #define SOS_DTYPE_F16 1

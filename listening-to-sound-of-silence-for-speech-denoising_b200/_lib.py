@@ -27,7 +27,9 @@ class ConvArgs(C.Structure):
                 ("act", i64), ("slope", C.c_void_p),
                 ("force_plan", i64), ("plan_out", C.POINTER(C.c_int32)),
                 ("stats_partial", C.c_void_p), ("stats_channels", i64), ("stats_rows_out", C.POINTER(C.c_int32)),
-                ("x_dtype", i64), ("y_dtype", i64), ("out_scale", C.c_void_p)]
+                ("x_dtype", i64), ("y_dtype", i64), ("out_scale", C.c_void_p),
+                ("bnr_y", C.c_void_p), ("bnr_scale", C.c_void_p), ("bnr_shift", C.c_void_p), ("bnr_mean", C.c_void_p), ("bnr_invstd", C.c_void_p),
+                ("bnr_partial", C.c_void_p), ("bnr_channels", i64), ("bnr_rows_out", C.POINTER(C.c_int32))]
 
 
 class WgradArgs(C.Structure):
@@ -74,6 +76,8 @@ _SIGS = {
     "sos_bn_act_half": (C.c_int, [c_f, C.c_int, c_f, i64, i64, c_f, c_f, C.c_int, c_f, S]),
     "sos_bn_act_backward_half": (C.c_int, [c_f, C.c_int, c_f, c_f, C.c_int, c_f, i64, i64, c_f, c_f, c_f, c_f, C.c_int, c_f, c_f, c_f, c_f, c_f,
                                            c_f, c_f, c_f, C.c_int, i64, S]),
+    "sos_bn_act_backward_half_pre": (C.c_int, [c_f, C.c_int, c_f, c_f, C.c_int, c_f, i64, i64, c_f, c_f, c_f, c_f, C.c_int, c_f, c_f, i64, c_f, c_f, c_f,
+                                               c_f, c_f, c_f, C.c_int, i64, S]),
     "sos_nchw_to_nhwc_half": (C.c_int, [c_f, i64, i64, i64, i64, c_f, i64, S]),
     "sos_accumulate_wgrad": (C.c_int, [c_f, i64, i64, i64, i64, i64, c_f, S]),
     "sos_accumulate_wgrad_clear": (C.c_int, [c_f, i64, i64, i64, i64, i64, c_f, S]),

@@ -64,11 +64,18 @@ struct alignas(64) RowParams {
   const float* out_scale;
   float* stats;
   int stats_c, n_out;
+  // fused BatchNorm-backward reduction of the layer below (sos_conv_args::bnr_*): its raw conv output and coefficients
+  const uint8_t* bnr_y;
+  long long bnr_sh, bnr_sw, bnr_sn;      // byte strides of bnr_y along H, W, image
+  const float *bnr_scale, *bnr_shift, *bnr_mean, *bnr_invstd;
+  float* bnr_partial;
+  int bnr_c;
 };
 
 // shared memory besides the A stages: alignment slack, resident weight tiles, two staging buffers, barriers (512 B), statistics
-__host__ __device__ inline int row_fixed_smem(int n_taps, int Cout, int cstore) {
-  return 1024 + n_taps * Cout * 128 + 2 * 128 * cstore * 2 + 512 + kRowEpiWarps * 2 * Cout * 4;
+// ([8 warps][2][Cout] forward sums, or -- with the fused BatchNorm-backward reduction -- [8][3][Cout] + the layer below's coefficient vectors)
+__host__ __device__ inline int row_fixed_smem(int n_taps, int Cout, int cstore, bool bnr = false) {
+  return 1024 + n_taps * Cout * 128 + 2 * 128 * cstore * 2 + 512 + kRowEpiWarps * (bnr ? 3 : 2) * Cout * 4 + (bnr ? 4 * Cout * 4 : 0);
 }
 
 struct RowItem { int n, hb, phi, k0, k1, i0, i1, L; };
@@ -279,14 +286,27 @@ __global__ void __launch_bounds__(kThreadsRow, 1) rowconv_f16_kernel(const __gri
     const float slope = ((p.act & SOS_ACT_MASK) == 2 && p.slope) ? *p.slope : 0.f;
     const float oscale = p.out_scale ? *p.out_scale : 1.f;
     const bool epi_math = p.shift || p.act || p.out_scale;
-    float* my_stats = stats_s + ewarp * 2 * Cout;
-    if (p.stats) {
-      for (int i = lane; i < 2 * Cout; i += 32) my_stats[i] = 0.f;
+    // per-warp running sums: [2][Cout] forward statistics, or [3][Cout] of the fused BatchNorm-backward reduction
+    const bool bnr = p.bnr_partial != nullptr;
+    const int sstride = (bnr ? 3 : 2) * Cout;
+    float* my_stats = stats_s + ewarp * sstride;
+    float* coef_s = stats_s + kRowEpiWarps * sstride;            // [4][Cout]: scale, shift, mean, invstd of the layer below
+    if (p.stats || bnr) {
+      for (int i = lane; i < sstride; i += 32) my_stats[i] = 0.f;
       __syncwarp();
+    }
+    if (bnr) {
+      for (int i = ethread; i < Cout; i += 128) {
+        coef_s[i] = __ldg(p.bnr_scale + i);
+        coef_s[Cout + i] = __ldg(p.bnr_shift + i);
+        coef_s[2 * Cout + i] = __ldg(p.bnr_mean + i);
+        coef_s[3 * Cout + i] = __ldg(p.bnr_invstd + i);
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
     }
     const uint32_t sbuf = staging_base + (uint32_t)eg * stg_bytes;
     const uint32_t srow = sbuf + (uint32_t)row * (uint32_t)(p.cstore * 2);
-    const int n_ec = Cout / 16;
+    constexpr int n_ec = 3;                        // Cout = 48 (sos_rowconv_eligible)
     int c_base = 0;
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
       const RowItem r = decode_row_item(p, it);
@@ -295,11 +315,20 @@ __global__ void __launch_bounds__(kThreadsRow, 1) rowconv_f16_kernel(const __gri
         const int c = c_base + (k - r.k0);
         if ((c & 1) != eg) continue;                                   // (R is even: a slot always belongs to the same group)
         const int slot = c % R;
+        // (fused reduction) this thread's pixel of the layer below's raw output: 6 x 16 bytes, in flight while the MMAs finish
+        uint4 yq[6];
+        if (bnr) {
+          const uint4* yp = reinterpret_cast<const uint4*>(p.bnr_y + (long long)r.n * p.bnr_sn + (long long)(r.hb * 128 + row) * p.bnr_sh +
+                                                          (long long)(r.phi + p.dwl * k) * p.bnr_sw);
+#pragma unroll
+          for (int j = 0; j < 6; ++j) yq[j] = __ldg(yp + j);
+        }
         mbar_wait(tfull_bar(slot), ((uint32_t)(c / R)) & 1u, 300);
         tc_fence_after();
         // the staging buffer is free once the previous store of this group has read it
         if (ethread == 0) bulk_wait_read<0>();
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#pragma unroll
         for (int cc = 0; cc < n_ec; ++cc) {
           uint32_t rg[16];
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * Cout + cc * 16), rg);
@@ -359,6 +388,45 @@ __global__ void __launch_bounds__(kThreadsRow, 1) rowconv_f16_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < 16; ++i) rg[i] = __float_as_uint(v[i]);
           }
+          if (bnr) {
+            // g = the value as stored (half) where the layer below was active; sums of g, g * xhat, g^2 per channel: the same
+            // transpose-reduce as the forward statistics, three quantities
+            float v[16], w[16], u[16];
+            const uint32_t* yw = reinterpret_cast<const uint32_t*>(&yq[2 * cc]);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int ch = cc * 16 + i;
+              const __half2 hy = *reinterpret_cast<const __half2*>(&yw[i >> 1]);
+              const float yv = (i & 1) ? __high2float(hy) : __low2float(hy);
+              const float g0 = __half2float(__float2half_rn(__uint_as_float(rg[i])));
+              const float pre = fmaf(yv, coef_s[ch], coef_s[Cout + ch]);
+              const float g = pre > 0.f ? g0 : 0.f;
+              v[i] = g;
+              w[i] = g * ((yv - coef_s[2 * Cout + ch]) * coef_s[3 * Cout + ch]);
+              u[i] = g * g;
+            }
+#pragma unroll
+            for (int st = 8; st >= 1; st >>= 1) {
+              const bool up = (lane & st) != 0;
+#pragma unroll
+              for (int i = 0; i < st; ++i) {
+                const float sv = up ? v[i] : v[i + st], kv = up ? v[i + st] : v[i];
+                const float sw = up ? w[i] : w[i + st], kw = up ? w[i + st] : w[i];
+                const float su = up ? u[i] : u[i + st], ku = up ? u[i + st] : u[i];
+                v[i] = kv + __shfl_xor_sync(0xffffffffu, sv, st);
+                w[i] = kw + __shfl_xor_sync(0xffffffffu, sw, st);
+                u[i] = ku + __shfl_xor_sync(0xffffffffu, su, st);
+              }
+            }
+            v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+            w[0] += __shfl_xor_sync(0xffffffffu, w[0], 16);
+            u[0] += __shfl_xor_sync(0xffffffffu, u[0], 16);
+            if (lane < 16) {
+              my_stats[cc * 16 + lane] += v[0];
+              my_stats[Cout + cc * 16 + lane] += w[0];
+              my_stats[2 * Cout + cc * 16 + lane] += u[0];
+            }
+          }
           // dense staging row of cstore halves (a 96-byte pitch: two-way bank conflicts between rows r and r + 4)
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
@@ -398,6 +466,20 @@ __global__ void __launch_bounds__(kThreadsRow, 1) rowconv_f16_kernel(const __gri
       float sum = 0.f;
       if (ch < N)
         for (int w = 0; w < kRowEpiWarps; ++w) sum += stats_s[w * 2 * N + half * N + ch];
+      dst[c] = sum;
+    }
+  }
+  if (p.bnr_partial) {
+    // one row [4][bnr_c] per CTA: sum g, sum g * xhat, 0 (PReLU slope term: the chains are ReLU), sum g^2
+    const int N = p.Cout;
+    float* dst = p.bnr_partial + (size_t)blockIdx.x * 4 * p.bnr_c;
+    for (int c = threadIdx.x; c < 4 * p.bnr_c; c += blockDim.x) {
+      const int qd = c / p.bnr_c, ch = c - qd * p.bnr_c;
+      float sum = 0.f;
+      if (ch < N && qd != 2) {
+        const int src = qd == 3 ? 2 : qd;
+        for (int w = 0; w < kRowEpiWarps; ++w) sum += stats_s[w * 3 * N + src * N + ch];
+      }
       dst[c] = sum;
     }
   }
@@ -463,7 +545,7 @@ bool sos_rowconv_eligible(const sos_conv_args& a) {
 
 namespace {
 
-int plan_rowconv(const sos_conv_args& a, RowPlan& out) {
+int plan_rowconv(const sos_conv_args& a, RowPlan& out, bool want_bnr) {
   RowParams& p = out.p;
   memset(&p, 0, sizeof(p));
   const int nt = (int)a.ntaps, Cin = (int)a.Cin, Cout = (int)a.Cout;
@@ -508,7 +590,7 @@ int plan_rowconv(const sos_conv_args& a, RowPlan& out) {
   p.stats_c = (int)a.stats_channels;
   p.n_out = Cout;
 
-  const int fixed = row_fixed_smem(nt, Cout, cstore);
+  const int fixed = row_fixed_smem(nt, Cout, cstore, want_bnr);
   p.n_stages = std::min(4, (kSmemLimit - fixed) / p.stage_bytes);
   SOS_CHECK_ARG(p.n_stages >= 2, "sos_conv2d_tc (row kernel): shared memory");
   out.smem = fixed + p.n_stages * p.stage_bytes;
@@ -568,7 +650,20 @@ int plan_rowconv(const sos_conv_args& a, RowPlan& out) {
 int sos_rowconv_launch(const sos_conv_args& a, cudaStream_t stream) {
   std::vector<int32_t> key;
   key.reserve(24 + 2 * (size_t)a.ntaps);
-  const int64_t fields[] = {a.N, a.H, a.W, a.Cin, a.Cout, a.ntaps, a.Cy, a.y_coff, a.stats_partial ? a.stats_channels : -1};
+  // the fused BatchNorm-backward reduction needs a little more shared memory: honoured where it still leaves two pipeline stages
+  bool want_bnr = a.bnr_partial && a.bnr_y && a.bnr_scale && a.bnr_shift && a.bnr_mean && a.bnr_invstd && a.y_coff == 0 && a.bnr_channels >= a.Cout &&
+                  !a.stats_partial;
+  if (want_bnr) {
+    int max_h = 0, dh = 0;
+    for (int t = 0; t < a.ntaps; ++t) {
+      max_h = std::max(max_h, (int)a.tap_dh[t]);
+      if (a.tap_dh[t] > 0) dh = dh ? std::min(dh, (int)a.tap_dh[t]) : (int)a.tap_dh[t];
+    }
+    const int stage = round_up((128 + 2 * max_h) * 128, 1024);
+    const int cstore = std::min(round_up((int)a.Cout, 8), (int)(a.Cy - a.y_coff));
+    if (row_fixed_smem((int)a.ntaps, (int)a.Cout, cstore, true) + 2 * stage > kSmemLimit) want_bnr = false;
+  }
+  const int64_t fields[] = {a.N, a.H, a.W, a.Cin, a.Cout, a.ntaps, a.Cy, a.y_coff, a.stats_partial ? a.stats_channels : -1, want_bnr ? 1 : 0};
   for (int64_t f : fields) key.push_back((int32_t)f);
   for (int t = 0; t < a.ntaps; ++t) { key.push_back(a.tap_dh[t]); key.push_back(a.tap_dw[t]); }
 
@@ -579,7 +674,7 @@ int sos_rowconv_launch(const sos_conv_args& a, cudaStream_t stream) {
     plan = it->second;
   } else {
     plan = new RowPlan();
-    if (int e = plan_rowconv(a, *plan)) { delete plan; return e; }
+    if (int e = plan_rowconv(a, *plan, want_bnr)) { delete plan; return e; }
     g_row_plans.emplace(std::move(key), plan);
   }
   RowParams& p = plan->p;
@@ -589,6 +684,13 @@ int sos_rowconv_launch(const sos_conv_args& a, cudaStream_t stream) {
   p.act = (int)a.act;
   p.slope = a.slope;
   p.stats = a.stats_partial;
+  p.bnr_partial = want_bnr ? a.bnr_partial : nullptr;
+  p.bnr_y = reinterpret_cast<const uint8_t*>(a.bnr_y);
+  p.bnr_scale = a.bnr_scale; p.bnr_shift = a.bnr_shift; p.bnr_mean = a.bnr_mean; p.bnr_invstd = a.bnr_invstd;
+  p.bnr_c = (int)a.bnr_channels;
+  p.bnr_sw = (long long)a.Cy * 2;
+  p.bnr_sh = p.bnr_sw * a.W;
+  p.bnr_sn = p.bnr_sh * a.H;
   const void* baseD = reinterpret_cast<const uint8_t*>(a.y) + plan->d_offset;
   if (plan->baseA != a.x) { if (int e = encode_spec(&p.mapA, plan->specA, a.x)) return e; plan->baseA = a.x; }
   if (plan->baseB != a.wk) { if (int e = encode_spec(&p.mapB, plan->specB, a.wk)) return e; plan->baseB = a.wk; }
@@ -605,6 +707,7 @@ int sos_rowconv_launch(const sos_conv_args& a, cudaStream_t stream) {
   rowconv_f16_kernel<<<plan->grid, kThreadsRow, plan->smem, stream>>>(p);
   SOS_CHECK_LAUNCH("sos_conv2d_tc (row kernel)");
   if (a.stats_rows_out) *a.stats_rows_out = plan->grid;
+  if (a.bnr_rows_out) *a.bnr_rows_out = want_bnr ? plan->grid : 0;
   if (a.plan_out) {
     const int32_t po[8] = {2, 1, p.dwl, 1, p.KH, p.n_stages, p.stage_bytes, plan->grid};      // [0] = 2: row-streaming kernel
     memcpy(a.plan_out, po, sizeof(po));

@@ -733,6 +733,7 @@ extern "C" int sos_conv2d_tc(const sos_conv_args* ap, cudaStream_t stream) {
                 "sos_conv2d_tc: fused BatchNorm statistics are taken of the RAW outputs (no affine / activation in the same call)");
 
   if (sos_rowconv_eligible(a)) return sos_rowconv_launch(a, stream);
+  if (a.bnr_rows_out) *a.bnr_rows_out = 0;             // (the tap GEMM has no fused BatchNorm-backward reduction: the caller runs pass 1 itself)
 
   std::vector<int32_t> key;
   key.reserve(24 + 2 * (size_t)a.ntaps);

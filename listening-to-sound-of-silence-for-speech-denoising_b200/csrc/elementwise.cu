@@ -1313,9 +1313,11 @@ template <typename TY, typename TDZ>
 static int bn_backward_h(const void* dz, const void* y, void* dy_half, long long rows, int C, const float* scale, const float* shift,
                          const float* mean, const float* invstd, int act, const float* slope, float* partial, float* dgamma, float* dbeta,
                          float* dslope, float* m1, float* m2, float* scal, int accumulate, int c_real, const float* in_inv, int G,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, bool reduce_done = false) {
   const size_t smem = (size_t)4 * C * sizeof(float);
-  if ((act & SOS_ACT_MASK) == 2)
+  if (reduce_done) {
+    // (pass 1 came out of the epilogue of the data-gradient GEMM that produced dz: sos_conv_args::bnr_partial)
+  } else if ((act & SOS_ACT_MASK) == 2)
     bn_bwd_reduce_h_kernel<TY, TDZ, true><<<G, kThreads, smem, stream>>>(reinterpret_cast<const TDZ*>(dz), reinterpret_cast<const TY*>(y), rows, C, scale,
                                                                          shift, mean, invstd, act, slope, partial);
   else
@@ -1542,6 +1544,21 @@ int sos_bn_act_backward_half(const void* dz, int dz_dtype, const float* dz_inv_s
   if (dz_dtype == SOS_DTYPE_F16) SOS_BN_BWD(float, __half);
   SOS_BN_BWD(float, float);
 #undef SOS_BN_BWD
+}
+
+int sos_bn_act_backward_half_pre(const void* dz, int dz_dtype, const float* dz_inv_scale, const void* y, int y_dtype, void* dy_half, int64_t rows,
+                                 int64_t channels, const float* scale, const float* shift, const float* mean, const float* invstd, int act,
+                                 const float* slope, const float* partial, int64_t partial_rows, float* dgamma, float* dbeta, float* dslope, float* m1,
+                                 float* m2, float* scal, int accumulate_param_grads, int64_t real_channels, cudaStream_t stream) {
+  SOS_CHECK_ARG(dz && y && dy_half && scale && shift && mean && invstd && partial && partial_rows > 0 && dgamma && dbeta && m1 && m2 && scal &&
+                    channels % 8 == 0 && channels <= 256,
+                "sos_bn_act_backward_half_pre: bad arguments");
+  SOS_CHECK_ARG(dz_dtype == SOS_DTYPE_F16 && y_dtype == SOS_DTYPE_F16 && (act & SOS_ACT_MASK) == 1,
+                "sos_bn_act_backward_half_pre: half dz / y and ReLU only (the fused reduction of an encoder chain)");
+  SOS_CHECK_ARG(rows * (channels / 8) < (1ll << 32), "sos_bn_act_backward_half_pre: too many elements");
+  const int C = (int)channels, cr = (int)(real_channels > 0 ? real_channels : channels);
+  return bn_backward_h<__half, __half>(dz, y, dy_half, rows, C, scale, shift, mean, invstd, act, slope, const_cast<float*>(partial), dgamma, dbeta,
+                                       dslope, m1, m2, scal, accumulate_param_grads, cr, dz_inv_scale, (int)partial_rows, stream, true);
 }
 
 int sos_to_half(const float* x, int64_t rows, int64_t cs, void* out_half, int64_t cd, float* scal, cudaStream_t stream) {

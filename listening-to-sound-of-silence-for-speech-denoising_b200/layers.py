@@ -190,7 +190,7 @@ def _conv_dgrad(dy, w, g, x_shape, out_scale=None):
     return dx
 
 
-def _conv_dgrad_raw(dy, w, g, x_shape, out_scale=None, y_half=False):
+def _conv_dgrad_raw(dy, w, g, x_shape, out_scale=None, y_half=False, bnr=None):
     """Gradient w.r.t. the (possibly reflect-padded) NHWC input buffer (fp32).  dy: fp32 (TF32) or half with its inverse
     scale `out_scale`.  y_half (stride-1 convolutions only): the result is stored as half -- pass out_scale=None then, so that it
     keeps dy's power-of-two scale (see EncoderChainH)."""
@@ -209,7 +209,7 @@ def _conv_dgrad_raw(dy, w, g, x_shape, out_scale=None, y_half=False):
     if g.stride == 1:
         wk = _pack_fwd(wt, g.taps, cout_p, half)
         return ops.conv_tc(dy, wk, [-o[0] for o in g.off], [-o[1] for o in g.off], Cin, H, W, 1, k_real=w.shape[0], tag="conv_dgrad",
-                           out_scale=out_scale, y_half=y_half)
+                           out_scale=out_scale, y_half=y_half, bnr=bnr)
     # stride 2: four output phases of the input lattice
     dx = torch.empty(N, H, W, _round8(Cin), device=dy.device, dtype=torch.float32)
     assert _round8(Cin) == Cin
@@ -327,6 +327,7 @@ def _wgrad_into(w, x, dy, g, out_scale):
     return _conv_wgrad(x, dy, w, g, out_scale)
 
 
+_FUSE_BNR = os.environ.get("SOS_FUSE_BNR", "1") != "0"          # A/B switch: BatchNorm-backward reduction inside the data-gradient epilogue
 _WGRAD_WS = os.environ.get("SOS_WGRAD_WS", "1") != "0"           # A/B switch: weight gradients through the shared zeroed workspace
 _Y_HALF = os.environ.get("SOS_Y_HALF", "1") != "0"                 # A/B switch: raw conv outputs (BatchNorm inputs) stored as half
 
@@ -400,6 +401,7 @@ class EncoderChainH(torch.autograd.Function):
         grads = [None] * (5 * n)
         dz, dz_inv = dz.contiguous(), None
         dx = None
+        pre = None                                    # pass 1 of this block's BatchNorm backward, when the GEMM above already did it
         for i in reversed(range(n)):
             x, y, stats = acts[3 * i:3 * i + 3]
             w, gamma, beta = prm[3 * i:3 * i + 3]
@@ -407,7 +409,8 @@ class EncoderChainH(torch.autograd.Function):
             direct = (_ASYNC_WGRAD and _DIRECT_GRADS and gamma.grad is not None and beta.grad is not None and gamma.grad.is_contiguous()
                       and beta.grad.is_contiguous())
             dy, dgamma, dbeta, _, scal = ops.bn_train_backward_half(dz, y, stats, ops.ACT_RELU, None, grad_into=(gamma.grad, beta.grad, None) if direct else None,
-                                                                    dz_inv=dz_inv)
+                                                                    dz_inv=dz_inv, pre_partial=pre)
+            pre = None
             inv = scal[1:2]
             xh = ops.hv(x)
             need_w = ctx.needs_input_grad[4 + 5 * i]
@@ -417,7 +420,12 @@ class EncoderChainH(torch.autograd.Function):
                 grads[5 * i + 1], grads[5 * i + 2] = dgamma[:Cn], dbeta[:Cn]
             if i > 0:
                 # data gradient stored as half, still carrying dy's scale (no out_scale): the next block's dz
-                dz = _conv_dgrad_raw(dy, w, g, xh.shape, None, y_half=True)
+                # (and, where the kernel can, the reduction pass of block i - 1's BatchNorm backward over the dz it is writing)
+                y_below, stats_below = acts[3 * (i - 1) + 1], acts[3 * (i - 1) + 2]
+                if _FUSE_BNR and y_below.dtype == torch.float16 and y_below.shape[:3] == xh.shape[:3]:
+                    dz, pre = _conv_dgrad_raw(dy, w, g, xh.shape, None, y_half=True, bnr=(y_below, stats_below))
+                else:
+                    dz = _conv_dgrad_raw(dy, w, g, xh.shape, None, y_half=True)
                 dz_inv = inv
             elif ctx.needs_input_grad[0]:
                 dx = _conv_dgrad(dy, w, g, xh.shape, inv)

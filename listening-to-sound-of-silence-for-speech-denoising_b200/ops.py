@@ -431,12 +431,14 @@ def bn_act_apply(y, stats, act, slope, half):
     return z
 
 
-def bn_train_backward_half(dz, y, stats, act, slope, grad_into=None, dz_inv=None):
+def bn_train_backward_half(dz, y, stats, act, slope, grad_into=None, dz_inv=None, pre_partial=None):
     """BatchNorm + activation backward with the gradient w.r.t. the conv output written as a scaled half operand.
     -> dy (real half tensor), dgamma, dbeta, dslope, scal [s, 1/s, sum dy^2].
     dz, y: fp32 or half storage; dz_inv: device scalar, the inverse of the power-of-two scale a half dz still carries.
     grad_into = (gamma.grad, beta.grad, slope.grad or None): the parameter gradients are ADDED straight into these (their first
-    gamma.grad.numel() channels; the map may carry zero-padded channels) and None is returned in their place."""
+    gamma.grad.numel() channels; the map may carry zero-padded channels) and None is returned in their place.
+    pre_partial (rows, 4, C): pass 1 (the reduction over dz, y) already came out of the epilogue of the GEMM that produced dz
+    (conv_tc(bnr=...)): only the finalize and apply kernels run."""
     Cn = y.shape[-1]
     rows = y.numel() // Cn
     G = lib().sos_bn_partial_blocks(rows, Cn)
@@ -449,6 +451,17 @@ def bn_train_backward_half(dz, y, stats, act, slope, grad_into=None, dz_inv=None
     op = lambda i: C.c_void_p(out[i].data_ptr())
     nbytes = y.numel() * (2.0 * dz.element_size() + 2.0 * y.element_size() + 2.0)
     e0 = _pb()
+    if pre_partial is not None:
+        assert (act & 15) == ACT_RELU and dz.dtype == torch.float16 and y.dtype == torch.float16 and pre_partial.shape[1:] == (4, Cn)
+        acc = grad_into is not None
+        gg, gb = (grad_into[0], grad_into[1]) if acc else (out[0], out[1])
+        nbytes = y.numel() * 6.0
+        check(lib().sos_bn_act_backward_half_pre(_p(dz), _dt(dz), _p(dz_inv), _p(y), _dt(y), _p(dy), rows, Cn, sp(2), sp(3), sp(0), sp(1), act & 15,
+                                                 None, _p(pre_partial), pre_partial.shape[0], _p(gg), _p(gb), None, op(2), op(3), _p(scal),
+                                                 1 if acc else 0, gg.numel() if acc else 0, _stream()), "sos_bn_act_backward_half_pre")
+        _pe("bn_bwd", e0, 0.0, nbytes)
+        _count(2)
+        return (dy, None, None, None, scal) if acc else (dy, out[0], out[1], None, scal)
     if grad_into is not None:
         gg, gb, gs = grad_into
         assert gg.is_contiguous() and gb.is_contiguous() and gg.numel() == gb.numel() <= Cn and (not prelu or gs is not None)
@@ -616,12 +629,15 @@ def pack_taps_half(w, taps, k_padded):
 
 
 def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lattice=(1, 1, 0, 0), epi_scale=None, epi_shift=None,
-            act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag="conv_fwd", want_stats=False, y_half=False, out_scale=None):
+            act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag="conv_fwd", want_stats=False, y_half=False, out_scale=None,
+            bnr=None):
     """Tap-list implicit GEMM on tcgen05 (see include/sos_b200.h: sos_conv2d_tc).
 
     x (N, H, W, Cin) NHWC; wk (Cout, ntaps*Cin); y (N, YH, YW, Cy) is allocated when None (dense, Cy = Cout
     rounded up to 8, zero filled if padded).  x and wk are both fp32 (read as TF32) or both half (kind::f16); y is fp32, or a
-    real half tensor with y_half.  out_scale: device scalar multiplied into the outputs."""
+    real half tensor with y_half.  out_scale: device scalar multiplied into the outputs.
+    bnr = (y_below, stats_below): a data-gradient call whose output is the dz of the layer below asks the epilogue for that layer's
+    BatchNorm-backward reduction as well; returns (y, partial or None) -- None when the kernel serving the call cannot do it."""
     N, H, W, Cin = x.shape
     ntaps = len(tap_dh)
     assert wk.shape == (Cout, ntaps * Cin), (wk.shape, Cout, ntaps, Cin)
@@ -655,6 +671,14 @@ def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lat
         partial = torch.empty(lib().sos_conv_stats_rows(), 2, y.shape[3], device=x.device, dtype=torch.float32)
         rows = (_I32 * 1)()
         a.stats_partial, a.stats_channels, a.stats_rows_out = partial.data_ptr(), y.shape[3], rows
+    bpart = brows = None
+    if bnr is not None:
+        yb, sb = bnr
+        assert yb.dtype == torch.float16 and yb.shape == y.shape and yb.is_contiguous() and y_coff == 0
+        bpart = torch.empty(lib().sos_conv_stats_rows(), 4, y.shape[3], device=x.device, dtype=torch.float32)
+        brows = (_I32 * 1)()
+        a.bnr_y, a.bnr_partial, a.bnr_channels, a.bnr_rows_out = yb.data_ptr(), bpart.data_ptr(), y.shape[3], brows
+        a.bnr_scale, a.bnr_shift, a.bnr_mean, a.bnr_invstd = sb[2].data_ptr(), sb[3].data_ptr(), sb[0].data_ptr(), sb[1].data_ptr()
     assert x.is_contiguous() and wk.is_contiguous() and y.is_contiguous()
     e0 = _pb()
     check(lib().sos_conv2d_tc(C.byref(a), _stream()), "sos_conv2d_tc")
@@ -663,6 +687,8 @@ def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lat
     _count()
     if plan_out is not None:
         plan_out[:] = list(po)
+    if bnr is not None:
+        return y, (bpart[:brows[0]] if brows[0] > 0 else None)
     if want_stats:
         return y, partial[:rows[0]]
     return y

@@ -12,7 +12,7 @@ def _gather(x, dh, dw, OH, OW, stride):
     return g * (vh[:, None] & vw[None, :])[None, :, :, None]
 
 
-def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lattice=(1, 1, 0, 0), epi_scale=None, epi_shift=None,
+def conv_tc(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lattice=(1, 1, 0, 0), epi_scale=None, epi_shift=None, bnr=None,
             act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag=None, want_stats=False, y_half=False, out_scale=None):
     N, H, W, Cin = x.shape
     osh, osw, oph, opw = lattice
@@ -57,7 +57,7 @@ def _f(t):
 
 
 def conv_tc_any(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0, lattice=(1, 1, 0, 0), epi_scale=None, epi_shift=None,
-                act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag=None, want_stats=False, y_half=False, out_scale=None):
+                act=0, slope=None, force_plan=-1, plan_out=None, k_real=None, tag=None, want_stats=False, y_half=False, out_scale=None, bnr=None):
     """sos_conv2d_tc for fp32 or half operands (fp32 accumulate); optional output scale, half output, BatchNorm partial sums."""
     xf, wf = _f(x), _f(wk)
     N = x.shape[0]
@@ -75,6 +75,8 @@ def conv_tc_any(x, wk, tap_dh, tap_dw, Cout, OH, OW, stride=1, y=None, y_coff=0,
     if y is None:
         y = torch.zeros(N, OH * osh, OW * osw, (Cout + 7) // 8 * 8, dtype=torch.float16 if y_half else torch.float32)
     y[:, oph::osh, opw::osw][:, :OH, :OW, y_coff:y_coff + Cout] = acc.to(y.dtype)
+    if bnr is not None:
+        return y, None                                 # (the emulation has no fused reduction: the caller runs pass 1 itself)
     if want_stats:
         flat = torch.nn.functional.pad(acc, (0, y.shape[3] - Cout)).reshape(-1, y.shape[3])
         return y, torch.stack([flat.sum(0), (flat * flat).sum(0)])[None]
@@ -139,7 +141,7 @@ def bn_act_apply(y, stats, act, slope, half):
     return h
 
 
-def bn_train_backward_half(dz, y, stats, act, slope, grad_into=None, dz_inv=None):
+def bn_train_backward_half(dz, y, stats, act, slope, grad_into=None, dz_inv=None, pre_partial=None):
     """dz / y may be stored as half; a half dz still carries the power-of-two scale of the layer above (inverse = dz_inv): the
     kernels work on the stored values, scale the parameter gradients by dz_inv and publish the COMPOSED scale of dy."""
     dz, y = _f(dz), _f(y)

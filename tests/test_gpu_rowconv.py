@@ -79,3 +79,43 @@ def test_rowconv_eval_epilogue(cuda):
     e = _rel(ops.hv(z).float().permute(0, 3, 1, 2).cpu(), ref)
     print(f"\nrowconv eval epilogue: {e:.2e}")
     assert e < 1.1e-3
+
+
+@pytest.mark.parametrize("d", [(1, 1), (4, 4), (8, 1)])
+def test_rowconv_fused_bn_backward_reduction(cuda, d):
+    """A data-gradient call inside an encoder chain also delivers pass 1 of the BatchNorm backward of the layer below (sos_conv_args::
+    bnr_*): per-channel sums of g, g * xhat and g^2 over the dz it writes, g = dz where that layer's ReLU was active.  Checked against
+    the same sums taken from the stored half dz, and end to end: sos_bn_act_backward_half_pre == sos_bn_act_backward_half."""
+    from sos_b200 import layers as L, ops
+    N, C, H, W = 2, 48, 128, 39
+    g = torch.Generator().manual_seed(7 + d[0])
+    dy = ops.to_half((torch.randn(N, H, W, C, generator=g) * 0.5).to(cuda))
+    w = (torch.randn(C, C, 5, 5, generator=g) / (C * 25) ** 0.5).to(cuda)
+    y_below = ops.to_half((torch.randn(N, H, W, C, generator=g) * 1.5 + 0.3).to(cuda))
+    mean, var = torch.randn(C, generator=g).to(cuda) * 0.2, (torch.rand(C, generator=g) + 0.5).to(cuda)
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).to(cuda), (torch.randn(C, generator=g) * 0.3).to(cuda)
+    invstd = torch.rsqrt(var + 1e-5)
+    scale = gamma * invstd
+    shift = beta - mean * scale
+    stats = [mean.contiguous(), invstd.contiguous(), scale.contiguous(), shift.contiguous()]
+    geom = L.ConvGeom("zero", 5, 5, d[0], d[1], 1)
+    dz, part = L._conv_dgrad_raw(dy, w, geom, (N, H, W, C), None, y_half=True, bnr=(y_below, stats))
+    torch.cuda.synchronize()
+    assert part is not None and part.shape[1:] == (4, C), "the row-streaming kernel did not deliver the fused reduction"
+    dzf, yf = dz.float().reshape(-1, C), y_below.float().reshape(-1, C)
+    gm = torch.where(yf * scale + shift > 0, dzf, torch.zeros_like(dzf)).double()
+    xhat = ((yf - mean) * invstd).double()
+    want = torch.stack([gm.sum(0), (gm * xhat).sum(0), torch.zeros(C, device=cuda, dtype=torch.float64), (gm * gm).sum(0)])
+    got = part.double().sum(0)
+    err = float((got - want).abs().max() / want.abs().max())
+    print(f"\nfused bn-backward reduction d={d}: rel err {err:.2e} over {part.shape[0]} partial rows")
+    assert err < 2e-5
+    # end to end: backward of the layer below from the fused partial sums == from its own reduction pass
+    inv = torch.ones(1, device=cuda)
+    a = ops.bn_train_backward_half(dz, y_below, stats, ops.ACT_RELU, None, dz_inv=inv, pre_partial=part)
+    b = ops.bn_train_backward_half(dz, y_below, stats, ops.ACT_RELU, None, dz_inv=inv)
+    torch.cuda.synchronize()
+    assert float((a[0].float() - b[0].float()).abs().max()) <= 2e-3 * float(b[0].float().abs().max())
+    for i in (1, 2):
+        assert float((a[i] - b[i]).abs().max()) <= 1e-4 * float(b[i].abs().max()), i
+    assert float((a[4][:2] - b[4][:2]).abs().max()) == 0.0          # the same power-of-two scale
