@@ -311,17 +311,31 @@ __global__ void __launch_bounds__(kThreadsRow, 1) rowconv_f16_kernel(const __gri
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
       const RowItem r = decode_row_item(p, it);
       if (r.k0 >= r.k1) continue;
+      bool have_next = false;
+      uint4 yn[6];
       for (int k = r.k0; k < r.k1; ++k) {
         const int c = c_base + (k - r.k0);
         if ((c & 1) != eg) continue;                                   // (R is even: a slot always belongs to the same group)
         const int slot = c % R;
-        // (fused reduction) this thread's pixel of the layer below's raw output: 6 x 16 bytes, in flight while the MMAs finish
+        // (fused reduction) this thread's pixel of the layer below's raw output, 6 x 16 bytes: loaded one column of this group ahead
+        // (k + 2), so that the ~1.5 us of an HBM read hide behind the column in between
         uint4 yq[6];
         if (bnr) {
-          const uint4* yp = reinterpret_cast<const uint4*>(p.bnr_y + (long long)r.n * p.bnr_sn + (long long)(r.hb * 128 + row) * p.bnr_sh +
-                                                          (long long)(r.phi + p.dwl * k) * p.bnr_sw);
+          const uint8_t* ybase = p.bnr_y + (long long)r.n * p.bnr_sn + (long long)(r.hb * 128 + row) * p.bnr_sh;
+          if (have_next) {
 #pragma unroll
-          for (int j = 0; j < 6; ++j) yq[j] = __ldg(yp + j);
+            for (int j = 0; j < 6; ++j) yq[j] = yn[j];
+          } else {
+            const uint4* yp = reinterpret_cast<const uint4*>(ybase + (long long)(r.phi + p.dwl * k) * p.bnr_sw);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) yq[j] = __ldg(yp + j);
+          }
+          have_next = k + 2 < r.k1;
+          if (have_next) {
+            const uint4* yp = reinterpret_cast<const uint4*>(ybase + (long long)(r.phi + p.dwl * (k + 2)) * p.bnr_sw);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) yn[j] = __ldg(yp + j);
+          }
         }
         mbar_wait(tfull_bar(slot), ((uint32_t)(c / R)) & 1u, 300);
         tc_fence_after();

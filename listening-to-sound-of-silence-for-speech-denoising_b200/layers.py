@@ -327,7 +327,11 @@ def _wgrad_into(w, x, dy, g, out_scale):
     return _conv_wgrad(x, dy, w, g, out_scale)
 
 
-_FUSE_BNR = os.environ.get("SOS_FUSE_BNR", "1") != "0"          # A/B switch: BatchNorm-backward reduction inside the data-gradient epilogue
+# BatchNorm-backward reduction inside the data-gradient epilogue of the row-streaming kernel (sos_conv_args::bnr_*).  OFF by default:
+# measured (scripts/bench_bnr.py, 48 -> 48 5x5 at batch 32) the data gradient goes from 0.168 to 0.262 ms -- the three-quantity warp
+# transpose-reduce makes its epilogue the bottleneck -- while the BatchNorm backward drops from 0.190 to 0.102 ms: a wash per layer and
+# in the step (79.3-79.9 ms either way).  SOS_FUSE_BNR=1 turns it on.
+_FUSE_BNR = os.environ.get("SOS_FUSE_BNR", "0") == "1"
 _WGRAD_WS = os.environ.get("SOS_WGRAD_WS", "1") != "0"           # A/B switch: weight gradients through the shared zeroed workspace
 _Y_HALF = os.environ.get("SOS_Y_HALF", "1") != "0"                 # A/B switch: raw conv outputs (BatchNorm inputs) stored as half
 
