@@ -149,8 +149,8 @@ int sos_bn_act_backward(const float* dz, const int32_t* dz_view, const float* y,
  * sos_bn_act_half: as sos_bn_act with a dense half output z (rows, channels), channels % 8 == 0.
  * sos_bn_act_backward_half: as sos_bn_act_backward (dense dz) with dy written as half(dy * s), s the power of two that brings
  *   the tensor's RMS to ~1 (fp16 keeps 11 significant bits from 6e-5 to 65504 only; gradient maps live near 1e-8).
- *   scal (3 floats, scal[2] zeroed by the caller): out scal[0] = s, scal[1] = 1/s (the out_scale of the consuming GEMMs),
- *   scal[2] = sum of dy^2.  partial: sos_bn_partial_blocks(rows, C) * 4 * C floats.  accumulate_param_grads: dgamma / dbeta
+ *   scal (3 floats; sos_bn_act_backward_half zeroes scal[2] itself, the _pre variant expects it zeroed by the caller): out scal[0] = s,
+ *   scal[1] = 1/s (the out_scale of the consuming GEMMs), scal[2] = sum of dy^2.  partial: sos_bn_partial_blocks(rows, C) * 4 * C floats.  accumulate_param_grads: dgamma / dbeta
  *   (first real_channels entries; 0 = all) are ADDED to (they are the parameters' .grad) instead of written.
  *   y_dtype / dz_dtype (SOS_DTYPE_TF32 = fp32 storage, SOS_DTYPE_F16 = half storage): the raw conv output y may be the half
  *   array sos_conv2d_tc writes with y_dtype = F16 (its batch statistics still come from the fp32 accumulators), and dz may be the
@@ -238,6 +238,15 @@ int sos_pack_taps(const float* w, int64_t rows, int64_t K, int64_t KP, int64_t r
 /* Same gather with a half output (operand of the kind::f16 GEMMs). */
 int sos_pack_taps_half(const float* w, int64_t rows, int64_t K, int64_t KP, int64_t row_stride, int64_t k_stride, int64_t ntaps,
                        const int32_t* tap_off, void* out_half, cudaStream_t stream);
+/* The same gather for MANY weights in one launch (a training step re-packs every convolution weight in its forward and data-gradient
+ * layouts once per optimiser step: 133 packs): `descs` is a DEVICE array of n descriptors with the arguments of sos_pack_taps_half. */
+typedef struct sos_pack_desc {
+  const void* w;           /* device, fp32 */
+  void* out_half;          /* device, rows x ntaps*KP halves */
+  int64_t rows, K, KP, row_stride, k_stride, ntaps;
+  int32_t tap_off[50];     /* ntaps <= 49 entries used */
+} sos_pack_desc;
+int sos_pack_taps_half_multi(const sos_pack_desc* descs_device, int64_t n, cudaStream_t stream);
 /* wgrad buffer [tap][CoutP][CinP] -> PyTorch (Cout, Cin, kh, kw) (transposed=0) or ConvTranspose (Cin, Cout, kh, kw)
  * (transposed=1, in which case src is [tap][CinP'][CoutP'] with the roles swapped by the caller). */
 int sos_unpack_wgrad(const float* src, int64_t Cout, int64_t Cin, int64_t ntaps, int64_t CinP, float* dst, int accumulate,

@@ -32,6 +32,11 @@ class ConvArgs(C.Structure):
                 ("bnr_partial", C.c_void_p), ("bnr_channels", i64), ("bnr_rows_out", C.POINTER(C.c_int32))]
 
 
+class PackDesc(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("out_half", C.c_void_p), ("rows", i64), ("K", i64), ("KP", i64), ("row_stride", i64), ("k_stride", i64),
+                ("ntaps", i64), ("tap_off", C.c_int32 * 50)]
+
+
 class WgradArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("dy", C.c_void_p), ("dw", C.c_void_p),
                 ("tap_dh", C.POINTER(C.c_int32)), ("tap_dw", C.POINTER(C.c_int32)),
@@ -101,6 +106,7 @@ _SIGS = {
     "sos_pack_conv_weight": (C.c_int, [c_f, i64, i64, i64, i64, i64, i64, C.c_int, c_f, S]),
     "sos_pack_taps": (C.c_int, [c_f, i64, i64, i64, i64, i64, i64, C.POINTER(C.c_int32), C.c_int, c_f, S]),
     "sos_pack_taps_half": (C.c_int, [c_f, i64, i64, i64, i64, i64, i64, C.POINTER(C.c_int32), c_f, S]),
+    "sos_pack_taps_half_multi": (C.c_int, [c_f, i64, S]),
     "sos_unpack_wgrad": (C.c_int, [c_f, i64, i64, i64, i64, c_f, C.c_int, S]),
     "sos_conv2d_tc": (C.c_int, [C.POINTER(ConvArgs), S]),
     "sos_conv2d_plan": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(C.c_int32)]),

@@ -288,6 +288,7 @@ class BaseAgent(object):
 
     def train_func(self, data):
         self.net.train()
+        L.pack_all()                                             # every weight operand the optimiser step invalidated, one launch
         outputs, losses = self.forward(data)
         self.update_network(losses)
         self.record_losses(losses, PHASE_TRAINING)
@@ -407,6 +408,7 @@ class GraphedTrainStep(object):
 
     def _part1(self):
         d, B = self.inp, self.batch
+        L.pack_all()                                             # (the first node of the step's graph: both models' weight operands)
         gated = tools.gate_noise(d["mixed"], self.ratio, d["bits"])
         spec = transform.stft_batch(torch.cat([d["mixed"], gated, d["clean"], d["full_noise"]]))
         self.spec = spec

@@ -678,8 +678,10 @@ template <typename TY, typename TDZ, bool PRELU>
 __global__ void __launch_bounds__(kThreads, 2) bn_bwd_reduce_h_kernel(const TDZ* __restrict__ dz, const TY* __restrict__ y, long long P, int C,
                                                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                                                       const float* __restrict__ mean, const float* __restrict__ invstd, int act,
-                                                                      const float* __restrict__ slope_ptr, float* __restrict__ partial /*[grid][4][C]*/) {
+                                                                      const float* __restrict__ slope_ptr, float* __restrict__ partial /*[grid][4][C]*/,
+                                                                      float* __restrict__ zero_me) {
   extern __shared__ float sm[];                 // [4][C] block totals
+  if (zero_me && blockIdx.x == 0 && threadIdx.x == 0) *zero_me = 0.f;      // (the finalize kernel accumulates sum dy^2 there: no fill launch)
   for (int i = threadIdx.x; i < 4 * C; i += kThreads) sm[i] = 0.f;
   __syncthreads();
   const int cg8 = C >> 3;
@@ -1275,6 +1277,22 @@ __global__ void pack_taps_half_kernel(const float* __restrict__ w, int R, int K,
   }
 }
 
+// All weight packs of a training step in ONE launch: block (i, j) does chunk j of descriptor i (include/sos_b200.h: sos_pack_desc).
+__global__ void pack_taps_half_multi_kernel(const sos_pack_desc* __restrict__ descs) {
+  const sos_pack_desc& d = descs[blockIdx.x];
+  const float* __restrict__ w = reinterpret_cast<const float*>(d.w);
+  __half* __restrict__ out = reinterpret_cast<__half*>(d.out_half);
+  const int KP = (int)d.KP, K = (int)d.K, ntaps = (int)d.ntaps;
+  const long long total = d.rows * ntaps * KP;
+  for (long long e = blockIdx.y * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.y * blockDim.x) {
+    const int k = (int)(e % KP);
+    const long long t2 = e / KP;
+    const int t = (int)(t2 % ntaps);
+    const long long r = t2 / ntaps;
+    out[e] = __float2half_rn(k < K ? fminf(fmaxf(w[r * d.row_stride + k * d.k_stride + d.tap_off[t]], -65504.f), 65504.f) : 0.f);
+  }
+}
+
 // wgrad result [taps][CoutP?]... -> PyTorch layout.  src is [tap][Cout][CinP] (tap-major), dst (Cout,Cin,kh,kw).
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, int Cout, int Cin, int ntaps, int CinP, float* __restrict__ dst,
                                     int accumulate) {
@@ -1319,10 +1337,10 @@ static int bn_backward_h(const void* dz, const void* y, void* dy_half, long long
     // (pass 1 came out of the epilogue of the data-gradient GEMM that produced dz: sos_conv_args::bnr_partial)
   } else if ((act & SOS_ACT_MASK) == 2)
     bn_bwd_reduce_h_kernel<TY, TDZ, true><<<G, kThreads, smem, stream>>>(reinterpret_cast<const TDZ*>(dz), reinterpret_cast<const TY*>(y), rows, C, scale,
-                                                                         shift, mean, invstd, act, slope, partial);
+                                                                         shift, mean, invstd, act, slope, partial, scal + 2);
   else
     bn_bwd_reduce_h_kernel<TY, TDZ, false><<<G, kThreads, smem, stream>>>(reinterpret_cast<const TDZ*>(dz), reinterpret_cast<const TY*>(y), rows, C, scale,
-                                                                          shift, mean, invstd, act, slope, partial);
+                                                                          shift, mean, invstd, act, slope, partial, scal + 2);
   SOS_CHECK_LAUNCH("sos_bn_act_backward_half(reduce)");
   bn_bwd_finalize_h_kernel<<<ceil_div(C, kFinCh), kFinCh * kFinRows, 0, stream>>>(partial, G, C, (double)rows, dgamma, dbeta,
                                                                                 (act & SOS_ACT_MASK) == 2 ? dslope : nullptr, m1, m2, scale, scal + 2,
@@ -1782,6 +1800,13 @@ int sos_pack_taps_half(const float* w, int64_t rows, int64_t K, int64_t KP, int6
   pack_taps_half_kernel<<<grid_for(rows * ntaps * KP), kThreads, 0, stream>>>(w, (int)rows, (int)K, (int)KP, row_stride, k_stride, (int)ntaps, t,
                                                                               reinterpret_cast<__half*>(out_half));
   SOS_CHECK_LAUNCH("sos_pack_taps_half");
+  return SOS_OK;
+}
+
+int sos_pack_taps_half_multi(const sos_pack_desc* descs_device, int64_t n, cudaStream_t stream) {
+  SOS_CHECK_ARG(descs_device && n > 0 && n <= 65535, "sos_pack_taps_half_multi: bad arguments");
+  pack_taps_half_multi_kernel<<<dim3((unsigned)n, 8), kThreads, 0, stream>>>(descs_device);
+  SOS_CHECK_LAUNCH("sos_pack_taps_half_multi");
   return SOS_OK;
 }
 

@@ -122,10 +122,16 @@ class ConvGeom:
 # Packed GEMM operands of the weights are cached per (weight storage, view, tap list): inference packs every weight ONCE, not once
 # per call.  An entry is valid while the weight's version counter and the global weight epoch are unchanged -- the optimiser
 # updates parameters through the flat buffer behind autograd's back, so FlatAdam / load_ckpt bump the epoch (`weights_changed`).
-# The entry holds the weight's storage, so its address cannot be recycled for another tensor while the entry lives.  Nothing is
-# cached (or served from the cache) while a CUDA graph is being captured: a replay must re-pack the updated weights itself.
+# The entry holds the weight's storage, so its address cannot be recycled for another tensor while the entry lives.
+# Training re-packs every weight once per optimiser step (133 packs: forward and data-gradient layouts): `pack_all()` refreshes ALL
+# cached entries IN PLACE with one launch (sos_pack_taps_half_multi over a device table of descriptors); the trainers call it at the
+# start of a step, and it is the first node of a captured step graph.  While a CUDA graph is being captured an entry is served only
+# if that capture contains a `pack_all()`; anything else is packed by its own (captured) launch, so a replay never reads stale weights.
 _WEIGHT_EPOCH = 0
-_PACKS = {}
+_PACKS = {}                       # key -> [ver, wk, storage, weight view, descriptor]
+_PACK_TABLE = [None, 0]           # device copy of the descriptors, number of entries it holds
+_CAPTURE_EPOCH = -1               # weight epoch of the capture whose graph holds a pack_all()
+_BATCH_PACK = os.environ.get("SOS_BATCH_PACK", "1") != "0"        # A/B switch
 
 
 def weights_changed():
@@ -133,20 +139,49 @@ def weights_changed():
     _WEIGHT_EPOCH += 1
 
 
+def _pack_key(w, taps, cin_p):
+    return (w.untyped_storage().data_ptr(), w.storage_offset(), tuple(w.shape), tuple(w.stride()), tuple(taps), cin_p)
+
+
+def pack_all():
+    """Bring every cached half weight operand up to date with ONE launch (no-op when nothing changed since the last call)."""
+    global _CAPTURE_EPOCH
+    if not (_BATCH_PACK and _PACKS):
+        return
+    capturing = torch.cuda.is_current_stream_capturing()
+    ents = list(_PACKS.values())
+    if not capturing and all(e[0] == (e[3]._version, _WEIGHT_EPOCH) for e in ents):
+        return
+    if _PACK_TABLE[0] is None or _PACK_TABLE[1] != len(ents):
+        if capturing:
+            return                                                  # (a table upload cannot be captured: the packs stay individual launches)
+        _PACK_TABLE[0] = ops.pack_table([e[4] for e in ents], ents[0][1].device)
+        _PACK_TABLE[1] = len(ents)
+    ops.pack_taps_half_multi(_PACK_TABLE[0], len(ents))
+    for e in ents:
+        e[0] = (e[3]._version, _WEIGHT_EPOCH)
+    if capturing:
+        _CAPTURE_EPOCH = _WEIGHT_EPOCH
+
+
 def _pack_fwd(w, taps, cin_p, half=False):
     """(Cout, Cin, kh, kw) view -> (Cout, len(taps)*cin_p), k = t*cin_p + ci, TF32-rounded fp32 or half (one gather kernel)."""
     if not half:
         return ops.pack_taps(w.detach(), taps, cin_p, round_tf32=True)
-    if w.is_cuda and torch.cuda.is_current_stream_capturing():
-        return ops.pack_taps_half(w.detach(), taps, cin_p)
-    st = w.untyped_storage()
-    key = (st.data_ptr(), w.storage_offset(), tuple(w.shape), tuple(w.stride()), tuple(taps), cin_p)
-    ver = (w._version, _WEIGHT_EPOCH)
+    key = _pack_key(w, taps, cin_p)
     ent = _PACKS.get(key)
-    if ent is not None and ent[0] == ver:
+    if w.is_cuda and torch.cuda.is_current_stream_capturing():
+        if ent is not None and _CAPTURE_EPOCH == _WEIGHT_EPOCH:
+            return ent[1]                                           # refreshed by the pack_all() node of this step's graph
+        return ops.pack_taps_half(w.detach(), taps, cin_p)
+    ver = (w._version, _WEIGHT_EPOCH)
+    if ent is not None:
+        if ent[0] != ver:                                           # stale: refresh in place (the entry's buffer is in the batch table)
+            ops.pack_taps_half(w.detach(), taps, cin_p, out=ent[1])
+            ent[0] = ver
         return ent[1]
     wk = ops.pack_taps_half(w.detach(), taps, cin_p)
-    _PACKS[key] = (ver, wk, st)
+    _PACKS[key] = [ver, wk, w.untyped_storage(), w.detach(), ops.pack_desc(w.detach(), taps, cin_p, wk)]
     return wk
 
 

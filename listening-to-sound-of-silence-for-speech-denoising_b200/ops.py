@@ -446,7 +446,8 @@ def bn_train_backward_half(dz, y, stats, act, slope, grad_into=None, dz_inv=None
     dy = torch.empty(y.shape, device=y.device, dtype=torch.float16)
     out = torch.empty(4, Cn, device=y.device, dtype=torch.float32)             # dgamma, dbeta, m1, m2
     prelu = (act & 15) == ACT_PRELU
-    scal = torch.zeros(3, device=y.device, dtype=torch.float32)
+    # (sum dy^2 accumulates in scal[2]: zeroed by the reduction kernel itself, by a fill only when that pass is skipped)
+    scal = (torch.zeros if pre_partial is not None else torch.empty)(3, device=y.device, dtype=torch.float32)
     sp = lambda i: C.c_void_p(stats[i].data_ptr())
     op = lambda i: C.c_void_p(out[i].data_ptr())
     nbytes = y.numel() * (2.0 * dz.element_size() + 2.0 * y.element_size() + 2.0)
@@ -615,12 +616,36 @@ def pack_taps(w, taps, k_padded, round_tf32=True):
     return out
 
 
-def pack_taps_half(w, taps, k_padded):
+def pack_desc(w, taps, k_padded, out):
+    """The sos_pack_desc of pack_taps_half(w, taps, k_padded) -> out (for pack_taps_half_multi)."""
+    from ._lib import PackDesc
+    st = w.stride()
+    d = PackDesc()
+    d.w, d.out_half = w.data_ptr(), out.data_ptr()
+    d.rows, d.K, d.KP, d.row_stride, d.k_stride, d.ntaps = w.shape[0], w.shape[1], k_padded, st[0], st[1], len(taps)
+    for i, (a, b) in enumerate(taps):
+        d.tap_off[i] = a * st[2] + b * st[3]
+    return d
+
+
+def pack_table(descs, device):
+    """Device copy of a list of sos_pack_desc (a uint8 tensor)."""
+    raw = b"".join(bytes(d) for d in descs)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+
+def pack_taps_half_multi(table, n):
+    check(lib().sos_pack_taps_half_multi(C.c_void_p(table.data_ptr()), n, _stream()), "sos_pack_taps_half_multi")
+    _count()
+
+
+def pack_taps_half(w, taps, k_padded, out=None):
     """pack_taps with a half output (operand of the kind::f16 GEMMs)."""
     assert w.dim() == 4 and w.is_cuda and w.dtype == torch.float32
     R, K = w.shape[0], w.shape[1]
     st = w.stride()
-    out = torch.empty(R, len(taps) * k_padded, device=w.device, dtype=torch.float16)
+    if out is None:
+        out = torch.empty(R, len(taps) * k_padded, device=w.device, dtype=torch.float16)
     offs = _i32arr([a * st[2] + b * st[3] for a, b in taps])
     check(lib().sos_pack_taps_half(C.c_void_p(w.data_ptr()), R, K, k_padded, st[0], st[1], len(taps), offs, _p(out), _stream()),
           "sos_pack_taps_half")
