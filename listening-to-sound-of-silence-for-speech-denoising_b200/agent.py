@@ -391,8 +391,14 @@ class GraphedTrainStep(object):
     runs; the Joint gradient follows; then the two fused Adam updates (device-resident step clock, FlatAdam.apply).
     The returned tensors are static buffers of the graphs: consume (or copy) them before the next call."""
 
-    def __init__(self, sid_agent, joint_agent, batch, length, sr=16000, fps=30.0, n_bits=None, warmup=3):
+    def __init__(self, sid_agent, joint_agent, batch, length, sr=16000, fps=30.0, n_bits=None, warmup=3, concurrent=None):
         self.sid, self.joint = sid_agent, joint_agent
+        # concurrent (SOS_CONCURRENT=1; default off): ONE graph in which the detector's step and the joint model's step are parallel
+        # branches (they share only the spectrograms), so that one's kernels could fill the SMs the other leaves idle (LSTM recurrences
+        # on 26 of 148 SMs, kernel tails).  Measured at batch 32: 79.6 ms against 79.5 ms for the two graphs in sequence -- the big
+        # kernels are persistent whole-GPU grids, two of them only time-slice -- and the sequential form overlaps the detector's
+        # gradient all-reduce with graph 2, so that one stays the default.
+        self.concurrent = (os.environ.get("SOS_CONCURRENT", "0") == "1") if concurrent is None else bool(concurrent)
         dev = sid_agent.device
         self.ratio = sr / fps
         n_bits = int(round(length / sr * fps)) if n_bits is None else n_bits
@@ -403,19 +409,24 @@ class GraphedTrainStep(object):
         self.g1 = self.g2 = None
         self.out = None
         self.launches_per_step = 0
-        self.stream = torch.cuda.Stream()
+        self.stream, self.stream2 = torch.cuda.Stream(), torch.cuda.Stream()
         self.world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
 
-    def _part1(self):
-        d, B = self.inp, self.batch
+    def _part0(self):
+        d = self.inp
         L.pack_all()                                             # (the first node of the step's graph: both models' weight operands)
         gated = tools.gate_noise(d["mixed"], self.ratio, d["bits"])
-        spec = transform.stft_batch(torch.cat([d["mixed"], gated, d["clean"], d["full_noise"]]))
-        self.spec = spec
+        self.spec = transform.stft_batch(torch.cat([d["mixed"], gated, d["clean"], d["full_noise"]]))
+
+    def _sid_part(self):
         self.sid.net.train()
-        _, l_sid = self.sid.forward({"audio": spec[:B], "label": d["label"]})
+        _, l_sid = self.sid.forward({"audio": self.spec[:self.batch], "label": self.inp["label"]})
         self.sid.backward(l_sid)
         return l_sid["bce"].detach()
+
+    def _part1(self):
+        self._part0()
+        return self._sid_part()
 
     def _part2(self):
         B, spec = self.batch, self.spec
@@ -424,6 +435,17 @@ class GraphedTrainStep(object):
         self.joint.backward(l_jt)
         wave = transform.istft_batch(self.joint.last_rec.detach())
         return l_jt["stage1"].detach(), l_jt["stage2"].detach(), wave
+
+    def _whole(self):
+        """The step with the detector's part as a parallel branch (on self.stream2) of the current stream."""
+        cur = torch.cuda.current_stream()
+        self._part0()
+        self.stream2.wait_stream(cur)                            # fork: the detector's branch starts once the spectrograms exist
+        with torch.cuda.stream(self.stream2):
+            bce = self._sid_part()
+        l1, l2, wave = self._part2()
+        cur.wait_stream(self.stream2)                            # join
+        return self._finish(bce, l1, l2, wave)
 
     def _finish(self, bce, l1, l2, wave):
         return {"losses": torch.stack([bce, l1, l2]), "wave": wave}
@@ -453,31 +475,41 @@ class GraphedTrainStep(object):
             cur = torch.cuda.current_stream()
             self.stream.wait_stream(cur)
             with torch.cuda.stream(self.stream):
-                bce = self._part1()
-                h = torch.distributed.all_reduce(self.sid.optimizer.flat_grad, async_op=True) if self.world > 1 else None
-                l1, l2, wave = self._part2()
-                out = self._finish(bce, l1, l2, wave)
-                self._exchange_and_update(h)
+                if self.concurrent:
+                    out = self._whole()                         # (same streams as the capture: its side streams / workspaces exist by then)
+                    self._exchange_and_update(None)
+                else:
+                    bce = self._part1()
+                    h = torch.distributed.all_reduce(self.sid.optimizer.flat_grad, async_op=True) if self.world > 1 else None
+                    l1, l2, wave = self._part2()
+                    out = self._finish(bce, l1, l2, wave)
+                    self._exchange_and_update(h)
             cur.wait_stream(self.stream)
             return out
         if self.g1 is None:
             torch.cuda.synchronize()
-            self.g1, self.g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             pool = torch.cuda.graph_pool_handle()
             from . import _lib
             n0 = _lib.launch_count
             # (thread_local: NCCL's watchdog thread polls CUDA events while we capture)
-            with torch.cuda.graph(self.g1, pool=pool, capture_error_mode="thread_local"):
-                bce = self._part1()
-            with torch.cuda.graph(self.g2, pool=pool, capture_error_mode="thread_local"):
-                l1, l2, wave = self._part2()
-                self.out = self._finish(bce, l1, l2, wave)
+            if self.concurrent:
+                self.g1, self.g2 = torch.cuda.CUDAGraph(), None
+                with torch.cuda.graph(self.g1, pool=pool, stream=self.stream, capture_error_mode="thread_local"):
+                    self.out = self._whole()
+            else:
+                self.g1, self.g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.g1, pool=pool, stream=self.stream, capture_error_mode="thread_local"):
+                    bce = self._part1()
+                with torch.cuda.graph(self.g2, pool=pool, stream=self.stream, capture_error_mode="thread_local"):
+                    l1, l2, wave = self._part2()
+                    self.out = self._finish(bce, l1, l2, wave)
             self.launches_per_step = _lib.launch_count - n0    # this library's kernels inside the two graphs
             for a in (self.sid, self.joint):                    # autograd replaced .grad views? re-attach (host only)
                 a.optimizer.zero_grad_views()
         self.g1.replay()
         h = torch.distributed.all_reduce(self.sid.optimizer.flat_grad, async_op=True) if self.world > 1 else None
-        self.g2.replay()
+        if self.g2 is not None:
+            self.g2.replay()
         self._exchange_and_update(h)
         return self.out
 

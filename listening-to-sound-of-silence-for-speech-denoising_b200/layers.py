@@ -58,15 +58,16 @@ def half_mode():
 # so the tensor-bound wgrad kernels overlap the HBM-bound BatchNorm passes of the following layers.  The caller joins the
 # streams (`join_wgrad()`) before it reads any gradient.
 _ASYNC_WGRAD = False
-_SIDE = None
+_SIDE = {}                         # main stream -> its weight-gradient side stream (concurrent graph branches get one each)
 _DIRECT_GRADS = os.environ.get("SOS_DIRECT_GRADS", "1") != "0"      # A/B switch: parameter gradients added straight into .grad
 
 
 def _side_stream():
-    global _SIDE
-    if _SIDE is None:
-        _SIDE = torch.cuda.Stream()
-    return _SIDE
+    key = torch.cuda.current_stream().cuda_stream
+    side = _SIDE.get(key)
+    if side is None:
+        side = _SIDE[key] = torch.cuda.Stream()
+    return side
 
 
 class async_wgrad(object):
@@ -81,8 +82,9 @@ class async_wgrad(object):
 
 
 def join_wgrad():
-    if _SIDE is not None:
-        torch.cuda.current_stream().wait_stream(_SIDE)
+    side = _SIDE.get(torch.cuda.current_stream().cuda_stream)
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)
 
 
 def _split(t):

@@ -542,9 +542,9 @@ _WGRAD_WS = {}
 
 def wgrad_workspace(ntaps, rows, cols, device):
     """A persistent zeroed (ntaps, rows, cols) fp32 buffer for conv_wgrad(dw=...) + accumulate_wgrad(clear=True): every user leaves it
-    zeroed, all users run in order on one stream (the weight-gradient side stream), so one buffer per shape serves every layer and a
-    training step needs no fill launches for its weight gradients."""
-    key = (str(device), ntaps, rows, cols)
+    zeroed, all users run in order on one stream (a weight-gradient side stream; the buffer is per stream), so one buffer per shape
+    serves every layer and a training step needs no fill launches for its weight gradients."""
+    key = (str(device), torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else 0, ntaps, rows, cols)
     ws = _WGRAD_WS.get(key)
     if ws is None:
         ws = _WGRAD_WS[key] = torch.zeros(ntaps, rows, cols, device=device, dtype=torch.float32)

@@ -21,8 +21,10 @@ def _agents():
     return sid, joint
 
 
-def test_graphed_step_matches_eager(cuda):
-    """Three identically initialised agent pairs see the same batches: two run eagerly (agent.train_func), one through
+@pytest.mark.parametrize("concurrent", [True, False])
+def test_graphed_step_matches_eager(cuda, concurrent):
+    """(concurrent: one graph with the detector's step as a parallel branch -- the default; else two graphs in sequence.)
+    Three identically initialised agent pairs see the same batches: two run eagerly (agent.train_func), one through
     GraphedTrainStep (2 eager warm-up steps, the capture, then replays).  The weight-gradient kernels merge their pixel slices with
     fp32 atomics, so even the two EAGER pairs drift apart from step to step; the graphed pair may differ from an eager pair by at
     most 3 x what the eager pairs differ from each other (plus a floor), in the three losses and in the recovered waveform."""
@@ -32,7 +34,7 @@ def test_graphed_step_matches_eager(cuda):
     ratio = 16000 / 30.0
     pairs = [_agents(), _agents()]
     sid_g, joint_g = _agents()
-    step = ag.GraphedTrainStep(sid_g, joint_g, B, L, 16000, 30.0, warmup=2)
+    step = ag.GraphedTrainStep(sid_g, joint_g, B, L, 16000, 30.0, warmup=2, concurrent=concurrent)
     worst = [0.0, 0.0, 0.0, 0.0]
     for i in range(STEPS):
         clips = synth.make_batch(B, length=L, start=10 * i)
@@ -63,7 +65,7 @@ def test_graphed_step_matches_eager(cuda):
         # BatchNorm over 2 clips -- so the bound uses the largest drift seen so far and a floor inside that scatter)
         assert d_ge <= 3 * worst[0] + 6e-3, (i, got, ref[0][0], ref[1][0])
         assert w_ge <= 3 * w_ee + 1e-4, (i, w_ge, w_ee)
-    assert step.g1 is not None and step.launches_per_step > 100
+    assert step.g1 is not None and (step.g2 is None) == concurrent and step.launches_per_step > 100
     assert sid_g.optimizer.step_count == STEPS and abs(float(sid_g.optimizer.state[1]) - STEPS) < 1e-6
     assert abs(float(joint_g.optimizer.state[0]) - LR / 4) < 1e-12
     for (k, p), (_, q) in zip(pairs[0][1].net.state_dict().items(), joint_g.net.state_dict().items()):
