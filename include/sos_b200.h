@@ -194,6 +194,10 @@ int sos_copy_view(const float* src, const int32_t* src_view, float* dst, const i
                   int64_t channels, int accumulate, cudaStream_t stream);
 int sos_copy_view_backward(const float* grad_dst, const int32_t* dst_view, float* grad_src, const int32_t* src_view,
                            int64_t batch, int64_t channels, cudaStream_t stream);
+/* Backward of reflect padding + concatenation in one pass (backward of nn.ReflectionPad2d over a torch.cat, M2/networks.py:104,129,198-204):
+ * dst(view) = interior of the padded gradient map + the border positions mirrored onto each pixel; the padded map is not modified. */
+int sos_copy_view_fold(const float* grad_padded, const int32_t* padded_view, float* dst, const int32_t* dst_view,
+                       int64_t batch, int64_t channels, cudaStream_t stream);
 int sos_reflect_fill(float* buf, int64_t batch, int64_t H, int64_t W, int64_t pad, int64_t channels, cudaStream_t stream);
 int sos_reflect_fold(float* grad_buf, int64_t batch, int64_t H, int64_t W, int64_t pad, int64_t channels,
                      cudaStream_t stream);

@@ -1161,8 +1161,9 @@ __global__ void __launch_bounds__(kThreads) reflect_fill_kernel(float* __restric
   }
 }
 
-// Adjoint: fold border gradients back into the interior (in place).  One thread per interior element gathers
-// the (up to 8) border positions that mirror onto it, so no atomics are needed.  One block per interior row (n, h).
+// Adjoint: fold border gradients back into the interior (in place).  An interior element gathers the (up to 8) border positions
+// that mirror onto it, so no atomics are needed; only the elements within `pad` of an edge have any (the others keep their value and
+// are not touched).  One block per interior row (n, h).
 __global__ void __launch_bounds__(kThreads) reflect_fold_kernel(float* __restrict__ g, int H, int W, int pad, int C) {
   const int Hp = H + 2 * pad, Wp = W + 2 * pad, cg = C >> 2;
   const int h = blockIdx.x, n = blockIdx.y;
@@ -1172,10 +1173,13 @@ __global__ void __launch_bounds__(kThreads) reflect_fold_kernel(float* __restric
   if (h >= 1 && h <= pad) hs[nh++] = -h;
   if (h <= H - 2 && h >= H - 1 - pad) hs[nh++] = 2 * (H - 1) - h;
   float* base = g + (long long)n * Hp * Wp * (long long)C;
-  const int total = W * cg;
+  const bool whole_row = nh > 1 || 2 * pad + 2 >= W;
+  const int ncols = whole_row ? W : 2 * pad;                   // else only columns 1..pad and W-1-pad..W-2 have mirror images
+  const int total = ncols * cg;
   for (int e = threadIdx.x; e < total; e += kThreads) {
-    const int w = e / cg;
-    const int c = (e - w * cg) * 4;
+    const int col = e / cg;
+    const int c = (e - col * cg) * 4;
+    const int w = whole_row ? col : (col < pad ? 1 + col : W - 1 - 2 * pad + col);
     int ws[3], nw = 0;
     ws[nw++] = w;
     if (w >= 1 && w <= pad) ws[nw++] = -w;
@@ -1187,6 +1191,37 @@ __global__ void __launch_bounds__(kThreads) reflect_fold_kernel(float* __restric
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
       }
     *reinterpret_cast<float4*>(base + ((long long)(h + pad) * Wp + w + pad) * C + c) = acc;
+  }
+}
+
+// Fold + un-pad + channel slice in one pass: dst(view, H x W) = the interior of the reflect-padded gradient map src(view: H x W at
+// offset (pad, pad) of Hp x Wp) plus the border positions that mirror onto each pixel.  Nothing is modified in place, so the
+// padded map needs no copy.  One block per row (n, h).
+__global__ void __launch_bounds__(kThreads) copy_view_fold_kernel(const float* __restrict__ src, View sv, float* __restrict__ dst, View dv,
+                                                                   int C) {
+  const int cg = C >> 2, H = sv.H, W = sv.W, pad = sv.ph;
+  const int h = blockIdx.x, n = blockIdx.y;
+  int hs[3], nh = 0;
+  hs[nh++] = h;
+  if (h >= 1 && h <= pad) hs[nh++] = -h;
+  if (h <= H - 2 && h >= H - 1 - pad) hs[nh++] = 2 * (H - 1) - h;
+  const float* sbase = src + (long long)n * sv.Hp * sv.Wp * (long long)sv.ld + sv.coff;
+  float* drow = dst + (((long long)n * dv.Hp + h + dv.ph) * dv.Wp + dv.pw) * (long long)dv.ld + dv.coff;
+  const int total = W * cg;
+  for (int e = threadIdx.x; e < total; e += kThreads) {
+    const int w = e / cg;
+    const int c = (e - w * cg) * 4;
+    int ws[3], nw = 0;
+    ws[nw++] = w;
+    if (w >= 1 && w <= pad) ws[nw++] = -w;
+    if (w <= W - 2 && w >= W - 1 - pad) ws[nw++] = 2 * (W - 1) - w;
+    float4 acc = {0, 0, 0, 0};
+    for (int i = 0; i < nh; ++i)
+      for (int j = 0; j < nw; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(sbase + ((long long)(hs[i] + pad) * sv.Wp + ws[j] + pad) * sv.ld + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    *reinterpret_cast<float4*>(drow + (long long)w * dv.ld + c) = acc;
   }
 }
 
@@ -1721,6 +1756,20 @@ int sos_copy_view(const float* src, const int32_t* src_view, float* dst, const i
   SOS_CHECK_ARG(batch <= 65535, "sos_copy_view: batch > 65535");
   copy_view_kernel<<<dim3((unsigned)dv.H, (unsigned)batch), kThreads, 0, stream>>>(src, sv, dst, dv, (int)channels, accumulate);
   SOS_CHECK_LAUNCH("sos_copy_view");
+  return SOS_OK;
+}
+
+int sos_copy_view_fold(const float* grad_padded, const int32_t* padded_view, float* dst, const int32_t* dst_view, int64_t batch,
+                       int64_t channels, cudaStream_t stream) {
+  SOS_CHECK_ARG(grad_padded && dst && padded_view && dst_view && batch > 0 && batch <= 65535 && channels >= 4 && channels % 4 == 0,
+                "sos_copy_view_fold: bad arguments");
+  const View sv = mk_view(padded_view), dv = mk_view(dst_view);
+  SOS_CHECK_ARG(view_ok(sv, (int)channels) && view_ok(dv, (int)channels), "sos_copy_view_fold: inconsistent view");
+  SOS_CHECK_ARG(sv.H == dv.H && sv.W == dv.W && sv.ph == sv.pw && sv.ph >= 0 && sv.Hp == sv.H + 2 * sv.ph && sv.Wp == sv.W + 2 * sv.pw &&
+                    sv.ph < sv.H && sv.ph < sv.W,
+                "sos_copy_view_fold: the source view must be an H x W interior with a symmetric reflect border, the destination H x W");
+  copy_view_fold_kernel<<<dim3((unsigned)dv.H, (unsigned)batch), kThreads, 0, stream>>>(grad_padded, sv, dst, dv, (int)channels);
+  SOS_CHECK_LAUNCH("sos_copy_view_fold");
   return SOS_OK;
 }
 

@@ -650,9 +650,7 @@ class PadCat(torch.autograd.Function):
     def backward(ctx, gbuf):
         pad, H, W, N, Ct = ctx.pad, ctx.H, ctx.W, ctx.N, ctx.Ct
         g = gbuf.contiguous()
-        if pad:
-            g = g.clone()
-            ops.reflect_fold(g, H, W, pad)
+        folded = pad == 0
         grads = []
         for i, (Hs, Ws, Cs, coff) in enumerate(ctx.meta):
             if not ctx.needs_input_grad[3 + i]:
@@ -661,8 +659,15 @@ class PadCat(torch.autograd.Function):
             dv = ops.view8(H, W, H + 2 * pad, W + 2 * pad, pad, pad, Ct, coff)
             if (Hs, Ws) == (H, W):
                 gs = torch.empty(N, Hs, Ws, Cs, device=g.device, dtype=torch.float32)
-                ops.copy_view(g, dv, gs, ops.view8(Hs, Ws, ld=Cs), N, Cs)
+                if folded:
+                    ops.copy_view(g, dv, gs, ops.view8(Hs, Ws, ld=Cs), N, Cs)
+                else:                                              # fold + un-pad + slice in one pass, the padded map stays as it is
+                    ops.copy_view_fold(g, dv, gs, ops.view8(Hs, Ws, ld=Cs), N, Cs)
             else:
+                if not folded:                                     # (a resized source: fold a copy in place first, once)
+                    g = g.clone()
+                    ops.reflect_fold(g, H, W, pad)
+                    folded = True
                 gs = torch.zeros(N, Hs, Ws, Cs, device=g.device, dtype=torch.float32)
                 ops.copy_view_backward(g, dv, gs, ops.view8(Hs, Ws, ld=Cs), N, Cs)
             grads.append(gs)

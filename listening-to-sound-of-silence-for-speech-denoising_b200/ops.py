@@ -569,6 +569,12 @@ def copy_view_backward(gdst, dview, gsrc, sview, batch, channels):
     _count()
 
 
+def copy_view_fold(gpad, pview, dst, dview, batch, channels):
+    """dst window = interior of the reflect-padded gradient map + the border positions mirrored onto it (gpad is not modified)."""
+    check(lib().sos_copy_view_fold(_p(gpad), pview, _p(dst), dview, batch, channels, _stream()), "sos_copy_view_fold")
+    _count()
+
+
 def reflect_fill(buf, H, W, pad):
     B, Hp, Wp, Cn = buf.shape
     assert Hp == H + 2 * pad and Wp == W + 2 * pad

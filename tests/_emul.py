@@ -201,6 +201,15 @@ def reflect_fold(gbuf, H, W, pad):
     gbuf[:, pad:pad + H, pad:pad + W] = inner.grad.permute(0, 2, 3, 1)
 
 
+def copy_view_fold(gpad, pview, dst, dview, batch, channels):
+    """sos_copy_view_fold: dst window = folded interior of the reflect-padded gradient map (which is left unchanged)."""
+    H, W, Hp, Wp, ph, pw, ld, coff = list(pview)
+    g = gpad.reshape(batch, Hp, Wp, ld)[..., coff:coff + channels].clone()
+    reflect_fold(g, H, W, ph)
+    dH, dW, dHp, dWp, dph, dpw, dld, dcoff = list(dview)
+    dst.reshape(batch, dHp, dWp, dld)[:, dph:dph + dH, dpw:dpw + dW, dcoff:dcoff + channels] = g[:, ph:ph + H, pw:pw + W]
+
+
 def copy_view_backward(gdst, dview, gsrc, sview, batch, channels):
     """sos_copy_view_backward: gsrc window += gdst window through the nearest map of copy_view."""
     sH, sW, sHp, sWp, sph, spw, sld, scoff = list(sview)

@@ -133,7 +133,7 @@ def emulated_half(monkeypatch):
                      ("pack_taps_half", _emul.pack_taps_half), ("to_half", _emul.to_half), ("bn_finalize_partial", _emul.bn_finalize_partial),
                      ("bn_act_apply", _emul.bn_act_apply), ("bn_train_backward_half", _emul.bn_train_backward_half),
                      ("copy_view", _emul.copy_view), ("reflect_fill", _emul.reflect_fill), ("reflect_fold", _emul.reflect_fold),
-                     ("copy_view_backward", _emul.copy_view_backward), ("init", lambda: None)):
+                     ("copy_view_backward", _emul.copy_view_backward), ("copy_view_fold", _emul.copy_view_fold), ("init", lambda: None)):
         monkeypatch.setattr(ops, name, fn)
 
 

@@ -252,6 +252,29 @@ def test_padcat_reflect_resize(cuda):
     assert float((ops.nhwc_to_nchw(bd.grad, 64).cpu() - b.grad).abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("pad,H,W", [(1, 16, 21), (2, 9, 7), (3, 16, 21), (2, 3, 5), (1, 2, 2)])
+def test_padcat_reflect_same_size(cuda, pad, H, W):
+    """Same-size sources: backward = sos_copy_view_fold (fold + un-pad + channel slice in one pass over the untouched padded map)."""
+    from sos_b200 import layers as L, ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(2, 8, H, W, generator=g, requires_grad=True)
+    b = torch.randn(2, 16, H, W, generator=g, requires_grad=True)
+    ref = F.pad(torch.cat([a, b], 1), (pad, pad, pad, pad), mode="reflect")
+    go = torch.randn(ref.shape, generator=g)
+    ref.backward(go)
+    ad = ops.nchw_to_nhwc(a.detach().to(cuda), 8).requires_grad_(True)
+    bd = ops.nchw_to_nhwc(b.detach().to(cuda), 16).requires_grad_(True)
+    out = L.PadCat.apply(pad, H, W, ad, bd)
+    gd = ops.nchw_to_nhwc(go.to(cuda), 24)
+    keep = gd.clone()
+    out.backward(gd)
+    assert torch.equal(gd, keep)                                           # the incoming gradient map is not modified
+    assert float((ops.nhwc_to_nchw(out, 24).cpu() - ref.detach()).abs().max()) == 0.0
+    assert float((ops.nhwc_to_nchw(ad.grad, 8).cpu() - a.grad).abs().max()) < 1e-5
+    assert float((ops.nhwc_to_nchw(bd.grad, 16).cpu() - b.grad).abs().max()) < 1e-5
+
+
 @pytest.mark.parametrize("I,H,T,B", [(96, 40, 13, 5), (64, 200, 37, 40), (32, 100, 60, 3), (48, 200, 29, 32), (16, 100, 17, 1), (24, 250, 9, 7)])
 def test_bilstm_matches_torch(cuda, I, H, T, B):
     """nn.LSTM(bidirectional) forward / backward.  Batches of at most 32 clips run the cluster kernels (one thread-block cluster per
