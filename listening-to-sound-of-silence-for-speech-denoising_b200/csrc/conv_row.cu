@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kThreadsRow, 1) rowconv_f16_kernel(const __gri
         mbar_wait(tfull_bar(slot), ((uint32_t)(c / R)) & 1u, 300);
         tc_fence_after();
         // the staging buffer is free once the previous store of this group has read it
-        if (ethread == 0) bulk_wait_read<0>();
+        if (ethread < 32 && elect_one_sync()) bulk_wait_read<0>();
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
 #pragma unroll
         for (int cc = 0; cc < n_ec; ++cc) {
@@ -459,14 +459,14 @@ __global__ void __launch_bounds__(kThreadsRow, 1) rowconv_f16_kernel(const __gri
         if (lane == 0) mbar_arrive(tempty_bar(slot));
         fence_proxy_async_smem();
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        if (ethread == 0) {
+        if (ethread < 32 && elect_one_sync()) {
           tma_store_4d(&p.mapD, sbuf, 0, r.hb * 128, r.phi + p.dwl * k, r.n);
           bulk_commit();
         }
       }
       c_base += r.k1 - r.k0;
     }
-    if (ethread == 0) bulk_wait<0>();
+    if (ethread < 32 && elect_one_sync()) bulk_wait<0>();
   }
 
   tc_fence_before();

@@ -48,6 +48,7 @@ struct alignas(64) TcParams {
   int n_stages, stage_bytes, a_box_bytes, a_box_stride, b_tile_stride, staging_bytes;
   int n_stg;                     // output staging buffers per epilogue group (2..8)
   int n_egroups;                 // epilogue groups in use: 2, or 1 (A/B switch SOS_EPI_GROUPS=1: warps 7-10 idle)
+  int dbg;                       // measurement aid (SOS_EPI_DBG): 1 no TMA stores, 2 no accumulator reads / staging writes
   int layout_type, sbo;
   uint32_t idesc;
   const float* scale;            // optional per-output-channel affine (eval-mode BN / bias) ...
@@ -261,9 +262,11 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
         for (int cc = 0; cc < n_ec; ++cc) {
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + s * p.N + cc * p.ec);
           uint32_t r[32];
-          tmem_ld16(taddr, r);
-          if (p.ec == 32) tmem_ld16(taddr + 16, r + 16);
-          tmem_ld_wait();
+          if (!(p.dbg & 2)) {
+            tmem_ld16(taddr, r);
+            if (p.ec == 32) tmem_ld16(taddr + 16, r + 16);
+            tmem_ld_wait();
+          }
           const int ch0 = tc.nb * p.N + cc * p.ec;
           if (p.stats) {
             // BatchNorm statistics of the raw outputs: transpose-reduce over the warp's 32 rows (31 shuffles per quantity),
@@ -370,7 +373,8 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
           // (row >> 1) & 3; 32B rows: chunk ^= (row >> 2) & 1), which is also bank-conflict free for a quarter-warp of
           // consecutive rows
           const int xr = erow == 128 ? (row & 7) : (erow == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1));
-          if (p.y_half) {
+          if (p.dbg & 2) {
+          } else if (p.y_half) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (j < p.ec / 8) {
@@ -393,7 +397,7 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
           fence_proxy_async_smem();
           // ONE barrier per chunk: before it thread 0 makes sure that at most n_stg - 2 earlier stores still read their
           // buffers, i.e. the buffer of the NEXT chunk is free by the time anybody passes the barrier
-          if (ethread == 0) {
+          if (ethread < 32 && elect_one_sync()) {      // (elected, not `ethread == 0`: keeps the bulk instructions straight-line)
             switch (n_stg) {                              // (the wait count is an immediate)
               case 2: bulk_wait_read<0>(); break;
               case 3: bulk_wait_read<1>(); break;
@@ -406,7 +410,7 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
             }
           }
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          if (ethread == 0) {
+          if (ethread < 32 && !(p.dbg & 1) && elect_one_sync()) {
             tma_store_5d(&p.mapD, sbuf, ch0, (tc.tfg * p.S + s) * p.FB, tc.ts * p.SB, tc.ph, tc.n);
             bulk_commit();
           }
@@ -422,7 +426,7 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
       if (neg == 2) acc_phase ^= 1;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (ethread == 0) bulk_wait<0>();
+    if (ethread < 32 && elect_one_sync()) bulk_wait<0>();
   }
 
   tc_fence_before();
@@ -610,6 +614,8 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
     p.staging_bytes = 2 * n_stg * stg_bytes;
     static const int one_group = getenv("SOS_EPI_GROUPS") && atoi(getenv("SOS_EPI_GROUPS")) == 1;     // A/B aid
     p.n_egroups = one_group ? 1 : 2;
+    static const int epi_dbg = getenv("SOS_EPI_DBG") ? atoi(getenv("SOS_EPI_DBG")) : 0;
+    p.dbg = epi_dbg;
   }
   {
     int n = 0;

@@ -1317,14 +1317,26 @@ __global__ void pack_taps_half_multi_kernel(const sos_pack_desc* __restrict__ de
   const sos_pack_desc& d = descs[blockIdx.x];
   const float* __restrict__ w = reinterpret_cast<const float*>(d.w);
   __half* __restrict__ out = reinterpret_cast<__half*>(d.out_half);
-  const int KP = (int)d.KP, K = (int)d.K, ntaps = (int)d.ntaps;
-  const long long total = d.rows * ntaps * KP;
-  for (long long e = blockIdx.y * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.y * blockDim.x) {
-    const int k = (int)(e % KP);
-    const long long t2 = e / KP;
-    const int t = (int)(t2 % ntaps);
-    const long long r = t2 / ntaps;
-    out[e] = __float2half_rn(k < K ? fminf(fmaxf(w[r * d.row_stride + k * d.k_stride + d.tap_off[t]], -65504.f), 65504.f) : 0.f);
+  const unsigned KP = (unsigned)d.KP, K = (unsigned)d.K, ntaps = (unsigned)d.ntaps;
+  const unsigned total = (unsigned)(d.rows * ntaps * KP);          // (a weight tensor: far below 2^32 elements)
+  const unsigned span = gridDim.y * blockDim.x;
+  // the gathers are latency bound (one scattered 4-byte read per element): four independent ones in flight per thread
+  for (unsigned e0 = blockIdx.y * blockDim.x + threadIdx.x; e0 < total; e0 += 4 * span) {
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned e = e0 + i * span;
+      v[i] = 0.f;
+      if (e < total) {
+        const unsigned k = e % KP, t2 = e / KP, t = t2 % ntaps, r = t2 / ntaps;
+        if (k < K) v[i] = __ldg(w + (long long)r * d.row_stride + (long long)k * d.k_stride + d.tap_off[t]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned e = e0 + i * span;
+      if (e < total) out[e] = __float2half_rn(fminf(fmaxf(v[i], -65504.f), 65504.f));
+    }
   }
 }
 
@@ -1854,7 +1866,7 @@ int sos_pack_taps_half(const float* w, int64_t rows, int64_t K, int64_t KP, int6
 
 int sos_pack_taps_half_multi(const sos_pack_desc* descs_device, int64_t n, cudaStream_t stream) {
   SOS_CHECK_ARG(descs_device && n > 0 && n <= 65535, "sos_pack_taps_half_multi: bad arguments");
-  pack_taps_half_multi_kernel<<<dim3((unsigned)n, 8), kThreads, 0, stream>>>(descs_device);
+  pack_taps_half_multi_kernel<<<dim3((unsigned)n, 32), kThreads, 0, stream>>>(descs_device);
   SOS_CHECK_LAUNCH("sos_pack_taps_half_multi");
   return SOS_OK;
 }
