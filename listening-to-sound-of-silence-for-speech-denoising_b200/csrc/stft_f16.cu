@@ -108,6 +108,7 @@ struct StftParams {
   const uint8_t* bits;
   const int* frame_lo;
   int L, T, n_frames_total, n_tiles, nb, gate_mode;
+  int tf;                          // frames per tile (<= 128, a multiple of 8): chosen so that the tiles fill whole waves of the grid
   int dbg;                         // ablation switches for measurements (SOS_STFT_DBG): 1 no builder arithmetic, 2 no drain stores, 4 no staging
   float inv_ratio;
 };
@@ -115,7 +116,7 @@ struct StftParams {
 // Samples of the tile's frames, per clip the tile touches: clip b0 + s covers samples [lo, hi) at x_tile + off.
 struct Seg { int lo, hi, off; };
 __device__ __forceinline__ void tile_segments(const StftParams& p, int tile, int& b0, int& nseg, Seg* seg) {
-  const int f0 = tile * 128, f1 = min(p.n_frames_total, f0 + 128) - 1;
+  const int f0 = tile * p.tf, f1 = min(p.n_frames_total, f0 + p.tf) - 1;
   b0 = f0 / p.T;
   const int b1 = f1 / p.T;
   nseg = min(b1 - b0 + 1, kMaxSeg);
@@ -241,9 +242,10 @@ __global__ void __launch_bounds__(kThreads, 1) stft_f16_kernel(const __grid_cons
     const int row = q * 32 + lane;
     int ni = 0;
     for (int tile = i0; tile < i1; ++tile, ++ni) {
-      const int f = tile * 128 + row;
-      const bool valid = f < p.n_frames_total && !(p.dbg & 2);
-      const int b = f < p.n_frames_total ? f / p.T : 0, t = f < p.n_frames_total ? f - b * p.T : 0;
+      const int f = tile * p.tf + row;
+      const bool in_tile = row < p.tf && f < p.n_frames_total;
+      const bool valid = in_tile && !(p.dbg & 2);
+      const int b = in_tile ? f / p.T : 0, t = in_tile ? f - b * p.T : 0;
 #pragma unroll 1
       for (int part = 0; part < 2; ++part) {
         mbar_wait(t_full(part), ni & 1, 904);
@@ -322,10 +324,10 @@ __global__ void __launch_bounds__(kThreads, 1) stft_f16_kernel(const __grid_cons
       int rc[16], rz[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int f = tile * 128 + bw + 8 * j;
+        const int f = tile * p.tf + bw + 8 * j;
         rc[j] = -1;
         rz[j] = 0;
-        if (f < p.n_frames_total) {
+        if (bw + 8 * j < p.tf && f < p.n_frames_total) {
           const int b = f / p.T, t = f - b * p.T;
           Seg sg = seg[0];
 #pragma unroll
@@ -420,7 +422,16 @@ int sos_stft_f16_launch(const float* wave, int64_t batch, int64_t length, float*
   p.T = T;
   SOS_CHECK_ARG(batch * (int64_t)p.T < (1ll << 30), "sos_stft_forward: too many frames");
   p.n_frames_total = (int)(batch * p.T);
-  p.n_tiles = ceil_div(p.n_frames_total, 128);
+  {
+    // 128-frame tiles leave a partial last wave (203 tiles on 148 SMs at 128 signals: the grid waits for the 55 CTAs with two
+    // tiles); shorter tiles in whole waves keep every SM equally busy -- an MMA over unused rows costs less than an idle SM
+    const int sms = sos_num_sms();
+    const int waves = ceil_div(ceil_div(p.n_frames_total, 128), sms);
+    static const int fixed = getenv("SOS_STFT_TF") ? atoi(getenv("SOS_STFT_TF")) : 0;          // A/B aid
+    p.tf = fixed > 0 ? fixed : std::min(128, round_up(ceil_div(p.n_frames_total, waves * sms), 8));
+    p.tf = std::max(8, std::min(128, p.tf & ~7));
+  }
+  p.n_tiles = ceil_div(p.n_frames_total, p.tf);
   p.nb = (int)n_bits;
   p.gate_mode = gate_mode;
   p.dbg = getenv("SOS_STFT_DBG") ? atoi(getenv("SOS_STFT_DBG")) : 0;
