@@ -239,9 +239,16 @@ int sos_pack_conv_weight(const float* w, int64_t Cout, int64_t Cin, int64_t kh, 
  *   rounded to TF32.  tap_off: host array, ntaps <= 49 entries. */
 int sos_pack_taps(const float* w, int64_t rows, int64_t K, int64_t KP, int64_t row_stride, int64_t k_stride, int64_t ntaps,
                   const int32_t* tap_off, int round_tf32, float* out, cudaStream_t stream);
-/* Same gather with a half output (operand of the kind::f16 GEMMs). */
+/* Same gather with a half output (operand of the kind::f16 GEMMs).  A NEGATIVE tap_off entry is a zero tap (row padding). */
 int sos_pack_taps_half(const float* w, int64_t rows, int64_t K, int64_t KP, int64_t row_stride, int64_t k_stride, int64_t ntaps,
                        const int32_t* tap_off, void* out_half, cudaStream_t stream);
+/* Taps folded into channels for the two-channel inputs (the real / imaginary spectrogram planes every network starts from,
+ * M1/networks.py:124, M2/networks.py:76,159,166): out[n, oh, ow, 2 t + c] = x[n, oh + dh_t, ow + dw_t, c], c < 2, zero outside the
+ * image and for the padding columns (out_channels >= 2 ntaps, a multiple of 8; ntaps <= 32).  The convolution then is a ONE-tap
+ * GEMM over 128-byte pixel rows instead of `ntaps` GEMMs over 16- / 32-byte rows, with the weight packed by sos_pack_taps_half
+ * (KP = K = 2, zero taps as padding). */
+int sos_im2col_half(const void* x_half, int64_t batch, int64_t H, int64_t W, int64_t channels, int64_t ntaps, const int32_t* tap_dh,
+                    const int32_t* tap_dw, int64_t OH, int64_t OW, void* out_half, int64_t out_channels, cudaStream_t stream);
 /* The same gather for MANY weights in one launch (a training step re-packs every convolution weight in its forward and data-gradient
  * layouts once per optimiser step: 133 packs): `descs` is a DEVICE array of n descriptors with the arguments of sos_pack_taps_half. */
 typedef struct sos_pack_desc {

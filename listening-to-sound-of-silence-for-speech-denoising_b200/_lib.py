@@ -92,6 +92,7 @@ _SIGS = {
     "sos_nhwc_to_nchw": (C.c_int, [c_f, i32p, i64, i64, c_f, S]),
     "sos_copy_view": (C.c_int, [c_f, i32p, c_f, i32p, i64, i64, C.c_int, S]),
     "sos_copy_view_backward": (C.c_int, [c_f, i32p, c_f, i32p, i64, i64, S]),
+    "sos_im2col_half": (C.c_int, [c_f, i64, i64, i64, i64, i64, i32p, i32p, i64, i64, c_f, i64, S]),
     "sos_copy_view_fold": (C.c_int, [c_f, i32p, c_f, i32p, i64, i64, S]),
     "sos_reflect_fill": (C.c_int, [c_f, i64, i64, i64, i64, i64, S]),
     "sos_reflect_fold": (C.c_int, [c_f, i64, i64, i64, i64, i64, S]),

@@ -48,6 +48,8 @@ struct alignas(64) TcParams {
   int n_stages, stage_bytes, a_box_bytes, a_box_stride, b_tile_stride, staging_bytes;
   int n_stg;                     // output staging buffers per epilogue group (2..8)
   int n_egroups;                 // epilogue groups in use: 2, or 1 (A/B switch SOS_EPI_GROUPS=1: warps 7-10 idle)
+  int sw;                        // register chunks (ec channels) per TMA store: 2 = half outputs staged as 128-byte rows of 64 channels
+  int wstore;                    // 1 (SOS_WARP_STORE=1): every epilogue warp stores its own 32 rows; 0: one store per group and chunk behind a barrier
   int dbg;                       // measurement aid (SOS_EPI_DBG): 1 no TMA stores, 2 no accumulator reads / staging writes
   int layout_type, sbo;
   uint32_t idesc;
@@ -139,7 +141,9 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
     // ===================================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int cu = unit0; cu < n_units; cu += grid_units) {
+    long long w_empty = 0, t_begin = clock64();
+    int n_tiles_done = 0;
+    for (int cu = unit0; cu < n_units; cu += grid_units, ++n_tiles_done) {
       const int ct = PAIR ? 2 * cu + (int)rank : cu;                 // (ct == total_ctiles: the dummy partner -- image index out of range,
       const TileCoord tc = decode_tile(p, ct);                       //  every box zero-filled, every store clipped)
       const int fast_t = tc.tfg * p.S * p.FB * p.stride, slow_t = tc.ts * p.SB * p.stride, wrow = tc.nb * p.N;
@@ -150,7 +154,9 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
         const uint32_t tx_bytes = (PAIR ? 2u : 1u) * (uint32_t)p.S * p.a_box_bytes + (uint32_t)n_sub * p.b_tile_bytes;
         const int fast0 = fast_t + grp.d_fast, slow0 = slow_t + grp.d_slow;
         for (int c = 0; c < p.n_chunks; ++c) {
+          const long long tw = (p.dbg & 16) ? clock64() : 0;
           mbar_wait(empty_bar(stage), phase ^ 1, 100);
+          if (p.dbg & 16) w_empty += clock64() - tw;
           if (elect_one_sync()) {
             const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
             const uint32_t bbase = sbase + (uint32_t)p.S * p.a_box_stride;
@@ -174,6 +180,8 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
         }
       }
     }
+    if ((p.dbg & 16) && blockIdx.x == 0 && lane == 0)
+      printf("tapgemm dbg: producer %d tiles, %lld cycles, %lld waiting for empty stages\n", n_tiles_done, clock64() - t_begin, w_empty);
   } else if (warp == 1 || warp == 6) {
     // ===================================================================== MMA issuer(s)
     const int issuer = warp == 1 ? 0 : 1;
@@ -194,8 +202,12 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
       const uint32_t b_lo0 = ((stages_base + (uint32_t)p.S * p.a_box_stride) >> 4) | lbo_bits;
       const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
       const int n_groups = p.n_groups, n_chunks = p.n_chunks, n_stages = p.n_stages;
+      long long w_te = 0, w_full = 0;
+      const long long t_begin = clock64();
       for (int cu = unit0; cu < n_units; cu += grid_units) {
+        long long tw = (p.dbg & 16) ? clock64() : 0;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1, 200);
+        if (p.dbg & 16) w_te += clock64() - tw;
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)acc * 256;
         uint32_t first_mask = 1u;
@@ -203,7 +215,9 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
           const int per = p.prog_n[g];                         // MMAs per issuer and stage; the program lists sub-tile 0's first
           const int m0 = p.prog0[g] + issuer * per, m1 = m0 + per;
           for (int c = 0; c < n_chunks; ++c) {
+            tw = (p.dbg & 16) ? clock64() : 0;
             mbar_wait(full_bar(stage), phase, 201);
+            if (p.dbg & 16) w_full += clock64() - tw;
             tc_fence_after();
             const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_step, b_lo = b_lo0 + (uint32_t)stage * stage_step;
 #pragma unroll 5
@@ -224,6 +238,8 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
         else umma_commit(tfull_bar(acc));                  // (tracks every MMA this thread issued before it)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if ((p.dbg & 16) && blockIdx.x == 0)
+        printf("tapgemm dbg: issuer %d %lld cycles, %lld waiting for a free accumulator, %lld for full stages\n", issuer, clock64() - t_begin, w_te, w_full);
     }
   } else {
     // ===================================================================== epilogue (warps 2..5 = group 0, 7..10 = group 1)
@@ -241,11 +257,11 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
     int buf = 0;
     const int n_stg = neg == 2 ? p.n_stg : 2 * p.n_stg;
     const uint32_t my_staging = staging_base + (neg == 2 ? (uint32_t)eg * (uint32_t)(p.staging_bytes >> 1) : 0u);
-    const int bar_id = 1 + eg;
     const float slope = ((p.act & SOS_ACT_MASK) == 2 && p.slope) ? *p.slope : 0.f;
     const float oscale = p.out_scale ? *p.out_scale : 1.f;
     const int n_ec = p.N / p.ec;
-    const int erow = p.ec * (p.y_half ? 2 : 4);          // bytes of one staging row
+    const int crow = p.ec * (p.y_half ? 2 : 4);          // bytes of one register chunk in a staging row
+    const int erow = crow * p.sw;                        // bytes of one staging row = the store's box width
     float* my_stats = stats_s + ewarp * 2 * p.N;         // this warp's [2][N]
     if (p.stats) {
       for (int i = lane; i < 2 * p.N; i += 32) my_stats[i] = 0.f;
@@ -253,10 +269,15 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
     }
     // pixel of this thread's accumulator row inside the tile (rows are [slow][fast])
     const int row_f = row % p.FB, row_s = row / p.FB;
+    const int wfast = (q * 32) % p.FB, wslow = (q * 32) / p.FB;        // this warp's 32 rows inside the tile
+    long long w_tfull = 0;
+    const long long t_begin = clock64();
     for (int cu = unit0 + eg * grid_units; cu < n_units && eg < neg; cu += neg * grid_units) {
       const int ct = PAIR ? 2 * cu + (int)rank : cu;
       const TileCoord tc = decode_tile(p, ct);
+      const long long tw = (p.dbg & 16) ? clock64() : 0;
       mbar_wait(tfull_bar(acc), acc_phase, 300);
+      if (p.dbg & 16) w_tfull += clock64() - tw;
       tc_fence_after();
       for (int s = 0; s < p.S; ++s) {
         for (int cc = 0; cc < n_ec; ++cc) {
@@ -373,6 +394,8 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
           // (row >> 1) & 3; 32B rows: chunk ^= (row >> 2) & 1), which is also bank-conflict free for a quarter-warp of
           // consecutive rows
           const int xr = erow == 128 ? (row & 7) : (erow == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+          const int sub = p.sw == 2 ? (cc & 1) : 0;                      // which half of a 2-chunk staging row this chunk fills
+          const int jb = sub * (crow >> 4);
           if (p.dbg & 2) {
           } else if (p.y_half) {
 #pragma unroll
@@ -381,7 +404,7 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
                 uint32_t h[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) h[k] = pack_half2(__uint_as_float(r[8 * j + 2 * k]), __uint_as_float(r[8 * j + 2 * k + 1]));
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + ((j ^ xr) << 4)), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3])
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((jb + j) ^ xr) << 4)), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3])
                              : "memory");
               }
             }
@@ -394,10 +417,16 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
                              : "memory");
             }
           }
+          if (sub != p.sw - 1 && cc != n_ec - 1) continue;               // (the row's other half comes with the next chunk)
+          const int ch_store = ch0 - sub * p.ec;
           fence_proxy_async_smem();
-          // ONE barrier per chunk: before it thread 0 makes sure that at most n_stg - 2 earlier stores still read their
-          // buffers, i.e. the buffer of the NEXT chunk is free by the time anybody passes the barrier
-          if (ethread < 32 && elect_one_sync()) {      // (elected, not `ethread == 0`: keeps the bulk instructions straight-line)
+          // Every warp stores ITS 32 rows (a quarter of the tile: box = ec x min(FB, 32) x max(1, 32 / FB) pixels) with its own
+          // bulk-group queue: no barrier between the four warps of a group, so the chains tcgen05.ld -> st.shared -> fence -> TMA
+          // store of the eight epilogue warps run independently (layers with little MMA work per tile are bound by that chain:
+          // ~2000 cycles per 128-row chunk when the four warps met at a barrier and one thread stored for all).  Before the
+          // warp-level sync the elected lane makes sure that at most n_stg - 2 of its earlier stores still read their buffers,
+          // i.e. the buffer of the NEXT chunk is free by the time the warp writes it.
+          if (p.wstore ? elect_one_sync() : (ethread < 32 && elect_one_sync())) {
             switch (n_stg) {                              // (the wait count is an immediate)
               case 2: bulk_wait_read<0>(); break;
               case 3: bulk_wait_read<1>(); break;
@@ -409,10 +438,18 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
               default: bulk_wait_read<7>(); break;
             }
           }
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-          if (ethread < 32 && !(p.dbg & 1) && elect_one_sync()) {
-            tma_store_5d(&p.mapD, sbuf, ch0, (tc.tfg * p.S + s) * p.FB, tc.ts * p.SB, tc.ph, tc.n);
-            bulk_commit();
+          if (p.wstore) {
+            __syncwarp();
+            if (!(p.dbg & 1) && elect_one_sync()) {
+              tma_store_5d(&p.mapD, sbuf + (uint32_t)(q * 32) * erow, ch_store, (tc.tfg * p.S + s) * p.FB + wfast, tc.ts * p.SB + wslow, tc.ph, tc.n);
+              bulk_commit();
+            }
+          } else {
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+            if (ethread < 32 && !(p.dbg & 1) && elect_one_sync()) {
+              tma_store_5d(&p.mapD, sbuf, ch_store, (tc.tfg * p.S + s) * p.FB, tc.ts * p.SB, tc.ph, tc.n);
+              bulk_commit();
+            }
           }
           if (++buf == n_stg) buf = 0;
         }
@@ -426,7 +463,9 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
       if (neg == 2) acc_phase ^= 1;
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (ethread < 32 && elect_one_sync()) bulk_wait<0>();
+    if ((p.dbg & 16) && blockIdx.x == 0 && ethread == 0)
+      printf("tapgemm dbg: epilogue group %d %lld cycles, %lld waiting for full accumulators\n", eg, clock64() - t_begin, w_tfull);
+    if ((p.wstore || ethread < 32) && elect_one_sync()) bulk_wait<0>();
   }
 
   tc_fence_before();
@@ -604,14 +643,20 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
     // 64 -> 2 and their gradients) are otherwise bound by the store latency (ncu r02: 1.3 TB/s of stores with 2 buffers).  Extra
     // buffers are taken from the operand pipeline, which keeps at least 2 (3 if it had them) stages.
     const double per_tile = (double)best.S * (N / ec) * 2000.0 / std::max(1.0, best.tile_cycles);
-    int n_stg = std::min(8, std::max(3, (int)std::ceil(per_tile / 2) + 1));      // per epilogue group (2 only when shared memory is short:
-                                                                                 // consecutive stores of a group then serialise)
+    // The store engine's cost is per ROW of the box (~10 cycles per pixel row whether it holds 64 or 128 bytes: SOS_EPI_DBG
+    // ablations), so a store-bound layer with half outputs stages TWO register chunks side by side: 128-byte
+    // rows of 64 channels, half the rows, fences and barriers per tile (the last store of 96 channels is clipped by the tensor map).
+    static const int wide_env = !(getenv("SOS_WIDE_STORE") && atoi(getenv("SOS_WIDE_STORE")) == 0);
+    p.sw = (wide_env && ysz == 2 && ec == 32 && N >= 64 && per_tile >= 3.0) ? 2 : 1;
+    const int sbytes = stg_bytes * p.sw;
+    int n_stg = std::min(p.sw == 2 ? 4 : 8, std::max(3, (int)std::ceil(per_tile / p.sw / 2) + 1));   // per epilogue group (2 only when shared memory is short:
+                                                                                     // consecutive stores of a group then serialise)
     const int budget = kSmemLimit - 1024 - 512 - stats_smem;
     const int keep = per_tile >= 3.0 ? std::min(p.n_stages, 2) : p.n_stages;   // (a third buffer never costs a tensor-bound layer a pipeline stage)
-    while (n_stg > 2 && (budget - 2 * n_stg * stg_bytes) / p.stage_bytes < keep) --n_stg;
-    p.n_stages = std::min(p.n_stages, (budget - 2 * n_stg * stg_bytes) / p.stage_bytes);
+    while (n_stg > 2 && (budget - 2 * n_stg * sbytes) / p.stage_bytes < keep) --n_stg;
+    p.n_stages = std::min(p.n_stages, (budget - 2 * n_stg * sbytes) / p.stage_bytes);
     p.n_stg = n_stg;
-    p.staging_bytes = 2 * n_stg * stg_bytes;
+    p.staging_bytes = 2 * n_stg * sbytes;
     static const int one_group = getenv("SOS_EPI_GROUPS") && atoi(getenv("SOS_EPI_GROUPS")) == 1;     // A/B aid
     p.n_egroups = one_group ? 1 : 2;
     static const int epi_dbg = getenv("SOS_EPI_DBG") ? atoi(getenv("SOS_EPI_DBG")) : 0;
@@ -675,9 +720,13 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
     const uint64_t sY_fast = fw ? sY_w : sY_h, sY_slow = fw ? sY_h : sY_w;
     uint64_t dims[5] = {(uint64_t)cstore, (uint64_t)out_fast, (uint64_t)(out_slow / g), (uint64_t)g, (uint64_t)a.N};
     uint64_t str[5] = {(uint64_t)ysz, sY_fast, sY_slow * g, sY_slow, pixY * a.YH * a.YW};
-    uint32_t box[5] = {(uint32_t)p.ec, (uint32_t)pl.FB, (uint32_t)pl.SB, 1, 1};
+    // (a store covers ONE epilogue warp's 32 accumulator rows of the FB x SB pixel tile)
+    // (per-warp stores: measured no gain in the step, 4x the store instructions -- off unless SOS_WARP_STORE=1)
+    static const int warp_store = getenv("SOS_WARP_STORE") && atoi(getenv("SOS_WARP_STORE")) == 1;
+    p.wstore = warp_store;
+    uint32_t box[5] = {(uint32_t)(p.ec * p.sw), (uint32_t)(warp_store ? std::min(pl.FB, 32) : pl.FB), (uint32_t)(warp_store ? std::max(1, 32 / pl.FB) : pl.SB), 1, 1};
     uint32_t es[5] = {1, 1, 1, 1, 1};
-    const int erow = ec * ysz;
+    const int erow = ec * p.sw * ysz;
     out.specD = make_spec(ysz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, dims, str, box, es,
                           erow == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (erow == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B), "output");
   }

@@ -1308,7 +1308,33 @@ __global__ void pack_taps_half_kernel(const float* __restrict__ w, int R, int K,
     const long long t2 = e / KP;
     const int t = (int)(t2 % ntaps);
     const int r = (int)(t2 / ntaps);
-    out[e] = __float2half_rn(k < K ? fminf(fmaxf(w[r * sr + k * sk + taps.off[t]], -65504.f), 65504.f) : 0.f);
+    const int off = taps.off[t];                                  // < 0: a zero tap (pads a folded operand row, see sos_im2col_half)
+    out[e] = __float2half_rn(k < K && off >= 0 ? fminf(fmaxf(w[r * sr + k * sk + off], -65504.f), 65504.f) : 0.f);
+  }
+}
+
+// Taps folded into channels for inputs with TWO real channels (the spectrogram inputs of all three networks): out[n, oh, ow, 2 t + c]
+// = x[n, oh + dh_t, ow + dw_t, c] (zero outside the image and for 2 t >= 2 ntaps).  A thread writes 8 halves = 4 taps.
+struct FoldTaps { int16_t dh[32], dw[32]; };
+__global__ void im2col_half_kernel(const __half* __restrict__ x, int H, int W, int Cp, int OH, int OW, int ntaps, FoldTaps taps,
+                                   uint4* __restrict__ out, int g8, long long total) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(e % g8);
+    long long pix = e / g8;
+    const int ow = (int)(pix % OW); pix /= OW;
+    const int oh = (int)(pix % OH);
+    const long long n = pix / OH;
+    uint32_t v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = 4 * q + i;
+      v[i] = 0u;
+      if (t < ntaps) {
+        const int ih = oh + taps.dh[t], iw = ow + taps.dw[t];
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v[i] = __ldg(reinterpret_cast<const uint32_t*>(x + ((n * H + ih) * W + iw) * (long long)Cp));
+      }
+    }
+    out[e] = make_uint4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -1329,7 +1355,8 @@ __global__ void pack_taps_half_multi_kernel(const sos_pack_desc* __restrict__ de
       v[i] = 0.f;
       if (e < total) {
         const unsigned k = e % KP, t2 = e / KP, t = t2 % ntaps, r = t2 / ntaps;
-        if (k < K) v[i] = __ldg(w + (long long)r * d.row_stride + (long long)k * d.k_stride + d.tap_off[t]);
+        const int off = d.tap_off[t];
+        if (k < K && off >= 0) v[i] = __ldg(w + (long long)r * d.row_stride + (long long)k * d.k_stride + off);
       }
     }
 #pragma unroll
@@ -1861,6 +1888,26 @@ int sos_pack_taps_half(const float* w, int64_t rows, int64_t K, int64_t KP, int6
   pack_taps_half_kernel<<<grid_for(rows * ntaps * KP), kThreads, 0, stream>>>(w, (int)rows, (int)K, (int)KP, row_stride, k_stride, (int)ntaps, t,
                                                                               reinterpret_cast<__half*>(out_half));
   SOS_CHECK_LAUNCH("sos_pack_taps_half");
+  return SOS_OK;
+}
+
+int sos_im2col_half(const void* x_half, int64_t batch, int64_t H, int64_t W, int64_t channels, int64_t ntaps, const int32_t* tap_dh,
+                    const int32_t* tap_dw, int64_t OH, int64_t OW, void* out_half, int64_t out_channels, cudaStream_t stream) {
+  SOS_CHECK_ARG(x_half && out_half && tap_dh && tap_dw && batch > 0 && H > 0 && W > 0 && OH > 0 && OW > 0, "sos_im2col_half: bad arguments");
+  SOS_CHECK_ARG(channels >= 2 && channels % 2 == 0 && ntaps > 0 && ntaps <= 32 && out_channels % 8 == 0 && out_channels >= 2 * ntaps,
+                "sos_im2col_half: needs pixels of an even number of halves, at most 32 taps and out_channels >= 2 * ntaps (multiple of 8)");
+  FoldTaps t;
+  for (int i = 0; i < 32; ++i) {
+    const int dh = i < ntaps ? tap_dh[i] : 0, dw = i < ntaps ? tap_dw[i] : 0;
+    SOS_CHECK_ARG(dh >= -32768 && dh < 32768 && dw >= -32768 && dw < 32768, "sos_im2col_half: tap offset out of range");
+    t.dh[i] = (int16_t)dh;
+    t.dw[i] = (int16_t)dw;
+  }
+  const int g8 = (int)(out_channels / 8);
+  const long long total = batch * OH * OW * g8;
+  im2col_half_kernel<<<grid_for(total), kThreads, 0, stream>>>(reinterpret_cast<const __half*>(x_half), (int)H, (int)W, (int)channels, (int)OH,
+                                                               (int)OW, (int)ntaps, t, reinterpret_cast<uint4*>(out_half), g8, total);
+  SOS_CHECK_LAUNCH("sos_im2col_half");
   return SOS_OK;
 }
 

@@ -187,6 +187,30 @@ def _pack_fwd(w, taps, cin_p, half=False):
     return wk
 
 
+# Two-channel inputs (the real / imaginary spectrogram planes every network starts from): a k x k convolution over 2 of 8 / 16 stored
+# channels is 7-25 tap GEMMs over 16- / 32-byte pixel rows -- thousands of tiny TMA requests per tile, the input re-fetched per tap
+# group (profiles/r02c_*_ncu.txt: the main loop starves the epilogue).  Folding the taps into the channel axis first
+# (ops.im2col_half: K = 2 * ntaps real columns in one 32- / 64- / 128-byte row per pixel) turns a pass into a ONE-tap GEMM.
+# Measured (scripts/bench_conv.py, batch 32): the weight gradient gains (2 -> 64 5x5: 0.274 -> 0.228 ms, 2 -> 96 1x7: 0.146 -> 0.126),
+# the forward pass does not (0.166 -> 0.262, 0.186 -> 0.214: a one-tap 64 -> 64 GEMM is bound by its epilogue and the im2col pass
+# comes on top), so only the weight gradient takes the folded form by default (_FOLD_FWD: SOS_FOLD_TAPS=2 folds the forward pass
+# too); the data gradient (needed only where the input is another network's output) always keeps the tap form.
+_FOLD_TAPS = os.environ.get("SOS_FOLD_TAPS", "1") != "0"           # A/B switch
+_FOLD_FWD = os.environ.get("SOS_FOLD_TAPS", "1") == "2"
+
+
+def _fold_kc(x, w, g):
+    """Folded row width (halves) when this half-mode convolution qualifies for the folded form, else 0."""
+    if not (_FOLD_TAPS and x.dtype == torch.float16 and g.kind != "convT" and g.stride == 1 and w.shape[1] == 2 and 1 < len(g.taps) <= 32):
+        return 0
+    k = 2 * len(g.taps)
+    return 16 if k <= 16 else (32 if k <= 32 else 64)
+
+
+def _fold_taps(g, kc):
+    return list(g.taps) + [None] * (kc // 2 - len(g.taps))
+
+
 def _conv_forward(x, w, g, epi=None, want_stats=False, y_half=False, y_out=None):
     """x NHWC (N,H,W,Cin_p); w PyTorch layout.  Returns y NHWC (N,OH,OW,round8(Cout)); with want_stats also the BatchNorm
     partial sums (G, 2, C) of y computed by the epilogue (the four sub-pixel launches of a transposed conv stack theirs)."""
@@ -197,6 +221,11 @@ def _conv_forward(x, w, g, epi=None, want_stats=False, y_half=False, y_out=None)
     kw["y_half"] = y_half
     if g.kind != "convT":
         Cout = w.shape[0]
+        kc = _fold_kc(x, w, g) if _FOLD_FWD else 0
+        if kc:
+            xcol = ops.im2col_half(x, [o[0] for o in g.off], [o[1] for o in g.off], OH, OW, kc)
+            wk = _pack_fwd(w, _fold_taps(g, kc), 2, True)                      # (Cout, kc): column 2 t + c
+            return ops.conv_tc(xcol, wk, [0], [0], Cout, OH, OW, 1, k_real=2 * len(g.taps), want_stats=want_stats, y=y_out, **kw)
         wk = _pack_fwd(w, g.taps, cin_p, half)
         return ops.conv_tc(x, wk, [o[0] for o in g.off], [o[1] for o in g.off], Cout, OH, OW, g.stride, k_real=w.shape[1],
                            want_stats=want_stats, y=y_out, **kw)
@@ -272,13 +301,25 @@ def _conv_wgrad_raw(x, dy, w, g, out_scale=None, workspace=False):
                               out_scale=out_scale, workspace=workspace)
     Cout, Cin = w.shape[0], w.shape[1]
     OH, OW = dy.shape[1], dy.shape[2]
+    kc = _fold_kc(x, w, g)
+    if kc:                                                                     # folded: (1, Cout_p, kc), column 2 t + c
+        xcol = ops.im2col_half(x, [o[0] for o in g.off], [o[1] for o in g.off], OH, OW, kc)
+        return ops.conv_wgrad(xcol, dy, [0], [0], dy.shape[3], OH, OW, 1, real=(2 * len(g.taps), Cout), out_scale=out_scale, workspace=workspace)
     return ops.conv_wgrad(x, dy, [o[0] for o in g.off], [o[1] for o in g.off], dy.shape[3], OH, OW, g.stride, real=(Cin, Cout),
                           out_scale=out_scale, workspace=workspace)
+
+
+def _unfold_wgrad(dwt, w, g):
+    """The folded weight-gradient buffer (1, Cout_p, kc) as a view in w's own layout (Cout, 2, kh, kw)."""
+    R, nt = w.shape[0], len(g.taps)
+    return dwt[0, :R, :2 * nt].reshape(R, nt, 2).permute(0, 2, 1).reshape(R, 2, g.kh, g.kw)
 
 
 def _conv_wgrad(x, dy, w, g, out_scale=None):
     """Returns the gradient in w's own layout."""
     dwt = _conv_wgrad_raw(x, dy, w, g, out_scale)
+    if _fold_kc(x, w, g):
+        return _unfold_wgrad(dwt, w, g).contiguous()
     R, Cc = w.shape[0], w.shape[1]
     return dwt[:, :R, :Cc].permute(1, 2, 0).reshape(R, Cc, g.kh, g.kw).contiguous()
 
@@ -351,7 +392,12 @@ def _wgrad_into(w, x, dy, g, out_scale):
         side, main = _side_stream(), torch.cuda.current_stream()
         side.wait_stream(main)                                     # x, dy, the scale (and the zeroed .grad) are ready
         with torch.cuda.stream(side):
-            if _DIRECT_GRADS and w.grad.is_contiguous():
+            if _DIRECT_GRADS and w.grad.is_contiguous() and _fold_kc(x, w, g):
+                dwt = _conv_wgrad_raw(x, dy, w, g, out_scale, workspace=_WGRAD_WS)
+                w.grad.add_(_unfold_wgrad(dwt, w, g))
+                if _WGRAD_WS:
+                    dwt.zero_()                                   # (the shared workspace is handed back empty)
+            elif _DIRECT_GRADS and w.grad.is_contiguous():
                 # one pass: un-pad, re-layout, add -- out of the side stream's shared workspace, which it leaves zeroed (no fill launch)
                 ops.accumulate_wgrad(_conv_wgrad_raw(x, dy, w, g, out_scale, workspace=_WGRAD_WS), w.grad, clear=_WGRAD_WS)
             else:

@@ -629,9 +629,20 @@ def pack_desc(w, taps, k_padded, out):
     d = PackDesc()
     d.w, d.out_half = w.data_ptr(), out.data_ptr()
     d.rows, d.K, d.KP, d.row_stride, d.k_stride, d.ntaps = w.shape[0], w.shape[1], k_padded, st[0], st[1], len(taps)
-    for i, (a, b) in enumerate(taps):
-        d.tap_off[i] = a * st[2] + b * st[3]
+    for i, t in enumerate(taps):
+        d.tap_off[i] = -1 if t is None else t[0] * st[2] + t[1] * st[3]         # None: a zero tap (padding of a folded operand)
     return d
+
+
+def im2col_half(x, tap_dh, tap_dw, OH, OW, Kc):
+    """x (N, H, W, Cp) half, its first TWO channels real -> (N, OH, OW, Kc) half with the taps folded into the channel axis:
+    column 2 t + c = x[n, oh + dh_t, ow + dw_t, c] (zero outside the image, zero padding columns)."""
+    N, H, W, Cp = x.shape
+    assert x.dtype == torch.float16 and x.is_contiguous() and Kc % 8 == 0 and 2 * len(tap_dh) <= Kc
+    out = torch.empty(N, OH, OW, Kc, device=x.device, dtype=torch.float16)
+    check(lib().sos_im2col_half(_p(x), N, H, W, Cp, len(tap_dh), _i32arr(tap_dh), _i32arr(tap_dw), OH, OW, _p(out), Kc, _stream()), "sos_im2col_half")
+    _count()
+    return out
 
 
 def pack_table(descs, device):
@@ -652,7 +663,7 @@ def pack_taps_half(w, taps, k_padded, out=None):
     st = w.stride()
     if out is None:
         out = torch.empty(R, len(taps) * k_padded, device=w.device, dtype=torch.float16)
-    offs = _i32arr([a * st[2] + b * st[3] for a, b in taps])
+    offs = _i32arr([-1 if t is None else t[0] * st[2] + t[1] * st[3] for t in taps])
     check(lib().sos_pack_taps_half(C.c_void_p(w.data_ptr()), R, K, k_padded, st[0], st[1], len(taps), offs, _p(out), _stream()),
           "sos_pack_taps_half")
     _count()

@@ -56,11 +56,12 @@ for name, kind, Cin, Cout, k, d, stride, H, W, cnt in LAYERS:
     if flt and flt not in name:
         continue
     g = L.ConvGeom(kind, k[0], k[1], d[0], d[1], stride)
+    Cw = Cin
     if HALF and Cin == 8:
-        Cin = 16
+        Cin, Cw = 16, 2                  # the spectrogram inputs: 2 real channels (the weight's) in 16 stored ones -> folded taps (layers._fold_kc)
     x = torch.randn(B, H, W, Cin, device=dev).relu_()
     x = ops.to_half(x) if HALF else ops.round_tf32_(x)
-    w = torch.randn((Cin, Cout, 3, 3) if kind == "convT" else (Cout, Cin, k[0], k[1]), device=dev) * 0.05
+    w = torch.randn((Cin, Cout, 3, 3) if kind == "convT" else (Cout, Cw, k[0], k[1]), device=dev) * 0.05
     OH, OW = g.out_size(H, W)
     y = L._conv_forward(x, w, g)
     dy = ops.to_half(torch.randn_like(y)) if HALF else ops.round_tf32_(torch.randn_like(y))

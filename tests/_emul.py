@@ -44,8 +44,17 @@ def pack_taps(w, taps, k_padded, round_tf32=True):
     """sos_pack_taps semantics: out[r, t*k_padded + k] = w[r, k, taps[t][0], taps[t][1]], zero padded (no rounding here)."""
     R, K = w.shape[0], w.shape[1]
     out = torch.zeros(R, len(taps) * k_padded)
-    for t, (a, b) in enumerate(taps):
-        out[:, t * k_padded:t * k_padded + K] = w[:, :, a, b]
+    for t, tap in enumerate(taps):
+        if tap is not None:                                                # None: a zero tap (padding of a folded operand row)
+            out[:, t * k_padded:t * k_padded + K] = w[:, :, tap[0], tap[1]]
+    return out
+
+
+def im2col_half(x, tap_dh, tap_dw, OH, OW, Kc):
+    """sos_im2col_half: column 2 t + c = x[n, oh + dh_t, ow + dw_t, c] for the two real channels, zero outside / in the padding."""
+    out = torch.zeros(x.shape[0], OH, OW, Kc, dtype=torch.float16)
+    for t, (dh, dw) in enumerate(zip(tap_dh, tap_dw)):
+        out[..., 2 * t:2 * t + 2] = _gather(x[..., :2].float(), dh, dw, OH, OW, 1).half()
     return out
 
 

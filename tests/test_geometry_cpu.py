@@ -133,7 +133,7 @@ def emulated_half(monkeypatch):
                      ("pack_taps_half", _emul.pack_taps_half), ("to_half", _emul.to_half), ("bn_finalize_partial", _emul.bn_finalize_partial),
                      ("bn_act_apply", _emul.bn_act_apply), ("bn_train_backward_half", _emul.bn_train_backward_half),
                      ("copy_view", _emul.copy_view), ("reflect_fill", _emul.reflect_fill), ("reflect_fold", _emul.reflect_fold),
-                     ("copy_view_backward", _emul.copy_view_backward), ("copy_view_fold", _emul.copy_view_fold), ("init", lambda: None)):
+                     ("copy_view_backward", _emul.copy_view_backward), ("copy_view_fold", _emul.copy_view_fold), ("im2col_half", _emul.im2col_half), ("init", lambda: None)):
         monkeypatch.setattr(ops, name, fn)
 
 
@@ -192,6 +192,49 @@ def test_half_path_wiring_cpu(emulated_half):
     for k in ref:
         assert got[k] is not None and got[k].shape == ref[k].shape, k
         assert errs[k] < 2e-2, errs
+
+
+@pytest.mark.parametrize("kind,k,d", [("zero", (1, 7), (1, 1)), ("valid", (5, 5), (1, 1)), ("zero", (3, 3), (2, 1))])
+def test_folded_taps_wiring_cpu(emulated_half, kind, k, d):
+    """Two-channel inputs take the folded form (layers._fold_kc: im2col of the taps into the channel axis, a ONE-tap GEMM with the
+    weight packed as column 2 t + c, the weight gradient un-folded into the parameter's layout); the data gradient keeps the tap
+    form.  Over the emulated kernels against nn.Conv2d + BatchNorm2d + ReLU, and against the unfolded path."""
+    torch.manual_seed(3)
+    N, H, W = 2, 9, 11
+    pad = ((k[0] - 1) // 2 * d[0], (k[1] - 1) // 2 * d[1]) if kind == "zero" else (0, 0)
+    x = torch.randn(N, 2, H, W)
+    conv = torch.nn.Conv2d(2, 16, k, 1, pad, d, bias=False)
+    bn = torch.nn.BatchNorm2d(16)
+    bn.weight.data.uniform_(0.5, 1.5)
+    bn.bias.data.uniform_(-0.3, 0.3)
+    xr = x.clone().requires_grad_(True)
+    zr = torch.relu(bn(conv(xr)))
+    go = torch.randn(zr.shape) * 1e-5
+    zr.backward(go)
+    ref = {"x": xr.grad, "w": conv.weight.grad.clone(), "g": bn.weight.grad.clone(), "b": bn.bias.grad.clone()}
+    g = L.ConvGeom(kind, k[0], k[1], d[0], d[1], 1)
+    to_nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
+    rel = lambda a, b: float((a - b).abs().max() / (b.abs().max() + 1e-30))
+    got = {}
+    for fold in (True, False):
+        for p_ in (conv.weight, bn.weight, bn.bias):
+            p_.grad = None
+        bn.reset_running_stats()
+        old, L._FOLD_TAPS, old_f, L._FOLD_FWD = L._FOLD_TAPS, fold, L._FOLD_FWD, fold
+        try:
+            x32 = to_nhwc(x).requires_grad_(True)
+            xh = L.ToHalf.apply(x32, 16)
+            assert bool(L._fold_kc(ops.hv(xh), conv.weight, g)) == fold
+            z = L.ConvBNActH.apply(xh, conv.weight, bn.weight, bn.bias, None, bn.running_mean, bn.running_var, bn.eps, bn.momentum,
+                                   ops.ACT_RELU, g, True)
+            assert rel(z.permute(0, 3, 1, 2), zr.detach()) < 5e-3
+            z.backward(to_nhwc(go))
+        finally:
+            L._FOLD_TAPS, L._FOLD_FWD = old, old_f
+        got[fold] = {"x": x32.grad.permute(0, 3, 1, 2)[:, :2], "w": conv.weight.grad.clone(), "g": bn.weight.grad.clone(), "b": bn.bias.grad.clone()}
+        for key in ref:
+            assert got[fold][key].shape == ref[key].shape and rel(got[fold][key], ref[key]) < 2e-2, (fold, key, rel(got[fold][key], ref[key]))
+    assert rel(got[True]["w"], got[False]["w"]) < 1e-3                      # same operand values, another summation order
 
 
 def test_encoder_chain_wiring_cpu(emulated_half):

@@ -42,6 +42,8 @@ CASES = [
     ("zero", 96, 8, (1, 1), (1, 1), 1, 2, 16, 21),
     ("zero", 48, 4, (1, 1), (1, 1), 1, 1, 16, 21),
     ("valid", 2, 64, (5, 5), (1, 1), 1, 1, 36, 27),
+    ("zero", 2, 48, (3, 3), (2, 1), 1, 2, 40, 33),           # two real input channels: the folded-tap form in half mode (16 / 32 / 64 columns)
+    ("zero", 2, 96, (5, 5), (1, 2), 1, 1, 130, 37),
     ("valid", 64, 128, (5, 5), (1, 1), 2, 2, 36, 31),
     ("valid", 128, 128, (5, 5), (1, 1), 1, 1, 20, 23),
     ("valid", 256, 256, (3, 3), (1, 1), 2, 1, 34, 29),
@@ -185,6 +187,45 @@ def test_tapconv_half_fwd_bwd(cuda, case, gscale):
     e_x = _rel(ops.nhwc_to_nchw(x32.grad, Cin).cpu(), x.grad)
     print(f"\nhalf {case} gscale {gscale}: fwd {e_f:.2e} dgrad {e_x:.2e} wgrad {e_w:.2e}")
     assert e_f < HALF_TOL and e_x < HALF_TOL and e_w < HALF_TOL, f"rel err: forward {e_f:.2e} dgrad {e_x:.2e} wgrad {e_w:.2e}"
+
+
+def test_im2col_half_kernel(cuda):
+    """sos_im2col_half against an index-level restatement: column 2 t + c = x[n, oh + dh_t, ow + dw_t, c], zeros outside the image
+    and in the padding columns; only the first two of the stored channels are read."""
+    from sos_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    for (N, H, W, Cp, offs, OH, OW, Kc) in [(2, 9, 13, 16, [(0, b - 3) for b in range(7)], 9, 13, 16),
+                                            (1, 12, 10, 8, [(a, b) for a in range(5) for b in range(5)], 8, 6, 64),
+                                            (3, 7, 5, 16, [(2 * (a - 1), b - 1) for a in range(3) for b in range(3)], 7, 5, 32)]:
+        x = torch.randn(N, H, W, Cp, generator=g).half()
+        out = ops.im2col_half(x.to(cuda), [o[0] for o in offs], [o[1] for o in offs], OH, OW, Kc).cpu()
+        ref = torch.zeros(N, OH, OW, Kc, dtype=torch.float16)
+        for t, (dh, dw) in enumerate(offs):
+            for oh in range(OH):
+                for ow in range(OW):
+                    if 0 <= oh + dh < H and 0 <= ow + dw < W:
+                        ref[:, oh, ow, 2 * t:2 * t + 2] = x[:, oh + dh, ow + dw, :2]
+        assert torch.equal(out, ref)
+
+
+def test_folded_taps_match_tap_form(cuda):
+    """The folded form and the tap form of a two-channel convolution multiply the same operand values: forward and weight gradient
+    agree to accumulation order."""
+    from sos_b200 import layers as L, ops
+    g = torch.Generator().manual_seed(6)
+    x = ops.to_half(torch.randn(2, 64, 45, 16, generator=g).to(cuda))
+    w = (torch.randn(64, 2, 5, 5, generator=g) * 0.1).to(cuda)
+    geom = L.ConvGeom("zero", 5, 5, 1, 1, 1)
+    dy = ops.to_half(torch.randn(2, 64, 45, 64, generator=g).to(cuda))
+    res = {}
+    for fold in (True, False):
+        old, L._FOLD_TAPS, old_f, L._FOLD_FWD = L._FOLD_TAPS, fold, L._FOLD_FWD, fold
+        try:
+            assert bool(L._fold_kc(x, w, geom)) == fold
+            res[fold] = (L._conv_forward(x, w, geom).clone(), L._conv_wgrad(x, dy, w, geom).clone())
+        finally:
+            L._FOLD_TAPS, L._FOLD_FWD = old, old_f
+    assert _rel(res[True][0], res[False][0]) < 1e-5 and _rel(res[True][1], res[False][1]) < 1e-5
 
 
 def test_conv_half_fused_epilogue(cuda):
