@@ -48,6 +48,7 @@ struct alignas(64) TcParams {
   int n_stages, stage_bytes, a_box_bytes, a_box_stride, b_tile_stride, staging_bytes;
   int n_stg;                     // output staging buffers per epilogue group (2..8)
   int n_egroups;                 // epilogue groups in use: 2, or 1 (A/B switch SOS_EPI_GROUPS=1: warps 7-10 idle)
+  int bmerge;                    // +-1: the weight tiles of a tap group's sub-taps arrive with ONE 3-D TMA load (taps equally spaced in the packed rows)
   int sw;                        // register chunks (ec channels) per TMA store: 2 = half outputs staged as 128-byte rows of 64 channels
   int wstore;                    // 1 (SOS_WARP_STORE=1): every epilogue warp stores its own 32 rows; 0: one store per group and chunk behind a barrier
   int dbg;                       // measurement aid (SOS_EPI_DBG): 1 no TMA stores, 2 no accumulator reads / staging writes
@@ -165,14 +166,18 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
               if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
               for (int s = 0; s < p.S; ++s)
                 tma_load_5d_pair(sbase + (uint32_t)s * p.a_box_stride, &p.mapA, fb, c * p.cbe, fast0 + s * p.FB * p.stride, slow0, tc.ph, tc.n);
-              for (int j = 0; j < n_sub; ++j)           // this CTA's half of the weight rows
-                tma_load_2d_pair(bbase + (uint32_t)j * p.b_tile_stride, &p.mapB, fb, grp.tap[j] * p.cin + c * p.cbe, wrow + (int)rank * (p.N >> 1));
+              if (p.bmerge) tma_load_3d_pair(bbase, &p.mapB, fb, grp.tap[p.bmerge > 0 ? 0 : n_sub - 1] * p.cin + c * p.cbe, wrow + (int)rank * (p.N >> 1), 0);
+              else
+                for (int j = 0; j < n_sub; ++j)           // this CTA's half of the weight rows
+                  tma_load_2d_pair(bbase + (uint32_t)j * p.b_tile_stride, &p.mapB, fb, grp.tap[j] * p.cin + c * p.cbe, wrow + (int)rank * (p.N >> 1));
             } else {
               mbar_expect_tx(full_bar(stage), tx_bytes);
               for (int s = 0; s < p.S; ++s)
                 tma_load_5d(sbase + (uint32_t)s * p.a_box_stride, &p.mapA, full_bar(stage), c * p.cbe, fast0 + s * p.FB * p.stride, slow0, tc.ph, tc.n);
-              for (int j = 0; j < n_sub; ++j)
-                tma_load_2d(bbase + (uint32_t)j * p.b_tile_stride, &p.mapB, full_bar(stage), grp.tap[j] * p.cin + c * p.cbe, wrow);
+              if (p.bmerge) tma_load_3d(bbase, &p.mapB, full_bar(stage), grp.tap[p.bmerge > 0 ? 0 : n_sub - 1] * p.cin + c * p.cbe, wrow, 0);
+              else
+                for (int j = 0; j < n_sub; ++j)
+                  tma_load_2d(bbase + (uint32_t)j * p.b_tile_stride, &p.mapB, full_bar(stage), grp.tap[j] * p.cin + c * p.cbe, wrow);
             }
           }
           __syncwarp();
@@ -635,6 +640,23 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
   p.a_box_bytes = best.a_box_bytes;
   p.a_box_stride = round_up(p.a_box_bytes, 1024);
   p.b_tile_stride = round_up(Nb * cb, 1024);
+  // The producer thread needs ~140 cycles per TMA instruction (role timers, SOS_EPI_DBG=16: on the 96-channel 5x5 layers it is busy
+  // 85 % of the time and the issuers wait 16 % of theirs for operands), so the n_sub weight tiles of a stage come with ONE 3-D load
+  // where the group's taps are equally spaced in the packed weight rows (k = tap * Cin + ci): dim 2 walks the taps -- upwards; a
+  // group whose taps run downwards (data gradients: negated offsets) is loaded from its last tap and its tiles are used in reverse.
+  int tstep = 0;
+  bool merge = !(getenv("SOS_B_MERGE") && atoi(getenv("SOS_B_MERGE")) == 0) && p.b_tile_stride == Nb * cb;
+  for (int gi = 0; gi < p.n_groups && merge; ++gi) {
+    const TapGroup& grp = p.groups[gi];
+    if (grp.n_sub != p.groups[0].n_sub || grp.n_sub < 2) merge = false;
+    for (int j = 1; j < grp.n_sub && merge; ++j) {
+      const int dlt = grp.tap[j] - grp.tap[j - 1];
+      if (dlt == 0 || (tstep && dlt != tstep)) merge = false;
+      tstep = dlt;
+    }
+  }
+  p.bmerge = merge ? (tstep > 0 ? 1 : -1) : 0;
+  if (tstep < 0) tstep = -tstep;
   p.stage_bytes = best.stage_bytes;
   p.n_stages = best.n_stages;
   {
@@ -676,7 +698,7 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
         for (int j = 0; j < grp.n_sub; ++j)
           for (int kk = 0; kk < kk_per_chunk; ++kk) {
             const uint32_t a_delta = (uint32_t)s2 * p.a_box_stride + (uint32_t)grp.a_off[j] * (p.FB * cb) + kk * 32;
-            const uint32_t b_delta = (uint32_t)j * p.b_tile_stride + kk * 32;
+            const uint32_t b_delta = (uint32_t)(p.bmerge < 0 ? grp.n_sub - 1 - j : j) * p.b_tile_stride + kk * 32;
             SOS_CHECK_ARG(n < kMaxProg, "sos_conv2d_tc: MMA program of %d entries is too long", n);
             p.prog[n++] = make_uint4(a_delta >> 4, b_delta >> 4, (uint32_t)s2 * N, (j == 0 && kk == 0) ? 1u : 0u);
           }
@@ -703,11 +725,20 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
     uint32_t es[5] = {1, (uint32_t)a.stride, (uint32_t)a.stride, 1, 1};
     SOS_CHECK_ARG(box[1] <= 256 && box[2] <= 256, "sos_conv2d_tc: activation box too large");
     out.specA = make_spec(dtA, 5, dims, str, box, es, sw, "activations");
-    uint64_t bd[2] = {(uint64_t)a.ntaps * Cin, (uint64_t)Cout};
-    uint64_t bs[2] = {(uint64_t)esz, (uint64_t)a.ntaps * Cin * esz};
-    uint32_t bb[2] = {(uint32_t)p.cbe, (uint32_t)(p.pair ? N / 2 : N)};      // (a CTA of a pair stages half the weight rows)
-    uint32_t be[2] = {1, 1};
-    out.specB = make_spec(dtA, 2, bd, bs, bb, be, sw, "weights");
+    const uint32_t nb_box = (uint32_t)(p.pair ? N / 2 : N);                  // (a CTA of a pair stages half the weight rows)
+    if (p.bmerge) {
+      uint64_t bd[3] = {(uint64_t)a.ntaps * Cin, (uint64_t)Cout, (uint64_t)((a.ntaps - 1) / tstep + 1)};
+      uint64_t bs[3] = {(uint64_t)esz, (uint64_t)a.ntaps * Cin * esz, (uint64_t)tstep * Cin * esz};
+      uint32_t bb[3] = {(uint32_t)p.cbe, nb_box, (uint32_t)p.groups[0].n_sub};
+      uint32_t be[3] = {1, 1, 1};
+      out.specB = make_spec(dtA, 3, bd, bs, bb, be, sw, "weights");
+    } else {
+      uint64_t bd[2] = {(uint64_t)a.ntaps * Cin, (uint64_t)Cout};
+      uint64_t bs[2] = {(uint64_t)esz, (uint64_t)a.ntaps * Cin * esz};
+      uint32_t bb[2] = {(uint32_t)p.cbe, nb_box};
+      uint32_t be[2] = {1, 1};
+      out.specB = make_spec(dtA, 2, bd, bs, bb, be, sw, "weights");
+    }
   }
   const int out_fast = fw ? (int)a.OW : (int)a.OH, out_slow = fw ? (int)a.OH : (int)a.OW;
   {
