@@ -48,6 +48,7 @@ struct alignas(64) TcParams {
   int n_stages, stage_bytes, a_box_bytes, a_box_stride, b_tile_stride, staging_bytes;
   int n_stg;                     // output staging buffers per epilogue group (2..8)
   int n_egroups;                 // epilogue groups in use: 2, or 1 (A/B switch SOS_EPI_GROUPS=1: warps 7-10 idle)
+  int tstep;                     // tap index step between a group's sub-taps (bmerge)
   int bmerge;                    // +-1: the weight tiles of a tap group's sub-taps arrive with ONE 3-D TMA load (taps equally spaced in the packed rows)
   int sw;                        // register chunks (ec channels) per TMA store: 2 = half outputs staged as 128-byte rows of 64 channels
   int wstore;                    // 1 (SOS_WARP_STORE=1): every epilogue warp stores its own 32 rows; 0: one store per group and chunk behind a barrier
@@ -166,7 +167,10 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
               if (rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
               for (int s = 0; s < p.S; ++s)
                 tma_load_5d_pair(sbase + (uint32_t)s * p.a_box_stride, &p.mapA, fb, c * p.cbe, fast0 + s * p.FB * p.stride, slow0, tc.ph, tc.n);
-              if (p.bmerge) tma_load_3d_pair(bbase, &p.mapB, fb, grp.tap[p.bmerge > 0 ? 0 : n_sub - 1] * p.cin + c * p.cbe, wrow + (int)rank * (p.N >> 1), 0);
+              if (p.bmerge) {
+                const int tb = grp.tap[p.bmerge > 0 ? 0 : n_sub - 1];
+                tma_load_4d_pair(bbase, &p.mapB, fb, c * p.cbe, wrow + (int)rank * (p.N >> 1), tb % p.tstep, tb / p.tstep);
+              }
               else
                 for (int j = 0; j < n_sub; ++j)           // this CTA's half of the weight rows
                   tma_load_2d_pair(bbase + (uint32_t)j * p.b_tile_stride, &p.mapB, fb, grp.tap[j] * p.cin + c * p.cbe, wrow + (int)rank * (p.N >> 1));
@@ -174,7 +178,10 @@ __device__ __forceinline__ void tapgemm_body(const TcParams& p) {
               mbar_expect_tx(full_bar(stage), tx_bytes);
               for (int s = 0; s < p.S; ++s)
                 tma_load_5d(sbase + (uint32_t)s * p.a_box_stride, &p.mapA, full_bar(stage), c * p.cbe, fast0 + s * p.FB * p.stride, slow0, tc.ph, tc.n);
-              if (p.bmerge) tma_load_3d(bbase, &p.mapB, full_bar(stage), grp.tap[p.bmerge > 0 ? 0 : n_sub - 1] * p.cin + c * p.cbe, wrow, 0);
+              if (p.bmerge) {
+                const int tb = grp.tap[p.bmerge > 0 ? 0 : n_sub - 1];
+                tma_load_4d(bbase, &p.mapB, full_bar(stage), c * p.cbe, wrow, tb % p.tstep, tb / p.tstep);
+              }
               else
                 for (int j = 0; j < n_sub; ++j)
                   tma_load_2d(bbase + (uint32_t)j * p.b_tile_stride, &p.mapB, full_bar(stage), grp.tap[j] * p.cin + c * p.cbe, wrow);
@@ -657,6 +664,7 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
   }
   p.bmerge = merge ? (tstep > 0 ? 1 : -1) : 0;
   if (tstep < 0) tstep = -tstep;
+  p.tstep = std::max(1, tstep);
   p.stage_bytes = best.stage_bytes;
   p.n_stages = best.n_stages;
   {
@@ -727,11 +735,13 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
     out.specA = make_spec(dtA, 5, dims, str, box, es, sw, "activations");
     const uint32_t nb_box = (uint32_t)(p.pair ? N / 2 : N);                  // (a CTA of a pair stages half the weight rows)
     if (p.bmerge) {
-      uint64_t bd[3] = {(uint64_t)a.ntaps * Cin, (uint64_t)Cout, (uint64_t)((a.ntaps - 1) / tstep + 1)};
-      uint64_t bs[3] = {(uint64_t)esz, (uint64_t)a.ntaps * Cin * esz, (uint64_t)tstep * Cin * esz};
-      uint32_t bb[3] = {(uint32_t)p.cbe, nb_box, (uint32_t)p.groups[0].n_sub};
-      uint32_t be[3] = {1, 1, 1};
-      out.specB = make_spec(dtA, 3, bd, bs, bb, be, sw, "weights");
+      // (k within the tap, weight row, tap index mod step, tap index / step): every coordinate is bounds-checked by TMA -- a chunk
+      // that reaches past the tap's Cin columns is zero filled, never read from the next tap / row / beyond the buffer
+      uint64_t bd[4] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)tstep, (uint64_t)((a.ntaps - 1) / tstep + 1)};
+      uint64_t bs[4] = {(uint64_t)esz, (uint64_t)a.ntaps * Cin * esz, (uint64_t)Cin * esz, (uint64_t)tstep * Cin * esz};
+      uint32_t bb[4] = {(uint32_t)p.cbe, nb_box, 1, (uint32_t)p.groups[0].n_sub};
+      uint32_t be[4] = {1, 1, 1, 1};
+      out.specB = make_spec(dtA, 4, bd, bs, bb, be, sw, "weights");
     } else {
       uint64_t bd[2] = {(uint64_t)a.ntaps * Cin, (uint64_t)Cout};
       uint64_t bs[2] = {(uint64_t)esz, (uint64_t)a.ntaps * Cin * esz};

@@ -1,5 +1,5 @@
 """GPU timeline of one training step through torch.profiler (CUPTI): busy time per stream, union busy time, idle gaps, and the
-largest gaps with the kernels around them."""
+largest gaps with the kernels around them.  `python scripts/timeline.py graph`: the graphed step (agent.GraphedTrainStep)."""
 import sys
 import torch
 from torch.profiler import profile, ProfilerActivity
@@ -28,7 +28,10 @@ def step():
     return transform.istft_batch(joint.last_rec.detach())
 
 
-for _ in range(4):
+if len(sys.argv) > 1 and sys.argv[1] == "graph":          # the step as bench.py times it: two CUDA-graph replays
+    gstep = ag.GraphedTrainStep(sid, joint, B, d["mixed"].shape[1], bench.SR, bench.FPS)
+    step = lambda: gstep(d["mixed"], d["clean"], d["full_noise"], d["bits"], d["label"])
+for _ in range(5):
     step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:

@@ -189,6 +189,27 @@ def test_tapconv_half_fwd_bwd(cuda, case, gscale):
     assert e_f < HALF_TOL and e_x < HALF_TOL and e_w < HALF_TOL, f"rel err: forward {e_f:.2e} dgrad {e_x:.2e} wgrad {e_w:.2e}"
 
 
+@pytest.mark.parametrize("Cin,Cout,k", [(48, 64, (3, 3)), (96, 96, (5, 5)), (24, 32, (3, 3)), (48, 8, (1, 1))])
+def test_conv_never_reads_past_its_weights(cuda, Cin, Cout, k):
+    """The operand chunks of the last tap / last weight row reach past the packed weight matrix when Cin is not a multiple of the
+    chunk width: whatever lies there must not enter the sums (0 x NaN = NaN).  The packed weights sit in the middle of a NaN-filled
+    buffer; results must equal those of a private copy."""
+    from sos_b200 import layers as L, ops
+    g = torch.Generator().manual_seed(11)
+    geom = L.ConvGeom("zero", k[0], k[1], 1, 1, 1)
+    x = ops.to_half(torch.randn(2, 40, 36, Cin, generator=g).to(cuda))
+    w = (torch.randn(Cout, Cin, k[0], k[1], generator=g) * 0.1).to(cuda)
+    wk = ops.pack_taps_half(w, geom.taps, Cin)
+    big = torch.full((wk.numel() + 16384,), float("nan"), device=cuda, dtype=torch.float16)
+    wk2 = big[8192:8192 + wk.numel()].view_as(wk)
+    wk2.copy_(wk)
+    dh, dw = [o[0] for o in geom.off], [o[1] for o in geom.off]
+    y1 = ops.conv_tc(x, wk, dh, dw, Cout, 40, 36, 1, y_half=True)
+    y2 = ops.conv_tc(x, wk2, dh, dw, Cout, 40, 36, 1, y_half=True)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(y2.float()).all()) and torch.equal(y1, y2)
+
+
 def test_im2col_half_kernel(cuda):
     """sos_im2col_half against an index-level restatement: column 2 t + c = x[n, oh + dh_t, ow + dw_t, c], zeros outside the image
     and in the padding columns; only the first two of the stored channels are read."""
