@@ -5,6 +5,7 @@
 //   BatchNorm (train/eval) + ReLU/PReLU fwd/bwd over NHWC activations
 //   layout changes (NCHW <-> NHWC, reflect borders, nearest resize, concat slices)
 #include "common.cuh"
+#include <stdlib.h>
 #include "sos_b200.h"
 
 namespace {
@@ -680,10 +681,8 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_reduce_h_kernel(const TDZ*
                                                                       const float* __restrict__ mean, const float* __restrict__ invstd, int act,
                                                                       const float* __restrict__ slope_ptr, float* __restrict__ partial /*[grid][4][C]*/,
                                                                       float* __restrict__ zero_me) {
-  extern __shared__ float sm[];                 // [4][C] block totals
+  extern __shared__ float sm[];                 // [rows per block][4][C]: every thread's sums, added up per (quantity, channel) below
   if (zero_me && blockIdx.x == 0 && threadIdx.x == 0) *zero_me = 0.f;      // (the finalize kernel accumulates sum dy^2 there: no fill launch)
-  for (int i = threadIdx.x; i < 4 * C; i += kThreads) sm[i] = 0.f;
-  __syncthreads();
   const int cg8 = C >> 3;
   const int rpb = kThreads / cg8;
   const int r = threadIdx.x / cg8, cgi = threadIdx.x - r * cg8;
@@ -729,16 +728,22 @@ __global__ void __launch_bounds__(kThreads, 2) bn_bwd_reduce_h_kernel(const TDZ*
         }
       }
     }
+    // (plain stores + a column sum below: shared-memory atomics of 21-42 threads per address serialised the end of every block)
+    float* mine = sm + (size_t)r * 4 * C + c;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      atomicAdd(sm + c + k, s1[k]);
-      atomicAdd(sm + C + c + k, s2[k]);
-      if (PRELU) atomicAdd(sm + 2 * C + c + k, s3[k]);
-      atomicAdd(sm + 3 * C + c + k, s4[k]);
+    for (int k = 0; k < 8; k += 4) {
+      *reinterpret_cast<float4*>(mine + k) = make_float4(s1[k], s1[k + 1], s1[k + 2], s1[k + 3]);
+      *reinterpret_cast<float4*>(mine + C + k) = make_float4(s2[k], s2[k + 1], s2[k + 2], s2[k + 3]);
+      *reinterpret_cast<float4*>(mine + 2 * C + k) = make_float4(s3[k], s3[k + 1], s3[k + 2], s3[k + 3]);
+      *reinterpret_cast<float4*>(mine + 3 * C + k) = make_float4(s4[k], s4[k + 1], s4[k + 2], s4[k + 3]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 4 * C; i += kThreads) partial[(size_t)blockIdx.x * 4 * C + i] = sm[i];
+  for (int i = threadIdx.x; i < 4 * C; i += kThreads) {
+    float t = 0.f;
+    for (int rr = 0; rr < rpb; ++rr) t += sm[(size_t)rr * 4 * C + i];
+    partial[(size_t)blockIdx.x * 4 * C + i] = t;
+  }
 }
 
 // Backward finalize for the kernels of this section: like bn_bwd_finalize_kernel<4>, with the incoming gradient's inverse scale.
@@ -1406,7 +1411,7 @@ static int bn_backward_h(const void* dz, const void* y, void* dy_half, long long
                          const float* mean, const float* invstd, int act, const float* slope, float* partial, float* dgamma, float* dbeta,
                          float* dslope, float* m1, float* m2, float* scal, int accumulate, int c_real, const float* in_inv, int G,
                          cudaStream_t stream, bool reduce_done = false) {
-  const size_t smem = (size_t)4 * C * sizeof(float);
+  const size_t smem = (size_t)(kThreads / (C / 8)) * 4 * C * sizeof(float);      // [rows per block][4][C] <= 32 KB
   if (reduce_done) {
     // (pass 1 came out of the epilogue of the data-gradient GEMM that produced dz: sos_conv_args::bnr_partial)
   } else if ((act & SOS_ACT_MASK) == 2)
@@ -1506,7 +1511,10 @@ int sos_bn_partial_blocks(int64_t rows, int64_t channels) {
   if (channels < 4 || channels % 4 || channels > 1024) return 0;
   const int rpb = kThreads / (int)(channels / 4);
   long long g = ceil_div_ll(rows, (long long)rpb * 8);
-  if (g > 148 * 4) g = 148 * 4;
+  // ONE wave of the reduction kernels (2 resident blocks per SM): measured at 32 x 256 x 203 x 48 halves, 592 / 296 / 148 blocks
+  // take 58.9 / 54.3 / 76.8 us (scripts/bench_bn.py; SOS_BN_G overrides)
+  static const int cap = getenv("SOS_BN_G") ? atoi(getenv("SOS_BN_G")) : 2 * sos_num_sms();
+  if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
 }
