@@ -77,7 +77,7 @@ for rep in sorted(f for f in os.listdir("gpurun_out") if f.endswith(".ncu-rep"))
                 return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
             if "dram__bytes_read.sum" in d:
                 t = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
-                if kn not in fresh or t > traffic[kn]["dram_bytes_per_launch"]:
+                if (kn not in fresh or t > traffic[kn]["dram_bytes_per_launch"]) and not (kn in traffic and kn not in fresh and "largest captured" not in traffic[kn].get("note", "")):
                     fresh.add(kn)
                     traffic[kn] = {"dram_bytes_per_launch": t, "duration_ms": float(d["gpu__time_duration.sum"][0].replace(",", "")),
                                    "note": f"largest captured launch of {kn} ({tag}, ncu --set full, profiles/{tag}_{name}_ncu.txt)"}
