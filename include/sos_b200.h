@@ -337,7 +337,8 @@ int sos_conv_stats_rows(void);   /* upper bound of *stats_rows_out (one row per 
  * per distinct (shapes, taps, types) key and reused; tensor maps are re-encoded only when a base pointer changes. */
 void sos_plan_cache_stats(int64_t* hits, int64_t* misses, int64_t* entries);
 int sos_conv2d_tc(const sos_conv_args* args, cudaStream_t stream);
-/* Host-only planner query (no CUDA call, pointers other than the tap arrays are ignored): info[16] = {fast_is_w, share, lattice g,
+/* Host-only planner query (no CUDA call, pointers other than the tap arrays are ignored): info[16] = {fast_is_w, share (+2: half outputs staged as
+ * 128-byte rows of 64 channels, +4: a stage's weight tiles arrive with one TMA load), lattice g,
  * sub-tiles S, tap groups, pipeline stages, stage bytes, grid, K chunk (elements), K chunks, N, epilogue chunk, FB, SB, output staging buffers
  * (+100 when the call runs on CTA pairs), dynamic shared memory}; info[0] = 2 (rest zero but N): the row-streaming kernel serves it. */
 int sos_conv2d_plan(const sos_conv_args* args, int32_t* info);

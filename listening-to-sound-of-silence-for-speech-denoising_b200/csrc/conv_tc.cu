@@ -919,7 +919,7 @@ extern "C" int sos_conv2d_plan(const sos_conv_args* ap, int32_t* info) {
   TcPlan plan;
   if (int e = plan_conv2d_tc(*ap, plan)) return e;
   const TcParams& p = plan.p;
-  const int32_t v[16] = {plan.plan_out[0], plan.plan_out[1], plan.plan_out[2], p.S, p.n_groups, p.n_stages, p.stage_bytes, plan.grid,
+  const int32_t v[16] = {plan.plan_out[0], plan.plan_out[1] + 2 * (p.sw == 2) + 4 * (p.bmerge != 0), plan.plan_out[2], p.S, p.n_groups, p.n_stages, p.stage_bytes, plan.grid,
                          p.cbe, p.n_chunks, p.N, p.ec, p.FB, p.SB, p.n_stg + 100 * p.pair, plan.smem};
   memcpy(info, v, sizeof(v));
   return SOS_OK;

@@ -15,7 +15,7 @@ LAYERS = [
     ("n48_k5_d16x1", 48, 48, (5, 5), (16, 1), 256, T), ("n48_k5_d32x32", 48, 48, (5, 5), (32, 32), 256, T),
     ("in_128_k5v", 128, 128, (5, 5), (1, 1), 132, 106), ("in_256_k3v", 256, 256, (3, 3), (1, 1), 66, 53),
 ]
-names = "fast_is_w share g S groups stages stage_B grid cbe chunks N ec FB SB n_stg smem".split()
+names = "fast_is_w share+2wide+4merge g S groups stages stage_B grid cbe chunks N ec FB SB n_stg smem".split()
 lib = _lib.lib()
 for name, Cin, Cout, k, d, H, W in LAYERS:
     valid = name.endswith("v")

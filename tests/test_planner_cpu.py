@@ -62,3 +62,15 @@ def test_epilogue_bound_layers_stay_on_single_ctas(lib, Cin, Cout, k):
     assert p["n_stg"] < 100 and p["stages"] >= 2
     if Cin == 16:
         assert p["cbe"] == 16                           # 16 real channels: no half-empty 32-wide chunk (TMA zero fill is not free)
+
+
+def test_store_bound_layers_stage_wide_rows_and_heavy_layers_merge_weight_loads(lib):
+    """info[1] bits: +2 = half outputs staged as 128-byte rows of 64 channels (store-bound layers only: the tensor-bound ones keep
+    their shared memory for operand stages), +4 = the weight tiles of a stage's sub-taps arrive with ONE TMA load (equally spaced
+    taps: the k x k layers; a 1 x 1 layer has nothing to merge)."""
+    heavy = _plan(*lib, 96, 96, (5, 5), (1, 1))
+    assert heavy["share"] & 4 and not heavy["share"] & 2, heavy
+    light = _plan(*lib, 16, 96, (1, 1), (1, 1))                      # 96 -> 8 data gradient: K = 16, N = 96, one tap
+    assert light["share"] & 2 and not light["share"] & 4, light
+    mid = _plan(*lib, 256, 256, (3, 3), (1, 1), 66, 53, valid=True)
+    assert mid["share"] & 4, mid
