@@ -548,8 +548,8 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
   // (only where a tile carries enough MMA work: layers with few taps / channels are bound by their epilogue and stores, and pairing
   //  costs them 5-15 % -- measured: 7x1 96->96, 1x7 2->96, the transposed convolutions)
   const double tile_mma = (double)a.ntaps * (CinK / kpe) * (N / 2.0) * (2 * N <= 256 ? 2 : 1);
-  const int pair = (pair_env == 1 && esz == 2 && n_nblk == 1 && N % 16 == 0 && N >= 48 &&
-                    (tile_mma >= 6000.0 || (a.ntaps >= 9 && tile_mma >= 3000.0)) && a.force_plan < 0) ? 1 : 0;
+  const int pair = (pair_env >= 1 && esz == 2 && n_nblk == 1 && N % 16 == 0 && N >= 48 &&
+                    (tile_mma >= 6000.0 || (a.ntaps >= 9 && tile_mma >= 3000.0) || pair_env == 2) && a.force_plan < 0) ? 1 : 0;
   const int Nb = pair ? N / 2 : N;                           // weight rows a CTA stages per tap
   const int ec = (N % 32 == 0) ? 32 : 16;
   const int stg_bytes = 128 * ec * ysz;                     // one output staging buffer (a multiple of 1024: swizzle-aligned)
@@ -595,7 +595,8 @@ int plan_conv2d_tc(const sos_conv_args& a, TcPlan& out) {
   static const int force_cbe = getenv("SOS_FORCE_CBE") ? atoi(getenv("SOS_FORCE_CBE")) : 0;     // debugging aid
   auto sweep = [&](bool fw, bool sh) -> bool {
     bool any = false;
-    for (int ms = sh ? kMaxSub : 1; ms >= 1; --ms) {
+    static const int force_ms = getenv("SOS_FORCE_MAXSUB") ? atoi(getenv("SOS_FORCE_MAXSUB")) : 0;   // debugging aid
+    for (int ms = sh ? (force_ms > 0 ? std::min(force_ms, kMaxSub) : kMaxSub) : 1; ms >= 1; --ms) {
       geo.max_sub = ms;
       Plan pl;
       if (!build_plan(geo, fw, sh, pl)) continue;

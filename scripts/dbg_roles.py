@@ -25,3 +25,4 @@ run("x96to8_k1", "zero", 96, 8, (1, 1), (1, 1), 256, T, "fwd")
 run("k1_64to64", "zero", 64, 64, (1, 1), (1, 1), 256, T, "fwd")
 run("in_64to2_k3", "valid", 64, 2, (3, 3), (1, 1), 258, T + 2, "dgrad")
 run("x96_k5", "zero", 96, 96, (5, 5), (1, 1), 256, T, "fwd")
+run("x96_k7x1", "zero", 96, 96, (7, 1), (1, 1), 256, T, "fwd")
