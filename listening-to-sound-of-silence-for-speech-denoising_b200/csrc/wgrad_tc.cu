@@ -79,6 +79,7 @@ struct alignas(64) WgParams {
   // pixels serves both the plain and the shifted half of the M rows.  L2 -> shared-memory traffic per tile: 164 -> 96 KB on the
   // 48-channel 5x5 layers.
   int uni, fbu_x, fbu_dy, xmin_fast, xmin_slow, dy_box_bytes;
+  int dbg;                          // SOS_WGRAD_DBG=1: role timers (cycles waiting on barriers) printed by block 0
   const float* out_scale;           // optional device scalar multiplied into the sums
   float* dw;
   int16_t job_coblk[kMaxJobs], job_g0[kMaxJobs], job_ng[kMaxJobs], job_s0[kMaxJobs], job_ns[kMaxJobs];
@@ -153,6 +154,8 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
     // ===================================================================== TMA producer
     int stage = 0;
     uint32_t phase = 0;
+    long long w_empty = 0;
+    const long long t_begin = clock64();
     for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
       const WgItem it = decode_wg_item(p, wi);
       const int job = it.job, t0 = it.t0, t1 = it.t1;
@@ -163,7 +166,9 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
                                 : (uint32_t)n_co_chunks * (p.stacked ? 2 : 1) * p.dy_chunk_bytes + (uint32_t)ng * p.n_ci_chunks * p.x_box_bytes;
       for (int tile = t0; tile < t1; ++tile) {
         const WgTile tc = decode_wg_tile(p, tile);
+        const long long tw = p.dbg ? clock64() : 0;
         mbar_wait(empty_bar(stage), phase ^ 1, 500);
+        if (p.dbg) w_empty += clock64() - tw;
         if (elect_one_sync()) {
           mbar_expect_tx(full_bar(stage), tx);
           const uint32_t sbase = stages_base + (uint32_t)stage * p.stage_bytes;
@@ -194,6 +199,7 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
         if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
       }
     }
+    if (p.dbg && blockIdx.x == 0 && lane == 0) printf("wgrad dbg: producer %lld cycles, %lld waiting for empty stages\n", clock64() - t_begin, w_empty);
   } else {
     // ===================================================================== MMA issuers (warps 1..5) + drain (warps 2..5)
     // The accumulator slots of a job are independent, so they are dealt round-robin to kIssuers elected threads (one per warp):
@@ -212,19 +218,25 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
     const uint32_t a_lo_base = (stages_base >> 4) | (p.a_lbo16 << 16);
     const uint32_t b_lo_base = (stages_base + (uint32_t)p.x_off) >> 4;      // (+ the slot's offset and chunk stride)
     const float oscale = p.out_scale ? *p.out_scale : 1.f;
+    long long w_te = 0, w_full = 0, w_drain = 0;
+    const long long t_begin = clock64();
     for (int wi = blockIdx.x; wi < n_items; wi += gridDim.x) {
       const WgItem it = decode_wg_item(p, wi);
       const int job = it.job, t0 = it.t0, t1 = it.t1;
       if (t0 >= t1) continue;
       const int coblk = p.job_coblk[job], s0 = p.job_s0[job], ns = p.job_ns[job];
       if (elect_one_sync()) {
+        long long tw = p.dbg ? clock64() : 0;
         mbar_wait(tempty_bar, acc_phase ^ 1, 600);
+        if (p.dbg) w_te += clock64() - tw;
         tc_fence_after();
         uint32_t first = 0u;
         int st = stage;
         uint32_t ph = phase;
         for (int tile = t0; tile < t1; ++tile) {
+          tw = p.dbg ? clock64() : 0;
           mbar_wait(full_bar(st), ph, 601);
+          if (p.dbg) w_full += clock64() - tw;
           tc_fence_after();
           const uint32_t a_lo0 = a_lo_base + (uint32_t)st * stage_step, b_lo0 = b_lo_base + (uint32_t)st * stage_step;
           for (int i = issuer; i < ns; i += kIssuers) {
@@ -256,6 +268,7 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
       if (warp >= 2) {
         // ---- drain: accumulator row q*32 + lane = output channel, and (stacked) which of the slot's two taps
         const int co = p.stacked ? (q & 1) * 32 + lane : coblk * 128 + q * 32 + lane;
+        const long long td = p.dbg ? clock64() : 0;
         mbar_wait(tfull_bar, acc_phase, 700);
         tc_fence_after();
         for (int i = 0; i < ns; ++i) {
@@ -279,9 +292,14 @@ __device__ __forceinline__ void wgrad_body(const WgParams& p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar);
+        if (p.dbg) w_drain += clock64() - td;
       }
       acc_phase ^= 1;
     }
+    // (w_te / w_full are the elected lane's; it may differ from lane 0, so every lane prints its own non-zero counters)
+    if (p.dbg && blockIdx.x == 0 && (w_full != 0 || (lane == 0 && warp == 2)))
+      printf("wgrad dbg: warp %d lane %d: %lld cycles, %lld waiting for the accumulator, %lld for full stages; drain (incl. wait for the last MMA) %lld\n",
+             warp, lane, clock64() - t_begin, w_te, w_full, w_drain);
   }
 
   tc_fence_before();
@@ -691,6 +709,8 @@ extern "C" int sos_conv2d_wgrad(const sos_wgrad_args* ap, cudaStream_t stream) {
   }
   WgParams& p = plan->p;
   p.out_scale = a.out_scale;
+  static const int wg_dbg = getenv("SOS_WGRAD_DBG") ? atoi(getenv("SOS_WGRAD_DBG")) : 0;
+  p.dbg = wg_dbg;
   p.dw = a.dw;
   const void* baseDY = reinterpret_cast<const uint8_t*>(a.dy) + a.dy_coff * esz;
   if (plan->baseX != a.x) { if (int e = encode_spec(&p.mapX, plan->specX, a.x)) return e; plan->baseX = a.x; }
