@@ -1,3 +1,5 @@
+"""Per-role wait cycles of the tap GEMM (run with SOS_EPI_DBG=16): light (96 -> 8 1x1, 64 -> 64 1x1, 64 -> 2 3x3), mid (96 -> 96 7x1) and
+heavy (96 -> 96 5x5) layers.  Each run() prints the counters of the warm-up forward call first, then those of the named role."""
 import os, sys, torch
 sys.path.insert(0, '.')
 import sos_b200
@@ -14,7 +16,6 @@ def run(name, kind, Cin, Cout, k, d, H, W, role):
     dy = ops.to_half(torch.randn_like(y))
     torch.cuda.synchronize()
     print("==", name, role, flush=True)
-    os.environ["X"] = "1"
     if role == "fwd":
         L._conv_forward(x, w, g, want_stats=True, y_half=True)
     else:
