@@ -69,7 +69,11 @@ def test_graphed_step_matches_eager(cuda, concurrent):
         # (the eager/eager drift itself scatters between 2e-4 and 1e-2 from step to step and run to run -- atomics order amplified by
         # BatchNorm over 2 clips -- so the bound uses the largest drift seen so far and a floor inside that scatter)
         assert d_ge <= 3 * worst[0] + 6e-3, (i, got, ref[0][0], ref[1][0])
-        assert w_ge <= 3 * w_ee + 1e-4, (i, w_ge, w_ee)
+        # (the first Adam step moves every weight by lr * sign(g): where the weight-gradient atomics decide a sign, or a gradient's
+        #  power-of-two half scale, an agent pair lands in one of a few discrete states -- 1.08e-4 of wave drift apart at step 1,
+        #  measured over six runs: sometimes the two eager pairs differ by it, sometimes only the graphed pair does; the floor sits
+        #  above that quantum and the bound uses the largest eager/eager drift seen so far)
+        assert w_ge <= 3 * worst[2] + 5e-4, (i, w_ge, w_ee, worst)
     assert step.g1 is not None and (step.g2 is None) == concurrent and step.launches_per_step > 100
     assert sid_g.optimizer.step_count == STEPS and abs(float(sid_g.optimizer.state[1]) - STEPS) < 1e-6
     assert abs(float(joint_g.optimizer.state[0]) - LR / 4) < 1e-12
