@@ -393,7 +393,7 @@ class GraphedTrainStep(object):
 
     def __init__(self, sid_agent, joint_agent, batch, length, sr=16000, fps=30.0, n_bits=None, warmup=3, concurrent=None):
         self.sid, self.joint = sid_agent, joint_agent
-        # concurrent (SOS_CONCURRENT=1; default off, EXPERIMENTAL: its graph-vs-eager test failed one run in ten): ONE graph in which the detector's step and the joint model's step are parallel
+        # concurrent (SOS_CONCURRENT=1; default off): ONE graph in which the detector's step and the joint model's step are parallel
         # branches (they share only the spectrograms), so that one's kernels could fill the SMs the other leaves idle (LSTM recurrences
         # on 26 of 148 SMs, kernel tails).  Measured at batch 32: 79.6 ms against 79.5 ms for the two graphs in sequence -- the big
         # kernels are persistent whole-GPU grids, two of them only time-slice -- and the sequential form overlaps the detector's

@@ -24,8 +24,7 @@ def _agents():
 @pytest.mark.parametrize("concurrent", [False, True])
 def test_graphed_step_matches_eager(cuda, concurrent):
     """(concurrent = False: two graphs in sequence, the default.  True: one graph with the detector's step as a parallel branch --
-    an opt-in mode (SOS_CONCURRENT=1) whose kernels interleave differently from run to run, so its drift against the eager agents
-    scatters more than the bound calibrated below allows in about one run of ten: tested only with SOS_TEST_CONCURRENT=1.)
+    an opt-in mode (SOS_CONCURRENT=1, no measured gain): tested only with SOS_TEST_CONCURRENT=1.)
     Three identically initialised agent pairs see the same batches: two run eagerly (agent.train_func), one through
     GraphedTrainStep (2 eager warm-up steps, the capture, then replays).  The weight-gradient kernels merge their pixel slices with
     fp32 atomics, so even the two EAGER pairs drift apart from step to step; the graphed pair may differ from an eager pair by at
