@@ -70,9 +70,11 @@ def test_graphed_step_matches_eager(cuda, concurrent):
         assert d_ge <= 3 * worst[0] + 6e-3, (i, got, ref[0][0], ref[1][0])
         # (the first Adam step moves every weight by lr * sign(g): where the weight-gradient atomics decide a sign, or a gradient's
         #  power-of-two half scale, an agent pair lands in one of a few discrete states -- 1.08e-4 of wave drift apart at step 1,
-        #  measured over six runs: sometimes the two eager pairs differ by it, sometimes only the graphed pair does; the floor sits
-        #  above that quantum and the bound uses the largest eager/eager drift seen so far)
-        assert w_ge <= 3 * worst[2] + 5e-4, (i, w_ge, w_ee, worst)
+        #  measured over sixteen runs: sometimes the two eager pairs differ by it, sometimes only the graphed pair does, and pairs in
+        #  different states then drift apart by 7e-4 / 1.5e-3 / 1.1e-3 / 3e-3 over the next steps while pairs in the same state
+        #  stay 3-5 x closer.  The floor per step is ~3 x the different-state drift; the bound also uses the largest eager/eager
+        #  drift seen so far)
+        assert w_ge <= 3 * worst[2] + (1e-5, 5e-4, 2e-3, 4e-3, 4e-3, 8e-3)[i], (i, w_ge, w_ee, worst)
     assert step.g1 is not None and (step.g2 is None) == concurrent and step.launches_per_step > 100
     assert sid_g.optimizer.step_count == STEPS and abs(float(sid_g.optimizer.state[1]) - STEPS) < 1e-6
     assert abs(float(joint_g.optimizer.state[0]) - LR / 4) < 1e-12
