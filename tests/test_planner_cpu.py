@@ -14,8 +14,10 @@ def lib():
     return sos_b200.lib(), sos_b200._lib
 
 
-def _plan(lib, mod, Cin, Cout, k, d, H=256, W=203, N=32, y_half=1, valid=False):
+def _plan(lib, mod, Cin, Cout, k, d, H=256, W=203, N=32, y_half=1, valid=False, negate=False):
     offs = [((a - (0 if valid else (k[0] - 1) // 2)) * d[0], (b - (0 if valid else (k[1] - 1) // 2)) * d[1]) for a in range(k[0]) for b in range(k[1])]
+    if negate:                                   # the tap list of a data gradient: same weight taps, mirrored offsets
+        offs = [(-a, -b) for a, b in offs]
     OH, OW = (H - (k[0] - 1) * d[0], W - (k[1] - 1) * d[1]) if valid else (H, W)
     a = mod.ConvArgs()
     dh = (C.c_int32 * len(offs))(*[o[0] for o in offs])
@@ -74,3 +76,5 @@ def test_store_bound_layers_stage_wide_rows_and_heavy_layers_merge_weight_loads(
     assert light["share"] & 2 and not light["share"] & 4, light
     mid = _plan(*lib, 256, 256, (3, 3), (1, 1), 66, 53, valid=True)
     assert mid["share"] & 4, mid
+    dgrad = _plan(*lib, 96, 96, (5, 5), (2, 2), negate=True)                 # taps of a box run DOWN the packed rows: loaded from the last one
+    assert dgrad["share"] & 4, dgrad
