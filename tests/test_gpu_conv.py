@@ -217,7 +217,10 @@ def test_im2col_half_kernel(cuda):
     g = torch.Generator().manual_seed(4)
     for (N, H, W, Cp, offs, OH, OW, Kc) in [(2, 9, 13, 16, [(0, b - 3) for b in range(7)], 9, 13, 16),
                                             (1, 12, 10, 8, [(a, b) for a in range(5) for b in range(5)], 8, 6, 64),
-                                            (3, 7, 5, 16, [(2 * (a - 1), b - 1) for a in range(3) for b in range(3)], 7, 5, 32)]:
+                                            (3, 7, 5, 16, [(2 * (a - 1), b - 1) for a in range(3) for b in range(3)], 7, 5, 32),
+                                            (2, 6, 150, 16, [(a - 2, b - 2) for a in range(5) for b in range(5)], 6, 150, 64),       # three column tiles
+                                            (1, 40, 70, 8, [(4 * (a - 1), 16 * (b - 1)) for a in range(3) for b in range(3)], 40, 70, 32),
+                                            (1, 12, 9, 16, [(a, 0) for a in range(9)], 4, 9, 32)]:       # 9 row offsets: the gather form
         x = torch.randn(N, H, W, Cp, generator=g).half()
         out = ops.im2col_half(x.to(cuda), [o[0] for o in offs], [o[1] for o in offs], OH, OW, Kc).cpu()
         ref = torch.zeros(N, OH, OW, Kc, dtype=torch.float16)
